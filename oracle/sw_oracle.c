@@ -1,0 +1,225 @@
+/*
+ * sw_oracle.c -- CPU ORACLE (test infrastructure, NOT product code).
+ *
+ * A plain-C restatement of the reference's Smith-Waterman scoring path, used only by
+ * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs as the
+ * checker.  The product (libswb.so) never links, loads or calls anything in this directory.
+ *
+ * What it follows in /root/reference (file:line):
+ *   recurrence        src/SWSolver.cu:246   H = max(0, left-g, up-g, diag+S), score = max over cells
+ *                     src/cpu.cpp:45-72     same shape, strict '>' updates, first max kept
+ *   gap penalty       src/SWSolver.cu:7 , src/cpu.cpp:8          linear, 2
+ *   BLOSUM50 table    src/SWSolver.cu:54-81  order ARNDCQEGHILKMFPSTWYVBJZX*, '*' row/col = 0
+ *   residue encoding  src/SWSolver.cu:91-120 anything outside the 24 letters -> '*' (24)
+ *   +3/-3 scheme      src/cpu.cpp:6-7,57-59  on raw chars
+ *   padding neutrality src/FASTAParsers.h:94-96, src/SWSolver.cu:268-269,318 ('/' -> '*' -> score 0)
+ *   result order      src/SWSolver.cu:383-390 (descending padded length, file order inside a bucket)
+ *   traceback         src/cpu.cpp:76-103     LEFT > TOP > DIAG tie-break by update order
+ *
+ * Parity pin: tests/test_oracle.py checks this file against lines 1-111 of the reference's golden
+ * files test/reference/P01008.txt / P02232.txt (committed as tests/golden/*.head111.txt), against
+ * the survey probe's 20x111 expected vectors, against the self-scores 3037 / 910 and against
+ * the compiled reference cpu.cpp (oracle/_ref/cpu_ref) in +3/-3 mode.  All arithmetic is int32.
+ *
+ * Alphabet used across the repo: 32 codes. 0..23 = ARNDCQEGHILKMFPSTWYVBJZX, 24 = '*' / unknown,
+ * 25..30 spare, 31 = PAD whose row and column are zero in every matrix.
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define SWO_ALPHA 32
+#define SWO_PAD 31
+#define SWO_STAR 24
+
+static const char *const k_order = "ARNDCQEGHILKMFPSTWYVBJZX";
+
+/* Lower triangle of BLOSUM50 in k_order (the matrix at SWSolver.cu:56-79 is symmetric). */
+static const char *const k_b50_lower[24] = {
+    "5",
+    "-2 7",
+    "-1 -1 7",
+    "-2 -2 2 8",
+    "-1 -4 -2 -4 13",
+    "-1 1 0 0 -3 7",
+    "-1 0 0 2 -3 2 6",
+    "0 -3 0 -1 -3 -2 -3 8",
+    "-2 0 1 -1 -3 1 0 -2 10",
+    "-1 -4 -3 -4 -2 -3 -4 -4 -4 5",
+    "-2 -3 -4 -4 -2 -2 -3 -4 -3 2 5",
+    "-1 3 0 -1 -3 2 1 -2 0 -3 -3 6",
+    "-1 -2 -2 -4 -2 0 -2 -3 -1 2 3 -2 7",
+    "-3 -3 -4 -5 -2 -4 -3 -4 -1 0 1 -4 0 8",
+    "-1 -3 -2 -1 -4 -1 -1 -2 -2 -3 -4 -1 -3 -4 10",
+    "1 -1 1 0 -1 0 -1 0 -1 -3 -3 0 -2 -3 -1 5",
+    "0 -1 0 -1 -1 -1 -1 -2 -2 -1 -1 -1 -1 -2 -1 2 5",
+    "-3 -3 -4 -5 -5 -1 -3 -3 -3 -3 -2 -3 -1 1 -4 -4 -3 15",
+    "-2 -1 -2 -3 -3 -1 -2 -3 2 -1 -1 -2 0 4 -3 -2 -2 2 8",
+    "0 -3 -3 -4 -1 -3 -3 -4 -4 4 1 -3 1 -1 -3 -2 0 -3 -1 5",
+    "-2 -1 5 6 -3 0 1 -1 0 -4 -4 0 -3 -4 -2 0 0 -5 -3 -3 6",
+    "-2 -3 -4 -4 -2 -3 -3 -4 -3 4 4 -3 2 1 -3 -3 -1 -2 -1 2 -4 4",
+    "-1 0 0 1 -3 4 5 -2 0 -3 -3 1 -1 -4 -1 0 -1 -2 -2 -3 1 -3 5",
+    "-1 -1 -1 -1 -1 -1 -1 -1 -1 -1 -1 -1 -1 -1 -1 -1 -1 -1 -1 -1 -1 -1 -1 -1",
+};
+
+/* 32x32 int8 matrix of the CUDA path: BLOSUM50 with the '*' row/column zeroed (SWSolver.cu:80 and
+ * the last column of every row), rows/cols 24..31 all zero. */
+void swo_matrix_blosum50(int8_t *m)
+{
+    memset(m, 0, SWO_ALPHA * SWO_ALPHA);
+    for (int i = 0; i < 24; ++i) {
+        const char *p = k_b50_lower[i];
+        for (int j = 0; j <= i; ++j) {
+            char *end;
+            long v = strtol(p, &end, 10);
+            p = end;
+            m[i * SWO_ALPHA + j] = (int8_t)v;
+            m[j * SWO_ALPHA + i] = (int8_t)v;
+        }
+    }
+}
+
+/* 32x32 int8 matrix of cpu.cpp:57-59: +3 when the two residues are the same char, else -3.
+ * Codes 0..30 stand for distinct chars; PAD (31) scores 0 against everything. */
+void swo_matrix_ident3(int8_t *m)
+{
+    for (int i = 0; i < SWO_ALPHA; ++i)
+        for (int j = 0; j < SWO_ALPHA; ++j)
+            m[i * SWO_ALPHA + j] = (i == SWO_PAD || j == SWO_PAD) ? 0 : (i == j ? 3 : -3);
+}
+
+/* SWSolver.cu:91-120: the 24 upper-case letters of k_order map to 0..23, everything else
+ * (including '/', 'U', 'O', lower case, '\r') to '*' = 24. */
+void swo_encode_blosum(const char *s, size_t n, uint8_t *out)
+{
+    uint8_t lut[256];
+    memset(lut, SWO_STAR, sizeof lut);
+    for (int i = 0; i < 24; ++i) lut[(unsigned char)k_order[i]] = (uint8_t)i;
+    for (size_t i = 0; i < n; ++i) out[i] = lut[(unsigned char)s[i]];
+}
+
+/* Encoding for the cpu.cpp scheme, which compares raw chars (cpu.cpp:58): every upper-case letter
+ * keeps its own code so that equal letters match and different letters do not.  The 24 letters of
+ * k_order keep codes 0..23; the two remaining letters 'O' and 'U' take 25 and 26; any other byte
+ * takes 30 (callers of the +3/-3 mode in this repo only pass upper-case protein letters). */
+void swo_encode_ident(const char *s, size_t n, uint8_t *out)
+{
+    uint8_t lut[256];
+    memset(lut, 30, sizeof lut);
+    for (int i = 0; i < 24; ++i) lut[(unsigned char)k_order[i]] = (uint8_t)i;
+    lut['O'] = 25;
+    lut['U'] = 26;
+    for (size_t i = 0; i < n; ++i) out[i] = lut[(unsigned char)s[i]];
+}
+
+/* Score of one (query, subject) pair; O(dlen) memory; int32 throughout.
+ * Loop nest: query rows outside, subject columns inside, as cpu.cpp:43-44. */
+int32_t swo_score(const uint8_t *q, uint32_t qlen, const uint8_t *d, uint32_t dlen,
+                  const int8_t *m, int32_t gap)
+{
+    if (qlen == 0 || dlen == 0) return 0;
+    int32_t *row = (int32_t *)calloc((size_t)dlen + 1, sizeof(int32_t));
+    int32_t best = 0;
+    for (uint32_t i = 0; i < qlen; ++i) {
+        const int8_t *srow = m + (size_t)q[i] * SWO_ALPHA;
+        int32_t diag = 0; /* H[i-1][j-1] */
+        int32_t left = 0; /* H[i][j-1]   */
+        for (uint32_t j = 1; j <= dlen; ++j) {
+            int32_t up = row[j];
+            int32_t h = 0;
+            if (left - gap > h) h = left - gap;
+            if (up - gap > h) h = up - gap;
+            if (diag + srow[d[j - 1]] > h) h = diag + srow[d[j - 1]];
+            if (h > best) best = h;
+            diag = up;
+            row[j] = h;
+            left = h;
+        }
+    }
+    free(row);
+    return best;
+}
+
+/* Database scan: out[k] = score(query, sequence k), sequences given as concatenated codes plus
+ * n+1 offsets (64-bit: the reference's int counters overflow at UniProt scale, FASTAParsers.h:69-71).
+ * stride/start select a sample (k = start, start+stride, ...) ; unsampled entries are left alone. */
+void swo_scan(const uint8_t *q, uint32_t qlen, const uint8_t *codes, const uint64_t *off,
+              uint32_t n, const int8_t *m, int32_t gap, int32_t *out, uint32_t start,
+              uint32_t stride, int nthreads)
+{
+    if (stride == 0) stride = 1;
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#else
+    (void)nthreads;
+#endif
+    long cnt = n > start ? (long)((n - start + stride - 1) / stride) : 0;
+#pragma omp parallel for schedule(dynamic, 16)
+    for (long t = 0; t < cnt; ++t) {
+        uint32_t k = start + (uint32_t)t * stride;
+        out[k] = swo_score(q, qlen, codes + off[k], (uint32_t)(off[k + 1] - off[k]), m, gap);
+    }
+}
+
+int swo_max_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+/* Full-matrix version with traceback, following cpu.cpp:39-103 step for step (update order
+ * LEFT, TOP, DIAG with strict '>', first row-major maximum, walk back until H == 0).
+ * a_out / b_out receive the two aligned strings (NUL-terminated, '-' for gaps) and must each
+ * hold qlen + dlen + 1 bytes.  q_txt / d_txt are the raw characters used for printing.
+ * Returns the score; *end_i / *end_j the 1-based cell of the maximum. */
+int32_t swo_align(const uint8_t *q, const char *q_txt, uint32_t qlen, const uint8_t *d,
+                  const char *d_txt, uint32_t dlen, const int8_t *m, int32_t gap, char *a_out,
+                  char *b_out, uint32_t *end_i, uint32_t *end_j)
+{
+    size_t W = (size_t)dlen + 1;
+    int32_t *H = (int32_t *)calloc((size_t)(qlen + 1) * W, sizeof(int32_t));
+    uint8_t *T = (uint8_t *)calloc((size_t)(qlen + 1) * W, 1);
+    int32_t best = 0;
+    uint32_t bi = 0, bj = 0;
+    for (uint32_t i = 1; i <= qlen; ++i) {
+        for (uint32_t j = 1; j <= dlen; ++j) {
+            int32_t h = 0;
+            uint8_t t = 0;
+            if (H[i * W + j - 1] - gap > h) { h = H[i * W + j - 1] - gap; t = 1; }
+            if (H[(i - 1) * W + j] - gap > h) { h = H[(i - 1) * W + j] - gap; t = 2; }
+            int32_t s = m[(size_t)q[i - 1] * SWO_ALPHA + d[j - 1]];
+            if (H[(i - 1) * W + j - 1] + s > h) { h = H[(i - 1) * W + j - 1] + s; t = 3; }
+            if (h > best) { best = h; bi = i; bj = j; }
+            H[i * W + j] = h;
+            T[i * W + j] = t;
+        }
+    }
+    size_t na = 0;
+    uint32_t i = bi, j = bj;
+    int32_t v = H[i * W + j];
+    while (v != 0) {
+        uint8_t t = T[i * W + j];
+        if (t == 1) { --j; a_out[na] = '-'; b_out[na] = d_txt[j]; }
+        else if (t == 2) { --i; a_out[na] = q_txt[i]; b_out[na] = '-'; }
+        else { --i; --j; a_out[na] = q_txt[i]; b_out[na] = d_txt[j]; }
+        ++na;
+        v = H[i * W + j];
+    }
+    for (size_t k = 0; k < na / 2; ++k) {
+        char c = a_out[k]; a_out[k] = a_out[na - 1 - k]; a_out[na - 1 - k] = c;
+        c = b_out[k]; b_out[k] = b_out[na - 1 - k]; b_out[na - 1 - k] = c;
+    }
+    a_out[na] = 0;
+    b_out[na] = 0;
+    if (end_i) *end_i = bi;
+    if (end_j) *end_j = bj;
+    free(H);
+    free(T);
+    return best;
+}

@@ -1,0 +1,350 @@
+#!/usr/bin/env python3
+"""Headline benchmark: GCUPS of the Smith-Waterman database scan (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1]): Swiss-Prot-shaped synthetic database (570,065 sequences, ~2.0e8
+residues, numpy seed 1782, log-normal lengths plus a 5k..35,213 tail) against the reference's standard
+20-query set (144..5478 residues, tests/golden/queries). One "step" = one scan of the whole database
+by all 20 queries. With N > 1 (launched by torchrun, one rank per GPU) the database is residue-sharded
+across the ranks (strong scaling: the total work is fixed) and rank 0 merges per-rank top hits.
+
+value   = true cells (sum qlen x sum len) / device time, database already resident in HBM
+e2e     = the same through the C ABI with HOST buffers: swb_db_load (plan + H2D + device pack) +
+          swb_search_batch with the score matrix copied back, wall clock around the calls
+roofline= score kernel against the integer SIMD issue peak measured live by swb_microbench
+cpu_baseline / --impl reference = the CPU oracle (a port of the reference recurrence, OpenMP over
+          sequences, all host cores) on a bounded sample of the same workload
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+PKG = "ece1782-smith-waterman-cuda_b200"
+METRIC = "GCUPS (whole box, device-timed) on Swiss-Prot scan at 1/2/4/8 B200"
+
+# Swiss-Prot amino-acid composition in percent (UniProt release statistics)
+COMPOSITION = {"L": 9.65, "A": 8.25, "G": 7.07, "V": 6.86, "E": 6.72, "S": 6.64, "I": 5.91, "K": 5.80, "R": 5.53,
+               "D": 5.46, "T": 5.35, "P": 4.74, "N": 4.06, "Q": 3.93, "F": 3.86, "Y": 2.92, "M": 2.41, "H": 2.27,
+               "C": 1.38, "W": 1.10}
+ORDER = "ARNDCQEGHILKMFPSTWYVBJZX"
+
+
+def synth_db(n=570000, seed=1782, scale=1.0):
+    """config 2 generator: returns (codes uint8, offsets uint64[n+1]); ids are shuffled w.r.t. length."""
+    rng = np.random.default_rng(seed)
+    n = int(n * scale)
+    lens = np.clip(np.round(rng.lognormal(5.58, 0.75, n)), 2, 35213).astype(np.int64)
+    ntail = max(1, int(64 * scale))
+    tail = np.round(np.exp(rng.uniform(np.log(5000), np.log(35213), ntail))).astype(np.int64)
+    lens = np.concatenate([lens, tail, [35213]])
+    rng.shuffle(lens)
+    total = int(lens.sum())
+    p = np.zeros(32)
+    for ch, f in COMPOSITION.items():
+        p[ORDER.index(ch)] = f
+    p = p / p.sum() * 0.999
+    for code in (23, 20, 22, 24):  # X, B, Z and an unknown ('U' encodes to '*' in the reference)
+        p[code] += 0.001 / 4
+    codes = rng.choice(32, size=total, p=p / p.sum()).astype(np.uint8)
+    offsets = np.zeros(len(lens) + 1, dtype=np.uint64)
+    offsets[1:] = np.cumsum(lens)
+    return codes, offsets
+
+
+def load_queries(swb):
+    qdir = os.path.join(ROOT, "tests", "golden", "queries")
+    names = sorted(fn[:-6] for fn in os.listdir(qdir) if fn.endswith(".fasta"))
+    qs = []
+    for nme in names:
+        txt = "".join(open(os.path.join(qdir, nme + ".fasta")).read().split("\n")[1:])
+        qs.append(swb.encode(txt) if swb else txt)
+    return names, qs
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out = self.proc.communicate(timeout=5)[0]
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().split("\n"):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for k, nme in enumerate(names):
+                if f[5 + k].lower().startswith("active"):
+                    reasons.add(nme)
+        busy = [s for s, pw in zip(sm, power) if pw > 200] or sm
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(power) if power else None}
+
+
+def cpu_sample_gcups(codes, offsets, qnames, qtexts, budget_s, threads=0):
+    """Oracle (port of the reference recurrence) on a bounded stride sample of the workload."""
+    from oracle_lib import Oracle
+    o = Oracle()
+    cores = threads or o.max_threads()
+    m = o.matrix("blosum50")
+    n = len(offsets) - 1
+    total_cells = float(sum(len(q) for q in qtexts)) * float(offsets[-1])
+    target = cores * 0.25e9 * budget_s
+    stride = max(1, int(np.ceil(total_cells / target)))
+    lens = np.diff(offsets.astype(np.int64))
+    sample_res = int(lens[0::stride].sum())
+    t0 = time.time()
+    cells = 0
+    for q in qtexts:
+        qc = o.encode(q)
+        o.scan(qc, codes, offsets, m, 2, 0, stride, cores)
+        cells += len(qc) * sample_res
+    dt = time.time() - t0
+    return {"value": cells / dt * 1e-9, "unit": "GCUPS", "cores": cores, "kind": "port",
+            "sample": "oracle/sw_oracle.c (OpenMP over sequences), every %d-th of %d sequences x all %d queries, "
+                      "%.3g cells in %.1f s" % (stride, n, len(qtexts), cells, dt)}, dt
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU formulation (score-only port, all host threads) on this config."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    codes, offsets = synth_db(scale=args.scale)
+    names, qtexts = load_queries(None)
+    budget = max(2.0, min(20.0, 150.0 / max(1, args.steps + args.warmup)))
+    times, vals, last = [], [], None
+    for it in range(args.warmup + args.steps):
+        cb, dt = cpu_sample_gcups(codes, offsets, names, qtexts, budget)
+        if it >= args.warmup:
+            times.append(dt)
+            vals.append(cb["value"])
+        last = cb
+    v = float(np.mean(vals))
+    last["value"] = v
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "GCUPS", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": float(np.mean(times)) * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": workload_config(offsets, qtexts, args), "cpu_baseline": last,
+            "e2e": {"value": v, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_config(offsets, qs, args):
+    return {"workload": "configs[1]: Swiss-Prot-shaped synthetic DB (seed 1782) x reference 20-query set",
+            "db_sequences": int(len(offsets) - 1), "db_residues": int(offsets[-1]), "queries": len(qs),
+            "query_residues": int(sum(len(q) for q in qs)), "scoring": "BLOSUM50 ('*' zeroed), linear gap 2",
+            "l2": "inputs larger than L2 (packed residues + boundary scratch >> 126 MB)", "scale": args.scale}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--scale", type=float, default=1.0, help="database size factor (1.0 = the named workload)")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--streams", type=int, default=0)
+    ap.add_argument("--k", type=int, default=0)
+    ap.add_argument("--group-len", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--per-query", action="store_true", help="also print device GCUPS per query")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the engine has no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    swb = importlib.import_module(PKG)
+    codes, offsets = synth_db(scale=args.scale)
+    names, qs = load_queries(swb)
+    qcodes, qoffs = swb.pack_sequences(qs)
+    total_cells = float(sum(len(q) for q in qs)) * float(offsets[-1])
+
+    opts = {}
+    if args.streams:
+        opts["streams"] = args.streams
+    if args.k:
+        opts["k"] = args.k
+    if args.group_len:
+        opts["group_len"] = args.group_len
+    eng = swb.Engine(local, **opts)
+    stream = torch.cuda.current_stream()
+    eng.set_stream(stream.cuda_stream)
+    eng.db_load(codes, offsets, rank, world)
+    nloc = eng.db_count()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        eng.search_batch_packed(qcodes, qoffs, fetch=False)
+
+    for _ in range(args.warmup):
+        step_resident()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    ev0 = torch.cuda.Event(enable_timing=True)
+    ev1 = torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    launches = 0
+    for _ in range(args.steps):
+        step_resident()
+        launches += eng.stats()["kernel_launches"]
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms = ev0.elapsed_time(ev1)
+    st = eng.stats()
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    ms_per_step = ms_max / args.steps
+    value = total_cells / (ms_per_step * 1e-3) * 1e-9
+
+    # end to end through the C ABI with host buffers (database upload + search + scores back), wall clock
+    out = np.zeros((len(qs), nloc), dtype=np.int32)
+    e2e_times = []
+    for it in range(args.e2e_steps + 1):
+        barrier()
+        t0 = time.perf_counter()
+        eng.db_load(codes, offsets, rank, world)
+        eng.search_batch_packed(qcodes, qoffs, fetch=True, out=out)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        if it > 0:
+            e2e_times.append(float(tt.item()))
+    e2e_s = float(np.mean(e2e_times)) if e2e_times else float("nan")
+    load_ms = eng.stats()["load_ms"]
+    e2e = {"value": total_cells / e2e_s * 1e-9, "unit": "GCUPS",
+           "h2d_bytes_per_step": int(codes.nbytes + offsets.nbytes + qcodes.nbytes + qoffs.nbytes),
+           "d2h_bytes_per_step": int(out.nbytes), "seconds_per_step": e2e_s, "db_load_ms": load_ms,
+           "api": "swb_db_load + swb_search_batch (host buffers)"}
+
+    # host merge of the per-rank hit lists (top-10 per query), checks the sharded path end to end
+    top_ok = None
+    if world > 1:
+        mine = []
+        for qi in range(len(qs)):
+            ids, top = eng.topk(out[qi], 10)
+            mine.append((ids.tolist(), top.tolist()))
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)
+        if rank == 0:
+            merged = []
+            for qi in range(len(qs)):
+                allh = [(s, i) for r in range(world) for i, s in zip(*gathered[r][qi])]
+                allh.sort(key=lambda x: (-x[0], x[1]))
+                merged.append(allh[:10])
+            top_ok = all(len(mm) == 10 for mm in merged)
+
+    if rank == 0:
+        # roofline of the dominant kernel (swb_score_kernel, V16): integer SIMD issue rate
+        mix = swb.microbench(local, 4)
+        per_kind = {swb.MICROBENCH_KINDS[k]: round(swb.microbench(local, k), 1) for k in (0, 1, 2, 3, 5, 6)}
+        instr_per_cell = 4.5 / 2.0
+        padded_cells = float(st["padded_cells"])
+        ach_padded = padded_cells * world / (ms_per_step * 1e-3) * 1e-9  # cells the kernel really executes
+        peak_gcups = mix / instr_per_cell
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        residues = float(st["db_residues"])
+        alg_bytes = len(qs) * residues  # one byte of DB residue per query pass
+        roofline = {"bound": "int_alu", "kernel": "swb_score_kernel<K,V16>", "achieved": value / world, "peak": peak_gcups,
+                    "unit": "GCUPS", "frac": (value / world) / peak_gcups, "traffic": None,
+                    "achieved_incl_padding": ach_padded / world,
+                    "frac_incl_padding": (ach_padded / world) / peak_gcups,
+                    "peak_source": "swb_microbench kind 4 (score-kernel instruction mix, 4.5 SIMD instr per cell pair) "
+                                   "measured live: %.0f Glane-instr/s" % mix,
+                    "instr_rates_glane_per_s": per_kind,
+                    "hbm": {"achieved": alg_bytes / (ms_per_step * 1e-3) * 1e-9, "peak": hbm_peak, "unit": "GB/s",
+                            "frac": alg_bytes / (ms_per_step * 1e-3) * 1e-9 / hbm_peak,
+                            "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}}
+        line = {"metric": METRIC, "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "s16x2 (int32 recompute on overflow)", "data": "synthetic",
+                "config": workload_config(offsets, qs, args), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+                "roofline": roofline, "engine": {k: st[k] for k in ("tiles", "tiles_by_group", "last_k",
+                                                                    "recomputed_tiles", "sm_count")},
+                "topk_merge_ok": top_ok}
+        if not args.no_cpu:
+            names_t, qtexts = load_queries(None)
+            line["cpu_baseline"], _ = cpu_sample_gcups(codes, offsets, names_t, qtexts, args.cpu_seconds)
+        else:
+            line["cpu_baseline"] = None
+        if args.per_query:
+            pq = {}
+            for nme, q in zip(names, qs):
+                eng.search_batch([q], fetch=False)
+                eng.search_batch([q], fetch=False)
+                s2 = eng.stats()
+                pq[nme] = {"qlen": len(q), "gcups": s2["cells"] / (s2["device_ms"] * 1e-3) * 1e-9, "k": s2["last_k"],
+                           "ms": s2["device_ms"]}
+            line["per_query"] = pq
+        print(json.dumps(line))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

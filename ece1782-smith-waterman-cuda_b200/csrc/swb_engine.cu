@@ -1,0 +1,681 @@
+// Engine behind the C ABI (include/swb.h): owns the device-resident packed database, the per-stream
+// scratch and the launch logic. One engine = one GPU (one process per GPU under torchrun).
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <sys/time.h>
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/swb.h"
+#include "swb_kernels.h"
+#include "swb_plan.h"
+
+#define SWB_MAX_SLOTS 4
+#define SWB_MAX_COUNTERS 64
+#define SWB_CHUNK_ROWS 7168u          // query rows per launch when a query does not fit shared memory
+#define SWB_SMALL_SMEM_LIMIT (100u * 1024u)
+#define SWB_STAGE_BYTES (32u << 20)   // pinned staging buffers for the raw database upload
+
+static thread_local std::string g_create_error;
+
+static double wall_ms()
+{
+    timeval tv;
+    gettimeofday(&tv, NULL);
+    return tv.tv_sec * 1e3 + tv.tv_usec * 1e-3;
+}
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    bool busy = false;
+    uint8_t *h_query = nullptr;  // pinned
+    uint8_t *d_query = nullptr;
+    uint32_t query_cap = 0;
+    int8_t *d_prof = nullptr;
+    size_t prof_cap = 0;
+    uint8_t *d_state = nullptr;  // [counters | flags | sorted scores], zeroed per query
+    size_t state_bytes = 0;
+    uint32_t *d_counters = nullptr;
+    uint32_t *d_recount = nullptr;  // tiles re-scored in int32, zeroed per batch
+    uint8_t *d_flags = nullptr;
+    int32_t *d_sorted = nullptr;
+    uint32_t *d_bnd16 = nullptr;
+    void *d_bnd32 = nullptr;
+    int32_t *h_scores = nullptr;  // pinned, n_local
+    int32_t *pending_dst = nullptr;
+};
+
+struct swb_engine {
+    int device = 0;
+    int sm_count = 0;
+    size_t smem_optin = 0;
+    std::string err;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t user_stream = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_fork = nullptr;
+    cudaEvent_t ev_join[SWB_MAX_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
+    // scoring
+    int8_t h_mat[SWB_ALPHA * SWB_ALPHA];
+    int gap = 2;
+    int max_s = 0;
+    bool scoring_set = false;
+    int8_t *d_mat = nullptr;
+    // options
+    SwbPlanOpts plan_opts;
+    int opt_k = 0;
+    int nslots = 2;
+    uint32_t chunk_rows = SWB_CHUNK_ROWS;  // query rows per launch for queries beyond shared memory
+    // database
+    bool db_loaded = false;
+    SwbPlan plan;
+    int max_logg = 0;
+    SwbTile *d_tiles = nullptr;
+    uint8_t *d_residues = nullptr;
+    uint32_t *d_out_pos = nullptr;
+    int32_t *d_out = nullptr;
+    size_t out_cap = 0;  // in score vectors
+    uint32_t last_nq = 0;
+    Slot slots[SWB_MAX_SLOTS];
+    uint32_t *h_recount = nullptr;  // pinned, SWB_MAX_SLOTS
+    swb_stats_t stats;
+};
+
+static int fail(swb_engine *e, int code, const std::string &msg)
+{
+    if (e) e->err = msg;
+    return code;
+}
+
+#define CU(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t _e = (call);                                                                     \
+        if (_e != cudaSuccess) {                                                                     \
+            char _b[512];                                                                            \
+            snprintf(_b, sizeof _b, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, \
+                     __LINE__);                                                                      \
+            return fail(e, SWB_ERR_CUDA, _b);                                                        \
+        }                                                                                            \
+    } while (0)
+
+static cudaStream_t main_stream(swb_engine *e) { return e->user_stream ? e->user_stream : e->own_stream; }
+
+static void free_slot_db(Slot &s)
+{
+    if (s.d_state) cudaFree(s.d_state);
+    if (s.d_bnd16) cudaFree(s.d_bnd16);
+    if (s.d_bnd32) cudaFree(s.d_bnd32);
+    if (s.h_scores) cudaFreeHost(s.h_scores);
+    s.d_state = nullptr;
+    s.d_bnd16 = nullptr;
+    s.d_bnd32 = nullptr;
+    s.h_scores = nullptr;
+    s.state_bytes = 0;
+}
+
+static void free_db(swb_engine *e)
+{
+    if (e->d_tiles) cudaFree(e->d_tiles);
+    if (e->d_residues) cudaFree(e->d_residues);
+    if (e->d_out_pos) cudaFree(e->d_out_pos);
+    if (e->d_out) cudaFree(e->d_out);
+    e->d_tiles = nullptr;
+    e->d_residues = nullptr;
+    e->d_out_pos = nullptr;
+    e->d_out = nullptr;
+    e->out_cap = 0;
+    for (int i = 0; i < SWB_MAX_SLOTS; ++i) free_slot_db(e->slots[i]);
+    e->db_loaded = false;
+}
+
+extern "C" int swb_create(swb_engine **out, int device)
+{
+    if (!out) return SWB_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0) {
+        g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(ce) +
+                         " (this library has no CPU fallback)";
+        return SWB_ERR_CUDA;
+    }
+    if (device < 0 || device >= ndev) {
+        g_create_error = "device index out of range";
+        return SWB_ERR_ARG;
+    }
+    swb_engine *e = new swb_engine();
+    e->device = device;
+    memset(&e->stats, 0, sizeof e->stats);
+    auto bail = [&](const char *what, cudaError_t err) {
+        g_create_error = std::string(what) + ": " + cudaGetErrorString(err);
+        delete e;
+        return SWB_ERR_CUDA;
+    };
+    if ((ce = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", ce);
+    cudaDeviceProp prop;
+    if ((ce = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail("cudaGetDeviceProperties", ce);
+    if (prop.major < 10) {
+        g_create_error = std::string("device ") + prop.name + " is not sm_100-class; this library targets B200 only";
+        delete e;
+        return SWB_ERR_CUDA;
+    }
+    e->sm_count = prop.multiProcessorCount;
+    e->smem_optin = prop.sharedMemPerBlockOptin;
+    if ((ce = cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking)) != cudaSuccess)
+        return bail("cudaStreamCreate", ce);
+    cudaEventCreate(&e->ev_start);
+    cudaEventCreate(&e->ev_stop);
+    cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming);
+    for (int i = 0; i < SWB_MAX_SLOTS; ++i) {
+        if ((ce = cudaStreamCreateWithFlags(&e->slots[i].stream, cudaStreamNonBlocking)) != cudaSuccess)
+            return bail("cudaStreamCreate", ce);
+        cudaEventCreateWithFlags(&e->slots[i].done, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&e->ev_join[i], cudaEventDisableTiming);
+        if ((ce = cudaMalloc(&e->slots[i].d_recount, sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc", ce);
+    }
+    if ((ce = cudaMalloc(&e->d_mat, SWB_ALPHA * SWB_ALPHA)) != cudaSuccess) return bail("cudaMalloc", ce);
+    if ((ce = cudaMallocHost(&e->h_recount, SWB_MAX_SLOTS * sizeof(uint32_t))) != cudaSuccess)
+        return bail("cudaMallocHost", ce);
+    e->stats.sm_count = (uint32_t)e->sm_count;
+    *out = e;
+    int rc = swb_set_scoring_preset(e, SWB_SCORING_BLOSUM50_REF);
+    if (rc != SWB_OK) {
+        g_create_error = e->err;
+        swb_destroy(e);
+        *out = nullptr;
+        return rc;
+    }
+    return SWB_OK;
+}
+
+extern "C" void swb_destroy(swb_engine *e)
+{
+    if (!e) return;
+    cudaSetDevice(e->device);
+    cudaDeviceSynchronize();
+    free_db(e);
+    for (int i = 0; i < SWB_MAX_SLOTS; ++i) {
+        Slot &s = e->slots[i];
+        if (s.h_query) cudaFreeHost(s.h_query);
+        if (s.d_query) cudaFree(s.d_query);
+        if (s.d_prof) cudaFree(s.d_prof);
+        if (s.d_recount) cudaFree(s.d_recount);
+        if (s.stream) cudaStreamDestroy(s.stream);
+        if (s.done) cudaEventDestroy(s.done);
+        if (e->ev_join[i]) cudaEventDestroy(e->ev_join[i]);
+    }
+    if (e->d_mat) cudaFree(e->d_mat);
+    if (e->h_recount) cudaFreeHost(e->h_recount);
+    if (e->ev_start) cudaEventDestroy(e->ev_start);
+    if (e->ev_stop) cudaEventDestroy(e->ev_stop);
+    if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+    if (e->own_stream) cudaStreamDestroy(e->own_stream);
+    delete e;
+}
+
+extern "C" const char *swb_last_error(const swb_engine *e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int swb_set_option(swb_engine *e, const char *key, int64_t value)
+{
+    if (!e || !key) return SWB_ERR_ARG;
+    if (!strcmp(key, "group_len")) {
+        if (value < 8 || value > (1 << 30)) return fail(e, SWB_ERR_ARG, "group_len out of range");
+        e->plan_opts.group_len = (uint32_t)value;
+    } else if (!strcmp(key, "k")) {
+        if (value != 0 && value != 8 && value != 16 && value != 32) return fail(e, SWB_ERR_ARG, "k must be 0, 8, 16 or 32");
+        e->opt_k = (int)value;
+    } else if (!strcmp(key, "streams")) {
+        if (value < 1 || value > SWB_MAX_SLOTS) return fail(e, SWB_ERR_ARG, "streams must be 1..4");
+        if (e->db_loaded) return fail(e, SWB_ERR_STATE, "set streams before swb_db_load");
+        e->nslots = (int)value;
+    } else if (!strcmp(key, "chunk_rows")) {
+        if (value < 1024 || value > SWB_CHUNK_ROWS || value % 1024) return fail(e, SWB_ERR_ARG, "chunk_rows must be a multiple of 1024 up to 7168");
+        e->chunk_rows = (uint32_t)value;
+    } else {
+        return fail(e, SWB_ERR_ARG, std::string("unknown option ") + key);
+    }
+    return SWB_OK;
+}
+
+extern "C" int swb_set_stream(swb_engine *e, void *cuda_stream)
+{
+    if (!e) return SWB_ERR_ARG;
+    e->user_stream = (cudaStream_t)cuda_stream;
+    return SWB_OK;
+}
+
+extern "C" int swb_set_scoring(swb_engine *e, const int8_t *matrix, int alpha, int gap)
+{
+    if (!e || !matrix) return SWB_ERR_ARG;
+    if (alpha < 1 || alpha > SWB_ALPHA) return fail(e, SWB_ERR_ARG, "alpha must be 1..32");
+    if (gap < 0 || gap > 64) return fail(e, SWB_ERR_ARG, "gap must be 0..64");
+    int8_t m[SWB_ALPHA * SWB_ALPHA];
+    memset(m, 0, sizeof m);
+    int mx = 0;
+    for (int i = 0; i < alpha; ++i)
+        for (int j = 0; j < alpha; ++j) {
+            int v = matrix[i * alpha + j];
+            if (i == SWB_PAD || j == SWB_PAD) v = 0;  // the padding code is score-neutral by construction
+            if (v + gap > 127 || v + gap < -128) return fail(e, SWB_ERR_ARG, "matrix entry + gap does not fit int8");
+            m[i * SWB_ALPHA + j] = (int8_t)v;
+            mx = std::max(mx, v);
+        }
+    CU(cudaSetDevice(e->device));
+    CU(cudaStreamSynchronize(main_stream(e)));
+    memcpy(e->h_mat, m, sizeof m);
+    e->gap = gap;
+    e->max_s = mx;
+    CU(cudaMemcpy(e->d_mat, e->h_mat, sizeof m, cudaMemcpyHostToDevice));
+    e->scoring_set = true;
+    return SWB_OK;
+}
+
+extern "C" int swb_set_scoring_preset(swb_engine *e, int preset)
+{
+    if (!e) return SWB_ERR_ARG;
+    int8_t m[SWB_ALPHA * SWB_ALPHA];
+    int gap = 0;
+    if (swb_scoring_matrix(preset, m, &gap) != SWB_OK) return fail(e, SWB_ERR_ARG, "unknown scoring preset");
+    return swb_set_scoring(e, m, SWB_ALPHA, gap);
+}
+
+// ---------------------------------------------------------------------------------------------
+extern "C" int swb_db_load(swb_engine *e, const uint8_t *codes, const uint64_t *offsets, uint32_t n, uint32_t shard,
+                           uint32_t nshards)
+{
+    if (!e || !offsets || (!codes && n && offsets[n] != offsets[0])) return SWB_ERR_ARG;
+    if (nshards == 0) nshards = 1;
+    if (shard >= nshards) return fail(e, SWB_ERR_ARG, "shard >= nshards");
+    const double t0 = wall_ms();
+    CU(cudaSetDevice(e->device));
+    CU(cudaDeviceSynchronize());
+    free_db(e);
+    int rc = swb_build_plan(offsets, n, shard, nshards, e->plan_opts, e->plan);
+    if (rc != 0) return fail(e, SWB_ERR_ARG, "bad offsets (decreasing, or a sequence longer than 2^31-16)");
+    SwbPlan &pl = e->plan;
+    e->max_logg = 0;
+    for (int l = 0; l <= SWB_MAX_LOGG; ++l)
+        if (pl.tiles_by_logg[l]) e->max_logg = l;
+    cudaStream_t st = main_stream(e);
+    const uint32_t nl = pl.n_local;
+    const uint32_t ntiles = (uint32_t)pl.tiles.size();
+    const uint64_t base = n ? offsets[0] : 0;
+    const uint64_t raw_bytes = pl.residues_total;
+
+    uint8_t *d_raw = nullptr;
+    uint64_t *d_seq_off = nullptr;
+    uint32_t *d_seq_len = nullptr;
+    uint8_t *h_stage[2] = {nullptr, nullptr};
+    cudaEvent_t ev_stage[2] = {nullptr, nullptr};
+    auto cleanup_tmp = [&]() {
+        if (d_raw) cudaFree(d_raw);
+        if (d_seq_off) cudaFree(d_seq_off);
+        if (d_seq_len) cudaFree(d_seq_len);
+        for (int i = 0; i < 2; ++i) {
+            if (h_stage[i]) cudaFreeHost(h_stage[i]);
+            if (ev_stage[i]) cudaEventDestroy(ev_stage[i]);
+        }
+    };
+#define CUL(call)                                                                                    \
+    do {                                                                                             \
+        cudaError_t _e = (call);                                                                     \
+        if (_e != cudaSuccess) {                                                                     \
+            char _b[512];                                                                            \
+            snprintf(_b, sizeof _b, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, \
+                     __LINE__);                                                                      \
+            cleanup_tmp();                                                                           \
+            free_db(e);                                                                              \
+            return fail(e, SWB_ERR_CUDA, _b);                                                        \
+        }                                                                                            \
+    } while (0)
+
+    if (nl > 0 && ntiles > 0) {
+        CUL(cudaMalloc(&d_raw, std::max<uint64_t>(raw_bytes, 16)));
+        CUL(cudaMalloc(&d_seq_off, sizeof(uint64_t) * nl));
+        CUL(cudaMalloc(&d_seq_len, sizeof(uint32_t) * nl));
+        CUL(cudaMalloc(&e->d_tiles, sizeof(SwbTile) * ntiles));
+        CUL(cudaMalloc(&e->d_residues, std::max<uint64_t>(pl.res_bytes, 16)));
+        CUL(cudaMalloc(&e->d_out_pos, sizeof(uint32_t) * nl));
+        // stream the raw codes through two pinned staging buffers (async H2D overlapped with the host copy)
+        if (raw_bytes) {
+            const size_t stage = (size_t)std::min<uint64_t>(SWB_STAGE_BYTES, raw_bytes);
+            for (int i = 0; i < 2; ++i) {
+                CUL(cudaMallocHost(&h_stage[i], stage));
+                CUL(cudaEventCreateWithFlags(&ev_stage[i], cudaEventDisableTiming));
+            }
+            int b = 0;
+            for (uint64_t off = 0; off < raw_bytes; off += stage, b ^= 1) {
+                const size_t len = (size_t)std::min<uint64_t>(stage, raw_bytes - off);
+                CUL(cudaEventSynchronize(ev_stage[b]));
+                memcpy(h_stage[b], codes + base + off, len);
+                CUL(cudaMemcpyAsync(d_raw + off, h_stage[b], len, cudaMemcpyHostToDevice, st));
+                CUL(cudaEventRecord(ev_stage[b], st));
+            }
+        }
+        // offsets relative to the start of the uploaded range
+        std::vector<uint64_t> rel(nl);
+        for (uint32_t s = 0; s < nl; ++s) rel[s] = pl.seq_off[s] - base;
+        CUL(cudaMemcpyAsync(d_seq_off, rel.data(), sizeof(uint64_t) * nl, cudaMemcpyHostToDevice, st));
+        CUL(cudaMemcpyAsync(d_seq_len, pl.seq_len.data(), sizeof(uint32_t) * nl, cudaMemcpyHostToDevice, st));
+        CUL(cudaMemcpyAsync(e->d_tiles, pl.tiles.data(), sizeof(SwbTile) * ntiles, cudaMemcpyHostToDevice, st));
+        CUL(cudaMemcpyAsync(e->d_out_pos, pl.out_pos.data(), sizeof(uint32_t) * nl, cudaMemcpyHostToDevice, st));
+        CUL(swb_launch_pack(e->d_tiles, ntiles, d_raw, d_seq_off, d_seq_len, nl, e->d_residues, st));
+        // per-stream scratch
+        const size_t flags_bytes = swb_roundup(ntiles, 16);
+        const size_t sorted_bytes = sizeof(int32_t) * 2 * (size_t)((nl + 1) / 2);
+        const size_t head = sizeof(uint32_t) * SWB_MAX_COUNTERS;
+        for (int i = 0; i < e->nslots; ++i) {
+            Slot &s = e->slots[i];
+            s.state_bytes = head + flags_bytes + sorted_bytes;
+            CUL(cudaMalloc(&s.d_state, s.state_bytes));
+            s.d_counters = reinterpret_cast<uint32_t *>(s.d_state);
+            s.d_flags = s.d_state + head;
+            s.d_sorted = reinterpret_cast<int32_t *>(s.d_state + head + flags_bytes);
+            CUL(cudaMalloc(&s.d_bnd16, std::max<uint64_t>(sizeof(uint32_t) * pl.bnd_elems, 16)));
+            CUL(cudaMallocHost(&s.h_scores, std::max<size_t>(sizeof(int32_t) * nl, 16)));
+            s.busy = false;
+        }
+        CUL(cudaStreamSynchronize(st));
+    }
+    cleanup_tmp();
+#undef CUL
+    e->db_loaded = true;
+    e->stats.load_ms = wall_ms() - t0;
+    e->stats.db_residues = pl.residues_local;
+    e->stats.db_residues_total = pl.residues_total;
+    e->stats.db_sequences = nl;
+    e->stats.tiles = ntiles;
+    for (int l = 0; l <= SWB_MAX_LOGG; ++l) e->stats.tiles_by_group[l] = pl.tiles_by_logg[l];
+    return SWB_OK;
+}
+
+extern "C" uint32_t swb_db_count(const swb_engine *e) { return (e && e->db_loaded) ? e->plan.n_local : 0; }
+
+extern "C" int swb_db_ids(const swb_engine *e, uint32_t *ids)
+{
+    if (!e || !ids) return SWB_ERR_ARG;
+    if (!e->db_loaded) return SWB_ERR_STATE;
+    memcpy(ids, e->plan.shard_ids.data(), sizeof(uint32_t) * e->plan.n_local);
+    return SWB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// rows per lane: the value that minimises the estimated issue cost over the shard's group mix
+static int choose_k(const swb_engine *e, uint32_t qlen)
+{
+    if (e->opt_k) return e->opt_k;
+    const int ks[3] = {32, 16, 8};
+    double best = 0;
+    int best_k = 32;
+    for (int i = 0; i < 3; ++i) {
+        const int K = ks[i];
+        double cost = 0;
+        for (int l = 0; l <= SWB_MAX_LOGG; ++l) {
+            if (!e->plan.cols_by_logg[l]) continue;
+            const double rows = swb_roundup(qlen, (uint32_t)K << l);
+            cost += (double)e->plan.cols_by_logg[l] * rows * (1.0 + 4.0 / K);
+        }
+        if (i == 0 || cost < best) { best = cost; best_k = K; }
+    }
+    return best_k;
+}
+
+struct LaunchShape {
+    int block_cfg;
+    int grid;
+    size_t smem;
+};
+
+static int shape_for(swb_engine *e, int K, bool i32, uint32_t smem_rows, LaunchShape &ls)
+{
+    ls.smem = (size_t)SWB_ALPHA * (smem_rows + 4);
+    if (ls.smem > e->smem_optin) return fail(e, SWB_ERR_ARG, "internal: query chunk does not fit shared memory");
+    ls.block_cfg = ls.smem <= SWB_SMALL_SMEM_LIMIT ? SWB_BLOCK_SMALL : SWB_BLOCK_LARGE;
+    int per_sm = 0;
+    CU(swb_score_occupancy(K, i32, ls.block_cfg, ls.smem, &per_sm));
+    if (per_sm < 1) return fail(e, SWB_ERR_CUDA, "score kernel does not fit on an SM");
+    const int nt = ls.block_cfg == SWB_BLOCK_SMALL ? SWB_NT_SMALL : SWB_NT_LARGE;
+    const uint32_t ntiles = (uint32_t)e->plan.tiles.size();
+    const int need = (int)((ntiles + nt / 32 - 1) / (nt / 32));
+    ls.grid = std::max(1, std::min(per_sm * e->sm_count, need));
+    return SWB_OK;
+}
+
+// Enqueues everything one query needs on the slot's stream; the result lands in d_out[qi].
+static int enqueue_query(swb_engine *e, Slot &s, uint32_t qi, const uint8_t *q, uint32_t qlen)
+{
+    SwbPlan &pl = e->plan;
+    const uint32_t nl = pl.n_local;
+    int32_t *out = e->d_out + (size_t)qi * nl;
+    if (nl == 0) return SWB_OK;
+    if (qlen == 0 || pl.tiles.empty() || pl.max_len == 0) {
+        CU(cudaMemsetAsync(out, 0, sizeof(int32_t) * nl, s.stream));
+        return SWB_OK;
+    }
+    // the s16 pass, and the int32 pass over flagged tiles when a score could exceed the s16 range at all
+    const bool need_i32 = (int64_t)e->max_s * std::min<uint32_t>(qlen, pl.max_len) > 32767 - e->max_s;
+    SwbQueryPlan qp[2];
+    swb_plan_query(qlen, choose_k(e, qlen), e->max_logg, e->chunk_rows, qp[0]);
+    if (need_i32) swb_plan_query(qlen, std::min(qp[0].K, 16), e->max_logg, e->chunk_rows, qp[1]);
+    const int npass = need_i32 ? 2 : 1;
+    if (npass * qp[0].chunks.size() > SWB_MAX_COUNTERS) return fail(e, SWB_ERR_ARG, "query too long");
+    const uint32_t prof_rows = need_i32 ? std::max(qp[0].prof_rows, qp[1].prof_rows) : qp[0].prof_rows;
+    const uint32_t prof_stride = swb_roundup(prof_rows, 16);
+    if (qlen > s.query_cap) {
+        if (s.h_query) cudaFreeHost(s.h_query);
+        if (s.d_query) cudaFree(s.d_query);
+        s.h_query = nullptr;
+        s.d_query = nullptr;
+        s.query_cap = 0;
+        const uint32_t cap = swb_roundup(qlen, 4096);
+        CU(cudaMallocHost(&s.h_query, cap));
+        CU(cudaMalloc(&s.d_query, cap));
+        s.query_cap = cap;
+    }
+    if ((size_t)prof_stride * SWB_ALPHA > s.prof_cap) {
+        if (s.d_prof) cudaFree(s.d_prof);
+        s.d_prof = nullptr;
+        s.prof_cap = 0;
+        const size_t cap = (size_t)swb_roundup(prof_stride, 4096) * SWB_ALPHA;
+        CU(cudaMalloc(&s.d_prof, cap));
+        s.prof_cap = cap;
+    }
+    if (need_i32 && !s.d_bnd32) CU(cudaMalloc(&s.d_bnd32, std::max<uint64_t>(8ull * pl.bnd_elems, 16)));
+
+    memcpy(s.h_query, q, qlen);
+    CU(cudaMemcpyAsync(s.d_query, s.h_query, qlen, cudaMemcpyHostToDevice, s.stream));
+    CU(swb_launch_profile(s.d_query, qlen, e->d_mat, e->gap, s.d_prof, prof_stride, prof_rows, s.stream));
+    CU(cudaMemsetAsync(s.d_state, 0, s.state_bytes, s.stream));
+    e->stats.kernel_launches += 1;
+
+    SwbScoreParams p;
+    memset(&p, 0, sizeof p);
+    p.tiles = e->d_tiles;
+    p.ntiles = (uint32_t)pl.tiles.size();
+    p.residues = e->d_residues;
+    p.profile = s.d_prof;
+    p.prof_stride = prof_stride;
+    p.scores = s.d_sorted;
+    p.flags = s.d_flags;
+    p.recount = s.d_recount;
+    p.gap = e->gap;
+    p.ovf_thr = 32767 - e->max_s;
+    uint32_t counter = 0;
+    for (int pass = 0; pass < npass; ++pass) {
+        const bool i32 = pass == 1;
+        p.bnd = i32 ? s.d_bnd32 : (void *)s.d_bnd16;
+        p.only_flagged = i32 ? 1u : 0u;
+        for (size_t c = 0; c < qp[pass].chunks.size(); ++c) {
+            const SwbQueryChunk &ch = qp[pass].chunks[c];
+            LaunchShape ls;
+            int rc = shape_for(e, qp[pass].K, i32, ch.smem_rows, ls);
+            if (rc != SWB_OK) return rc;
+            p.row0 = ch.row0;
+            p.rows = ch.rows;
+            p.smem_rows = ch.smem_rows;
+            p.first_chunk = ch.first;
+            p.last_chunk = ch.last;
+            p.counter = s.d_counters + counter++;
+            CU(swb_launch_score(qp[pass].K, i32, ls.block_cfg, p, ls.grid, ls.smem, s.stream));
+            e->stats.kernel_launches += 1;
+        }
+    }
+    CU(swb_launch_scatter(s.d_sorted, e->d_out_pos, nl, out, s.stream));
+    e->stats.kernel_launches += 1;
+    e->stats.last_k = (uint32_t)qp[0].K;
+    for (int l = 0; l <= SWB_MAX_LOGG; ++l)
+        e->stats.padded_cells += pl.cols_by_logg[l] * (uint64_t)swb_roundup(qlen, (uint32_t)qp[0].K << l);
+    e->stats.cells += (uint64_t)qlen * pl.residues_local;
+    return SWB_OK;
+}
+
+static int finish_slot(swb_engine *e, Slot &s)
+{
+    if (!s.busy) return SWB_OK;
+    CU(cudaEventSynchronize(s.done));
+    s.busy = false;
+    if (s.pending_dst) {
+        memcpy(s.pending_dst, s.h_scores, sizeof(int32_t) * e->plan.n_local);
+        s.pending_dst = nullptr;
+    }
+    return SWB_OK;
+}
+
+extern "C" int swb_search_batch(swb_engine *e, const uint8_t *qcodes, const uint64_t *qoffsets, uint32_t nq,
+                                int32_t *scores)
+{
+    if (!e || !qoffsets || (!qcodes && nq && qoffsets[nq] != qoffsets[0])) return SWB_ERR_ARG;
+    if (!e->db_loaded) return fail(e, SWB_ERR_STATE, "swb_search before swb_db_load");
+    if (!e->scoring_set) return fail(e, SWB_ERR_STATE, "no scoring set");
+    CU(cudaSetDevice(e->device));
+    const uint32_t nl = e->plan.n_local;
+    for (uint32_t i = 0; i < nq; ++i)
+        if (qoffsets[i + 1] < qoffsets[i] || qoffsets[i + 1] - qoffsets[i] > 0x7fffffffull)
+            return fail(e, SWB_ERR_ARG, "bad query offsets");
+    cudaStream_t ms = main_stream(e);
+    if ((size_t)nq > e->out_cap && nl > 0) {
+        CU(cudaStreamSynchronize(ms));
+        if (e->d_out) cudaFree(e->d_out);
+        e->d_out = nullptr;
+        e->out_cap = 0;
+        CU(cudaMalloc(&e->d_out, sizeof(int32_t) * (size_t)nq * nl));
+        e->out_cap = nq;
+    }
+    e->stats.cells = 0;
+    e->stats.padded_cells = 0;
+    e->stats.kernel_launches = 0;
+    e->stats.recomputed_tiles = 0;
+    e->last_nq = nq;
+    const int ns = e->nslots;
+    CU(cudaEventRecord(e->ev_start, ms));
+    CU(cudaEventRecord(e->ev_fork, ms));
+    for (int i = 0; i < ns; ++i) {
+        CU(cudaStreamWaitEvent(e->slots[i].stream, e->ev_fork, 0));
+        CU(cudaMemsetAsync(e->slots[i].d_recount, 0, sizeof(uint32_t), e->slots[i].stream));
+    }
+    int rc = SWB_OK;
+    for (uint32_t qi = 0; qi < nq && rc == SWB_OK; ++qi) {
+        Slot &s = e->slots[qi % ns];
+        if ((rc = finish_slot(e, s)) != SWB_OK) break;
+        const uint32_t qlen = (uint32_t)(qoffsets[qi + 1] - qoffsets[qi]);
+        if ((rc = enqueue_query(e, s, qi, qcodes + qoffsets[qi], qlen)) != SWB_OK) break;
+        if (scores && nl > 0) {
+            CU(cudaMemcpyAsync(s.h_scores, e->d_out + (size_t)qi * nl, sizeof(int32_t) * nl, cudaMemcpyDeviceToHost,
+                               s.stream));
+            s.pending_dst = scores + (size_t)qi * nl;
+        }
+        CU(cudaEventRecord(s.done, s.stream));
+        s.busy = true;
+    }
+    for (int i = 0; i < ns; ++i) {
+        CU(cudaMemcpyAsync(e->h_recount + i, e->slots[i].d_recount, sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                           e->slots[i].stream));
+        CU(cudaEventRecord(e->ev_join[i], e->slots[i].stream));
+        CU(cudaStreamWaitEvent(ms, e->ev_join[i], 0));
+    }
+    CU(cudaEventRecord(e->ev_stop, ms));
+    for (int i = 0; i < ns; ++i) {
+        int r2 = finish_slot(e, e->slots[i]);
+        if (rc == SWB_OK) rc = r2;
+    }
+    CU(cudaStreamSynchronize(ms));
+    if (rc != SWB_OK) return rc;
+    float ms_f = 0;
+    CU(cudaEventElapsedTime(&ms_f, e->ev_start, e->ev_stop));
+    e->stats.device_ms = ms_f;
+    for (int i = 0; i < ns; ++i) e->stats.recomputed_tiles += e->h_recount[i];
+    return SWB_OK;
+}
+
+extern "C" int swb_search(swb_engine *e, const uint8_t *query, uint32_t qlen, int32_t *scores)
+{
+    if (!e || (!query && qlen) || !scores) return SWB_ERR_ARG;
+    const uint64_t offs[2] = {0, qlen};
+    static const uint8_t dummy = 0;
+    return swb_search_batch(e, query ? query : &dummy, offs, 1, scores);
+}
+
+extern "C" int swb_fetch_scores(swb_engine *e, uint32_t query_index, int32_t *scores)
+{
+    if (!e || !scores) return SWB_ERR_ARG;
+    if (!e->db_loaded || query_index >= e->last_nq) return fail(e, SWB_ERR_STATE, "no such result");
+    CU(cudaSetDevice(e->device));
+    const uint32_t nl = e->plan.n_local;
+    if (nl == 0) return SWB_OK;
+    CU(cudaMemcpy(scores, e->d_out + (size_t)query_index * nl, sizeof(int32_t) * nl, cudaMemcpyDeviceToHost));
+    return SWB_OK;
+}
+
+extern "C" int swb_topk(const swb_engine *e, const int32_t *scores, uint32_t k, uint32_t *ids, int32_t *top)
+{
+    if (!e || !scores || !ids || !top) return SWB_ERR_ARG;
+    if (!e->db_loaded) return SWB_ERR_STATE;
+    const uint32_t nl = e->plan.n_local;
+    const uint32_t kk = std::min(k, nl);
+    std::vector<uint32_t> idx(nl);
+    for (uint32_t i = 0; i < nl; ++i) idx[i] = i;
+    auto better = [&](uint32_t a, uint32_t b) { return scores[a] != scores[b] ? scores[a] > scores[b] : a < b; };
+    std::partial_sort(idx.begin(), idx.begin() + kk, idx.end(), better);
+    for (uint32_t i = 0; i < kk; ++i) {
+        ids[i] = e->plan.shard_ids[idx[i]];
+        top[i] = scores[idx[i]];
+    }
+    for (uint32_t i = kk; i < k; ++i) {
+        ids[i] = 0xffffffffu;
+        top[i] = -1;
+    }
+    return SWB_OK;
+}
+
+extern "C" int swb_stats(const swb_engine *e, swb_stats_t *out)
+{
+    if (!e || !out) return SWB_ERR_ARG;
+    *out = e->stats;
+    return SWB_OK;
+}
+
+extern "C" int swb_plan_describe(const uint64_t *offsets, uint32_t n, uint32_t shard, uint32_t nshards,
+                                 uint32_t group_len, swb_plan_info_t *info, uint32_t *sorted_ids, uint32_t *shard_ids)
+{
+    if (!offsets || !info) return SWB_ERR_ARG;
+    SwbPlanOpts o;
+    if (group_len) o.group_len = group_len;
+    SwbPlan pl;
+    if (swb_build_plan(offsets, n, shard, nshards ? nshards : 1, o, pl) != 0) return SWB_ERR_ARG;
+    memset(info, 0, sizeof *info);
+    info->n_total = pl.n_total;
+    info->n_local = pl.n_local;
+    info->tiles = (uint32_t)pl.tiles.size();
+    info->max_len = pl.max_len;
+    info->residues_local = pl.residues_local;
+    info->residues_total = pl.residues_total;
+    info->res_bytes = pl.res_bytes;
+    info->bnd_elems = pl.bnd_elems;
+    info->padded_cols = pl.padded_cols;
+    for (int l = 0; l <= SWB_MAX_LOGG; ++l) info->tiles_by_group[l] = pl.tiles_by_logg[l];
+    if (sorted_ids) memcpy(sorted_ids, pl.sorted_ids.data(), sizeof(uint32_t) * pl.n_local);
+    if (shard_ids) memcpy(shard_ids, pl.shard_ids.data(), sizeof(uint32_t) * pl.n_local);
+    return SWB_OK;
+}

@@ -1,0 +1,193 @@
+// sm_100a kernels of the scan engine: score kernels (instantiations of swb_warp.cuh), query-profile
+// builder, device-side DB packer and score scatter. Host-side launch wrappers at the bottom.
+#include "swb_kernels.h"
+#include "swb_warp.cuh"
+
+// ---------------------------------------------------------------------------------------------
+struct DevBackend {
+    __device__ __forceinline__ int lane() const { return (int)(threadIdx.x & 31u); }
+    __device__ __forceinline__ uint32_t shfl_up(uint32_t v, int d, int w) const
+    {
+        return __shfl_up_sync(0xffffffffu, v, (unsigned)d, w);
+    }
+    __device__ __forceinline__ uint32_t shfl_xor(uint32_t v, int m, int w) const
+    {
+        return __shfl_xor_sync(0xffffffffu, v, m, w);
+    }
+    __device__ __forceinline__ void syncwarp() const { __syncwarp(); }
+    __device__ __forceinline__ bool any(bool f) const { return __any_sync(0xffffffffu, f) != 0; }
+    __device__ __forceinline__ uint32_t next_tile(uint32_t *counter) const
+    {
+        uint32_t v = 0;
+        if ((threadIdx.x & 31u) == 0) v = atomicAdd(counter, 1u);
+        return __shfl_sync(0xffffffffu, v, 0);
+    }
+    __device__ __forceinline__ void count(uint32_t *p) const { atomicAdd(p, 1u); }
+    __device__ __forceinline__ uint8_t ld_flag(const uint8_t *p) const { return __ldcg(p); }
+    __device__ __forceinline__ SwbTile ld_tile(const SwbTile *p) const
+    {
+        union { SwbTile t; uint4 v[2]; } u;
+        u.v[0] = __ldg(reinterpret_cast<const uint4 *>(p));
+        u.v[1] = __ldg(reinterpret_cast<const uint4 *>(p) + 1);
+        return u.t;
+    }
+    __device__ __forceinline__ uint2 ld_res(const uint2 *p) const { return __ldg(p); }
+    __device__ __forceinline__ uint32_t ld_cg(const uint32_t *p) const { return __ldcg(p); }
+    __device__ __forceinline__ uint2 ld_cg2(const uint2 *p) const { return __ldcg(p); }
+    __device__ __forceinline__ uint4 ld_cg4(const uint4 *p) const { return __ldcg(p); }
+    __device__ __forceinline__ void st_cg(uint32_t *p, uint32_t v) const { __stcg(p, v); }
+    __device__ __forceinline__ void st_cg2(uint2 *p, uint2 v) const { __stcg(p, v); }
+    __device__ __forceinline__ void st_cg4(uint4 *p, uint4 v) const { __stcg(p, v); }
+};
+
+static_assert(sizeof(SwbTile) == 32, "SwbTile must be 32 bytes");
+
+// Persistent blocks: stage the query profile of this chunk in shared memory once, then every warp
+// pulls tiles from the shared counter until the list is empty.
+// Shared profile layout: [32 codes][smem_rows + 4] int8. The +4 makes consecutive code rows start one
+// bank apart, so the 32 lanes of an LDS.32 (same row offset, per-lane code) never conflict: equal
+// codes broadcast, different codes hit different banks.
+template <int K, class V, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) swb_score_kernel(const SwbScoreParams p)
+{
+    extern __shared__ __align__(16) int8_t sprof[];
+    const uint32_t sstride = p.smem_rows + 4u;
+    const uint32_t wpr = p.smem_rows >> 2;  // words per code row
+    for (uint32_t i = threadIdx.x; i < wpr * SWB_ALPHA; i += NT) {
+        const uint32_t code = i / wpr, w = i - code * wpr;
+        reinterpret_cast<uint32_t *>(sprof + (size_t)code * sstride)[w] =
+            __ldg(reinterpret_cast<const uint32_t *>(p.profile + (size_t)code * p.prof_stride + p.row0) + w);
+    }
+    __syncthreads();
+    DevBackend be;
+    swb_warp_loop<K, V>(be, p, sprof, sstride);
+}
+
+// profile[code][r] = S(q_r, code) + gap for r < qlen, gap (score 0) for the padding rows.
+__global__ void swb_profile_kernel(const uint8_t *__restrict__ q, uint32_t qlen, const int8_t *__restrict__ mat,
+                                   int gap, int8_t *__restrict__ prof, uint32_t stride, uint32_t rows)
+{
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const uint32_t qc = r < qlen ? (uint32_t)(q[r] & 31u) : (uint32_t)SWB_PAD;
+#pragma unroll 4
+    for (uint32_t code = 0; code < SWB_ALPHA; ++code)
+        prof[(size_t)code * stride + r] = (int8_t)(mat[qc * SWB_ALPHA + code] + gap);
+}
+
+// One block per tile (grid-stride): gathers the tile's sequences from the raw concatenated codes into
+// the interleaved 8-byte words the score kernel streams.
+__global__ void swb_pack_kernel(const SwbTile *__restrict__ tiles, uint32_t ntiles, const uint8_t *__restrict__ raw,
+                                const uint64_t *__restrict__ seq_off, const uint32_t *__restrict__ seq_len,
+                                uint32_t nseq, uint8_t *__restrict__ residues)
+{
+    for (uint32_t ti = blockIdx.x; ti < ntiles; ti += gridDim.x) {
+        const SwbTile t = tiles[ti];
+        const uint32_t P = 32u >> t.logG;
+        const uint32_t total = (t.width >> 2) * P;
+        uint64_t *out = reinterpret_cast<uint64_t *>(residues + t.res_off);
+        for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
+            const uint32_t c = i / P, slot = i - c * P;
+            out[i] = swb_pack_word(t, c, slot, raw, seq_off, seq_len, nseq);
+        }
+    }
+}
+
+// scores in sorted order -> caller order
+__global__ void swb_scatter_kernel(const int32_t *__restrict__ sorted, const uint32_t *__restrict__ dst,
+                                   uint32_t n, int32_t *__restrict__ out)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[dst[i]] = sorted[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+template <int K, class V, int NT, int MINB>
+static cudaError_t launch_one(const SwbScoreParams &p, int grid, size_t smem, cudaStream_t st)
+{
+    auto kern = swb_score_kernel<K, V, NT, MINB>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, NT, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+template <int K, class V>
+static cudaError_t launch_k(const SwbScoreParams &p, int block_cfg, int grid, size_t smem, cudaStream_t st)
+{
+    if (block_cfg == SWB_BLOCK_SMALL) return launch_one<K, V, SWB_NT_SMALL, SWB_MINB_SMALL>(p, grid, smem, st);
+    return launch_one<K, V, SWB_NT_LARGE, 1>(p, grid, smem, st);
+}
+
+cudaError_t swb_launch_score(int K, bool i32, int block_cfg, const SwbScoreParams &p, int grid, size_t smem,
+                             cudaStream_t st)
+{
+    if (!i32) {
+        switch (K) {
+        case 8: return launch_k<8, V16>(p, block_cfg, grid, smem, st);
+        case 16: return launch_k<16, V16>(p, block_cfg, grid, smem, st);
+        case 32: return launch_k<32, V16>(p, block_cfg, grid, smem, st);
+        }
+    } else {
+        switch (K) {
+        case 8: return launch_k<8, V32>(p, block_cfg, grid, smem, st);
+        case 16: return launch_k<16, V32>(p, block_cfg, grid, smem, st);
+        }
+    }
+    return cudaErrorInvalidValue;
+}
+
+template <int K, class V>
+static cudaError_t occ_k(int block_cfg, size_t smem, int *blocks)
+{
+    if (block_cfg == SWB_BLOCK_SMALL) {
+        auto kern = swb_score_kernel<K, V, SWB_NT_SMALL, SWB_MINB_SMALL>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, kern, SWB_NT_SMALL, smem);
+    }
+    auto kern = swb_score_kernel<K, V, SWB_NT_LARGE, 1>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, kern, SWB_NT_LARGE, smem);
+}
+
+cudaError_t swb_score_occupancy(int K, bool i32, int block_cfg, size_t smem, int *blocks)
+{
+    if (!i32) {
+        switch (K) {
+        case 8: return occ_k<8, V16>(block_cfg, smem, blocks);
+        case 16: return occ_k<16, V16>(block_cfg, smem, blocks);
+        case 32: return occ_k<32, V16>(block_cfg, smem, blocks);
+        }
+    } else {
+        switch (K) {
+        case 8: return occ_k<8, V32>(block_cfg, smem, blocks);
+        case 16: return occ_k<16, V32>(block_cfg, smem, blocks);
+        }
+    }
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t swb_launch_profile(const uint8_t *q, uint32_t qlen, const int8_t *mat, int gap, int8_t *prof,
+                               uint32_t stride, uint32_t rows, cudaStream_t st)
+{
+    swb_profile_kernel<<<(rows + 255) / 256, 256, 0, st>>>(q, qlen, mat, gap, prof, stride, rows);
+    return cudaGetLastError();
+}
+
+cudaError_t swb_launch_pack(const SwbTile *tiles, uint32_t ntiles, const uint8_t *raw, const uint64_t *seq_off,
+                            const uint32_t *seq_len, uint32_t nseq, uint8_t *residues, cudaStream_t st)
+{
+    if (ntiles == 0) return cudaSuccess;
+    const uint32_t grid = ntiles < 65535u * 16u ? ntiles : 65535u * 16u;
+    swb_pack_kernel<<<grid, 256, 0, st>>>(tiles, ntiles, raw, seq_off, seq_len, nseq, residues);
+    return cudaGetLastError();
+}
+
+cudaError_t swb_launch_scatter(const int32_t *sorted, const uint32_t *dst, uint32_t n, int32_t *out, cudaStream_t st)
+{
+    if (n == 0) return cudaSuccess;
+    swb_scatter_kernel<<<(n + 255) / 256, 256, 0, st>>>(sorted, dst, n, out);
+    return cudaGetLastError();
+}

@@ -1,0 +1,22 @@
+// Internal C++ interface between the engine (swb_engine.cu) and the kernels (swb_kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include "swb_types.h"
+
+// block shapes of the score kernel: SMALL when the staged profile leaves room for several blocks per SM,
+// LARGE (one block per SM) when the profile of a long query fills most of the 227 KB of shared memory.
+#define SWB_BLOCK_SMALL 0
+#define SWB_BLOCK_LARGE 1
+#define SWB_NT_SMALL 256
+#define SWB_MINB_SMALL 2
+#define SWB_NT_LARGE 512
+
+cudaError_t swb_launch_score(int K, bool i32, int block_cfg, const SwbScoreParams &p, int grid, size_t smem,
+                             cudaStream_t st);
+cudaError_t swb_score_occupancy(int K, bool i32, int block_cfg, size_t smem, int *blocks_per_sm);
+cudaError_t swb_launch_profile(const uint8_t *q, uint32_t qlen, const int8_t *mat, int gap, int8_t *prof,
+                               uint32_t stride, uint32_t rows, cudaStream_t st);
+cudaError_t swb_launch_pack(const SwbTile *tiles, uint32_t ntiles, const uint8_t *raw, const uint64_t *seq_off,
+                            const uint32_t *seq_len, uint32_t nseq, uint8_t *residues, cudaStream_t st);
+cudaError_t swb_launch_scatter(const int32_t *sorted, const uint32_t *dst, uint32_t n, int32_t *out,
+                               cudaStream_t st);

@@ -1,0 +1,89 @@
+// Measurement support: issue-rate micro-benchmarks of the integer SIMD instructions the score kernel is
+// made of. bench.py uses the "mix" figure as the denominator of the integer-pipe roofline (SURVEY 8(d):
+// MEASURED_PEAKS.json only has HBM and bf16 numbers). Not part of the scoring path.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/swb.h"
+
+#define MB_CHAINS 8
+
+template <int KIND>
+__global__ void __launch_bounds__(256) swb_mb_kernel(uint32_t *out, uint32_t seed, int iters)
+{
+    uint32_t x[MB_CHAINS];
+    const uint32_t a = seed * 0x9E3779B9u + threadIdx.x, b = seed ^ 0x00010001u, one = (seed >> 31) + 1u;
+#pragma unroll
+    for (int c = 0; c < MB_CHAINS; ++c) x[c] = a + c * 0x00030005u;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int c = 0; c < MB_CHAINS; ++c) {
+            if (KIND == 0) x[c] = __viaddmax_s16x2_relu(x[c], b, a);
+            if (KIND == 1) x[c] = __vimax3_s16x2(x[c], b, a);
+            if (KIND == 2) x[c] = __vadd2(x[c], b);
+            if (KIND == 3) asm volatile("prmt.b32 %0, %1, %2, 0xC480;" : "=r"(x[c]) : "r"(x[c]), "r"(b));
+            if (KIND == 4) {  // the score kernel's per-cell-pair mix: 2 viaddmax, 1 vadd, 1 prmt, 1/2 vimax3
+                uint32_t s;
+                asm volatile("prmt.b32 %0, %1, %2, 0xD591;" : "=r"(s) : "r"(x[c]), "r"(b));
+                const uint32_t cc = __viaddmax_s16x2_relu(x[c], s, a);
+                x[c] = __viaddmax_s16x2(x[c], b, cc);
+                x[c] = __vadd2(x[c], b);
+                if (c & 1) x[c] = __vimax3_s16x2(x[c], x[c - 1], cc);
+            }
+            if (KIND == 5) {  // does an IMAD (fma pipe) issue beside the DPX op?
+                x[c] = __viaddmax_s16x2_relu(x[c], b, a);
+                x[c] = x[c] * one + b;
+            }
+            if (KIND == 6) x[c] = x[c] * one + b;  // IMAD alone
+            if (KIND == 7) x[c] = max(x[c] + b, a);  // scalar add+max (what the compiler makes of int32 cells)
+        }
+    }
+    uint32_t r = 0;
+#pragma unroll
+    for (int c = 0; c < MB_CHAINS; ++c) r ^= x[c];
+    if (r == 0x12345678u) out[0] = r;
+}
+
+static const double kInstrPerIter[8] = {MB_CHAINS, MB_CHAINS, MB_CHAINS, MB_CHAINS, MB_CHAINS * 4.5, MB_CHAINS * 2.0,
+                                        MB_CHAINS, MB_CHAINS};
+
+// kind 0 viaddmax.relu, 1 vimax3, 2 vadd2, 3 prmt, 4 score-kernel mix, 5 viaddmax+imad, 6 imad, 7 scalar add/max.
+// Returns giga lane-instructions per second (warp instructions x 32) over the whole GPU.
+extern "C" int swb_microbench(int device, int kind, double *glane_instr_per_s, double *ms_out)
+{
+    if (kind < 0 || kind > 7 || !glane_instr_per_s) return SWB_ERR_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return SWB_ERR_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return SWB_ERR_CUDA;
+    uint32_t *d = nullptr;
+    if (cudaMalloc(&d, 64) != cudaSuccess) return SWB_ERR_CUDA;
+    const int grid = prop.multiProcessorCount * 8, block = 256, iters = 4096;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(e0);
+        switch (kind) {
+        case 0: swb_mb_kernel<0><<<grid, block>>>(d, 7u + rep, iters); break;
+        case 1: swb_mb_kernel<1><<<grid, block>>>(d, 7u + rep, iters); break;
+        case 2: swb_mb_kernel<2><<<grid, block>>>(d, 7u + rep, iters); break;
+        case 3: swb_mb_kernel<3><<<grid, block>>>(d, 7u + rep, iters); break;
+        case 4: swb_mb_kernel<4><<<grid, block>>>(d, 7u + rep, iters); break;
+        case 5: swb_mb_kernel<5><<<grid, block>>>(d, 7u + rep, iters); break;
+        case 6: swb_mb_kernel<6><<<grid, block>>>(d, 7u + rep, iters); break;
+        default: swb_mb_kernel<7><<<grid, block>>>(d, 7u + rep, iters); break;
+        }
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(d); return SWB_ERR_CUDA; }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    const double lane_instr = (double)grid * block * iters * kInstrPerIter[kind];
+    *glane_instr_per_s = lane_instr / (best * 1e-3) * 1e-9;
+    if (ms_out) *ms_out = best;
+    return SWB_OK;
+}

@@ -1,0 +1,137 @@
+#include "swb_plan.h"
+#include <algorithm>
+#include <string.h>
+
+// Stable LSD radix sort of ids by DESCENDING length (16-bit digits; the high pass is skipped when all
+// lengths fit 16 bits, which is the case for protein databases up to titin's 35k).
+static void sort_by_length_desc(const std::vector<uint32_t> &len, std::vector<uint32_t> &ids)
+{
+    const uint32_t n = (uint32_t)len.size();
+    ids.resize(n);
+    for (uint32_t i = 0; i < n; ++i) ids[i] = i;
+    uint32_t maxlen = 0;
+    for (uint32_t i = 0; i < n; ++i) maxlen = std::max(maxlen, len[i]);
+    std::vector<uint32_t> tmp(n);
+    std::vector<uint32_t> cnt(65537);
+    const int passes = maxlen > 0xffffu ? 2 : 1;
+    for (int pass = 0; pass < passes; ++pass) {
+        const int shift = 16 * pass;
+        std::fill(cnt.begin(), cnt.end(), 0u);
+        // descending: bucket index = 0xffff - digit
+        for (uint32_t i = 0; i < n; ++i) cnt[(0xffffu - ((len[ids[i]] >> shift) & 0xffffu)) + 1]++;
+        for (uint32_t d = 0; d < 65536; ++d) cnt[d + 1] += cnt[d];
+        for (uint32_t i = 0; i < n; ++i) tmp[cnt[0xffffu - ((len[ids[i]] >> shift) & 0xffffu)]++] = ids[i];
+        ids.swap(tmp);
+    }
+}
+
+static uint8_t classify_logg(uint32_t len, uint32_t group_len)
+{
+    uint8_t lg = 0;
+    uint64_t cap = group_len ? group_len : 1;
+    while (lg < SWB_MAX_LOGG && len > cap) { cap <<= 1; ++lg; }
+    return lg;
+}
+
+int swb_build_plan(const uint64_t *offsets, uint32_t n, uint32_t shard, uint32_t nshards, const SwbPlanOpts &o,
+                   SwbPlan &plan)
+{
+    if (nshards == 0 || shard >= nshards) return -1;
+    plan = SwbPlan();
+    plan.n_total = n;
+    plan.shard = shard;
+    plan.nshards = nshards;
+    std::vector<uint32_t> len(n);
+    for (uint32_t i = 0; i < n; ++i) {
+        if (offsets[i + 1] < offsets[i]) return -2;
+        const uint64_t l = offsets[i + 1] - offsets[i];
+        if (l > 0x7ffffff0ull) return -3;
+        len[i] = (uint32_t)l;
+    }
+    plan.residues_total = n ? offsets[n] - offsets[0] : 0;
+    std::vector<uint32_t> order;
+    sort_by_length_desc(len, order);
+
+    // residue-balanced sharding: deal PAIRS of the length-sorted list round-robin, so every shard gets the
+    // same length mix and its residue total differs from the others by at most one pair per round
+    plan.sorted_ids.reserve(n / nshards + 2);
+    for (uint32_t s = 0; s < n; ++s)
+        if ((s >> 1) % nshards == shard) plan.sorted_ids.push_back(order[s]);
+    plan.n_local = (uint32_t)plan.sorted_ids.size();
+    const uint32_t nl = plan.n_local;
+
+    plan.shard_ids = plan.sorted_ids;
+    std::sort(plan.shard_ids.begin(), plan.shard_ids.end());
+    plan.out_pos.resize(nl);
+    if (nshards == 1) {
+        for (uint32_t s = 0; s < nl; ++s) plan.out_pos[s] = plan.sorted_ids[s];
+    } else {
+        for (uint32_t s = 0; s < nl; ++s)
+            plan.out_pos[s] = (uint32_t)(std::lower_bound(plan.shard_ids.begin(), plan.shard_ids.end(),
+                                                          plan.sorted_ids[s]) - plan.shard_ids.begin());
+    }
+    plan.seq_off.resize(nl);
+    plan.seq_len.resize(nl);
+    for (uint32_t s = 0; s < nl; ++s) {
+        plan.seq_off[s] = offsets[plan.sorted_ids[s]];
+        plan.seq_len[s] = len[plan.sorted_ids[s]];
+        plan.residues_local += plan.seq_len[s];
+    }
+    plan.max_len = nl ? plan.seq_len[0] : 0;
+
+    // tiles: consecutive pairs of the sorted list; the group size follows the tile's longest sequence
+    const uint32_t npairs_total = (nl + 1) / 2;
+    memset(plan.tiles_by_logg, 0, sizeof plan.tiles_by_logg);
+    memset(plan.cols_by_logg, 0, sizeof plan.cols_by_logg);
+    uint32_t pair = 0;
+    while (pair < npairs_total) {
+        const uint32_t head_len = plan.seq_len[2 * (size_t)pair];
+        SwbTile t;
+        memset(&t, 0, sizeof t);
+        t.logG = classify_logg(head_len, o.group_len);
+        const uint32_t slots = 32u >> t.logG;
+        t.first_pair = pair;
+        t.npairs = (uint16_t)std::min<uint32_t>(slots, npairs_total - pair);
+        t.width = swb_roundup(head_len, SWB_COLS_PER_CHUNK);
+        plan.tiles.push_back(t);
+        plan.tiles_by_logg[t.logG]++;
+        pair += t.npairs;
+    }
+    // longest-per-lane first: the dynamic scheduler then behaves like LPT list scheduling
+    std::stable_sort(plan.tiles.begin(), plan.tiles.end(), [](const SwbTile &a, const SwbTile &b) {
+        return ((uint64_t)a.width >> a.logG) > ((uint64_t)b.width >> b.logG);
+    });
+    uint64_t res = 0, bnd = 0;
+    for (size_t i = 0; i < plan.tiles.size(); ++i) {
+        SwbTile &t = plan.tiles[i];
+        const uint64_t slots = 32u >> t.logG;
+        t.res_off = res;
+        t.bnd_off = bnd;
+        res += (uint64_t)t.width * slots * 2u;
+        bnd += (uint64_t)t.width * slots;
+        plan.padded_cols += (uint64_t)t.width * slots * 2u;
+        plan.cols_by_logg[t.logG] += (uint64_t)t.width * slots * 2u;
+    }
+    plan.res_bytes = res;
+    plan.bnd_elems = bnd;
+    return 0;
+}
+
+void swb_plan_query(uint32_t qlen, int K, int max_logg, uint32_t chunk_rows, SwbQueryPlan &qp)
+{
+    qp.K = K;
+    qp.chunks.clear();
+    qp.prof_rows = 0;
+    const uint32_t gran = (uint32_t)K << max_logg;
+    const uint32_t nchunks = (qlen + chunk_rows - 1) / chunk_rows;
+    for (uint32_t c = 0; c < nchunks; ++c) {
+        SwbQueryChunk ch;
+        ch.row0 = c * chunk_rows;
+        ch.rows = std::min(chunk_rows, qlen - ch.row0);
+        ch.smem_rows = swb_roundup(swb_roundup(ch.rows, gran), 128);
+        ch.first = c == 0;
+        ch.last = c + 1 == nchunks;
+        qp.chunks.push_back(ch);
+        qp.prof_rows = std::max(qp.prof_rows, ch.row0 + ch.smem_rows);
+    }
+}

@@ -1,0 +1,51 @@
+// Host-side database plan: length sort, residue-balanced sharding, pairing and tiling.
+// Pure C++ (no CUDA) so it can be exercised on CPU-only machines through the C ABI (swb_plan_*).
+#pragma once
+#include <stdint.h>
+#include <vector>
+#include "swb_types.h"
+
+struct SwbPlanOpts {
+    uint32_t group_len;   // sequences up to this length run one lane per pair (G=1); each doubling of the
+                          // length doubles G up to 32
+    SwbPlanOpts() : group_len(384) {}
+};
+
+struct SwbPlan {
+    uint32_t n_total;                 // sequences in the whole database
+    uint32_t n_local;                 // sequences of this shard
+    uint32_t shard, nshards;
+    std::vector<uint32_t> sorted_ids; // [n_local] DB ids, longest first, ties in DB order
+    std::vector<uint32_t> out_pos;    // [n_local] position of sorted entry s in the shard's output order
+    std::vector<uint32_t> shard_ids;  // [n_local] DB ids in output order (ascending)
+    std::vector<uint64_t> seq_off;    // [n_local] offset of sorted entry s in the raw code buffer
+    std::vector<uint32_t> seq_len;    // [n_local]
+    std::vector<SwbTile> tiles;       // longest-per-lane first
+    uint64_t res_bytes;               // packed residue buffer size
+    uint64_t bnd_elems;               // boundary scratch elements
+    uint64_t residues_local;          // true residues of this shard
+    uint64_t residues_total;
+    uint64_t padded_cols;             // sum over tiles of width * slots * 2 (cells per query row incl. padding)
+    uint32_t max_len;                 // longest sequence of the shard
+    uint32_t tiles_by_logg[SWB_MAX_LOGG + 1];
+    uint64_t cols_by_logg[SWB_MAX_LOGG + 1];  // padded sequence-columns (width * slots * 2) per group size
+};
+
+// offsets: n+1 entries. Returns 0 or a negative error (lengths above 2^31-8).
+int swb_build_plan(const uint64_t *offsets, uint32_t n, uint32_t shard, uint32_t nshards, const SwbPlanOpts &o,
+                   SwbPlan &plan);
+
+// How one query is cut into score-kernel launches ("chunks" of query rows that fit shared memory).
+struct SwbQueryChunk {
+    uint32_t row0;       // first query row
+    uint32_t rows;       // query rows of the chunk
+    uint32_t smem_rows;  // rows staged per code (covers the largest group's padding, multiple of 128)
+    uint32_t first, last;
+};
+struct SwbQueryPlan {
+    int K;
+    uint32_t prof_rows;  // rows the global profile must provide (rows beyond qlen score 0)
+    std::vector<SwbQueryChunk> chunks;
+};
+// chunk_rows must be a multiple of 32 * 32 (all K <= 32 and group sizes then tile it exactly)
+void swb_plan_query(uint32_t qlen, int K, int max_logg, uint32_t chunk_rows, SwbQueryPlan &qp);

@@ -1,0 +1,51 @@
+// Shared host/device types of the B200 Smith-Waterman scan engine.
+#pragma once
+#include <stdint.h>
+
+#define SWB_ALPHA 32          // codes per residue (5 bits in a byte)
+#define SWB_PAD 31            // padding code: zero row and column in every scoring matrix
+#define SWB_STAR 24           // '*' / unknown (SWSolver.cu:41, 119 of the reference)
+#define SWB_COLS_PER_CHUNK 4  // DB columns per residue / boundary chunk
+#define SWB_MAX_LOGG 5        // lane-group sizes 1,2,4,8,16,32
+
+#if defined(__CUDACC__)
+#define SWB_HD __host__ __device__ __forceinline__
+#else
+#define SWB_HD inline
+#endif
+
+// One warp-tile: 32/G pairs of DB sequences of similar length, G lanes per pair.
+// Residues: [chunk c][slot p][4 columns x (seqA, seqB)] bytes, 8 bytes per (c, p), slots = 32 >> logG.
+// Boundary row scratch: width * slots elements (layout depends on logG, see swb_warp.cuh).
+struct SwbTile {
+    uint64_t res_off;     // byte offset into the packed residue buffer
+    uint64_t bnd_off;     // element offset into the boundary buffer
+    uint32_t first_pair;  // pair index (sorted order) of slot 0; sequences 2*pair, 2*pair+1
+    uint32_t width;       // columns (multiple of 4) = longest sequence of the tile rounded up
+    uint16_t npairs;      // occupied slots
+    uint8_t logG;         // log2 of lanes per pair
+    uint8_t reserved;
+};
+
+struct SwbScoreParams {
+    const SwbTile *tiles;
+    uint32_t ntiles;
+    const uint8_t *residues;
+    void *bnd;                // boundary scratch (uint32 per element for s16x2, 2x int32 for i32)
+    const int8_t *profile;    // global query profile [32][prof_stride], entry = S(q_row, code) + gap
+    uint32_t prof_stride;     // bytes per code row in global memory
+    uint32_t row0;            // first query row of this launch (query chunk)
+    uint32_t rows;            // query rows of this chunk that carry real residues or padding to use
+    uint32_t smem_rows;       // rows staged per code in shared memory (multiple of 128)
+    uint32_t first_chunk;     // 1: top boundary is zero
+    uint32_t last_chunk;      // 1: bottom boundary is not stored
+    int32_t *scores;          // per sequence, sorted order
+    uint32_t *counter;        // dynamic tile counter (zeroed before launch)
+    uint8_t *flags;           // per tile: s16 kernel sets 1 when a score may have wrapped
+    uint32_t only_flagged;    // i32 recompute: skip tiles whose flag is 0
+    uint32_t *recount;        // i32 recompute: number of tiles re-scored (may be null)
+    int32_t gap;
+    int32_t ovf_thr;          // s16: best > ovf_thr  =>  recompute in int32
+};
+
+SWB_HD uint32_t swb_roundup(uint32_t v, uint32_t m) { return (v + m - 1) / m * m; }

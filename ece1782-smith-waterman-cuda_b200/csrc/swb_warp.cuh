@@ -1,0 +1,373 @@
+// The warp program of the Smith-Waterman scan: one warp scores one tile (32/G pairs of DB sequences,
+// G lanes per pair) against the query rows staged in shared memory.
+//
+// Recurrence (reference: src/SWSolver.cu:246, src/cpu.cpp:45-72), linear gap g:
+//     H(i,j) = max(0, H(i-1,j-1) + S(q_i, d_j), H(i,j-1) - g, H(i-1,j) - g),   score = max H
+// restated so that the serial chain down a column is ONE fused op per cell:
+//     c(i,j) = max(0, [H(i-1,j-1)-g] + [S+g], [H(i,j-1)-g])      off the chain   (viaddmax.relu)
+//     H(i,j) = max(H(i-1,j) - g, c(i,j))                          on the chain    (viaddmax)
+//     store H(i,j)-g for the next column                          off the chain   (vadd)
+// With V16 both halves of a 32-bit word carry two different DB sequences (packed s16x2, DPX
+// instructions); with V32 the same program runs on two int32 lanes (exact recompute path).
+//
+// Work split: a lane keeps K consecutive query rows in registers ("strip") and walks along the DB
+// columns. G lanes of a group hold G consecutive strips and run a wavefront: lane g works on column
+// t-g at step t and hands its bottom H and the residue pair to lane g+1 by __shfl_up_sync. Rows beyond
+// K*G are covered by further passes ("super-strips"); the row between two passes goes through the
+// boundary scratch in global memory. G = 1 is the pure inter-task case (no shuffles), G = 32 the
+// intra-task warp wavefront for long sequences.
+//
+// The same source is compiled for the device (DevBackend, swb_kernels.cu) and, for CPU validation of
+// the indexing / wavefront logic, for the host with a thread-per-lane backend (tests/emu). The host
+// build is test infrastructure only and is never linked into libswb.so.
+#pragma once
+#include <cuda_runtime.h>
+#include "swb_types.h"
+
+// ---------------------------------------------------------------------------------------------
+// byte permute with sign replication (PTX prmt.b32 generic mode: selector nibble bit 3 = replicate
+// the sign of the selected byte)
+SWB_HD uint32_t swb_prmt(uint32_t a, uint32_t b, uint32_t sel)
+{
+#ifdef __CUDA_ARCH__
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+#else
+    uint64_t src = ((uint64_t)b << 32) | a;
+    uint32_t d = 0;
+    for (int i = 0; i < 4; ++i) {
+        uint32_t n = (sel >> (4 * i)) & 0xf;
+        uint32_t byte = (uint32_t)(src >> (8 * (n & 7))) & 0xff;
+        if (n & 8) byte = (byte & 0x80) ? 0xff : 0x00;
+        d |= byte << (8 * i);
+    }
+    return d;
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------
+// V16: two sequences per 32-bit word, signed 16-bit halves, DPX / video SIMD instructions.
+struct V16 {
+    typedef uint32_t T;
+    static const bool is16 = true;
+    static SWB_HD T zero() { return 0u; }
+    static SWB_HD T splat(int v) { uint32_t u = (uint32_t)v & 0xffffu; return u | (u << 16); }
+    static SWB_HD T add(T a, T b)
+    {
+#ifdef __CUDA_ARCH__
+        return __vadd2(a, b);
+#else
+        return ((a + b) & 0xffffu) | ((((a >> 16) + (b >> 16)) & 0xffffu) << 16);
+#endif
+    }
+    static SWB_HD T addmax(T a, T b, T c) { return __viaddmax_s16x2(a, b, c); }
+    static SWB_HD T addmax_relu(T a, T b, T c) { return __viaddmax_s16x2_relu(a, b, c); }
+    static SWB_HD T max2(T a, T b)
+    {
+#ifdef __CUDA_ARCH__
+        return __vmaxs2(a, b);
+#else
+        return __vimax3_s16x2(a, b, b);
+#endif
+    }
+    static SWB_HD T max3(T a, T b, T c) { return __vimax3_s16x2(a, b, c); }
+    // scores of profile byte i (0..3) of the A word and of the B word, sign-extended into one s16x2
+    template <int I> static SWB_HD T pair(uint32_t wa, uint32_t wb)
+    {
+        return swb_prmt(wa, wb, 0xC480u + 0x1111u * I);
+    }
+    static SWB_HD int lo(T v) { return (int)(int16_t)(v & 0xffffu); }
+    static SWB_HD int hi(T v) { return (int)(int16_t)(v >> 16); }
+    template <class BE> static SWB_HD T shfl_up(BE &be, T v, int d, int w) { return be.shfl_up(v, d, w); }
+    template <class BE> static SWB_HD T shfl_xor(BE &be, T v, int m, int w) { return be.shfl_xor(v, m, w); }
+    template <class BE> static SWB_HD T ld(BE &be, const T *p) { return be.ld_cg(p); }
+    template <class BE> static SWB_HD void st(BE &be, T *p, T v) { be.st_cg(p, v); }
+    template <class BE> static SWB_HD void ld4(BE &be, const T *p, T *o)
+    {
+        uint4 v = be.ld_cg4(reinterpret_cast<const uint4 *>(p));
+        o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+    }
+    template <class BE> static SWB_HD void st4(BE &be, T *p, const T *o)
+    {
+        be.st_cg4(reinterpret_cast<uint4 *>(p), make_uint4(o[0], o[1], o[2], o[3]));
+    }
+};
+
+// V32: the same two sequences on two int32 lanes (no wrap for any realistic input).
+struct V32 {
+    struct T { int a, b; };
+    static const bool is16 = false;
+    static SWB_HD T mk(int a, int b) { T t; t.a = a; t.b = b; return t; }
+    static SWB_HD T zero() { return mk(0, 0); }
+    static SWB_HD T splat(int v) { return mk(v, v); }
+    static SWB_HD int mx(int a, int b) { return a > b ? a : b; }
+    static SWB_HD T add(T a, T b) { return mk(a.a + b.a, a.b + b.b); }
+    static SWB_HD T addmax(T a, T b, T c) { return mk(mx(a.a + b.a, c.a), mx(a.b + b.b, c.b)); }
+    static SWB_HD T addmax_relu(T a, T b, T c)
+    {
+        return mk(mx(mx(a.a + b.a, c.a), 0), mx(mx(a.b + b.b, c.b), 0));
+    }
+    static SWB_HD T max2(T a, T b) { return mk(mx(a.a, b.a), mx(a.b, b.b)); }
+    static SWB_HD T max3(T a, T b, T c) { return max2(max2(a, b), c); }
+    template <int I> static SWB_HD T pair(uint32_t wa, uint32_t wb)
+    {
+        return mk((int)(int8_t)(wa >> (8 * I)), (int)(int8_t)(wb >> (8 * I)));
+    }
+    static SWB_HD int lo(T v) { return v.a; }
+    static SWB_HD int hi(T v) { return v.b; }
+    template <class BE> static SWB_HD T shfl_up(BE &be, T v, int d, int w)
+    {
+        return mk((int)be.shfl_up((uint32_t)v.a, d, w), (int)be.shfl_up((uint32_t)v.b, d, w));
+    }
+    template <class BE> static SWB_HD T shfl_xor(BE &be, T v, int m, int w)
+    {
+        return mk((int)be.shfl_xor((uint32_t)v.a, m, w), (int)be.shfl_xor((uint32_t)v.b, m, w));
+    }
+    template <class BE> static SWB_HD T ld(BE &be, const T *p)
+    {
+        uint2 v = be.ld_cg2(reinterpret_cast<const uint2 *>(p));
+        return mk((int)v.x, (int)v.y);
+    }
+    template <class BE> static SWB_HD void st(BE &be, T *p, T v)
+    {
+        be.st_cg2(reinterpret_cast<uint2 *>(p), make_uint2((uint32_t)v.a, (uint32_t)v.b));
+    }
+    template <class BE> static SWB_HD void ld4(BE &be, const T *p, T *o)
+    {
+        uint4 v = be.ld_cg4(reinterpret_cast<const uint4 *>(p));
+        uint4 w = be.ld_cg4(reinterpret_cast<const uint4 *>(p) + 1);
+        o[0] = mk((int)v.x, (int)v.y); o[1] = mk((int)v.z, (int)v.w);
+        o[2] = mk((int)w.x, (int)w.y); o[3] = mk((int)w.z, (int)w.w);
+    }
+    template <class BE> static SWB_HD void st4(BE &be, T *p, const T *o)
+    {
+        be.st_cg4(reinterpret_cast<uint4 *>(p), make_uint4(o[0].a, o[0].b, o[1].a, o[1].b));
+        be.st_cg4(reinterpret_cast<uint4 *>(p) + 1, make_uint4(o[2].a, o[2].b, o[3].a, o[3].b));
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// One DB column against the K query rows of this lane.
+//   up      H(top-1, j)            (plain)       from the lane above / boundary scratch / 0
+//   diag0g  H(top-1, j-1) - g      carried between columns
+//   leftg   H(k, j-1) - g          per row, updated in place
+//   prow    shared-memory profile, already offset to this lane's first row; code row stride sstride
+template <int K, class V>
+SWB_HD typename V::T swb_column(typename V::T up, typename V::T &diag0g, typename V::T (&leftg)[K],
+                                typename V::T &best, const typename V::T NEGG, uint32_t res,
+                                const int8_t *prow, uint32_t sstride)
+{
+    typedef typename V::T T;
+    const uint32_t *ra = reinterpret_cast<const uint32_t *>(prow + (res & 0xffu) * sstride);
+    const uint32_t *rb = reinterpret_cast<const uint32_t *>(prow + (res >> 8) * sstride);
+    T h = up;
+    T dg = diag0g;
+    diag0g = V::add(up, NEGG);
+#pragma unroll
+    for (int k4 = 0; k4 < K / 4; ++k4) {
+        const uint32_t wa = ra[k4];
+        const uint32_t wb = rb[k4];
+        T c0, c1, c2, c3;
+        {
+            const T s = V::template pair<0>(wa, wb);
+            c0 = V::addmax_relu(dg, s, leftg[4 * k4 + 0]);
+            dg = leftg[4 * k4 + 0];
+            h = V::addmax(h, NEGG, c0);
+            leftg[4 * k4 + 0] = V::add(h, NEGG);
+        }
+        {
+            const T s = V::template pair<1>(wa, wb);
+            c1 = V::addmax_relu(dg, s, leftg[4 * k4 + 1]);
+            dg = leftg[4 * k4 + 1];
+            h = V::addmax(h, NEGG, c1);
+            leftg[4 * k4 + 1] = V::add(h, NEGG);
+        }
+        best = V::max3(best, c0, c1);
+        {
+            const T s = V::template pair<2>(wa, wb);
+            c2 = V::addmax_relu(dg, s, leftg[4 * k4 + 2]);
+            dg = leftg[4 * k4 + 2];
+            h = V::addmax(h, NEGG, c2);
+            leftg[4 * k4 + 2] = V::add(h, NEGG);
+        }
+        {
+            const T s = V::template pair<3>(wa, wb);
+            c3 = V::addmax_relu(dg, s, leftg[4 * k4 + 3]);
+            dg = leftg[4 * k4 + 3];
+            h = V::addmax(h, NEGG, c3);
+            leftg[4 * k4 + 3] = V::add(h, NEGG);
+        }
+        best = V::max3(best, c2, c3);
+    }
+    return h;
+}
+
+// ---------------------------------------------------------------------------------------------
+// One tile, all query rows of the current chunk.
+// Boundary scratch layout (elements of V::T, base tile.bnd_off):
+//   G == 1 : [chunk c][lane][4 columns]   -> one 16/32-byte vector per lane and chunk
+//   G  > 1 : [column][slot]               -> scalar per step, touched by the first / last lane of a group
+template <int K, class V, bool GROUPED, class BE>
+SWB_HD void swb_run_tile(BE &be, const SwbScoreParams &p, const SwbTile &tile, uint32_t tile_idx,
+                         const int8_t *sprof, uint32_t sstride)
+{
+    typedef typename V::T T;
+    const int lane = be.lane();
+    const int logG = GROUPED ? (int)tile.logG : 0;
+    const int G = 1 << logG;
+    const int g = lane & (G - 1);
+    const int slot = lane >> logG;
+    const int P = 32 >> logG;
+    const uint32_t W = tile.width;
+    const uint32_t nchunks = W >> 2;
+    const bool lead = (g == 0);
+    const bool tail = (g == G - 1);
+    const uint32_t rows_per_super = (uint32_t)K << logG;
+    const uint32_t nsuper = (p.rows + rows_per_super - 1) / rows_per_super;
+    const uint32_t nsteps4 = GROUPED ? ((W + (uint32_t)G - 1u + 3u) >> 2) : nchunks;
+    const uint8_t *res = p.residues + tile.res_off + (size_t)slot * 8u;
+    const size_t res_stride = (size_t)P * 8u;
+    T *bnd = reinterpret_cast<T *>(p.bnd) + tile.bnd_off;
+    const T NEGG = V::splat(-p.gap);
+    const uint32_t PAD2 = (uint32_t)SWB_PAD | ((uint32_t)SWB_PAD << 8);
+    const uint32_t PAD4 = PAD2 | (PAD2 << 16);
+    T best = V::zero();
+
+    for (uint32_t ss = 0; ss < nsuper; ++ss) {
+        const int8_t *prow = sprof + (size_t)(((ss << logG) + (uint32_t)g) * (uint32_t)K);
+        const bool read_top = !(p.first_chunk && ss == 0);
+        const bool write_bot = !(p.last_chunk && ss + 1 == nsuper);
+        T leftg[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) leftg[k] = NEGG;
+        T diag0g = NEGG;
+        T hprev = V::zero();
+        uint32_t resprev = PAD2;
+
+        uint2 rc = make_uint2(PAD4, PAD4);
+        T bc[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) bc[u] = V::zero();
+        if (lead && nchunks > 0) {
+            rc = be.ld_res(reinterpret_cast<const uint2 *>(res));
+            if (read_top) {
+                if (!GROUPED) {
+                    V::ld4(be, bnd + (size_t)lane * 4u, bc);
+                } else {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) bc[u] = V::ld(be, bnd + (size_t)u * P + slot);
+                }
+            }
+        }
+        for (uint32_t c = 0; c < nsteps4; ++c) {
+            // prefetch the next chunk of residues and of the top boundary row
+            uint2 rn = make_uint2(PAD4, PAD4);
+            T bn[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) bn[u] = V::zero();
+            if (lead && c + 1 < nchunks) {
+                rn = be.ld_res(reinterpret_cast<const uint2 *>(res + (size_t)(c + 1) * res_stride));
+                if (read_top) {
+                    if (!GROUPED) {
+                        V::ld4(be, bnd + ((size_t)(c + 1) * 32u + lane) * 4u, bn);
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            bn[u] = V::ld(be, bnd + ((size_t)(c + 1) * 4u + u) * P + slot);
+                    }
+                }
+            }
+            T outb[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                uint32_t r = ((u < 2 ? rc.x : rc.y) >> (16 * (u & 1))) & 0xffffu;
+                T up = bc[u];
+                if (GROUPED) {
+                    const uint32_t r2 = be.shfl_up(resprev, 1, G);
+                    const T u2 = V::shfl_up(be, hprev, 1, G);
+                    if (!lead) { r = r2; up = u2; }
+                }
+                const T h = swb_column<K, V>(up, diag0g, leftg, best, NEGG, r, prow, sstride);
+                outb[u] = h;
+                hprev = h;
+                resprev = r;
+            }
+            if (write_bot) {
+                if (!GROUPED) {
+                    V::st4(be, bnd + ((size_t)c * 32u + lane) * 4u, outb);
+                } else if (tail) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int64_t col = (int64_t)c * 4 + u - (G - 1);
+                        if (col >= 0 && col < (int64_t)W) V::st(be, bnd + (size_t)col * P + slot, outb[u]);
+                    }
+                }
+            }
+            rc = rn;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) bc[u] = bn[u];
+        }
+        be.syncwarp();
+    }
+
+    if (GROUPED) {
+        for (int m = G >> 1; m >= 1; m >>= 1) best = V::max2(best, V::shfl_xor(be, best, m, G));
+    }
+    bool flagged = false;
+    if (lead && slot < (int)tile.npairs) {
+        const size_t s0 = 2u * ((size_t)tile.first_pair + (size_t)slot);
+        int a = V::lo(best), b = V::hi(best);
+        if (!p.first_chunk) {
+            const int pa = p.scores[s0], pb = p.scores[s0 + 1];
+            a = a > pa ? a : pa;
+            b = b > pb ? b : pb;
+        }
+        p.scores[s0] = a;
+        p.scores[s0 + 1] = b;
+        flagged = V::is16 && ((a > b ? a : b) > p.ovf_thr);
+    }
+    if (V::is16) {
+        if (be.any(flagged) && lane == 0) p.flags[tile_idx] = 1;
+    } else if (p.recount && p.last_chunk && lane == 0) {
+        be.count(p.recount);
+    }
+}
+
+// Per-warp loop over the dynamically scheduled tile list (tiles are sorted longest-first on the host).
+template <int K, class V, class BE>
+SWB_HD void swb_warp_loop(BE &be, const SwbScoreParams &p, const int8_t *sprof, uint32_t sstride)
+{
+    for (;;) {
+        const uint32_t ti = be.next_tile(p.counter);
+        if (ti >= p.ntiles) break;
+        if (p.only_flagged && !be.ld_flag(p.flags + ti)) continue;
+        const SwbTile tile = be.ld_tile(p.tiles + ti);
+        if (tile.logG == 0)
+            swb_run_tile<K, V, false>(be, p, tile, ti, sprof, sstride);
+        else
+            swb_run_tile<K, V, true>(be, p, tile, ti, sprof, sstride);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Packed residue word of a tile: 4 columns x (seqA, seqB) of one slot. raw = concatenated codes of
+// the whole DB; seq_off / seq_len are indexed by SORTED position. Shared by the device pack kernel
+// and the host emulation.
+SWB_HD uint64_t swb_pack_word(const SwbTile &t, uint32_t c, uint32_t slot, const uint8_t *raw,
+                              const uint64_t *seq_off, const uint32_t *seq_len, uint32_t nseq)
+{
+    uint64_t w = 0;
+    for (int half = 0; half < 2; ++half) {
+        const uint64_t s = 2ull * ((uint64_t)t.first_pair + slot) + half;
+        const bool live = slot < t.npairs && s < nseq;
+        const uint32_t len = live ? seq_len[s] : 0u;
+        const uint8_t *src = live ? raw + seq_off[s] : raw;
+        for (int u = 0; u < 4; ++u) {
+            const uint32_t col = c * 4u + u;
+            const uint32_t code = col < len ? (uint32_t)(src[col] & 31u) : (uint32_t)SWB_PAD;
+            w |= (uint64_t)code << (8 * (2 * u + half));
+        }
+    }
+    return w;
+}

@@ -1,0 +1,127 @@
+/*
+ * swb.h -- C ABI of the B200-native Smith-Waterman database-scan engine (libswb.so).
+ *
+ * Drop-in boundary for the hot path of MattAgostini/ECE1782-Smith-Waterman-CUDA:
+ *
+ *     void smith_waterman_cuda(FASTAQuery&, FASTADatabase&, std::vector<seqid_score>&)
+ *         reference: src/SWSolver.h:9, implemented in src/SWSolver.cu:266-404
+ *
+ * The reference does everything inside that one call (encode, pack, upload, launch, gather). Behind
+ * this ABI the same work is split into the pieces a binding needs:
+ *
+ *   reference step (file:line)                               entry point here
+ *   -------------------------------------------------------  ---------------------------------
+ *   residue encoding  convertStringToFloat  SWSolver.cu:91-120   swb_encode
+ *   blosum50[25][25] + GAP_PENALTY          SWSolver.cu:7,54-81  swb_scoring_matrix / swb_set_scoring*
+ *   (+3/-3 scheme of the CPU solver         cpu.cpp:6-8,57-59)   SWB_SCORING_IDENT3
+ *   host packing loop + managed upload      SWSolver.cu:301-359  swb_db_load   (once per database)
+ *   query upload to constQuery              SWSolver.cu:291-298  swb_search / swb_search_batch
+ *   f_scoreSequenceTiledCoalesced launches  SWSolver.cu:201-264, 346, 379      "
+ *   result gather                           SWSolver.cu:383-390  scores[] in database order
+ *
+ * Plain pointers and sizes only; all buffers are caller-owned host memory unless stated otherwise.
+ * Every function returns SWB_OK (0) or a negative error code; swb_last_error() gives the text.
+ * Scores are the exact int32 values of the recurrence (the reference stores `short`, SWSolver.cu:263).
+ * There is no CPU fallback: without a CUDA device swb_create fails.
+ *
+ * Residue codes: one byte per residue, 0..31. 0..23 = ARNDCQEGHILKMFPSTWYVBJZX, 24 = '*'/unknown,
+ * 25..30 free for other alphabets, 31 = padding (its matrix row and column are forced to zero).
+ */
+#ifndef SWB_H
+#define SWB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SWB_OK 0
+#define SWB_ERR_ARG (-1)    /* bad argument */
+#define SWB_ERR_CUDA (-2)   /* a CUDA call failed (text in swb_last_error) */
+#define SWB_ERR_STATE (-3)  /* call out of order (e.g. search before db_load) */
+#define SWB_ERR_NOMEM (-4)
+
+#define SWB_SCORING_BLOSUM50_REF 0 /* SWSolver.cu:54-81, gap 2 */
+#define SWB_SCORING_IDENT3 1       /* cpu.cpp:6-8, gap 2 */
+
+typedef struct swb_engine swb_engine;
+
+typedef struct swb_stats_t {
+    double device_ms;        /* CUDA-event time of the last search call: first kernel -> last result */
+    double load_ms;          /* wall time of the last swb_db_load */
+    uint64_t cells;          /* true cells (query length x shard residues) of the last search call */
+    uint64_t padded_cells;   /* cells actually computed, including row/column padding */
+    uint64_t db_residues;    /* residues of this shard */
+    uint64_t db_residues_total;
+    uint32_t db_sequences;   /* sequences of this shard */
+    uint32_t tiles;          /* warp tiles of this shard */
+    uint32_t tiles_by_group[6]; /* tiles with 1,2,4,8,16,32 lanes per sequence pair */
+    uint32_t recomputed_tiles;  /* tiles re-scored in int32 during the last search call */
+    uint32_t kernel_launches;   /* kernels launched by the last search call */
+    uint32_t last_k;            /* query rows per lane used by the last score kernel */
+    uint32_t sm_count;
+    uint32_t reserved;
+} swb_stats_t;
+
+/* ---- engine ------------------------------------------------------------------------------ */
+int swb_create(swb_engine **out, int device);
+void swb_destroy(swb_engine *e);
+/* e == NULL: error text of the last failed swb_create of this thread */
+const char *swb_last_error(const swb_engine *e);
+/* options: "group_len" (longest sequence handled by one lane per pair, default 384; set before db_load),
+ *          "k" (query rows per lane: 0 = auto, 8, 16, 32), "streams" (concurrent queries of a batch, 1..4),
+ *          "chunk_rows" (query rows per launch for queries beyond shared memory; multiple of 1024, <= 7168) */
+int swb_set_option(swb_engine *e, const char *key, int64_t value);
+/* run on the caller's CUDA stream (cudaStream_t as void*); NULL = the engine's own stream */
+int swb_set_stream(swb_engine *e, void *cuda_stream);
+
+/* ---- scoring (replaces blosum50 / GAP_PENALTY / convertStringToFloat) ---------------------- */
+/* matrix: alpha x alpha int8, row-major, alpha <= 32; S + gap must fit int8; gap >= 0 (linear gap) */
+int swb_set_scoring(swb_engine *e, const int8_t *matrix, int alpha, int gap);
+int swb_set_scoring_preset(swb_engine *e, int preset);
+/* host helpers, usable without a GPU: the 32 x 32 preset matrix and the preset's char -> code map */
+int swb_scoring_matrix(int preset, int8_t *matrix32x32, int *gap);
+int swb_encode(int preset, const char *text, size_t n, uint8_t *codes);
+
+/* ---- database (replaces the packing loop, SWSolver.cu:301-359) ----------------------------- */
+/* codes: concatenated residue codes; offsets: n+1 entries (64-bit, cf. FASTAParsers.h:69-71 overflow).
+ * shard / nshards: this engine keeps the shard-th of nshards residue-balanced parts (0,1 = everything).
+ * The packed database stays resident on the GPU until the next swb_db_load or swb_destroy. */
+int swb_db_load(swb_engine *e, const uint8_t *codes, const uint64_t *offsets, uint32_t n, uint32_t shard,
+                uint32_t nshards);
+uint32_t swb_db_count(const swb_engine *e);      /* sequences of this shard */
+int swb_db_ids(const swb_engine *e, uint32_t *ids); /* their database ids, ascending = order of scores[] */
+
+/* ---- search (replaces the kernel launches + gather, SWSolver.cu:346-390) ------------------- */
+/* scores: swb_db_count() entries, scores[k] belongs to database id ids[k] (id k when nshards == 1) */
+int swb_search(swb_engine *e, const uint8_t *query, uint32_t qlen, int32_t *scores);
+/* nq queries, concatenated codes + nq+1 offsets; scores: nq x swb_db_count(), or NULL to leave the
+ * results on the device (read them later with swb_fetch_scores) */
+int swb_search_batch(swb_engine *e, const uint8_t *qcodes, const uint64_t *qoffsets, uint32_t nq, int32_t *scores);
+int swb_fetch_scores(swb_engine *e, uint32_t query_index, int32_t *scores);
+/* k best (score desc, id asc) of one score vector of this shard; ids are database ids */
+int swb_topk(const swb_engine *e, const int32_t *scores, uint32_t k, uint32_t *ids, int32_t *top);
+int swb_stats(const swb_engine *e, swb_stats_t *out);
+
+/* ---- plan introspection, CPU only (host logic of swb_db_load) ------------------------------ */
+typedef struct swb_plan_info_t {
+    uint32_t n_total, n_local, tiles, max_len;
+    uint64_t residues_local, residues_total, res_bytes, bnd_elems, padded_cols;
+    uint32_t tiles_by_group[6];
+} swb_plan_info_t;
+/* sorted_ids / shard_ids may be NULL; otherwise n_local entries each (query n_local with NULLs first) */
+int swb_plan_describe(const uint64_t *offsets, uint32_t n, uint32_t shard, uint32_t nshards, uint32_t group_len,
+                      swb_plan_info_t *info, uint32_t *sorted_ids, uint32_t *shard_ids);
+
+/* ---- measurement support (not on the scoring path) ------------------------------------------- */
+/* Issue rate of the integer SIMD instructions the score kernel is built from, whole GPU, in giga
+ * lane-instructions/s. kind: 0 viaddmax.s16x2.relu, 1 vimax3.s16x2, 2 vadd2, 3 prmt, 4 the score kernel's
+ * per-cell mix, 5 viaddmax+imad, 6 imad, 7 scalar add+max. bench.py uses kind 4 as the roofline peak. */
+int swb_microbench(int device, int kind, double *glane_instr_per_s, double *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SWB_H */

@@ -1,0 +1,262 @@
+// TEST INFRASTRUCTURE (never linked into libswb.so): runs the SAME warp program the GPU runs
+// (csrc/swb_warp.cuh: swb_warp_loop / swb_run_tile / swb_column / swb_pack_word) on the CPU, one fiber
+// per lane, warp shuffles emulated by a lock-step exchange. It exists so that the indexing, wavefront,
+// boundary-scratch, chunking and overflow-recompute logic can be checked against the oracle in the
+// build container, which has no GPU. DPX intrinsics use the host implementations CUDA ships.
+#include <stdint.h>
+#include <string.h>
+#include <ucontext.h>
+#include <algorithm>
+#include <vector>
+
+#include "swb_plan.h"
+#include "swb_warp.cuh"
+
+namespace {
+
+struct WarpSim;
+
+struct HostBackend {
+    WarpSim *w;
+    int lane_id;
+    int lane() const { return lane_id; }
+    uint32_t shfl_up(uint32_t v, int d, int width);
+    uint32_t shfl_xor(uint32_t v, int m, int width);
+    void syncwarp();
+    bool any(bool f);
+    uint32_t next_tile(uint32_t *counter);
+    void count(uint32_t *p) { (*p)++; }
+    uint8_t ld_flag(const uint8_t *p) const { return *p; }
+    SwbTile ld_tile(const SwbTile *p) const { return *p; }
+    uint2 ld_res(const uint2 *p) const { return *p; }
+    uint32_t ld_cg(const uint32_t *p) const { return *p; }
+    uint2 ld_cg2(const uint2 *p) const { return *p; }
+    uint4 ld_cg4(const uint4 *p) const { return *p; }
+    void st_cg(uint32_t *p, uint32_t v) const { *p = v; }
+    void st_cg2(uint2 *p, uint2 v) const { *p = v; }
+    void st_cg4(uint4 *p, uint4 v) const { *p = v; }
+};
+
+typedef void (*LaneFn)(HostBackend &, void *);
+
+struct WarpSim {
+    ucontext_t sched;
+    ucontext_t ctx[32];
+    std::vector<char> stacks[32];
+    bool done[32];
+    int current;
+    uint32_t xchg[32];
+    uint32_t snap[32];
+    int arrived;
+    uint32_t gen;
+    LaneFn fn;
+    void *arg;
+
+    void yield() { swapcontext(&ctx[current], &sched); }
+    // all 32 lanes deposit, then all continue (lock-step point of a *_sync intrinsic)
+    void rendezvous(int lane, uint32_t v)
+    {
+        xchg[lane] = v;
+        const uint32_t my = gen;
+        if (++arrived == 32) {
+            arrived = 0;
+            memcpy(snap, xchg, sizeof snap);
+            ++gen;
+        }
+        while (gen == my) yield();
+    }
+    static void trampoline(unsigned lo, unsigned hi)
+    {
+        WarpSim *w = reinterpret_cast<WarpSim *>(((uintptr_t)hi << 32) | (uintptr_t)lo);
+        HostBackend be;
+        be.w = w;
+        be.lane_id = w->current;
+        w->fn(be, w->arg);
+        w->done[be.lane_id] = true;
+        swapcontext(&w->ctx[be.lane_id], &w->sched);
+    }
+    void run(LaneFn f, void *a)
+    {
+        fn = f;
+        arg = a;
+        arrived = 0;
+        gen = 0;
+        for (int l = 0; l < 32; ++l) {
+            stacks[l].resize(512 * 1024);
+            done[l] = false;
+            getcontext(&ctx[l]);
+            ctx[l].uc_stack.ss_sp = stacks[l].data();
+            ctx[l].uc_stack.ss_size = stacks[l].size();
+            ctx[l].uc_link = &sched;
+            const uintptr_t p = (uintptr_t)this;
+            makecontext(&ctx[l], (void (*)())trampoline, 2, (unsigned)(p & 0xffffffffu), (unsigned)(p >> 32));
+        }
+        for (;;) {
+            bool alive = false;
+            for (int l = 0; l < 32; ++l) {
+                if (done[l]) continue;
+                alive = true;
+                current = l;
+                swapcontext(&sched, &ctx[l]);
+            }
+            if (!alive) break;
+        }
+    }
+};
+
+uint32_t HostBackend::shfl_up(uint32_t v, int d, int width)
+{
+    w->rendezvous(lane_id, v);
+    const uint32_t r = (lane_id % width) >= d ? w->snap[lane_id - d] : v;
+    w->rendezvous(lane_id, 0);
+    return r;
+}
+uint32_t HostBackend::shfl_xor(uint32_t v, int m, int width)
+{
+    w->rendezvous(lane_id, v);
+    const int src = lane_id ^ m;
+    const uint32_t r = (src / width == lane_id / width) ? w->snap[src] : v;
+    w->rendezvous(lane_id, 0);
+    return r;
+}
+void HostBackend::syncwarp() { w->rendezvous(lane_id, 0); }
+bool HostBackend::any(bool f)
+{
+    w->rendezvous(lane_id, f ? 1u : 0u);
+    bool r = false;
+    for (int l = 0; l < 32; ++l) r = r || w->snap[l];
+    w->rendezvous(lane_id, 0);
+    return r;
+}
+uint32_t HostBackend::next_tile(uint32_t *counter)
+{
+    uint32_t v = 0;
+    if (lane_id == 0) v = (*counter)++;
+    w->rendezvous(lane_id, v);
+    const uint32_t r = w->snap[0];
+    w->rendezvous(lane_id, 0);
+    return r;
+}
+
+struct LaneArgs {
+    const SwbScoreParams *p;
+    const int8_t *sprof;
+    uint32_t sstride;
+    int K;
+    bool i32;
+};
+
+void lane_main(HostBackend &be, void *a)
+{
+    const LaneArgs *la = static_cast<const LaneArgs *>(a);
+    if (!la->i32) {
+        if (la->K == 8) swb_warp_loop<8, V16>(be, *la->p, la->sprof, la->sstride);
+        else if (la->K == 16) swb_warp_loop<16, V16>(be, *la->p, la->sprof, la->sstride);
+        else swb_warp_loop<32, V16>(be, *la->p, la->sprof, la->sstride);
+    } else {
+        if (la->K == 8) swb_warp_loop<8, V32>(be, *la->p, la->sprof, la->sstride);
+        else swb_warp_loop<16, V32>(be, *la->p, la->sprof, la->sstride);
+    }
+}
+
+}  // namespace
+
+// Mirrors swb_db_load + one swb_search of the engine (same plan, same chunking, same kernel
+// parameters), with the kernels replaced by the fiber emulation. force_i32: 0 = s16 pass then int32
+// recompute of flagged tiles (the product flow), 1 = int32 pass over every tile.
+// ovf_thr_override >= 0 replaces the s16 overflow threshold (lets tests force the recompute path).
+extern "C" int swbemu_search(const uint8_t *codes, const uint64_t *offsets, uint32_t n, uint32_t shard,
+                             uint32_t nshards, uint32_t group_len, const int8_t *mat32, int gap, const uint8_t *q,
+                             uint32_t qlen, int K, int force_i32, uint32_t chunk_rows, int ovf_thr_override,
+                             int32_t *scores_out, uint32_t *recomputed_tiles)
+{
+    SwbPlanOpts o;
+    if (group_len) o.group_len = group_len;
+    SwbPlan pl;
+    if (swb_build_plan(offsets, n, shard, nshards ? nshards : 1, o, pl) != 0) return -1;
+    const uint32_t nl = pl.n_local;
+    if (recomputed_tiles) *recomputed_tiles = 0;
+    if (nl == 0) return 0;
+    if (qlen == 0 || pl.tiles.empty() || pl.max_len == 0) {
+        memset(scores_out, 0, sizeof(int32_t) * nl);
+        return 0;
+    }
+    int max_logg = 0;
+    for (int l = 0; l <= SWB_MAX_LOGG; ++l)
+        if (pl.tiles_by_logg[l]) max_logg = l;
+    const uint8_t *raw = codes;
+    // pack (same function as the device pack kernel)
+    std::vector<uint64_t> residues(pl.res_bytes / 8 + 1);
+    for (size_t ti = 0; ti < pl.tiles.size(); ++ti) {
+        const SwbTile &t = pl.tiles[ti];
+        const uint32_t P = 32u >> t.logG;
+        uint64_t *out = residues.data() + t.res_off / 8;
+        for (uint32_t i = 0; i < (t.width >> 2) * P; ++i)
+            out[i] = swb_pack_word(t, i / P, i % P, raw, pl.seq_off.data(), pl.seq_len.data(), nl);
+    }
+    int max_s = 0;
+    for (int i = 0; i < SWB_ALPHA * SWB_ALPHA; ++i) max_s = std::max<int>(max_s, mat32[i]);
+    if (!chunk_rows) chunk_rows = 7168;
+    SwbQueryPlan qp[2];
+    swb_plan_query(qlen, K, max_logg, chunk_rows, qp[0]);
+    swb_plan_query(qlen, std::min(K, 16), max_logg, chunk_rows, qp[1]);
+    const uint32_t prof_rows = std::max(qp[0].prof_rows, qp[1].prof_rows);
+    const uint32_t prof_stride = swb_roundup(prof_rows, 16);
+    std::vector<int8_t> prof((size_t)prof_stride * SWB_ALPHA);
+    for (uint32_t r = 0; r < prof_rows; ++r) {
+        const uint32_t qc = r < qlen ? (q[r] & 31u) : (uint32_t)SWB_PAD;
+        for (uint32_t code = 0; code < SWB_ALPHA; ++code)
+            prof[(size_t)code * prof_stride + r] = (int8_t)(mat32[qc * SWB_ALPHA + code] + gap);
+    }
+    std::vector<int32_t> sorted(2 * (size_t)((nl + 1) / 2), 0);
+    std::vector<uint8_t> flags(pl.tiles.size(), 0);
+    std::vector<uint32_t> bnd16(pl.bnd_elems + 4);
+    std::vector<uint64_t> bnd32(pl.bnd_elems + 4);
+    uint32_t recount = 0;
+
+    SwbScoreParams p;
+    memset(&p, 0, sizeof p);
+    p.tiles = pl.tiles.data();
+    p.ntiles = (uint32_t)pl.tiles.size();
+    p.residues = reinterpret_cast<const uint8_t *>(residues.data());
+    p.profile = prof.data();
+    p.prof_stride = prof_stride;
+    p.scores = sorted.data();
+    p.flags = flags.data();
+    p.recount = &recount;
+    p.gap = gap;
+    p.ovf_thr = ovf_thr_override >= 0 ? ovf_thr_override : 32767 - max_s;
+    for (int pass = force_i32 ? 1 : 0; pass < 2; ++pass) {
+        const bool i32 = pass == 1;
+        p.bnd = i32 ? (void *)bnd32.data() : (void *)bnd16.data();
+        p.only_flagged = (i32 && !force_i32) ? 1u : 0u;
+        for (size_t c = 0; c < qp[pass].chunks.size(); ++c) {
+            const SwbQueryChunk &ch = qp[pass].chunks[c];
+            p.row0 = ch.row0;
+            p.rows = ch.rows;
+            p.smem_rows = ch.smem_rows;
+            p.first_chunk = ch.first;
+            p.last_chunk = ch.last;
+            uint32_t counter = 0;
+            p.counter = &counter;
+            // stage the chunk's profile exactly like swb_score_kernel
+            const uint32_t sstride = ch.smem_rows + 4;
+            std::vector<int8_t> sprof((size_t)sstride * SWB_ALPHA + 16);
+            for (uint32_t code = 0; code < SWB_ALPHA; ++code)
+                memcpy(sprof.data() + (size_t)code * sstride, prof.data() + (size_t)code * prof_stride + ch.row0,
+                       ch.smem_rows);
+            LaneArgs la;
+            la.p = &p;
+            la.sprof = sprof.data();
+            la.sstride = sstride;
+            la.K = qp[pass].K;
+            la.i32 = i32;
+            WarpSim *w = new WarpSim();
+            w->run(lane_main, &la);
+            delete w;
+        }
+    }
+    for (uint32_t s = 0; s < nl; ++s) scores_out[pl.out_pos[s]] = sorted[s];
+    if (recomputed_tiles) *recomputed_tiles = recount;
+    return 0;
+}

@@ -1,0 +1,206 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the golden vectors and the CPU oracle.
+Bit-exact integer scores are the bar everywhere."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT, random_db
+from oracle_lib import pack_db
+
+pytestmark = pytest.mark.gpu
+
+
+def _gold(name):
+    return np.array([int(x) for x in open(os.path.join(GOLDEN, name + ".head111.txt")).read().split()], dtype=np.int32)
+
+
+def test_config1_golden_heads(engine, swb, subset, queries):
+    """reference goldens (test/swissprot_tests.cpp:68-72), lines 1-111, both pinned queries"""
+    engine.set_scoring_preset(swb.SWB_SCORING_BLOSUM50_REF)
+    engine.db_load(subset["codes"], subset["offsets"])
+    for name in ("P01008", "P02232"):
+        got = engine.search(swb.encode(queries[name]))
+        assert np.array_equal(got, _gold(name)), name
+
+
+def test_config1_all_queries_vs_oracle_and_survey(engine, swb, oracle, subset, queries, survey_exp):
+    engine.set_scoring_preset(swb.SWB_SCORING_BLOSUM50_REF)
+    engine.db_load(subset["codes"], subset["offsets"])
+    m = oracle.matrix("blosum50")
+    names = sorted(queries)
+    batch = engine.search_batch([swb.encode(queries[n]) for n in names])
+    for i, name in enumerate(names):
+        want = oracle.scan(oracle.encode(queries[name]), subset["codes"], subset["offsets"], m)
+        assert np.array_equal(batch[i], want), name
+        assert np.array_equal(batch[i], np.array(survey_exp[name], dtype=np.int32)), name
+        single = engine.search(swb.encode(queries[name]))
+        assert np.array_equal(single, want), name
+
+
+def test_self_scores(engine, swb, queries):
+    """golden maxima: P01008 x itself = 3037, P02232 x itself = 910"""
+    engine.set_scoring_preset(swb.SWB_SCORING_BLOSUM50_REF)
+    for name, want in (("P01008", 3037), ("P02232", 910)):
+        q = swb.encode(queries[name])
+        codes, offs = swb.pack_sequences([q])
+        engine.db_load(codes, offs)
+        assert engine.search(q)[0] == want
+
+
+def test_ident3_matches_compiled_cpu_cpp(engine, swb, subset, queries):
+    """+3/-3 scheme against the scores the compiled reference cpu.cpp printed (tests/golden/cpu_ref_ident3.json)"""
+    import json
+    ref = json.load(open(os.path.join(GOLDEN, "cpu_ref_ident3.json")))
+    engine.set_scoring_preset(swb.SWB_SCORING_IDENT3)
+    codes, offs = swb.pack_sequences([swb.encode(s, swb.SWB_SCORING_IDENT3) for s in subset["seqs"]])
+    engine.db_load(codes, offs)
+    for name, want in ref["scans"].items():
+        got = engine.search(swb.encode(queries[name], swb.SWB_SCORING_IDENT3))
+        assert np.array_equal(got, np.array(want, dtype=np.int32)), name
+    for p in ref["pairs"]:
+        c, o = swb.pack_sequences([swb.encode(p["b"], swb.SWB_SCORING_IDENT3)])
+        engine.db_load(c, o)
+        assert engine.search(swb.encode(p["a"], swb.SWB_SCORING_IDENT3))[0] == p["score"]
+    engine.set_scoring_preset(swb.SWB_SCORING_BLOSUM50_REF)
+
+
+@pytest.mark.parametrize("k", [0, 8, 16, 32])
+@pytest.mark.parametrize("group_len", [16, 96, 384, 100000])
+def test_random_db_all_kernel_shapes(swb, oracle, k, group_len):
+    """every K and lane-group mix (group_len 16 forces 32-lane wavefronts, 100000 forces one lane per pair)"""
+    rng = np.random.default_rng(1000 + k + group_len)
+    lens = np.concatenate([rng.integers(0, 40, 70), rng.integers(40, 700, 300), rng.integers(700, 3000, 9), [0, 1, 2, 3]])
+    rng.shuffle(lens)
+    enc = random_db(rng, lens)
+    codes, offs = pack_db(enc)
+    m = oracle.matrix("blosum50")
+    e = swb.Engine(0, group_len=group_len, k=k)
+    try:
+        e.db_load(codes, offs)
+        for ql in (1, 7, 33, 144, 257, 1000):
+            q = rng.integers(0, 24, ql).astype(np.uint8)
+            assert np.array_equal(e.search(q), oracle.scan(q, codes, offs, m)), (k, group_len, ql)
+    finally:
+        e.close()
+
+
+def test_long_query_chunked_and_int32_recompute(swb, oracle):
+    """query longer than one shared-memory chunk + scores far above 32767 (self hits of W-rich sequences)"""
+    rng = np.random.default_rng(77)
+    m = oracle.matrix("blosum50")
+    long_q = rng.integers(0, 20, 9000).astype(np.uint8)
+    wq = np.full(2600, 17, dtype=np.uint8)  # 'W' x 2600: self score 15 * 2600 = 39000
+    enc = random_db(rng, rng.integers(20, 900, 150)) + [long_q.copy(), wq.copy(), long_q[:5000].copy(), wq[:2300].copy()]
+    codes, offs = pack_db(enc)
+    e = swb.Engine(0)
+    try:
+        e.db_load(codes, offs)
+        for q in (long_q, wq):
+            got = e.search(q)
+            want = oracle.scan(q, codes, offs, m)
+            assert np.array_equal(got, want)
+            assert got.max() > 32767
+            assert e.stats()["recomputed_tiles"] >= 1
+        e.set_option("chunk_rows", 1024)
+        for k in (8, 16, 32):
+            e.set_option("k", k)
+            assert np.array_equal(e.search(long_q[:4100]), oracle.scan(long_q[:4100], codes, offs, m)), k
+    finally:
+        e.close()
+
+
+def test_edge_cases(swb, oracle):
+    m = oracle.matrix("blosum50")
+    e = swb.Engine(0)
+    try:
+        q = swb.encode("MKVLAAGIW")
+        # empty database, database of empty sequences, empty query, one residue
+        c, o = pack_db([])
+        e.db_load(c, o)
+        assert e.db_count() == 0 and len(e.search(q)) == 0
+        c, o = pack_db([np.zeros(0, np.uint8)] * 5)
+        e.db_load(c, o)
+        assert np.array_equal(e.search(q), np.zeros(5, np.int32))
+        c, o = pack_db([swb.encode("W"), swb.encode("MKVLAAGIW"), np.zeros(0, np.uint8)])
+        e.db_load(c, o)
+        assert np.array_equal(e.search(np.zeros(0, np.uint8)), np.zeros(3, np.int32))
+        assert np.array_equal(e.search(q), oracle.scan(q, c, o, m))
+        assert np.array_equal(e.search(swb.encode("W")), np.array([15, 15, 0], np.int32))
+        # unknown characters behave like '*' (score 0) and padding is neutral (FASTAParsers.h:94-96)
+        a = e.search(swb.encode("MKVLAAGIW////"))
+        assert np.array_equal(a, e.search(q))
+    finally:
+        e.close()
+
+
+def test_batch_equals_single_and_resident_fetch(engine, swb, oracle, subset, queries):
+    engine.set_scoring_preset(swb.SWB_SCORING_BLOSUM50_REF)
+    engine.db_load(subset["codes"], subset["offsets"])
+    names = ["P02232", "Q9UKN1", "P01008", "P27895", "P05013"]
+    qs = [swb.encode(queries[n]) for n in names]
+    batch = engine.search_batch(qs)
+    assert engine.search_batch(qs, fetch=False) is None
+    st = engine.stats()
+    assert st["kernel_launches"] >= 3 * len(qs) and st["device_ms"] > 0
+    for i in range(len(qs)):
+        assert np.array_equal(engine.fetch_scores(i), batch[i])
+    for i, q in enumerate(qs):
+        assert np.array_equal(engine.search(q), batch[i])
+
+
+def test_shards_partition_and_agree(swb, oracle):
+    """config 3 on one GPU: 1, 2, 4, 8 shards must reproduce the unsharded score vector exactly"""
+    rng = np.random.default_rng(3)
+    enc = random_db(rng, np.clip(np.round(rng.lognormal(5.0, 0.8, 700)), 2, 4000))
+    codes, offs = pack_db(enc)
+    q = rng.integers(0, 20, 300).astype(np.uint8)
+    want = oracle.scan(q, codes, offs, oracle.matrix("blosum50"))
+    e = swb.Engine(0)
+    try:
+        for nshards in (1, 2, 4, 8):
+            merged = np.full(len(enc), -1, np.int32)
+            res = []
+            for s in range(nshards):
+                e.db_load(codes, offs, s, nshards)
+                ids = e.db_ids()
+                merged[ids] = e.search(q)
+                res.append(e.stats()["db_residues"])
+            assert np.array_equal(merged, want), nshards
+            assert max(res) - min(res) <= 2 * 4000
+        ids, top = e.topk(e.search(q), 5)
+    finally:
+        e.close()
+
+
+def test_dropin_result_order(swb, oracle, subset, queries, tmp_path):
+    """smith_waterman_cuda mirror: (id, score) pairs in descending padded length, file order inside a bucket
+    (SWSolver.cu:383-390); first ids 56, 34, 13 per SURVEY appendix A"""
+    db = swb.FASTADatabase(os.path.join(GOLDEN, "uniprot_subset.fasta"))
+    query = swb.FASTAQuery(os.path.join(GOLDEN, "queries", "P01008.fasta"))
+    result = []
+    swb.smith_waterman_cuda(query, db, result)
+    assert [r[0] for r in result[:3]] == [56, 34, 13]
+    gold = _gold("P01008")
+    assert len(result) == 111
+    for sid, score in result:
+        assert score == gold[sid]
+
+
+def test_reference_cuda_binary_agrees(swb, subset, queries, tmp_path):
+    """the reference's own SWSolver.cu, compiled unmodified for sm_100a (oracle/_ref/ref_cuda_scan), on the same
+    query/database files: identical id:score lines (queries within its 1024-row limit only, SWSolver.cu:85)"""
+    binary = os.path.join(ROOT, "oracle", "_ref", "ref_cuda_scan")
+    if not os.path.exists(binary):
+        pytest.skip("oracle/_ref/ref_cuda_scan not built")
+    dbpath = os.path.join(GOLDEN, "uniprot_subset.fasta")
+    db = swb.FASTADatabase(dbpath)
+    for name in ("P02232", "P01008", "P27895"):
+        qpath = os.path.join(GOLDEN, "queries", name + ".fasta")
+        out = subprocess.run([binary, qpath, dbpath], capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr
+        ref_lines = [l for l in out.stdout.split("\n") if l and not l.startswith("#")]
+        result = []
+        swb.smith_waterman_cuda(swb.FASTAQuery(qpath), db, result)
+        assert ref_lines == ["%d:%d" % r for r in result], name

@@ -2,6 +2,7 @@
 // scratch and the launch logic. One engine = one GPU (one process per GPU under torchrun).
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <sys/time.h>
 #include <algorithm>
@@ -37,14 +38,17 @@ struct Slot {
     int8_t *d_prof = nullptr;
     size_t prof_cap = 0;
     uint8_t *d_state = nullptr;  // [counters | flags | sorted scores], zeroed per query
-    size_t state_bytes = 0;
+    size_t state_bytes = 0, state_cap = 0;
     uint32_t *d_counters = nullptr;
     uint32_t *d_recount = nullptr;  // tiles re-scored in int32, zeroed per batch
     uint8_t *d_flags = nullptr;
     int32_t *d_sorted = nullptr;
     uint32_t *d_bnd16 = nullptr;
+    size_t bnd16_cap = 0;
     void *d_bnd32 = nullptr;
+    size_t bnd32_cap = 0;
     int32_t *h_scores = nullptr;  // pinned, n_local
+    size_t h_scores_cap = 0;
     int32_t *pending_dst = nullptr;
 };
 
@@ -75,8 +79,15 @@ struct swb_engine {
     SwbTile *d_tiles = nullptr;
     uint8_t *d_residues = nullptr;
     uint32_t *d_out_pos = nullptr;
+    uint8_t *d_raw = nullptr;       // raw concatenated codes (input of the pack kernel)
+    uint64_t *d_seq_off = nullptr;
+    uint32_t *d_seq_len = nullptr;
+    size_t tiles_cap = 0, residues_cap = 0, out_pos_cap = 0, raw_cap = 0, seq_off_cap = 0, seq_len_cap = 0;
+    uint8_t *h_stage[2] = {nullptr, nullptr};  // pinned staging for the raw upload
+    size_t stage_cap[2] = {0, 0};
+    cudaEvent_t ev_stage[2] = {nullptr, nullptr};
     int32_t *d_out = nullptr;
-    size_t out_cap = 0;  // in score vectors
+    size_t out_cap = 0;  // bytes
     uint32_t last_nq = 0;
     Slot slots[SWB_MAX_SLOTS];
     uint32_t *h_recount = nullptr;  // pinned, SWB_MAX_SLOTS
@@ -112,20 +123,30 @@ static void free_slot_db(Slot &s)
     s.d_bnd16 = nullptr;
     s.d_bnd32 = nullptr;
     s.h_scores = nullptr;
-    s.state_bytes = 0;
+    s.state_bytes = s.state_cap = s.bnd16_cap = s.bnd32_cap = s.h_scores_cap = 0;
 }
 
 static void free_db(swb_engine *e)
 {
-    if (e->d_tiles) cudaFree(e->d_tiles);
-    if (e->d_residues) cudaFree(e->d_residues);
-    if (e->d_out_pos) cudaFree(e->d_out_pos);
-    if (e->d_out) cudaFree(e->d_out);
+    void *dev[] = {e->d_tiles, e->d_residues, e->d_out_pos, e->d_out, e->d_raw, e->d_seq_off, e->d_seq_len};
+    for (void *p : dev)
+        if (p) cudaFree(p);
     e->d_tiles = nullptr;
     e->d_residues = nullptr;
     e->d_out_pos = nullptr;
     e->d_out = nullptr;
+    e->d_raw = nullptr;
+    e->d_seq_off = nullptr;
+    e->d_seq_len = nullptr;
+    e->tiles_cap = e->residues_cap = e->out_pos_cap = e->raw_cap = e->seq_off_cap = e->seq_len_cap = 0;
     e->out_cap = 0;
+    for (int i = 0; i < 2; ++i) {
+        if (e->h_stage[i]) cudaFreeHost(e->h_stage[i]);
+        if (e->ev_stage[i]) cudaEventDestroy(e->ev_stage[i]);
+        e->h_stage[i] = nullptr;
+        e->ev_stage[i] = nullptr;
+        e->stage_cap[i] = 0;
+    }
     for (int i = 0; i < SWB_MAX_SLOTS; ++i) free_slot_db(e->slots[i]);
     e->db_loaded = false;
 }
@@ -282,107 +303,113 @@ extern "C" int swb_set_scoring_preset(swb_engine *e, int preset)
 }
 
 // ---------------------------------------------------------------------------------------------
+// grow-only device / pinned buffers: a reload of a database of similar size reuses every allocation
+static cudaError_t grow_dev(void **p, size_t *cap, size_t need)
+{
+    if (need <= *cap && *p) return cudaSuccess;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+    need = std::max<size_t>(need + need / 16, 256);
+    cudaError_t e = cudaMalloc(p, need);
+    if (e == cudaSuccess) *cap = need;
+    return e;
+}
+static cudaError_t grow_host(void **p, size_t *cap, size_t need)
+{
+    if (need <= *cap && *p) return cudaSuccess;
+    if (*p) cudaFreeHost(*p);
+    *p = nullptr;
+    *cap = 0;
+    need = std::max<size_t>(need + need / 16, 256);
+    cudaError_t e = cudaMallocHost(p, need);
+    if (e == cudaSuccess) *cap = need;
+    return e;
+}
+#define GROW_DEV(ptr, cap, need) grow_dev(reinterpret_cast<void **>(&(ptr)), &(cap), (need))
+#define GROW_HOST(ptr, cap, need) grow_host(reinterpret_cast<void **>(&(ptr)), &(cap), (need))
+
 extern "C" int swb_db_load(swb_engine *e, const uint8_t *codes, const uint64_t *offsets, uint32_t n, uint32_t shard,
                            uint32_t nshards)
 {
     if (!e || !offsets || (!codes && n && offsets[n] != offsets[0])) return SWB_ERR_ARG;
     if (nshards == 0) nshards = 1;
     if (shard >= nshards) return fail(e, SWB_ERR_ARG, "shard >= nshards");
+    const bool timing = getenv("SWB_TIMING") != nullptr;
     const double t0 = wall_ms();
     CU(cudaSetDevice(e->device));
-    CU(cudaDeviceSynchronize());
-    free_db(e);
+    cudaStream_t st = main_stream(e);
+    CU(cudaStreamSynchronize(st));
+    for (int i = 0; i < SWB_MAX_SLOTS; ++i) CU(cudaStreamSynchronize(e->slots[i].stream));
+    e->db_loaded = false;
     int rc = swb_build_plan(offsets, n, shard, nshards, e->plan_opts, e->plan);
     if (rc != 0) return fail(e, SWB_ERR_ARG, "bad offsets (decreasing, or a sequence longer than 2^31-16)");
+    const double t1 = wall_ms();
     SwbPlan &pl = e->plan;
     e->max_logg = 0;
     for (int l = 0; l <= SWB_MAX_LOGG; ++l)
         if (pl.tiles_by_logg[l]) e->max_logg = l;
-    cudaStream_t st = main_stream(e);
     const uint32_t nl = pl.n_local;
     const uint32_t ntiles = (uint32_t)pl.tiles.size();
     const uint64_t base = n ? offsets[0] : 0;
     const uint64_t raw_bytes = pl.residues_total;
-
-    uint8_t *d_raw = nullptr;
-    uint64_t *d_seq_off = nullptr;
-    uint32_t *d_seq_len = nullptr;
-    uint8_t *h_stage[2] = {nullptr, nullptr};
-    cudaEvent_t ev_stage[2] = {nullptr, nullptr};
-    auto cleanup_tmp = [&]() {
-        if (d_raw) cudaFree(d_raw);
-        if (d_seq_off) cudaFree(d_seq_off);
-        if (d_seq_len) cudaFree(d_seq_len);
-        for (int i = 0; i < 2; ++i) {
-            if (h_stage[i]) cudaFreeHost(h_stage[i]);
-            if (ev_stage[i]) cudaEventDestroy(ev_stage[i]);
-        }
-    };
-#define CUL(call)                                                                                    \
-    do {                                                                                             \
-        cudaError_t _e = (call);                                                                     \
-        if (_e != cudaSuccess) {                                                                     \
-            char _b[512];                                                                            \
-            snprintf(_b, sizeof _b, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, \
-                     __LINE__);                                                                      \
-            cleanup_tmp();                                                                           \
-            free_db(e);                                                                              \
-            return fail(e, SWB_ERR_CUDA, _b);                                                        \
-        }                                                                                            \
-    } while (0)
+    double t2 = t1, t3 = t1;
 
     if (nl > 0 && ntiles > 0) {
-        CUL(cudaMalloc(&d_raw, std::max<uint64_t>(raw_bytes, 16)));
-        CUL(cudaMalloc(&d_seq_off, sizeof(uint64_t) * nl));
-        CUL(cudaMalloc(&d_seq_len, sizeof(uint32_t) * nl));
-        CUL(cudaMalloc(&e->d_tiles, sizeof(SwbTile) * ntiles));
-        CUL(cudaMalloc(&e->d_residues, std::max<uint64_t>(pl.res_bytes, 16)));
-        CUL(cudaMalloc(&e->d_out_pos, sizeof(uint32_t) * nl));
-        // stream the raw codes through two pinned staging buffers (async H2D overlapped with the host copy)
-        if (raw_bytes) {
-            const size_t stage = (size_t)std::min<uint64_t>(SWB_STAGE_BYTES, raw_bytes);
-            for (int i = 0; i < 2; ++i) {
-                CUL(cudaMallocHost(&h_stage[i], stage));
-                CUL(cudaEventCreateWithFlags(&ev_stage[i], cudaEventDisableTiming));
-            }
-            int b = 0;
-            for (uint64_t off = 0; off < raw_bytes; off += stage, b ^= 1) {
-                const size_t len = (size_t)std::min<uint64_t>(stage, raw_bytes - off);
-                CUL(cudaEventSynchronize(ev_stage[b]));
-                memcpy(h_stage[b], codes + base + off, len);
-                CUL(cudaMemcpyAsync(d_raw + off, h_stage[b], len, cudaMemcpyHostToDevice, st));
-                CUL(cudaEventRecord(ev_stage[b], st));
-            }
-        }
-        // offsets relative to the start of the uploaded range
-        std::vector<uint64_t> rel(nl);
-        for (uint32_t s = 0; s < nl; ++s) rel[s] = pl.seq_off[s] - base;
-        CUL(cudaMemcpyAsync(d_seq_off, rel.data(), sizeof(uint64_t) * nl, cudaMemcpyHostToDevice, st));
-        CUL(cudaMemcpyAsync(d_seq_len, pl.seq_len.data(), sizeof(uint32_t) * nl, cudaMemcpyHostToDevice, st));
-        CUL(cudaMemcpyAsync(e->d_tiles, pl.tiles.data(), sizeof(SwbTile) * ntiles, cudaMemcpyHostToDevice, st));
-        CUL(cudaMemcpyAsync(e->d_out_pos, pl.out_pos.data(), sizeof(uint32_t) * nl, cudaMemcpyHostToDevice, st));
-        CUL(swb_launch_pack(e->d_tiles, ntiles, d_raw, d_seq_off, d_seq_len, nl, e->d_residues, st));
-        // per-stream scratch
+        CU(GROW_DEV(e->d_raw, e->raw_cap, raw_bytes));
+        CU(GROW_DEV(e->d_seq_off, e->seq_off_cap, sizeof(uint64_t) * nl));
+        CU(GROW_DEV(e->d_seq_len, e->seq_len_cap, sizeof(uint32_t) * nl));
+        CU(GROW_DEV(e->d_tiles, e->tiles_cap, sizeof(SwbTile) * ntiles));
+        CU(GROW_DEV(e->d_residues, e->residues_cap, pl.res_bytes));
+        CU(GROW_DEV(e->d_out_pos, e->out_pos_cap, sizeof(uint32_t) * nl));
         const size_t flags_bytes = swb_roundup(ntiles, 16);
         const size_t sorted_bytes = sizeof(int32_t) * 2 * (size_t)((nl + 1) / 2);
         const size_t head = sizeof(uint32_t) * SWB_MAX_COUNTERS;
         for (int i = 0; i < e->nslots; ++i) {
             Slot &s = e->slots[i];
             s.state_bytes = head + flags_bytes + sorted_bytes;
-            CUL(cudaMalloc(&s.d_state, s.state_bytes));
+            CU(GROW_DEV(s.d_state, s.state_cap, s.state_bytes));
             s.d_counters = reinterpret_cast<uint32_t *>(s.d_state);
             s.d_flags = s.d_state + head;
             s.d_sorted = reinterpret_cast<int32_t *>(s.d_state + head + flags_bytes);
-            CUL(cudaMalloc(&s.d_bnd16, std::max<uint64_t>(sizeof(uint32_t) * pl.bnd_elems, 16)));
-            CUL(cudaMallocHost(&s.h_scores, std::max<size_t>(sizeof(int32_t) * nl, 16)));
+            CU(GROW_DEV(s.d_bnd16, s.bnd16_cap, sizeof(uint32_t) * pl.bnd_elems));
+            if (s.d_bnd32) CU(GROW_DEV(s.d_bnd32, s.bnd32_cap, 8ull * pl.bnd_elems));
+            CU(GROW_HOST(s.h_scores, s.h_scores_cap, sizeof(int32_t) * nl));
             s.busy = false;
         }
-        CUL(cudaStreamSynchronize(st));
+        t2 = wall_ms();
+        // stream the raw codes through two pinned staging buffers: the host copy of slice i+1 overlaps the
+        // asynchronous H2D of slice i
+        if (raw_bytes) {
+            const size_t stage = (size_t)std::min<uint64_t>(SWB_STAGE_BYTES, raw_bytes);
+            for (int i = 0; i < 2; ++i) {
+                CU(GROW_HOST(e->h_stage[i], e->stage_cap[i], stage));
+                if (!e->ev_stage[i]) CU(cudaEventCreateWithFlags(&e->ev_stage[i], cudaEventDisableTiming));
+            }
+            int b = 0;
+            for (uint64_t off = 0; off < raw_bytes; off += stage, b ^= 1) {
+                const size_t len = (size_t)std::min<uint64_t>(stage, raw_bytes - off);
+                CU(cudaEventSynchronize(e->ev_stage[b]));
+                memcpy(e->h_stage[b], codes + base + off, len);
+                CU(cudaMemcpyAsync(e->d_raw + off, e->h_stage[b], len, cudaMemcpyHostToDevice, st));
+                CU(cudaEventRecord(e->ev_stage[b], st));
+            }
+        }
+        // offsets relative to the start of the uploaded range
+        for (uint32_t s = 0; s < nl; ++s) pl.seq_off[s] -= base;
+        CU(cudaMemcpyAsync(e->d_seq_off, pl.seq_off.data(), sizeof(uint64_t) * nl, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(e->d_seq_len, pl.seq_len.data(), sizeof(uint32_t) * nl, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(e->d_tiles, pl.tiles.data(), sizeof(SwbTile) * ntiles, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(e->d_out_pos, pl.out_pos.data(), sizeof(uint32_t) * nl, cudaMemcpyHostToDevice, st));
+        t3 = wall_ms();
+        CU(swb_launch_pack(e->d_tiles, ntiles, e->d_raw, e->d_seq_off, e->d_seq_len, nl, e->d_residues, st));
+        CU(cudaStreamSynchronize(st));
     }
-    cleanup_tmp();
-#undef CUL
     e->db_loaded = true;
     e->stats.load_ms = wall_ms() - t0;
+    if (timing)
+        fprintf(stderr, "[swb] db_load: plan %.1f ms, alloc %.1f ms, stage+h2d enqueue %.1f ms, pack+sync %.1f ms, total %.1f ms\n",
+                t1 - t0, t2 - t1, t3 - t2, wall_ms() - t3, e->stats.load_ms);
     e->stats.db_residues = pl.residues_local;
     e->stats.db_residues_total = pl.residues_total;
     e->stats.db_sequences = nl;
@@ -482,7 +509,7 @@ static int enqueue_query(swb_engine *e, Slot &s, uint32_t qi, const uint8_t *q, 
         CU(cudaMalloc(&s.d_prof, cap));
         s.prof_cap = cap;
     }
-    if (need_i32 && !s.d_bnd32) CU(cudaMalloc(&s.d_bnd32, std::max<uint64_t>(8ull * pl.bnd_elems, 16)));
+    if (need_i32) CU(GROW_DEV(s.d_bnd32, s.bnd32_cap, 8ull * pl.bnd_elems));
 
     memcpy(s.h_query, q, qlen);
     CU(cudaMemcpyAsync(s.d_query, s.h_query, qlen, cudaMemcpyHostToDevice, s.stream));
@@ -555,13 +582,9 @@ extern "C" int swb_search_batch(swb_engine *e, const uint8_t *qcodes, const uint
         if (qoffsets[i + 1] < qoffsets[i] || qoffsets[i + 1] - qoffsets[i] > 0x7fffffffull)
             return fail(e, SWB_ERR_ARG, "bad query offsets");
     cudaStream_t ms = main_stream(e);
-    if ((size_t)nq > e->out_cap && nl > 0) {
+    if (sizeof(int32_t) * (size_t)nq * nl > e->out_cap && nl > 0) {
         CU(cudaStreamSynchronize(ms));
-        if (e->d_out) cudaFree(e->d_out);
-        e->d_out = nullptr;
-        e->out_cap = 0;
-        CU(cudaMalloc(&e->d_out, sizeof(int32_t) * (size_t)nq * nl));
-        e->out_cap = nq;
+        CU(GROW_DEV(e->d_out, e->out_cap, sizeof(int32_t) * (size_t)nq * nl));
     }
     e->stats.cells = 0;
     e->stats.padded_cells = 0;

@@ -60,15 +60,24 @@ int swb_build_plan(const uint64_t *offsets, uint32_t n, uint32_t shard, uint32_t
     plan.n_local = (uint32_t)plan.sorted_ids.size();
     const uint32_t nl = plan.n_local;
 
-    plan.shard_ids = plan.sorted_ids;
-    std::sort(plan.shard_ids.begin(), plan.shard_ids.end());
+    // output order = ascending DB id; rank_of[id] = position of id among the shard's ids (O(n), no sort)
+    plan.shard_ids.resize(nl);
     plan.out_pos.resize(nl);
     if (nshards == 1) {
-        for (uint32_t s = 0; s < nl; ++s) plan.out_pos[s] = plan.sorted_ids[s];
+        for (uint32_t s = 0; s < nl; ++s) {
+            plan.shard_ids[s] = s;
+            plan.out_pos[s] = plan.sorted_ids[s];
+        }
     } else {
-        for (uint32_t s = 0; s < nl; ++s)
-            plan.out_pos[s] = (uint32_t)(std::lower_bound(plan.shard_ids.begin(), plan.shard_ids.end(),
-                                                          plan.sorted_ids[s]) - plan.shard_ids.begin());
+        std::vector<uint32_t> rank_of(n, 0xffffffffu);
+        for (uint32_t s = 0; s < nl; ++s) rank_of[plan.sorted_ids[s]] = 0;
+        uint32_t r = 0;
+        for (uint32_t id = 0; id < n; ++id)
+            if (rank_of[id] == 0) {
+                plan.shard_ids[r] = id;
+                rank_of[id] = r++;
+            }
+        for (uint32_t s = 0; s < nl; ++s) plan.out_pos[s] = rank_of[plan.sorted_ids[s]];
     }
     plan.seq_off.resize(nl);
     plan.seq_len.resize(nl);

@@ -1,0 +1,117 @@
+"""CPU validation of the kernel logic: tests/emu/swb_emu.cu runs the SAME warp program as the GPU
+(csrc/swb_warp.cuh) lane by lane on the host -- same tiling plan, packing function, query chunking,
+boundary scratch, lane-group wavefront, overflow flagging and int32 recompute -- and must reproduce the
+oracle bit for bit. (The GPU run of the same code is covered by tests/test_gpu_parity.py.)"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import PKG, ROOT, random_db
+from oracle_lib import pack_db
+
+_u8p = ctypes.POINTER(ctypes.c_uint8)
+_i8p = ctypes.POINTER(ctypes.c_int8)
+_u64p = ctypes.POINTER(ctypes.c_uint64)
+_i32p = ctypes.POINTER(ctypes.c_int32)
+
+
+@pytest.fixture(scope="module")
+def emu():
+    so = os.path.join(ROOT, PKG, "lib", "libswbemu.so")
+    if not os.path.exists(so):
+        subprocess.run(["make", "-C", os.path.join(ROOT, PKG), "emu"], check=True, capture_output=True)
+    L = ctypes.CDLL(so)
+    L.swbemu_search.restype = ctypes.c_int
+    L.swbemu_search.argtypes = [_u8p, _u64p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, _i8p,
+                                ctypes.c_int, _u8p, ctypes.c_uint32, ctypes.c_int, ctypes.c_int, ctypes.c_uint32,
+                                ctypes.c_int, _i32p, ctypes.POINTER(ctypes.c_uint32)]
+
+    def search(codes, offs, m, q, K=32, group_len=384, force_i32=0, chunk_rows=0, thr=-1, gap=2, shard=0, nshards=1,
+               n_out=None):
+        codes = np.ascontiguousarray(codes, dtype=np.uint8)
+        if len(codes) == 0:
+            codes = np.zeros(1, dtype=np.uint8)
+        offs = np.ascontiguousarray(offs, dtype=np.uint64)
+        q = np.ascontiguousarray(q, dtype=np.uint8)
+        m = np.ascontiguousarray(m, dtype=np.int8)
+        n = len(offs) - 1
+        out = np.full(n if n_out is None else n_out, -7, dtype=np.int32)
+        rc = ctypes.c_uint32()
+        r = L.swbemu_search(codes.ctypes.data_as(_u8p), offs.ctypes.data_as(_u64p), n, shard, nshards, group_len,
+                            m.ctypes.data_as(_i8p), gap, q.ctypes.data_as(_u8p) if len(q) else None, len(q), K,
+                            force_i32, chunk_rows, thr, out.ctypes.data_as(_i32p), ctypes.byref(rc))
+        assert r == 0
+        return out, rc.value
+
+    return search
+
+
+@pytest.mark.parametrize("K,group_len", [(8, 2000), (16, 384), (32, 384), (32, 64), (16, 16), (8, 16)])
+def test_subset_all_shapes(emu, oracle, subset, queries, K, group_len):
+    m = oracle.matrix("blosum50")
+    q = oracle.encode(queries["P02232"])
+    want = oracle.scan(q, subset["codes"], subset["offsets"], m)
+    got, _ = emu(subset["codes"], subset["offsets"], m, q, K=K, group_len=group_len)
+    assert np.array_equal(got, want)
+
+
+def test_query_chunks_and_forced_recompute(emu, oracle, subset, queries):
+    m = oracle.matrix("blosum50")
+    q = oracle.encode(queries["P04775"])  # 2005 rows -> two chunks of 1024
+    want = oracle.scan(q, subset["codes"], subset["offsets"], m)
+    got, rc = emu(subset["codes"], subset["offsets"], m, q, K=32, group_len=384, chunk_rows=1024)
+    assert np.array_equal(got, want) and rc == 0
+    # threshold override: every tile whose best exceeds 300 is re-scored by the int32 path
+    got, rc = emu(subset["codes"], subset["offsets"], m, q, K=32, group_len=384, chunk_rows=1024, thr=300)
+    assert np.array_equal(got, want) and rc >= 1
+    got, rc = emu(subset["codes"], subset["offsets"], m, q, K=16, group_len=128, force_i32=1)
+    assert np.array_equal(got, want)
+
+
+def test_real_s16_overflow_is_caught(emu, oracle):
+    """W x 2300 against itself scores 34500 > 32767: the s16 pass must flag it and int32 must fix it"""
+    m = oracle.matrix("blosum50")
+    w = np.full(2300, 17, dtype=np.uint8)
+    rng = np.random.default_rng(2)
+    enc = [w, rng.integers(0, 20, 300).astype(np.uint8), w[:2200].copy(), rng.integers(0, 20, 50).astype(np.uint8)]
+    codes, offs = pack_db(enc)
+    want = oracle.scan(w, codes, offs, m)
+    assert want[0] == 34500 and want[2] == 33000
+    got, rc = emu(codes, offs, m, w, K=32, group_len=384)
+    assert np.array_equal(got, want) and rc >= 1
+
+
+def test_edges_ident3_and_shards(emu, oracle, subset, queries):
+    rng = np.random.default_rng(5)
+    m = oracle.matrix("blosum50")
+    lens = [0, 1, 2, 3, 4, 5, 7, 8, 9, 0, 33, 64, 65, 127, 128, 129, 1, 0, 300]
+    enc = random_db(rng, lens)
+    codes, offs = pack_db(enc)
+    for ql in (1, 8, 9, 33):
+        q = rng.integers(0, 24, ql).astype(np.uint8)
+        want = oracle.scan(q, codes, offs, m)
+        for K, gl in ((8, 8), (16, 16), (32, 384)):
+            got, _ = emu(codes, offs, m, q, K=K, group_len=gl)
+            assert np.array_equal(got, want), (ql, K, gl)
+    got, _ = emu(codes, offs, m, np.zeros(0, np.uint8), K=32)
+    assert np.array_equal(got, np.zeros(len(lens), np.int32))
+    # +3/-3 scheme
+    mi = oracle.matrix("ident3")
+    ic, io = pack_db([oracle.encode(s, "ident3") for s in subset["seqs"][:40]])
+    q = oracle.encode(queries["P02232"], "ident3")
+    got, _ = emu(ic, io, mi, q, K=16, group_len=128)
+    assert np.array_equal(got, oracle.scan(q, ic, io, mi))
+    # shards: union of the per-shard outputs equals the unsharded scan
+    q = oracle.encode(queries["P02232"])
+    want = oracle.scan(q, subset["codes"], subset["offsets"], m)
+    import importlib
+    swb = importlib.import_module(PKG)
+    merged = np.full(111, -1, np.int32)
+    for s in range(3):
+        info, _, ids = swb.plan_describe(subset["offsets"], s, 3, want_ids=True)
+        got, _ = emu(subset["codes"], subset["offsets"], m, q, K=32, shard=s, nshards=3, n_out=info.n_local)
+        merged[ids] = got
+    assert np.array_equal(merged, want)

@@ -204,3 +204,39 @@ def test_reference_cuda_binary_agrees(swb, subset, queries, tmp_path):
         result = []
         swb.smith_waterman_cuda(swb.FASTAQuery(qpath), db, result)
         assert ref_lines == ["%d:%d" % r for r in result], name
+
+
+def test_cli_and_reference_style_caller(swb, tmp_path):
+    """bin/main prints the reference's text (main.cpp:45-47, 58-60, 65-72); a caller written against the reference
+    headers links against libswb.so and reproduces the golden file"""
+    import re
+    pkg = os.path.join(ROOT, "ece1782-smith-waterman-cuda_b200")
+    main = os.path.join(pkg, "bin", "main")
+    qpath = os.path.join(GOLDEN, "queries", "P01008.fasta")
+    dbpath = os.path.join(GOLDEN, "uniprot_subset.fasta")
+    r = subprocess.run([main, "--query", qpath, "--db=" + dbpath], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.split("\n")
+    query = swb.FASTAQuery(qpath).get_buffer()
+    assert lines[0] == "Input buffer:" + query and lines[1] == ""
+    gold = _gold("P01008")
+    body = lines[2:2 + 111]
+    assert [int(l.split(":")[0]) for l in body[:3]] == [56, 34, 13]
+    for l in body:
+        sid, sc = l.split(":")
+        assert int(sc) == gold[int(sid)]
+    tail = lines[2 + 111:]
+    assert tail[0] == "=" * 80 and tail[1] == "METRICS:"
+    assert tail[2] == "Query length: 464 chars." and tail[3] == "Num subjects: 111"
+    assert tail[4] == "Sum of DB length: 26728 chars."
+    assert re.fullmatch(r"Time elapsed: [0-9.e+-]+ seconds\.", tail[5])
+    assert re.fullmatch(r"Performance: [0-9.e+-]+ GCUPS\.", tail[6])
+    # reference-style caller
+    exe = str(tmp_path / "caller")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-I" + os.path.join(ROOT, "include"), "-o", exe,
+                    os.path.join(ROOT, "tests", "cpp", "caller_compat.cpp"), os.path.join(pkg, "lib", "SWSolver.o"),
+                    "-L" + os.path.join(pkg, "lib"), "-lswb", "-Wl,-rpath," + os.path.join(pkg, "lib")], check=True)
+    r = subprocess.run([exe, qpath, dbpath, os.path.join(GOLDEN, "P01008.head111.txt")], capture_output=True, text=True,
+                       timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "mismatches 0" in r.stdout

@@ -1,0 +1,74 @@
+"""The CPU oracle (oracle/sw_oracle.c) pinned to everything the reference offers for this path:
+golden heads of test/reference/*.txt, the survey probe's 20 x 111 vectors, the self-scores, the
+Wikipedia pair, and the scores / aligned strings printed by the compiled reference cpu.cpp."""
+import json
+import os
+
+import numpy as np
+
+from conftest import GOLDEN
+from oracle_lib import pack_db
+
+
+def _gold(name):
+    return np.array([int(x) for x in open(os.path.join(GOLDEN, name + ".head111.txt")).read().split()], dtype=np.int32)
+
+
+def test_golden_heads(oracle, subset, queries):
+    m = oracle.matrix("blosum50")
+    for name, total in (("P01008", 31802), ("P02232", 18440)):
+        got = oracle.scan(oracle.encode(queries[name]), subset["codes"], subset["offsets"], m)
+        assert np.array_equal(got, _gold(name))
+        assert int(got.sum()) == total
+    assert list(_gold("P01008")[:5]) == [364, 368, 550, 223, 509]
+    assert list(_gold("P02232")[:5]) == [192, 206, 208, 165, 227]
+
+
+def test_survey_vectors_all_queries(oracle, subset, queries, survey_exp):
+    m = oracle.matrix("blosum50")
+    assert len(survey_exp) == 20
+    for name, want in survey_exp.items():
+        got = oracle.scan(oracle.encode(queries[name]), subset["codes"], subset["offsets"], m)
+        assert np.array_equal(got, np.array(want, dtype=np.int32)), name
+
+
+def test_self_scores_and_wikipedia_pair(oracle, queries):
+    m = oracle.matrix("blosum50")
+    for name, want in (("P01008", 3037), ("P02232", 910)):
+        q = oracle.encode(queries[name])
+        assert oracle.score(q, q, m) == want
+    assert oracle.score(oracle.encode("GGTTGACTA"), oracle.encode("TGTTACGG"), m) == 34
+    mi = oracle.matrix("ident3")
+    assert oracle.score(oracle.encode("GGTTGACTA", "ident3"), oracle.encode("TGTTACGG", "ident3"), mi) == 13
+
+
+def test_against_compiled_cpu_cpp(oracle, subset, queries):
+    ref = json.load(open(os.path.join(GOLDEN, "cpu_ref_ident3.json")))
+    mi = oracle.matrix("ident3")
+    for p in ref["pairs"]:
+        s, a, b, _ = oracle.align(p["a"], p["b"], "ident3")
+        assert (s, a, b) == (p["score"], p["aligned_a"], p["aligned_b"])
+        assert oracle.score(oracle.encode(p["a"], "ident3"), oracle.encode(p["b"], "ident3"), mi) == p["score"]
+    codes, offs = pack_db([oracle.encode(s, "ident3") for s in subset["seqs"]])
+    for name, want in ref["scans"].items():
+        got = oracle.scan(oracle.encode(queries[name], "ident3"), codes, offs, mi)
+        assert np.array_equal(got, np.array(want, dtype=np.int32)), name
+
+
+def test_matrix_properties(oracle):
+    m = oracle.matrix("blosum50").astype(int)
+    assert (m == m.T).all() and m.min() == -5 and m.max() == 15
+    assert (m[24:, :] == 0).all() and (m[:, 24:] == 0).all()  # '*' and spare codes score 0 (SWSolver.cu:80)
+    assert m[17, 17] == 15 and m[4, 4] == 13 and m[0, 0] == 5
+    mi = oracle.matrix("ident3").astype(int)
+    assert (np.diag(mi)[:31] == 3).all() and mi[31].max() == 0 and mi[0, 1] == -3
+
+
+def test_padding_is_score_neutral(oracle, queries):
+    """'/' padding of FASTAParsers.h:94-96 / SWSolver.cu:268-269 encodes to '*' and cannot change a score"""
+    m = oracle.matrix("blosum50")
+    q = queries["P02232"]
+    d = queries["P05013"]
+    base = oracle.score(oracle.encode(q), oracle.encode(d), m)
+    assert oracle.score(oracle.encode(q + "////"), oracle.encode(d + "///////"), m) == base
+    assert list(oracle.encode("AUO/z*\r")) == [0, 24, 24, 24, 24, 24, 24]

@@ -257,7 +257,7 @@ def main():
     # end to end through the C ABI with host buffers (database upload + search + scores back), wall clock
     out = np.zeros((len(qs), nloc), dtype=np.int32)
     e2e_times = []
-    for it in range(args.e2e_steps + 1):
+    for it in range(args.e2e_steps + 1 if args.e2e_steps > 0 else 0):
         barrier()
         t0 = time.perf_counter()
         eng.db_load(codes, offsets, rank, world)

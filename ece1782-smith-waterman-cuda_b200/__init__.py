@@ -404,3 +404,39 @@ def smith_waterman_cuda(query, db, result, device=0):
     for k, (sid, _) in enumerate(ordered):
         result.append((sid, int(scores[k])))
     return result
+
+
+# ---- multi-GPU host side: shards are independent, only small results are exchanged -------------
+def merge_shard_scores(n_total, parts):
+    """parts: iterable of (ids, scores) per shard (ids = database ids of that shard). Returns the full
+    score vector in database order; every id must be covered exactly once."""
+    out = np.full(n_total, np.iinfo(np.int32).min, dtype=np.int32)
+    seen = np.zeros(n_total, dtype=np.uint8)
+    for ids, scores in parts:
+        ids = np.asarray(ids, dtype=np.int64)
+        out[ids] = np.asarray(scores, dtype=np.int32)
+        seen[ids] += 1
+    if not (seen == 1).all():
+        raise SwbError("shards do not partition the database")
+    return out
+
+
+def merge_topk(parts, k):
+    """parts: iterable of (ids, scores) hit lists (one per GPU). k best overall: score descending, id ascending."""
+    hits = [(int(s), int(i)) for ids, scores in parts for i, s in zip(ids, scores) if int(i) != 0xFFFFFFFF]
+    hits.sort(key=lambda h: (-h[0], h[1]))
+    hits = hits[:k]
+    return np.array([h[1] for h in hits], dtype=np.uint32), np.array([h[0] for h in hits], dtype=np.int32)
+
+
+def sharded_search(engine, queries, rank, world, k=10, gather=None):
+    """One rank's part of a sharded scan: scores of this rank's shard for every query plus its top-k lists; with
+    `gather` (e.g. torch.distributed.all_gather_object wrapped to return the list) the lists are merged and the
+    merged (ids, scores) per query are returned as well."""
+    scores = engine.search_batch(queries)
+    mine = [engine.topk(scores[i], k) for i in range(len(queries))]
+    if gather is None:
+        return scores, mine, None
+    everyone = gather([(ids.tolist(), top.tolist()) for ids, top in mine])
+    merged = [merge_topk([everyone[r][qi] for r in range(world)], k) for qi in range(len(queries))]
+    return scores, mine, merged

@@ -187,6 +187,7 @@ def main():
     ap.add_argument("--streams", type=int, default=0)
     ap.add_argument("--k", type=int, default=0)
     ap.add_argument("--group-len", type=int, default=0)
+    ap.add_argument("--group-order", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--per-query", action="store_true", help="also print device GCUPS per query")
     args = ap.parse_args()
@@ -216,6 +217,8 @@ def main():
         opts["k"] = args.k
     if args.group_len:
         opts["group_len"] = args.group_len
+    if args.group_order:
+        opts["group_order"] = args.group_order
     eng = swb.Engine(local, **opts)
     stream = torch.cuda.current_stream()
     eng.set_stream(stream.cuda_stream)
@@ -294,8 +297,8 @@ def main():
             top_ok = all(len(mm) == 10 for mm in merged)
 
     if rank == 0:
-        # roofline of the dominant kernel (swb_score_kernel, V16): integer SIMD issue rate
-        mix = swb.microbench(local, 4)
+        # roofline of the dominant kernel (swb_score_kernel<K,V16>): issue rate of its own instruction mix
+        mix = swb.microbench(local, 4)  # Glane-instr/s of prmt + viaddmax.relu + viaddmax + vadd2 + 1/2 vimax3
         per_kind = {swb.MICROBENCH_KINDS[k]: round(swb.microbench(local, k), 1) for k in (0, 1, 2, 3, 5, 6)}
         instr_per_cell = 4.5 / 2.0
         padded_cells = float(st["padded_cells"])
@@ -313,8 +316,8 @@ def main():
                     "unit": "GCUPS", "frac": (value / world) / peak_gcups, "traffic": None,
                     "achieved_incl_padding": ach_padded / world,
                     "frac_incl_padding": (ach_padded / world) / peak_gcups,
-                    "peak_source": "swb_microbench kind 4 (score-kernel instruction mix, 4.5 SIMD instr per cell pair) "
-                                   "measured live: %.0f Glane-instr/s" % mix,
+                    "peak_source": "swb_microbench kind 4 measured live: %.0f Glane-instr/s for the kernel's own SIMD mix "
+                                   "(prmt + viaddmax.relu + viaddmax + vadd2 + 1/2 vimax3 = 4.5 instr per cell pair)" % mix,
                     "instr_rates_glane_per_s": per_kind,
                     "hbm": {"achieved": alg_bytes / (ms_per_step * 1e-3) * 1e-9, "peak": hbm_peak, "unit": "GB/s",
                             "frac": alg_bytes / (ms_per_step * 1e-3) * 1e-9 / hbm_peak,

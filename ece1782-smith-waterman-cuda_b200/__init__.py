@@ -192,8 +192,8 @@ def plan_describe(offsets, shard=0, nshards=1, group_len=0, want_ids=False):
     return info, sorted_ids, shard_ids
 
 
-MICROBENCH_KINDS = ["viaddmax_s16x2_relu", "vimax3_s16x2", "vadd2", "prmt", "score_mix", "viaddmax+imad", "imad",
-                    "scalar_addmax"]
+MICROBENCH_KINDS = ["viaddmax_s16x2_relu", "vimax3_s16x2", "vadd2", "prmt", "v16_mix", "viaddmax+imad", "imad",
+                    "scalar_addmax", "v16b_mix"]
 
 
 def microbench(device=0, kind=4):

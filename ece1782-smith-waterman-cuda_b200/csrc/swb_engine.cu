@@ -14,7 +14,8 @@
 #include "swb_plan.h"
 
 #define SWB_MAX_SLOTS 4
-#define SWB_MAX_COUNTERS 64
+#define SWB_MAX_COUNTERS 256
+#define SWB_MAX_SUB 2  // extra streams per slot: up to three distinct K values per query
 #define SWB_CHUNK_ROWS 7168u          // query rows per launch when a query does not fit shared memory
 #define SWB_SMALL_SMEM_LIMIT (100u * 1024u)
 #define SWB_STAGE_BYTES (32u << 20)   // pinned staging buffers for the raw database upload
@@ -30,6 +31,9 @@ static double wall_ms()
 
 struct Slot {
     cudaStream_t stream = nullptr;
+    cudaStream_t sub[SWB_MAX_SUB] = {nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr;
+    cudaEvent_t ev_sub[SWB_MAX_SUB] = {nullptr, nullptr};
     cudaEvent_t done = nullptr;
     bool busy = false;
     uint8_t *h_query = nullptr;  // pinned
@@ -65,12 +69,15 @@ struct swb_engine {
     int8_t h_mat[SWB_ALPHA * SWB_ALPHA];
     int gap = 2;
     int max_s = 0;
+    int min_s = 0;
     bool scoring_set = false;
     int8_t *d_mat = nullptr;
     // options
     SwbPlanOpts plan_opts;
     int opt_k = 0;
-    int nslots = 2;
+    int opt_group_order = 0;  // 0 auto (lone query: longest tiles first; batch: bulk first), 1 longest first, 2 bulk first
+    uint32_t cur_nq = 1;
+    int nslots = 3;
     uint32_t chunk_rows = SWB_CHUNK_ROWS;  // query rows per launch for queries beyond shared memory
     // database
     bool db_loaded = false;
@@ -193,6 +200,12 @@ extern "C" int swb_create(swb_engine **out, int device)
         if ((ce = cudaStreamCreateWithFlags(&e->slots[i].stream, cudaStreamNonBlocking)) != cudaSuccess)
             return bail("cudaStreamCreate", ce);
         cudaEventCreateWithFlags(&e->slots[i].done, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&e->slots[i].ev_fork, cudaEventDisableTiming);
+        for (int k = 0; k < SWB_MAX_SUB; ++k) {
+            if ((ce = cudaStreamCreateWithFlags(&e->slots[i].sub[k], cudaStreamNonBlocking)) != cudaSuccess)
+                return bail("cudaStreamCreate", ce);
+            cudaEventCreateWithFlags(&e->slots[i].ev_sub[k], cudaEventDisableTiming);
+        }
         cudaEventCreateWithFlags(&e->ev_join[i], cudaEventDisableTiming);
         if ((ce = cudaMalloc(&e->slots[i].d_recount, sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc", ce);
     }
@@ -224,6 +237,11 @@ extern "C" void swb_destroy(swb_engine *e)
         if (s.d_prof) cudaFree(s.d_prof);
         if (s.d_recount) cudaFree(s.d_recount);
         if (s.stream) cudaStreamDestroy(s.stream);
+        if (s.ev_fork) cudaEventDestroy(s.ev_fork);
+        for (int k = 0; k < SWB_MAX_SUB; ++k) {
+            if (s.sub[k]) cudaStreamDestroy(s.sub[k]);
+            if (s.ev_sub[k]) cudaEventDestroy(s.ev_sub[k]);
+        }
         if (s.done) cudaEventDestroy(s.done);
         if (e->ev_join[i]) cudaEventDestroy(e->ev_join[i]);
     }
@@ -251,6 +269,9 @@ extern "C" int swb_set_option(swb_engine *e, const char *key, int64_t value)
         if (value < 1 || value > SWB_MAX_SLOTS) return fail(e, SWB_ERR_ARG, "streams must be 1..4");
         if (e->db_loaded) return fail(e, SWB_ERR_STATE, "set streams before swb_db_load");
         e->nslots = (int)value;
+    } else if (!strcmp(key, "group_order")) {
+        if (value < 0 || value > 2) return fail(e, SWB_ERR_ARG, "group_order must be 0, 1 or 2");
+        e->opt_group_order = (int)value;
     } else if (!strcmp(key, "chunk_rows")) {
         if (value < 1024 || value > SWB_CHUNK_ROWS || value % 1024) return fail(e, SWB_ERR_ARG, "chunk_rows must be a multiple of 1024 up to 7168");
         e->chunk_rows = (uint32_t)value;
@@ -274,7 +295,7 @@ extern "C" int swb_set_scoring(swb_engine *e, const int8_t *matrix, int alpha, i
     if (gap < 0 || gap > 64) return fail(e, SWB_ERR_ARG, "gap must be 0..64");
     int8_t m[SWB_ALPHA * SWB_ALPHA];
     memset(m, 0, sizeof m);
-    int mx = 0;
+    int mx = 0, mn = 0;
     for (int i = 0; i < alpha; ++i)
         for (int j = 0; j < alpha; ++j) {
             int v = matrix[i * alpha + j];
@@ -282,12 +303,14 @@ extern "C" int swb_set_scoring(swb_engine *e, const int8_t *matrix, int alpha, i
             if (v + gap > 127 || v + gap < -128) return fail(e, SWB_ERR_ARG, "matrix entry + gap does not fit int8");
             m[i * SWB_ALPHA + j] = (int8_t)v;
             mx = std::max(mx, v);
+            mn = std::min(mn, v);
         }
     CU(cudaSetDevice(e->device));
     CU(cudaStreamSynchronize(main_stream(e)));
     memcpy(e->h_mat, m, sizeof m);
     e->gap = gap;
     e->max_s = mx;
+    e->min_s = mn;
     CU(cudaMemcpy(e->d_mat, e->h_mat, sizeof m, cudaMemcpyHostToDevice));
     e->scoring_set = true;
     return SWB_OK;
@@ -429,34 +452,16 @@ extern "C" int swb_db_ids(const swb_engine *e, uint32_t *ids)
 }
 
 // ---------------------------------------------------------------------------------------------
-// rows per lane: the value that minimises the estimated issue cost over the shard's group mix
-static int choose_k(const swb_engine *e, uint32_t qlen)
-{
-    if (e->opt_k) return e->opt_k;
-    const int ks[3] = {32, 16, 8};
-    double best = 0;
-    int best_k = 32;
-    for (int i = 0; i < 3; ++i) {
-        const int K = ks[i];
-        double cost = 0;
-        for (int l = 0; l <= SWB_MAX_LOGG; ++l) {
-            if (!e->plan.cols_by_logg[l]) continue;
-            const double rows = swb_roundup(qlen, (uint32_t)K << l);
-            cost += (double)e->plan.cols_by_logg[l] * rows * (1.0 + 4.0 / K);
-        }
-        if (i == 0 || cost < best) { best = cost; best_k = K; }
-    }
-    return best_k;
-}
-
 struct LaunchShape {
     int block_cfg;
     int grid;
     size_t smem;
+    uint32_t smem_rows;
 };
 
-static int shape_for(swb_engine *e, int K, bool i32, uint32_t smem_rows, LaunchShape &ls)
+static int shape_for(swb_engine *e, int K, bool i32, uint32_t smem_rows, uint32_t ntiles, LaunchShape &ls)
 {
+    ls.smem_rows = smem_rows;
     ls.smem = (size_t)SWB_ALPHA * (smem_rows + 4);
     if (ls.smem > e->smem_optin) return fail(e, SWB_ERR_ARG, "internal: query chunk does not fit shared memory");
     ls.block_cfg = ls.smem <= SWB_SMALL_SMEM_LIMIT ? SWB_BLOCK_SMALL : SWB_BLOCK_LARGE;
@@ -464,13 +469,15 @@ static int shape_for(swb_engine *e, int K, bool i32, uint32_t smem_rows, LaunchS
     CU(swb_score_occupancy(K, i32, ls.block_cfg, ls.smem, &per_sm));
     if (per_sm < 1) return fail(e, SWB_ERR_CUDA, "score kernel does not fit on an SM");
     const int nt = ls.block_cfg == SWB_BLOCK_SMALL ? SWB_NT_SMALL : SWB_NT_LARGE;
-    const uint32_t ntiles = (uint32_t)e->plan.tiles.size();
     const int need = (int)((ntiles + nt / 32 - 1) / (nt / 32));
     ls.grid = std::max(1, std::min(per_sm * e->sm_count, need));
     return SWB_OK;
 }
 
-// Enqueues everything one query needs on the slot's stream; the result lands in d_out[qi].
+// Enqueues everything one query needs; the result lands in d_out[qi].
+// Stream layout per slot: profile build and clears on slot.stream, then one sub-stream per distinct K (the tiles of
+// the group sizes that use that K for this query) so that the few long-sequence tiles run beside the bulk, then
+// the scatter back on slot.stream.
 static int enqueue_query(swb_engine *e, Slot &s, uint32_t qi, const uint8_t *q, uint32_t qlen)
 {
     SwbPlan &pl = e->plan;
@@ -481,13 +488,25 @@ static int enqueue_query(swb_engine *e, Slot &s, uint32_t qi, const uint8_t *q, 
         CU(cudaMemsetAsync(out, 0, sizeof(int32_t) * nl, s.stream));
         return SWB_OK;
     }
+    const int ovf_thr = 32767 - e->max_s;
     // the s16 pass, and the int32 pass over flagged tiles when a score could exceed the s16 range at all
-    const bool need_i32 = (int64_t)e->max_s * std::min<uint32_t>(qlen, pl.max_len) > 32767 - e->max_s;
+    const bool need_i32 = (int64_t)e->max_s * std::min<uint32_t>(qlen, pl.max_len) > ovf_thr;
+    uint32_t present = 0;
+    for (int l = 0; l <= SWB_MAX_LOGG; ++l)
+        if (pl.tiles_by_logg[l]) present |= 1u << l;
     SwbQueryPlan qp[2];
-    swb_plan_query(qlen, choose_k(e, qlen), e->max_logg, e->chunk_rows, qp[0]);
-    if (need_i32) swb_plan_query(qlen, std::min(qp[0].K, 16), e->max_logg, e->chunk_rows, qp[1]);
+    std::vector<SwbLaunchGroup> groups[2];
+    swb_plan_query(qlen, e->opt_k, 32, present, e->chunk_rows, qp[0]);
+    const bool longest_first = e->opt_group_order == 1 || (e->opt_group_order == 0 && e->cur_nq <= 1);
+    swb_plan_launch_groups(pl, qp[0], longest_first, groups[0]);
+    if (need_i32) {
+        swb_plan_query(qlen, e->opt_k, 16, present, e->chunk_rows, qp[1]);
+        swb_plan_launch_groups(pl, qp[1], longest_first, groups[1]);
+    }
     const int npass = need_i32 ? 2 : 1;
-    if (npass * qp[0].chunks.size() > SWB_MAX_COUNTERS) return fail(e, SWB_ERR_ARG, "query too long");
+    size_t nlaunch = 0;
+    for (int pass = 0; pass < npass; ++pass) nlaunch += groups[pass].size() * qp[pass].chunks.size();
+    if (nlaunch > SWB_MAX_COUNTERS) return fail(e, SWB_ERR_ARG, "query too long");
     const uint32_t prof_rows = need_i32 ? std::max(qp[0].prof_rows, qp[1].prof_rows) : qp[0].prof_rows;
     const uint32_t prof_stride = swb_roundup(prof_rows, 16);
     if (qlen > s.query_cap) {
@@ -520,7 +539,6 @@ static int enqueue_query(swb_engine *e, Slot &s, uint32_t qi, const uint8_t *q, 
     SwbScoreParams p;
     memset(&p, 0, sizeof p);
     p.tiles = e->d_tiles;
-    p.ntiles = (uint32_t)pl.tiles.size();
     p.residues = e->d_residues;
     p.profile = s.d_prof;
     p.prof_stride = prof_stride;
@@ -528,32 +546,53 @@ static int enqueue_query(swb_engine *e, Slot &s, uint32_t qi, const uint8_t *q, 
     p.flags = s.d_flags;
     p.recount = s.d_recount;
     p.gap = e->gap;
-    p.ovf_thr = 32767 - e->max_s;
+    p.ovf_thr = ovf_thr;
+    p.t0 = 0;
     uint32_t counter = 0;
     for (int pass = 0; pass < npass; ++pass) {
         const bool i32 = pass == 1;
         p.bnd = i32 ? s.d_bnd32 : (void *)s.d_bnd16;
         p.only_flagged = i32 ? 1u : 0u;
-        for (size_t c = 0; c < qp[pass].chunks.size(); ++c) {
-            const SwbQueryChunk &ch = qp[pass].chunks[c];
-            LaunchShape ls;
-            int rc = shape_for(e, qp[pass].K, i32, ch.smem_rows, ls);
-            if (rc != SWB_OK) return rc;
-            p.row0 = ch.row0;
-            p.rows = ch.rows;
-            p.smem_rows = ch.smem_rows;
-            p.first_chunk = ch.first;
-            p.last_chunk = ch.last;
-            p.counter = s.d_counters + counter++;
-            CU(swb_launch_score(qp[pass].K, i32, ls.block_cfg, p, ls.grid, ls.smem, s.stream));
-            e->stats.kernel_launches += 1;
+        const size_t ng = groups[pass].size();
+        // fork: the launch groups of a pass are independent of each other (disjoint tiles)
+        if (ng > 1) {
+            CU(cudaEventRecord(s.ev_fork, s.stream));
+            for (size_t gi = 1; gi < ng; ++gi) CU(cudaStreamWaitEvent(s.sub[gi - 1], s.ev_fork, 0));
+        }
+        for (size_t gi = 0; gi < ng; ++gi) {
+            const SwbLaunchGroup &g = groups[pass][gi];
+            cudaStream_t st = gi == 0 ? s.stream : s.sub[gi - 1];
+            p.ntiles = g.ntiles;
+            for (int r = 0; r < SWB_MAX_RANGES; ++r) {
+                p.range_start[r] = g.range_start[r];
+                p.range_cum[r] = g.range_cum[r];
+            }
+            for (size_t c = 0; c < qp[pass].chunks.size(); ++c) {
+                const SwbQueryChunk &ch = qp[pass].chunks[c];
+                LaunchShape ls;
+                int rc = shape_for(e, g.K, i32, swb_group_smem_rows(ch.rows, g), g.ntiles, ls);
+                if (rc != SWB_OK) return rc;
+                p.row0 = ch.row0;
+                p.rows = ch.rows;
+                p.smem_rows = ls.smem_rows;
+                p.first_chunk = ch.first;
+                p.last_chunk = ch.last;
+                p.counter = s.d_counters + counter++;
+                CU(swb_launch_score(g.K, i32, ls.block_cfg, p, ls.grid, ls.smem, st));
+                e->stats.kernel_launches += 1;
+            }
+        }
+        // join
+        for (size_t gi = 1; gi < ng; ++gi) {
+            CU(cudaEventRecord(s.ev_sub[gi - 1], s.sub[gi - 1]));
+            CU(cudaStreamWaitEvent(s.stream, s.ev_sub[gi - 1], 0));
         }
     }
     CU(swb_launch_scatter(s.d_sorted, e->d_out_pos, nl, out, s.stream));
     e->stats.kernel_launches += 1;
-    e->stats.last_k = (uint32_t)qp[0].K;
+    e->stats.last_k = (uint32_t)qp[0].k_by_logg[0];
     for (int l = 0; l <= SWB_MAX_LOGG; ++l)
-        e->stats.padded_cells += pl.cols_by_logg[l] * (uint64_t)swb_roundup(qlen, (uint32_t)qp[0].K << l);
+        e->stats.padded_cells += pl.cols_by_logg[l] * (uint64_t)swb_roundup(qlen, (uint32_t)qp[0].k_by_logg[l] << l);
     e->stats.cells += (uint64_t)qlen * pl.residues_local;
     return SWB_OK;
 }
@@ -591,6 +630,7 @@ extern "C" int swb_search_batch(swb_engine *e, const uint8_t *qcodes, const uint
     e->stats.kernel_launches = 0;
     e->stats.recomputed_tiles = 0;
     e->last_nq = nq;
+    e->cur_nq = nq;
     const int ns = e->nslots;
     CU(cudaEventRecord(e->ev_start, ms));
     CU(cudaEventRecord(e->ev_fork, ms));

@@ -63,16 +63,16 @@ __global__ void __launch_bounds__(NT, MINB) swb_score_kernel(const SwbScoreParam
     swb_warp_loop<K, V>(be, p, sprof, sstride);
 }
 
-// profile[code][r] = S(q_r, code) + gap for r < qlen, gap (score 0) for the padding rows.
+// profile[code][r] = S(q_r, code) + bias for r < qlen, bias (score 0) for the padding rows; bias = gap + t0.
 __global__ void swb_profile_kernel(const uint8_t *__restrict__ q, uint32_t qlen, const int8_t *__restrict__ mat,
-                                   int gap, int8_t *__restrict__ prof, uint32_t stride, uint32_t rows)
+                                   int bias, int8_t *__restrict__ prof, uint32_t stride, uint32_t rows)
 {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= rows) return;
     const uint32_t qc = r < qlen ? (uint32_t)(q[r] & 31u) : (uint32_t)SWB_PAD;
 #pragma unroll 4
     for (uint32_t code = 0; code < SWB_ALPHA; ++code)
-        prof[(size_t)code * stride + r] = (int8_t)(mat[qc * SWB_ALPHA + code] + gap);
+        prof[(size_t)code * stride + r] = (int8_t)(mat[qc * SWB_ALPHA + code] + bias);
 }
 
 // One block per tile (grid-stride): gathers the tile's sequences from the raw concatenated codes into
@@ -112,67 +112,59 @@ static cudaError_t launch_one(const SwbScoreParams &p, int grid, size_t smem, cu
     return cudaGetLastError();
 }
 
-template <int K, class V>
-static cudaError_t launch_k(const SwbScoreParams &p, int block_cfg, int grid, size_t smem, cudaStream_t st)
+template <int K, class V, int NT, int MINB>
+static cudaError_t occ_one(size_t smem, int *blocks)
 {
-    if (block_cfg == SWB_BLOCK_SMALL) return launch_one<K, V, SWB_NT_SMALL, SWB_MINB_SMALL>(p, grid, smem, st);
-    return launch_one<K, V, SWB_NT_LARGE, 1>(p, grid, smem, st);
+    auto kern = swb_score_kernel<K, V, NT, MINB>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, kern, NT, smem);
+}
+
+// op: 0 = launch, 1 = occupancy query
+template <int K, class V>
+static cudaError_t dispatch_cfg(int op, int block_cfg, const SwbScoreParams *p, int grid, size_t smem, cudaStream_t st,
+                                int *blocks)
+{
+    if (block_cfg == SWB_BLOCK_SMALL)
+        return op == 0 ? launch_one<K, V, SWB_NT_SMALL, SWB_MINB_SMALL>(*p, grid, smem, st)
+                       : occ_one<K, V, SWB_NT_SMALL, SWB_MINB_SMALL>(smem, blocks);
+    return op == 0 ? launch_one<K, V, SWB_NT_LARGE, 1>(*p, grid, smem, st) : occ_one<K, V, SWB_NT_LARGE, 1>(smem, blocks);
+}
+
+static cudaError_t dispatch(int op, int K, bool i32, int block_cfg, const SwbScoreParams *p, int grid, size_t smem,
+                            cudaStream_t st, int *blocks)
+{
+    if (!i32) {
+        switch (K) {
+        case 8: return dispatch_cfg<8, V16>(op, block_cfg, p, grid, smem, st, blocks);
+        case 16: return dispatch_cfg<16, V16>(op, block_cfg, p, grid, smem, st, blocks);
+        case 32: return dispatch_cfg<32, V16>(op, block_cfg, p, grid, smem, st, blocks);
+        }
+    } else {
+        switch (K) {
+        case 8: return dispatch_cfg<8, V32>(op, block_cfg, p, grid, smem, st, blocks);
+        case 16: return dispatch_cfg<16, V32>(op, block_cfg, p, grid, smem, st, blocks);
+        }
+    }
+    return cudaErrorInvalidValue;
 }
 
 cudaError_t swb_launch_score(int K, bool i32, int block_cfg, const SwbScoreParams &p, int grid, size_t smem,
                              cudaStream_t st)
 {
-    if (!i32) {
-        switch (K) {
-        case 8: return launch_k<8, V16>(p, block_cfg, grid, smem, st);
-        case 16: return launch_k<16, V16>(p, block_cfg, grid, smem, st);
-        case 32: return launch_k<32, V16>(p, block_cfg, grid, smem, st);
-        }
-    } else {
-        switch (K) {
-        case 8: return launch_k<8, V32>(p, block_cfg, grid, smem, st);
-        case 16: return launch_k<16, V32>(p, block_cfg, grid, smem, st);
-        }
-    }
-    return cudaErrorInvalidValue;
-}
-
-template <int K, class V>
-static cudaError_t occ_k(int block_cfg, size_t smem, int *blocks)
-{
-    if (block_cfg == SWB_BLOCK_SMALL) {
-        auto kern = swb_score_kernel<K, V, SWB_NT_SMALL, SWB_MINB_SMALL>;
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, kern, SWB_NT_SMALL, smem);
-    }
-    auto kern = swb_score_kernel<K, V, SWB_NT_LARGE, 1>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, kern, SWB_NT_LARGE, smem);
+    return dispatch(0, K, i32, block_cfg, &p, grid, smem, st, nullptr);
 }
 
 cudaError_t swb_score_occupancy(int K, bool i32, int block_cfg, size_t smem, int *blocks)
 {
-    if (!i32) {
-        switch (K) {
-        case 8: return occ_k<8, V16>(block_cfg, smem, blocks);
-        case 16: return occ_k<16, V16>(block_cfg, smem, blocks);
-        case 32: return occ_k<32, V16>(block_cfg, smem, blocks);
-        }
-    } else {
-        switch (K) {
-        case 8: return occ_k<8, V32>(block_cfg, smem, blocks);
-        case 16: return occ_k<16, V32>(block_cfg, smem, blocks);
-        }
-    }
-    return cudaErrorInvalidValue;
+    return dispatch(1, K, i32, block_cfg, nullptr, 0, smem, nullptr, blocks);
 }
 
-cudaError_t swb_launch_profile(const uint8_t *q, uint32_t qlen, const int8_t *mat, int gap, int8_t *prof,
+cudaError_t swb_launch_profile(const uint8_t *q, uint32_t qlen, const int8_t *mat, int bias, int8_t *prof,
                                uint32_t stride, uint32_t rows, cudaStream_t st)
 {
-    swb_profile_kernel<<<(rows + 255) / 256, 256, 0, st>>>(q, qlen, mat, gap, prof, stride, rows);
+    swb_profile_kernel<<<(rows + 255) / 256, 256, 0, st>>>(q, qlen, mat, bias, prof, stride, rows);
     return cudaGetLastError();
 }
 

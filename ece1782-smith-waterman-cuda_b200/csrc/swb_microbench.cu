@@ -35,6 +35,16 @@ __global__ void __launch_bounds__(256) swb_mb_kernel(uint32_t *out, uint32_t see
             }
             if (KIND == 6) x[c] = x[c] * one + b;  // IMAD alone
             if (KIND == 7) x[c] = max(x[c] + b, a);  // scalar add+max (what the compiler makes of int32 cells)
+            if (KIND == 8) {  // the biased policy's mix: prmt, vimax3, viaddmax, 1/2 vimax3 (ALU) + 3 imad (FMA)
+                uint32_t s, ds, l3;
+                asm volatile("prmt.b32 %0, %1, %2, 0xD591;" : "=r"(s) : "r"(x[c]), "r"(b));
+                asm volatile("mad.lo.u32 %0, %1, %2, %3;" : "=r"(ds) : "r"(x[c]), "r"(one), "r"(s));
+                asm volatile("mad.lo.u32 %0, %1, %2, %3;" : "=r"(l3) : "r"(x[c]), "r"(one), "r"(b));
+                const uint32_t cc = __vimax3_s16x2(ds, l3, a);
+                x[c] = __viaddmax_s16x2(x[c], b, cc);
+                asm volatile("mad.lo.u32 %0, %1, %2, %3;" : "=r"(x[c]) : "r"(x[c]), "r"(one), "r"(b));
+                if (c & 1) x[c] = __vimax3_s16x2(x[c], x[c - 1], cc);
+            }
         }
     }
     uint32_t r = 0;
@@ -43,14 +53,14 @@ __global__ void __launch_bounds__(256) swb_mb_kernel(uint32_t *out, uint32_t see
     if (r == 0x12345678u) out[0] = r;
 }
 
-static const double kInstrPerIter[8] = {MB_CHAINS, MB_CHAINS, MB_CHAINS, MB_CHAINS, MB_CHAINS * 4.5, MB_CHAINS * 2.0,
-                                        MB_CHAINS, MB_CHAINS};
+static const double kInstrPerIter[9] = {MB_CHAINS, MB_CHAINS, MB_CHAINS, MB_CHAINS, MB_CHAINS * 4.5, MB_CHAINS * 2.0,
+                                        MB_CHAINS, MB_CHAINS, MB_CHAINS * 6.5};
 
-// kind 0 viaddmax.relu, 1 vimax3, 2 vadd2, 3 prmt, 4 score-kernel mix, 5 viaddmax+imad, 6 imad, 7 scalar add/max.
+// kind 0 viaddmax.relu, 1 vimax3, 2 vadd2, 3 prmt, 4 V16 mix, 5 viaddmax+imad, 6 imad, 7 scalar add/max, 8 V16B mix.
 // Returns giga lane-instructions per second (warp instructions x 32) over the whole GPU.
 extern "C" int swb_microbench(int device, int kind, double *glane_instr_per_s, double *ms_out)
 {
-    if (kind < 0 || kind > 7 || !glane_instr_per_s) return SWB_ERR_ARG;
+    if (kind < 0 || kind > 8 || !glane_instr_per_s) return SWB_ERR_ARG;
     if (cudaSetDevice(device) != cudaSuccess) return SWB_ERR_CUDA;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return SWB_ERR_CUDA;
@@ -71,7 +81,8 @@ extern "C" int swb_microbench(int device, int kind, double *glane_instr_per_s, d
         case 4: swb_mb_kernel<4><<<grid, block>>>(d, 7u + rep, iters); break;
         case 5: swb_mb_kernel<5><<<grid, block>>>(d, 7u + rep, iters); break;
         case 6: swb_mb_kernel<6><<<grid, block>>>(d, 7u + rep, iters); break;
-        default: swb_mb_kernel<7><<<grid, block>>>(d, 7u + rep, iters); break;
+        case 7: swb_mb_kernel<7><<<grid, block>>>(d, 7u + rep, iters); break;
+        default: swb_mb_kernel<8><<<grid, block>>>(d, 7u + rep, iters); break;
         }
         cudaEventRecord(e1);
         if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(d); return SWB_ERR_CUDA; }

@@ -106,10 +106,15 @@ int swb_build_plan(const uint64_t *offsets, uint32_t n, uint32_t shard, uint32_t
         plan.tiles_by_logg[t.logG]++;
         pair += t.npairs;
     }
-    // longest-per-lane first: the dynamic scheduler then behaves like LPT list scheduling
-    std::stable_sort(plan.tiles.begin(), plan.tiles.end(), [](const SwbTile &a, const SwbTile &b) {
-        return ((uint64_t)a.width >> a.logG) > ((uint64_t)b.width >> b.logG);
-    });
+    // The walk above already produced the order the kernels want: group sizes from 32 lanes down to 1, longest
+    // tile first inside each, so a launch that takes its tiles in array order behaves like LPT list scheduling.
+    {
+        uint32_t at = 0;
+        for (int l = SWB_MAX_LOGG; l >= 0; --l) {
+            plan.tile_start_by_logg[l] = at;
+            at += plan.tiles_by_logg[l];
+        }
+    }
     uint64_t res = 0, bnd = 0;
     for (size_t i = 0; i < plan.tiles.size(); ++i) {
         SwbTile &t = plan.tiles[i];
@@ -126,21 +131,85 @@ int swb_build_plan(const uint64_t *offsets, uint32_t n, uint32_t shard, uint32_t
     return 0;
 }
 
-void swb_plan_query(uint32_t qlen, int K, int max_logg, uint32_t chunk_rows, SwbQueryPlan &qp)
+void swb_plan_query(uint32_t qlen, int k_force, int k_max, uint32_t logg_present, uint32_t chunk_rows,
+                    SwbQueryPlan &qp)
 {
-    qp.K = K;
     qp.chunks.clear();
     qp.prof_rows = 0;
-    const uint32_t gran = (uint32_t)K << max_logg;
+    qp.k_pack = 0;
     const uint32_t nchunks = (qlen + chunk_rows - 1) / chunk_rows;
+    // rows the dominant chunk has: all chunks but the last are chunk_rows long
+    const uint32_t typical = nchunks > 1 ? chunk_rows : qlen;
+    for (int l = 0; l <= SWB_MAX_LOGG; ++l) {
+        int best_k = std::min(32, k_max);
+        if (k_force) {
+            best_k = std::min(k_force, k_max);
+        } else {
+            double best = 0;
+            for (int K = std::min(32, k_max); K >= 8; K >>= 1) {
+                // padded rows x per-column overhead of a short strip (shuffles, address math, boundary I/O)
+                const double cost = (double)swb_roundup(typical, (uint32_t)K << l) * (1.0 + 4.0 / K);
+                if (K == std::min(32, k_max) || cost < best) { best = cost; best_k = K; }
+            }
+        }
+        qp.k_by_logg[l] = best_k;
+        qp.k_pack |= (uint32_t)(best_k == 8 ? 0 : best_k == 16 ? 1 : 2) << (4 * l);
+    }
     for (uint32_t c = 0; c < nchunks; ++c) {
         SwbQueryChunk ch;
         ch.row0 = c * chunk_rows;
         ch.rows = std::min(chunk_rows, qlen - ch.row0);
-        ch.smem_rows = swb_roundup(swb_roundup(ch.rows, gran), 128);
+        uint32_t need = ch.rows;
+        for (int l = 0; l <= SWB_MAX_LOGG; ++l)
+            if (logg_present & (1u << l)) need = std::max(need, swb_roundup(ch.rows, (uint32_t)qp.k_by_logg[l] << l));
+        ch.smem_rows = swb_roundup(need, 128);
         ch.first = c == 0;
         ch.last = c + 1 == nchunks;
         qp.chunks.push_back(ch);
         qp.prof_rows = std::max(qp.prof_rows, ch.row0 + ch.smem_rows);
     }
+}
+
+void swb_plan_launch_groups(const SwbPlan &plan, const SwbQueryPlan &qp, bool longest_first,
+                            std::vector<SwbLaunchGroup> &groups)
+{
+    groups.clear();
+    for (int K = 32; K >= 8; K >>= 1) {
+        SwbLaunchGroup g;
+        memset(&g, 0, sizeof g);
+        g.K = K;
+        uint32_t nr = 0;
+        for (int l = SWB_MAX_LOGG; l >= 0; --l) {
+            if (!plan.tiles_by_logg[l] || qp.k_by_logg[l] != K) continue;
+            g.logg_mask |= 1u << l;
+            g.range_start[nr] = plan.tile_start_by_logg[l];
+            g.ntiles += plan.tiles_by_logg[l];
+            g.range_cum[nr] = g.ntiles;
+            ++nr;
+        }
+        if (!nr) continue;
+        for (uint32_t r = nr; r < SWB_MAX_RANGES; ++r) {  // unused ranges can never be selected
+            g.range_start[r] = 0;
+            g.range_cum[r] = g.ntiles;
+        }
+        groups.push_back(g);
+    }
+    // launch order. longest_first (a lone query): the group that owns the largest group size, i.e. the longest
+    // tiles, goes first and the bulk last; a small group occupies few blocks, so the bulk still finds room and runs
+    // beside it, and the long tiles are not left for the end. Otherwise (a batch: the next query fills the GPU
+    // while this one drains) the bulk goes first.
+    if (longest_first)
+        std::stable_sort(groups.begin(), groups.end(),
+                         [](const SwbLaunchGroup &a, const SwbLaunchGroup &b) { return a.logg_mask > b.logg_mask; });
+    else
+        std::stable_sort(groups.begin(), groups.end(),
+                         [](const SwbLaunchGroup &a, const SwbLaunchGroup &b) { return a.ntiles > b.ntiles; });
+}
+
+uint32_t swb_group_smem_rows(uint32_t rows, const SwbLaunchGroup &g)
+{
+    uint32_t need = rows;
+    for (int l = 0; l <= SWB_MAX_LOGG; ++l)
+        if (g.logg_mask & (1u << l)) need = std::max(need, swb_roundup(rows, (uint32_t)g.K << l));
+    return swb_roundup(need, 128);
 }

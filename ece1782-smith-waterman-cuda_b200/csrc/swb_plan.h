@@ -20,7 +20,7 @@ struct SwbPlan {
     std::vector<uint32_t> shard_ids;  // [n_local] DB ids in output order (ascending)
     std::vector<uint64_t> seq_off;    // [n_local] offset of sorted entry s in the raw code buffer
     std::vector<uint32_t> seq_len;    // [n_local]
-    std::vector<SwbTile> tiles;       // longest-per-lane first
+    std::vector<SwbTile> tiles;       // by group size (32 lanes per pair first), longest first inside a group size
     uint64_t res_bytes;               // packed residue buffer size
     uint64_t bnd_elems;               // boundary scratch elements
     uint64_t residues_local;          // true residues of this shard
@@ -28,6 +28,7 @@ struct SwbPlan {
     uint64_t padded_cols;             // sum over tiles of width * slots * 2 (cells per query row incl. padding)
     uint32_t max_len;                 // longest sequence of the shard
     uint32_t tiles_by_logg[SWB_MAX_LOGG + 1];
+    uint32_t tile_start_by_logg[SWB_MAX_LOGG + 1];  // tiles are stored by group size, 32 lanes first
     uint64_t cols_by_logg[SWB_MAX_LOGG + 1];  // padded sequence-columns (width * slots * 2) per group size
 };
 
@@ -35,17 +36,37 @@ struct SwbPlan {
 int swb_build_plan(const uint64_t *offsets, uint32_t n, uint32_t shard, uint32_t nshards, const SwbPlanOpts &o,
                    SwbPlan &plan);
 
-// How one query is cut into score-kernel launches ("chunks" of query rows that fit shared memory).
+// How one query is cut into score-kernel launches ("chunks" of query rows that fit shared memory), and how many
+// query rows a lane holds for each group size.
 struct SwbQueryChunk {
     uint32_t row0;       // first query row
     uint32_t rows;       // query rows of the chunk
-    uint32_t smem_rows;  // rows staged per code (covers the largest group's padding, multiple of 128)
+    uint32_t smem_rows;  // rows staged per code (covers the padding of every group size, multiple of 128)
     uint32_t first, last;
 };
 struct SwbQueryPlan {
-    int K;
-    uint32_t prof_rows;  // rows the global profile must provide (rows beyond qlen score 0)
+    int k_by_logg[SWB_MAX_LOGG + 1];  // rows per lane (8, 16 or 32) for tiles of 1 << l lanes per pair
+    uint32_t k_pack;                  // the same, 4 bits per group size: K = 8 << nibble
+    uint32_t prof_rows;               // rows the global profile must provide (rows beyond qlen score 0)
     std::vector<SwbQueryChunk> chunks;
 };
-// chunk_rows must be a multiple of 32 * 32 (all K <= 32 and group sizes then tile it exactly)
-void swb_plan_query(uint32_t qlen, int K, int max_logg, uint32_t chunk_rows, SwbQueryPlan &qp);
+// k_force: 0 = choose per group size (least padded rows, which is also the shortest tile time), else 8/16/32.
+// k_max: 32 for the s16 passes, 16 for the int32 pass. logg_present: bit l set when the plan has tiles of that
+// group size. chunk_rows must be a multiple of 1024 (every K << l divides it).
+void swb_plan_query(uint32_t qlen, int k_force, int k_max, uint32_t logg_present, uint32_t chunk_rows,
+                    SwbQueryPlan &qp);
+
+// One score-kernel launch of a query pass: the tiles of all group sizes that share the same K.
+struct SwbLaunchGroup {
+    int K;
+    uint32_t logg_mask;
+    uint32_t ntiles;
+    uint32_t range_start[SWB_MAX_RANGES];
+    uint32_t range_cum[SWB_MAX_RANGES];
+};
+// one group per distinct K; longest_first puts the group owning the longest tiles first (lone query), otherwise the
+// group with most tiles first (batch); inside a group the ranges run from the largest group size (longest tiles) down
+void swb_plan_launch_groups(const SwbPlan &plan, const SwbQueryPlan &qp, bool longest_first,
+                            std::vector<SwbLaunchGroup> &groups);
+// rows a launch group must find in shared memory for a chunk of `rows` query rows (multiple of 128)
+uint32_t swb_group_smem_rows(uint32_t rows, const SwbLaunchGroup &g);

@@ -7,6 +7,7 @@
 #define SWB_STAR 24           // '*' / unknown (SWSolver.cu:41, 119 of the reference)
 #define SWB_COLS_PER_CHUNK 4  // DB columns per residue / boundary chunk
 #define SWB_MAX_LOGG 5        // lane-group sizes 1,2,4,8,16,32
+#define SWB_MAX_RANGES 6      // tile ranges per launch (one per lane-group size)
 
 #if defined(__CUDACC__)
 #define SWB_HD __host__ __device__ __forceinline__
@@ -28,11 +29,11 @@ struct SwbTile {
 };
 
 struct SwbScoreParams {
-    const SwbTile *tiles;
-    uint32_t ntiles;
+    const SwbTile *tiles;     // all tiles of the shard, grouped by lane-group size, longest first
+    uint32_t ntiles;          // tiles covered by this launch (sum of its ranges)
     const uint8_t *residues;
     void *bnd;                // boundary scratch (uint32 per element for s16x2, 2x int32 for i32)
-    const int8_t *profile;    // global query profile [32][prof_stride], entry = S(q_row, code) + gap
+    const int8_t *profile;    // global query profile [32][prof_stride], entry = S(q_row, code) + gap + t0
     uint32_t prof_stride;     // bytes per code row in global memory
     uint32_t row0;            // first query row of this launch (query chunk)
     uint32_t rows;            // query rows of this chunk that carry real residues or padding to use
@@ -46,6 +47,10 @@ struct SwbScoreParams {
     uint32_t *recount;        // i32 recompute: number of tiles re-scored (may be null)
     int32_t gap;
     int32_t ovf_thr;          // s16: best > ovf_thr  =>  recompute in int32
+    int32_t t0;               // profile entries are S + gap + t0 (always 0 at present)
+    // tiles of this launch: positions [0, ntiles) of the concatenation of up to SWB_MAX_RANGES ranges of `tiles`
+    uint32_t range_start[SWB_MAX_RANGES];
+    uint32_t range_cum[SWB_MAX_RANGES];  // cumulative tile count up to and including range r
 };
 
 SWB_HD uint32_t swb_roundup(uint32_t v, uint32_t m) { return (v + m - 1) / m * m; }

@@ -4,21 +4,25 @@
 // Recurrence (reference: src/SWSolver.cu:246, src/cpu.cpp:45-72), linear gap g:
 //     H(i,j) = max(0, H(i-1,j-1) + S(q_i, d_j), H(i,j-1) - g, H(i-1,j) - g),   score = max H
 // restated so that the serial chain down a column is ONE fused op per cell:
-//     c(i,j) = max(0, [H(i-1,j-1)-g] + [S+g], [H(i,j-1)-g])      off the chain   (viaddmax.relu)
+//     c(i,j) = max(0, H(i-1,j-1) + S, H(i,j-1) - g)               off the chain
 //     H(i,j) = max(H(i-1,j) - g, c(i,j))                          on the chain    (viaddmax)
-//     store H(i,j)-g for the next column                          off the chain   (vadd)
-// With V16 both halves of a 32-bit word carry two different DB sequences (packed s16x2, DPX
-// instructions); with V32 the same program runs on two int32 lanes (exact recompute path).
+//
+// Two arithmetic policies run the same program:
+//   V16   two DB sequences in the halves of a 32-bit word, signed s16x2 DPX instructions
+//         (prmt, viaddmax.relu, viaddmax, vadd2, 1/2 vimax3 = 4.5 ALU-pipe instructions per cell pair)
+//   V32   two int32 lanes; exact for any score; used to re-score tiles flagged by the s16 pass.
+// (A third policy that moved the additions to the FMA pipe as IMADs in a biased domain was measured
+//  slower on B200 -- register-file operand bandwidth, see DESIGN.md -- and was removed.)
 //
 // Work split: a lane keeps K consecutive query rows in registers ("strip") and walks along the DB
 // columns. G lanes of a group hold G consecutive strips and run a wavefront: lane g works on column
 // t-g at step t and hands its bottom H and the residue pair to lane g+1 by __shfl_up_sync. Rows beyond
 // K*G are covered by further passes ("super-strips"); the row between two passes goes through the
 // boundary scratch in global memory. G = 1 is the pure inter-task case (no shuffles), G = 32 the
-// intra-task warp wavefront for long sequences.
+// intra-task warp wavefront for long sequences. K is chosen per group size and query on the host.
 //
 // The same source is compiled for the device (DevBackend, swb_kernels.cu) and, for CPU validation of
-// the indexing / wavefront logic, for the host with a thread-per-lane backend (tests/emu). The host
+// the indexing / wavefront logic, for the host with a fiber-per-lane backend (tests/emu). The host
 // build is test infrastructure only and is never linked into libswb.so.
 #pragma once
 #include <cuda_runtime.h>
@@ -47,22 +51,11 @@ SWB_HD uint32_t swb_prmt(uint32_t a, uint32_t b, uint32_t sel)
 }
 
 // ---------------------------------------------------------------------------------------------
-// V16: two sequences per 32-bit word, signed 16-bit halves, DPX / video SIMD instructions.
-struct V16 {
+// shared pieces of the packed-s16 policy
+struct V16Base {
     typedef uint32_t T;
     static const bool is16 = true;
-    static SWB_HD T zero() { return 0u; }
     static SWB_HD T splat(int v) { uint32_t u = (uint32_t)v & 0xffffu; return u | (u << 16); }
-    static SWB_HD T add(T a, T b)
-    {
-#ifdef __CUDA_ARCH__
-        return __vadd2(a, b);
-#else
-        return ((a + b) & 0xffffu) | ((((a >> 16) + (b >> 16)) & 0xffffu) << 16);
-#endif
-    }
-    static SWB_HD T addmax(T a, T b, T c) { return __viaddmax_s16x2(a, b, c); }
-    static SWB_HD T addmax_relu(T a, T b, T c) { return __viaddmax_s16x2_relu(a, b, c); }
     static SWB_HD T max2(T a, T b)
     {
 #ifdef __CUDA_ARCH__
@@ -71,14 +64,10 @@ struct V16 {
         return __vimax3_s16x2(a, b, b);
 #endif
     }
-    static SWB_HD T max3(T a, T b, T c) { return __vimax3_s16x2(a, b, c); }
-    // scores of profile byte i (0..3) of the A word and of the B word, sign-extended into one s16x2
-    template <int I> static SWB_HD T pair(uint32_t wa, uint32_t wb)
-    {
-        return swb_prmt(wa, wb, 0xC480u + 0x1111u * I);
-    }
     static SWB_HD int lo(T v) { return (int)(int16_t)(v & 0xffffu); }
     static SWB_HD int hi(T v) { return (int)(int16_t)(v >> 16); }
+    // profile byte I (0..3) of the A word and of the B word, sign-extended into one s16x2
+    template <int I> static SWB_HD T pair(uint32_t wa, uint32_t wb) { return swb_prmt(wa, wb, 0xC480u + 0x1111u * I); }
     template <class BE> static SWB_HD T shfl_up(BE &be, T v, int d, int w) { return be.shfl_up(v, d, w); }
     template <class BE> static SWB_HD T shfl_xor(BE &be, T v, int m, int w) { return be.shfl_xor(v, m, w); }
     template <class BE> static SWB_HD T ld(BE &be, const T *p) { return be.ld_cg(p); }
@@ -94,28 +83,99 @@ struct V16 {
     }
 };
 
+// ---------------------------------------------------------------------------------------------
+// V16: plain signed domain. Stored per row: H(k, j-1) - g. Profile entry: S + g.
+//   c = viaddmax.relu(diag-g, S+g, left-g) ; h = viaddmax(h, -g, c) ; left' = vadd2(h, -g)
+struct V16 : V16Base {
+    struct C { T negg; };
+    static SWB_HD C consts(const SwbScoreParams &p) { C c; c.negg = splat(-p.gap); return c; }
+    static SWB_HD T hzero(const C &) { return 0u; }
+    static SWB_HD T lzero(const C &c) { return c.negg; }
+    static SWB_HD int score_lo(T best, const C &) { return lo(best); }
+    static SWB_HD int score_hi(T best, const C &) { return hi(best); }
+    static SWB_HD T add(T a, T b)
+    {
+#ifdef __CUDA_ARCH__
+        return __vadd2(a, b);
+#else
+        return ((a + b) & 0xffffu) | ((((a >> 16) + (b >> 16)) & 0xffffu) << 16);
+#endif
+    }
+    // one DB column against the K rows of this lane; returns the bottom H
+    template <int K>
+    static SWB_HD T column(T up, T &diag0, T (&left)[K], T &best, const C &cst, uint32_t res, const int8_t *prow,
+                           uint32_t sstride)
+    {
+        const uint32_t *ra = reinterpret_cast<const uint32_t *>(prow + (res & 0xffu) * sstride);
+        const uint32_t *rb = reinterpret_cast<const uint32_t *>(prow + (res >> 8) * sstride);
+        T h = up;
+        T dg = diag0;
+        diag0 = add(up, cst.negg);
+#pragma unroll
+        for (int k4 = 0; k4 < K / 4; ++k4) {
+            const uint32_t wa = ra[k4];
+            const uint32_t wb = rb[k4];
+            T c[4];
+#define SWB_CELL(I)                                                        \
+    {                                                                      \
+        const T s = pair<I>(wa, wb);                                       \
+        c[I] = __viaddmax_s16x2_relu(dg, s, left[4 * k4 + I]);             \
+        dg = left[4 * k4 + I];                                             \
+        h = __viaddmax_s16x2(h, cst.negg, c[I]);                           \
+        left[4 * k4 + I] = add(h, cst.negg);                               \
+    }
+            SWB_CELL(0) SWB_CELL(1)
+            best = __vimax3_s16x2(best, c[0], c[1]);
+            SWB_CELL(2) SWB_CELL(3)
+            best = __vimax3_s16x2(best, c[2], c[3]);
+#undef SWB_CELL
+        }
+        return h;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
 // V32: the same two sequences on two int32 lanes (no wrap for any realistic input).
 struct V32 {
     struct T { int a, b; };
+    struct C { int g, t0; };
     static const bool is16 = false;
     static SWB_HD T mk(int a, int b) { T t; t.a = a; t.b = b; return t; }
-    static SWB_HD T zero() { return mk(0, 0); }
-    static SWB_HD T splat(int v) { return mk(v, v); }
     static SWB_HD int mx(int a, int b) { return a > b ? a : b; }
-    static SWB_HD T add(T a, T b) { return mk(a.a + b.a, a.b + b.b); }
-    static SWB_HD T addmax(T a, T b, T c) { return mk(mx(a.a + b.a, c.a), mx(a.b + b.b, c.b)); }
-    static SWB_HD T addmax_relu(T a, T b, T c)
-    {
-        return mk(mx(mx(a.a + b.a, c.a), 0), mx(mx(a.b + b.b, c.b), 0));
-    }
+    static SWB_HD C consts(const SwbScoreParams &p) { C c; c.g = p.gap; c.t0 = p.t0; return c; }
+    static SWB_HD T hzero(const C &) { return mk(0, 0); }
+    static SWB_HD T lzero(const C &c) { return mk(-c.g, -c.g); }
+    static SWB_HD int score_lo(T best, const C &) { return best.a; }
+    static SWB_HD int score_hi(T best, const C &) { return best.b; }
     static SWB_HD T max2(T a, T b) { return mk(mx(a.a, b.a), mx(a.b, b.b)); }
-    static SWB_HD T max3(T a, T b, T c) { return max2(max2(a, b), c); }
-    template <int I> static SWB_HD T pair(uint32_t wa, uint32_t wb)
+    template <int K>
+    static SWB_HD T column(T up, T &diag0, T (&left)[K], T &best, const C &cst, uint32_t res, const int8_t *prow,
+                           uint32_t sstride)
     {
-        return mk((int)(int8_t)(wa >> (8 * I)), (int)(int8_t)(wb >> (8 * I)));
+        const uint32_t *ra = reinterpret_cast<const uint32_t *>(prow + (res & 0xffu) * sstride);
+        const uint32_t *rb = reinterpret_cast<const uint32_t *>(prow + (res >> 8) * sstride);
+        T h = up;
+        T dg = diag0;
+        diag0 = mk(up.a - cst.g, up.b - cst.g);
+#pragma unroll
+        for (int k4 = 0; k4 < K / 4; ++k4) {
+            const uint32_t wa = ra[k4];
+            const uint32_t wb = rb[k4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                // profile entry = S + g + t0
+                const int sa = (int)(int8_t)(wa >> (8 * i)) - cst.t0;
+                const int sb = (int)(int8_t)(wb >> (8 * i)) - cst.t0;
+                const T l = left[4 * k4 + i];
+                const T c = mk(mx(mx(dg.a + sa, l.a), 0), mx(mx(dg.b + sb, l.b), 0));
+                dg = l;
+                h = mk(mx(h.a - cst.g, c.a), mx(h.b - cst.g, c.b));
+                left[4 * k4 + i] = mk(h.a - cst.g, h.b - cst.g);
+                best = max2(best, c);
+            }
+        }
+        return h;
     }
-    static SWB_HD int lo(T v) { return v.a; }
-    static SWB_HD int hi(T v) { return v.b; }
     template <class BE> static SWB_HD T shfl_up(BE &be, T v, int d, int w)
     {
         return mk((int)be.shfl_up((uint32_t)v.a, d, w), (int)be.shfl_up((uint32_t)v.b, d, w));
@@ -148,64 +208,8 @@ struct V32 {
 };
 
 // ---------------------------------------------------------------------------------------------
-// One DB column against the K query rows of this lane.
-//   up      H(top-1, j)            (plain)       from the lane above / boundary scratch / 0
-//   diag0g  H(top-1, j-1) - g      carried between columns
-//   leftg   H(k, j-1) - g          per row, updated in place
-//   prow    shared-memory profile, already offset to this lane's first row; code row stride sstride
-template <int K, class V>
-SWB_HD typename V::T swb_column(typename V::T up, typename V::T &diag0g, typename V::T (&leftg)[K],
-                                typename V::T &best, const typename V::T NEGG, uint32_t res,
-                                const int8_t *prow, uint32_t sstride)
-{
-    typedef typename V::T T;
-    const uint32_t *ra = reinterpret_cast<const uint32_t *>(prow + (res & 0xffu) * sstride);
-    const uint32_t *rb = reinterpret_cast<const uint32_t *>(prow + (res >> 8) * sstride);
-    T h = up;
-    T dg = diag0g;
-    diag0g = V::add(up, NEGG);
-#pragma unroll
-    for (int k4 = 0; k4 < K / 4; ++k4) {
-        const uint32_t wa = ra[k4];
-        const uint32_t wb = rb[k4];
-        T c0, c1, c2, c3;
-        {
-            const T s = V::template pair<0>(wa, wb);
-            c0 = V::addmax_relu(dg, s, leftg[4 * k4 + 0]);
-            dg = leftg[4 * k4 + 0];
-            h = V::addmax(h, NEGG, c0);
-            leftg[4 * k4 + 0] = V::add(h, NEGG);
-        }
-        {
-            const T s = V::template pair<1>(wa, wb);
-            c1 = V::addmax_relu(dg, s, leftg[4 * k4 + 1]);
-            dg = leftg[4 * k4 + 1];
-            h = V::addmax(h, NEGG, c1);
-            leftg[4 * k4 + 1] = V::add(h, NEGG);
-        }
-        best = V::max3(best, c0, c1);
-        {
-            const T s = V::template pair<2>(wa, wb);
-            c2 = V::addmax_relu(dg, s, leftg[4 * k4 + 2]);
-            dg = leftg[4 * k4 + 2];
-            h = V::addmax(h, NEGG, c2);
-            leftg[4 * k4 + 2] = V::add(h, NEGG);
-        }
-        {
-            const T s = V::template pair<3>(wa, wb);
-            c3 = V::addmax_relu(dg, s, leftg[4 * k4 + 3]);
-            dg = leftg[4 * k4 + 3];
-            h = V::addmax(h, NEGG, c3);
-            leftg[4 * k4 + 3] = V::add(h, NEGG);
-        }
-        best = V::max3(best, c2, c3);
-    }
-    return h;
-}
-
-// ---------------------------------------------------------------------------------------------
 // One tile, all query rows of the current chunk.
-// Boundary scratch layout (elements of V::T, base tile.bnd_off):
+// Boundary scratch layout (elements of V::T, base tile.bnd_off), values in the policy's h domain:
 //   G == 1 : [chunk c][lane][4 columns]   -> one 16/32-byte vector per lane and chunk
 //   G  > 1 : [column][slot]               -> scalar per step, touched by the first / last lane of a group
 template <int K, class V, bool GROUPED, class BE>
@@ -213,6 +217,9 @@ SWB_HD void swb_run_tile(BE &be, const SwbScoreParams &p, const SwbTile &tile, u
                          const int8_t *sprof, uint32_t sstride)
 {
     typedef typename V::T T;
+    const typename V::C cst = V::consts(p);
+    const T HZERO = V::hzero(cst);
+    const T LZERO = V::lzero(cst);
     const int lane = be.lane();
     const int logG = GROUPED ? (int)tile.logG : 0;
     const int G = 1 << logG;
@@ -229,26 +236,25 @@ SWB_HD void swb_run_tile(BE &be, const SwbScoreParams &p, const SwbTile &tile, u
     const uint8_t *res = p.residues + tile.res_off + (size_t)slot * 8u;
     const size_t res_stride = (size_t)P * 8u;
     T *bnd = reinterpret_cast<T *>(p.bnd) + tile.bnd_off;
-    const T NEGG = V::splat(-p.gap);
     const uint32_t PAD2 = (uint32_t)SWB_PAD | ((uint32_t)SWB_PAD << 8);
     const uint32_t PAD4 = PAD2 | (PAD2 << 16);
-    T best = V::zero();
+    T best = HZERO;
 
     for (uint32_t ss = 0; ss < nsuper; ++ss) {
         const int8_t *prow = sprof + (size_t)(((ss << logG) + (uint32_t)g) * (uint32_t)K);
         const bool read_top = !(p.first_chunk && ss == 0);
         const bool write_bot = !(p.last_chunk && ss + 1 == nsuper);
-        T leftg[K];
+        T left[K];
 #pragma unroll
-        for (int k = 0; k < K; ++k) leftg[k] = NEGG;
-        T diag0g = NEGG;
-        T hprev = V::zero();
+        for (int k = 0; k < K; ++k) left[k] = LZERO;
+        T diag0 = LZERO;
+        T hprev = HZERO;
         uint32_t resprev = PAD2;
 
         uint2 rc = make_uint2(PAD4, PAD4);
         T bc[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) bc[u] = V::zero();
+        for (int u = 0; u < 4; ++u) bc[u] = HZERO;
         if (lead && nchunks > 0) {
             rc = be.ld_res(reinterpret_cast<const uint2 *>(res));
             if (read_top) {
@@ -265,7 +271,7 @@ SWB_HD void swb_run_tile(BE &be, const SwbScoreParams &p, const SwbTile &tile, u
             uint2 rn = make_uint2(PAD4, PAD4);
             T bn[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) bn[u] = V::zero();
+            for (int u = 0; u < 4; ++u) bn[u] = HZERO;
             if (lead && c + 1 < nchunks) {
                 rn = be.ld_res(reinterpret_cast<const uint2 *>(res + (size_t)(c + 1) * res_stride));
                 if (read_top) {
@@ -288,7 +294,7 @@ SWB_HD void swb_run_tile(BE &be, const SwbScoreParams &p, const SwbTile &tile, u
                     const T u2 = V::shfl_up(be, hprev, 1, G);
                     if (!lead) { r = r2; up = u2; }
                 }
-                const T h = swb_column<K, V>(up, diag0g, leftg, best, NEGG, r, prow, sstride);
+                const T h = V::template column<K>(up, diag0, left, best, cst, r, prow, sstride);
                 outb[u] = h;
                 hprev = h;
                 resprev = r;
@@ -317,7 +323,7 @@ SWB_HD void swb_run_tile(BE &be, const SwbScoreParams &p, const SwbTile &tile, u
     bool flagged = false;
     if (lead && slot < (int)tile.npairs) {
         const size_t s0 = 2u * ((size_t)tile.first_pair + (size_t)slot);
-        int a = V::lo(best), b = V::hi(best);
+        int a = V::score_lo(best, cst), b = V::score_hi(best, cst);
         if (!p.first_chunk) {
             const int pa = p.scores[s0], pb = p.scores[s0 + 1];
             a = a > pa ? a : pa;
@@ -334,13 +340,19 @@ SWB_HD void swb_run_tile(BE &be, const SwbScoreParams &p, const SwbTile &tile, u
     }
 }
 
-// Per-warp loop over the dynamically scheduled tile list (tiles are sorted longest-first on the host).
+// Per-warp loop over the dynamically scheduled tiles of one launch. A launch covers up to SWB_MAX_RANGES
+// ranges of the tile array (the tiles of the group sizes that use this kernel's K for this query); the shared
+// counter hands out positions of the concatenated ranges, longest tiles first.
 template <int K, class V, class BE>
 SWB_HD void swb_warp_loop(BE &be, const SwbScoreParams &p, const int8_t *sprof, uint32_t sstride)
 {
     for (;;) {
-        const uint32_t ti = be.next_tile(p.counter);
-        if (ti >= p.ntiles) break;
+        const uint32_t v = be.next_tile(p.counter);
+        if (v >= p.ntiles) break;
+        uint32_t ti = p.range_start[0] + v;
+#pragma unroll
+        for (int r = 1; r < SWB_MAX_RANGES; ++r)
+            if (v >= p.range_cum[r - 1]) ti = p.range_start[r] + (v - p.range_cum[r - 1]);
         if (p.only_flagged && !be.ld_flag(p.flags + ti)) continue;
         const SwbTile tile = be.ld_tile(p.tiles + ti);
         if (tile.logG == 0)

@@ -71,7 +71,9 @@ void swb_destroy(swb_engine *e);
 /* e == NULL: error text of the last failed swb_create of this thread */
 const char *swb_last_error(const swb_engine *e);
 /* options: "group_len" (longest sequence handled by one lane per pair, default 384; set before db_load),
- *          "k" (query rows per lane: 0 = auto, 8, 16, 32), "streams" (concurrent queries of a batch, 1..4),
+ *          "k" (query rows per lane: 0 = chosen per lane-group size and query, else 8, 16, 32),
+ *          "streams" (concurrent queries of a batch, 1..4, default 3; set before db_load),
+ *          "group_order" (0 = auto, 1 = launch the long-sequence tiles first, 2 = launch the bulk first),
  *          "chunk_rows" (query rows per launch for queries beyond shared memory; multiple of 1024, <= 7168) */
 int swb_set_option(swb_engine *e, const char *key, int64_t value);
 /* run on the caller's CUDA stream (cudaStream_t as void*); NULL = the engine's own stream */
@@ -117,8 +119,9 @@ int swb_plan_describe(const uint64_t *offsets, uint32_t n, uint32_t shard, uint3
 
 /* ---- measurement support (not on the scoring path) ------------------------------------------- */
 /* Issue rate of the integer SIMD instructions the score kernel is built from, whole GPU, in giga
- * lane-instructions/s. kind: 0 viaddmax.s16x2.relu, 1 vimax3.s16x2, 2 vadd2, 3 prmt, 4 the score kernel's
- * per-cell mix, 5 viaddmax+imad, 6 imad, 7 scalar add+max. bench.py uses kind 4 as the roofline peak. */
+ * lane-instructions/s. kind: 0 viaddmax.s16x2.relu, 1 vimax3.s16x2, 2 vadd2, 3 prmt, 4 the score kernel's per-cell
+ * mix, 5 viaddmax+imad, 6 imad, 7 scalar add+max, 8 the mix of the (rejected) biased FMA-pipe variant. bench.py
+ * uses kind 4 (4.5 instructions per cell pair) as the roofline peak of the score kernel. */
 int swb_microbench(int device, int kind, double *glane_instr_per_s, double *ms);
 
 #ifdef __cplusplus

@@ -162,8 +162,9 @@ void lane_main(HostBackend &be, void *a)
 }  // namespace
 
 // Mirrors swb_db_load + one swb_search of the engine (same plan, same chunking, same kernel
-// parameters), with the kernels replaced by the fiber emulation. force_i32: 0 = s16 pass then int32
-// recompute of flagged tiles (the product flow), 1 = int32 pass over every tile.
+// parameters, same launch groups), with the kernels replaced by the fiber emulation. K: 0 = per-group choice of the
+// planner (the product default), else 8/16/32 for every group size. force_i32: 0 = s16 pass then int32 recompute of
+// flagged tiles (the product flow), 1 = int32 pass over every tile.
 // ovf_thr_override >= 0 replaces the s16 overflow threshold (lets tests force the recompute path).
 extern "C" int swbemu_search(const uint8_t *codes, const uint64_t *offsets, uint32_t n, uint32_t shard,
                              uint32_t nshards, uint32_t group_len, const int8_t *mat32, int gap, const uint8_t *q,
@@ -181,9 +182,9 @@ extern "C" int swbemu_search(const uint8_t *codes, const uint64_t *offsets, uint
         memset(scores_out, 0, sizeof(int32_t) * nl);
         return 0;
     }
-    int max_logg = 0;
+    uint32_t present = 0;
     for (int l = 0; l <= SWB_MAX_LOGG; ++l)
-        if (pl.tiles_by_logg[l]) max_logg = l;
+        if (pl.tiles_by_logg[l]) present |= 1u << l;
     const uint8_t *raw = codes;
     // pack (same function as the device pack kernel)
     std::vector<uint64_t> residues(pl.res_bytes / 8 + 1);
@@ -194,19 +195,27 @@ extern "C" int swbemu_search(const uint8_t *codes, const uint64_t *offsets, uint
         for (uint32_t i = 0; i < (t.width >> 2) * P; ++i)
             out[i] = swb_pack_word(t, i / P, i % P, raw, pl.seq_off.data(), pl.seq_len.data(), nl);
     }
-    int max_s = 0;
-    for (int i = 0; i < SWB_ALPHA * SWB_ALPHA; ++i) max_s = std::max<int>(max_s, mat32[i]);
+    int max_s = 0, min_s = 0;
+    for (int i = 0; i < SWB_ALPHA * SWB_ALPHA; ++i) {
+        max_s = std::max<int>(max_s, mat32[i]);
+        min_s = std::min<int>(min_s, mat32[i]);
+    }
+    const int t0 = 0;
+    (void)min_s;
     if (!chunk_rows) chunk_rows = 7168;
     SwbQueryPlan qp[2];
-    swb_plan_query(qlen, K, max_logg, chunk_rows, qp[0]);
-    swb_plan_query(qlen, std::min(K, 16), max_logg, chunk_rows, qp[1]);
+    std::vector<SwbLaunchGroup> groups[2];
+    swb_plan_query(qlen, K, 32, present, chunk_rows, qp[0]);
+    swb_plan_query(qlen, K, 16, present, chunk_rows, qp[1]);
+    swb_plan_launch_groups(pl, qp[0], true, groups[0]);
+    swb_plan_launch_groups(pl, qp[1], true, groups[1]);
     const uint32_t prof_rows = std::max(qp[0].prof_rows, qp[1].prof_rows);
     const uint32_t prof_stride = swb_roundup(prof_rows, 16);
     std::vector<int8_t> prof((size_t)prof_stride * SWB_ALPHA);
     for (uint32_t r = 0; r < prof_rows; ++r) {
         const uint32_t qc = r < qlen ? (q[r] & 31u) : (uint32_t)SWB_PAD;
         for (uint32_t code = 0; code < SWB_ALPHA; ++code)
-            prof[(size_t)code * prof_stride + r] = (int8_t)(mat32[qc * SWB_ALPHA + code] + gap);
+            prof[(size_t)code * prof_stride + r] = (int8_t)(mat32[qc * SWB_ALPHA + code] + gap + t0);
     }
     std::vector<int32_t> sorted(2 * (size_t)((nl + 1) / 2), 0);
     std::vector<uint8_t> flags(pl.tiles.size(), 0);
@@ -217,7 +226,6 @@ extern "C" int swbemu_search(const uint8_t *codes, const uint64_t *offsets, uint
     SwbScoreParams p;
     memset(&p, 0, sizeof p);
     p.tiles = pl.tiles.data();
-    p.ntiles = (uint32_t)pl.tiles.size();
     p.residues = reinterpret_cast<const uint8_t *>(residues.data());
     p.profile = prof.data();
     p.prof_stride = prof_stride;
@@ -226,34 +234,43 @@ extern "C" int swbemu_search(const uint8_t *codes, const uint64_t *offsets, uint
     p.recount = &recount;
     p.gap = gap;
     p.ovf_thr = ovf_thr_override >= 0 ? ovf_thr_override : 32767 - max_s;
+    p.t0 = t0;
     for (int pass = force_i32 ? 1 : 0; pass < 2; ++pass) {
         const bool i32 = pass == 1;
         p.bnd = i32 ? (void *)bnd32.data() : (void *)bnd16.data();
         p.only_flagged = (i32 && !force_i32) ? 1u : 0u;
-        for (size_t c = 0; c < qp[pass].chunks.size(); ++c) {
-            const SwbQueryChunk &ch = qp[pass].chunks[c];
-            p.row0 = ch.row0;
-            p.rows = ch.rows;
-            p.smem_rows = ch.smem_rows;
-            p.first_chunk = ch.first;
-            p.last_chunk = ch.last;
-            uint32_t counter = 0;
-            p.counter = &counter;
-            // stage the chunk's profile exactly like swb_score_kernel
-            const uint32_t sstride = ch.smem_rows + 4;
-            std::vector<int8_t> sprof((size_t)sstride * SWB_ALPHA + 16);
-            for (uint32_t code = 0; code < SWB_ALPHA; ++code)
-                memcpy(sprof.data() + (size_t)code * sstride, prof.data() + (size_t)code * prof_stride + ch.row0,
-                       ch.smem_rows);
-            LaneArgs la;
-            la.p = &p;
-            la.sprof = sprof.data();
-            la.sstride = sstride;
-            la.K = qp[pass].K;
-            la.i32 = i32;
-            WarpSim *w = new WarpSim();
-            w->run(lane_main, &la);
-            delete w;
+        for (size_t gi = 0; gi < groups[pass].size(); ++gi) {
+            const SwbLaunchGroup &g = groups[pass][gi];
+            p.ntiles = g.ntiles;
+            for (int r = 0; r < SWB_MAX_RANGES; ++r) {
+                p.range_start[r] = g.range_start[r];
+                p.range_cum[r] = g.range_cum[r];
+            }
+            for (size_t c = 0; c < qp[pass].chunks.size(); ++c) {
+                const SwbQueryChunk &ch = qp[pass].chunks[c];
+                p.row0 = ch.row0;
+                p.rows = ch.rows;
+                p.smem_rows = swb_group_smem_rows(ch.rows, g);
+                p.first_chunk = ch.first;
+                p.last_chunk = ch.last;
+                uint32_t counter = 0;
+                p.counter = &counter;
+                // stage the chunk's profile exactly like swb_score_kernel
+                const uint32_t sstride = p.smem_rows + 4;
+                std::vector<int8_t> sprof((size_t)sstride * SWB_ALPHA + 16);
+                for (uint32_t code = 0; code < SWB_ALPHA; ++code)
+                    memcpy(sprof.data() + (size_t)code * sstride, prof.data() + (size_t)code * prof_stride + ch.row0,
+                           p.smem_rows);
+                LaneArgs la;
+                la.p = &p;
+                la.sprof = sprof.data();
+                la.sstride = sstride;
+                la.K = g.K;
+                la.i32 = i32;
+                WarpSim *w = new WarpSim();
+                w->run(lane_main, &la);
+                delete w;
+            }
         }
     }
     for (uint32_t s = 0; s < nl; ++s) scores_out[pl.out_pos[s]] = sorted[s];

@@ -49,8 +49,10 @@ def emu():
     return search
 
 
-@pytest.mark.parametrize("K,group_len", [(8, 2000), (16, 384), (32, 384), (32, 64), (16, 16), (8, 16)])
+@pytest.mark.parametrize("K,group_len", [(0, 384), (8, 2000), (16, 384), (32, 384), (32, 64), (16, 16), (0, 16), (0, 64)])
 def test_subset_all_shapes(emu, oracle, subset, queries, K, group_len):
+    """K = 0 lets the planner pick the rows per lane per group size (the product default: one launch group per
+    distinct K)"""
     m = oracle.matrix("blosum50")
     q = oracle.encode(queries["P02232"])
     want = oracle.scan(q, subset["codes"], subset["offsets"], m)
@@ -80,7 +82,7 @@ def test_real_s16_overflow_is_caught(emu, oracle):
     codes, offs = pack_db(enc)
     want = oracle.scan(w, codes, offs, m)
     assert want[0] == 34500 and want[2] == 33000
-    got, rc = emu(codes, offs, m, w, K=32, group_len=384)
+    got, rc = emu(codes, offs, m, w, K=0, group_len=384)
     assert np.array_equal(got, want) and rc >= 1
 
 
@@ -93,7 +95,7 @@ def test_edges_ident3_and_shards(emu, oracle, subset, queries):
     for ql in (1, 8, 9, 33):
         q = rng.integers(0, 24, ql).astype(np.uint8)
         want = oracle.scan(q, codes, offs, m)
-        for K, gl in ((8, 8), (16, 16), (32, 384)):
+        for K, gl in ((8, 8), (16, 16), (32, 384), (0, 16)):
             got, _ = emu(codes, offs, m, q, K=K, group_len=gl)
             assert np.array_equal(got, want), (ql, K, gl)
     got, _ = emu(codes, offs, m, np.zeros(0, np.uint8), K=32)

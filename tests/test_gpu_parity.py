@@ -69,7 +69,8 @@ def test_ident3_matches_compiled_cpu_cpp(engine, swb, subset, queries):
 @pytest.mark.parametrize("k", [0, 8, 16, 32])
 @pytest.mark.parametrize("group_len", [16, 96, 384, 100000])
 def test_random_db_all_kernel_shapes(swb, oracle, k, group_len):
-    """every K and lane-group mix (group_len 16 forces 32-lane wavefronts, 100000 forces one lane per pair)"""
+    """every K (0 = per-group choice, several concurrent launch groups) and lane-group mix (group_len 16 forces
+    32-lane wavefronts, 100000 forces one lane per pair)"""
     rng = np.random.default_rng(1000 + k + group_len)
     lens = np.concatenate([rng.integers(0, 40, 70), rng.integers(40, 700, 300), rng.integers(700, 3000, 9), [0, 1, 2, 3]])
     rng.shuffle(lens)

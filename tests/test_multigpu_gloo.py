@@ -40,7 +40,7 @@ def _worker(rank, world, port, q):
         mine = np.zeros(info.n_local, dtype=np.int32)
         rc = ctypes.c_uint32()
         assert emu.swbemu_search(codes.ctypes.data_as(u8p), offs.ctypes.data_as(u64p), len(seqs), rank, world, 384,
-                                 m.ctypes.data_as(i8p), 2, query.ctypes.data_as(u8p), len(query), 32, 0, 0, -1,
+                                 m.ctypes.data_as(i8p), 2, query.ctypes.data_as(u8p), len(query), 0, 0, 0, -1,
                                  mine.ctypes.data_as(i32p), ctypes.byref(rc)) == 0
         order = np.lexsort((ids, -mine))[:10]
         parts = [None] * world

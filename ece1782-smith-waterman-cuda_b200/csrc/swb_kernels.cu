@@ -31,7 +31,7 @@ struct DevBackend {
         u.v[1] = __ldg(reinterpret_cast<const uint4 *>(p) + 1);
         return u.t;
     }
-    __device__ __forceinline__ uint2 ld_res(const uint2 *p) const { return __ldg(p); }
+    __device__ __forceinline__ uint32_t ld_code(const uint8_t *p) const { return (uint32_t)__ldg(p); }
     __device__ __forceinline__ uint32_t ld_cg(const uint32_t *p) const { return __ldcg(p); }
     __device__ __forceinline__ uint2 ld_cg2(const uint2 *p) const { return __ldcg(p); }
     __device__ __forceinline__ uint4 ld_cg4(const uint4 *p) const { return __ldcg(p); }

@@ -103,11 +103,11 @@ struct V16 : V16Base {
     }
     // one DB column against the K rows of this lane; returns the bottom H
     template <int K>
-    static SWB_HD T column(T up, T &diag0, T (&left)[K], T &best, const C &cst, uint32_t res, const int8_t *prow,
-                           uint32_t sstride)
+    static SWB_HD T column(T up, T &diag0, T (&left)[K], T &best, const C &cst, uint32_t codeA, uint32_t codeB,
+                           const int8_t *prow, uint32_t sstride)
     {
-        const uint32_t *ra = reinterpret_cast<const uint32_t *>(prow + (res & 0xffu) * sstride);
-        const uint32_t *rb = reinterpret_cast<const uint32_t *>(prow + (res >> 8) * sstride);
+        const uint32_t *ra = reinterpret_cast<const uint32_t *>(prow + codeA * sstride);
+        const uint32_t *rb = reinterpret_cast<const uint32_t *>(prow + codeB * sstride);
         T h = up;
         T dg = diag0;
         diag0 = add(up, cst.negg);
@@ -149,11 +149,11 @@ struct V32 {
     static SWB_HD int score_hi(T best, const C &) { return best.b; }
     static SWB_HD T max2(T a, T b) { return mk(mx(a.a, b.a), mx(a.b, b.b)); }
     template <int K>
-    static SWB_HD T column(T up, T &diag0, T (&left)[K], T &best, const C &cst, uint32_t res, const int8_t *prow,
-                           uint32_t sstride)
+    static SWB_HD T column(T up, T &diag0, T (&left)[K], T &best, const C &cst, uint32_t codeA, uint32_t codeB,
+                           const int8_t *prow, uint32_t sstride)
     {
-        const uint32_t *ra = reinterpret_cast<const uint32_t *>(prow + (res & 0xffu) * sstride);
-        const uint32_t *rb = reinterpret_cast<const uint32_t *>(prow + (res >> 8) * sstride);
+        const uint32_t *ra = reinterpret_cast<const uint32_t *>(prow + codeA * sstride);
+        const uint32_t *rb = reinterpret_cast<const uint32_t *>(prow + codeB * sstride);
         T h = up;
         T dg = diag0;
         diag0 = mk(up.a - cst.g, up.b - cst.g);
@@ -211,7 +211,8 @@ struct V32 {
 // One tile, all query rows of the current chunk.
 // Boundary scratch layout (elements of V::T, base tile.bnd_off), values in the policy's h domain:
 //   G == 1 : [chunk c][lane][4 columns]   -> one 16/32-byte vector per lane and chunk
-//   G  > 1 : [column][slot]               -> scalar per step, touched by the first / last lane of a group
+//   G  > 1 : [slot][column]               -> the first lane of a group reads 4 columns as one vector, the last lane
+//                                            writes scalars (its columns lag G-1 behind, so they are not 4-aligned)
 template <int K, class V, bool GROUPED, class BE>
 SWB_HD void swb_run_tile(BE &be, const SwbScoreParams &p, const SwbTile &tile, uint32_t tile_idx,
                          const int8_t *sprof, uint32_t sstride)
@@ -236,8 +237,6 @@ SWB_HD void swb_run_tile(BE &be, const SwbScoreParams &p, const SwbTile &tile, u
     const uint8_t *res = p.residues + tile.res_off + (size_t)slot * 8u;
     const size_t res_stride = (size_t)P * 8u;
     T *bnd = reinterpret_cast<T *>(p.bnd) + tile.bnd_off;
-    const uint32_t PAD2 = (uint32_t)SWB_PAD | ((uint32_t)SWB_PAD << 8);
-    const uint32_t PAD4 = PAD2 | (PAD2 << 16);
     T best = HZERO;
 
     for (uint32_t ss = 0; ss < nsuper; ++ss) {
@@ -249,70 +248,91 @@ SWB_HD void swb_run_tile(BE &be, const SwbScoreParams &p, const SwbTile &tile, u
         for (int k = 0; k < K; ++k) left[k] = LZERO;
         T diag0 = LZERO;
         T hprev = HZERO;
-        uint32_t resprev = PAD2;
+        uint32_t aprev = SWB_PAD, bprev = SWB_PAD;
 
-        uint2 rc = make_uint2(PAD4, PAD4);
+        // residue codes of the current chunk (4 columns x two sequences), fetched by the lead lane with byte loads:
+        // the codes arrive zero-extended in registers, so no ALU-pipe instruction is spent on unpacking them
+        uint32_t ca[4], cb[4];
         T bc[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) bc[u] = HZERO;
+        for (int u = 0; u < 4; ++u) {
+            ca[u] = SWB_PAD;
+            cb[u] = SWB_PAD;
+            bc[u] = HZERO;
+        }
         if (lead && nchunks > 0) {
-            rc = be.ld_res(reinterpret_cast<const uint2 *>(res));
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                ca[u] = be.ld_code(res + 2 * u);
+                cb[u] = be.ld_code(res + 2 * u + 1);
+            }
             if (read_top) {
                 if (!GROUPED) {
                     V::ld4(be, bnd + (size_t)lane * 4u, bc);
                 } else {
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) bc[u] = V::ld(be, bnd + (size_t)u * P + slot);
+                    V::ld4(be, bnd + (size_t)slot * W, bc);
                 }
             }
         }
         for (uint32_t c = 0; c < nsteps4; ++c) {
             // prefetch the next chunk of residues and of the top boundary row
-            uint2 rn = make_uint2(PAD4, PAD4);
+            uint32_t na[4], nb[4];
             T bn[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) bn[u] = HZERO;
+            for (int u = 0; u < 4; ++u) {
+                na[u] = SWB_PAD;
+                nb[u] = SWB_PAD;
+                bn[u] = HZERO;
+            }
             if (lead && c + 1 < nchunks) {
-                rn = be.ld_res(reinterpret_cast<const uint2 *>(res + (size_t)(c + 1) * res_stride));
+                const uint8_t *rnext = res + (size_t)(c + 1) * res_stride;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    na[u] = be.ld_code(rnext + 2 * u);
+                    nb[u] = be.ld_code(rnext + 2 * u + 1);
+                }
                 if (read_top) {
                     if (!GROUPED) {
                         V::ld4(be, bnd + ((size_t)(c + 1) * 32u + lane) * 4u, bn);
                     } else {
-#pragma unroll
-                        for (int u = 0; u < 4; ++u)
-                            bn[u] = V::ld(be, bnd + ((size_t)(c + 1) * 4u + u) * P + slot);
+                        V::ld4(be, bnd + (size_t)slot * W + (size_t)(c + 1) * 4u, bn);
                     }
                 }
             }
             T outb[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                uint32_t r = ((u < 2 ? rc.x : rc.y) >> (16 * (u & 1))) & 0xffffu;
+                uint32_t a = ca[u], b = cb[u];
                 T up = bc[u];
                 if (GROUPED) {
-                    const uint32_t r2 = be.shfl_up(resprev, 1, G);
+                    const uint32_t a2 = be.shfl_up(aprev, 1, G);
+                    const uint32_t b2 = be.shfl_up(bprev, 1, G);
                     const T u2 = V::shfl_up(be, hprev, 1, G);
-                    if (!lead) { r = r2; up = u2; }
+                    if (!lead) { a = a2; b = b2; up = u2; }
                 }
-                const T h = V::template column<K>(up, diag0, left, best, cst, r, prow, sstride);
+                const T h = V::template column<K>(up, diag0, left, best, cst, a, b, prow, sstride);
                 outb[u] = h;
                 hprev = h;
-                resprev = r;
+                aprev = a;
+                bprev = b;
             }
             if (write_bot) {
                 if (!GROUPED) {
                     V::st4(be, bnd + ((size_t)c * 32u + lane) * 4u, outb);
                 } else if (tail) {
+                    const int32_t col0 = (int32_t)(c * 4u) - (G - 1);  // column of outb[0]
+                    T *dst = bnd + (size_t)slot * W + col0;
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int64_t col = (int64_t)c * 4 + u - (G - 1);
-                        if (col >= 0 && col < (int64_t)W) V::st(be, bnd + (size_t)col * P + slot, outb[u]);
-                    }
+                    for (int u = 0; u < 4; ++u)
+                        if (col0 + u >= 0 && col0 + u < (int32_t)W) V::st(be, dst + u, outb[u]);
                 }
             }
-            rc = rn;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) bc[u] = bn[u];
+            for (int u = 0; u < 4; ++u) {
+                ca[u] = na[u];
+                cb[u] = nb[u];
+                bc[u] = bn[u];
+            }
         }
         be.syncwarp();
     }

@@ -28,7 +28,7 @@ struct HostBackend {
     void count(uint32_t *p) { (*p)++; }
     uint8_t ld_flag(const uint8_t *p) const { return *p; }
     SwbTile ld_tile(const SwbTile *p) const { return *p; }
-    uint2 ld_res(const uint2 *p) const { return *p; }
+    uint32_t ld_code(const uint8_t *p) const { return *p; }
     uint32_t ld_cg(const uint32_t *p) const { return *p; }
     uint2 ld_cg2(const uint2 *p) const { return *p; }
     uint4 ld_cg4(const uint4 *p) const { return *p; }

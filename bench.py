@@ -313,7 +313,11 @@ def main():
         residues = float(st["db_residues"])
         alg_bytes = len(qs) * residues  # one byte of DB residue per query pass
         roofline = {"bound": "int_alu", "kernel": "swb_score_kernel<K,V16>", "achieved": value / world, "peak": peak_gcups,
-                    "unit": "GCUPS", "frac": (value / world) / peak_gcups, "traffic": None,
+                    "unit": "GCUPS", "frac": (value / world) / peak_gcups,
+                    # dram__bytes_read+write of ONE launch (Q = 4743 rows over the same database) from the committed
+                    # ncu --set full capture, profiles/r1_score_kernel_K32_V16_raw_selected.txt; the algorithmic bytes
+                    # of that launch are 0.203e9 (residues + scores): the rest is the strip-boundary rows
+                    "traffic": 32.44e9, "traffic_algorithmic": float(st["db_residues"]) + 4.0 * st["db_sequences"],
                     "achieved_incl_padding": ach_padded / world,
                     "frac_incl_padding": (ach_padded / world) / peak_gcups,
                     "peak_source": "swb_microbench kind 4 measured live: %.0f Glane-instr/s for the kernel's own SIMD mix "

@@ -241,3 +241,66 @@ def test_cli_and_reference_style_caller(swb, tmp_path):
                        timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "mismatches 0" in r.stdout
+
+
+def test_config4_titin_scale_queries_and_targets(swb, oracle):
+    """BASELINE configs[3]: queries of 5,000 / 20,000 / 35,213 residues against long targets, a 10 %-mutated copy and
+    the query itself (self score ~5.5 x L >> 32767: the s16 pass must flag it, the int32 pass must fix it). The
+    35,213-row query runs as five shared-memory chunks; 32-lane wavefront tiles carry the targets."""
+    rng = np.random.default_rng(1784)
+    m = oracle.matrix("blosum50")
+    targets = random_db(rng, np.round(np.exp(rng.uniform(np.log(5000), np.log(35213), 20))), alphabet=20)
+    e = swb.Engine(0)
+    try:
+        for qlen in (5000, 20000, 35213):
+            q = rng.integers(0, 20, qlen).astype(np.uint8)
+            mutated = q.copy()
+            pos = rng.choice(qlen, qlen // 10, replace=False)
+            mutated[pos] = rng.integers(0, 20, len(pos))
+            enc = targets + [mutated, q.copy(), rng.integers(0, 20, 300).astype(np.uint8)]
+            codes, offs = pack_db(enc)
+            e.db_load(codes, offs)
+            got = e.search(q)
+            want = oracle.scan(q, codes, offs, m)
+            assert np.array_equal(got, want), qlen
+            assert got[len(targets) + 1] > 5 * qlen > 32767  # the self hit
+            st = e.stats()
+            assert st["recomputed_tiles"] >= 1 and st["tiles_by_group"][5] >= 1
+    finally:
+        e.close()
+
+
+def test_config5_many_queries_sampled_parity_and_shard_checksum(swb, oracle):
+    """BASELINE configs[4], scaled to one GPU: a Swiss-Prot-shaped database (bench.synth_db, 0.25 scale) against 120
+    queries drawn from the same length law; parity on a 1/256 stride sample of the database for 12 queries, and the
+    size-independent property that the checksum of all scores is the same for 1 shard and for 4 shards."""
+    import bench
+    codes, offs = bench.synth_db(scale=0.25)
+    n = len(offs) - 1
+    rng = np.random.default_rng(1785)
+    qlens = np.clip(np.round(rng.lognormal(5.58, 0.75, 120)), 30, 5478).astype(int)
+    queries = [rng.integers(0, 20, l).astype(np.uint8) for l in qlens]
+    m = oracle.matrix("blosum50")
+    e = swb.Engine(0)
+    try:
+        e.db_load(codes, offs)
+        full = e.search_batch(queries)
+        assert full.shape == (120, n) and (full >= 0).all()
+        for qi in range(0, 120, 10):
+            want = oracle.scan(queries[qi], codes, offs, m, start=3, stride=256)
+            sel = want >= 0
+            assert sel.sum() >= n // 256
+            assert np.array_equal(full[qi][sel], want[sel]), qi
+        checksum = full.astype(np.int64).sum(axis=1)
+        acc = np.zeros(120, dtype=np.int64)
+        seen = 0
+        for s in range(4):
+            e.db_load(codes, offs, s, 4)
+            part = e.search_batch(queries)
+            acc += part.astype(np.int64).sum(axis=1)
+            ids = e.db_ids()
+            assert np.array_equal(part[:, :50], full[:, ids[:50]])
+            seen += len(ids)
+        assert seen == n and np.array_equal(acc, checksum)
+    finally:
+        e.close()

@@ -13,7 +13,7 @@
 #include "swb_kernels.h"
 #include "swb_plan.h"
 
-#define SWB_MAX_SLOTS 4
+#define SWB_MAX_SLOTS 24
 #define SWB_MAX_COUNTERS 256
 #define SWB_MAX_SUB 2  // extra streams per slot: up to three distinct K values per query
 #define SWB_CHUNK_ROWS 7168u          // query rows per launch when a query does not fit shared memory
@@ -36,6 +36,7 @@ struct Slot {
     cudaEvent_t ev_sub[SWB_MAX_SUB] = {nullptr, nullptr};
     cudaEvent_t done = nullptr;
     bool busy = false;
+    bool ready = false;  // scratch sized for the loaded database
     uint8_t *h_query = nullptr;  // pinned
     uint8_t *d_query = nullptr;
     uint32_t query_cap = 0;
@@ -64,7 +65,7 @@ struct swb_engine {
     cudaStream_t own_stream = nullptr;
     cudaStream_t user_stream = nullptr;
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_fork = nullptr;
-    cudaEvent_t ev_join[SWB_MAX_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_join[SWB_MAX_SLOTS] = {};
     // scoring
     int8_t h_mat[SWB_ALPHA * SWB_ALPHA];
     int gap = 2;
@@ -77,7 +78,7 @@ struct swb_engine {
     int opt_k = 0;
     int opt_group_order = 0;  // 0 auto (lone query: longest tiles first; batch: bulk first), 1 longest first, 2 bulk first
     uint32_t cur_nq = 1;
-    int nslots = 3;
+    int nslots = 16;
     uint32_t chunk_rows = SWB_CHUNK_ROWS;  // query rows per launch for queries beyond shared memory
     // database
     bool db_loaded = false;
@@ -266,8 +267,7 @@ extern "C" int swb_set_option(swb_engine *e, const char *key, int64_t value)
         if (value != 0 && value != 8 && value != 16 && value != 32) return fail(e, SWB_ERR_ARG, "k must be 0, 8, 16 or 32");
         e->opt_k = (int)value;
     } else if (!strcmp(key, "streams")) {
-        if (value < 1 || value > SWB_MAX_SLOTS) return fail(e, SWB_ERR_ARG, "streams must be 1..4");
-        if (e->db_loaded) return fail(e, SWB_ERR_STATE, "set streams before swb_db_load");
+        if (value < 1 || value > SWB_MAX_SLOTS) return fail(e, SWB_ERR_ARG, "streams must be 1..24");
         e->nslots = (int)value;
     } else if (!strcmp(key, "group_order")) {
         if (value < 0 || value > 2) return fail(e, SWB_ERR_ARG, "group_order must be 0, 1 or 2");
@@ -385,21 +385,7 @@ extern "C" int swb_db_load(swb_engine *e, const uint8_t *codes, const uint64_t *
         CU(GROW_DEV(e->d_tiles, e->tiles_cap, sizeof(SwbTile) * ntiles));
         CU(GROW_DEV(e->d_residues, e->residues_cap, pl.res_bytes));
         CU(GROW_DEV(e->d_out_pos, e->out_pos_cap, sizeof(uint32_t) * nl));
-        const size_t flags_bytes = swb_roundup(ntiles, 16);
-        const size_t sorted_bytes = sizeof(int32_t) * 2 * (size_t)((nl + 1) / 2);
-        const size_t head = sizeof(uint32_t) * SWB_MAX_COUNTERS;
-        for (int i = 0; i < e->nslots; ++i) {
-            Slot &s = e->slots[i];
-            s.state_bytes = head + flags_bytes + sorted_bytes;
-            CU(GROW_DEV(s.d_state, s.state_cap, s.state_bytes));
-            s.d_counters = reinterpret_cast<uint32_t *>(s.d_state);
-            s.d_flags = s.d_state + head;
-            s.d_sorted = reinterpret_cast<int32_t *>(s.d_state + head + flags_bytes);
-            CU(GROW_DEV(s.d_bnd16, s.bnd16_cap, sizeof(uint32_t) * pl.bnd_elems));
-            if (s.d_bnd32) CU(GROW_DEV(s.d_bnd32, s.bnd32_cap, 8ull * pl.bnd_elems));
-            CU(GROW_HOST(s.h_scores, s.h_scores_cap, sizeof(int32_t) * nl));
-            s.busy = false;
-        }
+        for (int i = 0; i < SWB_MAX_SLOTS; ++i) e->slots[i].ready = false;  // per-stream scratch is (re)sized on first use
         t2 = wall_ms();
         // stream the raw codes through two pinned staging buffers: the host copy of slice i+1 overlaps the
         // asynchronous H2D of slice i
@@ -474,6 +460,27 @@ static int shape_for(swb_engine *e, int K, bool i32, uint32_t smem_rows, uint32_
     return SWB_OK;
 }
 
+// Per-stream scratch of the loaded database, sized on the slot's first use after a load (grow-only buffers): a lone
+// query touches one slot, a batch as many as it has queries in flight.
+static int ensure_slot(swb_engine *e, Slot &s)
+{
+    if (s.ready) return SWB_OK;
+    const SwbPlan &pl = e->plan;
+    const uint32_t nl = pl.n_local;
+    const size_t flags_bytes = swb_roundup((uint32_t)pl.tiles.size(), 16);
+    const size_t sorted_bytes = sizeof(int32_t) * 2 * (size_t)((nl + 1) / 2);
+    const size_t head = sizeof(uint32_t) * SWB_MAX_COUNTERS;
+    s.state_bytes = head + flags_bytes + sorted_bytes;
+    CU(GROW_DEV(s.d_state, s.state_cap, s.state_bytes));
+    s.d_counters = reinterpret_cast<uint32_t *>(s.d_state);
+    s.d_flags = s.d_state + head;
+    s.d_sorted = reinterpret_cast<int32_t *>(s.d_state + head + flags_bytes);
+    CU(GROW_DEV(s.d_bnd16, s.bnd16_cap, sizeof(uint32_t) * pl.bnd_elems));
+    CU(GROW_HOST(s.h_scores, s.h_scores_cap, sizeof(int32_t) * nl));
+    s.ready = true;
+    return SWB_OK;
+}
+
 // Enqueues everything one query needs; the result lands in d_out[qi].
 // Stream layout per slot: profile build and clears on slot.stream, then one sub-stream per distinct K (the tiles of
 // the group sizes that use that K for this query) so that the few long-sequence tiles run beside the bulk, then
@@ -484,6 +491,8 @@ static int enqueue_query(swb_engine *e, Slot &s, uint32_t qi, const uint8_t *q, 
     const uint32_t nl = pl.n_local;
     int32_t *out = e->d_out + (size_t)qi * nl;
     if (nl == 0) return SWB_OK;
+    int rc0 = ensure_slot(e, s);
+    if (rc0 != SWB_OK) return rc0;
     if (qlen == 0 || pl.tiles.empty() || pl.max_len == 0) {
         CU(cudaMemsetAsync(out, 0, sizeof(int32_t) * nl, s.stream));
         return SWB_OK;
@@ -631,7 +640,7 @@ extern "C" int swb_search_batch(swb_engine *e, const uint8_t *qcodes, const uint
     e->stats.recomputed_tiles = 0;
     e->last_nq = nq;
     e->cur_nq = nq;
-    const int ns = e->nslots;
+    const int ns = (int)std::min<uint32_t>((uint32_t)e->nslots, std::max<uint32_t>(1u, nq));  // streams this batch uses
     CU(cudaEventRecord(e->ev_start, ms));
     CU(cudaEventRecord(e->ev_fork, ms));
     for (int i = 0; i < ns; ++i) {

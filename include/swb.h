@@ -72,7 +72,7 @@ void swb_destroy(swb_engine *e);
 const char *swb_last_error(const swb_engine *e);
 /* options: "group_len" (longest sequence handled by one lane per pair, default 384; set before db_load),
  *          "k" (query rows per lane: 0 = chosen per lane-group size and query, else 8, 16, 32),
- *          "streams" (concurrent queries of a batch, 1..4, default 3; set before db_load),
+ *          "streams" (queries of a batch in flight at once, 1..24, default 16; their scratch is allocated on first use),
  *          "group_order" (0 = auto, 1 = launch the long-sequence tiles first, 2 = launch the bulk first),
  *          "chunk_rows" (query rows per launch for queries beyond shared memory; multiple of 1024, <= 7168) */
 int swb_set_option(swb_engine *e, const char *key, int64_t value);

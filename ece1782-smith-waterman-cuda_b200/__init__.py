@@ -71,7 +71,7 @@ ABI_SYMBOLS = [
     "swb_create", "swb_destroy", "swb_last_error", "swb_set_option", "swb_set_stream", "swb_set_scoring",
     "swb_set_scoring_preset", "swb_scoring_matrix", "swb_encode", "swb_db_load", "swb_db_count", "swb_db_ids",
     "swb_search", "swb_search_batch", "swb_fetch_scores", "swb_topk", "swb_stats", "swb_plan_describe",
-    "swb_microbench",
+    "swb_microbench", "swb_align",
 ]
 
 _lib = None
@@ -132,6 +132,8 @@ def lib():
     L.swb_plan_describe.restype = ctypes.c_int
     L.swb_plan_describe.argtypes = [_u64p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32,
                                     ctypes.POINTER(SwbPlanInfo), _u32p, _u32p]
+    L.swb_align.restype = ctypes.c_int
+    L.swb_align.argtypes = [vp, _u8p, ctypes.c_uint32, ctypes.c_uint32, _i32p, _u32p, _u32p, _u8p, ctypes.c_uint32, _u32p]
     L.swb_microbench.restype = ctypes.c_int
     L.swb_microbench.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double),
                                  ctypes.POINTER(ctypes.c_double)]
@@ -299,6 +301,18 @@ class Engine:
                                      top.ctypes.data_as(_i32p)), "swb_topk")
         return ids, top
 
+    def align(self, query_codes, db_id, subject_len):
+        """traceback alignment against one database sequence: (score, end_i, end_j, ops) -- see swb_align"""
+        q = np.ascontiguousarray(query_codes, dtype=np.uint8)
+        cap = len(q) + int(subject_len) + 1
+        ops = np.zeros(cap, dtype=np.uint8)
+        score = ctypes.c_int32()
+        ei, ej, n = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint32()
+        qp = q.ctypes.data_as(_u8p) if len(q) else None
+        self._check(self._L.swb_align(self._h, qp, len(q), int(db_id), ctypes.byref(score), ctypes.byref(ei),
+                                      ctypes.byref(ej), ops.ctypes.data_as(_u8p), cap, ctypes.byref(n)), "swb_align")
+        return int(score.value), int(ei.value), int(ej.value), ops[:n.value].copy()
+
     def stats(self):
         s = SwbStats()
         self._check(self._L.swb_stats(self._h, ctypes.byref(s)), "swb_stats")
@@ -404,6 +418,28 @@ def smith_waterman_cuda(query, db, result, device=0):
     for k, (sid, _) in enumerate(ordered):
         result.append((sid, int(scores[k])))
     return result
+
+
+def render_alignment(query_text, subject_text, end_i, end_j, ops):
+    """The two aligned strings cpu.cpp prints (cpu.cpp:80-108) from swb_align's result."""
+    i = end_i - sum(1 for o in ops if o != 1)
+    j = end_j - sum(1 for o in ops if o != 2)
+    a, b = [], []
+    for o in ops:
+        if o == 1:
+            a.append("-")
+            b.append(subject_text[j])
+            j += 1
+        elif o == 2:
+            a.append(query_text[i])
+            b.append("-")
+            i += 1
+        else:
+            a.append(query_text[i])
+            b.append(subject_text[j])
+            i += 1
+            j += 1
+    return "".join(a), "".join(b)
 
 
 # ---- multi-GPU host side: shards are independent, only small results are exchanged -------------

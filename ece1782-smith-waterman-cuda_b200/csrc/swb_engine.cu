@@ -98,6 +98,12 @@ struct swb_engine {
     size_t out_cap = 0;  // bytes
     uint32_t last_nq = 0;
     Slot slots[SWB_MAX_SLOTS];
+    // scratch of swb_align (grow-only)
+    int32_t *d_align_h = nullptr;
+    uint8_t *d_align_dir = nullptr;
+    uint8_t *d_align_out = nullptr;  // [5 ints header | ops]
+    uint8_t *h_align_out = nullptr;  // pinned
+    size_t align_h_cap = 0, align_dir_cap = 0, align_out_cap = 0, align_hout_cap = 0;
     uint32_t *h_recount = nullptr;  // pinned, SWB_MAX_SLOTS
     swb_stats_t stats;
 };
@@ -148,6 +154,15 @@ static void free_db(swb_engine *e)
     e->d_seq_len = nullptr;
     e->tiles_cap = e->residues_cap = e->out_pos_cap = e->raw_cap = e->seq_off_cap = e->seq_len_cap = 0;
     e->out_cap = 0;
+    if (e->d_align_h) cudaFree(e->d_align_h);
+    if (e->d_align_dir) cudaFree(e->d_align_dir);
+    if (e->d_align_out) cudaFree(e->d_align_out);
+    if (e->h_align_out) cudaFreeHost(e->h_align_out);
+    e->d_align_h = nullptr;
+    e->d_align_dir = nullptr;
+    e->d_align_out = nullptr;
+    e->h_align_out = nullptr;
+    e->align_h_cap = e->align_dir_cap = e->align_out_cap = e->align_hout_cap = 0;
     for (int i = 0; i < 2; ++i) {
         if (e->h_stage[i]) cudaFreeHost(e->h_stage[i]);
         if (e->ev_stage[i]) cudaEventDestroy(e->ev_stage[i]);
@@ -697,6 +712,62 @@ extern "C" int swb_fetch_scores(swb_engine *e, uint32_t query_index, int32_t *sc
     const uint32_t nl = e->plan.n_local;
     if (nl == 0) return SWB_OK;
     CU(cudaMemcpy(scores, e->d_out + (size_t)query_index * nl, sizeof(int32_t) * nl, cudaMemcpyDeviceToHost));
+    return SWB_OK;
+}
+
+extern "C" int swb_align(swb_engine *e, const uint8_t *query, uint32_t qlen, uint32_t db_id, int32_t *score,
+                         uint32_t *end_i, uint32_t *end_j, uint8_t *ops, uint32_t cap, uint32_t *nops)
+{
+    if (!e || (!query && qlen) || !score) return SWB_ERR_ARG;
+    if (!e->db_loaded) return fail(e, SWB_ERR_STATE, "swb_align before swb_db_load");
+    const SwbPlan &pl = e->plan;
+    const std::vector<uint32_t>::const_iterator it = std::lower_bound(pl.shard_ids.begin(), pl.shard_ids.end(), db_id);
+    if (it == pl.shard_ids.end() || *it != db_id) return fail(e, SWB_ERR_ARG, "db_id is not part of this shard");
+    const uint32_t spos = pl.sorted_of_out[(size_t)(it - pl.shard_ids.begin())];
+    const uint32_t n = pl.seq_len[spos], m = qlen;
+    *score = 0;
+    if (end_i) *end_i = 0;
+    if (end_j) *end_j = 0;
+    if (nops) *nops = 0;
+    if (m == 0 || n == 0) return SWB_OK;
+    const uint64_t cells = (uint64_t)(m + 1) * (n + 1);
+    if (cells > (1ull << 31)) return fail(e, SWB_ERR_ARG, "alignment matrix larger than 2^31 cells");
+    CU(cudaSetDevice(e->device));
+    cudaStream_t st = main_stream(e);
+    Slot &s = e->slots[0];
+    if (qlen > s.query_cap) {
+        CU(cudaStreamSynchronize(s.stream));
+        if (s.h_query) cudaFreeHost(s.h_query);
+        if (s.d_query) cudaFree(s.d_query);
+        s.h_query = nullptr;
+        s.d_query = nullptr;
+        s.query_cap = 0;
+        const uint32_t qcap = swb_roundup(qlen, 4096);
+        CU(cudaMallocHost(&s.h_query, qcap));
+        CU(cudaMalloc(&s.d_query, qcap));
+        s.query_cap = qcap;
+    }
+    const size_t out_bytes = 5 * sizeof(int32_t) + (size_t)cap;
+    CU(GROW_DEV(e->d_align_h, e->align_h_cap, sizeof(int32_t) * 3 * (size_t)(m + 2)));
+    CU(GROW_DEV(e->d_align_dir, e->align_dir_cap, (size_t)cells));
+    CU(GROW_DEV(e->d_align_out, e->align_out_cap, out_bytes));
+    CU(GROW_HOST(e->h_align_out, e->align_hout_cap, out_bytes));
+    memcpy(s.h_query, query, qlen);
+    CU(cudaMemcpyAsync(s.d_query, s.h_query, qlen, cudaMemcpyHostToDevice, st));
+    CU(swb_launch_align(s.d_query, m, e->d_raw + pl.seq_off[spos], n, e->d_mat, e->gap, e->d_align_h, e->d_align_dir,
+                        reinterpret_cast<int32_t *>(e->d_align_out), e->d_align_out + 5 * sizeof(int32_t), cap, st));
+    CU(cudaMemcpyAsync(e->h_align_out, e->d_align_out, out_bytes, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    const int32_t *hdr = reinterpret_cast<const int32_t *>(e->h_align_out);
+    *score = hdr[0];
+    if (end_i) *end_i = (uint32_t)hdr[1];
+    if (end_j) *end_j = (uint32_t)hdr[2];
+    const uint32_t cnt = (uint32_t)hdr[3];
+    if (nops) *nops = cnt;
+    if (hdr[4] || cnt > cap) return fail(e, SWB_ERR_ARG, "ops buffer too small (qlen + subject length always suffices)");
+    // the kernel walks from the end of the alignment to its start (cpu.cpp:80-103); hand it out start to end
+    if (ops)
+        for (uint32_t k = 0; k < cnt; ++k) ops[k] = e->h_align_out[5 * sizeof(int32_t) + (cnt - 1 - k)];
     return SWB_OK;
 }
 

@@ -183,3 +183,87 @@ cudaError_t swb_launch_scatter(const int32_t *sorted, const uint32_t *dst, uint3
     swb_scatter_kernel<<<(n + 255) / 256, 256, 0, st>>>(sorted, dst, n, out);
     return cudaGetLastError();
 }
+
+// ---------------------------------------------------------------------------------------------
+// Alignment with traceback for one (query, subject) pair -- what the reference's cpu.cpp prints for two strings
+// (cpu.cpp:39-103): fill with the update order LEFT, TOP, DIAG and strict '>' (cpu.cpp:47-64), keep the first
+// row-major maximum (cpu.cpp:66-70), walk back until a cell with no direction, i.e. H == 0 (cpu.cpp:80-103).
+// One block; anti-diagonal wavefront; three rolling H diagonals in global scratch; one direction byte per cell.
+__global__ void __launch_bounds__(512) swb_align_kernel(const uint8_t *__restrict__ q, uint32_t m,
+                                                        const uint8_t *__restrict__ d, uint32_t n,
+                                                        const int8_t *__restrict__ mat, int gap, int32_t *hdiag,
+                                                        uint8_t *dir, int32_t *out_hdr, uint8_t *out_ops, uint32_t cap)
+{
+    __shared__ int s_best[512];
+    __shared__ uint32_t s_bi[512], s_bj[512];
+    const uint32_t W = n + 1;
+    int32_t *h0 = hdiag, *h1 = hdiag + (m + 2), *h2 = hdiag + 2 * (size_t)(m + 2);
+    for (uint32_t i = threadIdx.x; i < 3 * (m + 2); i += blockDim.x) hdiag[i] = 0;
+    int best = 0;
+    uint32_t bi = 0, bj = 0;
+    __syncthreads();
+    // diagonal dd = i + j; h2 = current, h1 = dd-1, h0 = dd-2, all indexed by i
+    for (uint32_t dd = 2; dd <= m + n; ++dd) {
+        const uint32_t ilo = dd > n ? dd - n : 1u;
+        const uint32_t ihi = dd - 1 < m ? dd - 1 : m;
+        for (uint32_t i = ilo + threadIdx.x; i <= ihi; i += blockDim.x) {
+            const uint32_t j = dd - i;
+            int h = 0;
+            uint8_t t = 0;
+            const int left = h1[i] - gap;      // H(i, j-1)
+            const int up = h1[i - 1] - gap;    // H(i-1, j)
+            const int dg = h0[i - 1] + mat[(uint32_t)(q[i - 1] & 31u) * SWB_ALPHA + (d[j - 1] & 31u)];
+            if (left > h) { h = left; t = 1; }
+            if (up > h) { h = up; t = 2; }
+            if (dg > h) { h = dg; t = 3; }
+            h2[i] = h;
+            dir[(size_t)i * W + j] = t;
+            // first row-major maximum: larger value, else smaller i, else smaller j
+            if (h > best || (h == best && h > 0 && (i < bi || (i == bi && j < bj)))) { best = h; bi = i; bj = j; }
+        }
+        __syncthreads();
+        // cells outside [ilo, ihi] of the new diagonal are borders (H = 0) for the next two diagonals
+        if (threadIdx.x == 0) {
+            if (ilo >= 1) h2[ilo - 1] = 0;
+            if (ihi + 1 <= m + 1) h2[ihi + 1] = 0;
+        }
+        int32_t *tmp = h0; h0 = h1; h1 = h2; h2 = tmp;
+        __syncthreads();
+    }
+    s_best[threadIdx.x] = best;
+    s_bi[threadIdx.x] = bi;
+    s_bj[threadIdx.x] = bj;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (uint32_t k = 1; k < blockDim.x; ++k) {
+            const int v = s_best[k];
+            if (v > best || (v == best && v > 0 && (s_bi[k] < bi || (s_bi[k] == bi && s_bj[k] < bj)))) {
+                best = v; bi = s_bi[k]; bj = s_bj[k];
+            }
+        }
+        uint32_t i = bi, j = bj, nops = 0;
+        bool overflow = false;
+        while (best > 0) {
+            const uint8_t t = dir[(size_t)i * W + j];
+            if (t == 0) break;
+            if (nops < cap) out_ops[nops] = t; else overflow = true;
+            ++nops;
+            if (t == 1) --j;
+            else if (t == 2) --i;
+            else { --i; --j; }
+        }
+        out_hdr[0] = best;
+        out_hdr[1] = (int32_t)bi;
+        out_hdr[2] = (int32_t)bj;
+        out_hdr[3] = (int32_t)nops;
+        out_hdr[4] = overflow ? 1 : 0;
+    }
+}
+
+cudaError_t swb_launch_align(const uint8_t *q, uint32_t m, const uint8_t *d, uint32_t n, const int8_t *mat, int gap,
+                             int32_t *hdiag, uint8_t *dir, int32_t *out_hdr, uint8_t *out_ops, uint32_t cap,
+                             cudaStream_t st)
+{
+    swb_align_kernel<<<1, 512, 0, st>>>(q, m, d, n, mat, gap, hdiag, dir, out_hdr, out_ops, cap);
+    return cudaGetLastError();
+}

@@ -21,3 +21,8 @@ cudaError_t swb_launch_pack(const SwbTile *tiles, uint32_t ntiles, const uint8_t
                             const uint32_t *seq_len, uint32_t nseq, uint8_t *residues, cudaStream_t st);
 cudaError_t swb_launch_scatter(const int32_t *sorted, const uint32_t *dst, uint32_t n, int32_t *out,
                                cudaStream_t st);
+// traceback alignment of one pair (cpu.cpp semantics); hdiag: 3*(m+2) ints, dir: (m+1)*(n+1) bytes, out_hdr: 5 ints
+// {score, end_i, end_j, nops, ops_overflow}, out_ops: ops from the END of the alignment back to its start
+cudaError_t swb_launch_align(const uint8_t *q, uint32_t m, const uint8_t *d, uint32_t n, const int8_t *mat, int gap,
+                             int32_t *hdiag, uint8_t *dir, int32_t *out_hdr, uint8_t *out_ops, uint32_t cap,
+                             cudaStream_t st);

@@ -79,6 +79,8 @@ int swb_build_plan(const uint64_t *offsets, uint32_t n, uint32_t shard, uint32_t
             }
         for (uint32_t s = 0; s < nl; ++s) plan.out_pos[s] = rank_of[plan.sorted_ids[s]];
     }
+    plan.sorted_of_out.resize(nl);
+    for (uint32_t s = 0; s < nl; ++s) plan.sorted_of_out[plan.out_pos[s]] = s;
     plan.seq_off.resize(nl);
     plan.seq_len.resize(nl);
     for (uint32_t s = 0; s < nl; ++s) {

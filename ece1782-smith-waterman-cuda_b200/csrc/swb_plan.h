@@ -17,6 +17,7 @@ struct SwbPlan {
     uint32_t shard, nshards;
     std::vector<uint32_t> sorted_ids; // [n_local] DB ids, longest first, ties in DB order
     std::vector<uint32_t> out_pos;    // [n_local] position of sorted entry s in the shard's output order
+    std::vector<uint32_t> sorted_of_out;  // [n_local] inverse of out_pos
     std::vector<uint32_t> shard_ids;  // [n_local] DB ids in output order (ascending)
     std::vector<uint64_t> seq_off;    // [n_local] offset of sorted entry s in the raw code buffer
     std::vector<uint32_t> seq_len;    // [n_local]

@@ -106,6 +106,13 @@ int swb_fetch_scores(swb_engine *e, uint32_t query_index, int32_t *scores);
 /* k best (score desc, id asc) of one score vector of this shard; ids are database ids */
 int swb_topk(const swb_engine *e, const int32_t *scores, uint32_t k, uint32_t *ids, int32_t *top);
 int swb_stats(const swb_engine *e, swb_stats_t *out);
+/* Alignment with traceback of the query against ONE database sequence of this shard (the top hits of a scan) -- what
+ * the reference's cpu.cpp prints for two strings (cpu.cpp:39-108): same update order LEFT, TOP, DIAG with strict '>',
+ * first row-major maximum, walk back until H == 0. end_i / end_j: 1-based cell of the maximum. ops: the alignment from
+ * its start to its end, one byte per column: 1 = gap in the query (consumes a subject residue, cpu.cpp FROM_LEFT),
+ * 2 = gap in the subject (FROM_TOP), 3 = aligned pair (FROM_TOP_LEFT). cap >= qlen + subject length always suffices. */
+int swb_align(swb_engine *e, const uint8_t *query, uint32_t qlen, uint32_t db_id, int32_t *score, uint32_t *end_i,
+              uint32_t *end_j, uint8_t *ops, uint32_t cap, uint32_t *nops);
 
 /* ---- plan introspection, CPU only (host logic of swb_db_load) ------------------------------ */
 typedef struct swb_plan_info_t {

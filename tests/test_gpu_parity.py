@@ -304,3 +304,35 @@ def test_config5_many_queries_sampled_parity_and_shard_checksum(swb, oracle):
         assert seen == n and np.array_equal(acc, checksum)
     finally:
         e.close()
+
+
+def test_traceback_alignment_matches_cpu_cpp_and_oracle(swb, oracle, subset, queries):
+    """swb_align (GPU traceback of a hit) against the aligned strings the compiled reference cpu.cpp printed (+3/-3
+    scheme, tests/golden/cpu_ref_ident3.json) and against the oracle's restatement of cpu.cpp:39-103 under BLOSUM50"""
+    import json
+    ref = json.load(open(os.path.join(GOLDEN, "cpu_ref_ident3.json")))
+    e = swb.Engine(0)
+    try:
+        e.set_scoring_preset(swb.SWB_SCORING_IDENT3)
+        for p in ref["pairs"]:
+            c, o = swb.pack_sequences([swb.encode(p["b"], swb.SWB_SCORING_IDENT3)])
+            e.db_load(c, o)
+            score, ei, ej, ops = e.align(swb.encode(p["a"], swb.SWB_SCORING_IDENT3), 0, len(p["b"]))
+            assert score == p["score"]
+            assert swb.render_alignment(p["a"], p["b"], ei, ej, ops) == (p["aligned_a"], p["aligned_b"])
+        e.set_scoring_preset(swb.SWB_SCORING_BLOSUM50_REF)
+        e.db_load(subset["codes"], subset["offsets"])
+        for name in ("P02232", "P01008"):
+            q = swb.encode(queries[name])
+            scores = e.search(q)
+            ids, top = e.topk(scores, 4)
+            for sid, sc in zip(ids, top):
+                subj = subset["seqs"][int(sid)]
+                score, ei, ej, ops = e.align(q, int(sid), len(subj))
+                want = oracle.align(queries[name], subj, "blosum50")
+                assert score == sc == want[0]
+                assert (ei, ej) == want[3]
+                assert swb.render_alignment(queries[name], subj, ei, ej, ops) == (want[1], want[2])
+        assert e.align(np.zeros(0, np.uint8), 3, 10)[0] == 0
+    finally:
+        e.close()

@@ -390,7 +390,9 @@ extern "C" int swb_db_load(swb_engine *e, const uint8_t *codes, const uint64_t *
     const uint32_t nl = pl.n_local;
     const uint32_t ntiles = (uint32_t)pl.tiles.size();
     const uint64_t base = n ? offsets[0] : 0;
-    const uint64_t raw_bytes = pl.residues_total;
+    // a sharded load uploads only the shard's residues (gathered in sorted order), a full load the caller's buffer
+    const bool gather = nshards > 1;
+    const uint64_t raw_bytes = gather ? pl.residues_local : pl.residues_total;
     double t2 = t1, t3 = t1;
 
     if (nl > 0 && ntiles > 0) {
@@ -411,16 +413,41 @@ extern "C" int swb_db_load(swb_engine *e, const uint8_t *codes, const uint64_t *
                 if (!e->ev_stage[i]) CU(cudaEventCreateWithFlags(&e->ev_stage[i], cudaEventDisableTiming));
             }
             int b = 0;
-            for (uint64_t off = 0; off < raw_bytes; off += stage, b ^= 1) {
-                const size_t len = (size_t)std::min<uint64_t>(stage, raw_bytes - off);
-                CU(cudaEventSynchronize(e->ev_stage[b]));
-                memcpy(e->h_stage[b], codes + base + off, len);
-                CU(cudaMemcpyAsync(e->d_raw + off, e->h_stage[b], len, cudaMemcpyHostToDevice, st));
-                CU(cudaEventRecord(e->ev_stage[b], st));
+            if (!gather) {
+                for (uint64_t off = 0; off < raw_bytes; off += stage, b ^= 1) {
+                    const size_t len = (size_t)std::min<uint64_t>(stage, raw_bytes - off);
+                    CU(cudaEventSynchronize(e->ev_stage[b]));
+                    memcpy(e->h_stage[b], codes + base + off, len);
+                    CU(cudaMemcpyAsync(e->d_raw + off, e->h_stage[b], len, cudaMemcpyHostToDevice, st));
+                    CU(cudaEventRecord(e->ev_stage[b], st));
+                }
+            } else {
+                uint64_t done = 0;
+                uint32_t sq = 0, within = 0;
+                while (done < raw_bytes) {
+                    CU(cudaEventSynchronize(e->ev_stage[b]));
+                    size_t fill = 0;
+                    while (fill < stage && sq < nl) {
+                        const size_t take = std::min<size_t>(pl.seq_len[sq] - within, stage - fill);
+                        memcpy(e->h_stage[b] + fill, codes + pl.seq_off[sq] + within, take);
+                        fill += take;
+                        within += (uint32_t)take;
+                        if (within == pl.seq_len[sq]) { ++sq; within = 0; }
+                    }
+                    CU(cudaMemcpyAsync(e->d_raw + done, e->h_stage[b], fill, cudaMemcpyHostToDevice, st));
+                    CU(cudaEventRecord(e->ev_stage[b], st));
+                    done += fill;
+                    b ^= 1;
+                }
             }
         }
-        // offsets relative to the start of the uploaded range
-        for (uint32_t s = 0; s < nl; ++s) pl.seq_off[s] -= base;
+        // offsets into the uploaded buffer
+        if (!gather) {
+            for (uint32_t s = 0; s < nl; ++s) pl.seq_off[s] -= base;
+        } else {
+            uint64_t at = 0;
+            for (uint32_t s = 0; s < nl; ++s) { pl.seq_off[s] = at; at += pl.seq_len[s]; }
+        }
         CU(cudaMemcpyAsync(e->d_seq_off, pl.seq_off.data(), sizeof(uint64_t) * nl, cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(e->d_seq_len, pl.seq_len.data(), sizeof(uint32_t) * nl, cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(e->d_tiles, pl.tiles.data(), sizeof(SwbTile) * ntiles, cudaMemcpyHostToDevice, st));

@@ -188,6 +188,7 @@ def main():
     ap.add_argument("--k", type=int, default=0)
     ap.add_argument("--group-len", type=int, default=0)
     ap.add_argument("--group-order", type=int, default=0)
+    ap.add_argument("--split", type=int, default=-1, help="pipelined passes for very long tiles: 1 on (default), 0 off")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--per-query", action="store_true", help="also print device GCUPS per query")
     args = ap.parse_args()
@@ -219,6 +220,8 @@ def main():
         opts["group_len"] = args.group_len
     if args.group_order:
         opts["group_order"] = args.group_order
+    if args.split >= 0:
+        opts["split"] = args.split
     eng = swb.Engine(local, **opts)
     stream = torch.cuda.current_stream()
     eng.set_stream(stream.cuda_stream)

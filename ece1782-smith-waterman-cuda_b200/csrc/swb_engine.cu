@@ -15,7 +15,7 @@
 
 #define SWB_MAX_SLOTS 24
 #define SWB_MAX_COUNTERS 256
-#define SWB_MAX_SUB 2  // extra streams per slot: up to three distinct K values per query
+#define SWB_MAX_SUB 3  // extra streams per slot: up to three distinct K values plus the split group per query
 #define SWB_CHUNK_ROWS 7168u          // query rows per launch when a query does not fit shared memory
 #define SWB_SMALL_SMEM_LIMIT (100u * 1024u)
 #define SWB_STAGE_BYTES (32u << 20)   // pinned staging buffers for the raw database upload
@@ -31,9 +31,9 @@ static double wall_ms()
 
 struct Slot {
     cudaStream_t stream = nullptr;
-    cudaStream_t sub[SWB_MAX_SUB] = {nullptr, nullptr};
+    cudaStream_t sub[SWB_MAX_SUB] = {};
     cudaEvent_t ev_fork = nullptr;
-    cudaEvent_t ev_sub[SWB_MAX_SUB] = {nullptr, nullptr};
+    cudaEvent_t ev_sub[SWB_MAX_SUB] = {};
     cudaEvent_t done = nullptr;
     bool busy = false;
     bool ready = false;  // scratch sized for the loaded database
@@ -46,6 +46,8 @@ struct Slot {
     size_t state_bytes = 0, state_cap = 0;
     uint32_t *d_counters = nullptr;
     uint32_t *d_recount = nullptr;  // tiles re-scored in int32, zeroed per batch
+    uint32_t *d_prog = nullptr;     // progress counters of the split (pipelined-pass) launches, zeroed per query
+    size_t prog_cap = 0;
     uint8_t *d_flags = nullptr;
     int32_t *d_sorted = nullptr;
     uint32_t *d_bnd16 = nullptr;
@@ -76,6 +78,7 @@ struct swb_engine {
     // options
     SwbPlanOpts plan_opts;
     int opt_k = 0;
+    int opt_split = 1;        // pipelined passes for the very long tiles
     int opt_group_order = 0;  // 0 auto (lone query: longest tiles first; batch: bulk first), 1 longest first, 2 bulk first
     uint32_t cur_nq = 1;
     int nslots = 16;
@@ -132,6 +135,9 @@ static void free_slot_db(Slot &s)
     if (s.d_state) cudaFree(s.d_state);
     if (s.d_bnd16) cudaFree(s.d_bnd16);
     if (s.d_bnd32) cudaFree(s.d_bnd32);
+    if (s.d_prog) cudaFree(s.d_prog);
+    s.d_prog = nullptr;
+    s.prog_cap = 0;
     if (s.h_scores) cudaFreeHost(s.h_scores);
     s.d_state = nullptr;
     s.d_bnd16 = nullptr;
@@ -284,6 +290,11 @@ extern "C" int swb_set_option(swb_engine *e, const char *key, int64_t value)
     } else if (!strcmp(key, "streams")) {
         if (value < 1 || value > SWB_MAX_SLOTS) return fail(e, SWB_ERR_ARG, "streams must be 1..24");
         e->nslots = (int)value;
+    } else if (!strcmp(key, "xl_len")) {
+        if (value < 0 || value > (1ll << 31)) return fail(e, SWB_ERR_ARG, "xl_len out of range");
+        e->plan_opts.xl_len = (uint32_t)value;
+    } else if (!strcmp(key, "split")) {
+        e->opt_split = value != 0;
     } else if (!strcmp(key, "group_order")) {
         if (value < 0 || value > 2) return fail(e, SWB_ERR_ARG, "group_order must be 0, 1 or 2");
         e->opt_group_order = (int)value;
@@ -487,14 +498,14 @@ struct LaunchShape {
     uint32_t smem_rows;
 };
 
-static int shape_for(swb_engine *e, int K, bool i32, uint32_t smem_rows, uint32_t ntiles, LaunchShape &ls)
+static int shape_for(swb_engine *e, int K, bool i32, bool split, uint32_t smem_rows, uint32_t ntiles, LaunchShape &ls)
 {
     ls.smem_rows = smem_rows;
     ls.smem = (size_t)SWB_ALPHA * (smem_rows + 4);
     if (ls.smem > e->smem_optin) return fail(e, SWB_ERR_ARG, "internal: query chunk does not fit shared memory");
     ls.block_cfg = ls.smem <= SWB_SMALL_SMEM_LIMIT ? SWB_BLOCK_SMALL : SWB_BLOCK_LARGE;
     int per_sm = 0;
-    CU(swb_score_occupancy(K, i32, ls.block_cfg, ls.smem, &per_sm));
+    CU(swb_score_occupancy(K, i32, split, ls.block_cfg, ls.smem, &per_sm));
     if (per_sm < 1) return fail(e, SWB_ERR_CUDA, "score kernel does not fit on an SM");
     const int nt = ls.block_cfg == SWB_BLOCK_SMALL ? SWB_NT_SMALL : SWB_NT_LARGE;
     const int need = (int)((ntiles + nt / 32 - 1) / (nt / 32));
@@ -549,10 +560,10 @@ static int enqueue_query(swb_engine *e, Slot &s, uint32_t qi, const uint8_t *q, 
     std::vector<SwbLaunchGroup> groups[2];
     swb_plan_query(qlen, e->opt_k, 32, present, e->chunk_rows, qp[0]);
     const bool longest_first = e->opt_group_order == 1 || (e->opt_group_order == 0 && e->cur_nq <= 1);
-    swb_plan_launch_groups(pl, qp[0], longest_first, groups[0]);
+    swb_plan_launch_groups(pl, qp[0], longest_first, e->opt_split != 0, groups[0]);
     if (need_i32) {
         swb_plan_query(qlen, e->opt_k, 16, present, e->chunk_rows, qp[1]);
-        swb_plan_launch_groups(pl, qp[1], longest_first, groups[1]);
+        swb_plan_launch_groups(pl, qp[1], longest_first, false, groups[1]);
     }
     const int npass = need_i32 ? 2 : 1;
     size_t nlaunch = 0;
@@ -580,11 +591,18 @@ static int enqueue_query(swb_engine *e, Slot &s, uint32_t qi, const uint8_t *q, 
         s.prof_cap = cap;
     }
     if (need_i32) CU(GROW_DEV(s.d_bnd32, s.bnd32_cap, 8ull * pl.bnd_elems));
+    // progress counters of the split group: one per (very long tile, pass) and chunk
+    size_t prog_words = 0;
+    if (!groups[0].empty() && groups[0][0].split)
+        for (size_t c = 0; c < qp[0].chunks.size(); ++c)
+            prog_words += (size_t)groups[0][0].ntiles * swb_split_passes(qp[0].chunks[c].rows);
+    if (prog_words) CU(GROW_DEV(s.d_prog, s.prog_cap, sizeof(uint32_t) * prog_words));
 
     memcpy(s.h_query, q, qlen);
     CU(cudaMemcpyAsync(s.d_query, s.h_query, qlen, cudaMemcpyHostToDevice, s.stream));
     CU(swb_launch_profile(s.d_query, qlen, e->d_mat, e->gap, s.d_prof, prof_stride, prof_rows, s.stream));
     CU(cudaMemsetAsync(s.d_state, 0, s.state_bytes, s.stream));
+    if (prog_words) CU(cudaMemsetAsync(s.d_prog, 0, sizeof(uint32_t) * prog_words, s.stream));
     e->stats.kernel_launches += 1;
 
     SwbScoreParams p;
@@ -613,15 +631,19 @@ static int enqueue_query(swb_engine *e, Slot &s, uint32_t qi, const uint8_t *q, 
         for (size_t gi = 0; gi < ng; ++gi) {
             const SwbLaunchGroup &g = groups[pass][gi];
             cudaStream_t st = gi == 0 ? s.stream : s.sub[gi - 1];
-            p.ntiles = g.ntiles;
             for (int r = 0; r < SWB_MAX_RANGES; ++r) {
                 p.range_start[r] = g.range_start[r];
                 p.range_cum[r] = g.range_cum[r];
             }
+            size_t prog_at = 0;
             for (size_t c = 0; c < qp[pass].chunks.size(); ++c) {
                 const SwbQueryChunk &ch = qp[pass].chunks[c];
+                p.split_passes = g.split ? swb_split_passes(ch.rows) : 0;
+                p.ntiles = g.split ? g.ntiles * p.split_passes : g.ntiles;  // work items of the launch
+                p.prog = g.split ? s.d_prog + prog_at : nullptr;
+                prog_at += (size_t)g.ntiles * p.split_passes;
                 LaunchShape ls;
-                int rc = shape_for(e, g.K, i32, swb_group_smem_rows(ch.rows, g), g.ntiles, ls);
+                int rc = shape_for(e, g.K, i32, g.split, swb_group_smem_rows(ch.rows, g), p.ntiles, ls);
                 if (rc != SWB_OK) return rc;
                 p.row0 = ch.row0;
                 p.rows = ch.rows;
@@ -629,7 +651,7 @@ static int enqueue_query(swb_engine *e, Slot &s, uint32_t qi, const uint8_t *q, 
                 p.first_chunk = ch.first;
                 p.last_chunk = ch.last;
                 p.counter = s.d_counters + counter++;
-                CU(swb_launch_score(g.K, i32, ls.block_cfg, p, ls.grid, ls.smem, st));
+                CU(swb_launch_score(g.K, i32, g.split, ls.block_cfg, p, ls.grid, ls.smem, st));
                 e->stats.kernel_launches += 1;
             }
         }

@@ -23,6 +23,19 @@ struct DevBackend {
         return __shfl_sync(0xffffffffu, v, 0);
     }
     __device__ __forceinline__ void count(uint32_t *p) const { atomicAdd(p, 1u); }
+    __device__ __forceinline__ void atomic_max(int32_t *p, int32_t v) const { atomicMax(p, v); }
+    // progress counters of SPLIT launches: publish after the boundary stores are visible, poll with a volatile load
+    __device__ __forceinline__ void publish(uint32_t *p, uint32_t v) const
+    {
+        __threadfence();
+        *reinterpret_cast<volatile uint32_t *>(p) = v;
+    }
+    __device__ __forceinline__ uint32_t poll(const uint32_t *p) const
+    {
+        const uint32_t v = *reinterpret_cast<const volatile uint32_t *>(p);
+        __threadfence();
+        return v;
+    }
     __device__ __forceinline__ uint8_t ld_flag(const uint8_t *p) const { return __ldcg(p); }
     __device__ __forceinline__ SwbTile ld_tile(const SwbTile *p) const
     {
@@ -47,7 +60,7 @@ static_assert(sizeof(SwbTile) == 32, "SwbTile must be 32 bytes");
 // Shared profile layout: [32 codes][smem_rows + 4] int8. The +4 makes consecutive code rows start one
 // bank apart, so the 32 lanes of an LDS.32 (same row offset, per-lane code) never conflict: equal
 // codes broadcast, different codes hit different banks.
-template <int K, class V, int NT, int MINB>
+template <int K, class V, int NT, int MINB, bool SPLIT>
 __global__ void __launch_bounds__(NT, MINB) swb_score_kernel(const SwbScoreParams p)
 {
     extern __shared__ __align__(16) int8_t sprof[];
@@ -60,7 +73,7 @@ __global__ void __launch_bounds__(NT, MINB) swb_score_kernel(const SwbScoreParam
     }
     __syncthreads();
     DevBackend be;
-    swb_warp_loop<K, V>(be, p, sprof, sstride);
+    swb_warp_loop<K, V, SPLIT>(be, p, sprof, sstride);
 }
 
 // profile[code][r] = S(q_r, code) + bias for r < qlen, bias (score 0) for the padding rows; bias = gap + t0.
@@ -102,63 +115,68 @@ __global__ void swb_scatter_kernel(const int32_t *__restrict__ sorted, const uin
 }
 
 // ---------------------------------------------------------------------------------------------
-template <int K, class V, int NT, int MINB>
+template <int K, class V, int NT, int MINB, bool SPLIT>
 static cudaError_t launch_one(const SwbScoreParams &p, int grid, size_t smem, cudaStream_t st)
 {
-    auto kern = swb_score_kernel<K, V, NT, MINB>;
+    auto kern = swb_score_kernel<K, V, NT, MINB, SPLIT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<grid, NT, smem, st>>>(p);
     return cudaGetLastError();
 }
 
-template <int K, class V, int NT, int MINB>
+template <int K, class V, int NT, int MINB, bool SPLIT>
 static cudaError_t occ_one(size_t smem, int *blocks)
 {
-    auto kern = swb_score_kernel<K, V, NT, MINB>;
+    auto kern = swb_score_kernel<K, V, NT, MINB, SPLIT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, kern, NT, smem);
 }
 
 // op: 0 = launch, 1 = occupancy query
-template <int K, class V>
+template <int K, class V, bool SPLIT>
 static cudaError_t dispatch_cfg(int op, int block_cfg, const SwbScoreParams *p, int grid, size_t smem, cudaStream_t st,
                                 int *blocks)
 {
     if (block_cfg == SWB_BLOCK_SMALL)
-        return op == 0 ? launch_one<K, V, SWB_NT_SMALL, SWB_MINB_SMALL>(*p, grid, smem, st)
-                       : occ_one<K, V, SWB_NT_SMALL, SWB_MINB_SMALL>(smem, blocks);
-    return op == 0 ? launch_one<K, V, SWB_NT_LARGE, 1>(*p, grid, smem, st) : occ_one<K, V, SWB_NT_LARGE, 1>(smem, blocks);
+        return op == 0 ? launch_one<K, V, SWB_NT_SMALL, SWB_MINB_SMALL, SPLIT>(*p, grid, smem, st)
+                       : occ_one<K, V, SWB_NT_SMALL, SWB_MINB_SMALL, SPLIT>(smem, blocks);
+    return op == 0 ? launch_one<K, V, SWB_NT_LARGE, 1, SPLIT>(*p, grid, smem, st)
+                   : occ_one<K, V, SWB_NT_LARGE, 1, SPLIT>(smem, blocks);
 }
 
-static cudaError_t dispatch(int op, int K, bool i32, int block_cfg, const SwbScoreParams *p, int grid, size_t smem,
-                            cudaStream_t st, int *blocks)
+static cudaError_t dispatch(int op, int K, bool i32, bool split, int block_cfg, const SwbScoreParams *p, int grid,
+                            size_t smem, cudaStream_t st, int *blocks)
 {
+    if (split) {  // pipelined passes: s16 only, K = 8
+        if (i32 || K != 8) return cudaErrorInvalidValue;
+        return dispatch_cfg<8, V16, true>(op, block_cfg, p, grid, smem, st, blocks);
+    }
     if (!i32) {
         switch (K) {
-        case 8: return dispatch_cfg<8, V16>(op, block_cfg, p, grid, smem, st, blocks);
-        case 16: return dispatch_cfg<16, V16>(op, block_cfg, p, grid, smem, st, blocks);
-        case 32: return dispatch_cfg<32, V16>(op, block_cfg, p, grid, smem, st, blocks);
+        case 8: return dispatch_cfg<8, V16, false>(op, block_cfg, p, grid, smem, st, blocks);
+        case 16: return dispatch_cfg<16, V16, false>(op, block_cfg, p, grid, smem, st, blocks);
+        case 32: return dispatch_cfg<32, V16, false>(op, block_cfg, p, grid, smem, st, blocks);
         }
     } else {
         switch (K) {
-        case 8: return dispatch_cfg<8, V32>(op, block_cfg, p, grid, smem, st, blocks);
-        case 16: return dispatch_cfg<16, V32>(op, block_cfg, p, grid, smem, st, blocks);
+        case 8: return dispatch_cfg<8, V32, false>(op, block_cfg, p, grid, smem, st, blocks);
+        case 16: return dispatch_cfg<16, V32, false>(op, block_cfg, p, grid, smem, st, blocks);
         }
     }
     return cudaErrorInvalidValue;
 }
 
-cudaError_t swb_launch_score(int K, bool i32, int block_cfg, const SwbScoreParams &p, int grid, size_t smem,
+cudaError_t swb_launch_score(int K, bool i32, bool split, int block_cfg, const SwbScoreParams &p, int grid, size_t smem,
                              cudaStream_t st)
 {
-    return dispatch(0, K, i32, block_cfg, &p, grid, smem, st, nullptr);
+    return dispatch(0, K, i32, split, block_cfg, &p, grid, smem, st, nullptr);
 }
 
-cudaError_t swb_score_occupancy(int K, bool i32, int block_cfg, size_t smem, int *blocks)
+cudaError_t swb_score_occupancy(int K, bool i32, bool split, int block_cfg, size_t smem, int *blocks)
 {
-    return dispatch(1, K, i32, block_cfg, nullptr, 0, smem, nullptr, blocks);
+    return dispatch(1, K, i32, split, block_cfg, nullptr, 0, smem, nullptr, blocks);
 }
 
 cudaError_t swb_launch_profile(const uint8_t *q, uint32_t qlen, const int8_t *mat, int bias, int8_t *prof,
@@ -243,7 +261,7 @@ __global__ void __launch_bounds__(512) swb_align_kernel(const uint8_t *__restric
         }
         uint32_t i = bi, j = bj, nops = 0;
         bool overflow = false;
-        while (best > 0) {
+        while (best > 0 && i > 0 && j > 0) {  // row 0 / column 0 are the H == 0 border (never written)
             const uint8_t t = dir[(size_t)i * W + j];
             if (t == 0) break;
             if (nops < cap) out_ops[nops] = t; else overflow = true;

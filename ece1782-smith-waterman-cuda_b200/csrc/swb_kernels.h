@@ -11,10 +11,11 @@
 #define SWB_MINB_SMALL 2
 #define SWB_NT_LARGE 512
 
-// K: query rows per lane (8, 16, 32; int32 pass 8 or 16). i32: the exact recompute policy.
-cudaError_t swb_launch_score(int K, bool i32, int block_cfg, const SwbScoreParams &p, int grid, size_t smem,
+// K: query rows per lane (8, 16, 32; int32 pass 8 or 16). i32: the exact recompute policy. split: the passes of a
+// tile are separate, pipelined work items (very long sequences; s16, K = 8 only).
+cudaError_t swb_launch_score(int K, bool i32, bool split, int block_cfg, const SwbScoreParams &p, int grid, size_t smem,
                              cudaStream_t st);
-cudaError_t swb_score_occupancy(int K, bool i32, int block_cfg, size_t smem, int *blocks_per_sm);
+cudaError_t swb_score_occupancy(int K, bool i32, bool split, int block_cfg, size_t smem, int *blocks_per_sm);
 cudaError_t swb_launch_profile(const uint8_t *q, uint32_t qlen, const int8_t *mat, int bias, int8_t *prof,
                                uint32_t stride, uint32_t rows, cudaStream_t st);
 cudaError_t swb_launch_pack(const SwbTile *tiles, uint32_t ntiles, const uint8_t *raw, const uint64_t *seq_off,

@@ -116,6 +116,9 @@ int swb_build_plan(const uint64_t *offsets, uint32_t n, uint32_t shard, uint32_t
             plan.tile_start_by_logg[l] = at;
             at += plan.tiles_by_logg[l];
         }
+        plan.n_xl = 0;
+        if (o.xl_len)
+            while (plan.n_xl < plan.tiles_by_logg[SWB_MAX_LOGG] && plan.tiles[plan.n_xl].width > o.xl_len) ++plan.n_xl;
     }
     uint64_t res = 0, bnd = 0;
     for (size_t i = 0; i < plan.tiles.size(); ++i) {
@@ -172,10 +175,11 @@ void swb_plan_query(uint32_t qlen, int k_force, int k_max, uint32_t logg_present
     }
 }
 
-void swb_plan_launch_groups(const SwbPlan &plan, const SwbQueryPlan &qp, bool longest_first,
+void swb_plan_launch_groups(const SwbPlan &plan, const SwbQueryPlan &qp, bool longest_first, bool with_split,
                             std::vector<SwbLaunchGroup> &groups)
 {
     groups.clear();
+    const uint32_t n_xl = with_split ? plan.n_xl : 0;
     for (int K = 32; K >= 8; K >>= 1) {
         SwbLaunchGroup g;
         memset(&g, 0, sizeof g);
@@ -183,9 +187,11 @@ void swb_plan_launch_groups(const SwbPlan &plan, const SwbQueryPlan &qp, bool lo
         uint32_t nr = 0;
         for (int l = SWB_MAX_LOGG; l >= 0; --l) {
             if (!plan.tiles_by_logg[l] || qp.k_by_logg[l] != K) continue;
+            const uint32_t skip = l == SWB_MAX_LOGG ? n_xl : 0;  // the very long tiles go to the split group
+            if (plan.tiles_by_logg[l] == skip) continue;
             g.logg_mask |= 1u << l;
-            g.range_start[nr] = plan.tile_start_by_logg[l];
-            g.ntiles += plan.tiles_by_logg[l];
+            g.range_start[nr] = plan.tile_start_by_logg[l] + skip;
+            g.ntiles += plan.tiles_by_logg[l] - skip;
             g.range_cum[nr] = g.ntiles;
             ++nr;
         }
@@ -200,11 +206,22 @@ void swb_plan_launch_groups(const SwbPlan &plan, const SwbQueryPlan &qp, bool lo
     // tiles, goes first and the bulk last; a small group occupies few blocks, so the bulk still finds room and runs
     // beside it, and the long tiles are not left for the end. Otherwise (a batch: the next query fills the GPU
     // while this one drains) the bulk goes first.
+    if (n_xl) {  // always first: its few warps then run beside everything else
+        SwbLaunchGroup g;
+        memset(&g, 0, sizeof g);
+        g.K = 8;
+        g.split = true;
+        g.logg_mask = 1u << SWB_MAX_LOGG;
+        g.ntiles = n_xl;
+        for (uint32_t r = 0; r < SWB_MAX_RANGES; ++r) g.range_cum[r] = n_xl;
+        groups.insert(groups.begin(), g);
+    }
+    std::vector<SwbLaunchGroup>::iterator first = groups.begin() + (n_xl ? 1 : 0);
     if (longest_first)
-        std::stable_sort(groups.begin(), groups.end(),
+        std::stable_sort(first, groups.end(),
                          [](const SwbLaunchGroup &a, const SwbLaunchGroup &b) { return a.logg_mask > b.logg_mask; });
     else
-        std::stable_sort(groups.begin(), groups.end(),
+        std::stable_sort(first, groups.end(),
                          [](const SwbLaunchGroup &a, const SwbLaunchGroup &b) { return a.ntiles > b.ntiles; });
 }
 

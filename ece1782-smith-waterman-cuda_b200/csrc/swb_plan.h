@@ -8,7 +8,8 @@
 struct SwbPlanOpts {
     uint32_t group_len;   // sequences up to this length run one lane per pair (G=1); each doubling of the
                           // length doubles G up to 32
-    SwbPlanOpts() : group_len(384) {}
+    uint32_t xl_len;      // 32-lane tiles wider than this run their passes as pipelined work items (0 = never)
+    SwbPlanOpts() : group_len(384), xl_len(8192) {}
 };
 
 struct SwbPlan {
@@ -30,6 +31,7 @@ struct SwbPlan {
     uint32_t max_len;                 // longest sequence of the shard
     uint32_t tiles_by_logg[SWB_MAX_LOGG + 1];
     uint32_t tile_start_by_logg[SWB_MAX_LOGG + 1];  // tiles are stored by group size, 32 lanes first
+    uint32_t n_xl;                    // leading 32-lane tiles wider than xl_len (the very long sequences)
     uint64_t cols_by_logg[SWB_MAX_LOGG + 1];  // padded sequence-columns (width * slots * 2) per group size
 };
 
@@ -60,6 +62,7 @@ void swb_plan_query(uint32_t qlen, int k_force, int k_max, uint32_t logg_present
 // One score-kernel launch of a query pass: the tiles of all group sizes that share the same K.
 struct SwbLaunchGroup {
     int K;
+    bool split;          // pipelined passes over the plan's n_xl leading tiles (K = 8, s16 only)
     uint32_t logg_mask;
     uint32_t ntiles;
     uint32_t range_start[SWB_MAX_RANGES];
@@ -67,7 +70,10 @@ struct SwbLaunchGroup {
 };
 // one group per distinct K; longest_first puts the group owning the longest tiles first (lone query), otherwise the
 // group with most tiles first (batch); inside a group the ranges run from the largest group size (longest tiles) down
-void swb_plan_launch_groups(const SwbPlan &plan, const SwbQueryPlan &qp, bool longest_first,
+// with_split: give the very long tiles their own pipelined group (s16 pass); otherwise they stay in the 32-lane range
+void swb_plan_launch_groups(const SwbPlan &plan, const SwbQueryPlan &qp, bool longest_first, bool with_split,
                             std::vector<SwbLaunchGroup> &groups);
+// passes (work items per tile) of a split group for a chunk of `rows` query rows
+inline uint32_t swb_split_passes(uint32_t rows) { return (rows + 255u) / 256u; }
 // rows a launch group must find in shared memory for a chunk of `rows` query rows (multiple of 128)
 uint32_t swb_group_smem_rows(uint32_t rows, const SwbLaunchGroup &g);

@@ -51,6 +51,9 @@ struct SwbScoreParams {
     // tiles of this launch: positions [0, ntiles) of the concatenation of up to SWB_MAX_RANGES ranges of `tiles`
     uint32_t range_start[SWB_MAX_RANGES];
     uint32_t range_cum[SWB_MAX_RANGES];  // cumulative tile count up to and including range r
+    // SPLIT launches (very long sequences): ntiles counts (tile, pass) items of range 0, split_passes per tile
+    uint32_t split_passes;
+    uint32_t *prog;           // [tiles of range 0][split_passes] columns published by each pass (zeroed per query)
 };
 
 SWB_HD uint32_t swb_roundup(uint32_t v, uint32_t m) { return (v + m - 1) / m * m; }

@@ -213,9 +213,16 @@ struct V32 {
 //   G == 1 : [chunk c][lane][4 columns]   -> one 16/32-byte vector per lane and chunk
 //   G  > 1 : [slot][column]               -> the first lane of a group reads 4 columns as one vector, the last lane
 //                                            writes scalars (its columns lag G-1 behind, so they are not 4-aligned)
-template <int K, class V, bool GROUPED, class BE>
+//
+// SPLIT (32-lane tiles of very long sequences only): the passes of one tile are separate work items taken by different
+// warps, which run as a pipeline over the columns. The warp of pass ss publishes how many columns of its bottom row are
+// in the boundary scratch (prog[ss], every 32 columns, after a fence); the warp of pass ss+1 polls it before it reads
+// them. Items are handed out in (tile, pass) order by one counter, so a waiting warp always waits for an item that a
+// resident warp already owns: no deadlock. Scores of the passes are combined with atomicMax.
+template <int K, class V, bool GROUPED, bool SPLIT, class BE>
 SWB_HD void swb_run_tile(BE &be, const SwbScoreParams &p, const SwbTile &tile, uint32_t tile_idx,
-                         const int8_t *sprof, uint32_t sstride)
+                         const int8_t *sprof, uint32_t sstride, uint32_t ss_begin = 0, uint32_t ss_count = 0xffffffffu,
+                         uint32_t *prog = nullptr)
 {
     typedef typename V::T T;
     const typename V::C cst = V::consts(p);
@@ -239,10 +246,13 @@ SWB_HD void swb_run_tile(BE &be, const SwbScoreParams &p, const SwbTile &tile, u
     T *bnd = reinterpret_cast<T *>(p.bnd) + tile.bnd_off;
     T best = HZERO;
 
-    for (uint32_t ss = 0; ss < nsuper; ++ss) {
+    const uint32_t ss_end = ss_count < nsuper - ss_begin ? ss_begin + ss_count : nsuper;
+    for (uint32_t ss = ss_begin; ss < ss_end; ++ss) {
         const int8_t *prow = sprof + (size_t)(((ss << logG) + (uint32_t)g) * (uint32_t)K);
         const bool read_top = !(p.first_chunk && ss == 0);
         const bool write_bot = !(p.last_chunk && ss + 1 == nsuper);
+        const bool wait_top = SPLIT && ss > 0;  // the row above comes from another warp of this launch
+        uint32_t avail = 0;                     // columns of that row known to be in the scratch
         T left[K];
 #pragma unroll
         for (int k = 0; k < K; ++k) left[k] = LZERO;
@@ -266,12 +276,16 @@ SWB_HD void swb_run_tile(BE &be, const SwbScoreParams &p, const SwbTile &tile, u
                 ca[u] = be.ld_code(res + 2 * u);
                 cb[u] = be.ld_code(res + 2 * u + 1);
             }
-            if (read_top) {
-                if (!GROUPED) {
-                    V::ld4(be, bnd + (size_t)lane * 4u, bc);
-                } else {
-                    V::ld4(be, bnd + (size_t)slot * W, bc);
-                }
+        }
+        if (wait_top) {
+            const uint32_t need = W < 4u ? W : 4u;
+            while (avail < need) avail = be.poll(prog + ss - 1);
+        }
+        if (lead && nchunks > 0 && read_top) {
+            if (!GROUPED) {
+                V::ld4(be, bnd + (size_t)lane * 4u, bc);
+            } else {
+                V::ld4(be, bnd + (size_t)slot * W, bc);
             }
         }
         for (uint32_t c = 0; c < nsteps4; ++c) {
@@ -283,6 +297,10 @@ SWB_HD void swb_run_tile(BE &be, const SwbScoreParams &p, const SwbTile &tile, u
                 na[u] = SWB_PAD;
                 nb[u] = SWB_PAD;
                 bn[u] = HZERO;
+            }
+            if (wait_top && c + 1 < nchunks) {
+                const uint32_t need = 4u * c + 8u < W ? 4u * c + 8u : W;
+                while (avail < need) avail = be.poll(prog + ss - 1);
             }
             if (lead && c + 1 < nchunks) {
                 const uint8_t *rnext = res + (size_t)(c + 1) * res_stride;
@@ -325,6 +343,10 @@ SWB_HD void swb_run_tile(BE &be, const SwbScoreParams &p, const SwbTile &tile, u
 #pragma unroll
                     for (int u = 0; u < 4; ++u)
                         if (col0 + u >= 0 && col0 + u < (int32_t)W) V::st(be, dst + u, outb[u]);
+                    if (SPLIT && ((c & 7u) == 7u || c + 1 == nsteps4)) {
+                        const int32_t done = col0 + 4 < 0 ? 0 : (col0 + 4 > (int32_t)W ? (int32_t)W : col0 + 4);
+                        be.publish(prog + ss, (uint32_t)done);
+                    }
                 }
             }
 #pragma unroll
@@ -344,13 +366,18 @@ SWB_HD void swb_run_tile(BE &be, const SwbScoreParams &p, const SwbTile &tile, u
     if (lead && slot < (int)tile.npairs) {
         const size_t s0 = 2u * ((size_t)tile.first_pair + (size_t)slot);
         int a = V::score_lo(best, cst), b = V::score_hi(best, cst);
-        if (!p.first_chunk) {
-            const int pa = p.scores[s0], pb = p.scores[s0 + 1];
-            a = a > pa ? a : pa;
-            b = b > pb ? b : pb;
+        if (SPLIT) {
+            be.atomic_max(p.scores + s0, a);
+            be.atomic_max(p.scores + s0 + 1, b);
+        } else {
+            if (!p.first_chunk) {
+                const int pa = p.scores[s0], pb = p.scores[s0 + 1];
+                a = a > pa ? a : pa;
+                b = b > pb ? b : pb;
+            }
+            p.scores[s0] = a;
+            p.scores[s0 + 1] = b;
         }
-        p.scores[s0] = a;
-        p.scores[s0 + 1] = b;
         flagged = V::is16 && ((a > b ? a : b) > p.ovf_thr);
     }
     if (V::is16) {
@@ -362,13 +389,21 @@ SWB_HD void swb_run_tile(BE &be, const SwbScoreParams &p, const SwbTile &tile, u
 
 // Per-warp loop over the dynamically scheduled tiles of one launch. A launch covers up to SWB_MAX_RANGES
 // ranges of the tile array (the tiles of the group sizes that use this kernel's K for this query); the shared
-// counter hands out positions of the concatenated ranges, longest tiles first.
-template <int K, class V, class BE>
+// counter hands out positions of the concatenated ranges, longest tiles first. SPLIT launches hand out (tile, pass)
+// items of the first range instead.
+template <int K, class V, bool SPLIT, class BE>
 SWB_HD void swb_warp_loop(BE &be, const SwbScoreParams &p, const int8_t *sprof, uint32_t sstride)
 {
     for (;;) {
         const uint32_t v = be.next_tile(p.counter);
         if (v >= p.ntiles) break;
+        if (SPLIT) {
+            const uint32_t t = v / p.split_passes, ss = v - t * p.split_passes;
+            const uint32_t ti = p.range_start[0] + t;
+            const SwbTile tile = be.ld_tile(p.tiles + ti);
+            swb_run_tile<K, V, true, true>(be, p, tile, ti, sprof, sstride, ss, 1u, p.prog + (size_t)t * p.split_passes);
+            continue;
+        }
         uint32_t ti = p.range_start[0] + v;
 #pragma unroll
         for (int r = 1; r < SWB_MAX_RANGES; ++r)
@@ -376,9 +411,9 @@ SWB_HD void swb_warp_loop(BE &be, const SwbScoreParams &p, const int8_t *sprof, 
         if (p.only_flagged && !be.ld_flag(p.flags + ti)) continue;
         const SwbTile tile = be.ld_tile(p.tiles + ti);
         if (tile.logG == 0)
-            swb_run_tile<K, V, false>(be, p, tile, ti, sprof, sstride);
+            swb_run_tile<K, V, false, false>(be, p, tile, ti, sprof, sstride);
         else
-            swb_run_tile<K, V, true>(be, p, tile, ti, sprof, sstride);
+            swb_run_tile<K, V, true, false>(be, p, tile, ti, sprof, sstride);
     }
 }
 

@@ -4,6 +4,7 @@
 // boundary-scratch, chunking and overflow-recompute logic can be checked against the oracle in the
 // build container, which has no GPU. DPX intrinsics use the host implementations CUDA ships.
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 #include <ucontext.h>
 #include <algorithm>
@@ -26,6 +27,16 @@ struct HostBackend {
     bool any(bool f);
     uint32_t next_tile(uint32_t *counter);
     void count(uint32_t *p) { (*p)++; }
+    void atomic_max(int32_t *p, int32_t v) { if (v > *p) *p = v; }
+    void publish(uint32_t *p, uint32_t v) { *p = v; }
+    // the emulation runs the work items one after the other in hand-out order, so whatever a pass waits for must
+    // already be there: a value that is too small here would be a deadlock on the GPU
+    uint32_t poll(const uint32_t *p)
+    {
+        if (++polls > 100000000ull) abort();  // a spin that never ends = the hand-out order guarantee is broken
+        return *p;
+    }
+    unsigned long long polls = 0;
     uint8_t ld_flag(const uint8_t *p) const { return *p; }
     SwbTile ld_tile(const SwbTile *p) const { return *p; }
     uint32_t ld_code(const uint8_t *p) const { return *p; }
@@ -144,18 +155,21 @@ struct LaneArgs {
     uint32_t sstride;
     int K;
     bool i32;
+    bool split;
 };
 
 void lane_main(HostBackend &be, void *a)
 {
     const LaneArgs *la = static_cast<const LaneArgs *>(a);
-    if (!la->i32) {
-        if (la->K == 8) swb_warp_loop<8, V16>(be, *la->p, la->sprof, la->sstride);
-        else if (la->K == 16) swb_warp_loop<16, V16>(be, *la->p, la->sprof, la->sstride);
-        else swb_warp_loop<32, V16>(be, *la->p, la->sprof, la->sstride);
+    if (la->split) {
+        swb_warp_loop<8, V16, true>(be, *la->p, la->sprof, la->sstride);
+    } else if (!la->i32) {
+        if (la->K == 8) swb_warp_loop<8, V16, false>(be, *la->p, la->sprof, la->sstride);
+        else if (la->K == 16) swb_warp_loop<16, V16, false>(be, *la->p, la->sprof, la->sstride);
+        else swb_warp_loop<32, V16, false>(be, *la->p, la->sprof, la->sstride);
     } else {
-        if (la->K == 8) swb_warp_loop<8, V32>(be, *la->p, la->sprof, la->sstride);
-        else swb_warp_loop<16, V32>(be, *la->p, la->sprof, la->sstride);
+        if (la->K == 8) swb_warp_loop<8, V32, false>(be, *la->p, la->sprof, la->sstride);
+        else swb_warp_loop<16, V32, false>(be, *la->p, la->sprof, la->sstride);
     }
 }
 
@@ -169,10 +183,11 @@ void lane_main(HostBackend &be, void *a)
 extern "C" int swbemu_search(const uint8_t *codes, const uint64_t *offsets, uint32_t n, uint32_t shard,
                              uint32_t nshards, uint32_t group_len, const int8_t *mat32, int gap, const uint8_t *q,
                              uint32_t qlen, int K, int force_i32, uint32_t chunk_rows, int ovf_thr_override,
-                             int32_t *scores_out, uint32_t *recomputed_tiles)
+                             uint32_t xl_len, int32_t *scores_out, uint32_t *recomputed_tiles)
 {
     SwbPlanOpts o;
     if (group_len) o.group_len = group_len;
+    o.xl_len = xl_len;
     SwbPlan pl;
     if (swb_build_plan(offsets, n, shard, nshards ? nshards : 1, o, pl) != 0) return -1;
     const uint32_t nl = pl.n_local;
@@ -207,8 +222,8 @@ extern "C" int swbemu_search(const uint8_t *codes, const uint64_t *offsets, uint
     std::vector<SwbLaunchGroup> groups[2];
     swb_plan_query(qlen, K, 32, present, chunk_rows, qp[0]);
     swb_plan_query(qlen, K, 16, present, chunk_rows, qp[1]);
-    swb_plan_launch_groups(pl, qp[0], true, groups[0]);
-    swb_plan_launch_groups(pl, qp[1], true, groups[1]);
+    swb_plan_launch_groups(pl, qp[0], true, true, groups[0]);
+    swb_plan_launch_groups(pl, qp[1], true, false, groups[1]);
     const uint32_t prof_rows = std::max(qp[0].prof_rows, qp[1].prof_rows);
     const uint32_t prof_stride = swb_roundup(prof_rows, 16);
     std::vector<int8_t> prof((size_t)prof_stride * SWB_ALPHA);
@@ -241,13 +256,16 @@ extern "C" int swbemu_search(const uint8_t *codes, const uint64_t *offsets, uint
         p.only_flagged = (i32 && !force_i32) ? 1u : 0u;
         for (size_t gi = 0; gi < groups[pass].size(); ++gi) {
             const SwbLaunchGroup &g = groups[pass][gi];
-            p.ntiles = g.ntiles;
             for (int r = 0; r < SWB_MAX_RANGES; ++r) {
                 p.range_start[r] = g.range_start[r];
                 p.range_cum[r] = g.range_cum[r];
             }
             for (size_t c = 0; c < qp[pass].chunks.size(); ++c) {
                 const SwbQueryChunk &ch = qp[pass].chunks[c];
+                p.split_passes = g.split ? swb_split_passes(ch.rows) : 0;
+                p.ntiles = g.split ? g.ntiles * p.split_passes : g.ntiles;
+                std::vector<uint32_t> prog((size_t)g.ntiles * p.split_passes + 1, 0u);
+                p.prog = prog.data();
                 p.row0 = ch.row0;
                 p.rows = ch.rows;
                 p.smem_rows = swb_group_smem_rows(ch.rows, g);
@@ -267,6 +285,7 @@ extern "C" int swbemu_search(const uint8_t *codes, const uint64_t *offsets, uint
                 la.sstride = sstride;
                 la.K = g.K;
                 la.i32 = i32;
+                la.split = g.split;
                 WarpSim *w = new WarpSim();
                 w->run(lane_main, &la);
                 delete w;

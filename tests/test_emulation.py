@@ -27,10 +27,10 @@ def emu():
     L.swbemu_search.restype = ctypes.c_int
     L.swbemu_search.argtypes = [_u8p, _u64p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, _i8p,
                                 ctypes.c_int, _u8p, ctypes.c_uint32, ctypes.c_int, ctypes.c_int, ctypes.c_uint32,
-                                ctypes.c_int, _i32p, ctypes.POINTER(ctypes.c_uint32)]
+                                ctypes.c_int, ctypes.c_uint32, _i32p, ctypes.POINTER(ctypes.c_uint32)]
 
     def search(codes, offs, m, q, K=32, group_len=384, force_i32=0, chunk_rows=0, thr=-1, gap=2, shard=0, nshards=1,
-               n_out=None):
+               n_out=None, xl_len=8192):
         codes = np.ascontiguousarray(codes, dtype=np.uint8)
         if len(codes) == 0:
             codes = np.zeros(1, dtype=np.uint8)
@@ -42,7 +42,7 @@ def emu():
         rc = ctypes.c_uint32()
         r = L.swbemu_search(codes.ctypes.data_as(_u8p), offs.ctypes.data_as(_u64p), n, shard, nshards, group_len,
                             m.ctypes.data_as(_i8p), gap, q.ctypes.data_as(_u8p) if len(q) else None, len(q), K,
-                            force_i32, chunk_rows, thr, out.ctypes.data_as(_i32p), ctypes.byref(rc))
+                            force_i32, chunk_rows, thr, xl_len, out.ctypes.data_as(_i32p), ctypes.byref(rc))
         assert r == 0
         return out, rc.value
 
@@ -117,3 +117,30 @@ def test_edges_ident3_and_shards(emu, oracle, subset, queries):
         got, _ = emu(subset["codes"], subset["offsets"], m, q, K=32, shard=s, nshards=3, n_out=info.n_local)
         merged[ids] = got
     assert np.array_equal(merged, want)
+
+
+def test_pipelined_passes_of_very_long_tiles(emu, oracle):
+    """xl_len: 32-lane tiles wider than it hand out their passes as separate, pipelined work items (boundary row
+    through the scratch + progress counters, scores merged with atomicMax). In the emulation the items run one after
+    the other in hand-out order, so a pass that had to wait for data that is not there yet would spin forever."""
+    rng = np.random.default_rng(21)
+    m = oracle.matrix("blosum50")
+    lens = [1500, 1333, 900, 801, 640, 300, 280, 120, 64, 30, 7, 1200]
+    enc = random_db(rng, lens, alphabet=20)
+    codes, offs = pack_db(enc)
+    for ql in (100, 256, 257, 700, 1100):
+        q = rng.integers(0, 20, ql).astype(np.uint8)
+        want = oracle.scan(q, codes, offs, m)
+        for gl, xl in ((16, 600), (16, 100), (32, 1000)):
+            got, _ = emu(codes, offs, m, q, K=0, group_len=gl, xl_len=xl)
+            assert np.array_equal(got, want), (ql, gl, xl)
+    # chunked query through split tiles, and an s16 overflow inside a split tile (flag -> int32 recompute of the tile)
+    q = rng.integers(0, 20, 2300).astype(np.uint8)
+    want = oracle.scan(q, codes, offs, m)
+    got, _ = emu(codes, offs, m, q, K=0, group_len=16, xl_len=500, chunk_rows=1024)
+    assert np.array_equal(got, want)
+    w = np.full(2300, 17, dtype=np.uint8)
+    c2, o2 = pack_db([w, w[:2250].copy(), enc[0], enc[1]])
+    want = oracle.scan(w, c2, o2, m)
+    got, rc = emu(c2, o2, m, w, K=0, group_len=16, xl_len=500)
+    assert want[0] == 34500 and np.array_equal(got, want) and rc >= 1

@@ -78,7 +78,8 @@ struct swb_engine {
     // options
     SwbPlanOpts plan_opts;
     int opt_k = 0;
-    int opt_split = 1;        // pipelined passes for the very long tiles
+    int opt_split = 0;        // pipelined passes for the very long tiles (opt-in: cuts the latency of a lone long query
+                              // on a small shard, costs ~1 % of batch throughput; measured in profiles/)
     int opt_group_order = 0;  // 0 auto (lone query: longest tiles first; batch: bulk first), 1 longest first, 2 bulk first
     uint32_t cur_nq = 1;
     int nslots = 16;
@@ -500,6 +501,7 @@ struct LaunchShape {
 
 static int shape_for(swb_engine *e, int K, bool i32, bool split, uint32_t smem_rows, uint32_t ntiles, LaunchShape &ls)
 {
+    if (split) smem_rows = (uint32_t)K * 32u;  // a split launch stages one pass per work item
     ls.smem_rows = smem_rows;
     ls.smem = (size_t)SWB_ALPHA * (smem_rows + 4);
     if (ls.smem > e->smem_optin) return fail(e, SWB_ERR_ARG, "internal: query chunk does not fit shared memory");
@@ -507,7 +509,7 @@ static int shape_for(swb_engine *e, int K, bool i32, bool split, uint32_t smem_r
     int per_sm = 0;
     CU(swb_score_occupancy(K, i32, split, ls.block_cfg, ls.smem, &per_sm));
     if (per_sm < 1) return fail(e, SWB_ERR_CUDA, "score kernel does not fit on an SM");
-    const int nt = ls.block_cfg == SWB_BLOCK_SMALL ? SWB_NT_SMALL : SWB_NT_LARGE;
+    const int nt = split ? 32 : (ls.block_cfg == SWB_BLOCK_SMALL ? SWB_NT_SMALL : SWB_NT_LARGE);
     const int need = (int)((ntiles + nt / 32 - 1) / (nt / 32));
     ls.grid = std::max(1, std::min(per_sm * e->sm_count, need));
     return SWB_OK;

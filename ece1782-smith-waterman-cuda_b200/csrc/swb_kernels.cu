@@ -30,9 +30,26 @@ struct DevBackend {
         __threadfence();
         *reinterpret_cast<volatile uint32_t *>(p) = v;
     }
-    __device__ __forceinline__ uint32_t poll(const uint32_t *p) const
+    // SPLIT launches: the warp copies `rows` profile rows of all 32 codes into its block's shared memory
+    __device__ __forceinline__ void stage_rows(int8_t *dst, uint32_t dstride, const int8_t *prof, uint32_t pstride,
+                                               uint32_t row0, uint32_t rows) const
     {
-        const uint32_t v = *reinterpret_cast<const volatile uint32_t *>(p);
+        __syncwarp();
+        const uint32_t wpr = rows >> 2;
+        for (uint32_t i = threadIdx.x & 31u; i < wpr * SWB_ALPHA; i += 32u) {
+            const uint32_t code = i / wpr, w = i - code * wpr;
+            reinterpret_cast<uint32_t *>(dst + (size_t)code * dstride)[w] =
+                __ldg(reinterpret_cast<const uint32_t *>(prof + (size_t)code * pstride + row0) + w);
+        }
+        __syncwarp();
+    }
+    __device__ __forceinline__ uint32_t wait_progress(const uint32_t *p, uint32_t need) const
+    {
+        uint32_t v = *reinterpret_cast<const volatile uint32_t *>(p);
+        while (v < need) {
+            __nanosleep(256);
+            v = *reinterpret_cast<const volatile uint32_t *>(p);
+        }
         __threadfence();
         return v;
     }
@@ -65,7 +82,7 @@ __global__ void __launch_bounds__(NT, MINB) swb_score_kernel(const SwbScoreParam
 {
     extern __shared__ __align__(16) int8_t sprof[];
     const uint32_t sstride = p.smem_rows + 4u;
-    const uint32_t wpr = p.smem_rows >> 2;  // words per code row
+    const uint32_t wpr = SPLIT ? 0u : p.smem_rows >> 2;  // words per code row (SPLIT stages per work item)
     for (uint32_t i = threadIdx.x; i < wpr * SWB_ALPHA; i += NT) {
         const uint32_t code = i / wpr, w = i - code * wpr;
         reinterpret_cast<uint32_t *>(sprof + (size_t)code * sstride)[w] =
@@ -149,9 +166,9 @@ static cudaError_t dispatch_cfg(int op, int block_cfg, const SwbScoreParams *p, 
 static cudaError_t dispatch(int op, int K, bool i32, bool split, int block_cfg, const SwbScoreParams *p, int grid,
                             size_t smem, cudaStream_t st, int *blocks)
 {
-    if (split) {  // pipelined passes: s16 only, K = 8
+    if (split) {  // pipelined passes: s16 only, K = 8, one warp per block
         if (i32 || K != 8) return cudaErrorInvalidValue;
-        return dispatch_cfg<8, V16, true>(op, block_cfg, p, grid, smem, st, blocks);
+        return op == 0 ? launch_one<8, V16, 32, 8, true>(*p, grid, smem, st) : occ_one<8, V16, 32, 8, true>(smem, blocks);
     }
     if (!i32) {
         switch (K) {

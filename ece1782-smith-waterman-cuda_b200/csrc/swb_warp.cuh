@@ -216,13 +216,14 @@ struct V32 {
 //
 // SPLIT (32-lane tiles of very long sequences only): the passes of one tile are separate work items taken by different
 // warps, which run as a pipeline over the columns. The warp of pass ss publishes how many columns of its bottom row are
-// in the boundary scratch (prog[ss], every 32 columns, after a fence); the warp of pass ss+1 polls it before it reads
+// in the boundary scratch (prog[ss], every 64 columns, after a fence); the warp of pass ss+1 polls it (with back-off)
+// before it reads
 // them. Items are handed out in (tile, pass) order by one counter, so a waiting warp always waits for an item that a
 // resident warp already owns: no deadlock. Scores of the passes are combined with atomicMax.
 template <int K, class V, bool GROUPED, bool SPLIT, class BE>
 SWB_HD void swb_run_tile(BE &be, const SwbScoreParams &p, const SwbTile &tile, uint32_t tile_idx,
                          const int8_t *sprof, uint32_t sstride, uint32_t ss_begin = 0, uint32_t ss_count = 0xffffffffu,
-                         uint32_t *prog = nullptr)
+                         uint32_t *prog = nullptr, uint32_t smem_ss0 = 0)
 {
     typedef typename V::T T;
     const typename V::C cst = V::consts(p);
@@ -248,7 +249,8 @@ SWB_HD void swb_run_tile(BE &be, const SwbScoreParams &p, const SwbTile &tile, u
 
     const uint32_t ss_end = ss_count < nsuper - ss_begin ? ss_begin + ss_count : nsuper;
     for (uint32_t ss = ss_begin; ss < ss_end; ++ss) {
-        const int8_t *prow = sprof + (size_t)(((ss << logG) + (uint32_t)g) * (uint32_t)K);
+        // smem_ss0: the pass whose first row sits at row 0 of the staged profile (0 except in SPLIT launches)
+        const int8_t *prow = sprof + (size_t)((((ss - smem_ss0) << logG) + (uint32_t)g) * (uint32_t)K);
         const bool read_top = !(p.first_chunk && ss == 0);
         const bool write_bot = !(p.last_chunk && ss + 1 == nsuper);
         const bool wait_top = SPLIT && ss > 0;  // the row above comes from another warp of this launch
@@ -279,7 +281,7 @@ SWB_HD void swb_run_tile(BE &be, const SwbScoreParams &p, const SwbTile &tile, u
         }
         if (wait_top) {
             const uint32_t need = W < 4u ? W : 4u;
-            while (avail < need) avail = be.poll(prog + ss - 1);
+            avail = be.wait_progress(prog + ss - 1, need);
         }
         if (lead && nchunks > 0 && read_top) {
             if (!GROUPED) {
@@ -300,7 +302,7 @@ SWB_HD void swb_run_tile(BE &be, const SwbScoreParams &p, const SwbTile &tile, u
             }
             if (wait_top && c + 1 < nchunks) {
                 const uint32_t need = 4u * c + 8u < W ? 4u * c + 8u : W;
-                while (avail < need) avail = be.poll(prog + ss - 1);
+                if (avail < need) avail = be.wait_progress(prog + ss - 1, need);
             }
             if (lead && c + 1 < nchunks) {
                 const uint8_t *rnext = res + (size_t)(c + 1) * res_stride;
@@ -343,7 +345,7 @@ SWB_HD void swb_run_tile(BE &be, const SwbScoreParams &p, const SwbTile &tile, u
 #pragma unroll
                     for (int u = 0; u < 4; ++u)
                         if (col0 + u >= 0 && col0 + u < (int32_t)W) V::st(be, dst + u, outb[u]);
-                    if (SPLIT && ((c & 7u) == 7u || c + 1 == nsteps4)) {
+                    if (SPLIT && ((c & 15u) == 15u || c + 1 == nsteps4)) {
                         const int32_t done = col0 + 4 < 0 ? 0 : (col0 + 4 > (int32_t)W ? (int32_t)W : col0 + 4);
                         be.publish(prog + ss, (uint32_t)done);
                     }
@@ -398,10 +400,14 @@ SWB_HD void swb_warp_loop(BE &be, const SwbScoreParams &p, const int8_t *sprof, 
         const uint32_t v = be.next_tile(p.counter);
         if (v >= p.ntiles) break;
         if (SPLIT) {
+            // one warp per block; it stages only the K * 32 profile rows of its pass (sstride = K * 32 + 4)
             const uint32_t t = v / p.split_passes, ss = v - t * p.split_passes;
             const uint32_t ti = p.range_start[0] + t;
             const SwbTile tile = be.ld_tile(p.tiles + ti);
-            swb_run_tile<K, V, true, true>(be, p, tile, ti, sprof, sstride, ss, 1u, p.prog + (size_t)t * p.split_passes);
+            be.stage_rows(const_cast<int8_t *>(sprof), sstride, p.profile, p.prof_stride, p.row0 + ss * (uint32_t)(K * 32),
+                          (uint32_t)(K * 32));
+            swb_run_tile<K, V, true, true>(be, p, tile, ti, sprof, sstride, ss, 1u, p.prog + (size_t)t * p.split_passes,
+                                           ss);
             continue;
         }
         uint32_t ti = p.range_start[0] + v;

@@ -74,6 +74,8 @@ const char *swb_last_error(const swb_engine *e);
  *          "k" (query rows per lane: 0 = chosen per lane-group size and query, else 8, 16, 32),
  *          "streams" (queries of a batch in flight at once, 1..24, default 16; their scratch is allocated on first use),
  *          "group_order" (0 = auto, 1 = launch the long-sequence tiles first, 2 = launch the bulk first),
+ *          "split" (1 = the passes of sequences longer than "xl_len" (8192) run as pipelined work items on
+ *          different warps: lower latency for a lone long query, ~1 % less batch throughput; default 0),
  *          "chunk_rows" (query rows per launch for queries beyond shared memory; multiple of 1024, <= 7168) */
 int swb_set_option(swb_engine *e, const char *key, int64_t value);
 /* run on the caller's CUDA stream (cudaStream_t as void*); NULL = the engine's own stream */

@@ -31,12 +31,19 @@ struct HostBackend {
     void publish(uint32_t *p, uint32_t v) { *p = v; }
     // the emulation runs the work items one after the other in hand-out order, so whatever a pass waits for must
     // already be there: a value that is too small here would be a deadlock on the GPU
-    uint32_t poll(const uint32_t *p)
+    void stage_rows(int8_t *dst, uint32_t dstride, const int8_t *prof, uint32_t pstride, uint32_t row0, uint32_t rows)
     {
-        if (++polls > 100000000ull) abort();  // a spin that never ends = the hand-out order guarantee is broken
+        if (lane_id == 0)
+            for (uint32_t code = 0; code < SWB_ALPHA; ++code)
+                memcpy(dst + (size_t)code * dstride, prof + (size_t)code * pstride + row0, rows);
+        syncwarp();
+    }
+    uint32_t wait_progress(const uint32_t *p, uint32_t need)
+    {
+        if (*p < need) abort();  // on the GPU this would be a spin that never ends: hand-out order guarantee broken
         return *p;
     }
-    unsigned long long polls = 0;
+
     uint8_t ld_flag(const uint8_t *p) const { return *p; }
     SwbTile ld_tile(const SwbTile *p) const { return *p; }
     uint32_t ld_code(const uint8_t *p) const { return *p; }
@@ -268,7 +275,7 @@ extern "C" int swbemu_search(const uint8_t *codes, const uint64_t *offsets, uint
                 p.prog = prog.data();
                 p.row0 = ch.row0;
                 p.rows = ch.rows;
-                p.smem_rows = swb_group_smem_rows(ch.rows, g);
+                p.smem_rows = g.split ? (uint32_t)g.K * 32u : swb_group_smem_rows(ch.rows, g);
                 p.first_chunk = ch.first;
                 p.last_chunk = ch.last;
                 uint32_t counter = 0;
@@ -276,9 +283,10 @@ extern "C" int swbemu_search(const uint8_t *codes, const uint64_t *offsets, uint
                 // stage the chunk's profile exactly like swb_score_kernel
                 const uint32_t sstride = p.smem_rows + 4;
                 std::vector<int8_t> sprof((size_t)sstride * SWB_ALPHA + 16);
-                for (uint32_t code = 0; code < SWB_ALPHA; ++code)
-                    memcpy(sprof.data() + (size_t)code * sstride, prof.data() + (size_t)code * prof_stride + ch.row0,
-                           p.smem_rows);
+                if (!g.split)
+                    for (uint32_t code = 0; code < SWB_ALPHA; ++code)
+                        memcpy(sprof.data() + (size_t)code * sstride, prof.data() + (size_t)code * prof_stride + ch.row0,
+                               p.smem_rows);
                 LaneArgs la;
                 la.p = &p;
                 la.sprof = sprof.data();

@@ -336,3 +336,26 @@ def test_traceback_alignment_matches_cpu_cpp_and_oracle(swb, oracle, subset, que
         assert e.align(np.zeros(0, np.uint8), 3, 10)[0] == 0
     finally:
         e.close()
+
+
+def test_pipelined_passes_option(swb, oracle):
+    """option split=1: 32-lane tiles wider than xl_len hand out their passes as pipelined work items (progress
+    counters in global memory, atomicMax merge); same scores, including a chunked query and an s16 overflow"""
+    rng = np.random.default_rng(99)
+    m = oracle.matrix("blosum50")
+    w = np.full(2400, 17, dtype=np.uint8)
+    enc = random_db(rng, [9000, 8200, 5000, 4100, 3000, 2500, 700, 300, 120, 40], alphabet=20) + [w.copy()]
+    codes, offs = pack_db(enc)
+    e = swb.Engine(0, split=1, xl_len=2048)
+    try:
+        e.db_load(codes, offs)
+        for q in (rng.integers(0, 20, 144).astype(np.uint8), rng.integers(0, 20, 1000).astype(np.uint8),
+                  rng.integers(0, 20, 5478).astype(np.uint8), w):
+            assert np.array_equal(e.search(q), oracle.scan(q, codes, offs, m)), len(q)
+        e.set_option("chunk_rows", 1024)
+        q = rng.integers(0, 20, 3000).astype(np.uint8)
+        assert np.array_equal(e.search(q), oracle.scan(q, codes, offs, m))
+        batch = e.search_batch([q[:500], q[:1500], q])
+        assert np.array_equal(batch[2], oracle.scan(q, codes, offs, m))
+    finally:
+        e.close()

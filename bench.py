@@ -188,7 +188,8 @@ def main():
     ap.add_argument("--k", type=int, default=0)
     ap.add_argument("--group-len", type=int, default=0)
     ap.add_argument("--group-order", type=int, default=0)
-    ap.add_argument("--split", type=int, default=-1, help="pipelined passes for very long tiles: 1 on (default), 0 off")
+    ap.add_argument("--split", type=int, default=-1, help="pipelined passes for very long tiles: 1 on, 0 off (default)")
+    ap.add_argument("--pair-queries", type=int, default=-1, help="pack two queries of a batch per lane: 1 (default), 0")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--per-query", action="store_true", help="also print device GCUPS per query")
     args = ap.parse_args()
@@ -222,6 +223,8 @@ def main():
         opts["group_order"] = args.group_order
     if args.split >= 0:
         opts["split"] = args.split
+    if args.pair_queries >= 0:
+        opts["pair_queries"] = args.pair_queries
     eng = swb.Engine(local, **opts)
     stream = torch.cuda.current_stream()
     eng.set_stream(stream.cuda_stream)

@@ -17,6 +17,7 @@
 #define SWB_MAX_COUNTERS 256
 #define SWB_MAX_SUB 3  // extra streams per slot: up to three distinct K values plus the split group per query
 #define SWB_CHUNK_ROWS 7168u          // query rows per launch when a query does not fit shared memory
+#define SWB_CHUNK_ROWS_QPAIR 1536u    // the same for query-pair jobs (4-byte profile entries)
 #define SWB_SMALL_SMEM_LIMIT (100u * 1024u)
 #define SWB_STAGE_BYTES (32u << 20)   // pinned staging buffers for the raw database upload
 
@@ -50,13 +51,16 @@ struct Slot {
     size_t prog_cap = 0;
     uint8_t *d_flags = nullptr;
     int32_t *d_sorted = nullptr;
+    int32_t *d_sorted2 = nullptr;  // second query of a query-pair job
+    uint32_t *d_profq = nullptr;   // query-pair profile [32][stride] of s16x2 words
+    size_t profq_cap = 0;
     uint32_t *d_bnd16 = nullptr;
     size_t bnd16_cap = 0;
     void *d_bnd32 = nullptr;
     size_t bnd32_cap = 0;
     int32_t *h_scores = nullptr;  // pinned, n_local
     size_t h_scores_cap = 0;
-    int32_t *pending_dst = nullptr;
+    int32_t *pending_dst[2] = {nullptr, nullptr};
 };
 
 struct swb_engine {
@@ -78,6 +82,8 @@ struct swb_engine {
     // options
     SwbPlanOpts plan_opts;
     int opt_k = 0;
+    int opt_pair_queries = 0; // batches: pack two queries into the halves of the s16x2 lanes (V16Q). Opt-in: measured
+                              // 0.77x of V16 on B200 (4 B of profile per packed cell: shared-memory bound)
     int opt_split = 0;        // pipelined passes for the very long tiles (opt-in: cuts the latency of a lone long query
                               // on a small shard, costs ~1 % of batch throughput; measured in profiles/)
     int opt_group_order = 0;  // 0 auto (lone query: longest tiles first; batch: bulk first), 1 longest first, 2 bulk first
@@ -139,6 +145,9 @@ static void free_slot_db(Slot &s)
     if (s.d_prog) cudaFree(s.d_prog);
     s.d_prog = nullptr;
     s.prog_cap = 0;
+    if (s.d_profq) cudaFree(s.d_profq);
+    s.d_profq = nullptr;
+    s.profq_cap = 0;
     if (s.h_scores) cudaFreeHost(s.h_scores);
     s.d_state = nullptr;
     s.d_bnd16 = nullptr;
@@ -294,6 +303,8 @@ extern "C" int swb_set_option(swb_engine *e, const char *key, int64_t value)
     } else if (!strcmp(key, "xl_len")) {
         if (value < 0 || value > (1ll << 31)) return fail(e, SWB_ERR_ARG, "xl_len out of range");
         e->plan_opts.xl_len = (uint32_t)value;
+    } else if (!strcmp(key, "pair_queries")) {
+        e->opt_pair_queries = value != 0;
     } else if (!strcmp(key, "split")) {
         e->opt_split = value != 0;
     } else if (!strcmp(key, "group_order")) {
@@ -499,15 +510,15 @@ struct LaunchShape {
     uint32_t smem_rows;
 };
 
-static int shape_for(swb_engine *e, int K, bool i32, bool split, uint32_t smem_rows, uint32_t ntiles, LaunchShape &ls)
+static int shape_for(swb_engine *e, int K, int mode, bool split, uint32_t smem_rows, uint32_t ntiles, LaunchShape &ls)
 {
     if (split) smem_rows = (uint32_t)K * 32u;  // a split launch stages one pass per work item
     ls.smem_rows = smem_rows;
-    ls.smem = (size_t)SWB_ALPHA * (smem_rows + 4);
+    ls.smem = mode == SWB_MODE_QPAIR ? (size_t)SWB_ALPHA * (smem_rows + 1) * 4 : (size_t)SWB_ALPHA * (smem_rows + 4);
     if (ls.smem > e->smem_optin) return fail(e, SWB_ERR_ARG, "internal: query chunk does not fit shared memory");
     ls.block_cfg = ls.smem <= SWB_SMALL_SMEM_LIMIT ? SWB_BLOCK_SMALL : SWB_BLOCK_LARGE;
     int per_sm = 0;
-    CU(swb_score_occupancy(K, i32, split, ls.block_cfg, ls.smem, &per_sm));
+    CU(swb_score_occupancy(K, mode, split, ls.block_cfg, ls.smem, &per_sm));
     if (per_sm < 1) return fail(e, SWB_ERR_CUDA, "score kernel does not fit on an SM");
     const int nt = split ? 32 : (ls.block_cfg == SWB_BLOCK_SMALL ? SWB_NT_SMALL : SWB_NT_LARGE);
     const int need = (int)((ntiles + nt / 32 - 1) / (nt / 32));
@@ -516,7 +527,8 @@ static int shape_for(swb_engine *e, int K, bool i32, bool split, uint32_t smem_r
 }
 
 // Per-stream scratch of the loaded database, sized on the slot's first use after a load (grow-only buffers): a lone
-// query touches one slot, a batch as many as it has queries in flight.
+// query touches one slot, a batch as many as it has jobs in flight. State layout: [launch counters | tile flags |
+// scores of query A in sorted order | scores of query B (query-pair jobs)].
 static int ensure_slot(swb_engine *e, Slot &s)
 {
     if (s.ready) return SWB_OK;
@@ -525,84 +537,149 @@ static int ensure_slot(swb_engine *e, Slot &s)
     const size_t flags_bytes = swb_roundup((uint32_t)pl.tiles.size(), 16);
     const size_t sorted_bytes = sizeof(int32_t) * 2 * (size_t)((nl + 1) / 2);
     const size_t head = sizeof(uint32_t) * SWB_MAX_COUNTERS;
-    s.state_bytes = head + flags_bytes + sorted_bytes;
+    s.state_bytes = head + flags_bytes + 2 * sorted_bytes;
     CU(GROW_DEV(s.d_state, s.state_cap, s.state_bytes));
     s.d_counters = reinterpret_cast<uint32_t *>(s.d_state);
     s.d_flags = s.d_state + head;
     s.d_sorted = reinterpret_cast<int32_t *>(s.d_state + head + flags_bytes);
+    s.d_sorted2 = reinterpret_cast<int32_t *>(s.d_state + head + flags_bytes + sorted_bytes);
     CU(GROW_DEV(s.d_bnd16, s.bnd16_cap, sizeof(uint32_t) * pl.bnd_elems));
-    CU(GROW_HOST(s.h_scores, s.h_scores_cap, sizeof(int32_t) * nl));
+    CU(GROW_HOST(s.h_scores, s.h_scores_cap, 2 * sizeof(int32_t) * (size_t)nl));
     s.ready = true;
     return SWB_OK;
 }
 
-// Enqueues everything one query needs; the result lands in d_out[qi].
-// Stream layout per slot: profile build and clears on slot.stream, then one sub-stream per distinct K (the tiles of
-// the group sizes that use that K for this query) so that the few long-sequence tiles run beside the bulk, then
-// the scatter back on slot.stream.
-static int enqueue_query(swb_engine *e, Slot &s, uint32_t qi, const uint8_t *q, uint32_t qlen)
+// the launches of one pass (one arithmetic policy over one profile): every launch group on its own stream
+static int enqueue_pass(swb_engine *e, Slot &s, int mode, SwbScoreParams &p, const SwbQueryPlan &qp,
+                        const std::vector<SwbLaunchGroup> &groups, uint32_t &counter)
+{
+    const size_t ng = groups.size();
+    if (ng > 1 + SWB_MAX_SUB) return fail(e, SWB_ERR_ARG, "internal: too many launch groups");
+    // fork: the launch groups of a pass are independent of each other (disjoint tiles)
+    if (ng > 1) {
+        CU(cudaEventRecord(s.ev_fork, s.stream));
+        for (size_t gi = 1; gi < ng; ++gi) CU(cudaStreamWaitEvent(s.sub[gi - 1], s.ev_fork, 0));
+    }
+    for (size_t gi = 0; gi < ng; ++gi) {
+        const SwbLaunchGroup &g = groups[gi];
+        cudaStream_t st = gi == 0 ? s.stream : s.sub[gi - 1];
+        for (int r = 0; r < SWB_MAX_RANGES; ++r) {
+            p.range_start[r] = g.range_start[r];
+            p.range_cum[r] = g.range_cum[r];
+        }
+        size_t prog_at = 0;
+        for (size_t c = 0; c < qp.chunks.size(); ++c) {
+            const SwbQueryChunk &ch = qp.chunks[c];
+            p.split_passes = g.split ? swb_split_passes(ch.rows) : 0;
+            // work items of the launch: tiles, (tile, pass) for split groups, (tile, half) for query pairs
+            p.ntiles = g.split ? g.ntiles * p.split_passes : (mode == SWB_MODE_QPAIR ? 2 * g.ntiles : g.ntiles);
+            p.prog = g.split ? s.d_prog + prog_at : nullptr;
+            prog_at += (size_t)g.ntiles * p.split_passes;
+            LaunchShape ls;
+            int rc = shape_for(e, g.K, mode, g.split, swb_group_smem_rows(ch.rows, g), p.ntiles, ls);
+            if (rc != SWB_OK) return rc;
+            p.row0 = ch.row0;
+            p.rows = ch.rows;
+            p.smem_rows = ls.smem_rows;
+            p.first_chunk = ch.first;
+            p.last_chunk = ch.last;
+            p.counter = s.d_counters + counter++;
+            CU(swb_launch_score(g.K, mode, g.split, ls.block_cfg, p, ls.grid, ls.smem, st));
+            e->stats.kernel_launches += 1;
+        }
+    }
+    for (size_t gi = 1; gi < ng; ++gi) {  // join
+        CU(cudaEventRecord(s.ev_sub[gi - 1], s.sub[gi - 1]));
+        CU(cudaStreamWaitEvent(s.stream, s.ev_sub[gi - 1], 0));
+    }
+    return SWB_OK;
+}
+
+// Enqueues everything one job needs; a job is one query, or two queries of a batch packed into the two halves of the
+// s16x2 lanes (V16Q). Results land in d_out[qi] (and d_out[qi2]).
+// Stream layout per slot: profile build and clears on slot.stream, then one sub-stream per launch group (the tiles of
+// the group sizes that share a K) so that the few long-sequence tiles run beside the bulk, then the scatter.
+static int enqueue_job(swb_engine *e, Slot &s, uint32_t qi, const uint8_t *q, uint32_t qlen, bool pair, uint32_t qi2,
+                       const uint8_t *q2, uint32_t qlen2)
 {
     SwbPlan &pl = e->plan;
     const uint32_t nl = pl.n_local;
-    int32_t *out = e->d_out + (size_t)qi * nl;
     if (nl == 0) return SWB_OK;
-    int rc0 = ensure_slot(e, s);
-    if (rc0 != SWB_OK) return rc0;
-    if (qlen == 0 || pl.tiles.empty() || pl.max_len == 0) {
+    int rc = ensure_slot(e, s);
+    if (rc != SWB_OK) return rc;
+    int32_t *out = e->d_out + (size_t)qi * nl;
+    int32_t *out2 = pair ? e->d_out + (size_t)qi2 * nl : nullptr;
+    const uint32_t rows = pair ? std::max(qlen, qlen2) : qlen;
+    if (rows == 0 || pl.tiles.empty() || pl.max_len == 0) {
         CU(cudaMemsetAsync(out, 0, sizeof(int32_t) * nl, s.stream));
+        if (pair) CU(cudaMemsetAsync(out2, 0, sizeof(int32_t) * nl, s.stream));
         return SWB_OK;
     }
     const int ovf_thr = 32767 - e->max_s;
-    // the s16 pass, and the int32 pass over flagged tiles when a score could exceed the s16 range at all
-    const bool need_i32 = (int64_t)e->max_s * std::min<uint32_t>(qlen, pl.max_len) > ovf_thr;
     uint32_t present = 0;
     for (int l = 0; l <= SWB_MAX_LOGG; ++l)
         if (pl.tiles_by_logg[l]) present |= 1u << l;
-    SwbQueryPlan qp[2];
-    std::vector<SwbLaunchGroup> groups[2];
-    swb_plan_query(qlen, e->opt_k, 32, present, e->chunk_rows, qp[0]);
     const bool longest_first = e->opt_group_order == 1 || (e->opt_group_order == 0 && e->cur_nq <= 1);
-    swb_plan_launch_groups(pl, qp[0], longest_first, e->opt_split != 0, groups[0]);
-    if (need_i32) {
-        swb_plan_query(qlen, e->opt_k, 16, present, e->chunk_rows, qp[1]);
-        swb_plan_launch_groups(pl, qp[1], longest_first, false, groups[1]);
+    const int mode0 = pair ? SWB_MODE_QPAIR : SWB_MODE_S16;
+
+    // pass 0: the s16 pass over all tiles
+    SwbQueryPlan qp0;
+    std::vector<SwbLaunchGroup> g0;
+    swb_plan_query(rows, e->opt_k, 32, present, pair ? SWB_CHUNK_ROWS_QPAIR : e->chunk_rows, qp0);
+    swb_plan_launch_groups(pl, qp0, longest_first, !pair && e->opt_split != 0, g0);
+    // int32 passes over flagged tiles, one per query, only when a score can exceed the s16 range at all
+    const uint32_t qlens[2] = {qlen, pair ? qlen2 : 0u};
+    bool need_i32[2];
+    SwbQueryPlan qp1[2];
+    std::vector<SwbLaunchGroup> g1[2];
+    size_t nlaunch = g0.size() * qp0.chunks.size();
+    uint32_t prof8_rows = pair ? 0u : qp0.prof_rows;
+    for (int k = 0; k < 2; ++k) {
+        need_i32[k] = qlens[k] > 0 && (int64_t)e->max_s * std::min<uint32_t>(qlens[k], pl.max_len) > ovf_thr;
+        if (!need_i32[k]) continue;
+        swb_plan_query(qlens[k], e->opt_k, 16, present, e->chunk_rows, qp1[k]);
+        swb_plan_launch_groups(pl, qp1[k], longest_first, false, g1[k]);
+        nlaunch += g1[k].size() * qp1[k].chunks.size();
+        prof8_rows = std::max(prof8_rows, qp1[k].prof_rows);
     }
-    const int npass = need_i32 ? 2 : 1;
-    size_t nlaunch = 0;
-    for (int pass = 0; pass < npass; ++pass) nlaunch += groups[pass].size() * qp[pass].chunks.size();
     if (nlaunch > SWB_MAX_COUNTERS) return fail(e, SWB_ERR_ARG, "query too long");
-    const uint32_t prof_rows = need_i32 ? std::max(qp[0].prof_rows, qp[1].prof_rows) : qp[0].prof_rows;
-    const uint32_t prof_stride = swb_roundup(prof_rows, 16);
-    if (qlen > s.query_cap) {
+    const uint32_t prof8_stride = swb_roundup(std::max(prof8_rows, 16u), 16);
+    const uint32_t profq_stride = pair ? swb_roundup(qp0.prof_rows, 16) : 0;
+
+    // buffers
+    const uint32_t qbytes = qlen + (pair ? qlen2 : 0u);
+    if (qbytes > s.query_cap) {
         if (s.h_query) cudaFreeHost(s.h_query);
         if (s.d_query) cudaFree(s.d_query);
         s.h_query = nullptr;
         s.d_query = nullptr;
         s.query_cap = 0;
-        const uint32_t cap = swb_roundup(qlen, 4096);
+        const uint32_t cap = swb_roundup(qbytes, 4096);
         CU(cudaMallocHost(&s.h_query, cap));
         CU(cudaMalloc(&s.d_query, cap));
         s.query_cap = cap;
     }
-    if ((size_t)prof_stride * SWB_ALPHA > s.prof_cap) {
-        if (s.d_prof) cudaFree(s.d_prof);
-        s.d_prof = nullptr;
-        s.prof_cap = 0;
-        const size_t cap = (size_t)swb_roundup(prof_stride, 4096) * SWB_ALPHA;
-        CU(cudaMalloc(&s.d_prof, cap));
-        s.prof_cap = cap;
+    if (prof8_rows) CU(GROW_DEV(s.d_prof, s.prof_cap, (size_t)prof8_stride * SWB_ALPHA));
+    if (pair) {
+        CU(GROW_DEV(s.d_profq, s.profq_cap, sizeof(uint32_t) * (size_t)profq_stride * SWB_ALPHA));
+        CU(GROW_DEV(s.d_bnd16, s.bnd16_cap, 2 * sizeof(uint32_t) * pl.bnd_elems));  // two work items per tile
     }
-    if (need_i32) CU(GROW_DEV(s.d_bnd32, s.bnd32_cap, 8ull * pl.bnd_elems));
+    if (need_i32[0] || need_i32[1]) CU(GROW_DEV(s.d_bnd32, s.bnd32_cap, 8ull * pl.bnd_elems));
     // progress counters of the split group: one per (very long tile, pass) and chunk
     size_t prog_words = 0;
-    if (!groups[0].empty() && groups[0][0].split)
-        for (size_t c = 0; c < qp[0].chunks.size(); ++c)
-            prog_words += (size_t)groups[0][0].ntiles * swb_split_passes(qp[0].chunks[c].rows);
+    if (!g0.empty() && g0[0].split)
+        for (size_t c = 0; c < qp0.chunks.size(); ++c)
+            prog_words += (size_t)g0[0].ntiles * swb_split_passes(qp0.chunks[c].rows);
     if (prog_words) CU(GROW_DEV(s.d_prog, s.prog_cap, sizeof(uint32_t) * prog_words));
 
     memcpy(s.h_query, q, qlen);
-    CU(cudaMemcpyAsync(s.d_query, s.h_query, qlen, cudaMemcpyHostToDevice, s.stream));
-    CU(swb_launch_profile(s.d_query, qlen, e->d_mat, e->gap, s.d_prof, prof_stride, prof_rows, s.stream));
+    if (pair) memcpy(s.h_query + qlen, q2, qlen2);
+    CU(cudaMemcpyAsync(s.d_query, s.h_query, qbytes, cudaMemcpyHostToDevice, s.stream));
+    if (pair)
+        CU(swb_launch_profile2(s.d_query, qlen, s.d_query + qlen, qlen2, e->d_mat, e->gap, s.d_profq, profq_stride,
+                               qp0.prof_rows, s.stream));
+    else
+        CU(swb_launch_profile(s.d_query, qlen, e->d_mat, e->gap, s.d_prof, prof8_stride, qp0.prof_rows, s.stream));
     CU(cudaMemsetAsync(s.d_state, 0, s.state_bytes, s.stream));
     if (prog_words) CU(cudaMemsetAsync(s.d_prog, 0, sizeof(uint32_t) * prog_words, s.stream));
     e->stats.kernel_launches += 1;
@@ -611,64 +688,42 @@ static int enqueue_query(swb_engine *e, Slot &s, uint32_t qi, const uint8_t *q, 
     memset(&p, 0, sizeof p);
     p.tiles = e->d_tiles;
     p.residues = e->d_residues;
-    p.profile = s.d_prof;
-    p.prof_stride = prof_stride;
-    p.scores = s.d_sorted;
     p.flags = s.d_flags;
     p.recount = s.d_recount;
     p.gap = e->gap;
     p.ovf_thr = ovf_thr;
     p.t0 = 0;
     uint32_t counter = 0;
-    for (int pass = 0; pass < npass; ++pass) {
-        const bool i32 = pass == 1;
-        p.bnd = i32 ? s.d_bnd32 : (void *)s.d_bnd16;
-        p.only_flagged = i32 ? 1u : 0u;
-        const size_t ng = groups[pass].size();
-        // fork: the launch groups of a pass are independent of each other (disjoint tiles)
-        if (ng > 1) {
-            CU(cudaEventRecord(s.ev_fork, s.stream));
-            for (size_t gi = 1; gi < ng; ++gi) CU(cudaStreamWaitEvent(s.sub[gi - 1], s.ev_fork, 0));
+    p.profile = pair ? reinterpret_cast<const int8_t *>(s.d_profq) : s.d_prof;
+    p.prof_stride = pair ? profq_stride : prof8_stride;
+    p.scores = s.d_sorted;
+    p.scores2 = s.d_sorted2;
+    p.bnd = s.d_bnd16;
+    p.only_flagged = 0;
+    if ((rc = enqueue_pass(e, s, mode0, p, qp0, g0, counter)) != SWB_OK) return rc;
+    for (int k = 0; k < 2; ++k) {
+        if (!need_i32[k]) continue;
+        if (pair) {  // the int32 pass works on a one-query int8 profile
+            CU(swb_launch_profile(s.d_query + (k ? qlen : 0u), qlens[k], e->d_mat, e->gap, s.d_prof, prof8_stride,
+                                  qp1[k].prof_rows, s.stream));
+            e->stats.kernel_launches += 1;
         }
-        for (size_t gi = 0; gi < ng; ++gi) {
-            const SwbLaunchGroup &g = groups[pass][gi];
-            cudaStream_t st = gi == 0 ? s.stream : s.sub[gi - 1];
-            for (int r = 0; r < SWB_MAX_RANGES; ++r) {
-                p.range_start[r] = g.range_start[r];
-                p.range_cum[r] = g.range_cum[r];
-            }
-            size_t prog_at = 0;
-            for (size_t c = 0; c < qp[pass].chunks.size(); ++c) {
-                const SwbQueryChunk &ch = qp[pass].chunks[c];
-                p.split_passes = g.split ? swb_split_passes(ch.rows) : 0;
-                p.ntiles = g.split ? g.ntiles * p.split_passes : g.ntiles;  // work items of the launch
-                p.prog = g.split ? s.d_prog + prog_at : nullptr;
-                prog_at += (size_t)g.ntiles * p.split_passes;
-                LaunchShape ls;
-                int rc = shape_for(e, g.K, i32, g.split, swb_group_smem_rows(ch.rows, g), p.ntiles, ls);
-                if (rc != SWB_OK) return rc;
-                p.row0 = ch.row0;
-                p.rows = ch.rows;
-                p.smem_rows = ls.smem_rows;
-                p.first_chunk = ch.first;
-                p.last_chunk = ch.last;
-                p.counter = s.d_counters + counter++;
-                CU(swb_launch_score(g.K, i32, g.split, ls.block_cfg, p, ls.grid, ls.smem, st));
-                e->stats.kernel_launches += 1;
-            }
-        }
-        // join
-        for (size_t gi = 1; gi < ng; ++gi) {
-            CU(cudaEventRecord(s.ev_sub[gi - 1], s.sub[gi - 1]));
-            CU(cudaStreamWaitEvent(s.stream, s.ev_sub[gi - 1], 0));
-        }
+        p.profile = s.d_prof;
+        p.prof_stride = prof8_stride;
+        p.scores = k ? s.d_sorted2 : s.d_sorted;
+        p.scores2 = nullptr;
+        p.bnd = s.d_bnd32;
+        p.only_flagged = 1;
+        if ((rc = enqueue_pass(e, s, SWB_MODE_I32, p, qp1[k], g1[k], counter)) != SWB_OK) return rc;
     }
     CU(swb_launch_scatter(s.d_sorted, e->d_out_pos, nl, out, s.stream));
-    e->stats.kernel_launches += 1;
-    e->stats.last_k = (uint32_t)qp[0].k_by_logg[0];
+    if (pair) CU(swb_launch_scatter(s.d_sorted2, e->d_out_pos, nl, out2, s.stream));
+    e->stats.kernel_launches += pair ? 2 : 1;
+    e->stats.last_k = (uint32_t)qp0.k_by_logg[0];
     for (int l = 0; l <= SWB_MAX_LOGG; ++l)
-        e->stats.padded_cells += pl.cols_by_logg[l] * (uint64_t)swb_roundup(qlen, (uint32_t)qp[0].k_by_logg[l] << l);
-    e->stats.cells += (uint64_t)qlen * pl.residues_local;
+        e->stats.padded_cells += pl.cols_by_logg[l] * (uint64_t)swb_roundup(rows, (uint32_t)qp0.k_by_logg[l] << l) *
+                                 (pair ? 2u : 1u);
+    e->stats.cells += (uint64_t)(qlen + (pair ? qlen2 : 0u)) * pl.residues_local;
     return SWB_OK;
 }
 
@@ -677,10 +732,12 @@ static int finish_slot(swb_engine *e, Slot &s)
     if (!s.busy) return SWB_OK;
     CU(cudaEventSynchronize(s.done));
     s.busy = false;
-    if (s.pending_dst) {
-        memcpy(s.pending_dst, s.h_scores, sizeof(int32_t) * e->plan.n_local);
-        s.pending_dst = nullptr;
-    }
+    const size_t nl = e->plan.n_local;
+    for (int k = 0; k < 2; ++k)
+        if (s.pending_dst[k]) {
+            memcpy(s.pending_dst[k], s.h_scores + k * nl, sizeof(int32_t) * nl);
+            s.pending_dst[k] = nullptr;
+        }
     return SWB_OK;
 }
 
@@ -706,7 +763,17 @@ extern "C" int swb_search_batch(swb_engine *e, const uint8_t *qcodes, const uint
     e->stats.recomputed_tiles = 0;
     e->last_nq = nq;
     e->cur_nq = nq;
-    const int ns = (int)std::min<uint32_t>((uint32_t)e->nslots, std::max<uint32_t>(1u, nq));  // streams this batch uses
+    // jobs: with query-pair packing the queries are taken longest first and neighbours in length share a job (the
+    // shorter one pays for the rows of the longer one); a query left over, or every query without packing, runs alone
+    std::vector<uint32_t> order(nq);
+    for (uint32_t i = 0; i < nq; ++i) order[i] = i;
+    const bool pairing = e->opt_pair_queries && nq >= 2;
+    if (pairing)
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+            return qoffsets[a + 1] - qoffsets[a] > qoffsets[b + 1] - qoffsets[b];
+        });
+    const uint32_t njobs = pairing ? (nq + 1) / 2 : nq;
+    const int ns = (int)std::min<uint32_t>((uint32_t)e->nslots, std::max<uint32_t>(1u, njobs));  // streams in use
     CU(cudaEventRecord(e->ev_start, ms));
     CU(cudaEventRecord(e->ev_fork, ms));
     for (int i = 0; i < ns; ++i) {
@@ -714,15 +781,25 @@ extern "C" int swb_search_batch(swb_engine *e, const uint8_t *qcodes, const uint
         CU(cudaMemsetAsync(e->slots[i].d_recount, 0, sizeof(uint32_t), e->slots[i].stream));
     }
     int rc = SWB_OK;
-    for (uint32_t qi = 0; qi < nq && rc == SWB_OK; ++qi) {
-        Slot &s = e->slots[qi % ns];
+    for (uint32_t j = 0; j < njobs && rc == SWB_OK; ++j) {
+        Slot &s = e->slots[j % ns];
         if ((rc = finish_slot(e, s)) != SWB_OK) break;
-        const uint32_t qlen = (uint32_t)(qoffsets[qi + 1] - qoffsets[qi]);
-        if ((rc = enqueue_query(e, s, qi, qcodes + qoffsets[qi], qlen)) != SWB_OK) break;
+        const uint32_t qa = pairing ? order[2 * j] : order[j];
+        const bool pair = pairing && 2 * j + 1 < nq;
+        const uint32_t qb = pair ? order[2 * j + 1] : 0u;
+        const uint32_t la = (uint32_t)(qoffsets[qa + 1] - qoffsets[qa]);
+        const uint32_t lb = pair ? (uint32_t)(qoffsets[qb + 1] - qoffsets[qb]) : 0u;
+        rc = enqueue_job(e, s, qa, qcodes + qoffsets[qa], la, pair, qb, pair ? qcodes + qoffsets[qb] : nullptr, lb);
+        if (rc != SWB_OK) break;
         if (scores && nl > 0) {
-            CU(cudaMemcpyAsync(s.h_scores, e->d_out + (size_t)qi * nl, sizeof(int32_t) * nl, cudaMemcpyDeviceToHost,
+            CU(cudaMemcpyAsync(s.h_scores, e->d_out + (size_t)qa * nl, sizeof(int32_t) * nl, cudaMemcpyDeviceToHost,
                                s.stream));
-            s.pending_dst = scores + (size_t)qi * nl;
+            s.pending_dst[0] = scores + (size_t)qa * nl;
+            if (pair) {
+                CU(cudaMemcpyAsync(s.h_scores + nl, e->d_out + (size_t)qb * nl, sizeof(int32_t) * nl,
+                                   cudaMemcpyDeviceToHost, s.stream));
+                s.pending_dst[1] = scores + (size_t)qb * nl;
+            }
         }
         CU(cudaEventRecord(s.done, s.stream));
         s.busy = true;

@@ -81,12 +81,15 @@ template <int K, class V, int NT, int MINB, bool SPLIT>
 __global__ void __launch_bounds__(NT, MINB) swb_score_kernel(const SwbScoreParams p)
 {
     extern __shared__ __align__(16) int8_t sprof[];
-    const uint32_t sstride = p.smem_rows + 4u;
-    const uint32_t wpr = SPLIT ? 0u : p.smem_rows >> 2;  // words per code row (SPLIT stages per work item)
+    // profile entries: 1 byte (S + g of one query) or, for query pairs, 4 bytes (s16x2 of the two queries); either way
+    // consecutive code rows start one bank apart
+    const uint32_t esz = V::qpair ? 4u : 1u;
+    const uint32_t sstride = V::qpair ? (p.smem_rows + 1u) * 4u : p.smem_rows + 4u;
+    const uint32_t wpr = SPLIT ? 0u : (p.smem_rows * esz) >> 2;  // words per code row (SPLIT stages per work item)
     for (uint32_t i = threadIdx.x; i < wpr * SWB_ALPHA; i += NT) {
         const uint32_t code = i / wpr, w = i - code * wpr;
-        reinterpret_cast<uint32_t *>(sprof + (size_t)code * sstride)[w] =
-            __ldg(reinterpret_cast<const uint32_t *>(p.profile + (size_t)code * p.prof_stride + p.row0) + w);
+        reinterpret_cast<uint32_t *>(sprof + (size_t)code * sstride)[w] = __ldg(
+            reinterpret_cast<const uint32_t *>(p.profile + ((size_t)code * p.prof_stride + p.row0) * esz) + w);
     }
     __syncthreads();
     DevBackend be;
@@ -103,6 +106,23 @@ __global__ void swb_profile_kernel(const uint8_t *__restrict__ q, uint32_t qlen,
 #pragma unroll 4
     for (uint32_t code = 0; code < SWB_ALPHA; ++code)
         prof[(size_t)code * stride + r] = (int8_t)(mat[qc * SWB_ALPHA + code] + bias);
+}
+
+// query-pair profile: prof[code][r] = s16x2(S(qa_r, code) + gap, S(qb_r, code) + gap); rows past a query's end score 0
+__global__ void swb_profile2_kernel(const uint8_t *__restrict__ qa, uint32_t la, const uint8_t *__restrict__ qb,
+                                    uint32_t lb, const int8_t *__restrict__ mat, int gap, uint32_t *__restrict__ prof,
+                                    uint32_t stride, uint32_t rows)
+{
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const uint32_t ca = r < la ? (uint32_t)(qa[r] & 31u) : (uint32_t)SWB_PAD;
+    const uint32_t cb = r < lb ? (uint32_t)(qb[r] & 31u) : (uint32_t)SWB_PAD;
+#pragma unroll 4
+    for (uint32_t code = 0; code < SWB_ALPHA; ++code) {
+        const uint32_t lo = (uint32_t)(mat[ca * SWB_ALPHA + code] + gap) & 0xffffu;
+        const uint32_t hi = (uint32_t)(mat[cb * SWB_ALPHA + code] + gap) & 0xffffu;
+        prof[(size_t)code * stride + r] = lo | (hi << 16);
+    }
 }
 
 // One block per tile (grid-stride): gathers the tile's sequences from the raw concatenated codes into
@@ -163,9 +183,19 @@ static cudaError_t dispatch_cfg(int op, int block_cfg, const SwbScoreParams *p, 
                    : occ_one<K, V, SWB_NT_LARGE, 1, SPLIT>(smem, blocks);
 }
 
-static cudaError_t dispatch(int op, int K, bool i32, bool split, int block_cfg, const SwbScoreParams *p, int grid,
+static cudaError_t dispatch(int op, int K, int mode, bool split, int block_cfg, const SwbScoreParams *p, int grid,
                             size_t smem, cudaStream_t st, int *blocks)
 {
+    const bool i32 = mode == SWB_MODE_I32;
+    if (mode == SWB_MODE_QPAIR) {
+        if (split) return cudaErrorInvalidValue;
+        switch (K) {
+        case 8: return dispatch_cfg<8, V16Q, false>(op, block_cfg, p, grid, smem, st, blocks);
+        case 16: return dispatch_cfg<16, V16Q, false>(op, block_cfg, p, grid, smem, st, blocks);
+        case 32: return dispatch_cfg<32, V16Q, false>(op, block_cfg, p, grid, smem, st, blocks);
+        }
+        return cudaErrorInvalidValue;
+    }
     if (split) {  // pipelined passes: s16 only, K = 8, one warp per block
         if (i32 || K != 8) return cudaErrorInvalidValue;
         return op == 0 ? launch_one<8, V16, 32, 8, true>(*p, grid, smem, st) : occ_one<8, V16, 32, 8, true>(smem, blocks);
@@ -185,15 +215,22 @@ static cudaError_t dispatch(int op, int K, bool i32, bool split, int block_cfg, 
     return cudaErrorInvalidValue;
 }
 
-cudaError_t swb_launch_score(int K, bool i32, bool split, int block_cfg, const SwbScoreParams &p, int grid, size_t smem,
+cudaError_t swb_launch_score(int K, int mode, bool split, int block_cfg, const SwbScoreParams &p, int grid, size_t smem,
                              cudaStream_t st)
 {
-    return dispatch(0, K, i32, split, block_cfg, &p, grid, smem, st, nullptr);
+    return dispatch(0, K, mode, split, block_cfg, &p, grid, smem, st, nullptr);
 }
 
-cudaError_t swb_score_occupancy(int K, bool i32, bool split, int block_cfg, size_t smem, int *blocks)
+cudaError_t swb_score_occupancy(int K, int mode, bool split, int block_cfg, size_t smem, int *blocks)
 {
-    return dispatch(1, K, i32, split, block_cfg, nullptr, 0, smem, nullptr, blocks);
+    return dispatch(1, K, mode, split, block_cfg, nullptr, 0, smem, nullptr, blocks);
+}
+
+cudaError_t swb_launch_profile2(const uint8_t *qa, uint32_t la, const uint8_t *qb, uint32_t lb, const int8_t *mat,
+                                int gap, uint32_t *prof, uint32_t stride, uint32_t rows, cudaStream_t st)
+{
+    swb_profile2_kernel<<<(rows + 255) / 256, 256, 0, st>>>(qa, la, qb, lb, mat, gap, prof, stride, rows);
+    return cudaGetLastError();
 }
 
 cudaError_t swb_launch_profile(const uint8_t *q, uint32_t qlen, const int8_t *mat, int bias, int8_t *prof,

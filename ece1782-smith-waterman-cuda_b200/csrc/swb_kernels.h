@@ -11,11 +11,18 @@
 #define SWB_MINB_SMALL 2
 #define SWB_NT_LARGE 512
 
-// K: query rows per lane (8, 16, 32; int32 pass 8 or 16). i32: the exact recompute policy. split: the passes of a
-// tile are separate, pipelined work items (very long sequences; s16, K = 8 only).
-cudaError_t swb_launch_score(int K, bool i32, bool split, int block_cfg, const SwbScoreParams &p, int grid, size_t smem,
+// arithmetic policy of a score launch (swb_warp.cuh)
+#define SWB_MODE_S16 0    // V16: two DB sequences per lane, one query
+#define SWB_MODE_I32 1    // V32: exact recompute of flagged tiles
+#define SWB_MODE_QPAIR 2  // V16Q: one DB sequence per lane, two queries (batches)
+
+// K: query rows per lane (8, 16, 32; int32 pass 8 or 16). split: the passes of a tile are separate, pipelined work
+// items (very long sequences; SWB_MODE_S16, K = 8 only).
+cudaError_t swb_launch_score(int K, int mode, bool split, int block_cfg, const SwbScoreParams &p, int grid, size_t smem,
                              cudaStream_t st);
-cudaError_t swb_score_occupancy(int K, bool i32, bool split, int block_cfg, size_t smem, int *blocks_per_sm);
+cudaError_t swb_score_occupancy(int K, int mode, bool split, int block_cfg, size_t smem, int *blocks_per_sm);
+cudaError_t swb_launch_profile2(const uint8_t *qa, uint32_t la, const uint8_t *qb, uint32_t lb, const int8_t *mat,
+                                int gap, uint32_t *prof, uint32_t stride, uint32_t rows, cudaStream_t st);
 cudaError_t swb_launch_profile(const uint8_t *q, uint32_t qlen, const int8_t *mat, int bias, int8_t *prof,
                                uint32_t stride, uint32_t rows, cudaStream_t st);
 cudaError_t swb_launch_pack(const SwbTile *tiles, uint32_t ntiles, const uint8_t *raw, const uint64_t *seq_off,

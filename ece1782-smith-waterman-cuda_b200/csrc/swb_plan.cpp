@@ -149,12 +149,16 @@ void swb_plan_query(uint32_t qlen, int k_force, int k_max, uint32_t logg_present
         int best_k = std::min(32, k_max);
         if (k_force) {
             best_k = std::min(k_force, k_max);
+            while (best_k > 8 && nchunks > 1 && chunk_rows % ((uint32_t)best_k << l)) best_k >>= 1;
         } else {
             double best = 0;
+            bool have = false;
             for (int K = std::min(32, k_max); K >= 8; K >>= 1) {
+                // a chunk boundary must be a pass boundary of every group size
+                if (nchunks > 1 && chunk_rows % ((uint32_t)K << l)) continue;
                 // padded rows x per-column overhead of a short strip (shuffles, address math, boundary I/O)
                 const double cost = (double)swb_roundup(typical, (uint32_t)K << l) * (1.0 + 4.0 / K);
-                if (K == std::min(32, k_max) || cost < best) { best = cost; best_k = K; }
+                if (!have || cost < best) { best = cost; best_k = K; have = true; }
             }
         }
         qp.k_by_logg[l] = best_k;

@@ -41,6 +41,7 @@ struct SwbScoreParams {
     uint32_t first_chunk;     // 1: top boundary is zero
     uint32_t last_chunk;      // 1: bottom boundary is not stored
     int32_t *scores;          // per sequence, sorted order
+    int32_t *scores2;         // query-pair launches: scores of the second query
     uint32_t *counter;        // dynamic tile counter (zeroed before launch)
     uint8_t *flags;           // per tile: s16 kernel sets 1 when a score may have wrapped
     uint32_t only_flagged;    // i32 recompute: skip tiles whose flag is 0

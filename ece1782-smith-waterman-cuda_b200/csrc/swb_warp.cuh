@@ -7,10 +7,12 @@
 //     c(i,j) = max(0, H(i-1,j-1) + S, H(i,j-1) - g)               off the chain
 //     H(i,j) = max(H(i-1,j) - g, c(i,j))                          on the chain    (viaddmax)
 //
-// Two arithmetic policies run the same program:
+// Three arithmetic policies run the same program:
 //   V16   two DB sequences in the halves of a 32-bit word, signed s16x2 DPX instructions
 //         (prmt, viaddmax.relu, viaddmax, vadd2, 1/2 vimax3 = 4.5 ALU-pipe instructions per cell pair)
-//   V32   two int32 lanes; exact for any score; used to re-score tiles flagged by the s16 pass.
+//   V16Q  the halves are two QUERIES against one DB sequence (batches): the packed score is one profile word, no prmt:
+//         3.5 ALU-pipe instructions per cell pair
+//   V32   two int32 lanes; exact for any score; used to re-score tiles flagged by the s16 passes.
 // (A third policy that moved the additions to the FMA pipe as IMADs in a biased domain was measured
 //  slower on B200 -- register-file operand bandwidth, see DESIGN.md -- and was removed.)
 //
@@ -87,6 +89,7 @@ struct V16Base {
 // V16: plain signed domain. Stored per row: H(k, j-1) - g. Profile entry: S + g.
 //   c = viaddmax.relu(diag-g, S+g, left-g) ; h = viaddmax(h, -g, c) ; left' = vadd2(h, -g)
 struct V16 : V16Base {
+    static const bool qpair = false;
     struct C { T negg; };
     static SWB_HD C consts(const SwbScoreParams &p) { C c; c.negg = splat(-p.gap); return c; }
     static SWB_HD T hzero(const C &) { return 0u; }
@@ -135,8 +138,46 @@ struct V16 : V16Base {
 };
 
 // ---------------------------------------------------------------------------------------------
+// V16Q: query-pair packing for batches. The two halves of a word are TWO QUERIES against ONE database sequence, so
+// the packed score of a cell is a single profile word [code][row] = (S(qA_row, code) + g, S(qB_row, code) + g): one
+// LDS.32 and no prmt -> 3.5 ALU-pipe instructions per cell pair instead of 4.5. A tile is processed as two work
+// items (the first and the second sequence of each pair); rows past the end of the shorter query score 0.
+struct V16Q : V16Base {
+    static const bool qpair = true;
+    struct C { T negg; };
+    static SWB_HD C consts(const SwbScoreParams &p) { C c; c.negg = splat(-p.gap); return c; }
+    static SWB_HD T hzero(const C &) { return 0u; }
+    static SWB_HD T lzero(const C &c) { return c.negg; }
+    static SWB_HD int score_lo(T best, const C &) { return lo(best); }
+    static SWB_HD int score_hi(T best, const C &) { return hi(best); }
+    template <int K>
+    static SWB_HD T column(T up, T &diag0, T (&left)[K], T &best, const C &cst, uint32_t code, uint32_t,
+                           const int8_t *prow, uint32_t sstride)
+    {
+        const uint32_t *r = reinterpret_cast<const uint32_t *>(prow + code * sstride);
+        T h = up;
+        T dg = diag0;
+        diag0 = V16::add(up, cst.negg);
+#pragma unroll
+        for (int k = 0; k < K; k += 2) {
+            const T c0 = __viaddmax_s16x2_relu(dg, r[k], left[k]);
+            dg = left[k];
+            h = __viaddmax_s16x2(h, cst.negg, c0);
+            left[k] = V16::add(h, cst.negg);
+            const T c1 = __viaddmax_s16x2_relu(dg, r[k + 1], left[k + 1]);
+            dg = left[k + 1];
+            h = __viaddmax_s16x2(h, cst.negg, c1);
+            left[k + 1] = V16::add(h, cst.negg);
+            best = __vimax3_s16x2(best, c0, c1);
+        }
+        return h;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
 // V32: the same two sequences on two int32 lanes (no wrap for any realistic input).
 struct V32 {
+    static const bool qpair = false;
     struct T { int a, b; };
     struct C { int g, t0; };
     static const bool is16 = false;
@@ -223,8 +264,9 @@ struct V32 {
 template <int K, class V, bool GROUPED, bool SPLIT, class BE>
 SWB_HD void swb_run_tile(BE &be, const SwbScoreParams &p, const SwbTile &tile, uint32_t tile_idx,
                          const int8_t *sprof, uint32_t sstride, uint32_t ss_begin = 0, uint32_t ss_count = 0xffffffffu,
-                         uint32_t *prog = nullptr, uint32_t smem_ss0 = 0)
+                         uint32_t *prog = nullptr, uint32_t smem_ss0 = 0, uint32_t half = 0)
 {
+    // V::qpair: this work item covers sequence `half` (0 / 1) of every pair of the tile, for two queries at once
     typedef typename V::T T;
     const typename V::C cst = V::consts(p);
     const T HZERO = V::hzero(cst);
@@ -242,15 +284,16 @@ SWB_HD void swb_run_tile(BE &be, const SwbScoreParams &p, const SwbTile &tile, u
     const uint32_t rows_per_super = (uint32_t)K << logG;
     const uint32_t nsuper = (p.rows + rows_per_super - 1) / rows_per_super;
     const uint32_t nsteps4 = GROUPED ? ((W + (uint32_t)G - 1u + 3u) >> 2) : nchunks;
-    const uint8_t *res = p.residues + tile.res_off + (size_t)slot * 8u;
+    const uint8_t *res = p.residues + tile.res_off + (size_t)slot * 8u + (V::qpair ? half : 0u);
     const size_t res_stride = (size_t)P * 8u;
-    T *bnd = reinterpret_cast<T *>(p.bnd) + tile.bnd_off;
+    // qpair: two work items per tile, each with its own boundary rows
+    T *bnd = reinterpret_cast<T *>(p.bnd) + (V::qpair ? 2u * tile.bnd_off + (size_t)half * W * P : tile.bnd_off);
     T best = HZERO;
 
     const uint32_t ss_end = ss_count < nsuper - ss_begin ? ss_begin + ss_count : nsuper;
     for (uint32_t ss = ss_begin; ss < ss_end; ++ss) {
         // smem_ss0: the pass whose first row sits at row 0 of the staged profile (0 except in SPLIT launches)
-        const int8_t *prow = sprof + (size_t)((((ss - smem_ss0) << logG) + (uint32_t)g) * (uint32_t)K);
+        const int8_t *prow = sprof + (size_t)((((ss - smem_ss0) << logG) + (uint32_t)g) * (uint32_t)K) * (V::qpair ? 4u : 1u);
         const bool read_top = !(p.first_chunk && ss == 0);
         const bool write_bot = !(p.last_chunk && ss + 1 == nsuper);
         const bool wait_top = SPLIT && ss > 0;  // the row above comes from another warp of this launch
@@ -276,7 +319,7 @@ SWB_HD void swb_run_tile(BE &be, const SwbScoreParams &p, const SwbTile &tile, u
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 ca[u] = be.ld_code(res + 2 * u);
-                cb[u] = be.ld_code(res + 2 * u + 1);
+                if (!V::qpair) cb[u] = be.ld_code(res + 2 * u + 1);
             }
         }
         if (wait_top) {
@@ -309,7 +352,7 @@ SWB_HD void swb_run_tile(BE &be, const SwbScoreParams &p, const SwbTile &tile, u
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     na[u] = be.ld_code(rnext + 2 * u);
-                    nb[u] = be.ld_code(rnext + 2 * u + 1);
+                    if (!V::qpair) nb[u] = be.ld_code(rnext + 2 * u + 1);
                 }
                 if (read_top) {
                     if (!GROUPED) {
@@ -326,7 +369,7 @@ SWB_HD void swb_run_tile(BE &be, const SwbScoreParams &p, const SwbTile &tile, u
                 T up = bc[u];
                 if (GROUPED) {
                     const uint32_t a2 = be.shfl_up(aprev, 1, G);
-                    const uint32_t b2 = be.shfl_up(bprev, 1, G);
+                    const uint32_t b2 = V::qpair ? 0u : be.shfl_up(bprev, 1, G);
                     const T u2 = V::shfl_up(be, hprev, 1, G);
                     if (!lead) { a = a2; b = b2; up = u2; }
                 }
@@ -368,7 +411,16 @@ SWB_HD void swb_run_tile(BE &be, const SwbScoreParams &p, const SwbTile &tile, u
     if (lead && slot < (int)tile.npairs) {
         const size_t s0 = 2u * ((size_t)tile.first_pair + (size_t)slot);
         int a = V::score_lo(best, cst), b = V::score_hi(best, cst);
-        if (SPLIT) {
+        if (V::qpair) {
+            // lo half = query A, hi half = query B, both against sequence s0 + half
+            int32_t *sa = p.scores + s0 + half, *sb = p.scores2 + s0 + half;
+            if (!p.first_chunk) {
+                a = a > *sa ? a : *sa;
+                b = b > *sb ? b : *sb;
+            }
+            *sa = a;
+            *sb = b;
+        } else if (SPLIT) {
             be.atomic_max(p.scores + s0, a);
             be.atomic_max(p.scores + s0 + 1, b);
         } else {
@@ -410,16 +462,19 @@ SWB_HD void swb_warp_loop(BE &be, const SwbScoreParams &p, const int8_t *sprof, 
                                            ss);
             continue;
         }
-        uint32_t ti = p.range_start[0] + v;
+        // qpair launches: two work items per tile (first / second sequence of every pair); ntiles counts items
+        const uint32_t half = V::qpair ? (v & 1u) : 0u;
+        const uint32_t vt = V::qpair ? (v >> 1) : v;
+        uint32_t ti = p.range_start[0] + vt;
 #pragma unroll
         for (int r = 1; r < SWB_MAX_RANGES; ++r)
-            if (v >= p.range_cum[r - 1]) ti = p.range_start[r] + (v - p.range_cum[r - 1]);
+            if (vt >= p.range_cum[r - 1]) ti = p.range_start[r] + (vt - p.range_cum[r - 1]);
         if (p.only_flagged && !be.ld_flag(p.flags + ti)) continue;
         const SwbTile tile = be.ld_tile(p.tiles + ti);
         if (tile.logG == 0)
-            swb_run_tile<K, V, false, false>(be, p, tile, ti, sprof, sstride);
+            swb_run_tile<K, V, false, false>(be, p, tile, ti, sprof, sstride, 0, 0xffffffffu, nullptr, 0, half);
         else
-            swb_run_tile<K, V, true, false>(be, p, tile, ti, sprof, sstride);
+            swb_run_tile<K, V, true, false>(be, p, tile, ti, sprof, sstride, 0, 0xffffffffu, nullptr, 0, half);
     }
 }
 

@@ -161,7 +161,7 @@ struct LaneArgs {
     const int8_t *sprof;
     uint32_t sstride;
     int K;
-    bool i32;
+    int mode;  // 0 V16, 1 V32, 2 V16Q
     bool split;
 };
 
@@ -170,7 +170,11 @@ void lane_main(HostBackend &be, void *a)
     const LaneArgs *la = static_cast<const LaneArgs *>(a);
     if (la->split) {
         swb_warp_loop<8, V16, true>(be, *la->p, la->sprof, la->sstride);
-    } else if (!la->i32) {
+    } else if (la->mode == 2) {
+        if (la->K == 8) swb_warp_loop<8, V16Q, false>(be, *la->p, la->sprof, la->sstride);
+        else if (la->K == 16) swb_warp_loop<16, V16Q, false>(be, *la->p, la->sprof, la->sstride);
+        else swb_warp_loop<32, V16Q, false>(be, *la->p, la->sprof, la->sstride);
+    } else if (la->mode == 0) {
         if (la->K == 8) swb_warp_loop<8, V16, false>(be, *la->p, la->sprof, la->sstride);
         else if (la->K == 16) swb_warp_loop<16, V16, false>(be, *la->p, la->sprof, la->sstride);
         else swb_warp_loop<32, V16, false>(be, *la->p, la->sprof, la->sstride);
@@ -182,32 +186,90 @@ void lane_main(HostBackend &be, void *a)
 
 }  // namespace
 
-// Mirrors swb_db_load + one swb_search of the engine (same plan, same chunking, same kernel
-// parameters, same launch groups), with the kernels replaced by the fiber emulation. K: 0 = per-group choice of the
-// planner (the product default), else 8/16/32 for every group size. force_i32: 0 = s16 pass then int32 recompute of
-// flagged tiles (the product flow), 1 = int32 pass over every tile.
-// ovf_thr_override >= 0 replaces the s16 overflow threshold (lets tests force the recompute path).
+// Mirrors swb_db_load + one job of swb_search_batch of the engine (same plan, same chunking, same kernel parameters,
+// same launch groups), with the kernels replaced by the fiber emulation. K: 0 = per-group choice of the planner (the
+// product default), else 8/16/32 for every group size. force_i32: 0 = s16 pass then int32 recompute of flagged tiles
+// (the product flow), 1 = int32 pass over every tile. ovf_thr_override >= 0 replaces the s16 overflow threshold (lets
+// tests force the recompute path). q2 != NULL: a query-pair job (policy V16Q), scores of the second query in
+// scores_out2. xl_len: tiles wider than it run as pipelined passes (single-query jobs only), 0 = never.
+namespace {
+
+struct EmuRun {
+    SwbScoreParams p;
+    uint32_t prof_stride;
+};
+
+void run_pass(SwbScoreParams &p, int mode, const SwbQueryPlan &qp, const std::vector<SwbLaunchGroup> &groups,
+              const std::vector<uint8_t> &profbytes, uint32_t prof_stride)
+{
+    const uint32_t esz = mode == 2 ? 4u : 1u;
+    for (size_t gi = 0; gi < groups.size(); ++gi) {
+        const SwbLaunchGroup &g = groups[gi];
+        for (int r = 0; r < SWB_MAX_RANGES; ++r) {
+            p.range_start[r] = g.range_start[r];
+            p.range_cum[r] = g.range_cum[r];
+        }
+        for (size_t c = 0; c < qp.chunks.size(); ++c) {
+            const SwbQueryChunk &ch = qp.chunks[c];
+            p.split_passes = g.split ? swb_split_passes(ch.rows) : 0;
+            p.ntiles = g.split ? g.ntiles * p.split_passes : (mode == 2 ? 2 * g.ntiles : g.ntiles);
+            std::vector<uint32_t> prog((size_t)g.ntiles * p.split_passes + 1, 0u);
+            p.prog = prog.data();
+            p.row0 = ch.row0;
+            p.rows = ch.rows;
+            p.smem_rows = g.split ? (uint32_t)g.K * 32u : swb_group_smem_rows(ch.rows, g);
+            p.first_chunk = ch.first;
+            p.last_chunk = ch.last;
+            uint32_t counter = 0;
+            p.counter = &counter;
+            // stage the chunk's profile exactly like swb_score_kernel
+            const uint32_t sstride = mode == 2 ? (p.smem_rows + 1u) * 4u : p.smem_rows + 4u;
+            std::vector<uint32_t> sprof_words(((size_t)sstride * SWB_ALPHA + 64) / 4);
+            int8_t *sprof = reinterpret_cast<int8_t *>(sprof_words.data());
+            if (!g.split)
+                for (uint32_t code = 0; code < SWB_ALPHA; ++code)
+                    memcpy(sprof + (size_t)code * sstride,
+                           profbytes.data() + ((size_t)code * prof_stride + ch.row0) * esz, (size_t)p.smem_rows * esz);
+            LaneArgs la;
+            la.p = &p;
+            la.sprof = sprof;
+            la.sstride = sstride;
+            la.K = g.K;
+            la.mode = mode;
+            la.split = g.split;
+            WarpSim *w = new WarpSim();
+            w->run(lane_main, &la);
+            delete w;
+        }
+    }
+}
+
+}  // namespace
+
 extern "C" int swbemu_search(const uint8_t *codes, const uint64_t *offsets, uint32_t n, uint32_t shard,
                              uint32_t nshards, uint32_t group_len, const int8_t *mat32, int gap, const uint8_t *q,
                              uint32_t qlen, int K, int force_i32, uint32_t chunk_rows, int ovf_thr_override,
-                             uint32_t xl_len, int32_t *scores_out, uint32_t *recomputed_tiles)
+                             uint32_t xl_len, int32_t *scores_out, uint32_t *recomputed_tiles, const uint8_t *q2,
+                             uint32_t qlen2, int32_t *scores_out2, uint32_t chunk_rows_pair)
 {
     SwbPlanOpts o;
     if (group_len) o.group_len = group_len;
     o.xl_len = xl_len;
     SwbPlan pl;
     if (swb_build_plan(offsets, n, shard, nshards ? nshards : 1, o, pl) != 0) return -1;
+    const bool pair = q2 != nullptr;
     const uint32_t nl = pl.n_local;
     if (recomputed_tiles) *recomputed_tiles = 0;
     if (nl == 0) return 0;
-    if (qlen == 0 || pl.tiles.empty() || pl.max_len == 0) {
+    const uint32_t rows = pair ? std::max(qlen, qlen2) : qlen;
+    if (rows == 0 || pl.tiles.empty() || pl.max_len == 0) {
         memset(scores_out, 0, sizeof(int32_t) * nl);
+        if (pair) memset(scores_out2, 0, sizeof(int32_t) * nl);
         return 0;
     }
     uint32_t present = 0;
     for (int l = 0; l <= SWB_MAX_LOGG; ++l)
         if (pl.tiles_by_logg[l]) present |= 1u << l;
-    const uint8_t *raw = codes;
     // pack (same function as the device pack kernel)
     std::vector<uint64_t> residues(pl.res_bytes / 8 + 1);
     for (size_t ti = 0; ti < pl.tiles.size(); ++ti) {
@@ -215,92 +277,92 @@ extern "C" int swbemu_search(const uint8_t *codes, const uint64_t *offsets, uint
         const uint32_t P = 32u >> t.logG;
         uint64_t *out = residues.data() + t.res_off / 8;
         for (uint32_t i = 0; i < (t.width >> 2) * P; ++i)
-            out[i] = swb_pack_word(t, i / P, i % P, raw, pl.seq_off.data(), pl.seq_len.data(), nl);
+            out[i] = swb_pack_word(t, i / P, i % P, codes, pl.seq_off.data(), pl.seq_len.data(), nl);
     }
-    int max_s = 0, min_s = 0;
-    for (int i = 0; i < SWB_ALPHA * SWB_ALPHA; ++i) {
-        max_s = std::max<int>(max_s, mat32[i]);
-        min_s = std::min<int>(min_s, mat32[i]);
-    }
-    const int t0 = 0;
-    (void)min_s;
+    int max_s = 0;
+    for (int i = 0; i < SWB_ALPHA * SWB_ALPHA; ++i) max_s = std::max<int>(max_s, mat32[i]);
     if (!chunk_rows) chunk_rows = 7168;
-    SwbQueryPlan qp[2];
-    std::vector<SwbLaunchGroup> groups[2];
-    swb_plan_query(qlen, K, 32, present, chunk_rows, qp[0]);
-    swb_plan_query(qlen, K, 16, present, chunk_rows, qp[1]);
-    swb_plan_launch_groups(pl, qp[0], true, true, groups[0]);
-    swb_plan_launch_groups(pl, qp[1], true, false, groups[1]);
-    const uint32_t prof_rows = std::max(qp[0].prof_rows, qp[1].prof_rows);
-    const uint32_t prof_stride = swb_roundup(prof_rows, 16);
-    std::vector<int8_t> prof((size_t)prof_stride * SWB_ALPHA);
-    for (uint32_t r = 0; r < prof_rows; ++r) {
-        const uint32_t qc = r < qlen ? (q[r] & 31u) : (uint32_t)SWB_PAD;
-        for (uint32_t code = 0; code < SWB_ALPHA; ++code)
-            prof[(size_t)code * prof_stride + r] = (int8_t)(mat32[qc * SWB_ALPHA + code] + gap + t0);
-    }
-    std::vector<int32_t> sorted(2 * (size_t)((nl + 1) / 2), 0);
+    if (!chunk_rows_pair) chunk_rows_pair = 1536;
+
+    std::vector<int32_t> sorted(2 * (size_t)((nl + 1) / 2), 0), sorted2(2 * (size_t)((nl + 1) / 2), 0);
     std::vector<uint8_t> flags(pl.tiles.size(), 0);
-    std::vector<uint32_t> bnd16(pl.bnd_elems + 4);
+    std::vector<uint32_t> bnd16(2 * pl.bnd_elems + 8);
     std::vector<uint64_t> bnd32(pl.bnd_elems + 4);
     uint32_t recount = 0;
-
     SwbScoreParams p;
     memset(&p, 0, sizeof p);
     p.tiles = pl.tiles.data();
     p.residues = reinterpret_cast<const uint8_t *>(residues.data());
-    p.profile = prof.data();
-    p.prof_stride = prof_stride;
-    p.scores = sorted.data();
     p.flags = flags.data();
     p.recount = &recount;
     p.gap = gap;
     p.ovf_thr = ovf_thr_override >= 0 ? ovf_thr_override : 32767 - max_s;
-    p.t0 = t0;
-    for (int pass = force_i32 ? 1 : 0; pass < 2; ++pass) {
-        const bool i32 = pass == 1;
-        p.bnd = i32 ? (void *)bnd32.data() : (void *)bnd16.data();
-        p.only_flagged = (i32 && !force_i32) ? 1u : 0u;
-        for (size_t gi = 0; gi < groups[pass].size(); ++gi) {
-            const SwbLaunchGroup &g = groups[pass][gi];
-            for (int r = 0; r < SWB_MAX_RANGES; ++r) {
-                p.range_start[r] = g.range_start[r];
-                p.range_cum[r] = g.range_cum[r];
-            }
-            for (size_t c = 0; c < qp[pass].chunks.size(); ++c) {
-                const SwbQueryChunk &ch = qp[pass].chunks[c];
-                p.split_passes = g.split ? swb_split_passes(ch.rows) : 0;
-                p.ntiles = g.split ? g.ntiles * p.split_passes : g.ntiles;
-                std::vector<uint32_t> prog((size_t)g.ntiles * p.split_passes + 1, 0u);
-                p.prog = prog.data();
-                p.row0 = ch.row0;
-                p.rows = ch.rows;
-                p.smem_rows = g.split ? (uint32_t)g.K * 32u : swb_group_smem_rows(ch.rows, g);
-                p.first_chunk = ch.first;
-                p.last_chunk = ch.last;
-                uint32_t counter = 0;
-                p.counter = &counter;
-                // stage the chunk's profile exactly like swb_score_kernel
-                const uint32_t sstride = p.smem_rows + 4;
-                std::vector<int8_t> sprof((size_t)sstride * SWB_ALPHA + 16);
-                if (!g.split)
-                    for (uint32_t code = 0; code < SWB_ALPHA; ++code)
-                        memcpy(sprof.data() + (size_t)code * sstride, prof.data() + (size_t)code * prof_stride + ch.row0,
-                               p.smem_rows);
-                LaneArgs la;
-                la.p = &p;
-                la.sprof = sprof.data();
-                la.sstride = sstride;
-                la.K = g.K;
-                la.i32 = i32;
-                la.split = g.split;
-                WarpSim *w = new WarpSim();
-                w->run(lane_main, &la);
-                delete w;
-            }
+    p.t0 = 0;
+
+    auto build_prof8 = [&](const uint8_t *qq, uint32_t ql, uint32_t prows, uint32_t stride, std::vector<uint8_t> &out) {
+        out.assign((size_t)stride * SWB_ALPHA, 0);
+        for (uint32_t r = 0; r < prows; ++r) {
+            const uint32_t qc = r < ql ? (qq[r] & 31u) : (uint32_t)SWB_PAD;
+            for (uint32_t code = 0; code < SWB_ALPHA; ++code)
+                out[(size_t)code * stride + r] = (uint8_t)(int8_t)(mat32[qc * SWB_ALPHA + code] + gap);
         }
+    };
+
+    // pass 0
+    if (!force_i32) {
+        SwbQueryPlan qp0;
+        std::vector<SwbLaunchGroup> g0;
+        swb_plan_query(rows, K, 32, present, pair ? chunk_rows_pair : chunk_rows, qp0);
+        swb_plan_launch_groups(pl, qp0, true, !pair, g0);
+        std::vector<uint8_t> prof;
+        const uint32_t stride = swb_roundup(qp0.prof_rows, 16);
+        if (pair) {
+            prof.assign((size_t)stride * SWB_ALPHA * 4, 0);
+            uint32_t *pw = reinterpret_cast<uint32_t *>(prof.data());
+            for (uint32_t r = 0; r < qp0.prof_rows; ++r) {
+                const uint32_t ca = r < qlen ? (q[r] & 31u) : (uint32_t)SWB_PAD;
+                const uint32_t cb = r < qlen2 ? (q2[r] & 31u) : (uint32_t)SWB_PAD;
+                for (uint32_t code = 0; code < SWB_ALPHA; ++code) {
+                    const uint32_t lo = (uint32_t)(mat32[ca * SWB_ALPHA + code] + gap) & 0xffffu;
+                    const uint32_t hi = (uint32_t)(mat32[cb * SWB_ALPHA + code] + gap) & 0xffffu;
+                    pw[(size_t)code * stride + r] = lo | (hi << 16);
+                }
+            }
+        } else {
+            build_prof8(q, qlen, qp0.prof_rows, stride, prof);
+        }
+        p.profile = reinterpret_cast<const int8_t *>(prof.data());
+        p.prof_stride = stride;
+        p.scores = sorted.data();
+        p.scores2 = sorted2.data();
+        p.bnd = bnd16.data();
+        p.only_flagged = 0;
+        run_pass(p, pair ? 2 : 0, qp0, g0, prof, stride);
     }
-    for (uint32_t s = 0; s < nl; ++s) scores_out[pl.out_pos[s]] = sorted[s];
+    // int32 passes, one per query
+    const uint8_t *qs[2] = {q, q2};
+    const uint32_t qls[2] = {qlen, pair ? qlen2 : 0u};
+    for (int k = 0; k < (pair ? 2 : 1); ++k) {
+        if (qls[k] == 0) continue;
+        SwbQueryPlan qp1;
+        std::vector<SwbLaunchGroup> g1;
+        swb_plan_query(qls[k], K, 16, present, chunk_rows, qp1);
+        swb_plan_launch_groups(pl, qp1, true, false, g1);
+        std::vector<uint8_t> prof;
+        const uint32_t stride = swb_roundup(qp1.prof_rows, 16);
+        build_prof8(qs[k], qls[k], qp1.prof_rows, stride, prof);
+        p.profile = reinterpret_cast<const int8_t *>(prof.data());
+        p.prof_stride = stride;
+        p.scores = k ? sorted2.data() : sorted.data();
+        p.scores2 = nullptr;
+        p.bnd = bnd32.data();
+        p.only_flagged = force_i32 ? 0u : 1u;
+        run_pass(p, 1, qp1, g1, prof, stride);
+    }
+    for (uint32_t s = 0; s < nl; ++s) {
+        scores_out[pl.out_pos[s]] = sorted[s];
+        if (pair) scores_out2[pl.out_pos[s]] = sorted2[s];
+    }
     if (recomputed_tiles) *recomputed_tiles = recount;
     return 0;
 }

@@ -27,10 +27,12 @@ def emu():
     L.swbemu_search.restype = ctypes.c_int
     L.swbemu_search.argtypes = [_u8p, _u64p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, _i8p,
                                 ctypes.c_int, _u8p, ctypes.c_uint32, ctypes.c_int, ctypes.c_int, ctypes.c_uint32,
-                                ctypes.c_int, ctypes.c_uint32, _i32p, ctypes.POINTER(ctypes.c_uint32)]
+                                ctypes.c_int, ctypes.c_uint32, _i32p, ctypes.POINTER(ctypes.c_uint32), _u8p,
+                                ctypes.c_uint32, _i32p, ctypes.c_uint32]
 
     def search(codes, offs, m, q, K=32, group_len=384, force_i32=0, chunk_rows=0, thr=-1, gap=2, shard=0, nshards=1,
-               n_out=None, xl_len=8192):
+               n_out=None, xl_len=8192, q2=None, chunk_rows_pair=0):
+        """q2 given: a query-pair job; returns ((scores, scores2), recomputed_tiles)"""
         codes = np.ascontiguousarray(codes, dtype=np.uint8)
         if len(codes) == 0:
             codes = np.zeros(1, dtype=np.uint8)
@@ -39,11 +41,20 @@ def emu():
         m = np.ascontiguousarray(m, dtype=np.int8)
         n = len(offs) - 1
         out = np.full(n if n_out is None else n_out, -7, dtype=np.int32)
+        out2 = np.full(len(out), -7, dtype=np.int32)
         rc = ctypes.c_uint32()
+        if q2 is not None:
+            q2 = np.ascontiguousarray(q2, dtype=np.uint8)
+            if len(q2) == 0:
+                q2 = np.zeros(1, dtype=np.uint8)[:0]
+        q2p = None if q2 is None else (q2.ctypes.data_as(_u8p) if len(q2) else ctypes.cast(out2.ctypes.data, _u8p))
         r = L.swbemu_search(codes.ctypes.data_as(_u8p), offs.ctypes.data_as(_u64p), n, shard, nshards, group_len,
                             m.ctypes.data_as(_i8p), gap, q.ctypes.data_as(_u8p) if len(q) else None, len(q), K,
-                            force_i32, chunk_rows, thr, xl_len, out.ctypes.data_as(_i32p), ctypes.byref(rc))
+                            force_i32, chunk_rows, thr, xl_len, out.ctypes.data_as(_i32p), ctypes.byref(rc), q2p,
+                            0 if q2 is None else len(q2), out2.ctypes.data_as(_i32p), chunk_rows_pair)
         assert r == 0
+        if q2 is not None:
+            return (out, out2), rc.value
         return out, rc.value
 
     return search
@@ -144,3 +155,28 @@ def test_pipelined_passes_of_very_long_tiles(emu, oracle):
     want = oracle.scan(w, c2, o2, m)
     got, rc = emu(c2, o2, m, w, K=0, group_len=16, xl_len=500)
     assert want[0] == 34500 and np.array_equal(got, want) and rc >= 1
+
+
+def test_query_pair_jobs(emu, oracle, subset, queries):
+    """V16Q: two queries in the halves of the s16x2 lanes against one DB sequence per lane; the tile is two work
+    items (first / second sequence of every pair). Unequal lengths, chunked profile, overflow of one query only."""
+    m = oracle.matrix("blosum50")
+    codes, offs = subset["codes"], subset["offsets"]
+    for na, nb, kw in (("P02232", "P05013", dict(K=0, group_len=384)), ("P01008", "P02232", dict(K=0, group_len=64)),
+                       ("P14942", "P14942", dict(K=16, group_len=16)),
+                       ("P27895", "P07327", dict(K=0, group_len=128, chunk_rows_pair=512))):
+        qa, qb = oracle.encode(queries[na]), oracle.encode(queries[nb])
+        (ga, gb), _ = emu(codes, offs, m, qa, q2=qb, **kw)
+        assert np.array_equal(ga, oracle.scan(qa, codes, offs, m)), (na, nb)
+        assert np.array_equal(gb, oracle.scan(qb, codes, offs, m)), (na, nb)
+    rng = np.random.default_rng(8)
+    w = np.full(2300, 17, dtype=np.uint8)
+    enc = [w, rng.integers(0, 20, 300).astype(np.uint8), w[:2200].copy(), rng.integers(0, 20, 50).astype(np.uint8),
+           np.zeros(0, np.uint8)]
+    c2, o2 = pack_db(enc)
+    qb = rng.integers(0, 20, 700).astype(np.uint8)
+    (ga, gb), rc = emu(c2, o2, m, w, q2=qb, K=0, group_len=384)
+    assert np.array_equal(ga, oracle.scan(w, c2, o2, m)) and ga[0] == 34500 and rc >= 1
+    assert np.array_equal(gb, oracle.scan(qb, c2, o2, m))
+    (ga, gb), _ = emu(c2, o2, m, qb[:9], q2=np.zeros(0, np.uint8), K=0)
+    assert np.array_equal(ga, oracle.scan(qb[:9], c2, o2, m)) and not gb.any()

@@ -359,3 +359,28 @@ def test_pipelined_passes_option(swb, oracle):
         assert np.array_equal(batch[2], oracle.scan(q, codes, offs, m))
     finally:
         e.close()
+
+
+def test_query_pair_packing_option(swb, oracle, subset, queries):
+    """option pair_queries=1: a batch runs two queries per job in the halves of the s16x2 lanes (policy V16Q), one
+    database sequence per lane; odd batch sizes, very different lengths, chunked pair profile, overflow of one query"""
+    m = oracle.matrix("blosum50")
+    e = swb.Engine(0, pair_queries=1)
+    try:
+        e.db_load(subset["codes"], subset["offsets"])
+        names = sorted(queries)[:7]
+        got = e.search_batch([swb.encode(queries[n]) for n in names])
+        for i, n in enumerate(names):
+            assert np.array_equal(got[i], oracle.scan(oracle.encode(queries[n]), subset["codes"], subset["offsets"], m)), n
+        rng = np.random.default_rng(4)
+        w = np.full(2400, 17, dtype=np.uint8)
+        enc = random_db(rng, rng.integers(1, 1500, 300), alphabet=20) + [w.copy(), w[:2300].copy()]
+        codes, offs = pack_db(enc)
+        e.db_load(codes, offs)
+        qs = [w, rng.integers(0, 20, 3000).astype(np.uint8), rng.integers(0, 20, 40).astype(np.uint8), np.zeros(0, np.uint8)]
+        got = e.search_batch(qs)
+        for i, q in enumerate(qs):
+            assert np.array_equal(got[i], oracle.scan(q, codes, offs, m)), i
+        assert got[0].max() == 15 * 2400 and e.stats()["recomputed_tiles"] >= 1
+    finally:
+        e.close()

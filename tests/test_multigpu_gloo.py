@@ -36,12 +36,13 @@ def _worker(rank, world, port, q):
         emu.swbemu_search.restype = ctypes.c_int
         emu.swbemu_search.argtypes = [u8p, u64p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, i8p,
                                       ctypes.c_int, u8p, ctypes.c_uint32, ctypes.c_int, ctypes.c_int, ctypes.c_uint32,
-                                      ctypes.c_int, ctypes.c_uint32, i32p, ctypes.POINTER(ctypes.c_uint32)]
+                                      ctypes.c_int, ctypes.c_uint32, i32p, ctypes.POINTER(ctypes.c_uint32), u8p,
+                                      ctypes.c_uint32, i32p, ctypes.c_uint32]
         mine = np.zeros(info.n_local, dtype=np.int32)
         rc = ctypes.c_uint32()
         assert emu.swbemu_search(codes.ctypes.data_as(u8p), offs.ctypes.data_as(u64p), len(seqs), rank, world, 384,
                                  m.ctypes.data_as(i8p), 2, query.ctypes.data_as(u8p), len(query), 0, 0, 0, -1, 8192,
-                                 mine.ctypes.data_as(i32p), ctypes.byref(rc)) == 0
+                                 mine.ctypes.data_as(i32p), ctypes.byref(rc), None, 0, None, 0) == 0
         order = np.lexsort((ids, -mine))[:10]
         parts = [None] * world
         dist.all_gather_object(parts, (ids.tolist(), mine.tolist(), ids[order].tolist(), mine[order].tolist()))

@@ -384,3 +384,31 @@ def test_query_pair_packing_option(swb, oracle, subset, queries):
         assert got[0].max() == 15 * 2400 and e.stats()["recomputed_tiles"] >= 1
     finally:
         e.close()
+
+
+def test_cli_missing_files_and_error_codes(swb, tmp_path):
+    """reference behaviour Q9: a nonexistent database is one empty record with id -1, a nonexistent query an
+    empty buffer -> every score is 0, exit code 0; C ABI argument errors come back as codes with a message"""
+    main = os.path.join(ROOT, "ece1782-smith-waterman-cuda_b200", "bin", "main")
+    r = subprocess.run([main, "--query", "/nonexistent/q.fasta", "--db", "/nonexistent/db.fasta"], capture_output=True,
+                       text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.split("\n")
+    assert lines[0] == "Input buffer:" and lines[2] == "-1:0" and lines[3] == "=" * 80
+    assert "Query length: 0 chars." in r.stdout and "Num subjects: 1" in r.stdout and "Sum of DB length: 0 chars." in r.stdout
+    e = swb.Engine(0)
+    try:
+        with pytest.raises(swb.SwbError):
+            e.search(np.zeros(5, np.uint8))          # no database yet
+        with pytest.raises(swb.SwbError):
+            e.set_option("k", 7)
+        with pytest.raises(swb.SwbError):
+            e.set_scoring(np.full((4, 4), 127, np.int8), 2)   # S + gap does not fit int8
+        with pytest.raises(swb.SwbError):
+            e.db_load(np.zeros(4, np.uint8), np.array([0, 3, 2], np.uint64))  # decreasing offsets
+        e.db_load(np.zeros(4, np.uint8), np.array([0, 3, 4], np.uint64))
+        with pytest.raises(swb.SwbError):
+            e.align(np.zeros(3, np.uint8), 7, 3)     # id not in the database
+        assert e.search(np.zeros(3, np.uint8)).tolist() == [15, 5]   # AAA vs AAA / A, BLOSUM50 A-A = 5
+    finally:
+        e.close()

@@ -71,7 +71,9 @@ ABI_SYMBOLS = [
     "swb_create", "swb_destroy", "swb_last_error", "swb_set_option", "swb_set_stream", "swb_set_scoring",
     "swb_set_scoring_preset", "swb_scoring_matrix", "swb_encode", "swb_db_load", "swb_db_count", "swb_db_ids",
     "swb_search", "swb_search_batch", "swb_fetch_scores", "swb_topk", "swb_stats", "swb_plan_describe",
-    "swb_microbench", "swb_align",
+    "swb_microbench", "swb_align", "swb_read_fasta", "swb_read_uniprot_dat", "swb_free", "swb_dbfile_write",
+    "swb_dbfile_open", "swb_dbfile_count", "swb_dbfile_first_id", "swb_dbfile_offsets", "swb_dbfile_codes",
+    "swb_dbfile_close",
 ]
 
 _lib = None
@@ -134,6 +136,27 @@ def lib():
                                     ctypes.POINTER(SwbPlanInfo), _u32p, _u32p]
     L.swb_align.restype = ctypes.c_int
     L.swb_align.argtypes = [vp, _u8p, ctypes.c_uint32, ctypes.c_uint32, _i32p, _u32p, _u32p, _u8p, ctypes.c_uint32, _u32p]
+    L.swb_read_fasta.restype = ctypes.c_int
+    L.swb_read_fasta.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(_u8p), ctypes.POINTER(_u64p), _u32p,
+                                 _i32p]
+    L.swb_read_uniprot_dat.restype = ctypes.c_int
+    L.swb_read_uniprot_dat.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(_u8p), ctypes.POINTER(_u64p), _u32p]
+    L.swb_free.restype = None
+    L.swb_free.argtypes = [vp]
+    L.swb_dbfile_write.restype = ctypes.c_int
+    L.swb_dbfile_write.argtypes = [ctypes.c_char_p, _u8p, _u64p, ctypes.c_uint32, ctypes.c_int32]
+    L.swb_dbfile_open.restype = ctypes.c_int
+    L.swb_dbfile_open.argtypes = [ctypes.c_char_p, ctypes.POINTER(vp)]
+    L.swb_dbfile_count.restype = ctypes.c_uint32
+    L.swb_dbfile_count.argtypes = [vp]
+    L.swb_dbfile_first_id.restype = ctypes.c_int32
+    L.swb_dbfile_first_id.argtypes = [vp]
+    L.swb_dbfile_offsets.restype = _u64p
+    L.swb_dbfile_offsets.argtypes = [vp]
+    L.swb_dbfile_codes.restype = _u8p
+    L.swb_dbfile_codes.argtypes = [vp]
+    L.swb_dbfile_close.restype = None
+    L.swb_dbfile_close.argtypes = [vp]
     L.swb_microbench.restype = ctypes.c_int
     L.swb_microbench.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double),
                                  ctypes.POINTER(ctypes.c_double)]
@@ -175,6 +198,64 @@ def pack_sequences(encoded):
     else:
         codes = np.zeros(1, dtype=np.uint8)
     return codes, offsets
+
+
+def _take(codes_p, offs_p, n):
+    """copies malloc'ed (codes, offsets) out of the library and releases them"""
+    L = lib()
+    offsets = np.ctypeslib.as_array(offs_p, shape=(n + 1,)).copy()
+    total = int(offsets[-1])
+    codes = np.ctypeslib.as_array(codes_p, shape=(max(total, 1),))[:total].copy()
+    L.swb_free(ctypes.cast(codes_p, ctypes.c_void_p))
+    L.swb_free(ctypes.cast(offs_p, ctypes.c_void_p))
+    return codes, offsets
+
+
+def read_fasta(path, preset=SWB_SCORING_BLOSUM50_REF):
+    """(codes, offsets, first_id): the records of a FASTA file as the reference parser cuts them, without '/' padding"""
+    cp, op, n, fid = _u8p(), _u64p(), ctypes.c_uint32(), ctypes.c_int32()
+    rc = lib().swb_read_fasta(os.fsencode(path), preset, ctypes.byref(cp), ctypes.byref(op), ctypes.byref(n),
+                              ctypes.byref(fid))
+    if rc != 0:
+        raise SwbError("swb_read_fasta(%s) failed (%d)" % (path, rc))
+    codes, offsets = _take(cp, op, n.value)
+    return codes, offsets, fid.value
+
+
+def read_uniprot_dat(path, preset=SWB_SCORING_BLOSUM50_REF):
+    cp, op, n = _u8p(), _u64p(), ctypes.c_uint32()
+    rc = lib().swb_read_uniprot_dat(os.fsencode(path), preset, ctypes.byref(cp), ctypes.byref(op), ctypes.byref(n))
+    if rc != 0:
+        raise SwbError("swb_read_uniprot_dat(%s) failed (%d)" % (path, rc))
+    return _take(cp, op, n.value)
+
+
+def dbfile_write(path, codes, offsets, first_id=0):
+    codes = np.ascontiguousarray(codes, dtype=np.uint8)
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    cpz = codes if len(codes) else np.zeros(1, np.uint8)
+    rc = lib().swb_dbfile_write(os.fsencode(path), cpz.ctypes.data_as(_u8p), offsets.ctypes.data_as(_u64p),
+                                len(offsets) - 1, first_id)
+    if rc != 0:
+        raise SwbError("swb_dbfile_write(%s) failed (%d)" % (path, rc))
+
+
+def dbfile_read(path):
+    """(codes, offsets, first_id) copied out of a memory-mapped encoded database"""
+    L = lib()
+    h = ctypes.c_void_p()
+    rc = L.swb_dbfile_open(os.fsencode(path), ctypes.byref(h))
+    if rc != 0:
+        raise SwbError("swb_dbfile_open(%s) failed (%d)" % (path, rc))
+    try:
+        n = L.swb_dbfile_count(h)
+        offsets = np.ctypeslib.as_array(L.swb_dbfile_offsets(h), shape=(n + 1,)).copy()
+        total = int(offsets[-1])
+        codes = np.ctypeslib.as_array(L.swb_dbfile_codes(h), shape=(max(total, 1),))[:total].copy() if total else \
+            np.zeros(0, np.uint8)
+        return codes, offsets, int(L.swb_dbfile_first_id(h))
+    finally:
+        L.swb_dbfile_close(h)
 
 
 def plan_describe(offsets, shard=0, nshards=1, group_len=0, want_ids=False):

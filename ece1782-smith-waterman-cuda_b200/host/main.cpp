@@ -7,8 +7,11 @@
 #include <string>
 #include <vector>
 
+#include <algorithm>
+
 #include "FASTAParsers.h"
 #include "SWSolver.h"
+#include "swb.h"
 
 static double wall_seconds()
 {
@@ -41,6 +44,63 @@ static int match_option(const std::string &name)
     }
     if (hit < 0) throw std::runtime_error("unrecognised option '--" + name + "'");
     return hit;
+}
+
+// Extension: --db <file>.swbdb takes an encoded database written by bin/swb_mkdb (include/swb.h, swb_dbfile_*)
+// instead of parsing text. Same stdout as the text path: ids, result order (descending padded length, file order
+// inside a bucket, SWSolver.cu:383-390) and the METRICS block are recomputed from the stored offsets.
+static int scan_encoded_db(const std::string &querypath, const std::string &datapath, double time_start)
+{
+    if (datapath.size() > 6 && datapath.compare(datapath.size() - 6, 6, ".swbdb") == 0)
+        return scan_encoded_db(querypath, datapath, time_start);
+
+    FASTAQuery query(querypath, true);
+    cout << "Input buffer:";
+    query.print_buffer();
+    cout << endl;
+    const string q = query.get_buffer();
+    swb_dbfile *dbf = nullptr;
+    if (swb_dbfile_open(datapath.c_str(), &dbf) != SWB_OK) throw std::runtime_error("cannot open encoded database " + datapath);
+    const uint32_t n = swb_dbfile_count(dbf);
+    const uint64_t *offsets = swb_dbfile_offsets(dbf);
+    const int first_id = swb_dbfile_first_id(dbf);
+    swb_engine *eng = nullptr;
+    if (swb_create(&eng, 0) != SWB_OK) throw std::runtime_error(std::string("swb_create: ") + swb_last_error(nullptr));
+    std::vector<uint8_t> qcodes(q.size() ? q.size() : 1);
+    swb_encode(SWB_SCORING_BLOSUM50_REF, q.data(), q.size(), qcodes.data());
+    std::vector<int32_t> scores(n ? n : 1);
+    if (swb_db_load(eng, swb_dbfile_codes(dbf), offsets, n, 0, 1) != SWB_OK ||
+        swb_search(eng, qcodes.data(), (uint32_t)q.size(), scores.data()) != SWB_OK)
+        throw std::runtime_error(std::string("scan failed: ") + swb_last_error(eng));
+    std::vector<uint32_t> order(n);
+    long long padded_sum = 0;
+    std::vector<uint64_t> padded(n);
+    for (uint32_t i = 0; i < n; ++i) {
+        order[i] = i;
+        padded[i] = (offsets[i + 1] - offsets[i] + TILE_SIZE - 1) / TILE_SIZE * TILE_SIZE;
+        padded_sum += (long long)padded[i];
+    }
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return padded[a] > padded[b]; });
+    std::string lines;
+    lines.reserve((size_t)n * 12);
+    for (uint32_t k = 0; k < n; ++k) {
+        lines += std::to_string((long long)order[k] + first_id);
+        lines += ':';
+        lines += std::to_string(scores[order[k]]);
+        lines += '\n';
+    }
+    cout << lines;
+    const double seconds_elapsed = wall_seconds() - time_start;
+    cout << std::string(80, '=') << endl;
+    cout << "METRICS:" << endl;
+    cout << "Query length: " << q.length() << " chars." << endl;
+    cout << "Num subjects: " << n << endl;
+    cout << "Sum of DB length: " << (int)padded_sum << " chars." << endl;
+    cout << "Time elapsed: " << seconds_elapsed << " seconds." << endl;
+    cout << "Performance: " << 1E-9 * ((double)q.length() * (double)padded_sum) / seconds_elapsed << " GCUPS." << endl;
+    swb_destroy(eng);
+    swb_dbfile_close(dbf);
+    return 0;
 }
 
 int main(int argc, char *argv[])

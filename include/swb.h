@@ -128,6 +128,25 @@ typedef struct swb_plan_info_t {
 int swb_plan_describe(const uint64_t *offsets, uint32_t n, uint32_t shard, uint32_t nshards, uint32_t group_len,
                       swb_plan_info_t *info, uint32_t *sorted_ids, uint32_t *shard_ids);
 
+/* ---- database ingest and the encoded on-disk database, CPU only (the reference re-parses and ---- */
+/* ---- re-packs text on every run, FASTAParsers.h:73-136, SWSolver.cu:301-359) ------------------------------- */
+typedef struct swb_dbfile swb_dbfile;
+/* Text -> encoded arrays (malloc'ed, release with swb_free). swb_read_fasta follows the record rules of the reference
+ * parser (records at '>' lines; a file without '>' is one record whose reference id is -1, reported in *first_id)
+ * without its '/' padding; swb_read_uniprot_dat takes the SQ blocks of a UniProt flat file (parse.py:24-35). */
+int swb_read_fasta(const char *path, int preset, uint8_t **codes, uint64_t **offsets, uint32_t *n, int32_t *first_id);
+int swb_read_uniprot_dat(const char *path, int preset, uint8_t **codes, uint64_t **offsets, uint32_t *n);
+void swb_free(void *p);
+/* One memory-mappable file: 32-byte header, n+1 64-bit offsets, the codes. The pointers of an open file stay valid
+ * until swb_dbfile_close and can be passed straight to swb_db_load. */
+int swb_dbfile_write(const char *path, const uint8_t *codes, const uint64_t *offsets, uint32_t n, int32_t first_id);
+int swb_dbfile_open(const char *path, swb_dbfile **out);
+uint32_t swb_dbfile_count(const swb_dbfile *d);
+int32_t swb_dbfile_first_id(const swb_dbfile *d);
+const uint64_t *swb_dbfile_offsets(const swb_dbfile *d);
+const uint8_t *swb_dbfile_codes(const swb_dbfile *d);
+void swb_dbfile_close(swb_dbfile *d);
+
 /* ---- measurement support (not on the scoring path) ------------------------------------------- */
 /* Issue rate of the integer SIMD instructions the score kernel is built from, whole GPU, in giga
  * lane-instructions/s. kind: 0 viaddmax.s16x2.relu, 1 vimax3.s16x2, 2 vadd2, 3 prmt, 4 the score kernel's per-cell

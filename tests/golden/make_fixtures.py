@@ -8,6 +8,7 @@ What it writes (all small, committed):
                             (SQ-block extraction recipe: src/parse.py:24-35), ids 0..110
   queries/*.fasta           the 20 query files of data/queries/, byte for byte
   test.dat                  data/dbs/test.dat (a header-less file; parser edge case)
+  uniprot_head5.dat         the first five entries of data/dbs/uniprot_subset.dat (UniProt flat-file text)
   P01008.head111.txt, P02232.head111.txt
                             lines 1-111 of test/reference/P01008.txt / P02232.txt: the reference's
                             golden scores (test/swissprot_tests.cpp:68-72) for DB ids 0..110
@@ -95,6 +96,16 @@ def main():
         with open(os.path.join(REF, "test/reference", g + ".txt")) as f:
             head = [next(f) for _ in range(111)]
         open(os.path.join(HERE, g + ".head111.txt"), "w").writelines(head)
+
+    # first five entries of the flat file (the last one without its "//"), for the flat-file reader
+    lines, seen = [], 0
+    for line in open(os.path.join(REF, "data/dbs/uniprot_subset.dat")):
+        lines.append(line)
+        if line.startswith("//"):
+            seen += 1
+            if seen == 5:
+                break
+    open(os.path.join(HERE, "uniprot_head5.dat"), "w").writelines(lines[:-1])
 
     exp_dir = os.path.join(ROOT, "baseline", "_ref", "exp")
     if os.path.isdir(exp_dir):

@@ -412,3 +412,28 @@ def test_cli_missing_files_and_error_codes(swb, tmp_path):
         assert e.search(np.zeros(3, np.uint8)).tolist() == [15, 5]   # AAA vs AAA / A, BLOSUM50 A-A = 5
     finally:
         e.close()
+
+
+def test_cli_encoded_database_matches_text_database(swb, tmp_path):
+    """bin/main --db <file>.swbdb (written by bin/swb_mkdb) prints the same ids, scores, order and METRICS counts as
+    the same database given as FASTA text"""
+    pkg = os.path.join(ROOT, "ece1782-smith-waterman-cuda_b200")
+    main, mkdb = os.path.join(pkg, "bin", "main"), os.path.join(pkg, "bin", "swb_mkdb")
+    fasta = os.path.join(GOLDEN, "uniprot_subset.fasta")
+    enc = str(tmp_path / "subset.swbdb")
+    assert subprocess.run([mkdb, fasta, enc], capture_output=True).returncode == 0
+    q = os.path.join(GOLDEN, "queries", "P02232.fasta")
+    outs = []
+    for db in (fasta, enc):
+        r = subprocess.run([main, "--query", q, "--db", db], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr
+        outs.append([l for l in r.stdout.split("\n") if not l.startswith(("Time elapsed", "Performance"))])
+    assert outs[0] == outs[1] and len(outs[0]) > 115
+    # header-less text file: one record with id -1 in both paths (FASTAParsers.h:82)
+    enc2 = str(tmp_path / "test.swbdb")
+    assert subprocess.run([mkdb, os.path.join(GOLDEN, "test.dat"), enc2], capture_output=True).returncode == 0
+    outs = []
+    for db in (os.path.join(GOLDEN, "test.dat"), enc2):
+        r = subprocess.run([main, "--query", q, "--db", db], capture_output=True, text=True, timeout=300)
+        outs.append([l for l in r.stdout.split("\n") if not l.startswith(("Time elapsed", "Performance"))])
+    assert outs[0] == outs[1] and outs[0][2].startswith("-1:")

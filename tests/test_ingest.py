@@ -1,0 +1,95 @@
+"""Database ingest and the encoded on-disk database (CPU only): swb_read_fasta must cut records exactly like the
+reference parser (checked against the expectations printed by /root/reference/src/FASTAParsers.h itself, minus its '/'
+padding), swb_read_uniprot_dat must find the SQ blocks the reference's parse.py recipe finds, and a written
+database file must map back bit for bit."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, PKG, ROOT
+from oracle_lib import read_fasta
+
+EXPECT = os.path.join(GOLDEN, "parser_expect")
+
+
+def _expected_records(name):
+    """(ids, sequences without '/' padding) in FILE order from the reference parser's dump"""
+    lines = open(os.path.join(EXPECT, name + ".db.txt"), "rb").read().decode("latin-1").split("\n")[4:]
+    recs = []
+    for l in lines:
+        if not l.strip() and l == "":
+            continue
+        sid, plen, seq = (l.split(" ", 2) + [""])[:3]
+        recs.append((int(sid), seq.rstrip("/") if seq.endswith("/") else seq))
+    recs.sort(key=lambda r: r[0])
+    return recs
+
+
+@pytest.mark.parametrize("name", ["uniprot_subset.fasta", "test.dat", "tricky.fasta", "empty.fasta", "noeol.fasta"])
+def test_read_fasta_matches_reference_parser(swb, name):
+    codes, offs, first_id = swb.read_fasta(os.path.join(GOLDEN, name))
+    recs = _expected_records(name)
+    assert len(offs) - 1 == len(recs)
+    assert first_id == recs[0][0]
+    for k, (sid, seq) in enumerate(recs):
+        assert sid == first_id + k
+        got = codes[int(offs[k]):int(offs[k + 1])]
+        want = swb.encode(seq)
+        # the reference pads with '/', which it cannot tell from a real trailing '/' either: compare up to padding
+        assert np.array_equal(got[:len(want)], want) and (got[len(want):] == 24).all(), (name, k)
+
+
+def test_read_fasta_missing_file_is_one_empty_record(swb):
+    codes, offs, first_id = swb.read_fasta("/nonexistent/file.fasta")
+    assert len(codes) == 0 and offs.tolist() == [0, 0] and first_id == -1
+
+
+def test_read_uniprot_dat(swb):
+    codes, offs = swb.read_uniprot_dat(os.path.join(GOLDEN, "uniprot_head5.dat"))
+    _, seqs = read_fasta(os.path.join(GOLDEN, "uniprot_subset.fasta"))
+    assert len(offs) - 1 == 5  # the fifth entry has no trailing "//"
+    for k in range(5):
+        assert np.array_equal(codes[int(offs[k]):int(offs[k + 1])], swb.encode(seqs[k])), k
+    with pytest.raises(swb.SwbError):
+        swb.read_uniprot_dat("/nonexistent/file.dat")
+
+
+def test_dbfile_roundtrip_and_rejects_garbage(swb, tmp_path):
+    rng = np.random.default_rng(3)
+    lens = [0, 5, 1, 300, 0, 17]
+    codes = rng.integers(0, 25, sum(lens)).astype(np.uint8)
+    offs = np.zeros(len(lens) + 1, np.uint64)
+    offs[1:] = np.cumsum(lens)
+    path = str(tmp_path / "db.swbdb")
+    swb.dbfile_write(path, codes, offs, first_id=0)
+    c2, o2, fid = swb.dbfile_read(path)
+    assert np.array_equal(c2, codes) and np.array_equal(o2, offs) and fid == 0
+    assert os.path.getsize(path) == 32 + 8 * (len(lens) + 1) + len(codes)
+    swb.dbfile_write(path, np.zeros(0, np.uint8), np.array([0], np.uint64), first_id=-1)
+    c3, o3, fid = swb.dbfile_read(path)
+    assert len(c3) == 0 and o3.tolist() == [0] and fid == -1
+    bad = str(tmp_path / "bad.swbdb")
+    open(bad, "wb").write(b"not a database file, definitely longer than the header")
+    with pytest.raises(swb.SwbError):
+        swb.dbfile_read(bad)
+    with pytest.raises(swb.SwbError):
+        swb.dbfile_read(str(tmp_path / "missing.swbdb"))
+
+
+def test_mkdb_tool(swb, tmp_path):
+    tool = os.path.join(ROOT, PKG, "bin", "swb_mkdb")
+    if not os.path.exists(tool):
+        swb.build()
+    out = str(tmp_path / "subset.swbdb")
+    r = subprocess.run([tool, os.path.join(GOLDEN, "uniprot_subset.fasta"), out], capture_output=True, text=True)
+    assert r.returncode == 0 and "111 sequences, 26299 residues" in r.stdout
+    codes, offs, fid = swb.dbfile_read(out)
+    c0, o0, f0 = swb.read_fasta(os.path.join(GOLDEN, "uniprot_subset.fasta"))
+    assert np.array_equal(codes, c0) and np.array_equal(offs, o0) and fid == f0 == 0
+    out2 = str(tmp_path / "head5.swbdb")
+    r = subprocess.run([tool, "--uniprot-dat", os.path.join(GOLDEN, "uniprot_head5.dat"), out2], capture_output=True,
+                       text=True)
+    assert r.returncode == 0 and r.stdout.startswith("5 sequences")
+    assert subprocess.run([tool], capture_output=True).returncode == 2

@@ -62,6 +62,31 @@ def synth_db(n=570000, seed=1782, scale=1.0):
     return codes, offsets
 
 
+def synth_db_uniprot_scale(parts=10):
+    """configs[4]: ~10 x Swiss-Prot: `parts` Swiss-Prot-shaped databases (seeds 1785, 1786, ...) back to back."""
+    all_codes, all_lens = [], []
+    for k in range(parts):
+        c, o = synth_db(seed=1785 + k)
+        all_codes.append(c)
+        all_lens.append(np.diff(o.astype(np.int64)))
+    codes = np.concatenate(all_codes)
+    lens = np.concatenate(all_lens)
+    offsets = np.zeros(len(lens) + 1, dtype=np.uint64)
+    offsets[1:] = np.cumsum(lens)
+    return codes, offsets
+
+
+def synth_queries(n=1000, seed=1785):
+    """configs[4]: queries drawn from the database length law, clipped to [30, 5478], Swiss-Prot composition"""
+    rng = np.random.default_rng(seed)
+    lens = np.clip(np.round(rng.lognormal(5.58, 0.75, n)), 30, 5478).astype(np.int64)
+    p = np.zeros(32)
+    for ch, f in COMPOSITION.items():
+        p[ORDER.index(ch)] = f
+    p /= p.sum()
+    return [rng.choice(32, size=int(l), p=p).astype(np.uint8) for l in lens]
+
+
 def load_queries(swb):
     qdir = os.path.join(ROOT, "tests", "golden", "queries")
     names = sorted(fn[:-6] for fn in os.listdir(qdir) if fn.endswith(".fasta"))
@@ -169,6 +194,11 @@ def run_reference(args):
 
 
 def workload_config(offsets, qs, args):
+    if getattr(args, "workload", "config2") == "config5":
+        return {"workload": "configs[4]: 1,000 synthetic queries x UniProt-scale synthetic DB (10 Swiss-Prot-shaped parts)",
+                "db_sequences": int(len(offsets) - 1), "db_residues": int(offsets[-1]), "queries": len(qs),
+                "query_residues": int(sum(len(q) for q in qs)), "scoring": "BLOSUM50 ('*' zeroed), linear gap 2",
+                "l2": "inputs larger than L2"}
     return {"workload": "configs[1]: Swiss-Prot-shaped synthetic DB (seed 1782) x reference 20-query set",
             "db_sequences": int(len(offsets) - 1), "db_residues": int(offsets[-1]), "queries": len(qs),
             "query_residues": int(sum(len(q) for q in qs)), "scoring": "BLOSUM50 ('*' zeroed), linear gap 2",
@@ -182,6 +212,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--scale", type=float, default=1.0, help="database size factor (1.0 = the named workload)")
+    ap.add_argument("--workload", default="config2", help="config2 (default, the headline) or config5 (1,000 queries "
+                    "x UniProt-scale database; meant for 8 GPUs)")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--streams", type=int, default=0)
@@ -207,8 +239,14 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     swb = importlib.import_module(PKG)
-    codes, offsets = synth_db(scale=args.scale)
-    names, qs = load_queries(swb)
+    if args.workload == "config5":
+        codes, offsets = synth_db_uniprot_scale()
+        qs = synth_queries()
+        names = ["q%d" % i for i in range(len(qs))]
+        args.no_cpu = True
+    else:
+        codes, offsets = synth_db(scale=args.scale)
+        names, qs = load_queries(swb)
     qcodes, qoffs = swb.pack_sequences(qs)
     total_cells = float(sum(len(q) for q in qs)) * float(offsets[-1])
 
@@ -263,8 +301,25 @@ def main():
     ms_per_step = ms_max / args.steps
     value = total_cells / (ms_per_step * 1e-3) * 1e-9
 
+    # configs[4] parity: 5 queries x a 1/1024 stride sample of this rank's shard against the oracle
+    sample_ok = None
+    if args.workload == "config5":
+        from oracle_lib import Oracle
+        o = Oracle()
+        ids = eng.db_ids()
+        sel = ids[::1024]
+        sub = [codes[int(offsets[i]):int(offsets[i + 1])] for i in sel]
+        sc, so = swb.pack_sequences(sub)
+        sample_ok = True
+        for qi in (0, 250, 500, 750, 999):
+            got = eng.fetch_scores(qi)[::1024]
+            want = o.scan(qs[qi], sc, so, o.matrix("blosum50"))
+            sample_ok = sample_ok and bool(np.array_equal(got, want))
+        args.e2e_steps = 0
+
     # end to end through the C ABI with host buffers (database upload + search + scores back), wall clock
-    out = np.zeros((len(qs), nloc), dtype=np.int32)
+    big = args.workload == "config5"  # no nq x n host matrix at UniProt scale: top hits come from fetch_scores
+    out = np.zeros((1 if big else len(qs), nloc), dtype=np.int32)
     e2e_times = []
     for it in range(args.e2e_steps + 1 if args.e2e_steps > 0 else 0):
         barrier()
@@ -282,7 +337,7 @@ def main():
     load_ms = eng.stats()["load_ms"]
     e2e = {"value": total_cells / e2e_s * 1e-9, "unit": "GCUPS",
            "h2d_bytes_per_step": int(codes.nbytes + offsets.nbytes + qcodes.nbytes + qoffs.nbytes),
-           "d2h_bytes_per_step": int(out.nbytes), "seconds_per_step": e2e_s, "db_load_ms": load_ms,
+           "d2h_bytes_per_step": int(4 * len(qs) * nloc), "seconds_per_step": e2e_s, "db_load_ms": load_ms,
            "api": "swb_db_load + swb_search_batch (host buffers)"}
 
     # host merge of the per-rank hit lists (top-10 per query), checks the sharded path end to end
@@ -290,7 +345,7 @@ def main():
     if world > 1:
         mine = []
         for qi in range(len(qs)):
-            ids, top = eng.topk(out[qi], 10)
+            ids, top = eng.topk(eng.fetch_scores(qi) if big else out[qi], 10)
             mine.append((ids.tolist(), top.tolist()))
         gathered = [None] * world
         dist.all_gather_object(gathered, mine)
@@ -338,7 +393,7 @@ def main():
                 "config": workload_config(offsets, qs, args), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
                 "roofline": roofline, "engine": {k: st[k] for k in ("tiles", "tiles_by_group", "last_k",
                                                                     "recomputed_tiles", "sm_count")},
-                "topk_merge_ok": top_ok}
+                "topk_merge_ok": top_ok, "config5_sample_parity_ok": sample_ok}
         if not args.no_cpu:
             names_t, qtexts = load_queries(None)
             line["cpu_baseline"], _ = cpu_sample_gcups(codes, offsets, names_t, qtexts, args.cpu_seconds)

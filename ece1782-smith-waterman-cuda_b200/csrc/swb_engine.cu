@@ -692,7 +692,6 @@ static int enqueue_job(swb_engine *e, Slot &s, uint32_t qi, const uint8_t *q, ui
     p.recount = s.d_recount;
     p.gap = e->gap;
     p.ovf_thr = ovf_thr;
-    p.t0 = 0;
     uint32_t counter = 0;
     p.profile = pair ? reinterpret_cast<const int8_t *>(s.d_profq) : s.d_prof;
     p.prof_stride = pair ? profq_stride : prof8_stride;

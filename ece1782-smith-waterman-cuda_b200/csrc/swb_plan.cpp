@@ -141,7 +141,6 @@ void swb_plan_query(uint32_t qlen, int k_force, int k_max, uint32_t logg_present
 {
     qp.chunks.clear();
     qp.prof_rows = 0;
-    qp.k_pack = 0;
     const uint32_t nchunks = (qlen + chunk_rows - 1) / chunk_rows;
     // rows the dominant chunk has: all chunks but the last are chunk_rows long
     const uint32_t typical = nchunks > 1 ? chunk_rows : qlen;
@@ -162,7 +161,6 @@ void swb_plan_query(uint32_t qlen, int k_force, int k_max, uint32_t logg_present
             }
         }
         qp.k_by_logg[l] = best_k;
-        qp.k_pack |= (uint32_t)(best_k == 8 ? 0 : best_k == 16 ? 1 : 2) << (4 * l);
     }
     for (uint32_t c = 0; c < nchunks; ++c) {
         SwbQueryChunk ch;

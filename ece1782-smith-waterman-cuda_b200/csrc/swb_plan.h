@@ -49,7 +49,6 @@ struct SwbQueryChunk {
 };
 struct SwbQueryPlan {
     int k_by_logg[SWB_MAX_LOGG + 1];  // rows per lane (8, 16 or 32) for tiles of 1 << l lanes per pair
-    uint32_t k_pack;                  // the same, 4 bits per group size: K = 8 << nibble
     uint32_t prof_rows;               // rows the global profile must provide (rows beyond qlen score 0)
     std::vector<SwbQueryChunk> chunks;
 };

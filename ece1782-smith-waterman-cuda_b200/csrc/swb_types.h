@@ -33,7 +33,7 @@ struct SwbScoreParams {
     uint32_t ntiles;          // tiles covered by this launch (sum of its ranges)
     const uint8_t *residues;
     void *bnd;                // boundary scratch (uint32 per element for s16x2, 2x int32 for i32)
-    const int8_t *profile;    // global query profile [32][prof_stride], entry = S(q_row, code) + gap + t0
+    const int8_t *profile;    // global query profile [32][prof_stride], entry = S(q_row, code) + gap (one byte; query-pair launches: s16x2 word of both queries)
     uint32_t prof_stride;     // bytes per code row in global memory
     uint32_t row0;            // first query row of this launch (query chunk)
     uint32_t rows;            // query rows of this chunk that carry real residues or padding to use
@@ -48,7 +48,6 @@ struct SwbScoreParams {
     uint32_t *recount;        // i32 recompute: number of tiles re-scored (may be null)
     int32_t gap;
     int32_t ovf_thr;          // s16: best > ovf_thr  =>  recompute in int32
-    int32_t t0;               // profile entries are S + gap + t0 (always 0 at present)
     // tiles of this launch: positions [0, ntiles) of the concatenation of up to SWB_MAX_RANGES ranges of `tiles`
     uint32_t range_start[SWB_MAX_RANGES];
     uint32_t range_cum[SWB_MAX_RANGES];  // cumulative tile count up to and including range r

@@ -179,11 +179,11 @@ struct V16Q : V16Base {
 struct V32 {
     static const bool qpair = false;
     struct T { int a, b; };
-    struct C { int g, t0; };
+    struct C { int g; };
     static const bool is16 = false;
     static SWB_HD T mk(int a, int b) { T t; t.a = a; t.b = b; return t; }
     static SWB_HD int mx(int a, int b) { return a > b ? a : b; }
-    static SWB_HD C consts(const SwbScoreParams &p) { C c; c.g = p.gap; c.t0 = p.t0; return c; }
+    static SWB_HD C consts(const SwbScoreParams &p) { C c; c.g = p.gap; return c; }
     static SWB_HD T hzero(const C &) { return mk(0, 0); }
     static SWB_HD T lzero(const C &c) { return mk(-c.g, -c.g); }
     static SWB_HD int score_lo(T best, const C &) { return best.a; }
@@ -204,9 +204,9 @@ struct V32 {
             const uint32_t wb = rb[k4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                // profile entry = S + g + t0
-                const int sa = (int)(int8_t)(wa >> (8 * i)) - cst.t0;
-                const int sb = (int)(int8_t)(wb >> (8 * i)) - cst.t0;
+                // profile entry = S + g
+                const int sa = (int)(int8_t)(wa >> (8 * i));
+                const int sb = (int)(int8_t)(wb >> (8 * i));
                 const T l = left[4 * k4 + i];
                 const T c = mk(mx(mx(dg.a + sa, l.a), 0), mx(mx(dg.b + sb, l.b), 0));
                 dg = l;

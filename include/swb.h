@@ -18,6 +18,8 @@
  *   query upload to constQuery              SWSolver.cu:291-298  swb_search / swb_search_batch
  *   f_scoreSequenceTiledCoalesced launches  SWSolver.cu:201-264, 346, 379      "
  *   result gather                           SWSolver.cu:383-390  scores[] in database order
+ *   traceback of a pair (CPU solver)        cpu.cpp:39-108       swb_align (one hit of a scan, on the GPU)
+ *   text parsing of the database            FASTAParsers.h:73-136 swb_read_fasta / swb_dbfile_* (optional fast path)
  *
  * Plain pointers and sizes only; all buffers are caller-owned host memory unless stated otherwise.
  * Every function returns SWB_OK (0) or a negative error code; swb_last_error() gives the text.

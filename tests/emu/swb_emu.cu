@@ -297,7 +297,6 @@ extern "C" int swbemu_search(const uint8_t *codes, const uint64_t *offsets, uint
     p.recount = &recount;
     p.gap = gap;
     p.ovf_thr = ovf_thr_override >= 0 ? ovf_thr_override : 32767 - max_s;
-    p.t0 = 0;
 
     auto build_prof8 = [&](const uint8_t *qq, uint32_t ql, uint32_t prows, uint32_t stride, std::vector<uint8_t> &out) {
         out.assign((size_t)stride * SWB_ALPHA, 0);

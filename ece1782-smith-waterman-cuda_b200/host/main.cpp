@@ -51,9 +51,6 @@ static int match_option(const std::string &name)
 // inside a bucket, SWSolver.cu:383-390) and the METRICS block are recomputed from the stored offsets.
 static int scan_encoded_db(const std::string &querypath, const std::string &datapath, double time_start)
 {
-    if (datapath.size() > 6 && datapath.compare(datapath.size() - 6, 6, ".swbdb") == 0)
-        return scan_encoded_db(querypath, datapath, time_start);
-
     FASTAQuery query(querypath, true);
     cout << "Input buffer:";
     query.print_buffer();
@@ -128,6 +125,9 @@ int main(int argc, char *argv[])
         usage();
         return 1;
     }
+
+    if (datapath.size() > 6 && datapath.compare(datapath.size() - 6, 6, ".swbdb") == 0)
+        return scan_encoded_db(querypath, datapath, time_start);
 
     FASTAQuery query(querypath, true);
     cout << "Input buffer:";

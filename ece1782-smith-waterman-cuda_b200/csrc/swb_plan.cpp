@@ -155,8 +155,11 @@ void swb_plan_query(uint32_t qlen, int k_force, int k_max, uint32_t logg_present
             for (int K = std::min(32, k_max); K >= 8; K >>= 1) {
                 // a chunk boundary must be a pass boundary of every group size
                 if (nchunks > 1 && chunk_rows % ((uint32_t)K << l)) continue;
-                // padded rows x per-column overhead of a short strip (shuffles, address math, boundary I/O)
-                const double cost = (double)swb_roundup(typical, (uint32_t)K << l) * (1.0 + 4.0 / K);
+                // padded rows x relative cost of a padded cell with K rows per lane, measured on B200 with all group
+                // sizes forced to one K (9024 / 7655 / 5228 GCUPS for K = 32 / 16 / 8): short strips pay the per-column
+                // work (residue fetch, shuffles, boundary I/O, loop control) over fewer cells
+                const double per_cell = K >= 32 ? 1.0 : (K == 16 ? 1.18 : 1.73);
+                const double cost = (double)swb_roundup(typical, (uint32_t)K << l) * per_cell;
                 if (!have || cost < best) { best = cost; best_k = K; have = true; }
             }
         }

@@ -176,9 +176,12 @@ template <int K, class V, bool SPLIT>
 static cudaError_t dispatch_cfg(int op, int block_cfg, const SwbScoreParams *p, int grid, size_t smem, cudaStream_t st,
                                 int *blocks)
 {
+    // short strips (K = 8) have less work per column to hide latency with: cap their registers so that three blocks
+    // (24 warps) fit on an SM instead of two
+    constexpr int kMinBlocks = (K == 8 && V::is16) ? 3 : SWB_MINB_SMALL;
     if (block_cfg == SWB_BLOCK_SMALL)
-        return op == 0 ? launch_one<K, V, SWB_NT_SMALL, SWB_MINB_SMALL, SPLIT>(*p, grid, smem, st)
-                       : occ_one<K, V, SWB_NT_SMALL, SWB_MINB_SMALL, SPLIT>(smem, blocks);
+        return op == 0 ? launch_one<K, V, SWB_NT_SMALL, kMinBlocks, SPLIT>(*p, grid, smem, st)
+                       : occ_one<K, V, SWB_NT_SMALL, kMinBlocks, SPLIT>(smem, blocks);
     return op == 0 ? launch_one<K, V, SWB_NT_LARGE, 1, SPLIT>(*p, grid, smem, st)
                    : occ_one<K, V, SWB_NT_LARGE, 1, SPLIT>(smem, blocks);
 }

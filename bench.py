@@ -394,7 +394,7 @@ def main():
                 "roofline": roofline, "engine": {k: st[k] for k in ("tiles", "tiles_by_group", "last_k",
                                                                     "recomputed_tiles", "sm_count")},
                 "topk_merge_ok": top_ok, "config5_sample_parity_ok": sample_ok}
-        if not args.no_cpu:
+        if not args.no_cpu and world == 1:  # the CPU baseline is reported at N = 1 only
             names_t, qtexts = load_queries(None)
             line["cpu_baseline"], _ = cpu_sample_gcups(codes, offsets, names_t, qtexts, args.cpu_seconds)
         else:

@@ -13,7 +13,7 @@ namespace {
 struct SolverState {
     swb_engine *engine = nullptr;
     const FASTADatabase *db = nullptr;
-    long long fingerprint = -1;
+    unsigned long long fingerprint = 0;
     std::vector<int> ids;  // ids in the reference's result order
     ~SolverState()
     {
@@ -42,7 +42,22 @@ void smith_waterman_cuda(FASTAQuery &query, FASTADatabase &db, std::vector<seqid
         if (rc != SWB_OK) throw std::runtime_error(std::string("swb_create: ") + swb_last_error(nullptr));
         check(swb_set_scoring_preset(st.engine, SWB_SCORING_BLOSUM50_REF), st.engine, "swb_set_scoring_preset");
     }
-    const long long fp = db.subjectLengthSum64 * 1000003ll + db.numSubjects64;
+    // content fingerprint (ids, lengths and the ends of every sequence): a different database at the same address
+    // must not hit the cache
+    unsigned long long fp = 1469598103934665603ull;
+    {
+        auto mix = [&fp](unsigned long long v) { fp = (fp ^ v) * 1099511628211ull; };
+        mix((unsigned long long)db.numSubjects64);
+        mix((unsigned long long)db.subjectLengthSum64);
+        for (map<int, vector<subject_sequence> >::const_iterator it = db.parsedDB.begin(); it != db.parsedDB.end(); ++it)
+            for (size_t i = 0; i < it->second.size(); ++i) {
+                const string &q = it->second[i].sequence;
+                mix((unsigned long long)(unsigned)it->second[i].id);
+                mix(q.size());
+                for (size_t k = 0; k < q.size() && k < 12; ++k) mix((unsigned char)q[k]);
+                for (size_t k = q.size() > 12 ? q.size() - 12 : 0; k < q.size(); ++k) mix((unsigned char)q[k]);
+            }
+    }
     if (st.db != &db || st.fingerprint != fp) {
         // database in the order the reference reports results: parsedDB.rbegin() .. rend() (SWSolver.cu:383-390)
         std::vector<uint8_t> codes;

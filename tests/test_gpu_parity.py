@@ -437,3 +437,20 @@ def test_cli_encoded_database_matches_text_database(swb, tmp_path):
         r = subprocess.run([main, "--query", q, "--db", db], capture_output=True, text=True, timeout=300)
         outs.append([l for l in r.stdout.split("\n") if not l.startswith(("Time elapsed", "Performance"))])
     assert outs[0] == outs[1] and outs[0][2].startswith("-1:")
+
+
+def test_cpp_shim_two_databases_in_one_process(swb, subset, tmp_path):
+    """the C++ drop-in caches the packed database per FASTADatabase content: alternating between two databases (the
+    second = the first with its records reversed) must give each its own scores"""
+    pkg = os.path.join(ROOT, "ece1782-smith-waterman-cuda_b200")
+    rev = str(tmp_path / "reversed.fasta")
+    with open(rev, "w") as f:
+        for k in range(len(subset["seqs"]) - 1, -1, -1):
+            f.write(">r%d\n%s\n" % (k, subset["seqs"][k]))
+    exe = str(tmp_path / "two_dbs")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-I" + os.path.join(ROOT, "include"), "-o", exe,
+                    os.path.join(ROOT, "tests", "cpp", "two_databases.cpp"), os.path.join(pkg, "lib", "SWSolver.o"),
+                    "-L" + os.path.join(pkg, "lib"), "-lswb", "-Wl,-rpath," + os.path.join(pkg, "lib")], check=True)
+    r = subprocess.run([exe, os.path.join(GOLDEN, "queries", "P01008.fasta"), os.path.join(GOLDEN, "uniprot_subset.fasta"),
+                        rev, os.path.join(GOLDEN, "P01008.head111.txt")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "mismatches 0" in r.stdout, r.stdout + r.stderr

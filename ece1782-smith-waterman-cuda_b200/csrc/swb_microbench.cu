@@ -1,11 +1,21 @@
 // Measurement support: issue-rate micro-benchmarks of the integer SIMD instructions the score kernel is
 // made of. bench.py uses the "mix" figure as the denominator of the integer-pipe roofline (SURVEY 8(d):
 // MEASURED_PEAKS.json only has HBM and bf16 numbers). Not part of the scoring path.
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "../../include/swb.h"
 
 #define MB_CHAINS 8
+
+// max of two s16x2 words through the fp16x2 comparator: exact for non-negative halves below 0x7C00 (31744), whose bit
+// patterns order like the integers
+__device__ __forceinline__ uint32_t swb_hmax2_bits(uint32_t a, uint32_t b)
+{
+    __half2 x = *reinterpret_cast<__half2 *>(&a), y = *reinterpret_cast<__half2 *>(&b);
+    __half2 r = __hmax2(x, y);
+    return *reinterpret_cast<uint32_t *>(&r);
+}
 
 template <int KIND>
 __global__ void __launch_bounds__(256) swb_mb_kernel(uint32_t *out, uint32_t seed, int iters)
@@ -35,6 +45,11 @@ __global__ void __launch_bounds__(256) swb_mb_kernel(uint32_t *out, uint32_t see
             }
             if (KIND == 6) x[c] = x[c] * one + b;  // IMAD alone
             if (KIND == 7) x[c] = max(x[c] + b, a);  // scalar add+max (what the compiler makes of int32 cells)
+            if (KIND == 9) x[c] = swb_hmax2_bits(x[c] & 0x3fff3fffu, b & 0x3fff3fffu);  // HMNMX2 (+ LOP3)
+            if (KIND == 10) {  // does HMNMX2 issue beside the DPX op?
+                x[c] = __viaddmax_s16x2_relu(x[c], b, a);
+                x[c] = swb_hmax2_bits(x[c], a);
+            }
             if (KIND == 8) {  // the biased policy's mix: prmt, vimax3, viaddmax, 1/2 vimax3 (ALU) + 3 imad (FMA)
                 uint32_t s, ds, l3;
                 asm volatile("prmt.b32 %0, %1, %2, 0xD591;" : "=r"(s) : "r"(x[c]), "r"(b));
@@ -53,14 +68,14 @@ __global__ void __launch_bounds__(256) swb_mb_kernel(uint32_t *out, uint32_t see
     if (r == 0x12345678u) out[0] = r;
 }
 
-static const double kInstrPerIter[9] = {MB_CHAINS, MB_CHAINS, MB_CHAINS, MB_CHAINS, MB_CHAINS * 4.5, MB_CHAINS * 2.0,
-                                        MB_CHAINS, MB_CHAINS, MB_CHAINS * 6.5};
+static const double kInstrPerIter[11] = {MB_CHAINS, MB_CHAINS, MB_CHAINS, MB_CHAINS, MB_CHAINS * 4.5, MB_CHAINS * 2.0,
+                                         MB_CHAINS, MB_CHAINS, MB_CHAINS * 6.5, MB_CHAINS * 3.0, MB_CHAINS * 2.0};
 
 // kind 0 viaddmax.relu, 1 vimax3, 2 vadd2, 3 prmt, 4 V16 mix, 5 viaddmax+imad, 6 imad, 7 scalar add/max, 8 V16B mix.
 // Returns giga lane-instructions per second (warp instructions x 32) over the whole GPU.
 extern "C" int swb_microbench(int device, int kind, double *glane_instr_per_s, double *ms_out)
 {
-    if (kind < 0 || kind > 8 || !glane_instr_per_s) return SWB_ERR_ARG;
+    if (kind < 0 || kind > 10 || !glane_instr_per_s) return SWB_ERR_ARG;
     if (cudaSetDevice(device) != cudaSuccess) return SWB_ERR_CUDA;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return SWB_ERR_CUDA;
@@ -82,7 +97,9 @@ extern "C" int swb_microbench(int device, int kind, double *glane_instr_per_s, d
         case 5: swb_mb_kernel<5><<<grid, block>>>(d, 7u + rep, iters); break;
         case 6: swb_mb_kernel<6><<<grid, block>>>(d, 7u + rep, iters); break;
         case 7: swb_mb_kernel<7><<<grid, block>>>(d, 7u + rep, iters); break;
-        default: swb_mb_kernel<8><<<grid, block>>>(d, 7u + rep, iters); break;
+        case 8: swb_mb_kernel<8><<<grid, block>>>(d, 7u + rep, iters); break;
+        case 9: swb_mb_kernel<9><<<grid, block>>>(d, 7u + rep, iters); break;
+        default: swb_mb_kernel<10><<<grid, block>>>(d, 7u + rep, iters); break;
         }
         cudaEventRecord(e1);
         if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(d); return SWB_ERR_CUDA; }

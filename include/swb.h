@@ -152,7 +152,8 @@ void swb_dbfile_close(swb_dbfile *d);
 /* ---- measurement support (not on the scoring path) ------------------------------------------- */
 /* Issue rate of the integer SIMD instructions the score kernel is built from, whole GPU, in giga
  * lane-instructions/s. kind: 0 viaddmax.s16x2.relu, 1 vimax3.s16x2, 2 vadd2, 3 prmt, 4 the score kernel's per-cell
- * mix, 5 viaddmax+imad, 6 imad, 7 scalar add+max, 8 the mix of the (rejected) biased FMA-pipe variant. bench.py
+ * mix, 5 viaddmax+imad, 6 imad, 7 scalar add+max, 8 the mix of the (rejected) biased FMA-pipe variant, 9 hmnmx2 (+ a
+ * mask), 10 viaddmax+hmnmx2 (18.3 T: the fp16 comparator shares the ALU pipe, so it cannot take over the max). bench.py
  * uses kind 4 (4.5 instructions per cell pair) as the roofline peak of the score kernel. */
 int swb_microbench(int device, int kind, double *glane_instr_per_s, double *ms);
 

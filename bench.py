@@ -194,6 +194,13 @@ def run_reference(args):
 
 
 def workload_config(offsets, qs, args):
+    cfg = _workload_config(offsets, qs, args)
+    if getattr(args, "affine", ""):
+        cfg["scoring"] = "BLOSUM50 ('*' zeroed), affine gaps open,extend = %s (side measurement)" % args.affine
+    return cfg
+
+
+def _workload_config(offsets, qs, args):
     if getattr(args, "workload", "config2") == "config5":
         return {"workload": "configs[4]: 1,000 synthetic queries x UniProt-scale synthetic DB (10 Swiss-Prot-shaped parts)",
                 "db_sequences": int(len(offsets) - 1), "db_residues": int(offsets[-1]), "queries": len(qs),
@@ -223,6 +230,8 @@ def main():
     ap.add_argument("--split", type=int, default=-1, help="pipelined passes for very long tiles: 1 on, 0 off (default)")
     ap.add_argument("--pair-queries", type=int, default=-1, help="pack two queries of a batch per lane: 1 (default), 0")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--affine", default="", help="GO,GE: affine gaps instead of the reference's linear gap 2 (a side "
+                    "measurement of the V16A kernels; not the headline metric, no CPU leg)")
     ap.add_argument("--per-query", action="store_true", help="also print device GCUPS per query")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -267,6 +276,10 @@ def main():
     stream = torch.cuda.current_stream()
     eng.set_stream(stream.cuda_stream)
     eng.db_load(codes, offsets, rank, world)
+    if args.affine:
+        go, ge = (int(x) for x in args.affine.split(","))
+        eng.set_scoring_affine(swb.scoring_matrix(swb.SWB_SCORING_BLOSUM50_REF)[0], go, ge)
+        args.no_cpu = True
     nloc = eng.db_count()
 
     def barrier():

@@ -69,7 +69,7 @@ class SwbPlanInfo(ctypes.Structure):
 # every symbol include/swb.h declares (tests check the library exports exactly these)
 ABI_SYMBOLS = [
     "swb_create", "swb_destroy", "swb_last_error", "swb_set_option", "swb_set_stream", "swb_set_scoring",
-    "swb_set_scoring_preset", "swb_scoring_matrix", "swb_encode", "swb_db_load", "swb_db_count", "swb_db_ids",
+    "swb_set_scoring_preset", "swb_set_scoring_affine", "swb_scoring_matrix", "swb_encode", "swb_db_load", "swb_db_count", "swb_db_ids",
     "swb_search", "swb_search_batch", "swb_fetch_scores", "swb_topk", "swb_stats", "swb_plan_describe",
     "swb_microbench", "swb_align", "swb_read_fasta", "swb_read_uniprot_dat", "swb_free", "swb_dbfile_write",
     "swb_dbfile_open", "swb_dbfile_count", "swb_dbfile_first_id", "swb_dbfile_offsets", "swb_dbfile_codes",
@@ -109,6 +109,8 @@ def lib():
     L.swb_set_stream.argtypes = [vp, vp]
     L.swb_set_scoring.restype = ctypes.c_int
     L.swb_set_scoring.argtypes = [vp, _i8p, ctypes.c_int, ctypes.c_int]
+    L.swb_set_scoring_affine.restype = ctypes.c_int
+    L.swb_set_scoring_affine.argtypes = [vp, _i8p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
     L.swb_set_scoring_preset.restype = ctypes.c_int
     L.swb_set_scoring_preset.argtypes = [vp, ctypes.c_int]
     L.swb_scoring_matrix.restype = ctypes.c_int
@@ -327,6 +329,13 @@ class Engine:
         m = np.ascontiguousarray(matrix, dtype=np.int8)
         assert m.ndim == 2 and m.shape[0] == m.shape[1]
         self._check(self._L.swb_set_scoring(self._h, m.ctypes.data_as(_i8p), m.shape[0], gap), "swb_set_scoring")
+
+    def set_scoring_affine(self, matrix, gap_open, gap_extend):
+        """Gotoh gaps: a gap of length L costs gap_open + (L-1)*gap_extend (gap_open == gap_extend: linear)."""
+        m = np.ascontiguousarray(matrix, dtype=np.int8)
+        assert m.ndim == 2 and m.shape[0] == m.shape[1]
+        self._check(self._L.swb_set_scoring_affine(self._h, m.ctypes.data_as(_i8p), m.shape[0], gap_open, gap_extend),
+                    "swb_set_scoring_affine")
 
     def set_scoring_preset(self, preset):
         self._check(self._L.swb_set_scoring_preset(self._h, preset), "swb_set_scoring_preset")

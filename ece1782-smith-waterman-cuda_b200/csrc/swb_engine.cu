@@ -74,7 +74,9 @@ struct swb_engine {
     cudaEvent_t ev_join[SWB_MAX_SLOTS] = {};
     // scoring
     int8_t h_mat[SWB_ALPHA * SWB_ALPHA];
-    int gap = 2;
+    int gap = 2;          // linear gap penalty (affine: the gap-open penalty)
+    int gap_extend = 2;   // == gap for the linear model
+    bool affine = false;  // gap_extend != gap: Gotoh recurrences (V16A / V32A policies)
     int max_s = 0;
     int min_s = 0;
     bool scoring_set = false;
@@ -328,9 +330,17 @@ extern "C" int swb_set_stream(swb_engine *e, void *cuda_stream)
 
 extern "C" int swb_set_scoring(swb_engine *e, const int8_t *matrix, int alpha, int gap)
 {
+    return swb_set_scoring_affine(e, matrix, alpha, gap, gap);
+}
+
+// gap_open: penalty of the first residue of a gap, gap_extend: of every further one (a gap of length L costs
+// gap_open + (L-1) * gap_extend). gap_open == gap_extend is the reference's linear model and runs the linear kernels.
+extern "C" int swb_set_scoring_affine(swb_engine *e, const int8_t *matrix, int alpha, int gap, int gap_extend)
+{
     if (!e || !matrix) return SWB_ERR_ARG;
     if (alpha < 1 || alpha > SWB_ALPHA) return fail(e, SWB_ERR_ARG, "alpha must be 1..32");
     if (gap < 0 || gap > 64) return fail(e, SWB_ERR_ARG, "gap must be 0..64");
+    if (gap_extend < 0 || gap_extend > gap) return fail(e, SWB_ERR_ARG, "gap_extend must be 0..gap_open");
     int8_t m[SWB_ALPHA * SWB_ALPHA];
     memset(m, 0, sizeof m);
     int mx = 0, mn = 0;
@@ -347,6 +357,8 @@ extern "C" int swb_set_scoring(swb_engine *e, const int8_t *matrix, int alpha, i
     CU(cudaStreamSynchronize(main_stream(e)));
     memcpy(e->h_mat, m, sizeof m);
     e->gap = gap;
+    e->gap_extend = gap_extend;
+    e->affine = gap_extend != gap;
     e->max_s = mx;
     e->min_s = mn;
     CU(cudaMemcpy(e->d_mat, e->h_mat, sizeof m, cudaMemcpyHostToDevice));
@@ -620,13 +632,16 @@ static int enqueue_job(swb_engine *e, Slot &s, uint32_t qi, const uint8_t *q, ui
     for (int l = 0; l <= SWB_MAX_LOGG; ++l)
         if (pl.tiles_by_logg[l]) present |= 1u << l;
     const bool longest_first = e->opt_group_order == 1 || (e->opt_group_order == 0 && e->cur_nq <= 1);
-    const int mode0 = pair ? SWB_MODE_QPAIR : SWB_MODE_S16;
+    const bool affine = e->affine;  // never paired (swb_search_batch), never split
+    const int mode0 = affine ? SWB_MODE_S16A : (pair ? SWB_MODE_QPAIR : SWB_MODE_S16);
+    const int mode1 = affine ? SWB_MODE_I32A : SWB_MODE_I32;
 
     // pass 0: the s16 pass over all tiles
     SwbQueryPlan qp0;
     std::vector<SwbLaunchGroup> g0;
-    swb_plan_query(rows, e->opt_k, 32, present, pair ? SWB_CHUNK_ROWS_QPAIR : e->chunk_rows, qp0);
-    swb_plan_launch_groups(pl, qp0, longest_first, !pair && e->opt_split != 0, g0);
+    // affine lanes carry (H, E) per row, so their strips stop at 16 rows (s16) / 8 rows (int32)
+    swb_plan_query(rows, e->opt_k, affine ? 16 : 32, present, pair ? SWB_CHUNK_ROWS_QPAIR : e->chunk_rows, qp0);
+    swb_plan_launch_groups(pl, qp0, longest_first, !pair && !affine && e->opt_split != 0, g0);
     // int32 passes over flagged tiles, one per query, only when a score can exceed the s16 range at all
     const uint32_t qlens[2] = {qlen, pair ? qlen2 : 0u};
     bool need_i32[2];
@@ -637,7 +652,7 @@ static int enqueue_job(swb_engine *e, Slot &s, uint32_t qi, const uint8_t *q, ui
     for (int k = 0; k < 2; ++k) {
         need_i32[k] = qlens[k] > 0 && (int64_t)e->max_s * std::min<uint32_t>(qlens[k], pl.max_len) > ovf_thr;
         if (!need_i32[k]) continue;
-        swb_plan_query(qlens[k], e->opt_k, 16, present, e->chunk_rows, qp1[k]);
+        swb_plan_query(qlens[k], e->opt_k, affine ? 8 : 16, present, e->chunk_rows, qp1[k]);
         swb_plan_launch_groups(pl, qp1[k], longest_first, false, g1[k]);
         nlaunch += g1[k].size() * qp1[k].chunks.size();
         prof8_rows = std::max(prof8_rows, qp1[k].prof_rows);
@@ -664,7 +679,9 @@ static int enqueue_job(swb_engine *e, Slot &s, uint32_t qi, const uint8_t *q, ui
         CU(GROW_DEV(s.d_profq, s.profq_cap, sizeof(uint32_t) * (size_t)profq_stride * SWB_ALPHA));
         CU(GROW_DEV(s.d_bnd16, s.bnd16_cap, 2 * sizeof(uint32_t) * pl.bnd_elems));  // two work items per tile
     }
-    if (need_i32[0] || need_i32[1]) CU(GROW_DEV(s.d_bnd32, s.bnd32_cap, 8ull * pl.bnd_elems));
+    // boundary elements: 4 B (V16), 8 B (V32, V16A: H and F), 16 B (V32A)
+    if (affine) CU(GROW_DEV(s.d_bnd16, s.bnd16_cap, 8ull * pl.bnd_elems));
+    if (need_i32[0] || need_i32[1]) CU(GROW_DEV(s.d_bnd32, s.bnd32_cap, (affine ? 16ull : 8ull) * pl.bnd_elems));
     // progress counters of the split group: one per (very long tile, pass) and chunk
     size_t prog_words = 0;
     if (!g0.empty() && g0[0].split)
@@ -691,6 +708,8 @@ static int enqueue_job(swb_engine *e, Slot &s, uint32_t qi, const uint8_t *q, ui
     p.flags = s.d_flags;
     p.recount = s.d_recount;
     p.gap = e->gap;
+    p.gap_open = e->gap;
+    p.gap_extend = e->gap_extend;
     p.ovf_thr = ovf_thr;
     uint32_t counter = 0;
     p.profile = pair ? reinterpret_cast<const int8_t *>(s.d_profq) : s.d_prof;
@@ -713,7 +732,7 @@ static int enqueue_job(swb_engine *e, Slot &s, uint32_t qi, const uint8_t *q, ui
         p.scores2 = nullptr;
         p.bnd = s.d_bnd32;
         p.only_flagged = 1;
-        if ((rc = enqueue_pass(e, s, SWB_MODE_I32, p, qp1[k], g1[k], counter)) != SWB_OK) return rc;
+        if ((rc = enqueue_pass(e, s, mode1, p, qp1[k], g1[k], counter)) != SWB_OK) return rc;
     }
     CU(swb_launch_scatter(s.d_sorted, e->d_out_pos, nl, out, s.stream));
     if (pair) CU(swb_launch_scatter(s.d_sorted2, e->d_out_pos, nl, out2, s.stream));
@@ -766,7 +785,7 @@ extern "C" int swb_search_batch(swb_engine *e, const uint8_t *qcodes, const uint
     // shorter one pays for the rows of the longer one); a query left over, or every query without packing, runs alone
     std::vector<uint32_t> order(nq);
     for (uint32_t i = 0; i < nq; ++i) order[i] = i;
-    const bool pairing = e->opt_pair_queries && nq >= 2;
+    const bool pairing = e->opt_pair_queries && nq >= 2 && !e->affine;
     if (pairing)
         std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
             return qoffsets[a + 1] - qoffsets[a] > qoffsets[b + 1] - qoffsets[b];
@@ -847,6 +866,7 @@ extern "C" int swb_align(swb_engine *e, const uint8_t *query, uint32_t qlen, uin
 {
     if (!e || (!query && qlen) || !score) return SWB_ERR_ARG;
     if (!e->db_loaded) return fail(e, SWB_ERR_STATE, "swb_align before swb_db_load");
+    if (e->affine) return fail(e, SWB_ERR_STATE, "swb_align implements the linear gap model only");
     const SwbPlan &pl = e->plan;
     const std::vector<uint32_t>::const_iterator it = std::lower_bound(pl.shard_ids.begin(), pl.shard_ids.end(), db_id);
     if (it == pl.shard_ids.end() || *it != db_id) return fail(e, SWB_ERR_ARG, "db_id is not part of this shard");

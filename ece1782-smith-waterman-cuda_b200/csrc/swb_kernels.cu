@@ -190,6 +190,18 @@ static cudaError_t dispatch(int op, int K, int mode, bool split, int block_cfg, 
                             size_t smem, cudaStream_t st, int *blocks)
 {
     const bool i32 = mode == SWB_MODE_I32;
+    if (mode == SWB_MODE_S16A || mode == SWB_MODE_I32A) {  // affine gaps: twice the row state, so shorter strips
+        if (split) return cudaErrorInvalidValue;
+        if (mode == SWB_MODE_S16A) {
+            switch (K) {
+            case 8: return dispatch_cfg<8, V16A, false>(op, block_cfg, p, grid, smem, st, blocks);
+            case 16: return dispatch_cfg<16, V16A, false>(op, block_cfg, p, grid, smem, st, blocks);
+            }
+        } else if (K == 8) {
+            return dispatch_cfg<8, V32A, false>(op, block_cfg, p, grid, smem, st, blocks);
+        }
+        return cudaErrorInvalidValue;
+    }
     if (mode == SWB_MODE_QPAIR) {
         if (split) return cudaErrorInvalidValue;
         switch (K) {

@@ -15,6 +15,8 @@
 #define SWB_MODE_S16 0    // V16: two DB sequences per lane, one query
 #define SWB_MODE_I32 1    // V32: exact recompute of flagged tiles
 #define SWB_MODE_QPAIR 2  // V16Q: one DB sequence per lane, two queries (batches)
+#define SWB_MODE_S16A 3   // V16A: affine gaps, s16x2 (K = 8, 16)
+#define SWB_MODE_I32A 4   // V32A: affine gaps, exact recompute (K = 8)
 
 // K: query rows per lane (8, 16, 32; int32 pass 8 or 16). split: the passes of a tile are separate, pipelined work
 // items (very long sequences; SWB_MODE_S16, K = 8 only).

@@ -46,7 +46,9 @@ struct SwbScoreParams {
     uint8_t *flags;           // per tile: s16 kernel sets 1 when a score may have wrapped
     uint32_t only_flagged;    // i32 recompute: skip tiles whose flag is 0
     uint32_t *recount;        // i32 recompute: number of tiles re-scored (may be null)
-    int32_t gap;
+    int32_t gap;              // linear policies: gap penalty
+    int32_t gap_open;         // affine policies: first residue of a gap
+    int32_t gap_extend;       // affine policies: every further residue
     int32_t ovf_thr;          // s16: best > ovf_thr  =>  recompute in int32
     // tiles of this launch: positions [0, ntiles) of the concatenation of up to SWB_MAX_RANGES ranges of `tiles`
     uint32_t range_start[SWB_MAX_RANGES];

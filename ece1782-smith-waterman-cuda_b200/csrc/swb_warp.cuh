@@ -13,6 +13,7 @@
 //   V16Q  the halves are two QUERIES against one DB sequence (batches): the packed score is one profile word, no prmt:
 //         3.5 ALU-pipe instructions per cell pair
 //   V32   two int32 lanes; exact for any score; used to re-score tiles flagged by the s16 passes.
+//   V16A / V32A  the affine-gap versions of V16 / V32 (two values per element: H and F along the chain, H and E per row)
 // (A third policy that moved the additions to the FMA pipe as IMADs in a biased domain was measured
 //  slower on B200 -- register-file operand bandwidth, see DESIGN.md -- and was removed.)
 //
@@ -245,6 +246,178 @@ struct V32 {
     {
         be.st_cg4(reinterpret_cast<uint4 *>(p), make_uint4(o[0].a, o[0].b, o[1].a, o[1].b));
         be.st_cg4(reinterpret_cast<uint4 *>(p) + 1, make_uint4(o[2].a, o[2].b, o[3].a, o[3].b));
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Affine gaps (Gotoh; SURVEY 8f rank 4, hinted at by the reference's "define affine penalty ?", SWSolver.cu:8):
+//     E(i,j) = max(E(i,j-1) - ge, H(i,j-1) - go)      F(i,j) = max(F(i-1,j) - ge, H(i-1,j) - go)
+//     H(i,j) = max(0, H(i-1,j-1) + S, E(i,j), F(i,j))           a gap of length L costs go + (L-1) * ge
+// The element type carries two values: along the chain and across lanes / passes (h = H, f = F); per row, kept from
+// the previous column (h = H - go, f = E). Profile entry: S + go. With go == ge this is the linear recurrence.
+// V16A: two DB sequences per word (s16x2, 6.5 ALU-pipe instructions per cell pair); V32A: exact int32 recompute.
+struct V16A {
+    static const bool qpair = false;
+    static const bool is16 = true;
+    struct T { uint32_t h, f; };
+    struct C { uint32_t neg_go, neg_ge; };
+    static SWB_HD T mk(uint32_t h, uint32_t f) { T t; t.h = h; t.f = f; return t; }
+    static SWB_HD C consts(const SwbScoreParams &p)
+    {
+        C c;
+        c.neg_go = V16Base::splat(-p.gap_open);
+        c.neg_ge = V16Base::splat(-p.gap_extend);
+        return c;
+    }
+    static SWB_HD T hzero(const C &c) { return mk(0u, c.neg_go); }       // H = 0, F = "none" (anything <= -go)
+    static SWB_HD T lzero(const C &c) { return mk(c.neg_go, c.neg_go); }  // H - go with H = 0, E = "none"
+    static SWB_HD int score_lo(T best, const C &) { return V16Base::lo(best.h); }
+    static SWB_HD int score_hi(T best, const C &) { return V16Base::hi(best.h); }
+    static SWB_HD T max2(T a, T b) { return mk(V16Base::max2(a.h, b.h), a.f); }
+    template <int K>
+    static SWB_HD T column(T up, T &diag0, T (&left)[K], T &best, const C &cst, uint32_t codeA, uint32_t codeB,
+                           const int8_t *prow, uint32_t sstride)
+    {
+        const uint32_t *ra = reinterpret_cast<const uint32_t *>(prow + codeA * sstride);
+        const uint32_t *rb = reinterpret_cast<const uint32_t *>(prow + codeB * sstride);
+        uint32_t hgo = V16::add(up.h, cst.neg_go);  // H(row above, j) - go
+        uint32_t f = up.f;
+        uint32_t dgo = diag0.h;
+        uint32_t h = up.h;
+        diag0.h = hgo;
+#pragma unroll
+        for (int k4 = 0; k4 < K / 4; ++k4) {
+            const uint32_t wa = ra[k4];
+            const uint32_t wb = rb[k4];
+            uint32_t hh[4];
+#define SWB_CELL(I)                                                                          \
+    {                                                                                        \
+        const uint32_t s = V16Base::pair<I>(wa, wb);                                         \
+        const uint32_t e = __viaddmax_s16x2(left[4 * k4 + I].f, cst.neg_ge, left[4 * k4 + I].h); \
+        f = __viaddmax_s16x2(f, cst.neg_ge, hgo);                                            \
+        h = __viaddmax_s16x2_relu(dgo, s, V16Base::max2(e, f));                              \
+        dgo = left[4 * k4 + I].h;                                                            \
+        hgo = V16::add(h, cst.neg_go);                                                       \
+        left[4 * k4 + I].h = hgo;                                                            \
+        left[4 * k4 + I].f = e;                                                              \
+        hh[I] = h;                                                                           \
+    }
+            SWB_CELL(0) SWB_CELL(1)
+            best.h = __vimax3_s16x2(best.h, hh[0], hh[1]);
+            SWB_CELL(2) SWB_CELL(3)
+            best.h = __vimax3_s16x2(best.h, hh[2], hh[3]);
+#undef SWB_CELL
+        }
+        return mk(h, f);
+    }
+    template <class BE> static SWB_HD T shfl_up(BE &be, T v, int d, int w)
+    {
+        return mk(be.shfl_up(v.h, d, w), be.shfl_up(v.f, d, w));
+    }
+    template <class BE> static SWB_HD T shfl_xor(BE &be, T v, int m, int w)
+    {
+        return mk(be.shfl_xor(v.h, m, w), be.shfl_xor(v.f, m, w));
+    }
+    template <class BE> static SWB_HD T ld(BE &be, const T *p)
+    {
+        uint2 v = be.ld_cg2(reinterpret_cast<const uint2 *>(p));
+        return mk(v.x, v.y);
+    }
+    template <class BE> static SWB_HD void st(BE &be, T *p, T v)
+    {
+        be.st_cg2(reinterpret_cast<uint2 *>(p), make_uint2(v.h, v.f));
+    }
+    template <class BE> static SWB_HD void ld4(BE &be, const T *p, T *o)
+    {
+        uint4 v = be.ld_cg4(reinterpret_cast<const uint4 *>(p));
+        uint4 w = be.ld_cg4(reinterpret_cast<const uint4 *>(p) + 1);
+        o[0] = mk(v.x, v.y); o[1] = mk(v.z, v.w);
+        o[2] = mk(w.x, w.y); o[3] = mk(w.z, w.w);
+    }
+    template <class BE> static SWB_HD void st4(BE &be, T *p, const T *o)
+    {
+        be.st_cg4(reinterpret_cast<uint4 *>(p), make_uint4(o[0].h, o[0].f, o[1].h, o[1].f));
+        be.st_cg4(reinterpret_cast<uint4 *>(p) + 1, make_uint4(o[2].h, o[2].f, o[3].h, o[3].f));
+    }
+};
+
+struct V32A {
+    static const bool qpair = false;
+    static const bool is16 = false;
+    struct T { int ha, hb, fa, fb; };
+    struct C { int go, ge; };
+    static SWB_HD T mk(int ha, int hb, int fa, int fb) { T t; t.ha = ha; t.hb = hb; t.fa = fa; t.fb = fb; return t; }
+    static SWB_HD int mx(int a, int b) { return a > b ? a : b; }
+    static SWB_HD C consts(const SwbScoreParams &p) { C c; c.go = p.gap_open; c.ge = p.gap_extend; return c; }
+    static SWB_HD T hzero(const C &c) { return mk(0, 0, -c.go, -c.go); }
+    static SWB_HD T lzero(const C &c) { return mk(-c.go, -c.go, -c.go, -c.go); }
+    static SWB_HD int score_lo(T best, const C &) { return best.ha; }
+    static SWB_HD int score_hi(T best, const C &) { return best.hb; }
+    static SWB_HD T max2(T a, T b) { return mk(mx(a.ha, b.ha), mx(a.hb, b.hb), a.fa, a.fb); }
+    template <int K>
+    static SWB_HD T column(T up, T &diag0, T (&left)[K], T &best, const C &cst, uint32_t codeA, uint32_t codeB,
+                           const int8_t *prow, uint32_t sstride)
+    {
+        const uint32_t *ra = reinterpret_cast<const uint32_t *>(prow + codeA * sstride);
+        const uint32_t *rb = reinterpret_cast<const uint32_t *>(prow + codeB * sstride);
+        int hgoa = up.ha - cst.go, hgob = up.hb - cst.go;
+        int fa = up.fa, fb = up.fb;
+        int dgoa = diag0.ha, dgob = diag0.hb;
+        int ha = up.ha, hb = up.hb;
+        diag0.ha = hgoa;
+        diag0.hb = hgob;
+#pragma unroll
+        for (int k4 = 0; k4 < K / 4; ++k4) {
+            const uint32_t wa = ra[k4];
+            const uint32_t wb = rb[k4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                T &l = left[4 * k4 + i];
+                const int sa = (int)(int8_t)(wa >> (8 * i));  // S + go
+                const int sb = (int)(int8_t)(wb >> (8 * i));
+                const int ea = mx(l.fa - cst.ge, l.ha), eb = mx(l.fb - cst.ge, l.hb);
+                fa = mx(fa - cst.ge, hgoa);
+                fb = mx(fb - cst.ge, hgob);
+                ha = mx(mx(dgoa + sa, mx(ea, fa)), 0);
+                hb = mx(mx(dgob + sb, mx(eb, fb)), 0);
+                dgoa = l.ha;
+                dgob = l.hb;
+                hgoa = ha - cst.go;
+                hgob = hb - cst.go;
+                l = mk(hgoa, hgob, ea, eb);
+                best.ha = mx(best.ha, ha);
+                best.hb = mx(best.hb, hb);
+            }
+        }
+        return mk(ha, hb, fa, fb);
+    }
+    template <class BE> static SWB_HD T shfl_up(BE &be, T v, int d, int w)
+    {
+        return mk((int)be.shfl_up((uint32_t)v.ha, d, w), (int)be.shfl_up((uint32_t)v.hb, d, w),
+                  (int)be.shfl_up((uint32_t)v.fa, d, w), (int)be.shfl_up((uint32_t)v.fb, d, w));
+    }
+    template <class BE> static SWB_HD T shfl_xor(BE &be, T v, int m, int w)
+    {
+        return mk((int)be.shfl_xor((uint32_t)v.ha, m, w), (int)be.shfl_xor((uint32_t)v.hb, m, w), v.fa, v.fb);
+    }
+    template <class BE> static SWB_HD T ld(BE &be, const T *p)
+    {
+        uint4 v = be.ld_cg4(reinterpret_cast<const uint4 *>(p));
+        return mk((int)v.x, (int)v.y, (int)v.z, (int)v.w);
+    }
+    template <class BE> static SWB_HD void st(BE &be, T *p, T v)
+    {
+        be.st_cg4(reinterpret_cast<uint4 *>(p), make_uint4(v.ha, v.hb, v.fa, v.fb));
+    }
+    template <class BE> static SWB_HD void ld4(BE &be, const T *p, T *o)
+    {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) o[u] = ld(be, p + u);
+    }
+    template <class BE> static SWB_HD void st4(BE &be, T *p, const T *o)
+    {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) st(be, p + u, o[u]);
     }
 };
 

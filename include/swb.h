@@ -89,6 +89,10 @@ int swb_set_stream(swb_engine *e, void *cuda_stream);
 /* matrix: alpha x alpha int8, row-major, alpha <= 32; S + gap must fit int8; gap >= 0 (linear gap) */
 int swb_set_scoring(swb_engine *e, const int8_t *matrix, int alpha, int gap);
 int swb_set_scoring_preset(swb_engine *e, int preset);
+/* Affine gaps (Gotoh): a gap of length L costs gap_open + (L-1) * gap_extend, 0 <= gap_extend <= gap_open <= 64.
+ * The reference only has the linear model ("define affine penalty ?", SWSolver.cu:8); gap_open == gap_extend is
+ * that model and runs the same kernels as swb_set_scoring. swb_align stays linear-only. */
+int swb_set_scoring_affine(swb_engine *e, const int8_t *matrix, int alpha, int gap_open, int gap_extend);
 /* host helpers, usable without a GPU: the 32 x 32 preset matrix and the preset's char -> code map */
 int swb_scoring_matrix(int preset, int8_t *matrix32x32, int *gap);
 int swb_encode(int preset, const char *text, size_t n, uint8_t *codes);

@@ -223,3 +223,57 @@ int32_t swo_align(const uint8_t *q, const char *q_txt, uint32_t qlen, const uint
     free(T);
     return best;
 }
+
+/* ---- affine gaps (not in the reference: SWSolver.cu:8 only carries the comment "define affine penalty ?") ------
+ * Gotoh's recurrences, the standard form for protein search: a gap of length L costs go + (L-1)*ge.
+ *   E(i,j) = max(E(i,j-1) - ge, H(i,j-1) - go),  F(i,j) = max(F(i-1,j) - ge, H(i-1,j) - go),
+ *   H(i,j) = max(0, H(i-1,j-1) + S, E(i,j), F(i,j)).   With go == ge it is the linear recurrence above.
+ * Parity of the engine's affine mode is against this restatement only (the reference has no goldens for it). */
+int32_t swo_score_affine(const uint8_t *q, uint32_t qlen, const uint8_t *d, uint32_t dlen, const int8_t *m,
+                         int32_t go, int32_t ge)
+{
+    if (qlen == 0 || dlen == 0) return 0;
+    const int32_t NEG = -(1 << 28);
+    int32_t *H = (int32_t *)calloc((size_t)dlen + 1, sizeof(int32_t));
+    int32_t *F = (int32_t *)malloc(((size_t)dlen + 1) * sizeof(int32_t));
+    for (uint32_t j = 0; j <= dlen; ++j) F[j] = NEG;
+    int32_t best = 0;
+    for (uint32_t i = 0; i < qlen; ++i) {
+        const int8_t *srow = m + (size_t)q[i] * SWO_ALPHA;
+        int32_t diag = 0, left = 0, e = NEG;
+        for (uint32_t j = 1; j <= dlen; ++j) {
+            e = e - ge > left - go ? e - ge : left - go;
+            int32_t f = F[j] - ge > H[j] - go ? F[j] - ge : H[j] - go;
+            int32_t h = diag + srow[d[j - 1]];
+            if (e > h) h = e;
+            if (f > h) h = f;
+            if (h < 0) h = 0;
+            if (h > best) best = h;
+            diag = H[j];
+            H[j] = h;
+            F[j] = f;
+            left = h;
+        }
+    }
+    free(H);
+    free(F);
+    return best;
+}
+
+void swo_scan_affine(const uint8_t *q, uint32_t qlen, const uint8_t *codes, const uint64_t *off, uint32_t n,
+                     const int8_t *m, int32_t go, int32_t ge, int32_t *out, uint32_t start, uint32_t stride,
+                     int nthreads)
+{
+    if (stride == 0) stride = 1;
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#else
+    (void)nthreads;
+#endif
+    long cnt = n > start ? (long)((n - start + stride - 1) / stride) : 0;
+#pragma omp parallel for schedule(dynamic, 16)
+    for (long t = 0; t < cnt; ++t) {
+        uint32_t k = start + (uint32_t)t * stride;
+        out[k] = swo_score_affine(q, qlen, codes + off[k], (uint32_t)(off[k + 1] - off[k]), m, go, ge);
+    }
+}

@@ -161,7 +161,7 @@ struct LaneArgs {
     const int8_t *sprof;
     uint32_t sstride;
     int K;
-    int mode;  // 0 V16, 1 V32, 2 V16Q
+    int mode;  // 0 V16, 1 V32, 2 V16Q, 3 V16A, 4 V32A
     bool split;
 };
 
@@ -174,6 +174,11 @@ void lane_main(HostBackend &be, void *a)
         if (la->K == 8) swb_warp_loop<8, V16Q, false>(be, *la->p, la->sprof, la->sstride);
         else if (la->K == 16) swb_warp_loop<16, V16Q, false>(be, *la->p, la->sprof, la->sstride);
         else swb_warp_loop<32, V16Q, false>(be, *la->p, la->sprof, la->sstride);
+    } else if (la->mode == 3) {
+        if (la->K == 8) swb_warp_loop<8, V16A, false>(be, *la->p, la->sprof, la->sstride);
+        else swb_warp_loop<16, V16A, false>(be, *la->p, la->sprof, la->sstride);
+    } else if (la->mode == 4) {
+        swb_warp_loop<8, V32A, false>(be, *la->p, la->sprof, la->sstride);
     } else if (la->mode == 0) {
         if (la->K == 8) swb_warp_loop<8, V16, false>(be, *la->p, la->sprof, la->sstride);
         else if (la->K == 16) swb_warp_loop<16, V16, false>(be, *la->p, la->sprof, la->sstride);
@@ -246,12 +251,15 @@ void run_pass(SwbScoreParams &p, int mode, const SwbQueryPlan &qp, const std::ve
 
 }  // namespace
 
-extern "C" int swbemu_search(const uint8_t *codes, const uint64_t *offsets, uint32_t n, uint32_t shard,
-                             uint32_t nshards, uint32_t group_len, const int8_t *mat32, int gap, const uint8_t *q,
-                             uint32_t qlen, int K, int force_i32, uint32_t chunk_rows, int ovf_thr_override,
-                             uint32_t xl_len, int32_t *scores_out, uint32_t *recomputed_tiles, const uint8_t *q2,
-                             uint32_t qlen2, int32_t *scores_out2, uint32_t chunk_rows_pair)
+// gap_extend != gap: the affine policies (V16A, then V32A on flagged tiles), as enqueue_job of the engine plans them
+static int emu_search(const uint8_t *codes, const uint64_t *offsets, uint32_t n, uint32_t shard, uint32_t nshards,
+                      uint32_t group_len, const int8_t *mat32, int gap, int gap_extend, const uint8_t *q, uint32_t qlen,
+                      int K, int force_i32, uint32_t chunk_rows, int ovf_thr_override, uint32_t xl_len,
+                      int32_t *scores_out, uint32_t *recomputed_tiles, const uint8_t *q2, uint32_t qlen2,
+                      int32_t *scores_out2, uint32_t chunk_rows_pair)
 {
+    const bool affine = gap_extend != gap;
+    if (affine && q2) return -2;
     SwbPlanOpts o;
     if (group_len) o.group_len = group_len;
     o.xl_len = xl_len;
@@ -287,7 +295,7 @@ extern "C" int swbemu_search(const uint8_t *codes, const uint64_t *offsets, uint
     std::vector<int32_t> sorted(2 * (size_t)((nl + 1) / 2), 0), sorted2(2 * (size_t)((nl + 1) / 2), 0);
     std::vector<uint8_t> flags(pl.tiles.size(), 0);
     std::vector<uint32_t> bnd16(2 * pl.bnd_elems + 8);
-    std::vector<uint64_t> bnd32(pl.bnd_elems + 4);
+    std::vector<uint64_t> bnd32((affine ? 2 : 1) * pl.bnd_elems + 4);
     uint32_t recount = 0;
     SwbScoreParams p;
     memset(&p, 0, sizeof p);
@@ -296,6 +304,8 @@ extern "C" int swbemu_search(const uint8_t *codes, const uint64_t *offsets, uint
     p.flags = flags.data();
     p.recount = &recount;
     p.gap = gap;
+    p.gap_open = gap;
+    p.gap_extend = gap_extend;
     p.ovf_thr = ovf_thr_override >= 0 ? ovf_thr_override : 32767 - max_s;
 
     auto build_prof8 = [&](const uint8_t *qq, uint32_t ql, uint32_t prows, uint32_t stride, std::vector<uint8_t> &out) {
@@ -311,8 +321,8 @@ extern "C" int swbemu_search(const uint8_t *codes, const uint64_t *offsets, uint
     if (!force_i32) {
         SwbQueryPlan qp0;
         std::vector<SwbLaunchGroup> g0;
-        swb_plan_query(rows, K, 32, present, pair ? chunk_rows_pair : chunk_rows, qp0);
-        swb_plan_launch_groups(pl, qp0, true, !pair, g0);
+        swb_plan_query(rows, K, affine ? 16 : 32, present, pair ? chunk_rows_pair : chunk_rows, qp0);
+        swb_plan_launch_groups(pl, qp0, true, !pair && !affine, g0);
         std::vector<uint8_t> prof;
         const uint32_t stride = swb_roundup(qp0.prof_rows, 16);
         if (pair) {
@@ -336,7 +346,7 @@ extern "C" int swbemu_search(const uint8_t *codes, const uint64_t *offsets, uint
         p.scores2 = sorted2.data();
         p.bnd = bnd16.data();
         p.only_flagged = 0;
-        run_pass(p, pair ? 2 : 0, qp0, g0, prof, stride);
+        run_pass(p, affine ? 3 : (pair ? 2 : 0), qp0, g0, prof, stride);
     }
     // int32 passes, one per query
     const uint8_t *qs[2] = {q, q2};
@@ -345,7 +355,7 @@ extern "C" int swbemu_search(const uint8_t *codes, const uint64_t *offsets, uint
         if (qls[k] == 0) continue;
         SwbQueryPlan qp1;
         std::vector<SwbLaunchGroup> g1;
-        swb_plan_query(qls[k], K, 16, present, chunk_rows, qp1);
+        swb_plan_query(qls[k], K, affine ? 8 : 16, present, chunk_rows, qp1);
         swb_plan_launch_groups(pl, qp1, true, false, g1);
         std::vector<uint8_t> prof;
         const uint32_t stride = swb_roundup(qp1.prof_rows, 16);
@@ -356,7 +366,7 @@ extern "C" int swbemu_search(const uint8_t *codes, const uint64_t *offsets, uint
         p.scores2 = nullptr;
         p.bnd = bnd32.data();
         p.only_flagged = force_i32 ? 0u : 1u;
-        run_pass(p, 1, qp1, g1, prof, stride);
+        run_pass(p, affine ? 4 : 1, qp1, g1, prof, stride);
     }
     for (uint32_t s = 0; s < nl; ++s) {
         scores_out[pl.out_pos[s]] = sorted[s];
@@ -364,4 +374,24 @@ extern "C" int swbemu_search(const uint8_t *codes, const uint64_t *offsets, uint
     }
     if (recomputed_tiles) *recomputed_tiles = recount;
     return 0;
+}
+
+extern "C" int swbemu_search(const uint8_t *codes, const uint64_t *offsets, uint32_t n, uint32_t shard,
+                             uint32_t nshards, uint32_t group_len, const int8_t *mat32, int gap, const uint8_t *q,
+                             uint32_t qlen, int K, int force_i32, uint32_t chunk_rows, int ovf_thr_override,
+                             uint32_t xl_len, int32_t *scores_out, uint32_t *recomputed_tiles, const uint8_t *q2,
+                             uint32_t qlen2, int32_t *scores_out2, uint32_t chunk_rows_pair)
+{
+    return emu_search(codes, offsets, n, shard, nshards, group_len, mat32, gap, gap, q, qlen, K, force_i32, chunk_rows,
+                      ovf_thr_override, xl_len, scores_out, recomputed_tiles, q2, qlen2, scores_out2, chunk_rows_pair);
+}
+
+extern "C" int swbemu_search_affine(const uint8_t *codes, const uint64_t *offsets, uint32_t n, uint32_t shard,
+                                    uint32_t nshards, uint32_t group_len, const int8_t *mat32, int gap_open,
+                                    int gap_extend, const uint8_t *q, uint32_t qlen, int K, int force_i32,
+                                    uint32_t chunk_rows, int ovf_thr_override, int32_t *scores_out,
+                                    uint32_t *recomputed_tiles)
+{
+    return emu_search(codes, offsets, n, shard, nshards, group_len, mat32, gap_open, gap_extend, q, qlen, K, force_i32,
+                      chunk_rows, ovf_thr_override, 0, scores_out, recomputed_tiles, nullptr, 0, nullptr, 0);
 }

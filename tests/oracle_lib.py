@@ -30,6 +30,9 @@ class Oracle:
         L.swo_scan.restype = None
         L.swo_scan.argtypes = [_u8p, ctypes.c_uint32, _u8p, _u64p, ctypes.c_uint32, _i8p, ctypes.c_int32,
                                _i32p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int]
+        L.swo_scan_affine.restype = None
+        L.swo_scan_affine.argtypes = [_u8p, ctypes.c_uint32, _u8p, _u64p, ctypes.c_uint32, _i8p, ctypes.c_int32,
+                                      ctypes.c_int32, _i32p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int]
         L.swo_align.restype = ctypes.c_int32
         L.swo_align.argtypes = [_u8p, ctypes.c_char_p, ctypes.c_uint32, _u8p, ctypes.c_char_p, ctypes.c_uint32,
                                 _i8p, ctypes.c_int32, ctypes.c_char_p, ctypes.c_char_p,
@@ -71,6 +74,17 @@ class Oracle:
             out = np.full(n, -1, dtype=np.int32)
         self.lib.swo_scan(_ptr(q, _u8p), len(q), _ptr(codes, _u8p), _ptr(offsets, _u64p), n, _ptr(m, _i8p), gap,
                           _ptr(out, _i32p), start, stride, threads)
+        return out
+
+    def scan_affine(self, q, codes, offsets, m, gap_open, gap_extend, start=0, stride=1, threads=0):
+        q = np.ascontiguousarray(q, dtype=np.uint8)
+        codes = np.ascontiguousarray(codes, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        m = np.ascontiguousarray(m, dtype=np.int8)
+        n = len(offsets) - 1
+        out = np.full(n, -1, dtype=np.int32)
+        self.lib.swo_scan_affine(_ptr(q, _u8p), len(q), _ptr(codes, _u8p), _ptr(offsets, _u64p), n, _ptr(m, _i8p),
+                                 gap_open, gap_extend, _ptr(out, _i32p), start, stride, threads)
         return out
 
     def align(self, qtxt, dtxt, scheme="ident3", gap=2):

@@ -180,3 +180,86 @@ def test_query_pair_jobs(emu, oracle, subset, queries):
     assert np.array_equal(gb, oracle.scan(qb, c2, o2, m))
     (ga, gb), _ = emu(c2, o2, m, qb[:9], q2=np.zeros(0, np.uint8), K=0)
     assert np.array_equal(ga, oracle.scan(qb[:9], c2, o2, m)) and not gb.any()
+
+
+# ---- affine gaps ("define affine penalty ?", SWSolver.cu:8) -------------------------------------------
+@pytest.fixture(scope="module")
+def emu_affine(emu):
+    L = ctypes.CDLL(os.path.join(ROOT, PKG, "lib", "libswbemu.so"))
+    L.swbemu_search_affine.restype = ctypes.c_int
+    L.swbemu_search_affine.argtypes = [_u8p, _u64p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32,
+                                       _i8p, ctypes.c_int, ctypes.c_int, _u8p, ctypes.c_uint32, ctypes.c_int,
+                                       ctypes.c_int, ctypes.c_uint32, ctypes.c_int, _i32p,
+                                       ctypes.POINTER(ctypes.c_uint32)]
+
+    def search(codes, offs, m, q, go, ge, K=0, group_len=384, force_i32=0, chunk_rows=0, thr=-1):
+        codes = np.ascontiguousarray(codes, dtype=np.uint8)
+        offs = np.ascontiguousarray(offs, dtype=np.uint64)
+        q = np.ascontiguousarray(q, dtype=np.uint8)
+        m = np.ascontiguousarray(m, dtype=np.int8)
+        n = len(offs) - 1
+        out = np.full(n, -7, dtype=np.int32)
+        rc = ctypes.c_uint32()
+        r = L.swbemu_search_affine(codes.ctypes.data_as(_u8p), offs.ctypes.data_as(_u64p), n, 0, 1, group_len,
+                                   m.ctypes.data_as(_i8p), go, ge, q.ctypes.data_as(_u8p), len(q), K, force_i32,
+                                   chunk_rows, thr, out.ctypes.data_as(_i32p), ctypes.byref(rc))
+        assert r == 0
+        return out, rc.value
+
+    return search
+
+
+def test_oracle_affine_degenerates_to_linear(oracle, subset, queries):
+    m = oracle.matrix("blosum50")
+    q = oracle.encode(queries["P02232"])
+    lin = oracle.scan(q, subset["codes"], subset["offsets"], m)
+    assert np.array_equal(oracle.scan_affine(q, subset["codes"], subset["offsets"], m, 2, 2), lin)
+    # a dearer opening can only lower a score, and never below the gap-free diagonal score
+    aff = oracle.scan_affine(q, subset["codes"], subset["offsets"], m, 10, 2)
+    assert (aff <= lin).all() and (aff < lin).any()
+    assert (oracle.scan_affine(q, subset["codes"], subset["offsets"], m, 64, 64) <= aff).all()
+
+
+@pytest.mark.parametrize("go,ge,K,group_len", [(10, 2, 0, 384), (10, 2, 8, 64), (12, 1, 16, 16), (5, 0, 0, 16),
+                                               (3, 2, 8, 2000)])
+def test_affine_subset(emu_affine, oracle, subset, queries, go, ge, K, group_len):
+    m = oracle.matrix("blosum50")
+    q = oracle.encode(queries["P02232"])
+    want = oracle.scan_affine(q, subset["codes"], subset["offsets"], m, go, ge)
+    got, _ = emu_affine(subset["codes"], subset["offsets"], m, q, go, ge, K=K, group_len=group_len)
+    assert np.array_equal(got, want)
+
+
+def test_affine_chunks_recompute_and_overflow(emu_affine, oracle, subset, queries):
+    m = oracle.matrix("blosum50")
+    q = oracle.encode(queries["P04775"])
+    want = oracle.scan_affine(q, subset["codes"], subset["offsets"], m, 10, 2)
+    got, rc = emu_affine(subset["codes"], subset["offsets"], m, q, 10, 2, chunk_rows=1024)
+    assert np.array_equal(got, want) and rc == 0
+    got, rc = emu_affine(subset["codes"], subset["offsets"], m, q, 10, 2, chunk_rows=1024, thr=60, group_len=128)
+    assert np.array_equal(got, want) and rc >= 1
+    got, rc = emu_affine(subset["codes"], subset["offsets"], m, q, 10, 2, force_i32=1, group_len=64)
+    assert np.array_equal(got, want)
+    # a real s16 overflow
+    w = np.full(2300, 17, dtype=np.uint8)
+    rng = np.random.default_rng(2)
+    codes, offs = pack_db([w, rng.integers(0, 20, 300).astype(np.uint8), w[:2200].copy()])
+    want = oracle.scan_affine(w, codes, offs, m, 10, 2)
+    assert want[0] == 34500
+    got, rc = emu_affine(codes, offs, m, w, 10, 2)
+    assert np.array_equal(got, want) and rc >= 1
+
+
+def test_affine_edges(emu_affine, oracle):
+    rng = np.random.default_rng(8)
+    m = oracle.matrix("blosum50")
+    lens = [0, 1, 2, 3, 4, 5, 7, 8, 9, 0, 33, 64, 65, 127, 128, 129, 1, 0, 300, 700]
+    codes, offs = pack_db(random_db(rng, lens))
+    for ql in (1, 8, 9, 33, 130):
+        # low-complexity queries make gapped paths win often
+        q = rng.integers(0, 4, ql).astype(np.uint8)
+        for go, ge in ((10, 2), (4, 1), (2, 0)):
+            want = oracle.scan_affine(q, codes, offs, m, go, ge)
+            for K, gl in ((8, 8), (16, 16), (0, 384)):
+                got, _ = emu_affine(codes, offs, m, q, go, ge, K=K, group_len=gl)
+                assert np.array_equal(got, want), (ql, go, ge, K, gl)

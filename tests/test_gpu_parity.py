@@ -454,3 +454,45 @@ def test_cpp_shim_two_databases_in_one_process(swb, subset, tmp_path):
     r = subprocess.run([exe, os.path.join(GOLDEN, "queries", "P01008.fasta"), os.path.join(GOLDEN, "uniprot_subset.fasta"),
                         rev, os.path.join(GOLDEN, "P01008.head111.txt")], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "mismatches 0" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("group_len,k", [(384, 0), (16, 8), (96, 16), (100000, 0)])
+def test_affine_gaps_vs_gotoh_oracle(swb, oracle, subset, queries, group_len, k):
+    """the affine model the reference left as a comment (SWSolver.cu:8). Kernels V16A / V32A against the
+    Gotoh restatement in oracle/sw_oracle.c; gap_open == gap_extend must reproduce the reference's linear goldens."""
+    rng = np.random.default_rng(4242 + group_len)
+    m = oracle.matrix("blosum50")
+    lens = np.concatenate([rng.integers(0, 40, 50), rng.integers(40, 700, 300), rng.integers(700, 3000, 9), [0, 1, 2]])
+    rng.shuffle(lens)
+    wq = np.full(2400, 17, dtype=np.uint8)  # self score 36000: s16 overflow -> V32A recompute
+    enc = random_db(rng, lens) + [wq.copy(), wq[:2250].copy()]
+    codes, offs = pack_db(enc)
+    e = swb.Engine(0, group_len=group_len, k=k)
+    try:
+        e.db_load(codes, offs)
+        for go, ge in ((10, 2), (12, 1), (3, 0)):
+            e.set_scoring_affine(m, go, ge)
+            for ql in (1, 9, 33, 257, 1000):
+                q = rng.integers(0, 6 if ql < 100 else 24, ql).astype(np.uint8)
+                assert np.array_equal(e.search(q), oracle.scan_affine(q, codes, offs, m, go, ge)), (go, ge, ql)
+            got = e.search(wq)
+            assert np.array_equal(got, oracle.scan_affine(wq, codes, offs, m, go, ge))
+            assert got.max() == 36000 and e.stats()["recomputed_tiles"] >= 1
+        # batches and a query longer than one profile chunk
+        e.set_scoring_affine(m, 10, 2)
+        e.set_option("chunk_rows", 1024)
+        qs = [rng.integers(0, 24, n).astype(np.uint8) for n in (300, 2100, 50, 1025)]
+        batch = e.search_batch(qs)
+        for q, got in zip(qs, batch):
+            assert np.array_equal(got, oracle.scan_affine(q, codes, offs, m, 10, 2)), len(q)
+        # traceback is linear-only and says so
+        with pytest.raises(swb.SwbError):
+            e.align(qs[0], 0, int(offs[1] - offs[0]))
+        # go == ge: the linear kernels, the reference's goldens
+        e.set_scoring_affine(m, 2, 2)
+        e.set_option("chunk_rows", 7168)
+        e.db_load(subset["codes"], subset["offsets"])
+        for name in ("P01008", "P02232"):
+            assert np.array_equal(e.search(swb.encode(queries[name])), _gold(name)), name
+    finally:
+        e.close()

@@ -229,6 +229,9 @@ def main():
     ap.add_argument("--group-order", type=int, default=0)
     ap.add_argument("--split", type=int, default=-1, help="pipelined passes for very long tiles: 1 on, 0 off (default)")
     ap.add_argument("--pair-queries", type=int, default=-1, help="pack two queries of a batch per lane: 1 (default), 0")
+    ap.add_argument("--batch-order", type=int, default=-1, help="0 longest query first (default), 1 as given")
+    ap.add_argument("--chunk-rows", type=int, default=0)
+    ap.add_argument("--xl-len", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--affine", default="", help="GO,GE: affine gaps instead of the reference's linear gap 2 (a side "
                     "measurement of the V16A kernels; not the headline metric, no CPU leg)")
@@ -272,6 +275,12 @@ def main():
         opts["split"] = args.split
     if args.pair_queries >= 0:
         opts["pair_queries"] = args.pair_queries
+    if args.batch_order >= 0:
+        opts["batch_order"] = args.batch_order
+    if args.chunk_rows:
+        opts["chunk_rows"] = args.chunk_rows
+    if args.xl_len:
+        opts["xl_len"] = args.xl_len
     eng = swb.Engine(local, **opts)
     stream = torch.cuda.current_stream()
     eng.set_stream(stream.cuda_stream)

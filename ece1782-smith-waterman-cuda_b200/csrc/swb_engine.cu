@@ -84,10 +84,13 @@ struct swb_engine {
     // options
     SwbPlanOpts plan_opts;
     int opt_k = 0;
+    int opt_batch_order = 0;  // batches: 0 = longest query first, 1 = in the caller's order
     int opt_pair_queries = 0; // batches: pack two queries into the halves of the s16x2 lanes (V16Q). Opt-in: measured
                               // 0.77x of V16 on B200 (4 B of profile per packed cell: shared-memory bound)
-    int opt_split = 0;        // pipelined passes for the very long tiles (opt-in: cuts the latency of a lone long query
-                              // on a small shard, costs ~1 % of batch throughput; measured in profiles/)
+    int opt_split = -1;       // pipelined passes for the very long tiles: 1 on, 0 off, -1 auto = on for small shards
+                              // (fewer tiles than twice the GPU's warp slots), where a few long tiles are the critical
+                              // path of a query (+10 % at 1/8 of Swiss-Prot, +3 % at 1/4); on a large shard the bulk
+                              // hides them and the extra launches cost ~0.5 % (measured in profiles/)
     int opt_group_order = 0;  // 0 auto (lone query: longest tiles first; batch: bulk first), 1 longest first, 2 bulk first
     uint32_t cur_nq = 1;
     int nslots = 16;
@@ -305,10 +308,14 @@ extern "C" int swb_set_option(swb_engine *e, const char *key, int64_t value)
     } else if (!strcmp(key, "xl_len")) {
         if (value < 0 || value > (1ll << 31)) return fail(e, SWB_ERR_ARG, "xl_len out of range");
         e->plan_opts.xl_len = (uint32_t)value;
+    } else if (!strcmp(key, "batch_order")) {
+        if (value < 0 || value > 1) return fail(e, SWB_ERR_ARG, "batch_order must be 0 (longest query first) or 1 (as given)");
+        e->opt_batch_order = (int)value;
     } else if (!strcmp(key, "pair_queries")) {
         e->opt_pair_queries = value != 0;
     } else if (!strcmp(key, "split")) {
-        e->opt_split = value != 0;
+        if (value < -1 || value > 1) return fail(e, SWB_ERR_ARG, "split must be -1 (auto), 0 or 1");
+        e->opt_split = (int)value;
     } else if (!strcmp(key, "group_order")) {
         if (value < 0 || value > 2) return fail(e, SWB_ERR_ARG, "group_order must be 0, 1 or 2");
         e->opt_group_order = (int)value;
@@ -641,7 +648,9 @@ static int enqueue_job(swb_engine *e, Slot &s, uint32_t qi, const uint8_t *q, ui
     std::vector<SwbLaunchGroup> g0;
     // affine lanes carry (H, E) per row, so their strips stop at 16 rows (s16) / 8 rows (int32)
     swb_plan_query(rows, e->opt_k, affine ? 16 : 32, present, pair ? SWB_CHUNK_ROWS_QPAIR : e->chunk_rows, qp0);
-    swb_plan_launch_groups(pl, qp0, longest_first, !pair && !affine && e->opt_split != 0, g0);
+    const bool small_shard = pl.tiles.size() < 2u * (size_t)e->sm_count * (SWB_NT_LARGE / 32);
+    const bool split = !pair && !affine && (e->opt_split == 1 || (e->opt_split < 0 && small_shard));
+    swb_plan_launch_groups(pl, qp0, longest_first, split, g0);
     // int32 passes over flagged tiles, one per query, only when a score can exceed the s16 range at all
     const uint32_t qlens[2] = {qlen, pair ? qlen2 : 0u};
     bool need_i32[2];
@@ -781,12 +790,14 @@ extern "C" int swb_search_batch(swb_engine *e, const uint8_t *qcodes, const uint
     e->stats.recomputed_tiles = 0;
     e->last_nq = nq;
     e->cur_nq = nq;
-    // jobs: with query-pair packing the queries are taken longest first and neighbours in length share a job (the
-    // shorter one pays for the rows of the longer one); a query left over, or every query without packing, runs alone
+    // jobs: queries are taken longest first (the tiles of a long query are long-running work items: started last they
+    // would leave the GPU half empty at the end of the batch; option batch_order = 1 keeps the caller's order). With
+    // query-pair packing neighbours in length share a job (the shorter one pays for the rows of the longer one); a query
+    // left over, or every query without packing, runs alone
     std::vector<uint32_t> order(nq);
     for (uint32_t i = 0; i < nq; ++i) order[i] = i;
     const bool pairing = e->opt_pair_queries && nq >= 2 && !e->affine;
-    if (pairing)
+    if (pairing || e->opt_batch_order == 0)
         std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
             return qoffsets[a + 1] - qoffsets[a] > qoffsets[b + 1] - qoffsets[b];
         });

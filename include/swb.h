@@ -76,10 +76,13 @@ const char *swb_last_error(const swb_engine *e);
  *          "k" (query rows per lane: 0 = chosen per lane-group size and query, else 8, 16, 32),
  *          "streams" (queries of a batch in flight at once, 1..24, default 16; their scratch is allocated on first use),
  *          "group_order" (0 = auto, 1 = launch the long-sequence tiles first, 2 = launch the bulk first),
+ *          "batch_order" (0 = a batch runs its longest query first (default), 1 = in the caller's order; the
+ *          results are always in the caller's order),
  *          "pair_queries" (1 = a batch packs two queries of similar length into the two s16 halves of a lane, one
  *          database sequence per lane, no byte permute; measured slower on B200 (shared-memory bound); default 0),
  *          "split" (1 = the passes of sequences longer than "xl_len" (8192) run as pipelined work items on
- *          different warps: lower latency for a lone long query, ~1 % less batch throughput; default 0),
+ *          different warps, 0 = never, -1 (default) = only on small shards, where those few tiles are the critical
+ *          path of a query: +10 % at 1/8 of Swiss-Prot per GPU; on a large shard it costs ~0.5 %),
  *          "chunk_rows" (query rows per launch for queries beyond shared memory; multiple of 1024, <= 7168) */
 int swb_set_option(swb_engine *e, const char *key, int64_t value);
 /* run on the caller's CUDA stream (cudaStream_t as void*); NULL = the engine's own stream */

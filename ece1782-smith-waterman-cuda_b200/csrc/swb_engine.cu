@@ -7,6 +7,8 @@
 #include <sys/time.h>
 #include <algorithm>
 #include <string>
+#include <chrono>
+#include <thread>
 #include <vector>
 
 #include "../../include/swb.h"
@@ -95,6 +97,7 @@ struct swb_engine {
     uint32_t cur_nq = 1;
     int nslots = 16;
     uint32_t chunk_rows = SWB_CHUNK_ROWS;  // query rows per launch for queries beyond shared memory
+    bool chunk_rows_set = false;           // false: batches on small shards use 2048-row launches (below)
     // database
     bool db_loaded = false;
     SwbPlan plan;
@@ -322,6 +325,7 @@ extern "C" int swb_set_option(swb_engine *e, const char *key, int64_t value)
     } else if (!strcmp(key, "chunk_rows")) {
         if (value < 1024 || value > SWB_CHUNK_ROWS || value % 1024) return fail(e, SWB_ERR_ARG, "chunk_rows must be a multiple of 1024 up to 7168");
         e->chunk_rows = (uint32_t)value;
+        e->chunk_rows_set = true;
     } else {
         return fail(e, SWB_ERR_ARG, std::string("unknown option ") + key);
     }
@@ -643,12 +647,16 @@ static int enqueue_job(swb_engine *e, Slot &s, uint32_t qi, const uint8_t *q, ui
     const int mode0 = affine ? SWB_MODE_S16A : (pair ? SWB_MODE_QPAIR : SWB_MODE_S16);
     const int mode1 = affine ? SWB_MODE_I32A : SWB_MODE_I32;
 
+    const bool small_shard = pl.tiles.size() < 2u * (size_t)e->sm_count * (SWB_NT_LARGE / 32);
+    // batches on small shards: 2048-row launches keep the shared-memory footprint of a block small, so blocks of several
+    // queries share an SM and fill each other's tails (+1..2 % at 1/8 and 1/4 of Swiss-Prot per GPU)
+    const uint32_t chunk_rows = !e->chunk_rows_set && small_shard && e->cur_nq > 1 ? 2048u : e->chunk_rows;
+
     // pass 0: the s16 pass over all tiles
     SwbQueryPlan qp0;
     std::vector<SwbLaunchGroup> g0;
     // affine lanes carry (H, E) per row, so their strips stop at 16 rows (s16) / 8 rows (int32)
-    swb_plan_query(rows, e->opt_k, affine ? 16 : 32, present, pair ? SWB_CHUNK_ROWS_QPAIR : e->chunk_rows, qp0);
-    const bool small_shard = pl.tiles.size() < 2u * (size_t)e->sm_count * (SWB_NT_LARGE / 32);
+    swb_plan_query(rows, e->opt_k, affine ? 16 : 32, present, pair ? SWB_CHUNK_ROWS_QPAIR : chunk_rows, qp0);
     const bool split = !pair && !affine && (e->opt_split == 1 || (e->opt_split < 0 && small_shard));
     swb_plan_launch_groups(pl, qp0, longest_first, split, g0);
     // int32 passes over flagged tiles, one per query, only when a score can exceed the s16 range at all
@@ -661,7 +669,7 @@ static int enqueue_job(swb_engine *e, Slot &s, uint32_t qi, const uint8_t *q, ui
     for (int k = 0; k < 2; ++k) {
         need_i32[k] = qlens[k] > 0 && (int64_t)e->max_s * std::min<uint32_t>(qlens[k], pl.max_len) > ovf_thr;
         if (!need_i32[k]) continue;
-        swb_plan_query(qlens[k], e->opt_k, affine ? 8 : 16, present, e->chunk_rows, qp1[k]);
+        swb_plan_query(qlens[k], e->opt_k, affine ? 8 : 16, present, chunk_rows, qp1[k]);
         swb_plan_launch_groups(pl, qp1[k], longest_first, false, g1[k]);
         nlaunch += g1[k].size() * qp1[k].chunks.size();
         prof8_rows = std::max(prof8_rows, qp1[k].prof_rows);
@@ -768,6 +776,21 @@ static int finish_slot(swb_engine *e, Slot &s)
     return SWB_OK;
 }
 
+// index of a slot among the first `ns` whose job has completed (polls the completion events)
+static int wait_any_slot(swb_engine *e, int ns, int *out)
+{
+    for (;;) {
+        for (int i = 0; i < ns; ++i) {
+            Slot &s = e->slots[i];
+            if (!s.busy) { *out = i; return SWB_OK; }
+            const cudaError_t q = cudaEventQuery(s.done);
+            if (q == cudaSuccess) { *out = i; return SWB_OK; }
+            if (q != cudaErrorNotReady) return fail(e, SWB_ERR_CUDA, std::string("cudaEventQuery: ") + cudaGetErrorString(q));
+        }
+        std::this_thread::sleep_for(std::chrono::microseconds(30));
+    }
+}
+
 extern "C" int swb_search_batch(swb_engine *e, const uint8_t *qcodes, const uint64_t *qoffsets, uint32_t nq,
                                 int32_t *scores)
 {
@@ -811,7 +834,11 @@ extern "C" int swb_search_batch(swb_engine *e, const uint8_t *qcodes, const uint
     }
     int rc = SWB_OK;
     for (uint32_t j = 0; j < njobs && rc == SWB_OK; ++j) {
-        Slot &s = e->slots[j % ns];
+        // the first `ns` jobs take the slots in turn; later ones take whichever slot finishes first (a slot that holds
+        // a long query must not hold up the queue behind it)
+        int si = (int)(j % (uint32_t)ns);
+        if (j >= (uint32_t)ns && (rc = wait_any_slot(e, ns, &si)) != SWB_OK) break;
+        Slot &s = e->slots[si];
         if ((rc = finish_slot(e, s)) != SWB_OK) break;
         const uint32_t qa = pairing ? order[2 * j] : order[j];
         const bool pair = pairing && 2 * j + 1 < nq;

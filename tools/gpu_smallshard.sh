@@ -13,10 +13,12 @@ for l in open("gpurun_out/ss_$name.log"):
         print("$name: value %.0f GCUPS ms/step %.2f e2e %.0f launches %s tiles %s" % (d["value"], d["ms_per_step"], d["e2e"]["value"], d["gpu_launches"], d["engine"]["tiles_by_group"]))
 PY
 }
-run s8_split_chunk2k --scale 0.125 --split 1 --chunk-rows 2048
-run s8_split_xl4k --scale 0.125 --split 1 --xl-len 4096
-run s8_split_xl2k --scale 0.125 --split 1 --xl-len 2048
-run s4_split --scale 0.25 --split 1
-run s2_lpt --scale 0.5
-run s2_split --scale 0.5 --split 1
-run s1_split --split 1
+run s8_new --scale 0.125
+run s8_new_s20 --scale 0.125 --streams 20
+run s8_new_chunk2k --scale 0.125 --chunk-rows 2048
+run s8_new_chunk3k --scale 0.125 --chunk-rows 3072
+run s8_new_chunk2k_s20 --scale 0.125 --chunk-rows 2048 --streams 20
+run s8_new_s12 --scale 0.125 --streams 12
+run s4_new --scale 0.25
+run s4_new_chunk2k --scale 0.25 --chunk-rows 2048
+run s1_new

@@ -87,6 +87,27 @@ def synth_queries(n=1000, seed=1785):
     return [rng.choice(32, size=int(l), p=p).astype(np.uint8) for l in lens]
 
 
+def synth_config4(seed=1784):
+    """configs[3] (SURVEY 8d "Config 4"): queries of 5,000 / 10,000 / 20,000 / 35,213 residues; database = 256 random
+    targets, log-uniform in [5,000, 35,213], plus a 10 %-mutated copy of every query and the query itself (self score
+    ~5.5 x L >> 32767: forces the int32 recompute). Uniform 20-letter residues."""
+    rng = np.random.default_rng(seed)
+    tl = np.round(np.exp(rng.uniform(np.log(5000), np.log(35213), 256))).astype(np.int64)
+    seqs = [rng.integers(0, 20, int(l)).astype(np.uint8) for l in tl]
+    qs = []
+    for ql in (5000, 10000, 20000, 35213):
+        q = rng.integers(0, 20, ql).astype(np.uint8)
+        mutated = q.copy()
+        pos = rng.choice(ql, ql // 10, replace=False)
+        mutated[pos] = rng.integers(0, 20, len(pos))
+        qs.append(q)
+        seqs += [mutated, q.copy()]
+    lens = np.array([len(x) for x in seqs], dtype=np.int64)
+    offsets = np.zeros(len(seqs) + 1, dtype=np.uint64)
+    offsets[1:] = np.cumsum(lens)
+    return np.concatenate(seqs), offsets, qs
+
+
 def load_queries(swb):
     qdir = os.path.join(ROOT, "tests", "golden", "queries")
     names = sorted(fn[:-6] for fn in os.listdir(qdir) if fn.endswith(".fasta"))
@@ -201,6 +222,12 @@ def workload_config(offsets, qs, args):
 
 
 def _workload_config(offsets, qs, args):
+    if getattr(args, "workload", "config2") == "config4":
+        return {"workload": "configs[3]: long-sequence path, 4 queries of 5,000..35,213 residues x 264 targets of 5k..35k "
+                            "(256 random + mutated copies + the queries themselves)",
+                "db_sequences": int(len(offsets) - 1), "db_residues": int(offsets[-1]), "queries": len(qs),
+                "query_residues": int(sum(len(q) for q in qs)), "scoring": "BLOSUM50 ('*' zeroed), linear gap 2",
+                "l2": "boundary scratch flushed through L2 between passes; inputs smaller than L2"}
     if getattr(args, "workload", "config2") == "config5":
         return {"workload": "configs[4]: 1,000 synthetic queries x UniProt-scale synthetic DB (10 Swiss-Prot-shaped parts)",
                 "db_sequences": int(len(offsets) - 1), "db_residues": int(offsets[-1]), "queries": len(qs),
@@ -255,6 +282,10 @@ def main():
         codes, offsets = synth_db_uniprot_scale()
         qs = synth_queries()
         names = ["q%d" % i for i in range(len(qs))]
+        args.no_cpu = True
+    elif args.workload == "config4":
+        codes, offsets, qs = synth_config4()
+        names = ["L%d" % len(q) for q in qs]
         args.no_cpu = True
     else:
         codes, offsets = synth_db(scale=args.scale)
@@ -339,6 +370,20 @@ def main():
             sample_ok = sample_ok and bool(np.array_equal(got, want))
         args.e2e_steps = 0
 
+    # configs[3] parity: every query against its mutated copy and itself (the int32-recompute hits) and 6 targets
+    if args.workload == "config4":
+        from oracle_lib import Oracle
+        o = Oracle()
+        ids = eng.db_ids()
+        sel = [i for i in ids if i >= 256 or i < 6]
+        pos = {int(g): k for k, g in enumerate(ids)}
+        sc, so = swb.pack_sequences([codes[int(offsets[i]):int(offsets[i + 1])] for i in sel])
+        sample_ok = True
+        for qi in range(len(qs)):
+            got = eng.fetch_scores(qi)[[pos[int(i)] for i in sel]]
+            want = o.scan(qs[qi], sc, so, o.matrix("blosum50"))
+            sample_ok = sample_ok and bool(np.array_equal(got, want))
+
     # end to end through the C ABI with host buffers (database upload + search + scores back), wall clock
     big = args.workload == "config5"  # no nq x n host matrix at UniProt scale: top hits come from fetch_scores
     out = np.zeros((1 if big else len(qs), nloc), dtype=np.int32)
@@ -415,7 +460,7 @@ def main():
                 "config": workload_config(offsets, qs, args), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
                 "roofline": roofline, "engine": {k: st[k] for k in ("tiles", "tiles_by_group", "last_k",
                                                                     "recomputed_tiles", "sm_count")},
-                "topk_merge_ok": top_ok, "config5_sample_parity_ok": sample_ok}
+                "topk_merge_ok": top_ok, "sample_parity_ok": sample_ok}
         if not args.no_cpu and world == 1:  # the CPU baseline is reported at N = 1 only
             names_t, qtexts = load_queries(None)
             line["cpu_baseline"], _ = cpu_sample_gcups(codes, offsets, names_t, qtexts, args.cpu_seconds)

@@ -529,6 +529,7 @@ extern "C" int swb_db_ids(const swb_engine *e, uint32_t *ids)
 struct LaunchShape {
     int block_cfg;
     int grid;
+    uint32_t warps_active;  // 0 = every warp of a block takes tiles
     size_t smem;
     uint32_t smem_rows;
 };
@@ -545,7 +546,19 @@ static int shape_for(swb_engine *e, int K, int mode, bool split, uint32_t smem_r
     if (per_sm < 1) return fail(e, SWB_ERR_CUDA, "score kernel does not fit on an SM");
     const int nt = split ? 32 : (ls.block_cfg == SWB_BLOCK_SMALL ? SWB_NT_SMALL : SWB_NT_LARGE);
     const int need = (int)((ntiles + nt / 32 - 1) / (nt / 32));
-    ls.grid = std::max(1, std::min(per_sm * e->sm_count, need));
+    const int slots = per_sm * e->sm_count;
+    ls.grid = std::max(1, std::min(slots, need));
+    ls.warps_active = 0;
+    // A lone query whose launch has fewer tiles than the GPU has warps: one tile per warp packed into full blocks would
+    // put 16 long-running warps on a few SMs and leave the others empty. Spread them: more blocks, fewer active warps
+    // each. (Not for batches: there other queries fill the SMs, and half-empty blocks would only hold shared memory.)
+    if (!split && e->cur_nq <= 1 && need < slots) {
+        const uint32_t wpb = std::max<uint32_t>(1u, (ntiles + (uint32_t)slots - 1u) / (uint32_t)slots);
+        if (wpb < (uint32_t)(nt / 32)) {
+            ls.warps_active = wpb;
+            ls.grid = std::max(1, (int)((ntiles + wpb - 1u) / wpb));
+        }
+    }
     return SWB_OK;
 }
 
@@ -593,17 +606,17 @@ static int enqueue_pass(swb_engine *e, Slot &s, int mode, SwbScoreParams &p, con
         size_t prog_at = 0;
         for (size_t c = 0; c < qp.chunks.size(); ++c) {
             const SwbQueryChunk &ch = qp.chunks[c];
-            p.split_passes = g.split ? swb_split_passes(ch.rows) : 0;
             // work items of the launch: tiles, (tile, pass) for split groups, (tile, half) for query pairs
-            p.ntiles = g.split ? g.ntiles * p.split_passes : (mode == SWB_MODE_QPAIR ? 2 * g.ntiles : g.ntiles);
+            p.ntiles = mode == SWB_MODE_QPAIR ? 2 * g.ntiles : g.ntiles;
             p.prog = g.split ? s.d_prog + prog_at : nullptr;
-            prog_at += (size_t)g.ntiles * p.split_passes;
+            if (g.split) prog_at += swb_split_items(ch.rows, g, &p);  // sets p.ntiles to the number of items
             LaunchShape ls;
             int rc = shape_for(e, g.K, mode, g.split, swb_group_smem_rows(ch.rows, g), p.ntiles, ls);
             if (rc != SWB_OK) return rc;
             p.row0 = ch.row0;
             p.rows = ch.rows;
             p.smem_rows = ls.smem_rows;
+            p.warps_active = ls.warps_active;
             p.first_chunk = ch.first;
             p.last_chunk = ch.last;
             p.counter = s.d_counters + counter++;
@@ -651,13 +664,13 @@ static int enqueue_job(swb_engine *e, Slot &s, uint32_t qi, const uint8_t *q, ui
     // batches on small shards: 2048-row launches keep the shared-memory footprint of a block small, so blocks of several
     // queries share an SM and fill each other's tails (+1..2 % at 1/8 and 1/4 of Swiss-Prot per GPU)
     const uint32_t chunk_rows = !e->chunk_rows_set && small_shard && e->cur_nq > 1 ? 2048u : e->chunk_rows;
+    const bool split = !pair && !affine && (e->opt_split == 1 || (e->opt_split < 0 && small_shard));
 
     // pass 0: the s16 pass over all tiles
     SwbQueryPlan qp0;
     std::vector<SwbLaunchGroup> g0;
     // affine lanes carry (H, E) per row, so their strips stop at 16 rows (s16) / 8 rows (int32)
     swb_plan_query(rows, e->opt_k, affine ? 16 : 32, present, pair ? SWB_CHUNK_ROWS_QPAIR : chunk_rows, qp0);
-    const bool split = !pair && !affine && (e->opt_split == 1 || (e->opt_split < 0 && small_shard));
     swb_plan_launch_groups(pl, qp0, longest_first, split, g0);
     // int32 passes over flagged tiles, one per query, only when a score can exceed the s16 range at all
     const uint32_t qlens[2] = {qlen, pair ? qlen2 : 0u};
@@ -670,7 +683,7 @@ static int enqueue_job(swb_engine *e, Slot &s, uint32_t qi, const uint8_t *q, ui
         need_i32[k] = qlens[k] > 0 && (int64_t)e->max_s * std::min<uint32_t>(qlens[k], pl.max_len) > ovf_thr;
         if (!need_i32[k]) continue;
         swb_plan_query(qlens[k], e->opt_k, affine ? 8 : 16, present, chunk_rows, qp1[k]);
-        swb_plan_launch_groups(pl, qp1[k], longest_first, false, g1[k]);
+        swb_plan_launch_groups(pl, qp1[k], longest_first, split, g1[k]);
         nlaunch += g1[k].size() * qp1[k].chunks.size();
         prof8_rows = std::max(prof8_rows, qp1[k].prof_rows);
     }
@@ -700,11 +713,16 @@ static int enqueue_job(swb_engine *e, Slot &s, uint32_t qi, const uint8_t *q, ui
     if (affine) CU(GROW_DEV(s.d_bnd16, s.bnd16_cap, 8ull * pl.bnd_elems));
     if (need_i32[0] || need_i32[1]) CU(GROW_DEV(s.d_bnd32, s.bnd32_cap, (affine ? 16ull : 8ull) * pl.bnd_elems));
     // progress counters of the split group: one per (very long tile, pass) and chunk
-    size_t prog_words = 0;
+    // (the int32 pass reuses the buffer after the s16 pass: same stream order, cleared in between)
+    size_t prog_words = 0, prog_words1 = 0;
     if (!g0.empty() && g0[0].split)
         for (size_t c = 0; c < qp0.chunks.size(); ++c)
-            prog_words += (size_t)g0[0].ntiles * swb_split_passes(qp0.chunks[c].rows);
-    if (prog_words) CU(GROW_DEV(s.d_prog, s.prog_cap, sizeof(uint32_t) * prog_words));
+            prog_words += swb_split_items(qp0.chunks[c].rows, g0[0], nullptr);
+    if (need_i32[0] && !g1[0].empty() && g1[0][0].split)
+        for (size_t c = 0; c < qp1[0].chunks.size(); ++c)
+            prog_words1 += swb_split_items(qp1[0].chunks[c].rows, g1[0][0], nullptr);
+    if (std::max(prog_words, prog_words1))
+        CU(GROW_DEV(s.d_prog, s.prog_cap, sizeof(uint32_t) * std::max(prog_words, prog_words1)));
 
     memcpy(s.h_query, q, qlen);
     if (pair) memcpy(s.h_query + qlen, q2, qlen2);
@@ -749,6 +767,11 @@ static int enqueue_job(swb_engine *e, Slot &s, uint32_t qi, const uint8_t *q, ui
         p.scores2 = nullptr;
         p.bnd = s.d_bnd32;
         p.only_flagged = 1;
+        if (!g1[k].empty() && g1[k][0].split) {  // pipelined work items combine their scores with atomicMax
+            CU(cudaMemsetAsync(s.d_prog, 0, sizeof(uint32_t) * prog_words1, s.stream));
+            CU(swb_launch_clear_flagged(e->d_tiles, (uint32_t)pl.tiles.size(), s.d_flags, p.scores, s.stream));
+            e->stats.kernel_launches += 1;
+        }
         if ((rc = enqueue_pass(e, s, mode1, p, qp1[k], g1[k], counter)) != SWB_OK) return rc;
     }
     CU(swb_launch_scatter(s.d_sorted, e->d_out_pos, nl, out, s.stream));

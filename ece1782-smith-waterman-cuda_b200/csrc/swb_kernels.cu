@@ -85,13 +85,16 @@ __global__ void __launch_bounds__(NT, MINB) swb_score_kernel(const SwbScoreParam
     // consecutive code rows start one bank apart
     const uint32_t esz = V::qpair ? 4u : 1u;
     const uint32_t sstride = V::qpair ? (p.smem_rows + 1u) * 4u : p.smem_rows + 4u;
-    const uint32_t wpr = SPLIT ? 0u : (p.smem_rows * esz) >> 2;  // words per code row (SPLIT stages per work item)
-    for (uint32_t i = threadIdx.x; i < wpr * SWB_ALPHA; i += NT) {
-        const uint32_t code = i / wpr, w = i - code * wpr;
-        reinterpret_cast<uint32_t *>(sprof + (size_t)code * sstride)[w] = __ldg(
-            reinterpret_cast<const uint32_t *>(p.profile + ((size_t)code * p.prof_stride + p.row0) * esz) + w);
+    if (!SPLIT) {  // SPLIT launches stage the rows of one pass per work item (swb_warp_loop)
+        const uint32_t wpr = (p.smem_rows * esz) >> 2;  // words per code row
+        for (uint32_t i = threadIdx.x; i < wpr * SWB_ALPHA; i += NT) {
+            const uint32_t code = i / wpr, w = i - code * wpr;
+            reinterpret_cast<uint32_t *>(sprof + (size_t)code * sstride)[w] = __ldg(
+                reinterpret_cast<const uint32_t *>(p.profile + ((size_t)code * p.prof_stride + p.row0) * esz) + w);
+        }
+        __syncthreads();
     }
-    __syncthreads();
+    if (p.warps_active && (threadIdx.x >> 5) >= p.warps_active) return;
     DevBackend be;
     swb_warp_loop<K, V, SPLIT>(be, p, sprof, sstride);
 }
@@ -149,6 +152,20 @@ __global__ void swb_scatter_kernel(const int32_t *__restrict__ sorted, const uin
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[dst[i]] = sorted[i];
+}
+
+// scores of the flagged tiles back to 0 before the int32 pass: its pipelined work items combine with atomicMax, and what
+// the s16 pass left there may be larger than the true score (wrapped values)
+__global__ void swb_clear_flagged_kernel(const SwbTile *__restrict__ tiles, uint32_t ntiles,
+                                         const uint8_t *__restrict__ flags, int32_t *__restrict__ scores)
+{
+    const uint32_t ti = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ti >= ntiles || !flags[ti]) return;
+    const SwbTile t = tiles[ti];
+    for (uint32_t s = 0; s < t.npairs; ++s) {
+        scores[2 * ((size_t)t.first_pair + s)] = 0;
+        scores[2 * ((size_t)t.first_pair + s) + 1] = 0;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -211,8 +228,11 @@ static cudaError_t dispatch(int op, int K, int mode, bool split, int block_cfg, 
         }
         return cudaErrorInvalidValue;
     }
-    if (split) {  // pipelined passes: s16 only, K = 8, one warp per block
-        if (i32 || K != 8) return cudaErrorInvalidValue;
+    if (split) {  // pipelined passes: K = 8, one warp per block
+        if (K != 8) return cudaErrorInvalidValue;
+        if (i32)
+            return op == 0 ? launch_one<8, V32, 32, 8, true>(*p, grid, smem, st)
+                           : occ_one<8, V32, 32, 8, true>(smem, blocks);
         return op == 0 ? launch_one<8, V16, 32, 8, true>(*p, grid, smem, st) : occ_one<8, V16, 32, 8, true>(smem, blocks);
     }
     if (!i32) {
@@ -239,6 +259,14 @@ cudaError_t swb_launch_score(int K, int mode, bool split, int block_cfg, const S
 cudaError_t swb_score_occupancy(int K, int mode, bool split, int block_cfg, size_t smem, int *blocks)
 {
     return dispatch(1, K, mode, split, block_cfg, nullptr, 0, smem, nullptr, blocks);
+}
+
+cudaError_t swb_launch_clear_flagged(const SwbTile *tiles, uint32_t ntiles, const uint8_t *flags, int32_t *scores,
+                                     cudaStream_t st)
+{
+    if (!ntiles) return cudaSuccess;
+    swb_clear_flagged_kernel<<<(ntiles + 255) / 256, 256, 0, st>>>(tiles, ntiles, flags, scores);
+    return cudaGetLastError();
 }
 
 cudaError_t swb_launch_profile2(const uint8_t *qa, uint32_t la, const uint8_t *qb, uint32_t lb, const int8_t *mat,

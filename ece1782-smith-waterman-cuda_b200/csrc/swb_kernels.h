@@ -19,9 +19,12 @@
 #define SWB_MODE_I32A 4   // V32A: affine gaps, exact recompute (K = 8)
 
 // K: query rows per lane (8, 16, 32; int32 pass 8 or 16). split: the passes of a tile are separate, pipelined work
-// items (very long sequences; SWB_MODE_S16, K = 8 only).
+// items (very long sequences; SWB_MODE_S16 and SWB_MODE_I32, K = 8 only).
 cudaError_t swb_launch_score(int K, int mode, bool split, int block_cfg, const SwbScoreParams &p, int grid, size_t smem,
                              cudaStream_t st);
+// zeroes the scores of every flagged tile (before an int32 pass with pipelined work items)
+cudaError_t swb_launch_clear_flagged(const SwbTile *tiles, uint32_t ntiles, const uint8_t *flags, int32_t *scores,
+                                     cudaStream_t st);
 cudaError_t swb_score_occupancy(int K, int mode, bool split, int block_cfg, size_t smem, int *blocks_per_sm);
 cudaError_t swb_launch_profile2(const uint8_t *qa, uint32_t la, const uint8_t *qb, uint32_t lb, const int8_t *mat,
                                 int gap, uint32_t *prof, uint32_t stride, uint32_t rows, cudaStream_t st);

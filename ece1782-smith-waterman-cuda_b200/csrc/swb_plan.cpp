@@ -116,9 +116,17 @@ int swb_build_plan(const uint64_t *offsets, uint32_t n, uint32_t shard, uint32_t
             plan.tile_start_by_logg[l] = at;
             at += plan.tiles_by_logg[l];
         }
+        // tiles are in descending width over the lane-group sizes, so "wider than xl_len" is a prefix of the array
         plan.n_xl = 0;
-        if (o.xl_len)
-            while (plan.n_xl < plan.tiles_by_logg[SWB_MAX_LOGG] && plan.tiles[plan.n_xl].width > o.xl_len) ++plan.n_xl;
+        memset(plan.xl_by_logg, 0, sizeof plan.xl_by_logg);
+        for (int l = SWB_MAX_LOGG; l >= 1 && o.xl_len; --l) {
+            const uint32_t s0 = plan.tile_start_by_logg[l];
+            uint32_t k = 0;
+            while (k < plan.tiles_by_logg[l] && plan.tiles[s0 + k].width > o.xl_len) ++k;
+            plan.xl_by_logg[l] = k;
+            plan.n_xl += k;
+            if (k < plan.tiles_by_logg[l]) break;
+        }
     }
     uint64_t res = 0, bnd = 0;
     for (size_t i = 0; i < plan.tiles.size(); ++i) {
@@ -192,7 +200,7 @@ void swb_plan_launch_groups(const SwbPlan &plan, const SwbQueryPlan &qp, bool lo
         uint32_t nr = 0;
         for (int l = SWB_MAX_LOGG; l >= 0; --l) {
             if (!plan.tiles_by_logg[l] || qp.k_by_logg[l] != K) continue;
-            const uint32_t skip = l == SWB_MAX_LOGG ? n_xl : 0;  // the very long tiles go to the split group
+            const uint32_t skip = n_xl ? plan.xl_by_logg[l] : 0;  // the long tiles go to the split group
             if (plan.tiles_by_logg[l] == skip) continue;
             g.logg_mask |= 1u << l;
             g.range_start[nr] = plan.tile_start_by_logg[l] + skip;
@@ -216,7 +224,10 @@ void swb_plan_launch_groups(const SwbPlan &plan, const SwbQueryPlan &qp, bool lo
         memset(&g, 0, sizeof g);
         g.K = 8;
         g.split = true;
-        g.logg_mask = 1u << SWB_MAX_LOGG;
+        for (int l = 1; l <= SWB_MAX_LOGG; ++l) {
+            g.xl_by_logg[l] = plan.xl_by_logg[l];
+            if (g.xl_by_logg[l]) g.logg_mask |= 1u << l;
+        }
         g.ntiles = n_xl;
         for (uint32_t r = 0; r < SWB_MAX_RANGES; ++r) g.range_cum[r] = n_xl;
         groups.insert(groups.begin(), g);
@@ -228,6 +239,22 @@ void swb_plan_launch_groups(const SwbPlan &plan, const SwbQueryPlan &qp, bool lo
     else
         std::stable_sort(first, groups.end(),
                          [](const SwbLaunchGroup &a, const SwbLaunchGroup &b) { return a.ntiles > b.ntiles; });
+}
+
+uint32_t swb_split_items(uint32_t rows, const SwbLaunchGroup &g, SwbScoreParams *p)
+{
+    uint32_t tiles = 0, items = 0;
+    for (int j = 0; j < SWB_MAX_LOGG; ++j) {
+        const int l = SWB_MAX_LOGG - j;
+        tiles += g.xl_by_logg[l];
+        items += g.xl_by_logg[l] * swb_split_passes(rows, l);
+        if (p) {
+            p->split_tile_end[j] = tiles;
+            p->split_item_end[j] = items;
+        }
+    }
+    if (p) p->ntiles = items;
+    return items;
 }
 
 uint32_t swb_group_smem_rows(uint32_t rows, const SwbLaunchGroup &g)

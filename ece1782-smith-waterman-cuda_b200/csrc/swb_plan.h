@@ -8,8 +8,9 @@
 struct SwbPlanOpts {
     uint32_t group_len;   // sequences up to this length run one lane per pair (G=1); each doubling of the
                           // length doubles G up to 32
-    uint32_t xl_len;      // 32-lane tiles wider than this run their passes as pipelined work items (0 = never)
-    SwbPlanOpts() : group_len(384), xl_len(8192) {}
+    uint32_t xl_len;      // lane-group tiles wider than this can run their passes as pipelined work items (the
+                          // engine decides per query whether they do); 0 = never
+    SwbPlanOpts() : group_len(384), xl_len(3072) {}
 };
 
 struct SwbPlan {
@@ -31,7 +32,8 @@ struct SwbPlan {
     uint32_t max_len;                 // longest sequence of the shard
     uint32_t tiles_by_logg[SWB_MAX_LOGG + 1];
     uint32_t tile_start_by_logg[SWB_MAX_LOGG + 1];  // tiles are stored by group size, 32 lanes first
-    uint32_t n_xl;                    // leading 32-lane tiles wider than xl_len (the very long sequences)
+    uint32_t n_xl;                    // leading tiles wider than xl_len (lane-group tiles only: the long sequences)
+    uint32_t xl_by_logg[SWB_MAX_LOGG + 1];  // of which per group size (a prefix of each group size's tiles)
     uint64_t cols_by_logg[SWB_MAX_LOGG + 1];  // padded sequence-columns (width * slots * 2) per group size
 };
 
@@ -61,7 +63,8 @@ void swb_plan_query(uint32_t qlen, int k_force, int k_max, uint32_t logg_present
 // One score-kernel launch of a query pass: the tiles of all group sizes that share the same K.
 struct SwbLaunchGroup {
     int K;
-    bool split;          // pipelined passes over the plan's n_xl leading tiles (K = 8, s16 only)
+    bool split;          // pipelined passes over the plan's n_xl leading tiles (K = 8)
+    uint32_t xl_by_logg[SWB_MAX_LOGG + 1];  // split group: its tiles per group size
     uint32_t logg_mask;
     uint32_t ntiles;
     uint32_t range_start[SWB_MAX_RANGES];
@@ -72,7 +75,9 @@ struct SwbLaunchGroup {
 // with_split: give the very long tiles their own pipelined group (s16 pass); otherwise they stay in the 32-lane range
 void swb_plan_launch_groups(const SwbPlan &plan, const SwbQueryPlan &qp, bool longest_first, bool with_split,
                             std::vector<SwbLaunchGroup> &groups);
-// passes (work items per tile) of a split group for a chunk of `rows` query rows
-inline uint32_t swb_split_passes(uint32_t rows) { return (rows + 255u) / 256u; }
+// split group: passes (work items) of a tile of 1 << l lanes per pair for a chunk of `rows` query rows (K = 8)
+inline uint32_t swb_split_passes(uint32_t rows, int l) { return (rows + (8u << l) - 1u) / (8u << l); }
+// work items of a split group for such a chunk; with p != NULL also fills p->ntiles and the class tables
+uint32_t swb_split_items(uint32_t rows, const SwbLaunchGroup &g, SwbScoreParams *p);
 // rows a launch group must find in shared memory for a chunk of `rows` query rows (multiple of 128)
 uint32_t swb_group_smem_rows(uint32_t rows, const SwbLaunchGroup &g);

@@ -53,9 +53,13 @@ struct SwbScoreParams {
     // tiles of this launch: positions [0, ntiles) of the concatenation of up to SWB_MAX_RANGES ranges of `tiles`
     uint32_t range_start[SWB_MAX_RANGES];
     uint32_t range_cum[SWB_MAX_RANGES];  // cumulative tile count up to and including range r
-    // SPLIT launches (very long sequences): ntiles counts (tile, pass) items of range 0, split_passes per tile
-    uint32_t split_passes;
-    uint32_t *prog;           // [tiles of range 0][split_passes] columns published by each pass (zeroed per query)
+    // SPLIT launches (long sequences): ntiles counts (tile, pass) items, handed out tile by tile, pass by pass;
+    // the split set is the leading tiles of the array; classes run from 32 lanes per pair (j = 0) down to 2 (j = 4):
+    // tiles [split_tile_end[j-1], split_tile_end[j]) belong to class j and own ceil(rows / (K << (5 - j))) items each
+    uint32_t split_tile_end[SWB_MAX_LOGG];
+    uint32_t split_item_end[SWB_MAX_LOGG];
+    uint32_t warps_active;    // warps of a block that take work (0 = all): a launch with few tiles spreads them over the SMs
+    uint32_t *prog;           // [item] columns of its bottom row that a pass has published (zeroed per query)
 };
 
 SWB_HD uint32_t swb_roundup(uint32_t v, uint32_t m) { return (v + m - 1) / m * m; }

@@ -561,7 +561,12 @@ SWB_HD void swb_run_tile(BE &be, const SwbScoreParams &p, const SwbTile &tile, u
 #pragma unroll
                     for (int u = 0; u < 4; ++u)
                         if (col0 + u >= 0 && col0 + u < (int32_t)W) V::st(be, dst + u, outb[u]);
-                    if (SPLIT && ((c & 15u) == 15u || c + 1 == nsteps4)) {
+                }
+                if (SPLIT && ((c & 15u) == 15u || c + 1 == nsteps4)) {
+                    // every slot's last lane has stored its columns: one lane publishes for the warp
+                    be.syncwarp();
+                    if (lane == 31) {
+                        const int32_t col0 = (int32_t)(c * 4u) - (G - 1);
                         const int32_t done = col0 + 4 < 0 ? 0 : (col0 + 4 > (int32_t)W ? (int32_t)W : col0 + 4);
                         be.publish(prog + ss, (uint32_t)done);
                     }
@@ -609,7 +614,7 @@ SWB_HD void swb_run_tile(BE &be, const SwbScoreParams &p, const SwbTile &tile, u
     }
     if (V::is16) {
         if (be.any(flagged) && lane == 0) p.flags[tile_idx] = 1;
-    } else if (p.recount && p.last_chunk && lane == 0) {
+    } else if (p.recount && p.last_chunk && (!SPLIT || ss_end == nsuper) && lane == 0) {
         be.count(p.recount);
     }
 }
@@ -625,13 +630,26 @@ SWB_HD void swb_warp_loop(BE &be, const SwbScoreParams &p, const int8_t *sprof, 
         const uint32_t v = be.next_tile(p.counter);
         if (v >= p.ntiles) break;
         if (SPLIT) {
-            // one warp per block; it stages only the K * 32 profile rows of its pass (sstride = K * 32 + 4)
-            const uint32_t t = v / p.split_passes, ss = v - t * p.split_passes;
-            const uint32_t ti = p.range_start[0] + t;
+            // one warp per block; it stages only the K << logG profile rows of its pass (sstride = K * 32 + 4).
+            // Item -> (tile, pass): the split set is the head of the tile array, one class per lane-group size
+            int l = SWB_MAX_LOGG;
+            uint32_t tile0 = 0, item0 = 0;
+#pragma unroll
+            for (int j = 0; j + 1 < SWB_MAX_LOGG; ++j)
+                if (v >= p.split_item_end[j]) {
+                    l = SWB_MAX_LOGG - 1 - j;
+                    tile0 = p.split_tile_end[j];
+                    item0 = p.split_item_end[j];
+                }
+            const uint32_t rows_per_pass = (uint32_t)K << l;
+            const uint32_t passes = (p.rows + rows_per_pass - 1u) / rows_per_pass;
+            const uint32_t t = (v - item0) / passes, ss = (v - item0) - t * passes;
+            const uint32_t ti = tile0 + t;
+            if (p.only_flagged && !be.ld_flag(p.flags + ti)) continue;  // every pass of the tile skips alike
             const SwbTile tile = be.ld_tile(p.tiles + ti);
-            be.stage_rows(const_cast<int8_t *>(sprof), sstride, p.profile, p.prof_stride, p.row0 + ss * (uint32_t)(K * 32),
-                          (uint32_t)(K * 32));
-            swb_run_tile<K, V, true, true>(be, p, tile, ti, sprof, sstride, ss, 1u, p.prog + (size_t)t * p.split_passes,
+            be.stage_rows(const_cast<int8_t *>(sprof), sstride, p.profile, p.prof_stride, p.row0 + ss * rows_per_pass,
+                          rows_per_pass);
+            swb_run_tile<K, V, true, true>(be, p, tile, ti, sprof, sstride, ss, 1u, p.prog + item0 + (size_t)t * passes,
                                            ss);
             continue;
         }

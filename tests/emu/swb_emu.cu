@@ -169,7 +169,8 @@ void lane_main(HostBackend &be, void *a)
 {
     const LaneArgs *la = static_cast<const LaneArgs *>(a);
     if (la->split) {
-        swb_warp_loop<8, V16, true>(be, *la->p, la->sprof, la->sstride);
+        if (la->mode == 1) swb_warp_loop<8, V32, true>(be, *la->p, la->sprof, la->sstride);
+        else swb_warp_loop<8, V16, true>(be, *la->p, la->sprof, la->sstride);
     } else if (la->mode == 2) {
         if (la->K == 8) swb_warp_loop<8, V16Q, false>(be, *la->p, la->sprof, la->sstride);
         else if (la->K == 16) swb_warp_loop<16, V16Q, false>(be, *la->p, la->sprof, la->sstride);
@@ -216,9 +217,8 @@ void run_pass(SwbScoreParams &p, int mode, const SwbQueryPlan &qp, const std::ve
         }
         for (size_t c = 0; c < qp.chunks.size(); ++c) {
             const SwbQueryChunk &ch = qp.chunks[c];
-            p.split_passes = g.split ? swb_split_passes(ch.rows) : 0;
-            p.ntiles = g.split ? g.ntiles * p.split_passes : (mode == 2 ? 2 * g.ntiles : g.ntiles);
-            std::vector<uint32_t> prog((size_t)g.ntiles * p.split_passes + 1, 0u);
+            p.ntiles = mode == 2 ? 2 * g.ntiles : g.ntiles;
+            std::vector<uint32_t> prog((g.split ? swb_split_items(ch.rows, g, &p) : 0u) + 1u, 0u);
             p.prog = prog.data();
             p.row0 = ch.row0;
             p.rows = ch.rows;
@@ -356,7 +356,14 @@ static int emu_search(const uint8_t *codes, const uint64_t *offsets, uint32_t n,
         SwbQueryPlan qp1;
         std::vector<SwbLaunchGroup> g1;
         swb_plan_query(qls[k], K, affine ? 8 : 16, present, chunk_rows, qp1);
-        swb_plan_launch_groups(pl, qp1, true, false, g1);
+        swb_plan_launch_groups(pl, qp1, true, !pair && !affine, g1);
+        if (!g1.empty() && g1[0].split) {  // swb_clear_flagged_kernel
+            int32_t *sc = k ? sorted2.data() : sorted.data();
+            for (size_t ti = 0; ti < pl.tiles.size(); ++ti)
+                if (flags[ti])
+                    for (uint32_t sl = 0; sl < pl.tiles[ti].npairs; ++sl)
+                        sc[2 * ((size_t)pl.tiles[ti].first_pair + sl)] = sc[2 * ((size_t)pl.tiles[ti].first_pair + sl) + 1] = 0;
+        }
         std::vector<uint8_t> prof;
         const uint32_t stride = swb_roundup(qp1.prof_rows, 16);
         build_prof8(qs[k], qls[k], qp1.prof_rows, stride, prof);

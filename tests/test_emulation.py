@@ -155,6 +155,13 @@ def test_pipelined_passes_of_very_long_tiles(emu, oracle):
     want = oracle.scan(w, c2, o2, m)
     got, rc = emu(c2, o2, m, w, K=0, group_len=16, xl_len=500)
     assert want[0] == 34500 and np.array_equal(got, want) and rc >= 1
+    # the int32 recompute of split tiles is pipelined too (scores cleared first, combined with atomicMax): a low
+    # threshold sends nearly every tile through it, over several query chunks; force_i32 runs it alone
+    want = oracle.scan(q, codes, offs, m)
+    got, rc = emu(codes, offs, m, q, K=0, group_len=16, xl_len=500, chunk_rows=1024, thr=40)
+    assert np.array_equal(got, want) and rc >= 3
+    got, _ = emu(codes, offs, m, q, K=0, group_len=16, xl_len=300, force_i32=1)
+    assert np.array_equal(got, want)
 
 
 def test_query_pair_jobs(emu, oracle, subset, queries):
@@ -232,21 +239,26 @@ def test_affine_subset(emu_affine, oracle, subset, queries, go, ge, K, group_len
 
 def test_affine_chunks_recompute_and_overflow(emu_affine, oracle, subset, queries):
     m = oracle.matrix("blosum50")
-    q = oracle.encode(queries["P04775"])
-    want = oracle.scan_affine(q, subset["codes"], subset["offsets"], m, 10, 2)
-    got, rc = emu_affine(subset["codes"], subset["offsets"], m, q, 10, 2, chunk_rows=1024)
+    q = oracle.encode(queries["P04775"])[:1100]  # two chunks of 1024 rows
+    n = 36  # the first 36 sequences of the subset keep the emulation short
+    offs = subset["offsets"][:n + 1]
+    codes = subset["codes"][:int(offs[-1])]
+    want = oracle.scan_affine(q, codes, offs, m, 10, 2)
+    got, rc = emu_affine(codes, offs, m, q, 10, 2, chunk_rows=1024)
     assert np.array_equal(got, want) and rc == 0
-    got, rc = emu_affine(subset["codes"], subset["offsets"], m, q, 10, 2, chunk_rows=1024, thr=60, group_len=128)
+    got, rc = emu_affine(codes, offs, m, q, 10, 2, chunk_rows=1024, thr=60, group_len=128)
     assert np.array_equal(got, want) and rc >= 1
-    got, rc = emu_affine(subset["codes"], subset["offsets"], m, q, 10, 2, force_i32=1, group_len=64)
+    got, rc = emu_affine(codes, offs, m, q, 10, 2, force_i32=1, group_len=64)
     assert np.array_equal(got, want)
-    # a real s16 overflow
-    w = np.full(2300, 17, dtype=np.uint8)
+    # a real s16 overflow (a matrix with W:W = 100 gets there with a short sequence; the GPU test uses BLOSUM50)
+    m2 = m.copy()
+    m2[17, 17] = 100
+    w = np.full(400, 17, dtype=np.uint8)
     rng = np.random.default_rng(2)
-    codes, offs = pack_db([w, rng.integers(0, 20, 300).astype(np.uint8), w[:2200].copy()])
-    want = oracle.scan_affine(w, codes, offs, m, 10, 2)
-    assert want[0] == 34500
-    got, rc = emu_affine(codes, offs, m, w, 10, 2)
+    codes, offs = pack_db([w, rng.integers(0, 20, 300).astype(np.uint8), w[:390].copy()])
+    want = oracle.scan_affine(w, codes, offs, m2, 10, 2)
+    assert want[0] == 40000 and want[2] == 39000
+    got, rc = emu_affine(codes, offs, m2, w, 10, 2)
     assert np.array_equal(got, want) and rc >= 1
 
 

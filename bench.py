@@ -259,6 +259,7 @@ def main():
     ap.add_argument("--batch-order", type=int, default=-1, help="0 longest query first (default), 1 as given")
     ap.add_argument("--chunk-rows", type=int, default=0)
     ap.add_argument("--xl-len", type=int, default=0)
+    ap.add_argument("--split-fill", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--affine", default="", help="GO,GE: affine gaps instead of the reference's linear gap 2 (a side "
                     "measurement of the V16A kernels; not the headline metric, no CPU leg)")
@@ -312,6 +313,8 @@ def main():
         opts["chunk_rows"] = args.chunk_rows
     if args.xl_len:
         opts["xl_len"] = args.xl_len
+    if args.split_fill:
+        opts["split_fill"] = args.split_fill
     eng = swb.Engine(local, **opts)
     stream = torch.cuda.current_stream()
     eng.set_stream(stream.cuda_stream)

@@ -86,6 +86,7 @@ struct swb_engine {
     // options
     SwbPlanOpts plan_opts;
     int opt_k = 0;
+    int opt_split_fill = 0;   // work items a split launch must keep before its K goes up from 8 (0 = K stays 8)
     int opt_batch_order = 0;  // batches: 0 = longest query first, 1 = in the caller's order
     int opt_pair_queries = 0; // batches: pack two queries into the halves of the s16x2 lanes (V16Q). Opt-in: measured
                               // 0.77x of V16 on B200 (4 B of profile per packed cell: shared-memory bound)
@@ -311,6 +312,9 @@ extern "C" int swb_set_option(swb_engine *e, const char *key, int64_t value)
     } else if (!strcmp(key, "xl_len")) {
         if (value < 0 || value > (1ll << 31)) return fail(e, SWB_ERR_ARG, "xl_len out of range");
         e->plan_opts.xl_len = (uint32_t)value;
+    } else if (!strcmp(key, "split_fill")) {
+        if (value < 0 || value > (1 << 30)) return fail(e, SWB_ERR_ARG, "split_fill out of range");
+        e->opt_split_fill = (int)value;
     } else if (!strcmp(key, "batch_order")) {
         if (value < 0 || value > 1) return fail(e, SWB_ERR_ARG, "batch_order must be 0 (longest query first) or 1 (as given)");
         e->opt_batch_order = (int)value;
@@ -536,7 +540,8 @@ struct LaunchShape {
 
 static int shape_for(swb_engine *e, int K, int mode, bool split, uint32_t smem_rows, uint32_t ntiles, LaunchShape &ls)
 {
-    if (split) smem_rows = (uint32_t)K * 32u;  // a split launch stages one pass per work item
+    const bool per_item = split && K == 8;  // one warp per block, each work item stages the rows of its pass
+    if (per_item) smem_rows = (uint32_t)K * 32u;
     ls.smem_rows = smem_rows;
     ls.smem = mode == SWB_MODE_QPAIR ? (size_t)SWB_ALPHA * (smem_rows + 1) * 4 : (size_t)SWB_ALPHA * (smem_rows + 4);
     if (ls.smem > e->smem_optin) return fail(e, SWB_ERR_ARG, "internal: query chunk does not fit shared memory");
@@ -544,7 +549,7 @@ static int shape_for(swb_engine *e, int K, int mode, bool split, uint32_t smem_r
     int per_sm = 0;
     CU(swb_score_occupancy(K, mode, split, ls.block_cfg, ls.smem, &per_sm));
     if (per_sm < 1) return fail(e, SWB_ERR_CUDA, "score kernel does not fit on an SM");
-    const int nt = split ? 32 : (ls.block_cfg == SWB_BLOCK_SMALL ? SWB_NT_SMALL : SWB_NT_LARGE);
+    const int nt = per_item ? 32 : (ls.block_cfg == SWB_BLOCK_SMALL ? SWB_NT_SMALL : SWB_NT_LARGE);
     const int need = (int)((ntiles + nt / 32 - 1) / (nt / 32));
     const int slots = per_sm * e->sm_count;
     ls.grid = std::max(1, std::min(slots, need));
@@ -552,7 +557,7 @@ static int shape_for(swb_engine *e, int K, int mode, bool split, uint32_t smem_r
     // A lone query whose launch has fewer tiles than the GPU has warps: one tile per warp packed into full blocks would
     // put 16 long-running warps on a few SMs and leave the others empty. Spread them: more blocks, fewer active warps
     // each. (Not for batches: there other queries fill the SMs, and half-empty blocks would only hold shared memory.)
-    if (!split && e->cur_nq <= 1 && need < slots) {
+    if (!per_item && e->cur_nq <= 1 && need < slots) {
         const uint32_t wpb = std::max<uint32_t>(1u, (ntiles + (uint32_t)slots - 1u) / (uint32_t)slots);
         if (wpb < (uint32_t)(nt / 32)) {
             ls.warps_active = wpb;
@@ -617,6 +622,7 @@ static int enqueue_pass(swb_engine *e, Slot &s, int mode, SwbScoreParams &p, con
             p.rows = ch.rows;
             p.smem_rows = ls.smem_rows;
             p.warps_active = ls.warps_active;
+            p.split_stage_item = g.split && g.K == 8;
             p.first_chunk = ch.first;
             p.last_chunk = ch.last;
             p.counter = s.d_counters + counter++;
@@ -662,16 +668,25 @@ static int enqueue_job(swb_engine *e, Slot &s, uint32_t qi, const uint8_t *q, ui
 
     const bool small_shard = pl.tiles.size() < 2u * (size_t)e->sm_count * (SWB_NT_LARGE / 32);
     // batches on small shards: 2048-row launches keep the shared-memory footprint of a block small, so blocks of several
-    // queries share an SM and fill each other's tails (+1..2 % at 1/8 and 1/4 of Swiss-Prot per GPU)
-    const uint32_t chunk_rows = !e->chunk_rows_set && small_shard && e->cur_nq > 1 ? 2048u : e->chunk_rows;
+    // queries share an SM and fill each other's tails (+1..2 % at 1/8 and 1/4 of Swiss-Prot per GPU); queries beyond one
+    // chunk keep the long chunks (several short launches in a row cost the titin-scale workload a factor of two)
+    const uint32_t chunk_rows =
+        !e->chunk_rows_set && small_shard && e->cur_nq > 1 && rows <= e->chunk_rows ? 2048u : e->chunk_rows;
     const bool split = !pair && !affine && (e->opt_split == 1 || (e->opt_split < 0 && small_shard));
 
     // pass 0: the s16 pass over all tiles
     SwbQueryPlan qp0;
     std::vector<SwbLaunchGroup> g0;
     // affine lanes carry (H, E) per row, so their strips stop at 16 rows (s16) / 8 rows (int32)
-    swb_plan_query(rows, e->opt_k, affine ? 16 : 32, present, pair ? SWB_CHUNK_ROWS_QPAIR : chunk_rows, qp0);
-    swb_plan_launch_groups(pl, qp0, longest_first, split, g0);
+    // rows per lane of the split groups: 8 (most passes in flight per tile). Option split_fill = N lets K grow to 16 / 32
+    // while a launch keeps N work items; measured slower on the titin-scale workload at every N (2,370 GCUPS with K = 8,
+    // 1,834 / 1,474 with K = 16 / 32), so it is off by default
+    const uint32_t fill = (uint32_t)e->opt_split_fill;
+    const int split_l = split && fill ? swb_plan_split_max_logg(pl) : -1;
+    const int sk0 = split_l > 0 ? swb_plan_split_k(pl, std::min(rows, chunk_rows), 32, fill) : 8;
+    swb_plan_query(rows, e->opt_k, affine ? 16 : 32, present, pair ? SWB_CHUNK_ROWS_QPAIR : chunk_rows, qp0,
+                   sk0 > 8 ? (uint32_t)sk0 << split_l : 0u);
+    swb_plan_launch_groups(pl, qp0, longest_first, split, g0, sk0);
     // int32 passes over flagged tiles, one per query, only when a score can exceed the s16 range at all
     const uint32_t qlens[2] = {qlen, pair ? qlen2 : 0u};
     bool need_i32[2];
@@ -682,8 +697,10 @@ static int enqueue_job(swb_engine *e, Slot &s, uint32_t qi, const uint8_t *q, ui
     for (int k = 0; k < 2; ++k) {
         need_i32[k] = qlens[k] > 0 && (int64_t)e->max_s * std::min<uint32_t>(qlens[k], pl.max_len) > ovf_thr;
         if (!need_i32[k]) continue;
-        swb_plan_query(qlens[k], e->opt_k, affine ? 8 : 16, present, chunk_rows, qp1[k]);
-        swb_plan_launch_groups(pl, qp1[k], longest_first, split, g1[k]);
+        const int sk1 = split_l > 0 ? swb_plan_split_k(pl, std::min(qlens[k], chunk_rows), 16, fill) : 8;
+        swb_plan_query(qlens[k], e->opt_k, affine ? 8 : 16, present, chunk_rows, qp1[k],
+                       sk1 > 8 ? (uint32_t)sk1 << split_l : 0u);
+        swb_plan_launch_groups(pl, qp1[k], longest_first, split, g1[k], sk1);
         nlaunch += g1[k].size() * qp1[k].chunks.size();
         prof8_rows = std::max(prof8_rows, qp1[k].prof_rows);
     }

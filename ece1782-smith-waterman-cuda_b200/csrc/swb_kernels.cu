@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(NT, MINB) swb_score_kernel(const SwbScoreParam
     // consecutive code rows start one bank apart
     const uint32_t esz = V::qpair ? 4u : 1u;
     const uint32_t sstride = V::qpair ? (p.smem_rows + 1u) * 4u : p.smem_rows + 4u;
-    if (!SPLIT) {  // SPLIT launches stage the rows of one pass per work item (swb_warp_loop)
+    if (!SPLIT || !p.split_stage_item) {  // else every work item stages the rows of its pass (swb_warp_loop)
         const uint32_t wpr = (p.smem_rows * esz) >> 2;  // words per code row
         for (uint32_t i = threadIdx.x; i < wpr * SWB_ALPHA; i += NT) {
             const uint32_t code = i / wpr, w = i - code * wpr;
@@ -228,12 +228,21 @@ static cudaError_t dispatch(int op, int K, int mode, bool split, int block_cfg, 
         }
         return cudaErrorInvalidValue;
     }
-    if (split) {  // pipelined passes: K = 8, one warp per block
-        if (K != 8) return cudaErrorInvalidValue;
-        if (i32)
-            return op == 0 ? launch_one<8, V32, 32, 8, true>(*p, grid, smem, st)
-                           : occ_one<8, V32, 32, 8, true>(smem, blocks);
-        return op == 0 ? launch_one<8, V16, 32, 8, true>(*p, grid, smem, st) : occ_one<8, V16, 32, 8, true>(smem, blocks);
+    if (split) {  // pipelined passes. K = 8: one warp per block, the rows of a pass staged per work item
+        if (K == 8) {
+            if (i32)
+                return op == 0 ? launch_one<8, V32, 32, 8, true>(*p, grid, smem, st)
+                               : occ_one<8, V32, 32, 8, true>(smem, blocks);
+            return op == 0 ? launch_one<8, V16, 32, 8, true>(*p, grid, smem, st)
+                           : occ_one<8, V16, 32, 8, true>(smem, blocks);
+        }
+        // K = 16 / 32: full blocks over the staged chunk, for launches with enough work items to fill the GPU
+        if (i32) return K == 16 ? dispatch_cfg<16, V32, true>(op, block_cfg, p, grid, smem, st, blocks) : cudaErrorInvalidValue;
+        switch (K) {
+        case 16: return dispatch_cfg<16, V16, true>(op, block_cfg, p, grid, smem, st, blocks);
+        case 32: return dispatch_cfg<32, V16, true>(op, block_cfg, p, grid, smem, st, blocks);
+        }
+        return cudaErrorInvalidValue;
     }
     if (!i32) {
         switch (K) {

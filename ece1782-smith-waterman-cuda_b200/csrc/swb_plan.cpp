@@ -145,7 +145,7 @@ int swb_build_plan(const uint64_t *offsets, uint32_t n, uint32_t shard, uint32_t
 }
 
 void swb_plan_query(uint32_t qlen, int k_force, int k_max, uint32_t logg_present, uint32_t chunk_rows,
-                    SwbQueryPlan &qp)
+                    SwbQueryPlan &qp, uint32_t extra_multiple)
 {
     qp.chunks.clear();
     qp.prof_rows = 0;
@@ -177,7 +177,7 @@ void swb_plan_query(uint32_t qlen, int k_force, int k_max, uint32_t logg_present
         SwbQueryChunk ch;
         ch.row0 = c * chunk_rows;
         ch.rows = std::min(chunk_rows, qlen - ch.row0);
-        uint32_t need = ch.rows;
+        uint32_t need = extra_multiple ? swb_roundup(ch.rows, extra_multiple) : ch.rows;
         for (int l = 0; l <= SWB_MAX_LOGG; ++l)
             if (logg_present & (1u << l)) need = std::max(need, swb_roundup(ch.rows, (uint32_t)qp.k_by_logg[l] << l));
         ch.smem_rows = swb_roundup(need, 128);
@@ -188,8 +188,25 @@ void swb_plan_query(uint32_t qlen, int k_force, int k_max, uint32_t logg_present
     }
 }
 
+int swb_plan_split_max_logg(const SwbPlan &plan)
+{
+    for (int l = SWB_MAX_LOGG; l >= 1; --l)
+        if (plan.xl_by_logg[l]) return l;
+    return -1;
+}
+
+int swb_plan_split_k(const SwbPlan &plan, uint32_t rows, int k_max, uint32_t fill)
+{
+    for (int K = std::min(32, k_max); K > 8; K >>= 1) {
+        uint64_t items = 0;
+        for (int l = 1; l <= SWB_MAX_LOGG; ++l) items += (uint64_t)plan.xl_by_logg[l] * swb_split_passes(rows, l, K);
+        if (items >= fill) return K;
+    }
+    return 8;
+}
+
 void swb_plan_launch_groups(const SwbPlan &plan, const SwbQueryPlan &qp, bool longest_first, bool with_split,
-                            std::vector<SwbLaunchGroup> &groups)
+                            std::vector<SwbLaunchGroup> &groups, int split_k)
 {
     groups.clear();
     const uint32_t n_xl = with_split ? plan.n_xl : 0;
@@ -222,7 +239,7 @@ void swb_plan_launch_groups(const SwbPlan &plan, const SwbQueryPlan &qp, bool lo
     if (n_xl) {  // always first: its few warps then run beside everything else
         SwbLaunchGroup g;
         memset(&g, 0, sizeof g);
-        g.K = 8;
+        g.K = split_k;
         g.split = true;
         for (int l = 1; l <= SWB_MAX_LOGG; ++l) {
             g.xl_by_logg[l] = plan.xl_by_logg[l];
@@ -247,7 +264,7 @@ uint32_t swb_split_items(uint32_t rows, const SwbLaunchGroup &g, SwbScoreParams 
     for (int j = 0; j < SWB_MAX_LOGG; ++j) {
         const int l = SWB_MAX_LOGG - j;
         tiles += g.xl_by_logg[l];
-        items += g.xl_by_logg[l] * swb_split_passes(rows, l);
+        items += g.xl_by_logg[l] * swb_split_passes(rows, l, g.K);
         if (p) {
             p->split_tile_end[j] = tiles;
             p->split_item_end[j] = items;

@@ -57,8 +57,10 @@ struct SwbQueryPlan {
 // k_force: 0 = choose per group size (least padded rows, which is also the shortest tile time), else 8/16/32.
 // k_max: 32 for the s16 passes, 16 for the int32 pass. logg_present: bit l set when the plan has tiles of that
 // group size. chunk_rows must be a multiple of 1024 (every K << l divides it).
+// extra_multiple: every chunk also stages its rows rounded up to this (the pass height of a split group whose K is
+// larger than the K of its group sizes); 0 = none. Must divide chunk_rows.
 void swb_plan_query(uint32_t qlen, int k_force, int k_max, uint32_t logg_present, uint32_t chunk_rows,
-                    SwbQueryPlan &qp);
+                    SwbQueryPlan &qp, uint32_t extra_multiple = 0);
 
 // One score-kernel launch of a query pass: the tiles of all group sizes that share the same K.
 struct SwbLaunchGroup {
@@ -73,10 +75,20 @@ struct SwbLaunchGroup {
 // one group per distinct K; longest_first puts the group owning the longest tiles first (lone query), otherwise the
 // group with most tiles first (batch); inside a group the ranges run from the largest group size (longest tiles) down
 // with_split: give the very long tiles their own pipelined group (s16 pass); otherwise they stay in the 32-lane range
+// split_k: rows per lane of the split group (8: one warp per block, each work item stages the rows of its pass;
+// 16 / 32: full blocks that stage the whole chunk, like the other groups)
 void swb_plan_launch_groups(const SwbPlan &plan, const SwbQueryPlan &qp, bool longest_first, bool with_split,
-                            std::vector<SwbLaunchGroup> &groups);
+                            std::vector<SwbLaunchGroup> &groups, int split_k = 8);
+// Rows per lane for the split group of a query whose chunks have up to `rows` rows: the largest K <= k_max that still
+// yields at least `fill` work items per launch (enough to occupy the GPU), else 8 (most passes in flight per tile).
+int swb_plan_split_k(const SwbPlan &plan, uint32_t rows, int k_max, uint32_t fill);
+// largest lane-group size (log2) that has tiles in the split set, -1 if none
+int swb_plan_split_max_logg(const SwbPlan &plan);
 // split group: passes (work items) of a tile of 1 << l lanes per pair for a chunk of `rows` query rows (K = 8)
-inline uint32_t swb_split_passes(uint32_t rows, int l) { return (rows + (8u << l) - 1u) / (8u << l); }
+inline uint32_t swb_split_passes(uint32_t rows, int l, int K = 8)
+{
+    return (rows + ((uint32_t)K << l) - 1u) / ((uint32_t)K << l);
+}
 // work items of a split group for such a chunk; with p != NULL also fills p->ntiles and the class tables
 uint32_t swb_split_items(uint32_t rows, const SwbLaunchGroup &g, SwbScoreParams *p);
 // rows a launch group must find in shared memory for a chunk of `rows` query rows (multiple of 128)

@@ -58,6 +58,8 @@ struct SwbScoreParams {
     // tiles [split_tile_end[j-1], split_tile_end[j]) belong to class j and own ceil(rows / (K << (5 - j))) items each
     uint32_t split_tile_end[SWB_MAX_LOGG];
     uint32_t split_item_end[SWB_MAX_LOGG];
+    uint32_t split_stage_item;  // SPLIT: 1 = every work item stages the profile rows of its pass (one warp per block),
+                                // 0 = the block staged the whole chunk
     uint32_t warps_active;    // warps of a block that take work (0 = all): a launch with few tiles spreads them over the SMs
     uint32_t *prog;           // [item] columns of its bottom row that a pass has published (zeroed per query)
 };

@@ -647,10 +647,11 @@ SWB_HD void swb_warp_loop(BE &be, const SwbScoreParams &p, const int8_t *sprof, 
             const uint32_t ti = tile0 + t;
             if (p.only_flagged && !be.ld_flag(p.flags + ti)) continue;  // every pass of the tile skips alike
             const SwbTile tile = be.ld_tile(p.tiles + ti);
-            be.stage_rows(const_cast<int8_t *>(sprof), sstride, p.profile, p.prof_stride, p.row0 + ss * rows_per_pass,
-                          rows_per_pass);
+            if (p.split_stage_item)
+                be.stage_rows(const_cast<int8_t *>(sprof), sstride, p.profile, p.prof_stride,
+                              p.row0 + ss * rows_per_pass, rows_per_pass);
             swb_run_tile<K, V, true, true>(be, p, tile, ti, sprof, sstride, ss, 1u, p.prog + item0 + (size_t)t * passes,
-                                           ss);
+                                           p.split_stage_item ? ss : 0u);
             continue;
         }
         // qpair launches: two work items per tile (first / second sequence of every pair); ntiles counts items

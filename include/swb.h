@@ -80,9 +80,12 @@ const char *swb_last_error(const swb_engine *e);
  *          results are always in the caller's order),
  *          "pair_queries" (1 = a batch packs two queries of similar length into the two s16 halves of a lane, one
  *          database sequence per lane, no byte permute; measured slower on B200 (shared-memory bound); default 0),
- *          "split" (1 = the passes of sequences longer than "xl_len" (8192) run as pipelined work items on
+ *          "split" (1 = the passes of sequences longer than "xl_len" run as pipelined work items on
  *          different warps, 0 = never, -1 (default) = only on small shards, where those few tiles are the critical
  *          path of a query: +10 % at 1/8 of Swiss-Prot per GPU; on a large shard it costs ~0.5 %),
+ *          "xl_len" (lane-group tiles wider than this are the ones "split" applies to, default 3072; before db_load),
+ *          "split_fill" (N > 0: split launches use 16 / 32 rows per lane while they keep N work items; measured
+ *          slower than 8 rows on B200, default 0 = always 8),
  *          "chunk_rows" (query rows per launch for queries beyond shared memory; multiple of 1024, <= 7168) */
 int swb_set_option(swb_engine *e, const char *key, int64_t value);
 /* run on the caller's CUDA stream (cudaStream_t as void*); NULL = the engine's own stream */

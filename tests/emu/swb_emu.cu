@@ -169,8 +169,14 @@ void lane_main(HostBackend &be, void *a)
 {
     const LaneArgs *la = static_cast<const LaneArgs *>(a);
     if (la->split) {
-        if (la->mode == 1) swb_warp_loop<8, V32, true>(be, *la->p, la->sprof, la->sstride);
-        else swb_warp_loop<8, V16, true>(be, *la->p, la->sprof, la->sstride);
+        if (la->mode == 1) {
+            if (la->K == 8) swb_warp_loop<8, V32, true>(be, *la->p, la->sprof, la->sstride);
+            else swb_warp_loop<16, V32, true>(be, *la->p, la->sprof, la->sstride);
+        } else {
+            if (la->K == 8) swb_warp_loop<8, V16, true>(be, *la->p, la->sprof, la->sstride);
+            else if (la->K == 16) swb_warp_loop<16, V16, true>(be, *la->p, la->sprof, la->sstride);
+            else swb_warp_loop<32, V16, true>(be, *la->p, la->sprof, la->sstride);
+        }
     } else if (la->mode == 2) {
         if (la->K == 8) swb_warp_loop<8, V16Q, false>(be, *la->p, la->sprof, la->sstride);
         else if (la->K == 16) swb_warp_loop<16, V16Q, false>(be, *la->p, la->sprof, la->sstride);
@@ -222,7 +228,9 @@ void run_pass(SwbScoreParams &p, int mode, const SwbQueryPlan &qp, const std::ve
             p.prog = prog.data();
             p.row0 = ch.row0;
             p.rows = ch.rows;
-            p.smem_rows = g.split ? (uint32_t)g.K * 32u : swb_group_smem_rows(ch.rows, g);
+            const bool per_item = g.split && g.K == 8;
+            p.split_stage_item = per_item;
+            p.smem_rows = per_item ? (uint32_t)g.K * 32u : swb_group_smem_rows(ch.rows, g);
             p.first_chunk = ch.first;
             p.last_chunk = ch.last;
             uint32_t counter = 0;
@@ -231,7 +239,7 @@ void run_pass(SwbScoreParams &p, int mode, const SwbQueryPlan &qp, const std::ve
             const uint32_t sstride = mode == 2 ? (p.smem_rows + 1u) * 4u : p.smem_rows + 4u;
             std::vector<uint32_t> sprof_words(((size_t)sstride * SWB_ALPHA + 64) / 4);
             int8_t *sprof = reinterpret_cast<int8_t *>(sprof_words.data());
-            if (!g.split)
+            if (!per_item)
                 for (uint32_t code = 0; code < SWB_ALPHA; ++code)
                     memcpy(sprof + (size_t)code * sstride,
                            profbytes.data() + ((size_t)code * prof_stride + ch.row0) * esz, (size_t)p.smem_rows * esz);
@@ -256,7 +264,7 @@ static int emu_search(const uint8_t *codes, const uint64_t *offsets, uint32_t n,
                       uint32_t group_len, const int8_t *mat32, int gap, int gap_extend, const uint8_t *q, uint32_t qlen,
                       int K, int force_i32, uint32_t chunk_rows, int ovf_thr_override, uint32_t xl_len,
                       int32_t *scores_out, uint32_t *recomputed_tiles, const uint8_t *q2, uint32_t qlen2,
-                      int32_t *scores_out2, uint32_t chunk_rows_pair)
+                      int32_t *scores_out2, uint32_t chunk_rows_pair, uint32_t split_fill)
 {
     const bool affine = gap_extend != gap;
     if (affine && q2) return -2;
@@ -321,8 +329,12 @@ static int emu_search(const uint8_t *codes, const uint64_t *offsets, uint32_t n,
     if (!force_i32) {
         SwbQueryPlan qp0;
         std::vector<SwbLaunchGroup> g0;
-        swb_plan_query(rows, K, affine ? 16 : 32, present, pair ? chunk_rows_pair : chunk_rows, qp0);
-        swb_plan_launch_groups(pl, qp0, true, !pair && !affine, g0);
+        const bool split = !pair && !affine;
+        const int split_l = split ? swb_plan_split_max_logg(pl) : -1;
+        const int sk0 = split_l > 0 && split_fill ? swb_plan_split_k(pl, std::min(rows, chunk_rows), 32, split_fill) : 8;
+        swb_plan_query(rows, K, affine ? 16 : 32, present, pair ? chunk_rows_pair : chunk_rows, qp0,
+                       sk0 > 8 ? (uint32_t)sk0 << split_l : 0u);
+        swb_plan_launch_groups(pl, qp0, true, split, g0, sk0);
         std::vector<uint8_t> prof;
         const uint32_t stride = swb_roundup(qp0.prof_rows, 16);
         if (pair) {
@@ -355,8 +367,11 @@ static int emu_search(const uint8_t *codes, const uint64_t *offsets, uint32_t n,
         if (qls[k] == 0) continue;
         SwbQueryPlan qp1;
         std::vector<SwbLaunchGroup> g1;
-        swb_plan_query(qls[k], K, affine ? 8 : 16, present, chunk_rows, qp1);
-        swb_plan_launch_groups(pl, qp1, true, !pair && !affine, g1);
+        const bool split = !pair && !affine;
+        const int split_l = split ? swb_plan_split_max_logg(pl) : -1;
+        const int sk1 = split_l > 0 && split_fill ? swb_plan_split_k(pl, std::min(qls[k], chunk_rows), 16, split_fill) : 8;
+        swb_plan_query(qls[k], K, affine ? 8 : 16, present, chunk_rows, qp1, sk1 > 8 ? (uint32_t)sk1 << split_l : 0u);
+        swb_plan_launch_groups(pl, qp1, true, split, g1, sk1);
         if (!g1.empty() && g1[0].split) {  // swb_clear_flagged_kernel
             int32_t *sc = k ? sorted2.data() : sorted.data();
             for (size_t ti = 0; ti < pl.tiles.size(); ++ti)
@@ -390,7 +405,7 @@ extern "C" int swbemu_search(const uint8_t *codes, const uint64_t *offsets, uint
                              uint32_t qlen2, int32_t *scores_out2, uint32_t chunk_rows_pair)
 {
     return emu_search(codes, offsets, n, shard, nshards, group_len, mat32, gap, gap, q, qlen, K, force_i32, chunk_rows,
-                      ovf_thr_override, xl_len, scores_out, recomputed_tiles, q2, qlen2, scores_out2, chunk_rows_pair);
+                      ovf_thr_override, xl_len, scores_out, recomputed_tiles, q2, qlen2, scores_out2, chunk_rows_pair, 0);
 }
 
 extern "C" int swbemu_search_affine(const uint8_t *codes, const uint64_t *offsets, uint32_t n, uint32_t shard,
@@ -400,5 +415,16 @@ extern "C" int swbemu_search_affine(const uint8_t *codes, const uint64_t *offset
                                     uint32_t *recomputed_tiles)
 {
     return emu_search(codes, offsets, n, shard, nshards, group_len, mat32, gap_open, gap_extend, q, qlen, K, force_i32,
-                      chunk_rows, ovf_thr_override, 0, scores_out, recomputed_tiles, nullptr, 0, nullptr, 0);
+                      chunk_rows, ovf_thr_override, 0, scores_out, recomputed_tiles, nullptr, 0, nullptr, 0, 0);
+}
+
+// split_fill: work items a split launch should have before its K goes up from 8 to 16 / 32 (the engine passes the
+// GPU's warp slots); exercises the block-staged split kernels
+extern "C" int swbemu_search_split(const uint8_t *codes, const uint64_t *offsets, uint32_t n, uint32_t group_len,
+                                   const int8_t *mat32, int gap, const uint8_t *q, uint32_t qlen, int force_i32,
+                                   uint32_t chunk_rows, int ovf_thr_override, uint32_t xl_len, uint32_t split_fill,
+                                   int32_t *scores_out, uint32_t *recomputed_tiles)
+{
+    return emu_search(codes, offsets, n, 0, 1, group_len, mat32, gap, gap, q, qlen, 0, force_i32, chunk_rows,
+                      ovf_thr_override, xl_len, scores_out, recomputed_tiles, nullptr, 0, nullptr, 0, split_fill);
 }

@@ -275,3 +275,40 @@ def test_affine_edges(emu_affine, oracle):
             for K, gl in ((8, 8), (16, 16), (0, 384)):
                 got, _ = emu_affine(codes, offs, m, q, go, ge, K=K, group_len=gl)
                 assert np.array_equal(got, want), (ql, go, ge, K, gl)
+
+
+def test_pipelined_passes_with_full_blocks(emu, oracle):
+    """split launches with enough work items run K = 16 / 32 strips over the block-staged chunk (the engine raises K
+    while the items still fill the GPU's warp slots; here split_fill = 1 always picks the largest K that applies)"""
+    L = ctypes.CDLL(os.path.join(ROOT, PKG, "lib", "libswbemu.so"))
+    L.swbemu_search_split.restype = ctypes.c_int
+    L.swbemu_search_split.argtypes = [_u8p, _u64p, ctypes.c_uint32, ctypes.c_uint32, _i8p, ctypes.c_int, _u8p,
+                                      ctypes.c_uint32, ctypes.c_int, ctypes.c_uint32, ctypes.c_int, ctypes.c_uint32,
+                                      ctypes.c_uint32, _i32p, ctypes.POINTER(ctypes.c_uint32)]
+
+    def run(codes, offs, m, q, group_len, xl_len, fill, chunk_rows=0, thr=-1, force_i32=0):
+        out = np.full(len(offs) - 1, -7, dtype=np.int32)
+        rc = ctypes.c_uint32()
+        r = L.swbemu_search_split(codes.ctypes.data_as(_u8p), offs.ctypes.data_as(_u64p), len(offs) - 1, group_len,
+                                  np.ascontiguousarray(m, dtype=np.int8).ctypes.data_as(_i8p), 2,
+                                  q.ctypes.data_as(_u8p), len(q), force_i32, chunk_rows, thr, xl_len, fill,
+                                  out.ctypes.data_as(_i32p), ctypes.byref(rc))
+        assert r == 0
+        return out, rc.value
+
+    rng = np.random.default_rng(23)
+    m = oracle.matrix("blosum50")
+    lens = [1500, 1333, 900, 801, 640, 300, 280, 120, 64, 30, 7, 1200]
+    codes, offs = pack_db(random_db(rng, lens, alphabet=20))
+    for ql in (100, 700, 1100):
+        q = rng.integers(0, 20, ql).astype(np.uint8)
+        want = oracle.scan(q, codes, offs, m)
+        for gl, xl, fill in ((16, 100, 1), (16, 600, 40), (32, 1000, 1)):
+            got, _ = run(codes, offs, m, q, gl, xl, fill)
+            assert np.array_equal(got, want), (ql, gl, xl, fill)
+    q = rng.integers(0, 20, 2300).astype(np.uint8)
+    want = oracle.scan(q, codes, offs, m)
+    got, rc = run(codes, offs, m, q, 16, 500, 1, chunk_rows=1024, thr=40)  # chunks + int32 recompute (K = 16 split)
+    assert np.array_equal(got, want) and rc >= 3
+    got, _ = run(codes, offs, m, q, 16, 300, 1, force_i32=1)
+    assert np.array_equal(got, want)

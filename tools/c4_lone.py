@@ -10,7 +10,7 @@ opts = {k: int(v) for k, v in (a.split("=") for a in sys.argv[2:])}
 q = [x for x in qs if len(x) == ql][0]
 e = swb.Engine(0, **opts)
 e.db_load(codes, offsets)
-for _ in range(2):
+for _ in range(3):
     t = time.time(); e.search(q); dt = time.time() - t
 st = e.stats()
 print("qlen %d: %.2f ms wall, device %.2f ms, %.0f GCUPS, launches %d, recomputed %d" % (

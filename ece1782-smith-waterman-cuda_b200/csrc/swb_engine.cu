@@ -417,6 +417,28 @@ static cudaError_t grow_host(void **p, size_t *cap, size_t need)
 #define GROW_DEV(ptr, cap, need) grow_dev(reinterpret_cast<void **>(&(ptr)), &(cap), (need))
 #define GROW_HOST(ptr, cap, need) grow_host(reinterpret_cast<void **>(&(ptr)), &(cap), (need))
 
+// streams `bytes` of host memory to d_raw through the two pinned staging buffers: the host copy of slice i+1 overlaps the
+// asynchronous H2D of slice i
+static cudaError_t upload_staged(swb_engine *e, const uint8_t *src, uint64_t bytes, cudaStream_t st)
+{
+    const size_t stage = (size_t)std::min<uint64_t>(SWB_STAGE_BYTES, bytes);
+    cudaError_t ce;
+    for (int i = 0; i < 2; ++i) {
+        if ((ce = GROW_HOST(e->h_stage[i], e->stage_cap[i], stage)) != cudaSuccess) return ce;
+        if (!e->ev_stage[i] && (ce = cudaEventCreateWithFlags(&e->ev_stage[i], cudaEventDisableTiming)) != cudaSuccess)
+            return ce;
+    }
+    int b = 0;
+    for (uint64_t off = 0; off < bytes; off += stage, b ^= 1) {
+        const size_t len = (size_t)std::min<uint64_t>(stage, bytes - off);
+        if ((ce = cudaEventSynchronize(e->ev_stage[b])) != cudaSuccess) return ce;
+        memcpy(e->h_stage[b], src + off, len);
+        if ((ce = cudaMemcpyAsync(e->d_raw + off, e->h_stage[b], len, cudaMemcpyHostToDevice, st)) != cudaSuccess) return ce;
+        if ((ce = cudaEventRecord(e->ev_stage[b], st)) != cudaSuccess) return ce;
+    }
+    return cudaSuccess;
+}
+
 extern "C" int swb_db_load(swb_engine *e, const uint8_t *codes, const uint64_t *offsets, uint32_t n, uint32_t shard,
                            uint32_t nshards)
 {
@@ -430,7 +452,24 @@ extern "C" int swb_db_load(swb_engine *e, const uint8_t *codes, const uint64_t *
     CU(cudaStreamSynchronize(st));
     for (int i = 0; i < SWB_MAX_SLOTS; ++i) CU(cudaStreamSynchronize(e->slots[i].stream));
     e->db_loaded = false;
-    int rc = swb_build_plan(offsets, n, shard, nshards, e->plan_opts, e->plan);
+    // An unsharded load uploads the caller's buffer as it is, which does not need the plan: the plan (length sort, tiling;
+    // ~20 ms for Swiss-Prot) is built on a helper thread while this one stages and uploads the residues.
+    bool early_upload = nshards == 1 && n > 0 && offsets[n] > offsets[0];
+    for (uint32_t i = 0; i < n && early_upload; ++i) early_upload = offsets[i + 1] >= offsets[i];  // else: fails below
+    int rc = 0;
+    std::thread planner;
+    if (early_upload) {
+        planner = std::thread([&]() { rc = swb_build_plan(offsets, n, shard, nshards, e->plan_opts, e->plan); });
+        const uint64_t bytes = offsets[n] - offsets[0];
+        int urc = SWB_OK;
+        cudaError_t ce = GROW_DEV(e->d_raw, e->raw_cap, bytes);
+        if (ce == cudaSuccess) ce = upload_staged(e, codes + offsets[0], bytes, st);
+        if (ce != cudaSuccess) urc = fail(e, SWB_ERR_CUDA, std::string("db upload: ") + cudaGetErrorString(ce));
+        planner.join();
+        if (urc != SWB_OK) return urc;
+    } else {
+        rc = swb_build_plan(offsets, n, shard, nshards, e->plan_opts, e->plan);
+    }
     if (rc != 0) return fail(e, SWB_ERR_ARG, "bad offsets (decreasing, or a sequence longer than 2^31-16)");
     const double t1 = wall_ms();
     SwbPlan &pl = e->plan;
@@ -456,7 +495,7 @@ extern "C" int swb_db_load(swb_engine *e, const uint8_t *codes, const uint64_t *
         t2 = wall_ms();
         // stream the raw codes through two pinned staging buffers: the host copy of slice i+1 overlaps the
         // asynchronous H2D of slice i
-        if (raw_bytes) {
+        if (raw_bytes && gather) {
             const size_t stage = (size_t)std::min<uint64_t>(SWB_STAGE_BYTES, raw_bytes);
             for (int i = 0; i < 2; ++i) {
                 CU(GROW_HOST(e->h_stage[i], e->stage_cap[i], stage));
@@ -464,13 +503,7 @@ extern "C" int swb_db_load(swb_engine *e, const uint8_t *codes, const uint64_t *
             }
             int b = 0;
             if (!gather) {
-                for (uint64_t off = 0; off < raw_bytes; off += stage, b ^= 1) {
-                    const size_t len = (size_t)std::min<uint64_t>(stage, raw_bytes - off);
-                    CU(cudaEventSynchronize(e->ev_stage[b]));
-                    memcpy(e->h_stage[b], codes + base + off, len);
-                    CU(cudaMemcpyAsync(e->d_raw + off, e->h_stage[b], len, cudaMemcpyHostToDevice, st));
-                    CU(cudaEventRecord(e->ev_stage[b], st));
-                }
+                // uploaded above, beside the plan build (early_upload)
             } else {
                 uint64_t done = 0;
                 uint32_t sq = 0, within = 0;
@@ -609,8 +642,10 @@ static int enqueue_pass(swb_engine *e, Slot &s, int mode, SwbScoreParams &p, con
             p.range_cum[r] = g.range_cum[r];
         }
         size_t prog_at = 0;
-        for (size_t c = 0; c < qp.chunks.size(); ++c) {
-            const SwbQueryChunk &ch = qp.chunks[c];
+        std::vector<SwbQueryChunk> chunks;
+        swb_group_chunks(qp, g, chunks);
+        for (size_t c = 0; c < chunks.size(); ++c) {
+            const SwbQueryChunk &ch = chunks[c];
             // work items of the launch: tiles, (tile, pass) for split groups, (tile, half) for query pairs
             p.ntiles = mode == SWB_MODE_QPAIR ? 2 * g.ntiles : g.ntiles;
             p.prog = g.split ? s.d_prog + prog_at : nullptr;
@@ -732,12 +767,15 @@ static int enqueue_job(swb_engine *e, Slot &s, uint32_t qi, const uint8_t *q, ui
     // progress counters of the split group: one per (very long tile, pass) and chunk
     // (the int32 pass reuses the buffer after the s16 pass: same stream order, cleared in between)
     size_t prog_words = 0, prog_words1 = 0;
-    if (!g0.empty() && g0[0].split)
-        for (size_t c = 0; c < qp0.chunks.size(); ++c)
-            prog_words += swb_split_items(qp0.chunks[c].rows, g0[0], nullptr);
-    if (need_i32[0] && !g1[0].empty() && g1[0][0].split)
-        for (size_t c = 0; c < qp1[0].chunks.size(); ++c)
-            prog_words1 += swb_split_items(qp1[0].chunks[c].rows, g1[0][0], nullptr);
+    std::vector<SwbQueryChunk> sch;
+    if (!g0.empty() && g0[0].split) {
+        swb_group_chunks(qp0, g0[0], sch);
+        for (size_t c = 0; c < sch.size(); ++c) prog_words += swb_split_items(sch[c].rows, g0[0], nullptr);
+    }
+    if (need_i32[0] && !g1[0].empty() && g1[0][0].split) {
+        swb_group_chunks(qp1[0], g1[0][0], sch);
+        for (size_t c = 0; c < sch.size(); ++c) prog_words1 += swb_split_items(sch[c].rows, g1[0][0], nullptr);
+    }
     if (std::max(prog_words, prog_words1))
         CU(GROW_DEV(s.d_prog, s.prog_cap, sizeof(uint32_t) * std::max(prog_words, prog_words1)));
 

@@ -231,10 +231,10 @@ static cudaError_t dispatch(int op, int K, int mode, bool split, int block_cfg, 
     if (split) {  // pipelined passes. K = 8: one warp per block, the rows of a pass staged per work item
         if (K == 8) {
             if (i32)
-                return op == 0 ? launch_one<8, V32, 32, 8, true>(*p, grid, smem, st)
-                               : occ_one<8, V32, 32, 8, true>(smem, blocks);
-            return op == 0 ? launch_one<8, V16, 32, 8, true>(*p, grid, smem, st)
-                           : occ_one<8, V16, 32, 8, true>(smem, blocks);
+                return op == 0 ? launch_one<8, V32, 32, 20, true>(*p, grid, smem, st)
+                               : occ_one<8, V32, 32, 20, true>(smem, blocks);
+            return op == 0 ? launch_one<8, V16, 32, 28, true>(*p, grid, smem, st)
+                           : occ_one<8, V16, 32, 28, true>(smem, blocks);
         }
         // K = 16 / 32: full blocks over the staged chunk, for launches with enough work items to fill the GPU
         if (i32) return K == 16 ? dispatch_cfg<16, V32, true>(op, block_cfg, p, grid, smem, st, blocks) : cudaErrorInvalidValue;

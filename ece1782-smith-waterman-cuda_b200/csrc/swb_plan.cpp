@@ -258,6 +258,16 @@ void swb_plan_launch_groups(const SwbPlan &plan, const SwbQueryPlan &qp, bool lo
                          [](const SwbLaunchGroup &a, const SwbLaunchGroup &b) { return a.ntiles > b.ntiles; });
 }
 
+void swb_group_chunks(const SwbQueryPlan &qp, const SwbLaunchGroup &g, std::vector<SwbQueryChunk> &out)
+{
+    out = qp.chunks;
+    if (!(g.split && g.K == 8) || out.size() < 2) return;
+    SwbQueryChunk all = out.front();
+    all.rows = out.back().row0 + out.back().rows;
+    all.first = all.last = 1;
+    out.assign(1, all);
+}
+
 uint32_t swb_split_items(uint32_t rows, const SwbLaunchGroup &g, SwbScoreParams *p)
 {
     uint32_t tiles = 0, items = 0;

@@ -91,5 +91,9 @@ inline uint32_t swb_split_passes(uint32_t rows, int l, int K = 8)
 }
 // work items of a split group for such a chunk; with p != NULL also fills p->ntiles and the class tables
 uint32_t swb_split_items(uint32_t rows, const SwbLaunchGroup &g, SwbScoreParams *p);
+// The launches of a group over the query rows: the chunks of the query plan, except for a split group that stages per
+// work item (K = 8) -- shared memory does not limit it, so it covers all rows in ONE launch (no drain between chunks,
+// several times the work items in flight).
+void swb_group_chunks(const SwbQueryPlan &qp, const SwbLaunchGroup &g, std::vector<SwbQueryChunk> &out);
 // rows a launch group must find in shared memory for a chunk of `rows` query rows (multiple of 128)
 uint32_t swb_group_smem_rows(uint32_t rows, const SwbLaunchGroup &g);

@@ -221,8 +221,10 @@ void run_pass(SwbScoreParams &p, int mode, const SwbQueryPlan &qp, const std::ve
             p.range_start[r] = g.range_start[r];
             p.range_cum[r] = g.range_cum[r];
         }
-        for (size_t c = 0; c < qp.chunks.size(); ++c) {
-            const SwbQueryChunk &ch = qp.chunks[c];
+        std::vector<SwbQueryChunk> chunks;
+        swb_group_chunks(qp, g, chunks);
+        for (size_t c = 0; c < chunks.size(); ++c) {
+            const SwbQueryChunk &ch = chunks[c];
             p.ntiles = mode == 2 ? 2 * g.ntiles : g.ntiles;
             std::vector<uint32_t> prog((g.split ? swb_split_items(ch.rows, g, &p) : 0u) + 1u, 0u);
             p.prog = prog.data();

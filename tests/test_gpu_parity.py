@@ -82,7 +82,12 @@ def test_random_db_all_kernel_shapes(swb, oracle, k, group_len):
         e.db_load(codes, offs)
         for ql in (1, 7, 33, 144, 257, 1000):
             q = rng.integers(0, 24, ql).astype(np.uint8)
-            assert np.array_equal(e.search(q), oracle.scan(q, codes, offs, m)), (k, group_len, ql)
+            want = oracle.scan(q, codes, offs, m)
+            # a database this small takes the small-shard path (pipelined passes for the lane-group tiles, spread
+            # launches); split = 0 is what a full-size shard runs
+            for split in (-1, 0):
+                e.set_option("split", split)
+                assert np.array_equal(e.search(q), want), (k, group_len, ql, split)
     finally:
         e.close()
 
@@ -99,11 +104,14 @@ def test_long_query_chunked_and_int32_recompute(swb, oracle):
     try:
         e.db_load(codes, offs)
         for q in (long_q, wq):
-            got = e.search(q)
             want = oracle.scan(q, codes, offs, m)
-            assert np.array_equal(got, want)
-            assert got.max() > 32767
-            assert e.stats()["recomputed_tiles"] >= 1
+            for split in (-1, 0, 1):  # auto (on: small shard), the full-size-shard path, forced
+                e.set_option("split", split)
+                got = e.search(q)
+                assert np.array_equal(got, want), split
+                assert got.max() > 32767
+                assert e.stats()["recomputed_tiles"] >= 1
+        e.set_option("split", -1)
         e.set_option("chunk_rows", 1024)
         for k in (8, 16, 32):
             e.set_option("k", k)
@@ -149,6 +157,18 @@ def test_batch_equals_single_and_resident_fetch(engine, swb, oracle, subset, que
         assert np.array_equal(engine.fetch_scores(i), batch[i])
     for i, q in enumerate(qs):
         assert np.array_equal(engine.search(q), batch[i])
+    # the batch runs its longest query first; results stay in the caller's order either way, also with more queries
+    # than job slots (slots are reused as jobs finish)
+    many = [qs[i % len(qs)][: 40 + 37 * i] for i in range(40)]
+    engine.set_option("batch_order", 1)
+    as_given = engine.search_batch(many)
+    engine.set_option("batch_order", 0)
+    longest_first = engine.search_batch(many)
+    m = oracle.matrix("blosum50")
+    for i, q in enumerate(many):
+        assert np.array_equal(as_given[i], longest_first[i]), i
+        if i % 7 == 0:
+            assert np.array_equal(as_given[i], oracle.scan(q, subset["codes"], subset["offsets"], m)), i
 
 
 def test_shards_partition_and_agree(swb, oracle):

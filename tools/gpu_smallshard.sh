@@ -13,12 +13,11 @@ for l in open("gpurun_out/ss_$name.log"):
         print("$name: value %.0f GCUPS ms/step %.2f e2e %.0f launches %s tiles %s" % (d["value"], d["ms_per_step"], d["e2e"]["value"], d["gpu_launches"], d["engine"]["tiles_by_group"]))
 PY
 }
-run s8_new --scale 0.125
-run s8_new_s20 --scale 0.125 --streams 20
-run s8_new_chunk2k --scale 0.125 --chunk-rows 2048
-run s8_new_chunk3k --scale 0.125 --chunk-rows 3072
-run s8_new_chunk2k_s20 --scale 0.125 --chunk-rows 2048 --streams 20
-run s8_new_s12 --scale 0.125 --streams 12
-run s4_new --scale 0.25
-run s4_new_chunk2k --scale 0.25 --chunk-rows 2048
-run s1_new
+run s8_xl3072 --scale 0.125
+run s8_xl1536 --scale 0.125 --xl-len 1536
+run s8_xl768 --scale 0.125 --xl-len 768
+run s4_xl3072 --scale 0.25
+run s4_xl1536 --scale 0.25 --xl-len 1536
+run s1_split1 --split 1
+run s1_split1_xl6144 --split 1 --xl-len 6144
+run s1_split0 --split 0

@@ -712,14 +712,14 @@ static int enqueue_job(swb_engine *e, Slot &s, uint32_t qi, const uint8_t *q, ui
     // pass 0: the s16 pass over all tiles
     SwbQueryPlan qp0;
     std::vector<SwbLaunchGroup> g0;
-    // affine lanes carry (H, E) per row, so their strips stop at 16 rows (s16) / 8 rows (int32)
+    // affine lanes carry (H, E) per row: the int32 recompute stops at 8 rows per lane
     // rows per lane of the split groups: 8 (most passes in flight per tile). Option split_fill = N lets K grow to 16 / 32
     // while a launch keeps N work items; measured slower on the titin-scale workload at every N (2,370 GCUPS with K = 8,
     // 1,834 / 1,474 with K = 16 / 32), so it is off by default
     const uint32_t fill = (uint32_t)e->opt_split_fill;
     const int split_l = split && fill ? swb_plan_split_max_logg(pl) : -1;
     const int sk0 = split_l > 0 ? swb_plan_split_k(pl, std::min(rows, chunk_rows), 32, fill) : 8;
-    swb_plan_query(rows, e->opt_k, affine ? 16 : 32, present, pair ? SWB_CHUNK_ROWS_QPAIR : chunk_rows, qp0,
+    swb_plan_query(rows, e->opt_k, 32, present, pair ? SWB_CHUNK_ROWS_QPAIR : chunk_rows, qp0,
                    sk0 > 8 ? (uint32_t)sk0 << split_l : 0u);
     swb_plan_launch_groups(pl, qp0, longest_first, split, g0, sk0);
     // int32 passes over flagged tiles, one per query, only when a score can exceed the s16 range at all

@@ -213,6 +213,7 @@ static cudaError_t dispatch(int op, int K, int mode, bool split, int block_cfg, 
             switch (K) {
             case 8: return dispatch_cfg<8, V16A, false>(op, block_cfg, p, grid, smem, st, blocks);
             case 16: return dispatch_cfg<16, V16A, false>(op, block_cfg, p, grid, smem, st, blocks);
+            case 32: return dispatch_cfg<32, V16A, false>(op, block_cfg, p, grid, smem, st, blocks);
             }
         } else if (K == 8) {
             return dispatch_cfg<8, V32A, false>(op, block_cfg, p, grid, smem, st, blocks);

@@ -183,7 +183,8 @@ void lane_main(HostBackend &be, void *a)
         else swb_warp_loop<32, V16Q, false>(be, *la->p, la->sprof, la->sstride);
     } else if (la->mode == 3) {
         if (la->K == 8) swb_warp_loop<8, V16A, false>(be, *la->p, la->sprof, la->sstride);
-        else swb_warp_loop<16, V16A, false>(be, *la->p, la->sprof, la->sstride);
+        else if (la->K == 16) swb_warp_loop<16, V16A, false>(be, *la->p, la->sprof, la->sstride);
+        else swb_warp_loop<32, V16A, false>(be, *la->p, la->sprof, la->sstride);
     } else if (la->mode == 4) {
         swb_warp_loop<8, V32A, false>(be, *la->p, la->sprof, la->sstride);
     } else if (la->mode == 0) {
@@ -334,7 +335,7 @@ static int emu_search(const uint8_t *codes, const uint64_t *offsets, uint32_t n,
         const bool split = !pair && !affine;
         const int split_l = split ? swb_plan_split_max_logg(pl) : -1;
         const int sk0 = split_l > 0 && split_fill ? swb_plan_split_k(pl, std::min(rows, chunk_rows), 32, split_fill) : 8;
-        swb_plan_query(rows, K, affine ? 16 : 32, present, pair ? chunk_rows_pair : chunk_rows, qp0,
+        swb_plan_query(rows, K, 32, present, pair ? chunk_rows_pair : chunk_rows, qp0,
                        sk0 > 8 ? (uint32_t)sk0 << split_l : 0u);
         swb_plan_launch_groups(pl, qp0, true, split, g0, sk0);
         std::vector<uint8_t> prof;

@@ -227,7 +227,7 @@ def test_oracle_affine_degenerates_to_linear(oracle, subset, queries):
     assert (oracle.scan_affine(q, subset["codes"], subset["offsets"], m, 64, 64) <= aff).all()
 
 
-@pytest.mark.parametrize("go,ge,K,group_len", [(10, 2, 0, 384), (10, 2, 8, 64), (12, 1, 16, 16), (5, 0, 0, 16),
+@pytest.mark.parametrize("go,ge,K,group_len", [(10, 2, 0, 384), (10, 2, 8, 64), (12, 1, 16, 16), (5, 0, 0, 16), (11, 1, 32, 96),
                                                (3, 2, 8, 2000)])
 def test_affine_subset(emu_affine, oracle, subset, queries, go, ge, K, group_len):
     m = oracle.matrix("blosum50")

@@ -15,7 +15,9 @@
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
+#include <algorithm>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/swb.h"
@@ -33,39 +35,171 @@ struct FileHeader {
 static_assert(sizeof(FileHeader) == 32, "header is 32 bytes");
 const char kMagic[8] = {'S', 'W', 'B', 'D', 'B', 0, 1, 0};
 
-bool slurp(const char *path, std::string &data)
-{
-    data.clear();
-    FILE *f = fopen(path, "rb");
-    if (!f) return false;
-    fseek(f, 0, SEEK_END);
-    const long size = ftell(f);
-    fseek(f, 0, SEEK_SET);
-    if (size > 0) {
-        data.resize((size_t)size);
-        const size_t got = fread(&data[0], 1, (size_t)size, f);
-        data.resize(got);
+// read-only view of a whole file (mmap; a missing or empty file is an empty view)
+struct FileView {
+    const char *data = nullptr;
+    size_t size = 0;
+    void *map = nullptr;
+    bool opened = false;
+    explicit FileView(const char *path)
+    {
+        const int fd = open(path, O_RDONLY);
+        if (fd < 0) return;
+        opened = true;
+        struct stat st;
+        if (fstat(fd, &st) == 0 && st.st_size > 0) {
+            void *m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+            if (m != MAP_FAILED) {
+                map = m;
+                data = static_cast<const char *>(m);
+                size = (size_t)st.st_size;
+                madvise(m, size, MADV_SEQUENTIAL);
+            }
+        }
+        close(fd);
     }
-    fclose(f);
-    return true;
+    ~FileView()
+    {
+        if (map) munmap(map, size);
+    }
+};
+
+// What one worker found in its slice of the text: the codes it wrote (at `out`, which starts at the slice's own offset
+// in the shared output buffer -- a slice never yields more codes than it has bytes) and where records start in them.
+struct SliceResult {
+    size_t begin = 0, end = 0;  // byte range of the slice
+    size_t ncodes = 0;
+    std::vector<uint64_t> starts;  // FASTA: code position of every header line; flat file: of every SQ line
+};
+
+unsigned worker_count(size_t bytes)
+{
+    unsigned hw = std::thread::hardware_concurrency();
+    if (hw == 0) hw = 1;
+    size_t per_worker = 8u << 20;  // at least 8 MB of text per worker (SWB_INGEST_SLICE_BYTES: tests cut small files)
+    if (const char *env = getenv("SWB_INGEST_SLICE_BYTES")) per_worker = (size_t)std::max(1L, atol(env));
+    const size_t by_size = bytes / per_worker + 1;
+    return (unsigned)std::min<size_t>(std::min<size_t>(hw, 32), by_size);
 }
 
-int hand_out(const std::vector<uint8_t> &codes, const std::vector<uint64_t> &offsets, uint8_t **codes_out,
+// FASTA slice: starts at a header line (or is the whole header-less file)
+void parse_fasta_slice(const char *d, const uint8_t *lut, uint8_t *out, SliceResult &r)
+{
+    uint8_t *w = out;
+    size_t pos = r.begin;
+    while (pos < r.end) {
+        const char *nlp = static_cast<const char *>(memchr(d + pos, '\n', r.end - pos));
+        const size_t nl = nlp ? (size_t)(nlp - d) : r.end;
+        if (nl > pos && d[pos] == '>') {
+            r.starts.push_back((uint64_t)(w - out));
+        } else {
+            for (size_t k = pos; k < nl; ++k) *w++ = lut[(unsigned char)d[k]];
+        }
+        pos = nl + 1;
+    }
+    r.ncodes = (size_t)(w - out);
+}
+
+// flat-file slice: starts at the beginning of a line that follows a "//" line (or at byte 0)
+void parse_dat_slice(const char *d, const uint8_t *lut, uint8_t *out, SliceResult &r)
+{
+    uint8_t *w = out;
+    bool in_seq = false;
+    size_t pos = r.begin;
+    while (pos < r.end) {
+        const char *nlp = static_cast<const char *>(memchr(d + pos, '\n', r.end - pos));
+        const size_t nl = nlp ? (size_t)(nlp - d) : r.end;
+        const size_t len = nl - pos;
+        if (len >= 2 && d[pos] == 'S' && d[pos + 1] == 'Q' && (len == 2 || d[pos + 2] == ' ')) {
+            r.starts.push_back((uint64_t)(w - out));  // also closes an entry that lacks its "//"
+            in_seq = true;
+        } else if (len >= 2 && d[pos] == '/' && d[pos + 1] == '/') {
+            in_seq = false;
+        } else if (in_seq) {
+            for (size_t k = pos; k < nl; ++k) {
+                const char ch = d[k];
+                if (ch != ' ' && ch != '\t' && ch != '\r') *w++ = lut[(unsigned char)ch];
+            }
+        }
+        pos = nl + 1;
+    }
+    r.ncodes = (size_t)(w - out);
+}
+
+// Cuts [begin, size) into up to `want` slices whose starts satisfy `is_cut(pos)` (pos = first byte of a line).
+template <class IsCut>
+void cut_slices(const char *d, size_t begin, size_t size, unsigned want, IsCut is_cut, std::vector<SliceResult> &out)
+{
+    out.clear();
+    size_t at = begin;
+    for (unsigned i = 1; i <= want && at < size; ++i) {
+        size_t stop = size;
+        if (i < want) {
+            size_t guess = begin + (size - begin) / want * i;
+            if (guess <= at) continue;
+            // next line start at or after `guess` that is a valid cut
+            stop = size;
+            size_t p = guess;
+            while (p < size) {
+                const char *nlp = static_cast<const char *>(memchr(d + p, '\n', size - p));
+                if (!nlp) break;
+                p = (size_t)(nlp - d) + 1;
+                if (p < size && is_cut(p)) { stop = p; break; }
+            }
+        }
+        SliceResult r;
+        r.begin = at;
+        r.end = stop;
+        out.push_back(r);
+        at = stop;
+    }
+}
+
+template <class Fn>
+void run_slices(std::vector<SliceResult> &slices, Fn fn)
+{
+    std::vector<std::thread> th;
+    for (size_t i = 1; i < slices.size(); ++i) th.emplace_back([&, i]() { fn(slices[i]); });
+    if (!slices.empty()) fn(slices[0]);
+    for (size_t i = 0; i < th.size(); ++i) th[i].join();
+}
+
+// moves every slice's codes down to close the gaps (left to right: destinations never overtake sources)
+size_t compact(uint8_t *buf, size_t buf_begin, std::vector<SliceResult> &slices, std::vector<size_t> &base)
+{
+    size_t at = 0;
+    base.resize(slices.size());
+    for (size_t i = 0; i < slices.size(); ++i) {
+        base[i] = at;
+        const size_t src = slices[i].begin - buf_begin;
+        if (src != at && slices[i].ncodes) memmove(buf + at, buf + src, slices[i].ncodes);
+        at += slices[i].ncodes;
+    }
+    return at;
+}
+
+bool make_lut(int preset, uint8_t *lut)
+{
+    char all[256];
+    for (int i = 0; i < 256; ++i) all[i] = (char)i;
+    return swb_encode(preset, all, 256, lut) == SWB_OK;
+}
+
+int hand_out(uint8_t *codes, size_t ncodes, const std::vector<uint64_t> &offsets, uint8_t **codes_out,
              uint64_t **offsets_out, uint32_t *n_out)
 {
-    const size_t n = offsets.size() - 1;
-    uint8_t *c = (uint8_t *)malloc(codes.size() ? codes.size() : 1);
     uint64_t *o = (uint64_t *)malloc(sizeof(uint64_t) * offsets.size());
+    uint8_t *c = codes ? (uint8_t *)realloc(codes, ncodes ? ncodes : 1) : (uint8_t *)malloc(1);
+    if (!c) c = codes;  // a shrinking realloc that fails leaves the block valid
     if (!c || !o) {
         free(c);
         free(o);
         return SWB_ERR_NOMEM;
     }
-    if (!codes.empty()) memcpy(c, codes.data(), codes.size());
     memcpy(o, offsets.data(), sizeof(uint64_t) * offsets.size());
     *codes_out = c;
     *offsets_out = o;
-    *n_out = (uint32_t)n;
+    *n_out = (uint32_t)(offsets.size() - 1);
     return SWB_OK;
 }
 
@@ -77,41 +211,48 @@ struct swb_dbfile {
     FileHeader hdr;
 };
 
+// The file is mapped, cut at record boundaries into one slice per host thread (8 MB of text or more each), every slice
+// is encoded by its own thread straight into the output buffer, and the slices are then closed up.
 extern "C" int swb_read_fasta(const char *path, int preset, uint8_t **codes_out, uint64_t **offsets_out, uint32_t *n_out,
                               int32_t *first_id)
 {
     if (!path || !codes_out || !offsets_out || !n_out) return SWB_ERR_ARG;
     uint8_t lut[256];
-    {
-        char all[256];
-        for (int i = 0; i < 256; ++i) all[i] = (char)i;
-        if (swb_encode(preset, all, 256, lut) != SWB_OK) return SWB_ERR_ARG;
-    }
-    std::string data;
-    slurp(path, data);  // a missing file reads as empty: one empty record, like the reference parser
-    std::vector<uint8_t> codes;
-    std::vector<uint64_t> offsets(1, 0);
-    codes.reserve(data.size());
+    if (!make_lut(preset, lut)) return SWB_ERR_ARG;
+    FileView f(path);  // a missing file reads as empty: one empty record, like the reference parser
+    const char *d = f.data;
+    const size_t size = f.size;
+    // first header line: text before it is dropped; without any the whole file is one record (first id -1)
+    size_t h0 = size;
     bool seen_header = false;
-    size_t rec_start = 0;  // codes.size() at the start of the current record
-    size_t pos = 0;
-    const size_t size = data.size();
-    while (pos < size) {
-        size_t nl = data.find('\n', pos);
-        if (nl == std::string::npos) nl = size;
-        if (nl > pos && data[pos] == '>') {
-            if (seen_header) offsets.push_back(codes.size());
-            else codes.resize(rec_start);  // text before the first '>' is dropped
-            seen_header = true;
-            rec_start = codes.size();
-        } else {
-            for (size_t k = pos; k < nl; ++k) codes.push_back(lut[(unsigned char)data[k]]);
-        }
+    for (size_t pos = 0; pos < size;) {
+        const char *nlp = static_cast<const char *>(memchr(d + pos, '\n', size - pos));
+        const size_t nl = nlp ? (size_t)(nlp - d) : size;
+        if (nl > pos && d[pos] == '>') { h0 = pos; seen_header = true; break; }
         pos = nl + 1;
     }
-    offsets.push_back(codes.size());
+    const size_t begin = seen_header ? h0 : 0;
+    uint8_t *buf = size > begin ? (uint8_t *)malloc(size - begin) : nullptr;
+    if (size > begin && !buf) return SWB_ERR_NOMEM;
+    std::vector<SliceResult> slices;
+    // a header-less file is one record: any line start may cut it; otherwise slices start at header lines
+    if (seen_header)
+        cut_slices(d, begin, size, worker_count(size - begin), [&](size_t p) { return d[p] == '>'; }, slices);
+    else
+        cut_slices(d, begin, size, worker_count(size - begin), [&](size_t) { return true; }, slices);
+    run_slices(slices, [&](SliceResult &r) { parse_fasta_slice(d, lut, buf + (r.begin - begin), r); });
+    std::vector<size_t> base;
+    const size_t ncodes = compact(buf, begin, slices, base);
+    std::vector<uint64_t> offsets;
+    if (seen_header) {
+        for (size_t i = 0; i < slices.size(); ++i)
+            for (size_t k = 0; k < slices[i].starts.size(); ++k) offsets.push_back(base[i] + slices[i].starts[k]);
+    } else {
+        offsets.push_back(0);
+    }
+    offsets.push_back(ncodes);
     if (first_id) *first_id = seen_header ? 0 : -1;
-    return hand_out(codes, offsets, codes_out, offsets_out, n_out);
+    return hand_out(buf, ncodes, offsets, codes_out, offsets_out, n_out);
 }
 
 extern "C" int swb_read_uniprot_dat(const char *path, int preset, uint8_t **codes_out, uint64_t **offsets_out,
@@ -119,38 +260,27 @@ extern "C" int swb_read_uniprot_dat(const char *path, int preset, uint8_t **code
 {
     if (!path || !codes_out || !offsets_out || !n_out) return SWB_ERR_ARG;
     uint8_t lut[256];
-    {
-        char all[256];
-        for (int i = 0; i < 256; ++i) all[i] = (char)i;
-        if (swb_encode(preset, all, 256, lut) != SWB_OK) return SWB_ERR_ARG;
-    }
-    std::string data;
-    if (!slurp(path, data)) return SWB_ERR_ARG;
-    std::vector<uint8_t> codes;
-    std::vector<uint64_t> offsets(1, 0);
-    bool in_seq = false;
-    size_t pos = 0;
-    const size_t size = data.size();
-    while (pos < size) {
-        size_t nl = data.find('\n', pos);
-        if (nl == std::string::npos) nl = size;
-        const size_t len = nl - pos;
-        if (len >= 2 && data[pos] == 'S' && data[pos + 1] == 'Q' && (len == 2 || data[pos + 2] == ' ')) {
-            if (in_seq) offsets.push_back(codes.size());
-            in_seq = true;
-        } else if (len >= 2 && data[pos] == '/' && data[pos + 1] == '/') {
-            if (in_seq) offsets.push_back(codes.size());
-            in_seq = false;
-        } else if (in_seq) {
-            for (size_t k = pos; k < nl; ++k) {
-                const char ch = data[k];
-                if (ch != ' ' && ch != '\t' && ch != '\r') codes.push_back(lut[(unsigned char)ch]);
-            }
-        }
-        pos = nl + 1;
-    }
-    if (in_seq) offsets.push_back(codes.size());  // the last entry may lack its "//"
-    return hand_out(codes, offsets, codes_out, offsets_out, n_out);
+    if (!make_lut(preset, lut)) return SWB_ERR_ARG;
+    FileView f(path);
+    if (!f.opened) return SWB_ERR_ARG;
+    const char *d = f.data;
+    const size_t size = f.size;
+    uint8_t *buf = size ? (uint8_t *)malloc(size) : nullptr;
+    if (size && !buf) return SWB_ERR_NOMEM;
+    std::vector<SliceResult> slices;
+    // cut after "//" lines: p is a line start whose previous line is "//"
+    cut_slices(d, 0, size, worker_count(size),
+               [&](size_t p) { return p >= 3 && d[p - 2] == '/' && d[p - 3] == '/' && (p == 3 || d[p - 4] == '\n'); }, slices);
+    run_slices(slices, [&](SliceResult &r) { parse_dat_slice(d, lut, buf + r.begin, r); });
+    std::vector<size_t> base;
+    const size_t ncodes = compact(buf, 0, slices, base);
+    // entries are back to back in the code stream: offsets = every start, then the end of the last entry
+    std::vector<uint64_t> offsets;
+    for (size_t i = 0; i < slices.size(); ++i)
+        for (size_t k = 0; k < slices[i].starts.size(); ++k) offsets.push_back(base[i] + slices[i].starts[k]);
+    if (offsets.empty()) offsets.push_back(0);
+    else offsets.push_back(ncodes);
+    return hand_out(buf, ncodes, offsets, codes_out, offsets_out, n_out);
 }
 
 extern "C" void swb_free(void *p) { free(p); }

@@ -93,3 +93,66 @@ def test_mkdb_tool(swb, tmp_path):
                        text=True)
     assert r.returncode == 0 and r.stdout.startswith("5 sequences")
     assert subprocess.run([tool], capture_output=True).returncode == 2
+
+
+def _ref_fasta_records(data):
+    """the record rule restated line by line (FASTAParsers.h:73-136 without the '/' padding)"""
+    recs, cur, seen = [], bytearray(), False
+    for line in data.split(b"\n"):
+        if line[:1] == b">":
+            if seen:
+                recs.append(bytes(cur))
+            cur = bytearray()
+            seen = True
+        else:
+            cur += line
+    recs.append(bytes(cur))
+    return recs, (0 if seen else -1)
+
+
+@pytest.mark.parametrize("slice_bytes", [1, 7, 64, 1000])
+def test_parallel_slices_cut_like_the_sequential_rule(swb, tmp_path, monkeypatch, slice_bytes):
+    """the readers cut a file into one slice per host thread at record boundaries; forcing tiny slices on files full
+    of edge cases ('>' inside a line, blank lines, CR, text before the first header, no header, no final newline)
+    must give the records of the line-by-line rule"""
+    monkeypatch.setenv("SWB_INGEST_SLICE_BYTES", str(slice_bytes))
+    rng = np.random.default_rng(slice_bytes)
+    letters = np.frombuffer(b"ARNDCQEGHILKMFPSTWYVBJZX*UO", dtype=np.uint8)
+    cases = [b"junk before\nMORE\n>a\nAC>D\n\n>b\n\n>c\nAC\r\nD\n>\n>d x\nWW", b"NOHEADER\nLINES\n\nONLY\n", b">only\n", b"\n\n>x\nA\n"]
+    big = bytearray()
+    for i in range(300):
+        big += b">sp|%d| desc > with gt\n" % i
+        n = int(rng.integers(0, 200))
+        s = letters[rng.integers(0, len(letters), n)].tobytes()
+        for k in range(0, n, 60):
+            big += s[k:k + 60] + (b"\r\n" if i % 17 == 0 else b"\n")
+        if i % 23 == 0:
+            big += b"\n"
+    cases.append(bytes(big))
+    for ci, data in enumerate(cases):
+        path = tmp_path / ("c%d.fasta" % ci)
+        path.write_bytes(data)
+        codes, offs, first_id = swb.read_fasta(str(path))
+        recs, want_first = _ref_fasta_records(data)
+        assert first_id == want_first and len(offs) - 1 == len(recs), ci
+        for k, r in enumerate(recs):
+            assert np.array_equal(codes[int(offs[k]):int(offs[k + 1])], swb.encode(r.decode("latin-1"))), (ci, k)
+    # flat file: "//" inside other lines, the last entry without its "//"
+    dat = bytearray()
+    want = []
+    for i in range(120):
+        n = int(rng.integers(1, 300))
+        s = letters[rng.integers(0, 24, n)].tobytes()
+        dat += b"ID   X%d\nDE   // not a terminator here\nSQ   SEQUENCE %d AA;\n" % (i, n)
+        for k in range(0, n, 60):
+            row = s[k:k + 60]
+            dat += b"     " + b" ".join(row[j:j + 10] for j in range(0, len(row), 10)) + b"\n"
+        want.append(s)
+        if i != 119:
+            dat += b"//\n"
+    path = tmp_path / "x.dat"
+    path.write_bytes(bytes(dat))
+    codes, offs = swb.read_uniprot_dat(str(path))
+    assert len(offs) - 1 == len(want)
+    for k, s in enumerate(want):
+        assert np.array_equal(codes[int(offs[k]):int(offs[k + 1])], swb.encode(s.decode("latin-1"))), k

@@ -86,6 +86,7 @@ struct swb_engine {
     // options
     SwbPlanOpts plan_opts;
     int opt_k = 0;
+    bool group_len_auto = true;  // swb_db_load picks group_len from the shard size (below) unless the option sets it
     int opt_split_fill = 0;   // work items a split launch must keep before its K goes up from 8 (0 = K stays 8)
     int opt_batch_order = 0;  // batches: 0 = longest query first, 1 = in the caller's order
     int opt_pair_queries = 0; // batches: pack two queries into the halves of the s16x2 lanes (V16Q). Opt-in: measured
@@ -301,8 +302,9 @@ extern "C" int swb_set_option(swb_engine *e, const char *key, int64_t value)
 {
     if (!e || !key) return SWB_ERR_ARG;
     if (!strcmp(key, "group_len")) {
-        if (value < 8 || value > (1 << 30)) return fail(e, SWB_ERR_ARG, "group_len out of range");
-        e->plan_opts.group_len = (uint32_t)value;
+        if (value != 0 && (value < 8 || value > (1 << 30))) return fail(e, SWB_ERR_ARG, "group_len out of range");
+        e->group_len_auto = value == 0;
+        if (value) e->plan_opts.group_len = (uint32_t)value;
     } else if (!strcmp(key, "k")) {
         if (value != 0 && value != 8 && value != 16 && value != 32) return fail(e, SWB_ERR_ARG, "k must be 0, 8, 16 or 32");
         e->opt_k = (int)value;
@@ -452,6 +454,16 @@ extern "C" int swb_db_load(swb_engine *e, const uint8_t *codes, const uint64_t *
     CU(cudaStreamSynchronize(st));
     for (int i = 0; i < SWB_MAX_SLOTS; ++i) CU(cudaStreamSynchronize(e->slots[i].stream));
     e->db_loaded = false;
+    // group_len (longest sequence that runs one lane per pair). One-lane tiles are the cheapest per cell (no shuffles,
+    // conflict-free profile reads, least row padding), so a shard with plenty of tiles wants them for as many sequences
+    // as possible: measured on the benchmark database, 384 / 768 / 1536 give 8,830 / 9,094 / 9,108 GCUPS (20 reference
+    // queries) and 8,234 / 8,614 / 8,745 (150 short queries). A small shard is the opposite case: with about as many
+    // tiles as warp slots, the long one-lane tiles become its critical path (1/8 of the database: 7,234 with 768 against
+    // 8,312 with 384).
+    if (e->group_len_auto) {
+        const uint64_t slots = (uint64_t)e->sm_count * (SWB_NT_LARGE / 32);
+        e->plan_opts.group_len = (uint64_t)(n / nshards) / 64u >= 2u * slots ? 1536u : 384u;
+    }
     // An unsharded load uploads the caller's buffer as it is, which does not need the plan: the plan (length sort, tiling;
     // ~20 ms for Swiss-Prot) is built on a helper thread while this one stages and uploads the residues.
     bool early_upload = nshards == 1 && n > 0 && offsets[n] > offsets[0];

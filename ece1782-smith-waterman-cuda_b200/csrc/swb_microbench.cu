@@ -50,6 +50,13 @@ __global__ void __launch_bounds__(256) swb_mb_kernel(uint32_t *out, uint32_t see
                 x[c] = __viaddmax_s16x2_relu(x[c], b, a);
                 x[c] = swb_hmax2_bits(x[c], a);
             }
+            // which of the kernel's instructions issue beside VIADDMNMX (i.e. not on the same 64-lane pipe)?
+            if (KIND == 11) { x[c] = __viaddmax_s16x2_relu(x[c], b, a); x[c] = __vadd2(x[c], b); }
+            if (KIND == 12) {
+                x[c] = __viaddmax_s16x2_relu(x[c], b, a);
+                asm volatile("prmt.b32 %0, %1, %2, 0xC480;" : "=r"(x[c]) : "r"(x[c]), "r"(b));
+            }
+            if (KIND == 13) { x[c] = __viaddmax_s16x2_relu(x[c], b, a); x[c] = __vimax3_s16x2(x[c], b, a); }
             if (KIND == 8) {  // the biased policy's mix: prmt, vimax3, viaddmax, 1/2 vimax3 (ALU) + 3 imad (FMA)
                 uint32_t s, ds, l3;
                 asm volatile("prmt.b32 %0, %1, %2, 0xD591;" : "=r"(s) : "r"(x[c]), "r"(b));
@@ -68,14 +75,15 @@ __global__ void __launch_bounds__(256) swb_mb_kernel(uint32_t *out, uint32_t see
     if (r == 0x12345678u) out[0] = r;
 }
 
-static const double kInstrPerIter[11] = {MB_CHAINS, MB_CHAINS, MB_CHAINS, MB_CHAINS, MB_CHAINS * 4.5, MB_CHAINS * 2.0,
-                                         MB_CHAINS, MB_CHAINS, MB_CHAINS * 6.5, MB_CHAINS * 3.0, MB_CHAINS * 2.0};
+static const double kInstrPerIter[14] = {MB_CHAINS, MB_CHAINS, MB_CHAINS, MB_CHAINS, MB_CHAINS * 4.5, MB_CHAINS * 2.0,
+                                         MB_CHAINS, MB_CHAINS, MB_CHAINS * 6.5, MB_CHAINS * 3.0, MB_CHAINS * 2.0,
+                                         MB_CHAINS * 2.0, MB_CHAINS * 2.0, MB_CHAINS * 2.0};
 
 // kind 0 viaddmax.relu, 1 vimax3, 2 vadd2, 3 prmt, 4 V16 mix, 5 viaddmax+imad, 6 imad, 7 scalar add/max, 8 V16B mix.
 // Returns giga lane-instructions per second (warp instructions x 32) over the whole GPU.
 extern "C" int swb_microbench(int device, int kind, double *glane_instr_per_s, double *ms_out)
 {
-    if (kind < 0 || kind > 10 || !glane_instr_per_s) return SWB_ERR_ARG;
+    if (kind < 0 || kind > 13 || !glane_instr_per_s) return SWB_ERR_ARG;
     if (cudaSetDevice(device) != cudaSuccess) return SWB_ERR_CUDA;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return SWB_ERR_CUDA;
@@ -99,6 +107,9 @@ extern "C" int swb_microbench(int device, int kind, double *glane_instr_per_s, d
         case 7: swb_mb_kernel<7><<<grid, block>>>(d, 7u + rep, iters); break;
         case 8: swb_mb_kernel<8><<<grid, block>>>(d, 7u + rep, iters); break;
         case 9: swb_mb_kernel<9><<<grid, block>>>(d, 7u + rep, iters); break;
+        case 11: swb_mb_kernel<11><<<grid, block>>>(d, 7u + rep, iters); break;
+        case 12: swb_mb_kernel<12><<<grid, block>>>(d, 7u + rep, iters); break;
+        case 13: swb_mb_kernel<13><<<grid, block>>>(d, 7u + rep, iters); break;
         default: swb_mb_kernel<10><<<grid, block>>>(d, 7u + rep, iters); break;
         }
         cudaEventRecord(e1);

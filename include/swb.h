@@ -72,7 +72,8 @@ int swb_create(swb_engine **out, int device);
 void swb_destroy(swb_engine *e);
 /* e == NULL: error text of the last failed swb_create of this thread */
 const char *swb_last_error(const swb_engine *e);
-/* options: "group_len" (longest sequence handled by one lane per pair, default 384; set before db_load),
+/* options: "group_len" (longest sequence handled by one lane per pair; set before db_load. Default 0 = chosen per
+ *          load: 1536 for a shard with at least ~300 k sequences, 384 for smaller ones),
  *          "k" (query rows per lane: 0 = chosen per lane-group size and query, else 8, 16, 32),
  *          "streams" (queries of a batch in flight at once, 1..24, default 16; their scratch is allocated on first use),
  *          "group_order" (0 = auto, 1 = launch the long-sequence tiles first, 2 = launch the bulk first),

@@ -13,11 +13,10 @@ for l in open("gpurun_out/ss_$name.log"):
         print("$name: value %.0f GCUPS ms/step %.2f e2e %.0f launches %s tiles %s" % (d["value"], d["ms_per_step"], d["e2e"]["value"], d["gpu_launches"], d["engine"]["tiles_by_group"]))
 PY
 }
-run s8_xl3072 --scale 0.125
-run s8_xl1536 --scale 0.125 --xl-len 1536
-run s8_xl768 --scale 0.125 --xl-len 768
-run s4_xl3072 --scale 0.25
-run s4_xl1536 --scale 0.25 --xl-len 1536
-run s1_split1 --split 1
-run s1_split1_xl6144 --split 1 --xl-len 6144
-run s1_split0 --split 0
+run gl384 --steps 2
+run gl768 --steps 2 --group-len 768
+run gl1536 --steps 2 --group-len 1536
+run sq_gl384 --steps 2 --synth-queries 150
+run sq_gl768 --steps 2 --synth-queries 150 --group-len 768
+run sq_gl1536 --steps 2 --synth-queries 150 --group-len 1536
+run s8_gl768 --scale 0.125 --group-len 768

@@ -165,8 +165,9 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(power) if power else None}
 
 
-def cpu_sample_gcups(codes, offsets, qnames, qtexts, budget_s, threads=0):
-    """Oracle (port of the reference recurrence) on a bounded stride sample of the workload."""
+def cpu_sample_gcups(codes, offsets, qnames, qtexts, budget_s, threads=0, keep=None):
+    """Oracle (port of the reference recurrence) on a bounded stride sample of the workload. keep: a list that
+    receives (stride, scores of query k at the sampled sequences) for a parity check against the GPU's scores."""
     from oracle_lib import Oracle
     o = Oracle()
     cores = threads or o.max_threads()
@@ -181,7 +182,9 @@ def cpu_sample_gcups(codes, offsets, qnames, qtexts, budget_s, threads=0):
     cells = 0
     for q in qtexts:
         qc = o.encode(q)
-        o.scan(qc, codes, offsets, m, 2, 0, stride, cores)
+        sc = o.scan(qc, codes, offsets, m, 2, 0, stride, cores)
+        if keep is not None:
+            keep.append((stride, sc[0::stride].copy()))
         cells += len(qc) * sample_res
     dt = time.time() - t0
     return {"value": cells / dt * 1e-9, "unit": "GCUPS", "cores": cores, "kind": "port",
@@ -482,7 +485,18 @@ def main():
                 "topk_merge_ok": top_ok, "sample_parity_ok": sample_ok}
         if not args.no_cpu and world == 1:  # the CPU baseline is reported at N = 1 only
             names_t, qtexts = load_queries(None)
-            line["cpu_baseline"], _ = cpu_sample_gcups(codes, offsets, names_t, qtexts, args.cpu_seconds)
+            kept = []
+            line["cpu_baseline"], _ = cpu_sample_gcups(codes, offsets, names_t, qtexts, args.cpu_seconds, keep=kept)
+            # the oracle's scores of that sample double as a parity check of the measured configuration (full-size
+            # database, the engine's own choice of group_len and K): every query, every sampled sequence, bit-exact
+            try:
+                if args.workload == "config2" and not args.synth_queries and not args.affine and e2e_times:
+                    line["sample_parity_ok"] = bool(all(
+                        np.array_equal(out[qi][0::stride], want) for qi, (stride, want) in enumerate(kept)))
+                    line["sample_parity"] = "oracle vs GPU scores, every %d-th sequence x %d queries" % (
+                        kept[0][0], len(kept))
+            except Exception as ex:  # never lose the bench line to the checker
+                line["sample_parity"] = "check failed to run: %r" % (ex,)
         else:
             line["cpu_baseline"] = None
         if args.per_query:

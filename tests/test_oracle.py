@@ -72,3 +72,42 @@ def test_padding_is_score_neutral(oracle, queries):
     base = oracle.score(oracle.encode(q), oracle.encode(d), m)
     assert oracle.score(oracle.encode(q + "////"), oracle.encode(d + "///////"), m) == base
     assert list(oracle.encode("AUO/z*\r")) == [0, 24, 24, 24, 24, 24, 24]
+
+
+def _gotoh_py(q, d, m, go, ge):
+    """independent restatement (pure Python, full matrices) of the affine recurrences in oracle/sw_oracle.c"""
+    neg = -10 ** 9
+    H = [[0] * (len(d) + 1) for _ in range(len(q) + 1)]
+    E = [[neg] * (len(d) + 1) for _ in range(len(q) + 1)]
+    F = [[neg] * (len(d) + 1) for _ in range(len(q) + 1)]
+    best = 0
+    for i in range(1, len(q) + 1):
+        for j in range(1, len(d) + 1):
+            E[i][j] = max(E[i][j - 1] - ge, H[i][j - 1] - go)
+            F[i][j] = max(F[i - 1][j] - ge, H[i - 1][j] - go)
+            H[i][j] = max(0, H[i - 1][j - 1] + int(m[q[i - 1], d[j - 1]]), E[i][j], F[i][j])
+            best = max(best, H[i][j])
+    return best
+
+
+def test_affine_restatement_against_independent_gotoh(oracle):
+    """the reference has no affine mode (SWSolver.cu:8 is a comment), so the C restatement is pinned against a second,
+    independent implementation and against two hand-checked cases"""
+    from oracle_lib import pack_db
+    m = oracle.matrix("blosum50")
+    rng = np.random.default_rng(11)
+    seqs = [rng.integers(0, 5, int(n)).astype(np.uint8) for n in (0, 1, 7, 30, 64, 90)]
+    codes, offs = pack_db(seqs)
+    for ql in (1, 9, 40):
+        q = rng.integers(0, 5, ql).astype(np.uint8)
+        for go, ge in ((10, 2), (4, 1), (3, 0), (2, 2)):
+            got = oracle.scan_affine(q, codes, offs, m, go, ge)
+            want = [_gotoh_py(q, s, m, go, ge) for s in seqs]
+            assert got.tolist() == want, (ql, go, ge)
+    # hand-checked: AAAA vs AAGGAA with A:A = 5, gap of two: open 3 + extend 1 -> 4 * 5 - 4 = 16 (ungapped best: 10);
+    # with open 12 the gap no longer pays: 10
+    a = np.zeros(4, np.uint8)
+    d = np.array([0, 0, 7, 7, 0, 0], np.uint8)
+    c, o = pack_db([d])
+    assert oracle.scan_affine(a, c, o, m, 3, 1)[0] == 16
+    assert oracle.scan_affine(a, c, o, m, 12, 1)[0] == 10

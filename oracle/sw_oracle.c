@@ -228,7 +228,9 @@ int32_t swo_align(const uint8_t *q, const char *q_txt, uint32_t qlen, const uint
  * Gotoh's recurrences, the standard form for protein search: a gap of length L costs go + (L-1)*ge.
  *   E(i,j) = max(E(i,j-1) - ge, H(i,j-1) - go),  F(i,j) = max(F(i-1,j) - ge, H(i-1,j) - go),
  *   H(i,j) = max(0, H(i-1,j-1) + S, E(i,j), F(i,j)).   With go == ge it is the linear recurrence above.
- * Parity of the engine's affine mode is against this restatement only (the reference has no goldens for it). */
+ * Parity of the engine's affine mode is against this restatement only: the reference has no goldens for it, so for
+ * this mode the oracle is "parity unpinned" against the reference; tests/test_oracle.py pins it against an independent
+ * pure-Python Gotoh and two hand-checked cases instead. */
 int32_t swo_score_affine(const uint8_t *q, uint32_t qlen, const uint8_t *d, uint32_t dlen, const int8_t *m,
                          int32_t go, int32_t ge)
 {

@@ -312,3 +312,30 @@ def test_pipelined_passes_with_full_blocks(emu, oracle):
     assert np.array_equal(got, want) and rc >= 3
     got, _ = run(codes, offs, m, q, 16, 300, 1, force_i32=1)
     assert np.array_equal(got, want)
+
+
+def test_pipelined_passes_every_lane_group_class(oracle):
+    """a split set that reaches down to 2 lanes per pair: tiles with several pairs per warp (slots) publish one
+    progress value for all of them, items map to (tile, pass) through the per-class tables"""
+    L = ctypes.CDLL(os.path.join(ROOT, PKG, "lib", "libswbemu.so"))
+    L.swbemu_search_split.restype = ctypes.c_int
+    L.swbemu_search_split.argtypes = [_u8p, _u64p, ctypes.c_uint32, ctypes.c_uint32, _i8p, ctypes.c_int, _u8p,
+                                      ctypes.c_uint32, ctypes.c_int, ctypes.c_uint32, ctypes.c_int, ctypes.c_uint32,
+                                      ctypes.c_uint32, _i32p, ctypes.POINTER(ctypes.c_uint32)]
+    m = oracle.matrix("blosum50")
+    rng = np.random.default_rng(99)
+    lens = [17, 18, 20, 25, 31, 32, 33, 40, 60, 64, 65, 100, 128, 129, 200, 256, 257, 300, 500, 700, 5, 9, 12, 16]
+    rng.shuffle(lens)
+    codes, offs = pack_db(random_db(rng, lens, alphabet=20))
+    mm = np.ascontiguousarray(m, dtype=np.int8)
+    for ql in (1, 9, 33, 257):
+        q = rng.integers(0, 20, ql).astype(np.uint8)
+        want = oracle.scan(q, codes, offs, m)
+        for gl, xl in ((16, 16), (16, 40), (8, 8), (32, 32)):
+            for thr in (-1, 30):  # 30: most tiles also go through the pipelined int32 recompute
+                out = np.full(len(offs) - 1, -7, dtype=np.int32)
+                rc = ctypes.c_uint32()
+                r = L.swbemu_search_split(codes.ctypes.data_as(_u8p), offs.ctypes.data_as(_u64p), len(offs) - 1, gl,
+                                          mm.ctypes.data_as(_i8p), 2, q.ctypes.data_as(_u8p), len(q), 0, 0, thr, xl, 0,
+                                          out.ctypes.data_as(_i32p), ctypes.byref(rc))
+                assert r == 0 and np.array_equal(out, want), (ql, gl, xl, thr)

@@ -339,3 +339,23 @@ def test_pipelined_passes_every_lane_group_class(oracle):
                                           mm.ctypes.data_as(_i8p), 2, q.ctypes.data_as(_u8p), len(q), 0, 0, thr, xl, 0,
                                           out.ctypes.data_as(_i32p), ctypes.byref(rc))
                 assert r == 0 and np.array_equal(out, want), (ql, gl, xl, thr)
+
+
+def test_randomized_configurations(emu, oracle):
+    """40 random (database, query, group_len, K, xl_len, overflow threshold) draws through the host emulation of the
+    warp program, each against the oracle (fixed seed: the draw is part of the test)"""
+    rng = np.random.default_rng(20261018)
+    m = oracle.matrix("blosum50")
+    for it in range(40):
+        nseq = int(rng.integers(1, 40))
+        top = int(rng.choice([12, 60, 300, 900]))
+        lens = rng.integers(0, top, nseq)
+        codes, offs = pack_db(random_db(rng, lens, alphabet=int(rng.choice([4, 20, 25]))))
+        q = rng.integers(0, 24, int(rng.choice([1, 5, 8, 31, 64, 130, 400]))).astype(np.uint8)
+        gl = int(rng.choice([8, 16, 32, 64, 384]))
+        K = int(rng.choice([0, 8, 16, 32]))
+        xl = int(rng.choice([0, 16, 64, 256, 8192]))
+        thr = int(rng.choice([-1, -1, 10, 40, 200]))
+        want = oracle.scan(q, codes, offs, m)
+        got, _ = emu(codes, offs, m, q, K=K, group_len=gl, xl_len=xl, thr=thr)
+        assert np.array_equal(got, want), (it, nseq, top, len(q), gl, K, xl, thr)

@@ -70,7 +70,12 @@ class SwbPlanInfo(ctypes.Structure):
 ABI_SYMBOLS = [
     "swb_create", "swb_destroy", "swb_last_error", "swb_set_option", "swb_set_stream", "swb_set_scoring",
     "swb_set_scoring_preset", "swb_set_scoring_affine", "swb_scoring_matrix", "swb_encode", "swb_db_load", "swb_db_count", "swb_db_ids",
-    "swb_search", "swb_search_batch", "swb_fetch_scores", "swb_topk", "swb_stats", "swb_plan_describe",
+    "swb_search", "swb_search_batch", "swb_search_batch_scatter", "swb_search_batch_topk", "swb_fetch_scores",
+    "swb_topk", "swb_stats", "swb_plan_describe",
+    "swb_group_create", "swb_group_create_env", "swb_group_destroy", "swb_group_last_error", "swb_group_size", "swb_group_engine",
+    "swb_group_db_parts", "swb_group_set_option", "swb_group_set_scoring", "swb_group_set_scoring_preset",
+    "swb_group_set_scoring_affine", "swb_group_db_load", "swb_group_search_batch", "swb_group_search_batch_topk",
+    "swb_group_stats", "swb_layout_parts", "swb_layout_query_groups",
     "swb_microbench", "swb_align", "swb_read_fasta", "swb_read_uniprot_dat", "swb_free", "swb_dbfile_write",
     "swb_dbfile_open", "swb_dbfile_count", "swb_dbfile_first_id", "swb_dbfile_offsets", "swb_dbfile_codes",
     "swb_dbfile_close",
@@ -127,6 +132,42 @@ def lib():
     L.swb_search.argtypes = [vp, _u8p, ctypes.c_uint32, _i32p]
     L.swb_search_batch.restype = ctypes.c_int
     L.swb_search_batch.argtypes = [vp, _u8p, _u64p, ctypes.c_uint32, _i32p]
+    L.swb_search_batch_scatter.restype = ctypes.c_int
+    L.swb_search_batch_scatter.argtypes = [vp, _u8p, _u64p, ctypes.c_uint32, _i32p, ctypes.c_uint64]
+    L.swb_search_batch_topk.restype = ctypes.c_int
+    L.swb_search_batch_topk.argtypes = [vp, _u8p, _u64p, ctypes.c_uint32, ctypes.c_uint32, _u32p, _i32p]
+    L.swb_group_create.restype = ctypes.c_int
+    L.swb_group_create.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_int), ctypes.c_int]
+    L.swb_group_destroy.restype = None
+    L.swb_group_destroy.argtypes = [vp]
+    L.swb_group_last_error.restype = ctypes.c_char_p
+    L.swb_group_last_error.argtypes = [vp]
+    L.swb_group_size.restype = ctypes.c_int
+    L.swb_group_size.argtypes = [vp]
+    L.swb_group_engine.restype = vp
+    L.swb_group_engine.argtypes = [vp, ctypes.c_int]
+    L.swb_group_db_parts.restype = ctypes.c_int
+    L.swb_group_db_parts.argtypes = [vp]
+    L.swb_group_set_option.restype = ctypes.c_int
+    L.swb_group_set_option.argtypes = [vp, ctypes.c_char_p, ctypes.c_int64]
+    L.swb_group_set_scoring.restype = ctypes.c_int
+    L.swb_group_set_scoring.argtypes = [vp, _i8p, ctypes.c_int, ctypes.c_int]
+    L.swb_group_set_scoring_preset.restype = ctypes.c_int
+    L.swb_group_set_scoring_preset.argtypes = [vp, ctypes.c_int]
+    L.swb_group_set_scoring_affine.restype = ctypes.c_int
+    L.swb_group_set_scoring_affine.argtypes = [vp, _i8p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    L.swb_group_db_load.restype = ctypes.c_int
+    L.swb_group_db_load.argtypes = [vp, _u8p, _u64p, ctypes.c_uint32]
+    L.swb_group_search_batch.restype = ctypes.c_int
+    L.swb_group_search_batch.argtypes = [vp, _u8p, _u64p, ctypes.c_uint32, _i32p]
+    L.swb_group_search_batch_topk.restype = ctypes.c_int
+    L.swb_group_search_batch_topk.argtypes = [vp, _u8p, _u64p, ctypes.c_uint32, ctypes.c_uint32, _u32p, _i32p]
+    L.swb_group_stats.restype = ctypes.c_int
+    L.swb_group_stats.argtypes = [vp, ctypes.POINTER(SwbStats)]
+    L.swb_layout_parts.restype = ctypes.c_int
+    L.swb_layout_parts.argtypes = [ctypes.c_uint32, ctypes.c_int, ctypes.c_uint32]
+    L.swb_layout_query_groups.restype = ctypes.c_int
+    L.swb_layout_query_groups.argtypes = [_u64p, ctypes.c_uint32, ctypes.c_int, _u32p]
     L.swb_fetch_scores.restype = ctypes.c_int
     L.swb_fetch_scores.argtypes = [vp, ctypes.c_uint32, _i32p]
     L.swb_topk.restype = ctypes.c_int
@@ -260,6 +301,22 @@ def dbfile_read(path):
         L.swb_dbfile_close(h)
 
 
+def layout_parts(n, ndev, min_part_sequences=250000):
+    """database parts P of the P x R device grid (include/swb.h, engine group)"""
+    return int(lib().swb_layout_parts(int(n), int(ndev), int(min_part_sequences)))
+
+
+def layout_query_groups(qoffsets, groups):
+    """group (0..groups-1) of every query of a batch: equal total length, longest-processing-time first"""
+    qoffsets = np.ascontiguousarray(qoffsets, dtype=np.uint64)
+    nq = len(qoffsets) - 1
+    out = np.zeros(max(nq, 1), dtype=np.uint32)
+    rc = lib().swb_layout_query_groups(qoffsets.ctypes.data_as(_u64p), nq, int(groups), out.ctypes.data_as(_u32p))
+    if rc != 0:
+        raise SwbError("swb_layout_query_groups failed")
+    return out[:nq]
+
+
 def plan_describe(offsets, shard=0, nshards=1, group_len=0, want_ids=False):
     offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
     n = len(offsets) - 1
@@ -379,6 +436,25 @@ class Engine:
                                              outp), "swb_search_batch")
         return out if fetch else None
 
+    def search_batch_scatter(self, qcodes, qoffs, out):
+        """scores by database id into `out` (nq x n_total, shared by the engines of all shards)"""
+        nq = len(qoffs) - 1
+        assert out.dtype == np.int32 and out.flags.c_contiguous and out.shape[0] == nq
+        self._check(self._L.swb_search_batch_scatter(self._h, qcodes.ctypes.data_as(_u8p), qoffs.ctypes.data_as(_u64p),
+                                                     nq, out.ctypes.data_as(_i32p), out.shape[1]),
+                    "swb_search_batch_scatter")
+        return out
+
+    def search_batch_topk(self, qcodes, qoffs, k):
+        """device-side hit lists: (ids, scores), each nq x k, score descending / database id ascending"""
+        nq = len(qoffs) - 1
+        ids = np.zeros((nq, k), dtype=np.uint32)
+        top = np.zeros((nq, k), dtype=np.int32)
+        self._check(self._L.swb_search_batch_topk(self._h, qcodes.ctypes.data_as(_u8p), qoffs.ctypes.data_as(_u64p),
+                                                  nq, k, ids.ctypes.data_as(_u32p), top.ctypes.data_as(_i32p)),
+                    "swb_search_batch_topk")
+        return ids, top
+
     def fetch_scores(self, query_index):
         out = np.zeros(self.db_count(), dtype=np.int32)
         self._check(self._L.swb_fetch_scores(self._h, query_index, out.ctypes.data_as(_i32p)), "swb_fetch_scores")
@@ -407,6 +483,91 @@ class Engine:
     def stats(self):
         s = SwbStats()
         self._check(self._L.swb_stats(self._h, ctypes.byref(s)), "swb_stats")
+        return s.as_dict()
+
+
+class EngineGroup:
+    """Every GPU of the box in one process (swb_group_*): P database parts x R query groups."""
+
+    def __init__(self, devices=None, **options):
+        self._h = ctypes.c_void_p()
+        self._L = lib()
+        if devices is None:
+            rc = self._L.swb_group_create(ctypes.byref(self._h), None, 0)
+        elif isinstance(devices, int):
+            rc = self._L.swb_group_create(ctypes.byref(self._h), None, devices)
+        else:
+            arr = (ctypes.c_int * len(devices))(*devices)
+            rc = self._L.swb_group_create(ctypes.byref(self._h), arr, len(devices))
+        if rc != 0:
+            raise SwbError("swb_group_create failed: %s" % self._L.swb_group_last_error(None).decode())
+        self.n_total = 0
+        for k, v in options.items():
+            self.set_option(k, v)
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise SwbError("%s failed (%d): %s" % (what, rc, self._L.swb_group_last_error(self._h).decode()))
+
+    def close(self):
+        if self._h:
+            self._L.swb_group_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def size(self):
+        return int(self._L.swb_group_size(self._h))
+
+    def db_parts(self):
+        return int(self._L.swb_group_db_parts(self._h))
+
+    def set_option(self, key, value):
+        self._check(self._L.swb_group_set_option(self._h, key.encode(), int(value)), "swb_group_set_option(%s)" % key)
+
+    def set_scoring_preset(self, preset):
+        self._check(self._L.swb_group_set_scoring_preset(self._h, preset), "swb_group_set_scoring_preset")
+
+    def set_scoring_affine(self, matrix, gap_open, gap_extend):
+        m = np.ascontiguousarray(matrix, dtype=np.int8)
+        self._check(self._L.swb_group_set_scoring_affine(self._h, m.ctypes.data_as(_i8p), m.shape[0], gap_open,
+                                                         gap_extend), "swb_group_set_scoring_affine")
+
+    def db_load(self, codes, offsets):
+        codes = np.ascontiguousarray(codes, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        self._check(self._L.swb_group_db_load(self._h, codes.ctypes.data_as(_u8p), offsets.ctypes.data_as(_u64p),
+                                              len(offsets) - 1), "swb_group_db_load")
+        self.n_total = len(offsets) - 1
+
+    def search_batch_packed(self, qcodes, qoffs, out=None):
+        nq = len(qoffs) - 1
+        if out is None:
+            out = np.zeros((nq, self.n_total), dtype=np.int32)
+        self._check(self._L.swb_group_search_batch(self._h, qcodes.ctypes.data_as(_u8p), qoffs.ctypes.data_as(_u64p),
+                                                   nq, out.ctypes.data_as(_i32p)), "swb_group_search_batch")
+        return out
+
+    def search_batch(self, queries, out=None):
+        qcodes, qoffs = pack_sequences([np.ascontiguousarray(q, dtype=np.uint8) for q in queries])
+        return self.search_batch_packed(qcodes, qoffs, out=out)
+
+    def search_batch_topk(self, qcodes, qoffs, k):
+        nq = len(qoffs) - 1
+        ids = np.zeros((nq, k), dtype=np.uint32)
+        top = np.zeros((nq, k), dtype=np.int32)
+        self._check(self._L.swb_group_search_batch_topk(self._h, qcodes.ctypes.data_as(_u8p),
+                                                        qoffs.ctypes.data_as(_u64p), nq, k, ids.ctypes.data_as(_u32p),
+                                                        top.ctypes.data_as(_i32p)), "swb_group_search_batch_topk")
+        return ids, top
+
+    def stats(self):
+        s = SwbStats()
+        self._check(self._L.swb_group_stats(self._h, ctypes.byref(s)), "swb_group_stats")
         return s.as_dict()
 
 

@@ -325,9 +325,17 @@ extern "C" int swb_dbfile_open(const char *path, swb_dbfile **out)
     d->map = map;
     d->bytes = (size_t)st.st_size;
     memcpy(&d->hdr, map, sizeof(FileHeader));
-    const uint64_t need = sizeof(FileHeader) + sizeof(uint64_t) * ((uint64_t)d->hdr.n + 1) + d->hdr.residues;
+    // validate the header without overflow before any offset is touched: the sizes must add up to the file size exactly,
+    // the offsets must start at 0, never decrease and end at the residue count
+    const uint64_t body = d->bytes - sizeof(FileHeader);
     const uint64_t *offs = reinterpret_cast<const uint64_t *>((const char *)map + sizeof(FileHeader));
-    if (memcmp(d->hdr.magic, kMagic, 8) != 0 || need != d->bytes || offs[0] != 0 || offs[d->hdr.n] != d->hdr.residues) {
+    bool ok = memcmp(d->hdr.magic, kMagic, 8) == 0 && (uint64_t)d->hdr.n + 1 <= body / sizeof(uint64_t);
+    if (ok) {
+        const uint64_t offs_bytes = sizeof(uint64_t) * ((uint64_t)d->hdr.n + 1);
+        ok = d->hdr.residues == body - offs_bytes && offs[0] == 0 && offs[d->hdr.n] == d->hdr.residues;
+    }
+    for (uint64_t i = 0; ok && i < d->hdr.n; ++i) ok = offs[i + 1] >= offs[i] && offs[i + 1] <= d->hdr.residues;
+    if (!ok) {
         munmap(map, d->bytes);
         delete d;
         return SWB_ERR_ARG;

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "../../include/swb.h"
+#include "swb_internal.h"
 #include "swb_kernels.h"
 #include "swb_plan.h"
 
@@ -19,7 +20,6 @@
 #define SWB_MAX_COUNTERS 256
 #define SWB_MAX_SUB 3  // extra streams per slot: up to three distinct K values plus the split group per query
 #define SWB_CHUNK_ROWS 7168u          // query rows per launch when a query does not fit shared memory
-#define SWB_CHUNK_ROWS_QPAIR 1536u    // the same for query-pair jobs (4-byte profile entries)
 #define SWB_SMALL_SMEM_LIMIT (100u * 1024u)
 #define SWB_STAGE_BYTES (32u << 20)   // pinned staging buffers for the raw database upload
 
@@ -53,16 +53,22 @@ struct Slot {
     size_t prog_cap = 0;
     uint8_t *d_flags = nullptr;
     int32_t *d_sorted = nullptr;
-    int32_t *d_sorted2 = nullptr;  // second query of a query-pair job
-    uint32_t *d_profq = nullptr;   // query-pair profile [32][stride] of s16x2 words
-    size_t profq_cap = 0;
     uint32_t *d_bnd16 = nullptr;
     size_t bnd16_cap = 0;
     void *d_bnd32 = nullptr;
     size_t bnd32_cap = 0;
+    void *d_blog = nullptr;  // V16R: base log of the boundary rows
+    size_t blog_cap = 0;
     int32_t *h_scores = nullptr;  // pinned, n_local
     size_t h_scores_cap = 0;
-    int32_t *pending_dst[2] = {nullptr, nullptr};
+    int32_t *pending_dst = nullptr;   // caller memory the scores of the job in flight go to (finish_slot)
+    bool pending_scatter = false;     // pending_dst is a full-database vector: entry shard_ids[k] receives score k
+    uint32_t *d_topk = nullptr;       // device-side selection: [k ids | k scores]
+    uint32_t *h_topk = nullptr;       // pinned copy
+    size_t topk_cap = 0, h_topk_cap = 0;
+    uint32_t *pending_ids = nullptr;  // caller memory of the job's hit list
+    int32_t *pending_top = nullptr;
+    uint32_t pending_k = 0;
 };
 
 struct swb_engine {
@@ -87,10 +93,13 @@ struct swb_engine {
     SwbPlanOpts plan_opts;
     int opt_k = 0;
     bool group_len_auto = true;  // swb_db_load picks group_len from the shard size (below) unless the option sets it
-    int opt_split_fill = 0;   // work items a split launch must keep before its K goes up from 8 (0 = K stays 8)
     int opt_batch_order = 0;  // batches: 0 = longest query first, 1 = in the caller's order
-    int opt_pair_queries = 0; // batches: pack two queries into the halves of the s16x2 lanes (V16Q). Opt-in: measured
-                              // 0.77x of V16 on B200 (4 B of profile per packed cell: shared-memory bound)
+    int rebase_shift = 0;     // V16R block size for the current scoring scheme (0: V16R cannot run, exact passes use V32)
+    int opt_exact = 0;        // exact passes: 0 = V16R where the scheme allows it, 1 = always V32 (int32)
+    int opt_split_k = 0;      // rows per lane of the pipelined-pass groups: 0 = auto, 8, 16
+    uint32_t opt_direct_len = 10000;  // pipelined tiles at least this wide against queries at least this long skip the
+                              // plain s16 pass and are scored by V16R at once (their true scores pass 32767 anyway:
+                              // with the reference's gap of 2, random long sequences score ~2.7 per residue); 0 = never
     int opt_split = -1;       // pipelined passes for the very long tiles: 1 on, 0 off, -1 auto = on for small shards
                               // (fewer tiles than twice the GPU's warp slots), where a few long tiles are the critical
                               // path of a query (+10 % at 1/8 of Swiss-Prot, +3 % at 1/4); on a large shard the bulk
@@ -98,6 +107,7 @@ struct swb_engine {
     int opt_group_order = 0;  // 0 auto (lone query: longest tiles first; batch: bulk first), 1 longest first, 2 bulk first
     uint32_t cur_nq = 1;
     int nslots = 16;
+    int load_threads = 4;  // host threads that gather a sharded load into the staging buffers
     uint32_t chunk_rows = SWB_CHUNK_ROWS;  // query rows per launch for queries beyond shared memory
     bool chunk_rows_set = false;           // false: batches on small shards use 2048-row launches (below)
     // database
@@ -107,10 +117,11 @@ struct swb_engine {
     SwbTile *d_tiles = nullptr;
     uint8_t *d_residues = nullptr;
     uint32_t *d_out_pos = nullptr;
+    uint32_t *d_shard_ids = nullptr;  // database ids of the shard in output order (sharded loads; else position == id)
     uint8_t *d_raw = nullptr;       // raw concatenated codes (input of the pack kernel)
     uint64_t *d_seq_off = nullptr;
     uint32_t *d_seq_len = nullptr;
-    size_t tiles_cap = 0, residues_cap = 0, out_pos_cap = 0, raw_cap = 0, seq_off_cap = 0, seq_len_cap = 0;
+    size_t tiles_cap = 0, residues_cap = 0, out_pos_cap = 0, raw_cap = 0, seq_off_cap = 0, seq_len_cap = 0, shard_ids_cap = 0;
     uint8_t *h_stage[2] = {nullptr, nullptr};  // pinned staging for the raw upload
     size_t stage_cap[2] = {0, 0};
     cudaEvent_t ev_stage[2] = {nullptr, nullptr};
@@ -152,12 +163,21 @@ static void free_slot_db(Slot &s)
     if (s.d_state) cudaFree(s.d_state);
     if (s.d_bnd16) cudaFree(s.d_bnd16);
     if (s.d_bnd32) cudaFree(s.d_bnd32);
+    if (s.d_blog) cudaFree(s.d_blog);
+    s.d_blog = nullptr;
+    s.blog_cap = 0;
     if (s.d_prog) cudaFree(s.d_prog);
     s.d_prog = nullptr;
     s.prog_cap = 0;
-    if (s.d_profq) cudaFree(s.d_profq);
-    s.d_profq = nullptr;
-    s.profq_cap = 0;
+    if (s.d_topk) cudaFree(s.d_topk);
+    if (s.h_topk) cudaFreeHost(s.h_topk);
+    s.d_topk = nullptr;
+    s.h_topk = nullptr;
+    s.topk_cap = s.h_topk_cap = 0;
+    s.busy = false;
+    s.pending_dst = nullptr;
+    s.pending_ids = nullptr;
+    s.pending_top = nullptr;
     if (s.h_scores) cudaFreeHost(s.h_scores);
     s.d_state = nullptr;
     s.d_bnd16 = nullptr;
@@ -168,7 +188,7 @@ static void free_slot_db(Slot &s)
 
 static void free_db(swb_engine *e)
 {
-    void *dev[] = {e->d_tiles, e->d_residues, e->d_out_pos, e->d_out, e->d_raw, e->d_seq_off, e->d_seq_len};
+    void *dev[] = {e->d_tiles, e->d_residues, e->d_out_pos, e->d_out, e->d_raw, e->d_seq_off, e->d_seq_len, e->d_shard_ids};
     for (void *p : dev)
         if (p) cudaFree(p);
     e->d_tiles = nullptr;
@@ -178,7 +198,8 @@ static void free_db(swb_engine *e)
     e->d_raw = nullptr;
     e->d_seq_off = nullptr;
     e->d_seq_len = nullptr;
-    e->tiles_cap = e->residues_cap = e->out_pos_cap = e->raw_cap = e->seq_off_cap = e->seq_len_cap = 0;
+    e->d_shard_ids = nullptr;
+    e->tiles_cap = e->residues_cap = e->out_pos_cap = e->raw_cap = e->seq_off_cap = e->seq_len_cap = e->shard_ids_cap = 0;
     e->out_cap = 0;
     if (e->d_align_h) cudaFree(e->d_align_h);
     if (e->d_align_dir) cudaFree(e->d_align_dir);
@@ -198,6 +219,7 @@ static void free_db(swb_engine *e)
     }
     for (int i = 0; i < SWB_MAX_SLOTS; ++i) free_slot_db(e->slots[i]);
     e->db_loaded = false;
+    e->last_nq = 0;
 }
 
 extern "C" int swb_create(swb_engine **out, int device)
@@ -218,9 +240,10 @@ extern "C" int swb_create(swb_engine **out, int device)
     swb_engine *e = new swb_engine();
     e->device = device;
     memset(&e->stats, 0, sizeof e->stats);
+    // every failure path releases what was created so far (swb_destroy copes with a half-built engine)
     auto bail = [&](const char *what, cudaError_t err) {
         g_create_error = std::string(what) + ": " + cudaGetErrorString(err);
-        delete e;
+        swb_destroy(e);
         return SWB_ERR_CUDA;
     };
     if ((ce = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", ce);
@@ -228,28 +251,30 @@ extern "C" int swb_create(swb_engine **out, int device)
     if ((ce = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail("cudaGetDeviceProperties", ce);
     if (prop.major < 10) {
         g_create_error = std::string("device ") + prop.name + " is not sm_100-class; this library targets B200 only";
-        delete e;
+        swb_destroy(e);
         return SWB_ERR_CUDA;
     }
     e->sm_count = prop.multiProcessorCount;
     e->smem_optin = prop.sharedMemPerBlockOptin;
+    auto quiet_event = [&](cudaEvent_t *ev) { return cudaEventCreateWithFlags(ev, cudaEventDisableTiming); };
     if ((ce = cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking)) != cudaSuccess)
         return bail("cudaStreamCreate", ce);
-    cudaEventCreate(&e->ev_start);
-    cudaEventCreate(&e->ev_stop);
-    cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming);
+    if ((ce = cudaEventCreate(&e->ev_start)) != cudaSuccess) return bail("cudaEventCreate", ce);
+    if ((ce = cudaEventCreate(&e->ev_stop)) != cudaSuccess) return bail("cudaEventCreate", ce);
+    if ((ce = quiet_event(&e->ev_fork)) != cudaSuccess) return bail("cudaEventCreate", ce);
     for (int i = 0; i < SWB_MAX_SLOTS; ++i) {
-        if ((ce = cudaStreamCreateWithFlags(&e->slots[i].stream, cudaStreamNonBlocking)) != cudaSuccess)
+        Slot &sl = e->slots[i];
+        if ((ce = cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking)) != cudaSuccess)
             return bail("cudaStreamCreate", ce);
-        cudaEventCreateWithFlags(&e->slots[i].done, cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&e->slots[i].ev_fork, cudaEventDisableTiming);
+        if ((ce = quiet_event(&sl.done)) != cudaSuccess) return bail("cudaEventCreate", ce);
+        if ((ce = quiet_event(&sl.ev_fork)) != cudaSuccess) return bail("cudaEventCreate", ce);
         for (int k = 0; k < SWB_MAX_SUB; ++k) {
-            if ((ce = cudaStreamCreateWithFlags(&e->slots[i].sub[k], cudaStreamNonBlocking)) != cudaSuccess)
+            if ((ce = cudaStreamCreateWithFlags(&sl.sub[k], cudaStreamNonBlocking)) != cudaSuccess)
                 return bail("cudaStreamCreate", ce);
-            cudaEventCreateWithFlags(&e->slots[i].ev_sub[k], cudaEventDisableTiming);
+            if ((ce = quiet_event(&sl.ev_sub[k])) != cudaSuccess) return bail("cudaEventCreate", ce);
         }
-        cudaEventCreateWithFlags(&e->ev_join[i], cudaEventDisableTiming);
-        if ((ce = cudaMalloc(&e->slots[i].d_recount, sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc", ce);
+        if ((ce = quiet_event(&e->ev_join[i])) != cudaSuccess) return bail("cudaEventCreate", ce);
+        if ((ce = cudaMalloc(&sl.d_recount, sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc", ce);
     }
     if ((ce = cudaMalloc(&e->d_mat, SWB_ALPHA * SWB_ALPHA)) != cudaSuccess) return bail("cudaMalloc", ce);
     if ((ce = cudaMallocHost(&e->h_recount, SWB_MAX_SLOTS * sizeof(uint32_t))) != cudaSuccess)
@@ -314,20 +339,27 @@ extern "C" int swb_set_option(swb_engine *e, const char *key, int64_t value)
     } else if (!strcmp(key, "xl_len")) {
         if (value < 0 || value > (1ll << 31)) return fail(e, SWB_ERR_ARG, "xl_len out of range");
         e->plan_opts.xl_len = (uint32_t)value;
-    } else if (!strcmp(key, "split_fill")) {
-        if (value < 0 || value > (1 << 30)) return fail(e, SWB_ERR_ARG, "split_fill out of range");
-        e->opt_split_fill = (int)value;
     } else if (!strcmp(key, "batch_order")) {
         if (value < 0 || value > 1) return fail(e, SWB_ERR_ARG, "batch_order must be 0 (longest query first) or 1 (as given)");
         e->opt_batch_order = (int)value;
-    } else if (!strcmp(key, "pair_queries")) {
-        e->opt_pair_queries = value != 0;
     } else if (!strcmp(key, "split")) {
         if (value < -1 || value > 1) return fail(e, SWB_ERR_ARG, "split must be -1 (auto), 0 or 1");
         e->opt_split = (int)value;
     } else if (!strcmp(key, "group_order")) {
         if (value < 0 || value > 2) return fail(e, SWB_ERR_ARG, "group_order must be 0, 1 or 2");
         e->opt_group_order = (int)value;
+    } else if (!strcmp(key, "exact")) {
+        if (value < 0 || value > 1) return fail(e, SWB_ERR_ARG, "exact must be 0 (rebased s16 where possible) or 1 (int32)");
+        e->opt_exact = (int)value;
+    } else if (!strcmp(key, "split_k")) {
+        if (value != 0 && value != 8 && value != 16) return fail(e, SWB_ERR_ARG, "split_k must be 0, 8 or 16");
+        e->opt_split_k = (int)value;
+    } else if (!strcmp(key, "direct_len")) {
+        if (value < 0 || value > (1ll << 31)) return fail(e, SWB_ERR_ARG, "direct_len out of range");
+        e->opt_direct_len = (uint32_t)value;
+    } else if (!strcmp(key, "load_threads")) {
+        if (value < 1 || value > 64) return fail(e, SWB_ERR_ARG, "load_threads must be 1..64");
+        e->load_threads = (int)value;
     } else if (!strcmp(key, "chunk_rows")) {
         if (value < 1024 || value > SWB_CHUNK_ROWS || value % 1024) return fail(e, SWB_ERR_ARG, "chunk_rows must be a multiple of 1024 up to 7168");
         e->chunk_rows = (uint32_t)value;
@@ -378,6 +410,7 @@ extern "C" int swb_set_scoring_affine(swb_engine *e, const int8_t *matrix, int a
     e->affine = gap_extend != gap;
     e->max_s = mx;
     e->min_s = mn;
+    e->rebase_shift = e->affine ? 0 : swb_rebase_shift(mx, mn, gap, 16u * 32u);
     CU(cudaMemcpy(e->d_mat, e->h_mat, sizeof m, cudaMemcpyHostToDevice));
     e->scoring_set = true;
     return SWB_OK;
@@ -441,8 +474,35 @@ static cudaError_t upload_staged(swb_engine *e, const uint8_t *src, uint64_t byt
     return cudaSuccess;
 }
 
-extern "C" int swb_db_load(swb_engine *e, const uint8_t *codes, const uint64_t *offsets, uint32_t n, uint32_t shard,
-                           uint32_t nshards)
+// Fills dst with bytes [lo, hi) of the shard's residues in sorted order (sequence s sits at goff[s] of that stream): the
+// gather of a sharded load, cut into equal byte ranges for `threads` host threads.
+static void gather_range(const SwbPlan &pl, const std::vector<uint64_t> &goff, const uint8_t *codes, uint64_t lo,
+                         uint64_t hi, uint8_t *dst, int threads)
+{
+    auto work = [&](uint64_t a, uint64_t b) {
+        if (a >= b) return;
+        size_t sq = (size_t)(std::upper_bound(goff.begin(), goff.end(), a) - goff.begin()) - 1;
+        while (a < b) {
+            const uint64_t within = a - goff[sq];
+            const uint64_t take = std::min<uint64_t>(pl.seq_len[sq] - within, b - a);
+            memcpy(dst + (a - lo), codes + pl.seq_off[sq] + within, (size_t)take);
+            a += take;
+            ++sq;
+        }
+    };
+    if (threads <= 1 || hi - lo < (1u << 20)) return work(lo, hi);
+    std::vector<std::thread> pool;
+    const uint64_t step = (hi - lo + (uint64_t)threads - 1) / (uint64_t)threads;
+    for (int t = 1; t < threads; ++t)
+        pool.emplace_back(work, std::min(hi, lo + step * (uint64_t)t), std::min(hi, lo + step * (uint64_t)(t + 1)));
+    work(lo, std::min(hi, lo + step));
+    for (std::thread &th : pool) th.join();
+}
+
+// sorted_order: the ids of the WHOLE database by descending length (swb_sort_by_length), or NULL to sort here. An engine
+// group sorts once and hands the same order to all of its engines.
+int swb_db_load_sorted(swb_engine *e, const uint8_t *codes, const uint64_t *offsets, uint32_t n, uint32_t shard,
+                       uint32_t nshards, const uint32_t *sorted_order)
 {
     if (!e || !offsets || (!codes && n && offsets[n] != offsets[0])) return SWB_ERR_ARG;
     if (nshards == 0) nshards = 1;
@@ -454,6 +514,7 @@ extern "C" int swb_db_load(swb_engine *e, const uint8_t *codes, const uint64_t *
     CU(cudaStreamSynchronize(st));
     for (int i = 0; i < SWB_MAX_SLOTS; ++i) CU(cudaStreamSynchronize(e->slots[i].stream));
     e->db_loaded = false;
+    e->last_nq = 0;  // results of the previous database are gone (swb_fetch_scores must not index the new shard with them)
     // group_len (longest sequence that runs one lane per pair). One-lane tiles are the cheapest per cell (no shuffles,
     // conflict-free profile reads, least row padding), so a shard with plenty of tiles wants them for as many sequences
     // as possible: measured on the benchmark database, 384 / 768 / 1536 give 8,830 / 9,094 / 9,108 GCUPS (20 reference
@@ -471,7 +532,8 @@ extern "C" int swb_db_load(swb_engine *e, const uint8_t *codes, const uint64_t *
     int rc = 0;
     std::thread planner;
     if (early_upload) {
-        planner = std::thread([&]() { rc = swb_build_plan(offsets, n, shard, nshards, e->plan_opts, e->plan); });
+        planner = std::thread(
+            [&]() { rc = swb_build_plan(offsets, n, shard, nshards, e->plan_opts, e->plan, sorted_order); });
         const uint64_t bytes = offsets[n] - offsets[0];
         int urc = SWB_OK;
         cudaError_t ce = GROW_DEV(e->d_raw, e->raw_cap, bytes);
@@ -480,7 +542,7 @@ extern "C" int swb_db_load(swb_engine *e, const uint8_t *codes, const uint64_t *
         planner.join();
         if (urc != SWB_OK) return urc;
     } else {
-        rc = swb_build_plan(offsets, n, shard, nshards, e->plan_opts, e->plan);
+        rc = swb_build_plan(offsets, n, shard, nshards, e->plan_opts, e->plan, sorted_order);
     }
     if (rc != 0) return fail(e, SWB_ERR_ARG, "bad offsets (decreasing, or a sequence longer than 2^31-16)");
     const double t1 = wall_ms();
@@ -503,45 +565,34 @@ extern "C" int swb_db_load(swb_engine *e, const uint8_t *codes, const uint64_t *
         CU(GROW_DEV(e->d_tiles, e->tiles_cap, sizeof(SwbTile) * ntiles));
         CU(GROW_DEV(e->d_residues, e->residues_cap, pl.res_bytes));
         CU(GROW_DEV(e->d_out_pos, e->out_pos_cap, sizeof(uint32_t) * nl));
+        if (gather) CU(GROW_DEV(e->d_shard_ids, e->shard_ids_cap, sizeof(uint32_t) * nl));
         for (int i = 0; i < SWB_MAX_SLOTS; ++i) e->slots[i].ready = false;  // per-stream scratch is (re)sized on first use
         t2 = wall_ms();
-        // stream the raw codes through two pinned staging buffers: the host copy of slice i+1 overlaps the
-        // asynchronous H2D of slice i
-        if (raw_bytes && gather) {
-            const size_t stage = (size_t)std::min<uint64_t>(SWB_STAGE_BYTES, raw_bytes);
-            for (int i = 0; i < 2; ++i) {
-                CU(GROW_HOST(e->h_stage[i], e->stage_cap[i], stage));
-                if (!e->ev_stage[i]) CU(cudaEventCreateWithFlags(&e->ev_stage[i], cudaEventDisableTiming));
-            }
-            int b = 0;
-            if (!gather) {
-                // uploaded above, beside the plan build (early_upload)
-            } else {
-                uint64_t done = 0;
-                uint32_t sq = 0, within = 0;
-                while (done < raw_bytes) {
+        if (gather) {
+            // positions in the gathered stream, then the stream itself through the two pinned staging buffers: the host
+            // gather of slice i+1 (a few threads, byte-balanced) overlaps the asynchronous H2D of slice i
+            std::vector<uint64_t> goff(nl + 1);
+            goff[0] = 0;
+            for (uint32_t s = 0; s < nl; ++s) goff[s + 1] = goff[s] + pl.seq_len[s];
+            if (raw_bytes) {
+                const size_t stage = (size_t)std::min<uint64_t>(SWB_STAGE_BYTES, raw_bytes);
+                for (int i = 0; i < 2; ++i) {
+                    CU(GROW_HOST(e->h_stage[i], e->stage_cap[i], stage));
+                    if (!e->ev_stage[i]) CU(cudaEventCreateWithFlags(&e->ev_stage[i], cudaEventDisableTiming));
+                }
+                int b = 0;
+                for (uint64_t done = 0; done < raw_bytes; done += stage, b ^= 1) {
+                    const uint64_t len = std::min<uint64_t>(stage, raw_bytes - done);
                     CU(cudaEventSynchronize(e->ev_stage[b]));
-                    size_t fill = 0;
-                    while (fill < stage && sq < nl) {
-                        const size_t take = std::min<size_t>(pl.seq_len[sq] - within, stage - fill);
-                        memcpy(e->h_stage[b] + fill, codes + pl.seq_off[sq] + within, take);
-                        fill += take;
-                        within += (uint32_t)take;
-                        if (within == pl.seq_len[sq]) { ++sq; within = 0; }
-                    }
-                    CU(cudaMemcpyAsync(e->d_raw + done, e->h_stage[b], fill, cudaMemcpyHostToDevice, st));
+                    gather_range(pl, goff, codes, done, done + len, e->h_stage[b], e->load_threads);
+                    CU(cudaMemcpyAsync(e->d_raw + done, e->h_stage[b], (size_t)len, cudaMemcpyHostToDevice, st));
                     CU(cudaEventRecord(e->ev_stage[b], st));
-                    done += fill;
-                    b ^= 1;
                 }
             }
-        }
-        // offsets into the uploaded buffer
-        if (!gather) {
-            for (uint32_t s = 0; s < nl; ++s) pl.seq_off[s] -= base;
+            for (uint32_t s = 0; s < nl; ++s) pl.seq_off[s] = goff[s];  // offsets into the uploaded buffer
+            CU(cudaMemcpyAsync(e->d_shard_ids, pl.shard_ids.data(), sizeof(uint32_t) * nl, cudaMemcpyHostToDevice, st));
         } else {
-            uint64_t at = 0;
-            for (uint32_t s = 0; s < nl; ++s) { pl.seq_off[s] = at; at += pl.seq_len[s]; }
+            for (uint32_t s = 0; s < nl; ++s) pl.seq_off[s] -= base;
         }
         CU(cudaMemcpyAsync(e->d_seq_off, pl.seq_off.data(), sizeof(uint64_t) * nl, cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(e->d_seq_len, pl.seq_len.data(), sizeof(uint32_t) * nl, cudaMemcpyHostToDevice, st));
@@ -562,6 +613,12 @@ extern "C" int swb_db_load(swb_engine *e, const uint8_t *codes, const uint64_t *
     e->stats.tiles = ntiles;
     for (int l = 0; l <= SWB_MAX_LOGG; ++l) e->stats.tiles_by_group[l] = pl.tiles_by_logg[l];
     return SWB_OK;
+}
+
+extern "C" int swb_db_load(swb_engine *e, const uint8_t *codes, const uint64_t *offsets, uint32_t n, uint32_t shard,
+                           uint32_t nshards)
+{
+    return swb_db_load_sorted(e, codes, offsets, n, shard, nshards, nullptr);
 }
 
 extern "C" uint32_t swb_db_count(const swb_engine *e) { return (e && e->db_loaded) ? e->plan.n_local : 0; }
@@ -585,10 +642,10 @@ struct LaunchShape {
 
 static int shape_for(swb_engine *e, int K, int mode, bool split, uint32_t smem_rows, uint32_t ntiles, LaunchShape &ls)
 {
-    const bool per_item = split && K == 8;  // one warp per block, each work item stages the rows of its pass
+    const bool per_item = split;  // one warp per block, each work item stages the rows of its pass
     if (per_item) smem_rows = (uint32_t)K * 32u;
     ls.smem_rows = smem_rows;
-    ls.smem = mode == SWB_MODE_QPAIR ? (size_t)SWB_ALPHA * (smem_rows + 1) * 4 : (size_t)SWB_ALPHA * (smem_rows + 4);
+    ls.smem = (size_t)SWB_ALPHA * (smem_rows + 4);
     if (ls.smem > e->smem_optin) return fail(e, SWB_ERR_ARG, "internal: query chunk does not fit shared memory");
     ls.block_cfg = ls.smem <= SWB_SMALL_SMEM_LIMIT ? SWB_BLOCK_SMALL : SWB_BLOCK_LARGE;
     int per_sm = 0;
@@ -614,7 +671,7 @@ static int shape_for(swb_engine *e, int K, int mode, bool split, uint32_t smem_r
 
 // Per-stream scratch of the loaded database, sized on the slot's first use after a load (grow-only buffers): a lone
 // query touches one slot, a batch as many as it has jobs in flight. State layout: [launch counters | tile flags |
-// scores of query A in sorted order | scores of query B (query-pair jobs)].
+// scores in sorted order].
 static int ensure_slot(swb_engine *e, Slot &s)
 {
     if (s.ready) return SWB_OK;
@@ -623,23 +680,25 @@ static int ensure_slot(swb_engine *e, Slot &s)
     const size_t flags_bytes = swb_roundup((uint32_t)pl.tiles.size(), 16);
     const size_t sorted_bytes = sizeof(int32_t) * 2 * (size_t)((nl + 1) / 2);
     const size_t head = sizeof(uint32_t) * SWB_MAX_COUNTERS;
-    s.state_bytes = head + flags_bytes + 2 * sorted_bytes;
+    s.state_bytes = head + flags_bytes + sorted_bytes;
     CU(GROW_DEV(s.d_state, s.state_cap, s.state_bytes));
     s.d_counters = reinterpret_cast<uint32_t *>(s.d_state);
     s.d_flags = s.d_state + head;
     s.d_sorted = reinterpret_cast<int32_t *>(s.d_state + head + flags_bytes);
-    s.d_sorted2 = reinterpret_cast<int32_t *>(s.d_state + head + flags_bytes + sorted_bytes);
     CU(GROW_DEV(s.d_bnd16, s.bnd16_cap, sizeof(uint32_t) * pl.bnd_elems));
-    CU(GROW_HOST(s.h_scores, s.h_scores_cap, 2 * sizeof(int32_t) * (size_t)nl));
+    CU(GROW_HOST(s.h_scores, s.h_scores_cap, sizeof(int32_t) * (size_t)nl));
     s.ready = true;
     return SWB_OK;
 }
 
-// the launches of one pass (one arithmetic policy over one profile): every launch group on its own stream
+// the launches of one pass (one arithmetic policy over one profile): every launch group on its own stream. `extra`
+// (may be NULL) are groups of the V16R policy that run beside this pass on tiles of their own (the direct set).
 static int enqueue_pass(swb_engine *e, Slot &s, int mode, SwbScoreParams &p, const SwbQueryPlan &qp,
-                        const std::vector<SwbLaunchGroup> &groups, uint32_t &counter)
+                        const std::vector<SwbLaunchGroup> &groups, uint32_t &counter, uint32_t *prog,
+                        const std::vector<SwbLaunchGroup> *extra, uint32_t *prog_extra)
 {
-    const size_t ng = groups.size();
+    const size_t nmain = groups.size();
+    const size_t ng = nmain + (extra ? extra->size() : 0);
     if (ng > 1 + SWB_MAX_SUB) return fail(e, SWB_ERR_ARG, "internal: too many launch groups");
     // fork: the launch groups of a pass are independent of each other (disjoint tiles)
     if (ng > 1) {
@@ -647,7 +706,9 @@ static int enqueue_pass(swb_engine *e, Slot &s, int mode, SwbScoreParams &p, con
         for (size_t gi = 1; gi < ng; ++gi) CU(cudaStreamWaitEvent(s.sub[gi - 1], s.ev_fork, 0));
     }
     for (size_t gi = 0; gi < ng; ++gi) {
-        const SwbLaunchGroup &g = groups[gi];
+        const bool is_extra = gi >= nmain;
+        const SwbLaunchGroup &g = is_extra ? (*extra)[gi - nmain] : groups[gi];
+        const int gmode = is_extra ? SWB_MODE_R16 : mode;
         cudaStream_t st = gi == 0 ? s.stream : s.sub[gi - 1];
         for (int r = 0; r < SWB_MAX_RANGES; ++r) {
             p.range_start[r] = g.range_start[r];
@@ -656,26 +717,28 @@ static int enqueue_pass(swb_engine *e, Slot &s, int mode, SwbScoreParams &p, con
         size_t prog_at = 0;
         std::vector<SwbQueryChunk> chunks;
         swb_group_chunks(qp, g, chunks);
+        uint32_t *const recount = p.recount;
+        if (is_extra) p.recount = nullptr;  // tiles scored by V16R at once are no recomputes
         for (size_t c = 0; c < chunks.size(); ++c) {
             const SwbQueryChunk &ch = chunks[c];
-            // work items of the launch: tiles, (tile, pass) for split groups, (tile, half) for query pairs
-            p.ntiles = mode == SWB_MODE_QPAIR ? 2 * g.ntiles : g.ntiles;
-            p.prog = g.split ? s.d_prog + prog_at : nullptr;
+            // work items of the launch: tiles, or (tile, pass) for split groups
+            p.ntiles = g.ntiles;
+            p.prog = g.split ? (is_extra ? prog_extra : prog) + prog_at : nullptr;
             if (g.split) prog_at += swb_split_items(ch.rows, g, &p);  // sets p.ntiles to the number of items
             LaunchShape ls;
-            int rc = shape_for(e, g.K, mode, g.split, swb_group_smem_rows(ch.rows, g), p.ntiles, ls);
+            int rc = shape_for(e, g.K, gmode, g.split, swb_group_smem_rows(ch.rows, g), p.ntiles, ls);
             if (rc != SWB_OK) return rc;
             p.row0 = ch.row0;
             p.rows = ch.rows;
             p.smem_rows = ls.smem_rows;
             p.warps_active = ls.warps_active;
-            p.split_stage_item = g.split && g.K == 8;
             p.first_chunk = ch.first;
             p.last_chunk = ch.last;
             p.counter = s.d_counters + counter++;
-            CU(swb_launch_score(g.K, mode, g.split, ls.block_cfg, p, ls.grid, ls.smem, st));
+            CU(swb_launch_score(g.K, gmode, g.split, ls.block_cfg, p, ls.grid, ls.smem, st));
             e->stats.kernel_launches += 1;
         }
+        p.recount = recount;
     }
     for (size_t gi = 1; gi < ng; ++gi) {  // join
         CU(cudaEventRecord(s.ev_sub[gi - 1], s.sub[gi - 1]));
@@ -684,12 +747,10 @@ static int enqueue_pass(swb_engine *e, Slot &s, int mode, SwbScoreParams &p, con
     return SWB_OK;
 }
 
-// Enqueues everything one job needs; a job is one query, or two queries of a batch packed into the two halves of the
-// s16x2 lanes (V16Q). Results land in d_out[qi] (and d_out[qi2]).
+// Enqueues everything one query needs. Results land in d_out[qi].
 // Stream layout per slot: profile build and clears on slot.stream, then one sub-stream per launch group (the tiles of
 // the group sizes that share a K) so that the few long-sequence tiles run beside the bulk, then the scatter.
-static int enqueue_job(swb_engine *e, Slot &s, uint32_t qi, const uint8_t *q, uint32_t qlen, bool pair, uint32_t qi2,
-                       const uint8_t *q2, uint32_t qlen2)
+static int enqueue_job(swb_engine *e, Slot &s, uint32_t qi, const uint8_t *q, uint32_t qlen)
 {
     SwbPlan &pl = e->plan;
     const uint32_t nl = pl.n_local;
@@ -697,11 +758,9 @@ static int enqueue_job(swb_engine *e, Slot &s, uint32_t qi, const uint8_t *q, ui
     int rc = ensure_slot(e, s);
     if (rc != SWB_OK) return rc;
     int32_t *out = e->d_out + (size_t)qi * nl;
-    int32_t *out2 = pair ? e->d_out + (size_t)qi2 * nl : nullptr;
-    const uint32_t rows = pair ? std::max(qlen, qlen2) : qlen;
+    const uint32_t rows = qlen;
     if (rows == 0 || pl.tiles.empty() || pl.max_len == 0) {
         CU(cudaMemsetAsync(out, 0, sizeof(int32_t) * nl, s.stream));
-        if (pair) CU(cudaMemsetAsync(out2, 0, sizeof(int32_t) * nl, s.stream));
         return SWB_OK;
     }
     const int ovf_thr = 32767 - e->max_s;
@@ -709,9 +768,8 @@ static int enqueue_job(swb_engine *e, Slot &s, uint32_t qi, const uint8_t *q, ui
     for (int l = 0; l <= SWB_MAX_LOGG; ++l)
         if (pl.tiles_by_logg[l]) present |= 1u << l;
     const bool longest_first = e->opt_group_order == 1 || (e->opt_group_order == 0 && e->cur_nq <= 1);
-    const bool affine = e->affine;  // never paired (swb_search_batch), never split
-    const int mode0 = affine ? SWB_MODE_S16A : (pair ? SWB_MODE_QPAIR : SWB_MODE_S16);
-    const int mode1 = affine ? SWB_MODE_I32A : SWB_MODE_I32;
+    const bool affine = e->affine;  // never split
+    const int mode0 = affine ? SWB_MODE_S16A : SWB_MODE_S16;
 
     const bool small_shard = pl.tiles.size() < 2u * (size_t)e->sm_count * (SWB_NT_LARGE / 32);
     // batches on small shards: 2048-row launches keep the shared-memory footprint of a block small, so blocks of several
@@ -719,88 +777,103 @@ static int enqueue_job(swb_engine *e, Slot &s, uint32_t qi, const uint8_t *q, ui
     // chunk keep the long chunks (several short launches in a row cost the titin-scale workload a factor of two)
     const uint32_t chunk_rows =
         !e->chunk_rows_set && small_shard && e->cur_nq > 1 && rows <= e->chunk_rows ? 2048u : e->chunk_rows;
-    const bool split = !pair && !affine && (e->opt_split == 1 || (e->opt_split < 0 && small_shard));
+    const bool split = !affine && (e->opt_split == 1 || (e->opt_split < 0 && small_shard));
 
-    // pass 0: the s16 pass over all tiles
+    // Exact passes (scores beyond the s16 range): V16R where the scoring scheme allows it, else int32
+    const bool r16 = !affine && e->rebase_shift > 0 && e->opt_exact == 0;
+    const int mode1 = affine ? SWB_MODE_I32A : (r16 ? SWB_MODE_R16 : SWB_MODE_I32);
+    // The tiles of the pipelined-pass ("split") set, per lane-group size: the leading `direct` of them -- at least
+    // direct_len wide, against a query at least that long -- go to V16R at once, the others through the s16 pass.
+    uint32_t xl[SWB_MAX_LOGG + 1] = {}, direct[SWB_MAX_LOGG + 1] = {}, rest[SWB_MAX_LOGG + 1] = {};
+    uint32_t n_direct = 0, n_rest = 0;
+    if (split)
+        for (int l = 1; l <= SWB_MAX_LOGG; ++l) {
+            xl[l] = pl.xl_by_logg[l];
+            if (r16 && e->opt_direct_len && rows >= e->opt_direct_len)
+                while (direct[l] < xl[l] && pl.tiles[pl.tile_start_by_logg[l] + direct[l]].width >= e->opt_direct_len)
+                    ++direct[l];
+            rest[l] = xl[l] - direct[l];
+            n_direct += direct[l];
+            n_rest += rest[l];
+        }
+    // rows per lane of the split groups: 16 when that still leaves more work items than one-warp blocks fit on the GPU
+    // (13 per SM with 16.5 KB of staged rows each), else 8 (twice the passes in flight per tile)
+    auto pick_split_k = [&](const uint32_t *cnt) {
+        if (e->opt_split_k) return e->opt_split_k;
+        uint64_t items16 = 0;
+        for (int l = 1; l <= SWB_MAX_LOGG; ++l) items16 += (uint64_t)cnt[l] * swb_split_passes(rows, l, 16);
+        return items16 >= 13ull * (uint64_t)e->sm_count ? 16 : 8;
+    };
+
+    // pass 0: the s16 pass over all tiles but the direct ones
     SwbQueryPlan qp0;
-    std::vector<SwbLaunchGroup> g0;
-    // affine lanes carry (H, E) per row: the int32 recompute stops at 8 rows per lane
-    // rows per lane of the split groups: 8 (most passes in flight per tile). Option split_fill = N lets K grow to 16 / 32
-    // while a launch keeps N work items; measured slower on the titin-scale workload at every N (2,370 GCUPS with K = 8,
-    // 1,834 / 1,474 with K = 16 / 32), so it is off by default
-    const uint32_t fill = (uint32_t)e->opt_split_fill;
-    const int split_l = split && fill ? swb_plan_split_max_logg(pl) : -1;
-    const int sk0 = split_l > 0 ? swb_plan_split_k(pl, std::min(rows, chunk_rows), 32, fill) : 8;
-    swb_plan_query(rows, e->opt_k, 32, present, pair ? SWB_CHUNK_ROWS_QPAIR : chunk_rows, qp0,
-                   sk0 > 8 ? (uint32_t)sk0 << split_l : 0u);
-    swb_plan_launch_groups(pl, qp0, longest_first, split, g0, sk0);
-    // int32 passes over flagged tiles, one per query, only when a score can exceed the s16 range at all
-    const uint32_t qlens[2] = {qlen, pair ? qlen2 : 0u};
-    bool need_i32[2];
-    SwbQueryPlan qp1[2];
-    std::vector<SwbLaunchGroup> g1[2];
-    size_t nlaunch = g0.size() * qp0.chunks.size();
-    uint32_t prof8_rows = pair ? 0u : qp0.prof_rows;
-    for (int k = 0; k < 2; ++k) {
-        need_i32[k] = qlens[k] > 0 && (int64_t)e->max_s * std::min<uint32_t>(qlens[k], pl.max_len) > ovf_thr;
-        if (!need_i32[k]) continue;
-        const int sk1 = split_l > 0 ? swb_plan_split_k(pl, std::min(qlens[k], chunk_rows), 16, fill) : 8;
-        swb_plan_query(qlens[k], e->opt_k, affine ? 8 : 16, present, chunk_rows, qp1[k],
-                       sk1 > 8 ? (uint32_t)sk1 << split_l : 0u);
-        swb_plan_launch_groups(pl, qp1[k], longest_first, split, g1[k], sk1);
-        nlaunch += g1[k].size() * qp1[k].chunks.size();
-        prof8_rows = std::max(prof8_rows, qp1[k].prof_rows);
+    std::vector<SwbLaunchGroup> g0, gd;
+    swb_plan_query(rows, e->opt_k, 32, present, chunk_rows, qp0);
+    if (n_rest) {
+        SwbLaunchGroup g;
+        if (swb_plan_split_group(pl, direct, rest, pick_split_k(rest), g)) g0.push_back(g);
     }
+    swb_plan_bulk_groups(pl, qp0, longest_first, split ? xl : nullptr, 0x3fu, g0);
+    if (n_direct) {
+        SwbLaunchGroup g;
+        if (swb_plan_split_group(pl, nullptr, direct, pick_split_k(direct), g)) gd.push_back(g);
+    }
+    // exact pass over flagged tiles, only when a score can exceed the s16 range at all
+    // (affine lanes carry (H, E) per row: their int32 recompute stops at 8 rows per lane)
+    const bool need_i32 = (int64_t)e->max_s * std::min<uint32_t>(qlen, pl.max_len) > ovf_thr;
+    SwbQueryPlan qp1;
+    std::vector<SwbLaunchGroup> g1;
+    uint32_t prof8_rows = qp0.prof_rows;
+    if (need_i32 || n_direct) {
+        swb_plan_query(qlen, e->opt_k, affine ? 8 : 16, present, chunk_rows, qp1);
+        prof8_rows = std::max(prof8_rows, qp1.prof_rows);
+    }
+    if (split) prof8_rows = std::max(prof8_rows, swb_roundup(rows, 16u << SWB_MAX_LOGG));  // the last pass of a split item
+    if (need_i32) {
+        if (n_rest) {
+            SwbLaunchGroup g;
+            // the int32 kernels of the split groups exist for 8 rows per lane only
+            if (swb_plan_split_group(pl, direct, rest, r16 ? pick_split_k(rest) : 8, g)) g1.push_back(g);
+        }
+        swb_plan_bulk_groups(pl, qp1, longest_first, split ? xl : nullptr, 0x3fu, g1);
+    }
+    size_t nlaunch = g0.size() * qp0.chunks.size() + gd.size() + g1.size() * (need_i32 ? qp1.chunks.size() : 0);
     if (nlaunch > SWB_MAX_COUNTERS) return fail(e, SWB_ERR_ARG, "query too long");
+    if (g0.size() + gd.size() > 1 + SWB_MAX_SUB) return fail(e, SWB_ERR_ARG, "internal: too many launch groups");
     const uint32_t prof8_stride = swb_roundup(std::max(prof8_rows, 16u), 16);
-    const uint32_t profq_stride = pair ? swb_roundup(qp0.prof_rows, 16) : 0;
 
     // buffers
-    const uint32_t qbytes = qlen + (pair ? qlen2 : 0u);
-    if (qbytes > s.query_cap) {
+    if (qlen > s.query_cap) {
         if (s.h_query) cudaFreeHost(s.h_query);
         if (s.d_query) cudaFree(s.d_query);
         s.h_query = nullptr;
         s.d_query = nullptr;
         s.query_cap = 0;
-        const uint32_t cap = swb_roundup(qbytes, 4096);
+        const uint32_t cap = swb_roundup(qlen, 4096);
         CU(cudaMallocHost(&s.h_query, cap));
         CU(cudaMalloc(&s.d_query, cap));
         s.query_cap = cap;
     }
-    if (prof8_rows) CU(GROW_DEV(s.d_prof, s.prof_cap, (size_t)prof8_stride * SWB_ALPHA));
-    if (pair) {
-        CU(GROW_DEV(s.d_profq, s.profq_cap, sizeof(uint32_t) * (size_t)profq_stride * SWB_ALPHA));
-        CU(GROW_DEV(s.d_bnd16, s.bnd16_cap, 2 * sizeof(uint32_t) * pl.bnd_elems));  // two work items per tile
-    }
-    // boundary elements: 4 B (V16), 8 B (V32, V16A: H and F), 16 B (V32A)
+    CU(GROW_DEV(s.d_prof, s.prof_cap, (size_t)prof8_stride * SWB_ALPHA));
+    // boundary elements: 4 B (V16, V16R), 8 B (V32, V16A: H and F), 16 B (V32A)
     if (affine) CU(GROW_DEV(s.d_bnd16, s.bnd16_cap, 8ull * pl.bnd_elems));
-    if (need_i32[0] || need_i32[1]) CU(GROW_DEV(s.d_bnd32, s.bnd32_cap, (affine ? 16ull : 8ull) * pl.bnd_elems));
-    // progress counters of the split group: one per (very long tile, pass) and chunk
-    // (the int32 pass reuses the buffer after the s16 pass: same stream order, cleared in between)
-    size_t prog_words = 0, prog_words1 = 0;
-    std::vector<SwbQueryChunk> sch;
-    if (!g0.empty() && g0[0].split) {
-        swb_group_chunks(qp0, g0[0], sch);
-        for (size_t c = 0; c < sch.size(); ++c) prog_words += swb_split_items(sch[c].rows, g0[0], nullptr);
-    }
-    if (need_i32[0] && !g1[0].empty() && g1[0][0].split) {
-        swb_group_chunks(qp1[0], g1[0][0], sch);
-        for (size_t c = 0; c < sch.size(); ++c) prog_words1 += swb_split_items(sch[c].rows, g1[0][0], nullptr);
-    }
-    if (std::max(prog_words, prog_words1))
-        CU(GROW_DEV(s.d_prog, s.prog_cap, sizeof(uint32_t) * std::max(prog_words, prog_words1)));
+    if (need_i32 && !r16) CU(GROW_DEV(s.d_bnd32, s.bnd32_cap, (affine ? 16ull : 8ull) * pl.bnd_elems));
+    if (r16 && (need_i32 || n_direct))
+        CU(GROW_DEV(s.d_blog, s.blog_cap, sizeof(uint2) * swb_blog_elems(pl.bnd_elems, (uint32_t)pl.tiles.size())));
+    // progress counters of the split groups: one per (tile, pass); the direct group's follow those of the s16 group, and
+    // the exact pass reuses the s16 group's after it (same stream order, cleared in between)
+    size_t prog_words = 0, prog_direct = 0, prog_words1 = 0;
+    if (!g0.empty() && g0[0].split) prog_words = swb_split_items(rows, g0[0], nullptr);
+    if (!gd.empty()) prog_direct = swb_split_items(rows, gd[0], nullptr);
+    if (need_i32 && !g1.empty() && g1[0].split) prog_words1 = swb_split_items(rows, g1[0], nullptr);
+    const size_t prog_main = std::max(prog_words, prog_words1);
+    if (prog_main + prog_direct) CU(GROW_DEV(s.d_prog, s.prog_cap, sizeof(uint32_t) * (prog_main + prog_direct)));
 
     memcpy(s.h_query, q, qlen);
-    if (pair) memcpy(s.h_query + qlen, q2, qlen2);
-    CU(cudaMemcpyAsync(s.d_query, s.h_query, qbytes, cudaMemcpyHostToDevice, s.stream));
-    if (pair)
-        CU(swb_launch_profile2(s.d_query, qlen, s.d_query + qlen, qlen2, e->d_mat, e->gap, s.d_profq, profq_stride,
-                               qp0.prof_rows, s.stream));
-    else
-        CU(swb_launch_profile(s.d_query, qlen, e->d_mat, e->gap, s.d_prof, prof8_stride, qp0.prof_rows, s.stream));
+    CU(cudaMemcpyAsync(s.d_query, s.h_query, qlen, cudaMemcpyHostToDevice, s.stream));
+    CU(swb_launch_profile(s.d_query, qlen, e->d_mat, e->gap, s.d_prof, prof8_stride, prof8_rows, s.stream));
     CU(cudaMemsetAsync(s.d_state, 0, s.state_bytes, s.stream));
-    if (prog_words) CU(cudaMemsetAsync(s.d_prog, 0, sizeof(uint32_t) * prog_words, s.stream));
+    if (prog_main + prog_direct) CU(cudaMemsetAsync(s.d_prog, 0, sizeof(uint32_t) * (prog_main + prog_direct), s.stream));
     e->stats.kernel_launches += 1;
 
     SwbScoreParams p;
@@ -813,56 +886,58 @@ static int enqueue_job(swb_engine *e, Slot &s, uint32_t qi, const uint8_t *q, ui
     p.gap_open = e->gap;
     p.gap_extend = e->gap_extend;
     p.ovf_thr = ovf_thr;
+    p.rebase_shift = (uint32_t)e->rebase_shift;
+    p.blog = s.d_blog;
     uint32_t counter = 0;
-    p.profile = pair ? reinterpret_cast<const int8_t *>(s.d_profq) : s.d_prof;
-    p.prof_stride = pair ? profq_stride : prof8_stride;
+    p.profile = s.d_prof;
+    p.prof_stride = prof8_stride;
     p.scores = s.d_sorted;
-    p.scores2 = s.d_sorted2;
     p.bnd = s.d_bnd16;
     p.only_flagged = 0;
-    if ((rc = enqueue_pass(e, s, mode0, p, qp0, g0, counter)) != SWB_OK) return rc;
-    for (int k = 0; k < 2; ++k) {
-        if (!need_i32[k]) continue;
-        if (pair) {  // the int32 pass works on a one-query int8 profile
-            CU(swb_launch_profile(s.d_query + (k ? qlen : 0u), qlens[k], e->d_mat, e->gap, s.d_prof, prof8_stride,
-                                  qp1[k].prof_rows, s.stream));
-            e->stats.kernel_launches += 1;
-        }
-        p.profile = s.d_prof;
-        p.prof_stride = prof8_stride;
-        p.scores = k ? s.d_sorted2 : s.d_sorted;
-        p.scores2 = nullptr;
-        p.bnd = s.d_bnd32;
+    // the direct group runs beside the s16 pass (disjoint tiles): it is enqueued as one more launch group of pass 0
+    if ((rc = enqueue_pass(e, s, mode0, p, qp0, g0, counter, s.d_prog, &gd, s.d_prog + prog_main)) != SWB_OK) return rc;
+    if (need_i32 && !g1.empty()) {
+        p.bnd = r16 ? (void *)s.d_bnd16 : s.d_bnd32;
         p.only_flagged = 1;
-        if (!g1[k].empty() && g1[k][0].split) {  // pipelined work items combine their scores with atomicMax
+        if (g1[0].split) {  // pipelined work items combine their scores with atomicMax
             CU(cudaMemsetAsync(s.d_prog, 0, sizeof(uint32_t) * prog_words1, s.stream));
             CU(swb_launch_clear_flagged(e->d_tiles, (uint32_t)pl.tiles.size(), s.d_flags, p.scores, s.stream));
             e->stats.kernel_launches += 1;
         }
-        if ((rc = enqueue_pass(e, s, mode1, p, qp1[k], g1[k], counter)) != SWB_OK) return rc;
+        if ((rc = enqueue_pass(e, s, mode1, p, qp1, g1, counter, s.d_prog, nullptr, nullptr)) != SWB_OK) return rc;
     }
     CU(swb_launch_scatter(s.d_sorted, e->d_out_pos, nl, out, s.stream));
-    if (pair) CU(swb_launch_scatter(s.d_sorted2, e->d_out_pos, nl, out2, s.stream));
-    e->stats.kernel_launches += pair ? 2 : 1;
+    e->stats.kernel_launches += 1;
     e->stats.last_k = (uint32_t)qp0.k_by_logg[0];
     for (int l = 0; l <= SWB_MAX_LOGG; ++l)
-        e->stats.padded_cells += pl.cols_by_logg[l] * (uint64_t)swb_roundup(rows, (uint32_t)qp0.k_by_logg[l] << l) *
-                                 (pair ? 2u : 1u);
-    e->stats.cells += (uint64_t)(qlen + (pair ? qlen2 : 0u)) * pl.residues_local;
+        e->stats.padded_cells += pl.cols_by_logg[l] * (uint64_t)swb_roundup(rows, (uint32_t)qp0.k_by_logg[l] << l);
+    e->stats.cells += (uint64_t)qlen * pl.residues_local;
     return SWB_OK;
 }
 
+// waits for the slot's job and hands its results to the caller's memory
 static int finish_slot(swb_engine *e, Slot &s)
 {
     if (!s.busy) return SWB_OK;
-    CU(cudaEventSynchronize(s.done));
     s.busy = false;
+    int32_t *dst = s.pending_dst;
+    uint32_t *ids = s.pending_ids;
+    int32_t *top = s.pending_top;
+    s.pending_dst = nullptr;
+    s.pending_ids = nullptr;
+    s.pending_top = nullptr;
+    CU(cudaEventSynchronize(s.done));
     const size_t nl = e->plan.n_local;
-    for (int k = 0; k < 2; ++k)
-        if (s.pending_dst[k]) {
-            memcpy(s.pending_dst[k], s.h_scores + k * nl, sizeof(int32_t) * nl);
-            s.pending_dst[k] = nullptr;
-        }
+    if (dst && !s.pending_scatter) {
+        memcpy(dst, s.h_scores, sizeof(int32_t) * nl);
+    } else if (dst) {  // a full-database vector shared with the engines of the other shards
+        const uint32_t *sid = e->plan.shard_ids.data();
+        for (size_t k = 0; k < nl; ++k) dst[sid[k]] = s.h_scores[k];
+    }
+    if (ids && top) {
+        memcpy(ids, s.h_topk, sizeof(uint32_t) * s.pending_k);
+        memcpy(top, s.h_topk + s.pending_k, sizeof(int32_t) * s.pending_k);
+    }
     return SWB_OK;
 }
 
@@ -881,8 +956,44 @@ static int wait_any_slot(swb_engine *e, int ns, int *out)
     }
 }
 
-extern "C" int swb_search_batch(swb_engine *e, const uint8_t *qcodes, const uint64_t *qoffsets, uint32_t nq,
-                                int32_t *scores)
+// what a batch hands back per query
+struct BatchOut {
+    int32_t *scores = nullptr;   // nq x n_local (database order of the shard), or, with full_stride != 0,
+    uint64_t full_stride = 0;    //   rows of full_stride entries: vectors of the WHOLE database, this shard fills its ids
+    const uint32_t *row_of = nullptr;  // full_stride != 0: row of query q (NULL: q)
+    uint32_t k = 0;              // device-side selection: k best per query
+    uint32_t *ids = nullptr;     // nq x k
+    int32_t *top = nullptr;      // nq x k
+};
+
+// the copies and the selection kernel that follow the scan of query qa on the slot's stream
+static int enqueue_results(swb_engine *e, Slot &s, uint32_t qa, const BatchOut &bo)
+{
+    const uint32_t nl = e->plan.n_local;
+    if (bo.k) {
+        const size_t bytes = 2 * sizeof(uint32_t) * (size_t)bo.k;
+        CU(GROW_DEV(s.d_topk, s.topk_cap, bytes));
+        CU(GROW_HOST(s.h_topk, s.h_topk_cap, bytes));
+        CU(swb_launch_topk(e->d_out + (size_t)qa * nl, nl, e->plan.nshards > 1 ? e->d_shard_ids : nullptr, bo.k, s.d_topk,
+                           reinterpret_cast<int32_t *>(s.d_topk + bo.k), s.stream));
+        e->stats.kernel_launches += 1;
+        CU(cudaMemcpyAsync(s.h_topk, s.d_topk, bytes, cudaMemcpyDeviceToHost, s.stream));
+        s.pending_ids = bo.ids + (size_t)qa * bo.k;
+        s.pending_top = bo.top + (size_t)qa * bo.k;
+        s.pending_k = bo.k;
+    }
+    if (bo.scores && nl > 0) {
+        CU(cudaMemcpyAsync(s.h_scores, e->d_out + (size_t)qa * nl, sizeof(int32_t) * nl, cudaMemcpyDeviceToHost,
+                           s.stream));
+        s.pending_scatter = bo.full_stride != 0;
+        s.pending_dst = bo.full_stride ? bo.scores + (size_t)(bo.row_of ? bo.row_of[qa] : qa) * bo.full_stride
+                                       : bo.scores + (size_t)qa * nl;
+    }
+    return SWB_OK;
+}
+
+static int search_batch_impl(swb_engine *e, const uint8_t *qcodes, const uint64_t *qoffsets, uint32_t nq,
+                             const BatchOut &bo)
 {
     if (!e || !qoffsets || (!qcodes && nq && qoffsets[nq] != qoffsets[0])) return SWB_ERR_ARG;
     if (!e->db_loaded) return fail(e, SWB_ERR_STATE, "swb_search before swb_db_load");
@@ -893,6 +1004,7 @@ extern "C" int swb_search_batch(swb_engine *e, const uint8_t *qcodes, const uint
         if (qoffsets[i + 1] < qoffsets[i] || qoffsets[i + 1] - qoffsets[i] > 0x7fffffffull)
             return fail(e, SWB_ERR_ARG, "bad query offsets");
     cudaStream_t ms = main_stream(e);
+    e->last_nq = 0;  // set again once every result of this batch is in place
     if (sizeof(int32_t) * (size_t)nq * nl > e->out_cap && nl > 0) {
         CU(cudaStreamSynchronize(ms));
         CU(GROW_DEV(e->d_out, e->out_cap, sizeof(int32_t) * (size_t)nq * nl));
@@ -901,73 +1013,124 @@ extern "C" int swb_search_batch(swb_engine *e, const uint8_t *qcodes, const uint
     e->stats.padded_cells = 0;
     e->stats.kernel_launches = 0;
     e->stats.recomputed_tiles = 0;
-    e->last_nq = nq;
     e->cur_nq = nq;
     // jobs: queries are taken longest first (the tiles of a long query are long-running work items: started last they
-    // would leave the GPU half empty at the end of the batch; option batch_order = 1 keeps the caller's order). With
-    // query-pair packing neighbours in length share a job (the shorter one pays for the rows of the longer one); a query
-    // left over, or every query without packing, runs alone
+    // would leave the GPU half empty at the end of the batch; option batch_order = 1 keeps the caller's order)
     std::vector<uint32_t> order(nq);
     for (uint32_t i = 0; i < nq; ++i) order[i] = i;
-    const bool pairing = e->opt_pair_queries && nq >= 2 && !e->affine;
-    if (pairing || e->opt_batch_order == 0)
+    if (e->opt_batch_order == 0)
         std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
             return qoffsets[a + 1] - qoffsets[a] > qoffsets[b + 1] - qoffsets[b];
         });
-    const uint32_t njobs = pairing ? (nq + 1) / 2 : nq;
-    const int ns = (int)std::min<uint32_t>((uint32_t)e->nslots, std::max<uint32_t>(1u, njobs));  // streams in use
-    CU(cudaEventRecord(e->ev_start, ms));
-    CU(cudaEventRecord(e->ev_fork, ms));
-    for (int i = 0; i < ns; ++i) {
-        CU(cudaStreamWaitEvent(e->slots[i].stream, e->ev_fork, 0));
-        CU(cudaMemsetAsync(e->slots[i].d_recount, 0, sizeof(uint32_t), e->slots[i].stream));
-    }
+    const int ns = (int)std::min<uint32_t>((uint32_t)e->nslots, std::max<uint32_t>(1u, nq));  // streams in use
+    // From the first enqueue on, a failure must not return before the common epilogue has waited for the slots and
+    // cleared their pending destinations: they point into the caller's buffers of THIS call.
     int rc = SWB_OK;
-    for (uint32_t j = 0; j < njobs && rc == SWB_OK; ++j) {
+    auto cu = [&](cudaError_t ce, const char *what) {
+        if (ce == cudaSuccess || rc != SWB_OK) return ce == cudaSuccess;
+        rc = fail(e, SWB_ERR_CUDA, std::string(what) + " failed: " + cudaGetErrorString(ce));
+        return false;
+    };
+    cu(cudaEventRecord(e->ev_start, ms), "cudaEventRecord");
+    cu(cudaEventRecord(e->ev_fork, ms), "cudaEventRecord");
+    for (int i = 0; i < ns && rc == SWB_OK; ++i) {
+        cu(cudaStreamWaitEvent(e->slots[i].stream, e->ev_fork, 0), "cudaStreamWaitEvent");
+        cu(cudaMemsetAsync(e->slots[i].d_recount, 0, sizeof(uint32_t), e->slots[i].stream), "cudaMemsetAsync");
+    }
+    for (uint32_t j = 0; j < nq && rc == SWB_OK; ++j) {
         // the first `ns` jobs take the slots in turn; later ones take whichever slot finishes first (a slot that holds
         // a long query must not hold up the queue behind it)
         int si = (int)(j % (uint32_t)ns);
         if (j >= (uint32_t)ns && (rc = wait_any_slot(e, ns, &si)) != SWB_OK) break;
         Slot &s = e->slots[si];
         if ((rc = finish_slot(e, s)) != SWB_OK) break;
-        const uint32_t qa = pairing ? order[2 * j] : order[j];
-        const bool pair = pairing && 2 * j + 1 < nq;
-        const uint32_t qb = pair ? order[2 * j + 1] : 0u;
+        const uint32_t qa = order[j];
         const uint32_t la = (uint32_t)(qoffsets[qa + 1] - qoffsets[qa]);
-        const uint32_t lb = pair ? (uint32_t)(qoffsets[qb + 1] - qoffsets[qb]) : 0u;
-        rc = enqueue_job(e, s, qa, qcodes + qoffsets[qa], la, pair, qb, pair ? qcodes + qoffsets[qb] : nullptr, lb);
-        if (rc != SWB_OK) break;
-        if (scores && nl > 0) {
-            CU(cudaMemcpyAsync(s.h_scores, e->d_out + (size_t)qa * nl, sizeof(int32_t) * nl, cudaMemcpyDeviceToHost,
-                               s.stream));
-            s.pending_dst[0] = scores + (size_t)qa * nl;
-            if (pair) {
-                CU(cudaMemcpyAsync(s.h_scores + nl, e->d_out + (size_t)qb * nl, sizeof(int32_t) * nl,
-                                   cudaMemcpyDeviceToHost, s.stream));
-                s.pending_dst[1] = scores + (size_t)qb * nl;
-            }
-        }
-        CU(cudaEventRecord(s.done, s.stream));
+        if ((rc = enqueue_job(e, s, qa, qcodes + qoffsets[qa], la)) != SWB_OK) break;
+        if ((rc = enqueue_results(e, s, qa, bo)) != SWB_OK) break;
+        if (!cu(cudaEventRecord(s.done, s.stream), "cudaEventRecord")) break;
         s.busy = true;
     }
-    for (int i = 0; i < ns; ++i) {
-        CU(cudaMemcpyAsync(e->h_recount + i, e->slots[i].d_recount, sizeof(uint32_t), cudaMemcpyDeviceToHost,
-                           e->slots[i].stream));
-        CU(cudaEventRecord(e->ev_join[i], e->slots[i].stream));
-        CU(cudaStreamWaitEvent(ms, e->ev_join[i], 0));
+    for (int i = 0; i < ns && rc == SWB_OK; ++i) {
+        cu(cudaMemcpyAsync(e->h_recount + i, e->slots[i].d_recount, sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                           e->slots[i].stream), "cudaMemcpyAsync");
+        cu(cudaEventRecord(e->ev_join[i], e->slots[i].stream), "cudaEventRecord");
+        cu(cudaStreamWaitEvent(ms, e->ev_join[i], 0), "cudaStreamWaitEvent");
     }
-    CU(cudaEventRecord(e->ev_stop, ms));
-    for (int i = 0; i < ns; ++i) {
-        int r2 = finish_slot(e, e->slots[i]);
-        if (rc == SWB_OK) rc = r2;
+    if (rc == SWB_OK) cu(cudaEventRecord(e->ev_stop, ms), "cudaEventRecord");
+    if (rc == SWB_OK) {
+        for (int i = 0; i < ns; ++i) {
+            const int r2 = finish_slot(e, e->slots[i]);
+            if (rc == SWB_OK) rc = r2;
+        }
+        if (rc == SWB_OK) cu(cudaStreamSynchronize(ms), "cudaStreamSynchronize");
     }
-    CU(cudaStreamSynchronize(ms));
-    if (rc != SWB_OK) return rc;
+    if (rc != SWB_OK) {
+        // drain whatever was enqueued and forget the destinations of this call
+        const std::string msg = e->err;
+        for (int i = 0; i < SWB_MAX_SLOTS; ++i) {
+            Slot &s = e->slots[i];
+            cudaStreamSynchronize(s.stream);
+            s.busy = false;
+            s.pending_dst = nullptr;
+            s.pending_ids = nullptr;
+            s.pending_top = nullptr;
+        }
+        cudaStreamSynchronize(ms);
+        e->err = msg;
+        return rc;
+    }
     float ms_f = 0;
     CU(cudaEventElapsedTime(&ms_f, e->ev_start, e->ev_stop));
     e->stats.device_ms = ms_f;
     for (int i = 0; i < ns; ++i) e->stats.recomputed_tiles += e->h_recount[i];
+    e->last_nq = nq;
     return SWB_OK;
+}
+
+extern "C" int swb_search_batch(swb_engine *e, const uint8_t *qcodes, const uint64_t *qoffsets, uint32_t nq,
+                                int32_t *scores)
+{
+    BatchOut bo;
+    bo.scores = scores;
+    return search_batch_impl(e, qcodes, qoffsets, nq, bo);
+}
+
+int swb_search_batch_rows(swb_engine *e, const uint8_t *qcodes, const uint64_t *qoffsets, uint32_t nq,
+                          int32_t *scores_full, uint64_t n_total, const uint32_t *row_of)
+{
+    if (!e || !scores_full) return SWB_ERR_ARG;
+    if (e->db_loaded && n_total < e->plan.n_total) return fail(e, SWB_ERR_ARG, "n_total is smaller than the database");
+    BatchOut bo;
+    bo.scores = scores_full;
+    bo.full_stride = n_total ? n_total : 1;
+    bo.row_of = row_of;
+    return search_batch_impl(e, qcodes, qoffsets, nq, bo);
+}
+
+extern "C" int swb_search_batch_scatter(swb_engine *e, const uint8_t *qcodes, const uint64_t *qoffsets, uint32_t nq,
+                                        int32_t *scores_full, uint64_t n_total)
+{
+    return swb_search_batch_rows(e, qcodes, qoffsets, nq, scores_full, n_total, nullptr);
+}
+
+extern "C" int swb_search_batch_topk(swb_engine *e, const uint8_t *qcodes, const uint64_t *qoffsets, uint32_t nq,
+                                     uint32_t k, uint32_t *ids, int32_t *top)
+{
+    if (!e || !ids || !top) return SWB_ERR_ARG;
+    if (k < 1 || k > SWB_TOPK_MAX) return fail(e, SWB_ERR_ARG, "k must be 1..1024");
+    BatchOut bo;
+    bo.k = k;
+    bo.ids = ids;
+    bo.top = top;
+    if (e->db_loaded && e->plan.n_local == 0) {  // an empty shard has no hits
+        for (size_t i = 0; i < (size_t)nq * k; ++i) {
+            ids[i] = 0xffffffffu;
+            top[i] = -1;
+        }
+        bo.k = 0;
+    }
+    return search_batch_impl(e, qcodes, qoffsets, nq, bo);
 }
 
 extern "C" int swb_search(swb_engine *e, const uint8_t *query, uint32_t qlen, int32_t *scores)
@@ -985,6 +1148,7 @@ extern "C" int swb_fetch_scores(swb_engine *e, uint32_t query_index, int32_t *sc
     CU(cudaSetDevice(e->device));
     const uint32_t nl = e->plan.n_local;
     if (nl == 0) return SWB_OK;
+    if (sizeof(int32_t) * ((size_t)query_index + 1) * nl > e->out_cap) return fail(e, SWB_ERR_STATE, "no such result");
     CU(cudaMemcpy(scores, e->d_out + (size_t)query_index * nl, sizeof(int32_t) * nl, cudaMemcpyDeviceToHost));
     return SWB_OK;
 }

@@ -81,16 +81,13 @@ template <int K, class V, int NT, int MINB, bool SPLIT>
 __global__ void __launch_bounds__(NT, MINB) swb_score_kernel(const SwbScoreParams p)
 {
     extern __shared__ __align__(16) int8_t sprof[];
-    // profile entries: 1 byte (S + g of one query) or, for query pairs, 4 bytes (s16x2 of the two queries); either way
-    // consecutive code rows start one bank apart
-    const uint32_t esz = V::qpair ? 4u : 1u;
-    const uint32_t sstride = V::qpair ? (p.smem_rows + 1u) * 4u : p.smem_rows + 4u;
-    if (!SPLIT || !p.split_stage_item) {  // else every work item stages the rows of its pass (swb_warp_loop)
-        const uint32_t wpr = (p.smem_rows * esz) >> 2;  // words per code row
+    const uint32_t sstride = p.smem_rows + 4u;
+    if (!SPLIT) {  // SPLIT: every work item stages the rows of its own pass (swb_warp_loop)
+        const uint32_t wpr = p.smem_rows >> 2;  // words per code row
         for (uint32_t i = threadIdx.x; i < wpr * SWB_ALPHA; i += NT) {
             const uint32_t code = i / wpr, w = i - code * wpr;
-            reinterpret_cast<uint32_t *>(sprof + (size_t)code * sstride)[w] = __ldg(
-                reinterpret_cast<const uint32_t *>(p.profile + ((size_t)code * p.prof_stride + p.row0) * esz) + w);
+            reinterpret_cast<uint32_t *>(sprof + (size_t)code * sstride)[w] =
+                __ldg(reinterpret_cast<const uint32_t *>(p.profile + (size_t)code * p.prof_stride + p.row0) + w);
         }
         __syncthreads();
     }
@@ -109,23 +106,6 @@ __global__ void swb_profile_kernel(const uint8_t *__restrict__ q, uint32_t qlen,
 #pragma unroll 4
     for (uint32_t code = 0; code < SWB_ALPHA; ++code)
         prof[(size_t)code * stride + r] = (int8_t)(mat[qc * SWB_ALPHA + code] + bias);
-}
-
-// query-pair profile: prof[code][r] = s16x2(S(qa_r, code) + gap, S(qb_r, code) + gap); rows past a query's end score 0
-__global__ void swb_profile2_kernel(const uint8_t *__restrict__ qa, uint32_t la, const uint8_t *__restrict__ qb,
-                                    uint32_t lb, const int8_t *__restrict__ mat, int gap, uint32_t *__restrict__ prof,
-                                    uint32_t stride, uint32_t rows)
-{
-    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= rows) return;
-    const uint32_t ca = r < la ? (uint32_t)(qa[r] & 31u) : (uint32_t)SWB_PAD;
-    const uint32_t cb = r < lb ? (uint32_t)(qb[r] & 31u) : (uint32_t)SWB_PAD;
-#pragma unroll 4
-    for (uint32_t code = 0; code < SWB_ALPHA; ++code) {
-        const uint32_t lo = (uint32_t)(mat[ca * SWB_ALPHA + code] + gap) & 0xffffu;
-        const uint32_t hi = (uint32_t)(mat[cb * SWB_ALPHA + code] + gap) & 0xffffu;
-        prof[(size_t)code * stride + r] = lo | (hi << 16);
-    }
 }
 
 // One block per tile (grid-stride): gathers the tile's sequences from the raw concatenated codes into
@@ -220,28 +200,31 @@ static cudaError_t dispatch(int op, int K, int mode, bool split, int block_cfg, 
         }
         return cudaErrorInvalidValue;
     }
-    if (mode == SWB_MODE_QPAIR) {
-        if (split) return cudaErrorInvalidValue;
-        switch (K) {
-        case 8: return dispatch_cfg<8, V16Q, false>(op, block_cfg, p, grid, smem, st, blocks);
-        case 16: return dispatch_cfg<16, V16Q, false>(op, block_cfg, p, grid, smem, st, blocks);
-        case 32: return dispatch_cfg<32, V16Q, false>(op, block_cfg, p, grid, smem, st, blocks);
-        }
-        return cudaErrorInvalidValue;
-    }
-    if (split) {  // pipelined passes. K = 8: one warp per block, the rows of a pass staged per work item
+    const bool r16 = mode == SWB_MODE_R16;
+    if (split) {  // pipelined passes: one warp per block, the profile rows of a pass staged per work item
         if (K == 8) {
             if (i32)
                 return op == 0 ? launch_one<8, V32, 32, 20, true>(*p, grid, smem, st)
                                : occ_one<8, V32, 32, 20, true>(smem, blocks);
+            if (r16)
+                return op == 0 ? launch_one<8, V16R, 32, 24, true>(*p, grid, smem, st)
+                               : occ_one<8, V16R, 32, 24, true>(smem, blocks);
             return op == 0 ? launch_one<8, V16, 32, 28, true>(*p, grid, smem, st)
                            : occ_one<8, V16, 32, 28, true>(smem, blocks);
         }
-        // K = 16 / 32: full blocks over the staged chunk, for launches with enough work items to fill the GPU
-        if (i32) return K == 16 ? dispatch_cfg<16, V32, true>(op, block_cfg, p, grid, smem, st, blocks) : cudaErrorInvalidValue;
+        if (K == 16 && !i32) {  // 16.5 KB of staged rows per work item: 13 blocks per SM
+            if (r16)
+                return op == 0 ? launch_one<16, V16R, 32, 13, true>(*p, grid, smem, st)
+                               : occ_one<16, V16R, 32, 13, true>(smem, blocks);
+            return op == 0 ? launch_one<16, V16, 32, 13, true>(*p, grid, smem, st)
+                           : occ_one<16, V16, 32, 13, true>(smem, blocks);
+        }
+        return cudaErrorInvalidValue;
+    }
+    if (r16) {
         switch (K) {
-        case 16: return dispatch_cfg<16, V16, true>(op, block_cfg, p, grid, smem, st, blocks);
-        case 32: return dispatch_cfg<32, V16, true>(op, block_cfg, p, grid, smem, st, blocks);
+        case 8: return dispatch_cfg<8, V16R, false>(op, block_cfg, p, grid, smem, st, blocks);
+        case 16: return dispatch_cfg<16, V16R, false>(op, block_cfg, p, grid, smem, st, blocks);
         }
         return cudaErrorInvalidValue;
     }
@@ -279,13 +262,6 @@ cudaError_t swb_launch_clear_flagged(const SwbTile *tiles, uint32_t ntiles, cons
     return cudaGetLastError();
 }
 
-cudaError_t swb_launch_profile2(const uint8_t *qa, uint32_t la, const uint8_t *qb, uint32_t lb, const int8_t *mat,
-                                int gap, uint32_t *prof, uint32_t stride, uint32_t rows, cudaStream_t st)
-{
-    swb_profile2_kernel<<<(rows + 255) / 256, 256, 0, st>>>(qa, la, qb, lb, mat, gap, prof, stride, rows);
-    return cudaGetLastError();
-}
-
 cudaError_t swb_launch_profile(const uint8_t *q, uint32_t qlen, const int8_t *mat, int bias, int8_t *prof,
                                uint32_t stride, uint32_t rows, cudaStream_t st)
 {
@@ -306,6 +282,146 @@ cudaError_t swb_launch_scatter(const int32_t *sorted, const uint32_t *dst, uint3
 {
     if (n == 0) return cudaSuccess;
     swb_scatter_kernel<<<(n + 255) / 256, 256, 0, st>>>(sorted, dst, n, out);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// The k best entries of one score vector, on the device: score descending, position ascending (the positions of a
+// shard's vector are its database ids in ascending order, so this is "score desc, id asc"). What the reference does
+// instead is hand all n scores back (SWSolver.cu:383-390); a scan of many queries then returns 8 k bytes per query and
+// GPU instead of 4 n.
+// One block per vector. All keys score << pbits | (n - 1 - position) are distinct, so the k best are the k largest
+// keys: radix select, 11 bits per pass, on the significant bits only (scores are >= 0: the bits of the largest score plus
+// the bits of n - 1, typically 3 passes), then one pass that collects the keys at or above the threshold and a bitonic
+// sort of those k in shared memory.
+#define SWB_TOPK_NT 512
+#define SWB_TOPK_BINS 2048
+__global__ void __launch_bounds__(SWB_TOPK_NT) swb_topk_kernel(const int32_t *__restrict__ scores, uint32_t n,
+                                                                const uint32_t *__restrict__ ids, uint32_t k,
+                                                                uint32_t *__restrict__ out_ids,
+                                                                int32_t *__restrict__ out_scores)
+{
+    __shared__ uint32_t hist[SWB_TOPK_BINS];
+    __shared__ unsigned long long sel[SWB_TOPK_MAX];
+    __shared__ uint32_t s_red[SWB_TOPK_NT / 32];
+    __shared__ uint32_t s_bin, s_above, s_count;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t kk = k < n ? k : n;
+    // largest score -> number of significant score bits
+    uint32_t mx = 0;
+    for (uint32_t i = tid; i < n; i += SWB_TOPK_NT) {
+        const int32_t v = scores[i];
+        mx = max(mx, (uint32_t)(v < 0 ? 0 : v));
+    }
+    for (int m = 16; m >= 1; m >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, m));
+    if ((tid & 31u) == 0) s_red[tid >> 5] = mx;
+    __syncthreads();
+    mx = 0;
+    for (uint32_t w = 0; w < SWB_TOPK_NT / 32; ++w) mx = max(mx, s_red[w]);
+    const uint32_t pbits = n > 1 ? 32u - (uint32_t)__clz((int)(n - 1)) : 0u;
+    const uint32_t sbits = mx ? 32u - (uint32_t)__clz((int)mx) : 0u;
+    const uint32_t bits = pbits + sbits;  // <= 63
+    const unsigned long long pmask = (1ull << pbits) - 1ull;
+    auto key_of = [&](uint32_t i) {
+        const int32_t v = scores[i];
+        return ((unsigned long long)(uint32_t)(v < 0 ? 0 : v) << pbits) | (unsigned long long)(n - 1u - i);
+    };
+    unsigned long long prefix = 0;  // the digits chosen so far
+    uint32_t remaining = kk;
+    int shift = (int)bits;          // bits below the chosen prefix
+    unsigned long long threshold = 0;
+    while (kk > 0 && shift > 0) {
+        const int width = shift >= 11 ? 11 : shift;
+        const int lo = shift - width;
+        for (uint32_t b = tid; b < SWB_TOPK_BINS; b += SWB_TOPK_NT) hist[b] = 0;
+        __syncthreads();
+        for (uint32_t i = tid; i < n; i += SWB_TOPK_NT) {
+            const unsigned long long key = key_of(i);
+            if ((key >> shift) == prefix) atomicAdd(&hist[(uint32_t)(key >> lo) & ((1u << width) - 1u)], 1u);
+        }
+        __syncthreads();
+        // the bin that holds the remaining-th largest key: suffix sums over the bins, 4 bins per thread
+        uint32_t c[4], mine = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            c[j] = hist[SWB_TOPK_BINS - 1u - (tid * 4u + j)];  // bins in descending order
+            mine += c[j];
+        }
+        uint32_t incl = mine;
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+            if ((tid & 31u) >= (uint32_t)d) incl += t;
+        }
+        if ((tid & 31u) == 31u) s_red[tid >> 5] = incl;
+        __syncthreads();
+        uint32_t before = incl - mine;  // keys in larger bins than this thread's four
+        for (uint32_t w = 0; w < (tid >> 5); ++w) before += s_red[w];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (before < remaining && before + c[j] >= remaining) {
+                s_bin = SWB_TOPK_BINS - 1u - (tid * 4u + j);
+                s_above = before;
+                s_count = c[j];
+            }
+            before += c[j];
+        }
+        __syncthreads();
+        prefix = (prefix << width) | s_bin;
+        remaining -= s_above;
+        shift = lo;
+        const uint32_t in_bin = s_count;
+        __syncthreads();
+        if (in_bin == remaining) break;  // every key with this prefix is among the k best
+    }
+    threshold = prefix << shift;
+    // collect the kk keys at or above the threshold, then sort them
+    if (tid == 0) s_count = 0;
+    uint32_t p2 = 1;
+    while (p2 < kk) p2 <<= 1;
+    for (uint32_t j = tid; j < p2; j += SWB_TOPK_NT) sel[j] = 0ull;
+    __syncthreads();
+    if (kk > 0)
+        for (uint32_t i = tid; i < n; i += SWB_TOPK_NT) {
+            const unsigned long long key = key_of(i);
+            if (key >= threshold) {
+                const uint32_t at = atomicAdd(&s_count, 1u);
+                if (at < SWB_TOPK_MAX) sel[at] = key + 1ull;  // + 1: a real key never equals the padding value 0
+            }
+        }
+    __syncthreads();
+    for (uint32_t size = 2; size <= p2; size <<= 1)
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            for (uint32_t j = tid; j < p2; j += SWB_TOPK_NT) {
+                const uint32_t partner = j ^ stride;
+                if (partner > j) {
+                    const bool desc = (j & size) == 0;
+                    const unsigned long long a = sel[j], b = sel[partner];
+                    if (desc ? a < b : a > b) {
+                        sel[j] = b;
+                        sel[partner] = a;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    for (uint32_t j = tid; j < k; j += SWB_TOPK_NT) {
+        if (j < kk) {
+            const unsigned long long key = sel[j] - 1ull;
+            const uint32_t pos = n - 1u - (uint32_t)(key & pmask);
+            out_ids[j] = ids ? ids[pos] : pos;
+            out_scores[j] = (int32_t)(key >> pbits);
+        } else {
+            out_ids[j] = 0xffffffffu;
+            out_scores[j] = -1;
+        }
+    }
+}
+
+cudaError_t swb_launch_topk(const int32_t *scores, uint32_t n, const uint32_t *ids, uint32_t k, uint32_t *out_ids,
+                            int32_t *out_scores, cudaStream_t st)
+{
+    if (k == 0 || k > SWB_TOPK_MAX) return cudaErrorInvalidValue;
+    swb_topk_kernel<<<1, SWB_TOPK_NT, 0, st>>>(scores, n, ids, k, out_ids, out_scores);
     return cudaGetLastError();
 }
 

@@ -14,24 +14,26 @@
 // arithmetic policy of a score launch (swb_warp.cuh)
 #define SWB_MODE_S16 0    // V16: two DB sequences per lane, one query
 #define SWB_MODE_I32 1    // V32: exact recompute of flagged tiles
-#define SWB_MODE_QPAIR 2  // V16Q: one DB sequence per lane, two queries (batches)
+#define SWB_MODE_R16 2    // V16R: rebased s16x2, exact (K = 8, 16): recompute of flagged tiles, long-against-long tiles
 #define SWB_MODE_S16A 3   // V16A: affine gaps, s16x2 (K = 8, 16)
 #define SWB_MODE_I32A 4   // V32A: affine gaps, exact recompute (K = 8)
 
-// K: query rows per lane (8, 16, 32; int32 pass 8 or 16). split: the passes of a tile are separate, pipelined work
-// items (very long sequences; SWB_MODE_S16 and SWB_MODE_I32, K = 8 only).
+// K: query rows per lane (8, 16, 32; exact passes 8 or 16). split: the passes of a tile are separate, pipelined work
+// items (very long sequences; SWB_MODE_S16 / SWB_MODE_R16 with K = 8, 16, SWB_MODE_I32 with K = 8).
 cudaError_t swb_launch_score(int K, int mode, bool split, int block_cfg, const SwbScoreParams &p, int grid, size_t smem,
                              cudaStream_t st);
 // zeroes the scores of every flagged tile (before an int32 pass with pipelined work items)
 cudaError_t swb_launch_clear_flagged(const SwbTile *tiles, uint32_t ntiles, const uint8_t *flags, int32_t *scores,
                                      cudaStream_t st);
 cudaError_t swb_score_occupancy(int K, int mode, bool split, int block_cfg, size_t smem, int *blocks_per_sm);
-cudaError_t swb_launch_profile2(const uint8_t *qa, uint32_t la, const uint8_t *qb, uint32_t lb, const int8_t *mat,
-                                int gap, uint32_t *prof, uint32_t stride, uint32_t rows, cudaStream_t st);
 cudaError_t swb_launch_profile(const uint8_t *q, uint32_t qlen, const int8_t *mat, int bias, int8_t *prof,
                                uint32_t stride, uint32_t rows, cudaStream_t st);
 cudaError_t swb_launch_pack(const SwbTile *tiles, uint32_t ntiles, const uint8_t *raw, const uint64_t *seq_off,
                             const uint32_t *seq_len, uint32_t nseq, uint8_t *residues, cudaStream_t st);
+// k best (score descending, position ascending) of a score vector; ids: database id per position or NULL (position)
+#define SWB_TOPK_MAX 1024
+cudaError_t swb_launch_topk(const int32_t *scores, uint32_t n, const uint32_t *ids, uint32_t k, uint32_t *out_ids,
+                            int32_t *out_scores, cudaStream_t st);
 cudaError_t swb_launch_scatter(const int32_t *sorted, const uint32_t *dst, uint32_t n, int32_t *out,
                                cudaStream_t st);
 // traceback alignment of one pair (cpu.cpp semantics); hdiag: 3*(m+2) ints, dir: (m+1)*(n+1) bytes, out_hdr: 5 ints

@@ -33,8 +33,19 @@ static uint8_t classify_logg(uint32_t len, uint32_t group_len)
     return lg;
 }
 
+int swb_sort_by_length(const uint64_t *offsets, uint32_t n, std::vector<uint32_t> &order)
+{
+    std::vector<uint32_t> len(n);
+    for (uint32_t i = 0; i < n; ++i) {
+        if (offsets[i + 1] < offsets[i] || offsets[i + 1] - offsets[i] > 0x7ffffff0ull) return -1;
+        len[i] = (uint32_t)(offsets[i + 1] - offsets[i]);
+    }
+    sort_by_length_desc(len, order);
+    return 0;
+}
+
 int swb_build_plan(const uint64_t *offsets, uint32_t n, uint32_t shard, uint32_t nshards, const SwbPlanOpts &o,
-                   SwbPlan &plan)
+                   SwbPlan &plan, const uint32_t *sorted_order)
 {
     if (nshards == 0 || shard >= nshards) return -1;
     plan = SwbPlan();
@@ -49,8 +60,12 @@ int swb_build_plan(const uint64_t *offsets, uint32_t n, uint32_t shard, uint32_t
         len[i] = (uint32_t)l;
     }
     plan.residues_total = n ? offsets[n] - offsets[0] : 0;
-    std::vector<uint32_t> order;
-    sort_by_length_desc(len, order);
+    std::vector<uint32_t> own_order;
+    if (!sorted_order) {
+        sort_by_length_desc(len, own_order);
+        sorted_order = own_order.data();
+    }
+    const uint32_t *order = sorted_order;
 
     // residue-balanced sharding: deal PAIRS of the length-sorted list round-robin, so every shard gets the
     // same length mix and its residue total differs from the others by at most one pair per round
@@ -145,7 +160,7 @@ int swb_build_plan(const uint64_t *offsets, uint32_t n, uint32_t shard, uint32_t
 }
 
 void swb_plan_query(uint32_t qlen, int k_force, int k_max, uint32_t logg_present, uint32_t chunk_rows,
-                    SwbQueryPlan &qp, uint32_t extra_multiple)
+                    SwbQueryPlan &qp)
 {
     qp.chunks.clear();
     qp.prof_rows = 0;
@@ -177,7 +192,7 @@ void swb_plan_query(uint32_t qlen, int k_force, int k_max, uint32_t logg_present
         SwbQueryChunk ch;
         ch.row0 = c * chunk_rows;
         ch.rows = std::min(chunk_rows, qlen - ch.row0);
-        uint32_t need = extra_multiple ? swb_roundup(ch.rows, extra_multiple) : ch.rows;
+        uint32_t need = ch.rows;
         for (int l = 0; l <= SWB_MAX_LOGG; ++l)
             if (logg_present & (1u << l)) need = std::max(need, swb_roundup(ch.rows, (uint32_t)qp.k_by_logg[l] << l));
         ch.smem_rows = swb_roundup(need, 128);
@@ -188,36 +203,18 @@ void swb_plan_query(uint32_t qlen, int k_force, int k_max, uint32_t logg_present
     }
 }
 
-int swb_plan_split_max_logg(const SwbPlan &plan)
+void swb_plan_bulk_groups(const SwbPlan &plan, const SwbQueryPlan &qp, bool longest_first, const uint32_t *skip_by_logg,
+                          uint32_t logg_mask, std::vector<SwbLaunchGroup> &groups)
 {
-    for (int l = SWB_MAX_LOGG; l >= 1; --l)
-        if (plan.xl_by_logg[l]) return l;
-    return -1;
-}
-
-int swb_plan_split_k(const SwbPlan &plan, uint32_t rows, int k_max, uint32_t fill)
-{
-    for (int K = std::min(32, k_max); K > 8; K >>= 1) {
-        uint64_t items = 0;
-        for (int l = 1; l <= SWB_MAX_LOGG; ++l) items += (uint64_t)plan.xl_by_logg[l] * swb_split_passes(rows, l, K);
-        if (items >= fill) return K;
-    }
-    return 8;
-}
-
-void swb_plan_launch_groups(const SwbPlan &plan, const SwbQueryPlan &qp, bool longest_first, bool with_split,
-                            std::vector<SwbLaunchGroup> &groups, int split_k)
-{
-    groups.clear();
-    const uint32_t n_xl = with_split ? plan.n_xl : 0;
+    const size_t first = groups.size();
     for (int K = 32; K >= 8; K >>= 1) {
         SwbLaunchGroup g;
         memset(&g, 0, sizeof g);
         g.K = K;
         uint32_t nr = 0;
         for (int l = SWB_MAX_LOGG; l >= 0; --l) {
-            if (!plan.tiles_by_logg[l] || qp.k_by_logg[l] != K) continue;
-            const uint32_t skip = n_xl ? plan.xl_by_logg[l] : 0;  // the long tiles go to the split group
+            if (!(logg_mask & (1u << l)) || !plan.tiles_by_logg[l] || qp.k_by_logg[l] != K) continue;
+            const uint32_t skip = skip_by_logg ? std::min(skip_by_logg[l], plan.tiles_by_logg[l]) : 0u;
             if (plan.tiles_by_logg[l] == skip) continue;
             g.logg_mask |= 1u << l;
             g.range_start[nr] = plan.tile_start_by_logg[l] + skip;
@@ -236,32 +233,36 @@ void swb_plan_launch_groups(const SwbPlan &plan, const SwbQueryPlan &qp, bool lo
     // tiles, goes first and the bulk last; a small group occupies few blocks, so the bulk still finds room and runs
     // beside it, and the long tiles are not left for the end. Otherwise (a batch: the next query fills the GPU
     // while this one drains) the bulk goes first.
-    if (n_xl) {  // always first: its few warps then run beside everything else
-        SwbLaunchGroup g;
-        memset(&g, 0, sizeof g);
-        g.K = split_k;
-        g.split = true;
-        for (int l = 1; l <= SWB_MAX_LOGG; ++l) {
-            g.xl_by_logg[l] = plan.xl_by_logg[l];
-            if (g.xl_by_logg[l]) g.logg_mask |= 1u << l;
-        }
-        g.ntiles = n_xl;
-        for (uint32_t r = 0; r < SWB_MAX_RANGES; ++r) g.range_cum[r] = n_xl;
-        groups.insert(groups.begin(), g);
-    }
-    std::vector<SwbLaunchGroup>::iterator first = groups.begin() + (n_xl ? 1 : 0);
     if (longest_first)
-        std::stable_sort(first, groups.end(),
+        std::stable_sort(groups.begin() + first, groups.end(),
                          [](const SwbLaunchGroup &a, const SwbLaunchGroup &b) { return a.logg_mask > b.logg_mask; });
     else
-        std::stable_sort(first, groups.end(),
+        std::stable_sort(groups.begin() + first, groups.end(),
                          [](const SwbLaunchGroup &a, const SwbLaunchGroup &b) { return a.ntiles > b.ntiles; });
+}
+
+bool swb_plan_split_group(const SwbPlan &plan, const uint32_t *first_by_logg, const uint32_t *count_by_logg, int K,
+                          SwbLaunchGroup &g)
+{
+    memset(&g, 0, sizeof g);
+    g.K = K;
+    g.split = true;
+    for (int l = 1; l <= SWB_MAX_LOGG; ++l) {
+        const uint32_t first = first_by_logg ? first_by_logg[l] : 0u;
+        if (first >= plan.tiles_by_logg[l]) continue;
+        g.xl_start[l] = plan.tile_start_by_logg[l] + first;
+        g.xl_by_logg[l] = std::min(count_by_logg[l], plan.tiles_by_logg[l] - first);
+        if (g.xl_by_logg[l]) g.logg_mask |= 1u << l;
+        g.ntiles += g.xl_by_logg[l];
+    }
+    for (uint32_t r = 0; r < SWB_MAX_RANGES; ++r) g.range_cum[r] = g.ntiles;
+    return g.ntiles != 0;
 }
 
 void swb_group_chunks(const SwbQueryPlan &qp, const SwbLaunchGroup &g, std::vector<SwbQueryChunk> &out)
 {
     out = qp.chunks;
-    if (!(g.split && g.K == 8) || out.size() < 2) return;
+    if (!g.split || out.size() < 2) return;
     SwbQueryChunk all = out.front();
     all.rows = out.back().row0 + out.back().rows;
     all.first = all.last = 1;
@@ -270,13 +271,12 @@ void swb_group_chunks(const SwbQueryPlan &qp, const SwbLaunchGroup &g, std::vect
 
 uint32_t swb_split_items(uint32_t rows, const SwbLaunchGroup &g, SwbScoreParams *p)
 {
-    uint32_t tiles = 0, items = 0;
+    uint32_t items = 0;
     for (int j = 0; j < SWB_MAX_LOGG; ++j) {
         const int l = SWB_MAX_LOGG - j;
-        tiles += g.xl_by_logg[l];
         items += g.xl_by_logg[l] * swb_split_passes(rows, l, g.K);
         if (p) {
-            p->split_tile_end[j] = tiles;
+            p->split_tile_start[j] = g.xl_start[l];
             p->split_item_end[j] = items;
         }
     }
@@ -290,4 +290,17 @@ uint32_t swb_group_smem_rows(uint32_t rows, const SwbLaunchGroup &g)
     for (int l = 0; l <= SWB_MAX_LOGG; ++l)
         if (g.logg_mask & (1u << l)) need = std::max(need, swb_roundup(rows, (uint32_t)g.K << l));
     return swb_roundup(need, 128);
+}
+
+int swb_rebase_shift(int max_s, int min_s, int gap, uint32_t pass_rows)
+{
+    // all values of a pass over one block lie within (pass_rows + cols + 2) * step of the block's base (swb_warp.cuh,
+    // V16R); they, the transient diag + S and the clamped floors (-32000) must stay inside [-32768, 32767]
+    const int step = std::max(1, max_s + gap);
+    const int lowest = std::max(0, -min_s);
+    const int span = 31000 - lowest - gap - std::max(0, max_s);
+    const long cols = (long)span / step - (long)pass_rows - 2;
+    int shift = 0;
+    while (shift < 15 && (2L << shift) <= cols) ++shift;
+    return shift >= 6 ? shift : 0;
 }

@@ -37,9 +37,12 @@ struct SwbPlan {
     uint64_t cols_by_logg[SWB_MAX_LOGG + 1];  // padded sequence-columns (width * slots * 2) per group size
 };
 
-// offsets: n+1 entries. Returns 0 or a negative error (lengths above 2^31-8).
+// offsets: n+1 entries. Returns 0 or a negative error (lengths above 2^31-8). sorted_order: the n ids by descending
+// length as swb_sort_by_length returns them (several shards of one database share one sort), or NULL to sort here.
 int swb_build_plan(const uint64_t *offsets, uint32_t n, uint32_t shard, uint32_t nshards, const SwbPlanOpts &o,
-                   SwbPlan &plan);
+                   SwbPlan &plan, const uint32_t *sorted_order = nullptr);
+// ids 0..n-1 by descending length, ties in id order (stable); -1 on decreasing offsets / a length above 2^31-16
+int swb_sort_by_length(const uint64_t *offsets, uint32_t n, std::vector<uint32_t> &order);
 
 // How one query is cut into score-kernel launches ("chunks" of query rows that fit shared memory), and how many
 // query rows a lane holds for each group size.
@@ -57,43 +60,43 @@ struct SwbQueryPlan {
 // k_force: 0 = choose per group size (least padded rows, which is also the shortest tile time), else 8/16/32.
 // k_max: 32 for the s16 passes, 16 for the int32 pass. logg_present: bit l set when the plan has tiles of that
 // group size. chunk_rows must be a multiple of 1024 (every K << l divides it).
-// extra_multiple: every chunk also stages its rows rounded up to this (the pass height of a split group whose K is
-// larger than the K of its group sizes); 0 = none. Must divide chunk_rows.
 void swb_plan_query(uint32_t qlen, int k_force, int k_max, uint32_t logg_present, uint32_t chunk_rows,
-                    SwbQueryPlan &qp, uint32_t extra_multiple = 0);
+                    SwbQueryPlan &qp);
 
 // One score-kernel launch of a query pass: the tiles of all group sizes that share the same K.
 struct SwbLaunchGroup {
     int K;
-    bool split;          // pipelined passes over the plan's n_xl leading tiles (K = 8)
-    uint32_t xl_by_logg[SWB_MAX_LOGG + 1];  // split group: its tiles per group size
+    bool split;          // pipelined passes: the work items are (tile, pass), one warp per block
+    uint32_t xl_start[SWB_MAX_LOGG + 1];    // split group: first tile (index into the tile array) per group size ...
+    uint32_t xl_by_logg[SWB_MAX_LOGG + 1];  // ... and how many
     uint32_t logg_mask;
     uint32_t ntiles;
     uint32_t range_start[SWB_MAX_RANGES];
     uint32_t range_cum[SWB_MAX_RANGES];
 };
-// one group per distinct K; longest_first puts the group owning the longest tiles first (lone query), otherwise the
-// group with most tiles first (batch); inside a group the ranges run from the largest group size (longest tiles) down
-// with_split: give the very long tiles their own pipelined group (s16 pass); otherwise they stay in the 32-lane range
-// split_k: rows per lane of the split group (8: one warp per block, each work item stages the rows of its pass;
-// 16 / 32: full blocks that stage the whole chunk, like the other groups)
-void swb_plan_launch_groups(const SwbPlan &plan, const SwbQueryPlan &qp, bool longest_first, bool with_split,
-                            std::vector<SwbLaunchGroup> &groups, int split_k = 8);
-// Rows per lane for the split group of a query whose chunks have up to `rows` rows: the largest K <= k_max that still
-// yields at least `fill` work items per launch (enough to occupy the GPU), else 8 (most passes in flight per tile).
-int swb_plan_split_k(const SwbPlan &plan, uint32_t rows, int k_max, uint32_t fill);
-// largest lane-group size (log2) that has tiles in the split set, -1 if none
-int swb_plan_split_max_logg(const SwbPlan &plan);
-// split group: passes (work items) of a tile of 1 << l lanes per pair for a chunk of `rows` query rows (K = 8)
-inline uint32_t swb_split_passes(uint32_t rows, int l, int K = 8)
+// The bulk groups, one per distinct K, over the group sizes in logg_mask; skip_by_logg[l] (may be NULL) leading tiles of
+// group size l are left out (they run in split groups). longest_first puts the group owning the longest tiles first (a
+// lone query), otherwise the group with most tiles first (batch); inside a group the ranges run from the largest
+// group size (longest tiles) down. Appends to `groups`.
+void swb_plan_bulk_groups(const SwbPlan &plan, const SwbQueryPlan &qp, bool longest_first, const uint32_t *skip_by_logg,
+                          uint32_t logg_mask, std::vector<SwbLaunchGroup> &groups);
+// A split group over count_by_logg[l] tiles of group size l >= 1 starting first_by_logg[l] tiles into that group
+// size; K rows per lane (8 or 16). Returns false when the set is empty.
+bool swb_plan_split_group(const SwbPlan &plan, const uint32_t *first_by_logg, const uint32_t *count_by_logg, int K,
+                          SwbLaunchGroup &g);
+// passes (work items) of a tile of 1 << l lanes per pair for `rows` query rows
+inline uint32_t swb_split_passes(uint32_t rows, int l, int K)
 {
     return (rows + ((uint32_t)K << l) - 1u) / ((uint32_t)K << l);
 }
-// work items of a split group for such a chunk; with p != NULL also fills p->ntiles and the class tables
+// work items of a split group for `rows` query rows; with p != NULL also fills p->ntiles and the class tables
 uint32_t swb_split_items(uint32_t rows, const SwbLaunchGroup &g, SwbScoreParams *p);
-// The launches of a group over the query rows: the chunks of the query plan, except for a split group that stages per
-// work item (K = 8) -- shared memory does not limit it, so it covers all rows in ONE launch (no drain between chunks,
-// several times the work items in flight).
+// The launches of a group over the query rows: the chunks of the query plan, except for a split group: it stages per
+// work item, shared memory does not limit it, so it covers all rows in ONE launch (no drain between chunks, several
+// times the work items in flight).
 void swb_group_chunks(const SwbQueryPlan &qp, const SwbLaunchGroup &g, std::vector<SwbQueryChunk> &out);
 // rows a launch group must find in shared memory for a chunk of `rows` query rows (multiple of 128)
 uint32_t swb_group_smem_rows(uint32_t rows, const SwbLaunchGroup &g);
+// V16R: log2 of the columns per rebase block for a linear scheme (largest score max_s, smallest min_s, gap) with passes
+// of up to `pass_rows` rows, or 0 when the scheme's steps are too large for the 16-bit window (use V32 then)
+int swb_rebase_shift(int max_s, int min_s, int gap, uint32_t pass_rows);

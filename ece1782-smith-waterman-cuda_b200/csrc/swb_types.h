@@ -33,7 +33,7 @@ struct SwbScoreParams {
     uint32_t ntiles;          // tiles covered by this launch (sum of its ranges)
     const uint8_t *residues;
     void *bnd;                // boundary scratch (uint32 per element for s16x2, 2x int32 for i32)
-    const int8_t *profile;    // global query profile [32][prof_stride], entry = S(q_row, code) + gap (one byte; query-pair launches: s16x2 word of both queries)
+    const int8_t *profile;    // global query profile [32][prof_stride], one byte per entry = S(q_row, code) + gap
     uint32_t prof_stride;     // bytes per code row in global memory
     uint32_t row0;            // first query row of this launch (query chunk)
     uint32_t rows;            // query rows of this chunk that carry real residues or padding to use
@@ -41,7 +41,6 @@ struct SwbScoreParams {
     uint32_t first_chunk;     // 1: top boundary is zero
     uint32_t last_chunk;      // 1: bottom boundary is not stored
     int32_t *scores;          // per sequence, sorted order
-    int32_t *scores2;         // query-pair launches: scores of the second query
     uint32_t *counter;        // dynamic tile counter (zeroed before launch)
     uint8_t *flags;           // per tile: s16 kernel sets 1 when a score may have wrapped
     uint32_t only_flagged;    // i32 recompute: skip tiles whose flag is 0
@@ -54,14 +53,21 @@ struct SwbScoreParams {
     uint32_t range_start[SWB_MAX_RANGES];
     uint32_t range_cum[SWB_MAX_RANGES];  // cumulative tile count up to and including range r
     // SPLIT launches (long sequences): ntiles counts (tile, pass) items, handed out tile by tile, pass by pass;
-    // the split set is the leading tiles of the array; classes run from 32 lanes per pair (j = 0) down to 2 (j = 4):
-    // tiles [split_tile_end[j-1], split_tile_end[j]) belong to class j and own ceil(rows / (K << (5 - j))) items each
-    uint32_t split_tile_end[SWB_MAX_LOGG];
+    // classes run from 32 lanes per pair (j = 0) down to 2 (j = 4): class j is a run of tiles starting at
+    // split_tile_start[j], each owning ceil(rows / (K << (5 - j))) items; split_item_end[j] = items of classes 0..j
+    uint32_t split_tile_start[SWB_MAX_LOGG];
     uint32_t split_item_end[SWB_MAX_LOGG];
-    uint32_t split_stage_item;  // SPLIT: 1 = every work item stages the profile rows of its pass (one warp per block),
-                                // 0 = the block staged the whole chunk
     uint32_t warps_active;    // warps of a block that take work (0 = all): a launch with few tiles spreads them over the SMs
     uint32_t *prog;           // [item] columns of its bottom row that a pass has published (zeroed per query)
+    // V16R (rebased s16): columns per block = 1 << rebase_shift (chosen by the host from the scoring scheme so that a
+    // pass over one block spans less than 2^15 score points); blog = base log of the boundary rows, two int32 per
+    // (pass parity, slot, block), see swb_blog_offset
+    uint32_t rebase_shift;
+    void *blog;
 };
+
+// base log (V16R): element offset (uint2) of a tile's region, 2 * (((width * slots) >> 6) + 33) elements long
+SWB_HD size_t swb_blog_offset(uint64_t bnd_off, uint32_t tile_idx) { return 2u * ((size_t)(bnd_off >> 6) + 34u * (size_t)tile_idx); }
+SWB_HD size_t swb_blog_elems(uint64_t bnd_elems, uint32_t ntiles) { return 2u * ((size_t)(bnd_elems >> 6) + 34u * (size_t)ntiles) + 68u; }
 
 SWB_HD uint32_t swb_roundup(uint32_t v, uint32_t m) { return (v + m - 1) / m * m; }

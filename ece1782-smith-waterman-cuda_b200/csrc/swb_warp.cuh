@@ -10,12 +10,14 @@
 // Three arithmetic policies run the same program:
 //   V16   two DB sequences in the halves of a 32-bit word, signed s16x2 DPX instructions
 //         (prmt, viaddmax.relu, viaddmax, vadd2, 1/2 vimax3 = 4.5 ALU-pipe instructions per cell pair)
-//   V16Q  the halves are two QUERIES against one DB sequence (batches): the packed score is one profile word, no prmt:
-//         3.5 ALU-pipe instructions per cell pair
-//   V32   two int32 lanes; exact for any score; used to re-score tiles flagged by the s16 passes.
+//   V32   two int32 lanes; exact for any score; re-scores flagged one-lane tiles (and everything when V16R cannot run).
+//   V16R  packed s16x2 RELATIVE to a base that moves with the columns ("rebased"): exact for any score at 4.5
+//         ALU-pipe instructions per cell pair; lane-group tiles only. Re-scores flagged lane-group tiles and scores
+//         long-against-long tiles directly (their true scores pass 32767 anyway).
 //   V16A / V32A  the affine-gap versions of V16 / V32 (two values per element: H and F along the chain, H and E per row)
-// (A third policy that moved the additions to the FMA pipe as IMADs in a biased domain was measured
-//  slower on B200 -- register-file operand bandwidth, see DESIGN.md -- and was removed.)
+// (Two more policies were measured slower on B200 and removed, see DESIGN.md: one that moved the additions to the FMA
+//  pipe as IMADs in a biased domain -- register-file operand bandwidth -- and one that packed two QUERIES into the
+//  halves of a word -- 4 B of shared-memory profile per packed cell.)
 //
 // Work split: a lane keeps K consecutive query rows in registers ("strip") and walks along the DB
 // columns. G lanes of a group hold G consecutive strips and run a wavefront: lane g works on column
@@ -67,6 +69,14 @@ struct V16Base {
         return __vimax3_s16x2(a, b, b);
 #endif
     }
+    static SWB_HD T add(T a, T b)
+    {
+#ifdef __CUDA_ARCH__
+        return __vadd2(a, b);
+#else
+        return ((a + b) & 0xffffu) | ((((a >> 16) + (b >> 16)) & 0xffffu) << 16);
+#endif
+    }
     static SWB_HD int lo(T v) { return (int)(int16_t)(v & 0xffffu); }
     static SWB_HD int hi(T v) { return (int)(int16_t)(v >> 16); }
     // profile byte I (0..3) of the A word and of the B word, sign-extended into one s16x2
@@ -90,21 +100,13 @@ struct V16Base {
 // V16: plain signed domain. Stored per row: H(k, j-1) - g. Profile entry: S + g.
 //   c = viaddmax.relu(diag-g, S+g, left-g) ; h = viaddmax(h, -g, c) ; left' = vadd2(h, -g)
 struct V16 : V16Base {
-    static const bool qpair = false;
+    static const bool rebased = false;
     struct C { T negg; };
     static SWB_HD C consts(const SwbScoreParams &p) { C c; c.negg = splat(-p.gap); return c; }
     static SWB_HD T hzero(const C &) { return 0u; }
     static SWB_HD T lzero(const C &c) { return c.negg; }
     static SWB_HD int score_lo(T best, const C &) { return lo(best); }
     static SWB_HD int score_hi(T best, const C &) { return hi(best); }
-    static SWB_HD T add(T a, T b)
-    {
-#ifdef __CUDA_ARCH__
-        return __vadd2(a, b);
-#else
-        return ((a + b) & 0xffffu) | ((((a >> 16) + (b >> 16)) & 0xffffu) << 16);
-#endif
-    }
     // one DB column against the K rows of this lane; returns the bottom H
     template <int K>
     static SWB_HD T column(T up, T &diag0, T (&left)[K], T &best, const C &cst, uint32_t codeA, uint32_t codeB,
@@ -139,37 +141,104 @@ struct V16 : V16Base {
 };
 
 // ---------------------------------------------------------------------------------------------
-// V16Q: query-pair packing for batches. The two halves of a word are TWO QUERIES against ONE database sequence, so
-// the packed score of a cell is a single profile word [code][row] = (S(qA_row, code) + g, S(qB_row, code) + g): one
-// LDS.32 and no prmt -> 3.5 ALU-pipe instructions per cell pair instead of 4.5. A tile is processed as two work
-// items (the first and the second sequence of each pair); rows past the end of the shorter query score 0.
-struct V16Q : V16Base {
-    static const bool qpair = true;
-    struct C { T negg; };
-    static SWB_HD C consts(const SwbScoreParams &p) { C c; c.negg = splat(-p.gap); return c; }
-    static SWB_HD T hzero(const C &) { return 0u; }
-    static SWB_HD T lzero(const C &c) { return c.negg; }
-    static SWB_HD int score_lo(T best, const C &) { return lo(best); }
-    static SWB_HD int score_hi(T best, const C &) { return hi(best); }
+// V16R: s16x2 values relative to a per-sequence base that follows the data ("rebased").
+// Neighbouring cells of the H matrix differ by at most maxS + g (H(i,j) >= H(i,j-1) - g by the gap term, and
+// H(i,j) <= H(i,j-1) + maxS + g by induction over the four terms; the same along i), so all values of one pass
+// (R = K * G rows) over one block of CB columns lie within (R + CB) * (maxS + g) of any one of them. With that span below
+// 2^15 the block is computed exactly in wrapping 16-bit arithmetic relative to base = H(bottom row of the group's
+// first lane, column before the block), whatever the absolute scores are. At the first column of a block a lane
+// subtracts the new base from its row state (the amount travels down the lane group one column behind the data), folds
+// its running maximum into an int32 and starts a new relative one. The host picks CB (SwbScoreParams::rebase_shift).
+// The floor of the recurrence is not 0 in this domain, so the relu form of V16 does not apply; instead
+//     c = viaddmax(diag - g, S + g, left) ; h = viaddmax(h, -g, c) ; left' = viaddmax(h, -g, floor)
+// with floor = -g - base (clamped to -32000: far below every live value once base is large): the stored row state
+// max(h - g, -g) equals H - g for the true H = max(h, 0), h itself may run g below zero along the chain, which never
+// wins a later max (c >= left' >= -g). One viaddmax replaces V16's vadd2: 4.5 ALU-pipe instructions per cell pair.
+// The boundary row between passes keeps relative values plus a log of the writer's base per block (SwbScoreParams::
+// blog); the reader adds (writer's base - its own base) with one vadd2 per column.
+struct V16R : V16Base {
+    static const bool rebased = true;
+    static const bool is16 = false;  // exact: never flags, counts as a recompute pass
+    struct C {
+        T negg, fl, zrel;   // -g | floor of the row state (-g absolute) | zero (absolute) in the current base
+        int g;
+        int baseA, baseB;   // current base of the two sequences (absolute H values)
+        int bestA, bestB;   // running maxima of the blocks behind
+    };
+    static SWB_HD int clampf(int v) { return v < -32000 ? -32000 : v; }
+    static SWB_HD T pack(int a, int b) { return ((uint32_t)a & 0xffffu) | ((uint32_t)b << 16); }
+    static SWB_HD void set_base(C &c, int a, int b)
+    {
+        c.baseA = a;
+        c.baseB = b;
+        c.fl = pack(clampf(-c.g - a), clampf(-c.g - b));
+        c.zrel = pack(clampf(-a), clampf(-b));
+    }
+    static SWB_HD C consts(const SwbScoreParams &p)
+    {
+        C c;
+        c.g = p.gap;
+        c.negg = splat(-p.gap);
+        c.bestA = c.bestB = 0;
+        set_base(c, 0, 0);
+        return c;
+    }
+    static SWB_HD T hzero(const C &c) { return c.zrel; }
+    static SWB_HD T lzero(const C &c) { return c.negg; }  // only used at the start of a pass, where the base is 0
+    static SWB_HD int score_lo(T, const C &c) { return c.bestA; }
+    static SWB_HD int score_hi(T, const C &c) { return c.bestB; }
+    static SWB_HD T sub(T a, T b)
+    {
+#ifdef __CUDA_ARCH__
+        return __vsub2(a, b);
+#else
+        return ((a - b) & 0xffffu) | ((((a >> 16) - (b >> 16)) & 0xffffu) << 16);
+#endif
+    }
+    // the running relative maximum joins the absolute one; a new relative maximum starts
+    static SWB_HD void fold(T &best, C &c)
+    {
+        const int a = c.baseA + lo(best), b = c.baseB + hi(best);
+        c.bestA = a > c.bestA ? a : c.bestA;
+        c.bestB = b > c.bestB ? b : c.bestB;
+        best = 0x80008000u;
+    }
+    // new base = old base + d (d: relative value of the reference cell): all row state moves by -d
+    template <int K> static SWB_HD void rebase(T d, T &diag0, T (&left)[K], T &best, C &c)
+    {
+        fold(best, c);
+        set_base(c, c.baseA + lo(d), c.baseB + hi(d));
+#pragma unroll
+        for (int k = 0; k < K; ++k) left[k] = sub(left[k], d);
+        diag0 = sub(diag0, d);
+    }
     template <int K>
-    static SWB_HD T column(T up, T &diag0, T (&left)[K], T &best, const C &cst, uint32_t code, uint32_t,
+    static SWB_HD T column(T up, T &diag0, T (&left)[K], T &best, const C &cst, uint32_t codeA, uint32_t codeB,
                            const int8_t *prow, uint32_t sstride)
     {
-        const uint32_t *r = reinterpret_cast<const uint32_t *>(prow + code * sstride);
+        const uint32_t *ra = reinterpret_cast<const uint32_t *>(prow + codeA * sstride);
+        const uint32_t *rb = reinterpret_cast<const uint32_t *>(prow + codeB * sstride);
         T h = up;
         T dg = diag0;
-        diag0 = V16::add(up, cst.negg);
+        diag0 = __viaddmax_s16x2(up, cst.negg, cst.fl);
 #pragma unroll
-        for (int k = 0; k < K; k += 2) {
-            const T c0 = __viaddmax_s16x2_relu(dg, r[k], left[k]);
-            dg = left[k];
-            h = __viaddmax_s16x2(h, cst.negg, c0);
-            left[k] = V16::add(h, cst.negg);
-            const T c1 = __viaddmax_s16x2_relu(dg, r[k + 1], left[k + 1]);
-            dg = left[k + 1];
-            h = __viaddmax_s16x2(h, cst.negg, c1);
-            left[k + 1] = V16::add(h, cst.negg);
-            best = __vimax3_s16x2(best, c0, c1);
+        for (int k4 = 0; k4 < K / 4; ++k4) {
+            const uint32_t wa = ra[k4];
+            const uint32_t wb = rb[k4];
+            T c[4];
+#define SWB_CELL(I)                                                        \
+    {                                                                      \
+        const T s = pair<I>(wa, wb);                                       \
+        c[I] = __viaddmax_s16x2(dg, s, left[4 * k4 + I]);                  \
+        dg = left[4 * k4 + I];                                             \
+        h = __viaddmax_s16x2(h, cst.negg, c[I]);                           \
+        left[4 * k4 + I] = __viaddmax_s16x2(h, cst.negg, cst.fl);          \
+    }
+            SWB_CELL(0) SWB_CELL(1)
+            best = __vimax3_s16x2(best, c[0], c[1]);
+            SWB_CELL(2) SWB_CELL(3)
+            best = __vimax3_s16x2(best, c[2], c[3]);
+#undef SWB_CELL
         }
         return h;
     }
@@ -178,7 +247,7 @@ struct V16Q : V16Base {
 // ---------------------------------------------------------------------------------------------
 // V32: the same two sequences on two int32 lanes (no wrap for any realistic input).
 struct V32 {
-    static const bool qpair = false;
+    static const bool rebased = false;
     struct T { int a, b; };
     struct C { int g; };
     static const bool is16 = false;
@@ -257,7 +326,7 @@ struct V32 {
 // the previous column (h = H - go, f = E). Profile entry: S + go. With go == ge this is the linear recurrence.
 // V16A: two DB sequences per word (s16x2, 6.5 ALU-pipe instructions per cell pair); V32A: exact int32 recompute.
 struct V16A {
-    static const bool qpair = false;
+    static const bool rebased = false;
     static const bool is16 = true;
     struct T { uint32_t h, f; };
     struct C { uint32_t neg_go, neg_ge; };
@@ -342,7 +411,7 @@ struct V16A {
 };
 
 struct V32A {
-    static const bool qpair = false;
+    static const bool rebased = false;
     static const bool is16 = false;
     struct T { int ha, hb, fa, fb; };
     struct C { int go, ge; };
@@ -437,12 +506,10 @@ struct V32A {
 template <int K, class V, bool GROUPED, bool SPLIT, class BE>
 SWB_HD void swb_run_tile(BE &be, const SwbScoreParams &p, const SwbTile &tile, uint32_t tile_idx,
                          const int8_t *sprof, uint32_t sstride, uint32_t ss_begin = 0, uint32_t ss_count = 0xffffffffu,
-                         uint32_t *prog = nullptr, uint32_t smem_ss0 = 0, uint32_t half = 0)
+                         uint32_t *prog = nullptr, uint32_t smem_ss0 = 0)
 {
-    // V::qpair: this work item covers sequence `half` (0 / 1) of every pair of the tile, for two queries at once
     typedef typename V::T T;
-    const typename V::C cst = V::consts(p);
-    const T HZERO = V::hzero(cst);
+    typename V::C cst = V::consts(p);
     const T LZERO = V::lzero(cst);
     const int lane = be.lane();
     const int logG = GROUPED ? (int)tile.logG : 0;
@@ -457,16 +524,21 @@ SWB_HD void swb_run_tile(BE &be, const SwbScoreParams &p, const SwbTile &tile, u
     const uint32_t rows_per_super = (uint32_t)K << logG;
     const uint32_t nsuper = (p.rows + rows_per_super - 1) / rows_per_super;
     const uint32_t nsteps4 = GROUPED ? ((W + (uint32_t)G - 1u + 3u) >> 2) : nchunks;
-    const uint8_t *res = p.residues + tile.res_off + (size_t)slot * 8u + (V::qpair ? half : 0u);
+    const uint8_t *res = p.residues + tile.res_off + (size_t)slot * 8u;
     const size_t res_stride = (size_t)P * 8u;
-    // qpair: two work items per tile, each with its own boundary rows
-    T *bnd = reinterpret_cast<T *>(p.bnd) + (V::qpair ? 2u * tile.bnd_off + (size_t)half * W * P : tile.bnd_off);
-    T best = HZERO;
+    T *bnd = reinterpret_cast<T *>(p.bnd) + tile.bnd_off;
+    T best = V::hzero(cst);
+    // V16R: base log of the boundary rows, [pass parity][slot][block] (see swb_blog_*)
+    const uint32_t cbmask = V::rebased ? (1u << p.rebase_shift) - 1u : 0u;
+    const uint32_t blog_nb = V::rebased ? (W >> p.rebase_shift) + 2u : 0u;
+    const size_t blog_par = ((size_t)W * (size_t)P >> 6) + 33u;
+    uint2 *blog = V::rebased ? reinterpret_cast<uint2 *>(p.blog) + swb_blog_offset(tile.bnd_off, tile_idx) : nullptr;
+    const uint32_t pass0 = V::rebased ? p.row0 / rows_per_super : 0u;  // passes of the query chunks before this launch
 
     const uint32_t ss_end = ss_count < nsuper - ss_begin ? ss_begin + ss_count : nsuper;
     for (uint32_t ss = ss_begin; ss < ss_end; ++ss) {
         // smem_ss0: the pass whose first row sits at row 0 of the staged profile (0 except in SPLIT launches)
-        const int8_t *prow = sprof + (size_t)((((ss - smem_ss0) << logG) + (uint32_t)g) * (uint32_t)K) * (V::qpair ? 4u : 1u);
+        const int8_t *prow = sprof + (size_t)((((ss - smem_ss0) << logG) + (uint32_t)g) * (uint32_t)K);
         const bool read_top = !(p.first_chunk && ss == 0);
         const bool write_bot = !(p.last_chunk && ss + 1 == nsuper);
         const bool wait_top = SPLIT && ss > 0;  // the row above comes from another warp of this launch
@@ -475,8 +547,16 @@ SWB_HD void swb_run_tile(BE &be, const SwbScoreParams &p, const SwbTile &tile, u
 #pragma unroll
         for (int k = 0; k < K; ++k) left[k] = LZERO;
         T diag0 = LZERO;
-        T hprev = HZERO;
+        T hprev = V::hzero(cst);
         uint32_t aprev = SWB_PAD, bprev = SWB_PAD;
+        // V16R: this lane's column, the base difference to the row above, the amount of the latest rebase
+        int colg = -g;
+        T dconv = T(), dcur = T();
+        uint2 *blog_rd = nullptr, *blog_wr = nullptr;
+        if constexpr (V::rebased) {
+            blog_wr = blog + (size_t)((pass0 + ss) & 1u) * blog_par + (size_t)slot * blog_nb;
+            blog_rd = blog + (size_t)((pass0 + ss + 1u) & 1u) * blog_par + (size_t)slot * blog_nb;
+        }
 
         // residue codes of the current chunk (4 columns x two sequences), fetched by the lead lane with byte loads:
         // the codes arrive zero-extended in registers, so no ALU-pipe instruction is spent on unpacking them
@@ -486,13 +566,14 @@ SWB_HD void swb_run_tile(BE &be, const SwbScoreParams &p, const SwbTile &tile, u
         for (int u = 0; u < 4; ++u) {
             ca[u] = SWB_PAD;
             cb[u] = SWB_PAD;
-            bc[u] = HZERO;
+            bc[u] = V::hzero(cst);
         }
+        bool top_cur = nchunks > 0 && read_top;  // bc holds values of the row above (uniform over the warp)
         if (lead && nchunks > 0) {
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 ca[u] = be.ld_code(res + 2 * u);
-                if (!V::qpair) cb[u] = be.ld_code(res + 2 * u + 1);
+                cb[u] = be.ld_code(res + 2 * u + 1);
             }
         }
         if (wait_top) {
@@ -514,8 +595,9 @@ SWB_HD void swb_run_tile(BE &be, const SwbScoreParams &p, const SwbTile &tile, u
             for (int u = 0; u < 4; ++u) {
                 na[u] = SWB_PAD;
                 nb[u] = SWB_PAD;
-                bn[u] = HZERO;
+                bn[u] = V::hzero(cst);
             }
+            const bool top_next = c + 1 < nchunks && read_top;
             if (wait_top && c + 1 < nchunks) {
                 const uint32_t need = 4u * c + 8u < W ? 4u * c + 8u : W;
                 if (avail < need) avail = be.wait_progress(prog + ss - 1, need);
@@ -525,7 +607,7 @@ SWB_HD void swb_run_tile(BE &be, const SwbScoreParams &p, const SwbTile &tile, u
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     na[u] = be.ld_code(rnext + 2 * u);
-                    if (!V::qpair) nb[u] = be.ld_code(rnext + 2 * u + 1);
+                    nb[u] = be.ld_code(rnext + 2 * u + 1);
                 }
                 if (read_top) {
                     if (!GROUPED) {
@@ -542,8 +624,31 @@ SWB_HD void swb_run_tile(BE &be, const SwbScoreParams &p, const SwbTile &tile, u
                 T up = bc[u];
                 if (GROUPED) {
                     const uint32_t a2 = be.shfl_up(aprev, 1, G);
-                    const uint32_t b2 = V::qpair ? 0u : be.shfl_up(bprev, 1, G);
+                    const uint32_t b2 = be.shfl_up(bprev, 1, G);
                     const T u2 = V::shfl_up(be, hprev, 1, G);
+                    if constexpr (V::rebased) {
+                        // first column of a block: move to the new base. The first lane of the group takes it from its
+                        // own bottom row (the column just behind), the others receive the amount from the lane above,
+                        // which made the same move one column step ago.
+                        const T d2 = V::shfl_up(be, dcur, 1, G);
+                        if (colg > 0 && ((uint32_t)colg & cbmask) == 0u) {
+                            const T d = lead ? hprev : d2;
+                            dcur = d;
+                            V::template rebase<K>(d, diag0, left, best, cst);
+                            const uint32_t blk = (uint32_t)colg >> p.rebase_shift;
+                            if (lead) {
+                                dconv = T();
+                                if (read_top) {
+                                    const uint2 bw = be.ld_cg2(blog_rd + blk);
+                                    dconv = V::pack((int)bw.x - cst.baseA, (int)bw.y - cst.baseB);
+                                }
+                            }
+                            if (tail && write_bot) be.st_cg2(blog_wr + blk, make_uint2((uint32_t)cst.baseA, (uint32_t)cst.baseB));
+                        }
+                        // the row above: relative to its writer's base -> to this lane's base; none: zero (absolute)
+                        up = top_cur ? V::add(up, dconv) : V::hzero(cst);
+                        ++colg;
+                    }
                     if (!lead) { a = a2; b = b2; up = u2; }
                 }
                 const T h = V::template column<K>(up, diag0, left, best, cst, a, b, prow, sstride);
@@ -578,27 +683,29 @@ SWB_HD void swb_run_tile(BE &be, const SwbScoreParams &p, const SwbTile &tile, u
                 cb[u] = nb[u];
                 bc[u] = bn[u];
             }
+            top_cur = top_next;
+        }
+        if constexpr (V::rebased) {  // the next pass starts at base 0 again
+            V::fold(best, cst);
+            V::set_base(cst, 0, 0);
         }
         be.syncwarp();
     }
 
-    if (GROUPED) {
+    if constexpr (V::rebased) {
+        for (int m = G >> 1; m >= 1; m >>= 1) {
+            const int oa = (int)be.shfl_xor((uint32_t)cst.bestA, m, G), ob = (int)be.shfl_xor((uint32_t)cst.bestB, m, G);
+            cst.bestA = oa > cst.bestA ? oa : cst.bestA;
+            cst.bestB = ob > cst.bestB ? ob : cst.bestB;
+        }
+    } else if (GROUPED) {
         for (int m = G >> 1; m >= 1; m >>= 1) best = V::max2(best, V::shfl_xor(be, best, m, G));
     }
     bool flagged = false;
     if (lead && slot < (int)tile.npairs) {
         const size_t s0 = 2u * ((size_t)tile.first_pair + (size_t)slot);
         int a = V::score_lo(best, cst), b = V::score_hi(best, cst);
-        if (V::qpair) {
-            // lo half = query A, hi half = query B, both against sequence s0 + half
-            int32_t *sa = p.scores + s0 + half, *sb = p.scores2 + s0 + half;
-            if (!p.first_chunk) {
-                a = a > *sa ? a : *sa;
-                b = b > *sb ? b : *sb;
-            }
-            *sa = a;
-            *sb = b;
-        } else if (SPLIT) {
+        if (SPLIT) {
             be.atomic_max(p.scores + s0, a);
             be.atomic_max(p.scores + s0 + 1, b);
         } else {
@@ -631,14 +738,14 @@ SWB_HD void swb_warp_loop(BE &be, const SwbScoreParams &p, const int8_t *sprof, 
         if (v >= p.ntiles) break;
         if (SPLIT) {
             // one warp per block; it stages only the K << logG profile rows of its pass (sstride = K * 32 + 4).
-            // Item -> (tile, pass): the split set is the head of the tile array, one class per lane-group size
+            // Item -> (tile, pass): the split set is a run of tiles per lane-group size (class j = 32 >> j lanes)
             int l = SWB_MAX_LOGG;
-            uint32_t tile0 = 0, item0 = 0;
+            uint32_t tile0 = p.split_tile_start[0], item0 = 0;
 #pragma unroll
             for (int j = 0; j + 1 < SWB_MAX_LOGG; ++j)
                 if (v >= p.split_item_end[j]) {
                     l = SWB_MAX_LOGG - 1 - j;
-                    tile0 = p.split_tile_end[j];
+                    tile0 = p.split_tile_start[j + 1];
                     item0 = p.split_item_end[j];
                 }
             const uint32_t rows_per_pass = (uint32_t)K << l;
@@ -647,26 +754,26 @@ SWB_HD void swb_warp_loop(BE &be, const SwbScoreParams &p, const int8_t *sprof, 
             const uint32_t ti = tile0 + t;
             if (p.only_flagged && !be.ld_flag(p.flags + ti)) continue;  // every pass of the tile skips alike
             const SwbTile tile = be.ld_tile(p.tiles + ti);
-            if (p.split_stage_item)
-                be.stage_rows(const_cast<int8_t *>(sprof), sstride, p.profile, p.prof_stride,
-                              p.row0 + ss * rows_per_pass, rows_per_pass);
-            swb_run_tile<K, V, true, true>(be, p, tile, ti, sprof, sstride, ss, 1u, p.prog + item0 + (size_t)t * passes,
-                                           p.split_stage_item ? ss : 0u);
+            be.stage_rows(const_cast<int8_t *>(sprof), sstride, p.profile, p.prof_stride, p.row0 + ss * rows_per_pass,
+                          rows_per_pass);
+            swb_run_tile<K, V, true, true>(be, p, tile, ti, sprof, sstride, ss, 1u, p.prog + item0 + (size_t)t * passes, ss);
             continue;
         }
-        // qpair launches: two work items per tile (first / second sequence of every pair); ntiles counts items
-        const uint32_t half = V::qpair ? (v & 1u) : 0u;
-        const uint32_t vt = V::qpair ? (v >> 1) : v;
+        const uint32_t vt = v;
         uint32_t ti = p.range_start[0] + vt;
 #pragma unroll
         for (int r = 1; r < SWB_MAX_RANGES; ++r)
             if (vt >= p.range_cum[r - 1]) ti = p.range_start[r] + (vt - p.range_cum[r - 1]);
         if (p.only_flagged && !be.ld_flag(p.flags + ti)) continue;
         const SwbTile tile = be.ld_tile(p.tiles + ti);
-        if (tile.logG == 0)
-            swb_run_tile<K, V, false, false>(be, p, tile, ti, sprof, sstride, 0, 0xffffffffu, nullptr, 0, half);
-        else
-            swb_run_tile<K, V, true, false>(be, p, tile, ti, sprof, sstride, 0, 0xffffffffu, nullptr, 0, half);
+        if constexpr (V::rebased) {  // rebasing lives in the lane-group program; one lane per pair is its G = 1 case
+            swb_run_tile<K, V, true, false>(be, p, tile, ti, sprof, sstride);
+        } else {
+            if (tile.logG == 0)
+                swb_run_tile<K, V, false, false>(be, p, tile, ti, sprof, sstride);
+            else
+                swb_run_tile<K, V, true, false>(be, p, tile, ti, sprof, sstride);
+        }
     }
 }
 

@@ -2,6 +2,9 @@
 // as --flag=value and as unambiguous prefixes like boost::program_options accepts), same stdout text, same
 // exit codes (1 for help / no arguments / a missing required option, 0 after a scan). An unknown option is
 // an uncaught exception, as in the reference (main.cpp:38 only catches po::required_option).
+// Extension that leaves the default output untouched: --gpus N scans on the first N visible GPUs (default: all of them;
+// the database is residue-sharded across the devices inside this one process, include/swb.h swb_group_*).
+#include <stdlib.h>
 #include <sys/time.h>
 #include <stdexcept>
 #include <string>
@@ -29,12 +32,12 @@ static void usage()
             "  --db arg              Path to database file (required)\n";
 }
 
-// 0 help, 1 query, 2 db; throws on unknown / ambiguous names
+// 0 help, 1 query, 2 db, 3 gpus; throws on unknown / ambiguous names
 static int match_option(const std::string &name)
 {
-    static const char *const names[3] = {"help", "query", "db"};
+    static const char *const names[4] = {"help", "query", "db", "gpus"};
     int hit = -1;
-    for (int i = 0; i < 3; ++i) {
+    for (int i = 0; i < 4; ++i) {
         const std::string full(names[i]);
         if (full == name) return i;
         if (!name.empty() && full.compare(0, name.size(), name) == 0) {
@@ -61,14 +64,17 @@ static int scan_encoded_db(const std::string &querypath, const std::string &data
     const uint32_t n = swb_dbfile_count(dbf);
     const uint64_t *offsets = swb_dbfile_offsets(dbf);
     const int first_id = swb_dbfile_first_id(dbf);
-    swb_engine *eng = nullptr;
-    if (swb_create(&eng, 0) != SWB_OK) throw std::runtime_error(std::string("swb_create: ") + swb_last_error(nullptr));
+    swb_group *eng = nullptr;
+    if (swb_group_create_env(&eng) != SWB_OK)
+        throw std::runtime_error(std::string("swb_group_create: ") + swb_group_last_error(nullptr));
     std::vector<uint8_t> qcodes(q.size() ? q.size() : 1);
     swb_encode(SWB_SCORING_BLOSUM50_REF, q.data(), q.size(), qcodes.data());
     std::vector<int32_t> scores(n ? n : 1);
-    if (swb_db_load(eng, swb_dbfile_codes(dbf), offsets, n, 0, 1) != SWB_OK ||
-        swb_search(eng, qcodes.data(), (uint32_t)q.size(), scores.data()) != SWB_OK)
-        throw std::runtime_error(std::string("scan failed: ") + swb_last_error(eng));
+    const uint64_t qoffs[2] = {0, q.size()};
+    if (swb_group_set_option(eng, "db_parts", swb_group_size(eng)) != SWB_OK ||
+        swb_group_db_load(eng, swb_dbfile_codes(dbf), offsets, n) != SWB_OK ||
+        swb_group_search_batch(eng, qcodes.data(), qoffs, 1, scores.data()) != SWB_OK)
+        throw std::runtime_error(std::string("scan failed: ") + swb_group_last_error(eng));
     std::vector<uint32_t> order(n);
     long long padded_sum = 0;
     std::vector<uint64_t> padded(n);
@@ -95,7 +101,7 @@ static int scan_encoded_db(const std::string &querypath, const std::string &data
     cout << "Sum of DB length: " << (int)padded_sum << " chars." << endl;
     cout << "Time elapsed: " << seconds_elapsed << " seconds." << endl;
     cout << "Performance: " << 1E-9 * ((double)q.length() * (double)padded_sum) / seconds_elapsed << " GCUPS." << endl;
-    swb_destroy(eng);
+    swb_group_destroy(eng);
     swb_dbfile_close(dbf);
     return 0;
 }
@@ -119,7 +125,8 @@ int main(int argc, char *argv[])
         else if (i + 1 < argc) value = argv[++i];
         else throw std::runtime_error("the required argument for option '" + arg + "' is missing");
         if (opt == 1) { querypath = value; have_query = true; }
-        else { datapath = value; have_db = true; }
+        else if (opt == 2) { datapath = value; have_db = true; }
+        else setenv("SWB_GPUS", value.c_str(), 1);  // read where the engine group is created
     }
     if (help || argc <= 1 || !have_query || !have_db) {
         usage();

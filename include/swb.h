@@ -17,7 +17,8 @@
  *   host packing loop + managed upload      SWSolver.cu:301-359  swb_db_load   (once per database)
  *   query upload to constQuery              SWSolver.cu:291-298  swb_search / swb_search_batch
  *   f_scoreSequenceTiledCoalesced launches  SWSolver.cu:201-264, 346, 379      "
- *   result gather                           SWSolver.cu:383-390  scores[] in database order
+ *   result gather                           SWSolver.cu:383-390  scores[] in database order; swb_search_batch_topk
+ *   the whole call on every GPU of the box  main.cpp:52-56       swb_group_* (one process, one engine per GPU)
  *   traceback of a pair (CPU solver)        cpu.cpp:39-108       swb_align (one hit of a scan, on the GPU)
  *   text parsing of the database            FASTAParsers.h:73-136 swb_read_fasta / swb_dbfile_* (optional fast path)
  *
@@ -79,14 +80,11 @@ const char *swb_last_error(const swb_engine *e);
  *          "group_order" (0 = auto, 1 = launch the long-sequence tiles first, 2 = launch the bulk first),
  *          "batch_order" (0 = a batch runs its longest query first (default), 1 = in the caller's order; the
  *          results are always in the caller's order),
- *          "pair_queries" (1 = a batch packs two queries of similar length into the two s16 halves of a lane, one
- *          database sequence per lane, no byte permute; measured slower on B200 (shared-memory bound); default 0),
  *          "split" (1 = the passes of sequences longer than "xl_len" run as pipelined work items on
  *          different warps, 0 = never, -1 (default) = only on small shards, where those few tiles are the critical
  *          path of a query: +10 % at 1/8 of Swiss-Prot per GPU; on a large shard it costs ~0.5 %),
  *          "xl_len" (lane-group tiles wider than this are the ones "split" applies to, default 3072; before db_load),
- *          "split_fill" (N > 0: split launches use 16 / 32 rows per lane while they keep N work items; measured
- *          slower than 8 rows on B200, default 0 = always 8),
+ *          "load_threads" (host threads that gather the residues of a sharded load, default 4),
  *          "chunk_rows" (query rows per launch for queries beyond shared memory; multiple of 1024, <= 7168) */
 int swb_set_option(swb_engine *e, const char *key, int64_t value);
 /* run on the caller's CUDA stream (cudaStream_t as void*); NULL = the engine's own stream */
@@ -120,7 +118,18 @@ int swb_search(swb_engine *e, const uint8_t *query, uint32_t qlen, int32_t *scor
  * results on the device (read them later with swb_fetch_scores) */
 int swb_search_batch(swb_engine *e, const uint8_t *qcodes, const uint64_t *qoffsets, uint32_t nq, int32_t *scores);
 int swb_fetch_scores(swb_engine *e, uint32_t query_index, int32_t *scores);
-/* k best (score desc, id asc) of one score vector of this shard; ids are database ids */
+/* The same scan, results written by DATABASE ID into vectors of the whole database: scores_full is nq x n_total
+ * (n_total = the n of swb_db_load), query q, database id i -> scores_full[q * n_total + i]; this engine fills the ids
+ * of its own shard and leaves the others alone, so the engines of all shards (one per GPU) can share one matrix. */
+int swb_search_batch_scatter(swb_engine *e, const uint8_t *qcodes, const uint64_t *qoffsets, uint32_t nq,
+                             int32_t *scores_full, uint64_t n_total);
+/* The same scan with the hit list selected ON THE DEVICE: per query the k best sequences of this shard, score
+ * descending, database id ascending on equal scores (k <= 1024): ids[q * k + j], top[q * k + j]; when the shard has
+ * fewer than k sequences the rest is id 0xffffffff, score -1. Copies 8 k bytes per query back instead of 4 n (the
+ * reference returns every score, SWSolver.cu:383-390); the full vectors stay on the device for swb_fetch_scores. */
+int swb_search_batch_topk(swb_engine *e, const uint8_t *qcodes, const uint64_t *qoffsets, uint32_t nq, uint32_t k,
+                          uint32_t *ids, int32_t *top);
+/* k best (score desc, id asc) of one score vector of this shard that is already in HOST memory; ids are database ids */
 int swb_topk(const swb_engine *e, const int32_t *scores, uint32_t k, uint32_t *ids, int32_t *top);
 int swb_stats(const swb_engine *e, swb_stats_t *out);
 /* Alignment with traceback of the query against ONE database sequence of this shard (the top hits of a scan) -- what
@@ -130,6 +139,41 @@ int swb_stats(const swb_engine *e, swb_stats_t *out);
  * 2 = gap in the subject (FROM_TOP), 3 = aligned pair (FROM_TOP_LEFT). cap >= qlen + subject length always suffices. */
 int swb_align(swb_engine *e, const uint8_t *query, uint32_t qlen, uint32_t db_id, int32_t *score, uint32_t *end_i,
               uint32_t *end_j, uint8_t *ops, uint32_t cap, uint32_t *nops);
+
+/* ---- engine group: every GPU of the box in one process (the reference is one process, main.cpp:52-56) --- */
+/* One engine, one host worker thread and one stream set per device. The devices form P database parts x R query groups
+ * (P * R = devices): device (p, r) keeps part p of the residue-balanced sharding resident and scores the queries of
+ * group r of a batch (groups of equal total length, longest-processing-time first). P = the largest divisor of the
+ * device count whose parts keep at least "min_part_sequences" sequences (default 250,000: smaller shards have fewer
+ * warp tiles than a B200 has warp slots); option "db_parts" forces it (= devices: pure database sharding). */
+typedef struct swb_group swb_group;
+/* devices == NULL: devices 0 .. ndev-1; ndev == 0: every visible device */
+int swb_group_create(swb_group **out, const int *devices, int ndev);
+/* the same from the environment: SWB_DEVICES=<i,j,...> (indices may repeat: several engines on one device), else
+ * SWB_GPUS=<n> (the first n devices), else every visible device */
+int swb_group_create_env(swb_group **out);
+void swb_group_destroy(swb_group *g);
+const char *swb_group_last_error(const swb_group *g); /* g == NULL: last failed swb_group_create of this thread */
+int swb_group_size(const swb_group *g);
+swb_engine *swb_group_engine(swb_group *g, int i); /* the engine of device i (stats, options) */
+int swb_group_db_parts(const swb_group *g);        /* P of the loaded layout, 0 before swb_group_db_load */
+/* "db_parts", "min_part_sequences", or any swb_set_option key (applied to every engine) */
+int swb_group_set_option(swb_group *g, const char *key, int64_t value);
+int swb_group_set_scoring(swb_group *g, const int8_t *matrix, int alpha, int gap);
+int swb_group_set_scoring_preset(swb_group *g, int preset);
+int swb_group_set_scoring_affine(swb_group *g, const int8_t *matrix, int alpha, int gap_open, int gap_extend);
+/* one length sort for all parts; the devices load their parts concurrently */
+int swb_group_db_load(swb_group *g, const uint8_t *codes, const uint64_t *offsets, uint32_t n);
+/* scores: nq x n in database order, as swb_search_batch returns them on one GPU */
+int swb_group_search_batch(swb_group *g, const uint8_t *qcodes, const uint64_t *qoffsets, uint32_t nq, int32_t *scores);
+/* per-GPU device-side hit lists merged on the host: ids / top are nq x k, score descending, id ascending */
+int swb_group_search_batch_topk(swb_group *g, const uint8_t *qcodes, const uint64_t *qoffsets, uint32_t nq, uint32_t k,
+                                uint32_t *ids, int32_t *top);
+/* totals over the devices of the last call (device_ms = the slowest device) */
+int swb_group_stats(const swb_group *g, swb_stats_t *out);
+/* the layout rules, CPU only: P for n sequences on ndev devices; group_of[q] for R groups of a batch (LPT) */
+int swb_layout_parts(uint32_t n, int ndev, uint32_t min_part_sequences);
+int swb_layout_query_groups(const uint64_t *qoffsets, uint32_t nq, int groups, uint32_t *group_of);
 
 /* ---- plan introspection, CPU only (host logic of swb_db_load) ------------------------------ */
 typedef struct swb_plan_info_t {
@@ -162,10 +206,15 @@ void swb_dbfile_close(swb_dbfile *d);
 
 /* ---- measurement support (not on the scoring path) ------------------------------------------- */
 /* Issue rate of the integer SIMD instructions the score kernel is built from, whole GPU, in giga
- * lane-instructions/s. kind: 0 viaddmax.s16x2.relu, 1 vimax3.s16x2, 2 vadd2, 3 prmt, 4 the score kernel's per-cell
- * mix, 5 viaddmax+imad, 6 imad, 7 scalar add+max, 8 the mix of the (rejected) biased FMA-pipe variant, 9 hmnmx2 (+ a
- * mask), 10 viaddmax+hmnmx2 (18.3 T: the fp16 comparator shares the ALU pipe, so it cannot take over the max). bench.py
- * uses kind 4 (4.5 instructions per cell pair) as the roofline peak of the score kernel. */
+ * lane-instructions/s. kind: 0 viaddmax.s16x2.relu, 1 vimax3.s16x2, 2 vadd2, 3 prmt, 4 a dependent-chain loop of the
+ * score kernel's per-cell mix, 5 viaddmax+imad, 6 imad, 7 scalar add+max, 8 the mix of the (rejected) biased FMA-pipe
+ * variant, 9 hmnmx2 (+ a mask), 10 viaddmax+hmnmx2 (18.3 T: the fp16 comparator shares the ALU pipe, so it cannot take
+ * over the max), 11 viaddmax+vadd2, 12 viaddmax+prmt, 13 viaddmax+vimax3 in one loop.
+ * Roofline accounting (bench.py): the peak of the score kernel is the ALU-pipe issue rate (kind 0: 64 lanes/clk/SM)
+ * divided by the ALU-pipe instructions per cell. Per cell PAIR the kernel issues prmt + viaddmax.relu + viaddmax +
+ * 1/2 vimax3 on that pipe (3.5) plus one vadd2; kinds 11..13 decide where the vadd2 goes: viaddmax+vadd2 runs at twice
+ * the single rate (vadd2 issues on another pipe -> 3.5 per pair), the other pairs at the single rate (same pipe). If
+ * kind 11 did not double, the count would be 4.5. bench.py prints both variants and the flag it derived. */
 int swb_microbench(int device, int kind, double *glane_instr_per_s, double *ms);
 
 #ifdef __cplusplus

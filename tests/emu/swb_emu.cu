@@ -161,7 +161,7 @@ struct LaneArgs {
     const int8_t *sprof;
     uint32_t sstride;
     int K;
-    int mode;  // 0 V16, 1 V32, 2 V16Q, 3 V16A, 4 V32A
+    int mode;  // 0 V16, 1 V32, 2 V16R, 3 V16A, 4 V32A
     bool split;
 };
 
@@ -170,17 +170,17 @@ void lane_main(HostBackend &be, void *a)
     const LaneArgs *la = static_cast<const LaneArgs *>(a);
     if (la->split) {
         if (la->mode == 1) {
-            if (la->K == 8) swb_warp_loop<8, V32, true>(be, *la->p, la->sprof, la->sstride);
-            else swb_warp_loop<16, V32, true>(be, *la->p, la->sprof, la->sstride);
+            swb_warp_loop<8, V32, true>(be, *la->p, la->sprof, la->sstride);
+        } else if (la->mode == 2) {
+            if (la->K == 8) swb_warp_loop<8, V16R, true>(be, *la->p, la->sprof, la->sstride);
+            else swb_warp_loop<16, V16R, true>(be, *la->p, la->sprof, la->sstride);
         } else {
             if (la->K == 8) swb_warp_loop<8, V16, true>(be, *la->p, la->sprof, la->sstride);
-            else if (la->K == 16) swb_warp_loop<16, V16, true>(be, *la->p, la->sprof, la->sstride);
-            else swb_warp_loop<32, V16, true>(be, *la->p, la->sprof, la->sstride);
+            else swb_warp_loop<16, V16, true>(be, *la->p, la->sprof, la->sstride);
         }
     } else if (la->mode == 2) {
-        if (la->K == 8) swb_warp_loop<8, V16Q, false>(be, *la->p, la->sprof, la->sstride);
-        else if (la->K == 16) swb_warp_loop<16, V16Q, false>(be, *la->p, la->sprof, la->sstride);
-        else swb_warp_loop<32, V16Q, false>(be, *la->p, la->sprof, la->sstride);
+        if (la->K == 8) swb_warp_loop<8, V16R, false>(be, *la->p, la->sprof, la->sstride);
+        else swb_warp_loop<16, V16R, false>(be, *la->p, la->sprof, la->sstride);
     } else if (la->mode == 3) {
         if (la->K == 8) swb_warp_loop<8, V16A, false>(be, *la->p, la->sprof, la->sstride);
         else if (la->K == 16) swb_warp_loop<16, V16A, false>(be, *la->p, la->sprof, la->sstride);
@@ -201,21 +201,17 @@ void lane_main(HostBackend &be, void *a)
 
 // Mirrors swb_db_load + one job of swb_search_batch of the engine (same plan, same chunking, same kernel parameters,
 // same launch groups), with the kernels replaced by the fiber emulation. K: 0 = per-group choice of the planner (the
-// product default), else 8/16/32 for every group size. force_i32: 0 = s16 pass then int32 recompute of flagged tiles
-// (the product flow), 1 = int32 pass over every tile. ovf_thr_override >= 0 replaces the s16 overflow threshold (lets
-// tests force the recompute path). q2 != NULL: a query-pair job (policy V16Q), scores of the second query in
-// scores_out2. xl_len: tiles wider than it run as pipelined passes (single-query jobs only), 0 = never.
+// product default), else 8/16/32 for every group size. force_exact: 0 = s16 pass then exact recompute of flagged tiles
+// (the product flow), 1 = exact pass over every tile. ovf_thr_override >= 0 replaces the s16 overflow threshold (lets
+// tests force the recompute path). xl_len: lane-group tiles wider than it run as pipelined passes, 0 = never.
+// split_k: rows per lane of the pipelined groups (8 / 16). exact_i32: 1 = exact passes in int32 (V32) instead of the
+// rebased s16 policy (V16R). direct_len: pipelined tiles at least this wide (and a query at least this long) are
+// scored by V16R at once; 0 = never. rebase_shift: log2 of the columns per V16R block, 0 = what the engine computes.
 namespace {
-
-struct EmuRun {
-    SwbScoreParams p;
-    uint32_t prof_stride;
-};
 
 void run_pass(SwbScoreParams &p, int mode, const SwbQueryPlan &qp, const std::vector<SwbLaunchGroup> &groups,
               const std::vector<uint8_t> &profbytes, uint32_t prof_stride)
 {
-    const uint32_t esz = mode == 2 ? 4u : 1u;
     for (size_t gi = 0; gi < groups.size(); ++gi) {
         const SwbLaunchGroup &g = groups[gi];
         for (int r = 0; r < SWB_MAX_RANGES; ++r) {
@@ -226,26 +222,24 @@ void run_pass(SwbScoreParams &p, int mode, const SwbQueryPlan &qp, const std::ve
         swb_group_chunks(qp, g, chunks);
         for (size_t c = 0; c < chunks.size(); ++c) {
             const SwbQueryChunk &ch = chunks[c];
-            p.ntiles = mode == 2 ? 2 * g.ntiles : g.ntiles;
+            p.ntiles = g.ntiles;
             std::vector<uint32_t> prog((g.split ? swb_split_items(ch.rows, g, &p) : 0u) + 1u, 0u);
             p.prog = prog.data();
             p.row0 = ch.row0;
             p.rows = ch.rows;
-            const bool per_item = g.split && g.K == 8;
-            p.split_stage_item = per_item;
-            p.smem_rows = per_item ? (uint32_t)g.K * 32u : swb_group_smem_rows(ch.rows, g);
+            p.smem_rows = g.split ? (uint32_t)g.K * 32u : swb_group_smem_rows(ch.rows, g);
             p.first_chunk = ch.first;
             p.last_chunk = ch.last;
             uint32_t counter = 0;
             p.counter = &counter;
-            // stage the chunk's profile exactly like swb_score_kernel
-            const uint32_t sstride = mode == 2 ? (p.smem_rows + 1u) * 4u : p.smem_rows + 4u;
+            // stage the chunk's profile exactly like swb_score_kernel (split groups stage per work item)
+            const uint32_t sstride = p.smem_rows + 4u;
             std::vector<uint32_t> sprof_words(((size_t)sstride * SWB_ALPHA + 64) / 4);
             int8_t *sprof = reinterpret_cast<int8_t *>(sprof_words.data());
-            if (!per_item)
+            if (!g.split)
                 for (uint32_t code = 0; code < SWB_ALPHA; ++code)
-                    memcpy(sprof + (size_t)code * sstride,
-                           profbytes.data() + ((size_t)code * prof_stride + ch.row0) * esz, (size_t)p.smem_rows * esz);
+                    memcpy(sprof + (size_t)code * sstride, profbytes.data() + (size_t)code * prof_stride + ch.row0,
+                           (size_t)p.smem_rows);
             LaneArgs la;
             la.p = &p;
             la.sprof = sprof;
@@ -263,27 +257,24 @@ void run_pass(SwbScoreParams &p, int mode, const SwbQueryPlan &qp, const std::ve
 }  // namespace
 
 // gap_extend != gap: the affine policies (V16A, then V32A on flagged tiles), as enqueue_job of the engine plans them
-static int emu_search(const uint8_t *codes, const uint64_t *offsets, uint32_t n, uint32_t shard, uint32_t nshards,
-                      uint32_t group_len, const int8_t *mat32, int gap, int gap_extend, const uint8_t *q, uint32_t qlen,
-                      int K, int force_i32, uint32_t chunk_rows, int ovf_thr_override, uint32_t xl_len,
-                      int32_t *scores_out, uint32_t *recomputed_tiles, const uint8_t *q2, uint32_t qlen2,
-                      int32_t *scores_out2, uint32_t chunk_rows_pair, uint32_t split_fill)
+extern "C" int swbemu_search(const uint8_t *codes, const uint64_t *offsets, uint32_t n, uint32_t shard, uint32_t nshards,
+                             uint32_t group_len, const int8_t *mat32, int gap, int gap_extend, const uint8_t *q,
+                             uint32_t qlen, int K, int force_exact, uint32_t chunk_rows, int ovf_thr_override,
+                             uint32_t xl_len, int split_k, int exact_i32, uint32_t direct_len, int rebase_shift,
+                             int32_t *scores_out, uint32_t *recomputed_tiles)
 {
     const bool affine = gap_extend != gap;
-    if (affine && q2) return -2;
     SwbPlanOpts o;
     if (group_len) o.group_len = group_len;
     o.xl_len = xl_len;
     SwbPlan pl;
     if (swb_build_plan(offsets, n, shard, nshards ? nshards : 1, o, pl) != 0) return -1;
-    const bool pair = q2 != nullptr;
     const uint32_t nl = pl.n_local;
     if (recomputed_tiles) *recomputed_tiles = 0;
     if (nl == 0) return 0;
-    const uint32_t rows = pair ? std::max(qlen, qlen2) : qlen;
+    const uint32_t rows = qlen;
     if (rows == 0 || pl.tiles.empty() || pl.max_len == 0) {
         memset(scores_out, 0, sizeof(int32_t) * nl);
-        if (pair) memset(scores_out2, 0, sizeof(int32_t) * nl);
         return 0;
     }
     uint32_t present = 0;
@@ -298,15 +289,26 @@ static int emu_search(const uint8_t *codes, const uint64_t *offsets, uint32_t n,
         for (uint32_t i = 0; i < (t.width >> 2) * P; ++i)
             out[i] = swb_pack_word(t, i / P, i % P, codes, pl.seq_off.data(), pl.seq_len.data(), nl);
     }
-    int max_s = 0;
-    for (int i = 0; i < SWB_ALPHA * SWB_ALPHA; ++i) max_s = std::max<int>(max_s, mat32[i]);
+    int max_s = 0, min_s = 0;
+    for (int i = 0; i < SWB_ALPHA * SWB_ALPHA; ++i) {
+        max_s = std::max<int>(max_s, mat32[i]);
+        min_s = std::min<int>(min_s, mat32[i]);
+    }
     if (!chunk_rows) chunk_rows = 7168;
-    if (!chunk_rows_pair) chunk_rows_pair = 1536;
+    if (!split_k) split_k = 8;
+    const int eng_shift = affine ? 0 : swb_rebase_shift(max_s, min_s, gap, 16u * 32u);
+    const bool r16 = !affine && eng_shift > 0 && !exact_i32;
+    if (r16 && rebase_shift >= 6) {
+        if (rebase_shift > eng_shift) return -3;  // a larger block than the scheme allows would not be exact
+    } else {
+        rebase_shift = eng_shift;
+    }
 
-    std::vector<int32_t> sorted(2 * (size_t)((nl + 1) / 2), 0), sorted2(2 * (size_t)((nl + 1) / 2), 0);
+    std::vector<int32_t> sorted(2 * (size_t)((nl + 1) / 2), 0);
     std::vector<uint8_t> flags(pl.tiles.size(), 0);
     std::vector<uint32_t> bnd16(2 * pl.bnd_elems + 8);
     std::vector<uint64_t> bnd32((affine ? 2 : 1) * pl.bnd_elems + 4);
+    std::vector<uint64_t> blog(swb_blog_elems(pl.bnd_elems, (uint32_t)pl.tiles.size()), 0x7f7f7f7f7f7f7f7full);
     uint32_t recount = 0;
     SwbScoreParams p;
     memset(&p, 0, sizeof p);
@@ -318,116 +320,73 @@ static int emu_search(const uint8_t *codes, const uint64_t *offsets, uint32_t n,
     p.gap_open = gap;
     p.gap_extend = gap_extend;
     p.ovf_thr = ovf_thr_override >= 0 ? ovf_thr_override : 32767 - max_s;
+    p.rebase_shift = (uint32_t)rebase_shift;
+    p.blog = blog.data();
+    p.scores = sorted.data();
 
-    auto build_prof8 = [&](const uint8_t *qq, uint32_t ql, uint32_t prows, uint32_t stride, std::vector<uint8_t> &out) {
-        out.assign((size_t)stride * SWB_ALPHA, 0);
-        for (uint32_t r = 0; r < prows; ++r) {
-            const uint32_t qc = r < ql ? (qq[r] & 31u) : (uint32_t)SWB_PAD;
-            for (uint32_t code = 0; code < SWB_ALPHA; ++code)
-                out[(size_t)code * stride + r] = (uint8_t)(int8_t)(mat32[qc * SWB_ALPHA + code] + gap);
+    // the split set and its direct part, as enqueue_job
+    uint32_t xl[SWB_MAX_LOGG + 1] = {}, direct[SWB_MAX_LOGG + 1] = {}, rest[SWB_MAX_LOGG + 1] = {};
+    uint32_t n_direct = 0, n_rest = 0;
+    const bool split = !affine;
+    if (split)
+        for (int l = 1; l <= SWB_MAX_LOGG; ++l) {
+            xl[l] = pl.xl_by_logg[l];
+            if (r16 && direct_len && rows >= direct_len && !force_exact)
+                while (direct[l] < xl[l] && pl.tiles[pl.tile_start_by_logg[l] + direct[l]].width >= direct_len) ++direct[l];
+            rest[l] = xl[l] - direct[l];
+            n_direct += direct[l];
+            n_rest += rest[l];
         }
-    };
+    SwbQueryPlan qp0, qp1;
+    swb_plan_query(rows, K, 32, present, chunk_rows, qp0);
+    swb_plan_query(rows, K, affine ? 8 : 16, present, chunk_rows, qp1);
+    uint32_t prof_rows = std::max(qp0.prof_rows, qp1.prof_rows);
+    if (split) prof_rows = std::max(prof_rows, swb_roundup(rows, 16u << SWB_MAX_LOGG));
+    const uint32_t stride = swb_roundup(std::max(prof_rows, 16u), 16);
+    std::vector<uint8_t> prof((size_t)stride * SWB_ALPHA, 0);
+    for (uint32_t r = 0; r < prof_rows; ++r) {
+        const uint32_t qc = r < qlen ? (q[r] & 31u) : (uint32_t)SWB_PAD;
+        for (uint32_t code = 0; code < SWB_ALPHA; ++code)
+            prof[(size_t)code * stride + r] = (uint8_t)(int8_t)(mat32[qc * SWB_ALPHA + code] + gap);
+    }
+    p.profile = reinterpret_cast<const int8_t *>(prof.data());
+    p.prof_stride = stride;
 
-    // pass 0
-    if (!force_i32) {
-        SwbQueryPlan qp0;
-        std::vector<SwbLaunchGroup> g0;
-        const bool split = !pair && !affine;
-        const int split_l = split ? swb_plan_split_max_logg(pl) : -1;
-        const int sk0 = split_l > 0 && split_fill ? swb_plan_split_k(pl, std::min(rows, chunk_rows), 32, split_fill) : 8;
-        swb_plan_query(rows, K, 32, present, pair ? chunk_rows_pair : chunk_rows, qp0,
-                       sk0 > 8 ? (uint32_t)sk0 << split_l : 0u);
-        swb_plan_launch_groups(pl, qp0, true, split, g0, sk0);
-        std::vector<uint8_t> prof;
-        const uint32_t stride = swb_roundup(qp0.prof_rows, 16);
-        if (pair) {
-            prof.assign((size_t)stride * SWB_ALPHA * 4, 0);
-            uint32_t *pw = reinterpret_cast<uint32_t *>(prof.data());
-            for (uint32_t r = 0; r < qp0.prof_rows; ++r) {
-                const uint32_t ca = r < qlen ? (q[r] & 31u) : (uint32_t)SWB_PAD;
-                const uint32_t cb = r < qlen2 ? (q2[r] & 31u) : (uint32_t)SWB_PAD;
-                for (uint32_t code = 0; code < SWB_ALPHA; ++code) {
-                    const uint32_t lo = (uint32_t)(mat32[ca * SWB_ALPHA + code] + gap) & 0xffffu;
-                    const uint32_t hi = (uint32_t)(mat32[cb * SWB_ALPHA + code] + gap) & 0xffffu;
-                    pw[(size_t)code * stride + r] = lo | (hi << 16);
-                }
-            }
-        } else {
-            build_prof8(q, qlen, qp0.prof_rows, stride, prof);
-        }
-        p.profile = reinterpret_cast<const int8_t *>(prof.data());
-        p.prof_stride = stride;
-        p.scores = sorted.data();
-        p.scores2 = sorted2.data();
+    if (!force_exact) {
+        // pass 0: s16 over everything but the direct tiles, V16R over those
+        std::vector<SwbLaunchGroup> g0, gd;
+        SwbLaunchGroup g;
+        if (n_rest && swb_plan_split_group(pl, direct, rest, split_k, g)) g0.push_back(g);
+        swb_plan_bulk_groups(pl, qp0, true, split ? xl : nullptr, 0x3fu, g0);
+        if (n_direct && swb_plan_split_group(pl, nullptr, direct, split_k, g)) gd.push_back(g);
         p.bnd = bnd16.data();
         p.only_flagged = 0;
-        run_pass(p, affine ? 3 : (pair ? 2 : 0), qp0, g0, prof, stride);
+        run_pass(p, affine ? 3 : 0, qp0, g0, prof, stride);
+        p.recount = nullptr;
+        run_pass(p, 2, qp0, gd, prof, stride);
+        p.recount = &recount;
     }
-    // int32 passes, one per query
-    const uint8_t *qs[2] = {q, q2};
-    const uint32_t qls[2] = {qlen, pair ? qlen2 : 0u};
-    for (int k = 0; k < (pair ? 2 : 1); ++k) {
-        if (qls[k] == 0) continue;
-        SwbQueryPlan qp1;
+    {
+        // exact pass: over flagged tiles, or over every tile
         std::vector<SwbLaunchGroup> g1;
-        const bool split = !pair && !affine;
-        const int split_l = split ? swb_plan_split_max_logg(pl) : -1;
-        const int sk1 = split_l > 0 && split_fill ? swb_plan_split_k(pl, std::min(qls[k], chunk_rows), 16, split_fill) : 8;
-        swb_plan_query(qls[k], K, affine ? 8 : 16, present, chunk_rows, qp1, sk1 > 8 ? (uint32_t)sk1 << split_l : 0u);
-        swb_plan_launch_groups(pl, qp1, true, split, g1, sk1);
-        if (!g1.empty() && g1[0].split) {  // swb_clear_flagged_kernel
-            int32_t *sc = k ? sorted2.data() : sorted.data();
+        SwbLaunchGroup g;
+        uint32_t none[SWB_MAX_LOGG + 1] = {};
+        const uint32_t *first = force_exact ? none : direct;
+        const uint32_t *cnt = force_exact ? xl : rest;
+        uint32_t any = 0;
+        for (int l = 1; l <= SWB_MAX_LOGG; ++l) any += cnt[l];
+        if (split && any && swb_plan_split_group(pl, first, cnt, r16 ? split_k : 8, g)) g1.push_back(g);
+        swb_plan_bulk_groups(pl, qp1, true, split ? xl : nullptr, 0x3fu, g1);
+        if (!g1.empty() && g1[0].split)  // swb_clear_flagged_kernel
             for (size_t ti = 0; ti < pl.tiles.size(); ++ti)
-                if (flags[ti])
+                if (flags[ti] || force_exact)
                     for (uint32_t sl = 0; sl < pl.tiles[ti].npairs; ++sl)
-                        sc[2 * ((size_t)pl.tiles[ti].first_pair + sl)] = sc[2 * ((size_t)pl.tiles[ti].first_pair + sl) + 1] = 0;
-        }
-        std::vector<uint8_t> prof;
-        const uint32_t stride = swb_roundup(qp1.prof_rows, 16);
-        build_prof8(qs[k], qls[k], qp1.prof_rows, stride, prof);
-        p.profile = reinterpret_cast<const int8_t *>(prof.data());
-        p.prof_stride = stride;
-        p.scores = k ? sorted2.data() : sorted.data();
-        p.scores2 = nullptr;
-        p.bnd = bnd32.data();
-        p.only_flagged = force_i32 ? 0u : 1u;
-        run_pass(p, affine ? 4 : 1, qp1, g1, prof, stride);
+                        sorted[2 * ((size_t)pl.tiles[ti].first_pair + sl)] = sorted[2 * ((size_t)pl.tiles[ti].first_pair + sl) + 1] = 0;
+        p.bnd = r16 ? (void *)bnd16.data() : (void *)bnd32.data();
+        p.only_flagged = force_exact ? 0u : 1u;
+        run_pass(p, affine ? 4 : (r16 ? 2 : 1), qp1, g1, prof, stride);
     }
-    for (uint32_t s = 0; s < nl; ++s) {
-        scores_out[pl.out_pos[s]] = sorted[s];
-        if (pair) scores_out2[pl.out_pos[s]] = sorted2[s];
-    }
+    for (uint32_t s = 0; s < nl; ++s) scores_out[pl.out_pos[s]] = sorted[s];
     if (recomputed_tiles) *recomputed_tiles = recount;
     return 0;
-}
-
-extern "C" int swbemu_search(const uint8_t *codes, const uint64_t *offsets, uint32_t n, uint32_t shard,
-                             uint32_t nshards, uint32_t group_len, const int8_t *mat32, int gap, const uint8_t *q,
-                             uint32_t qlen, int K, int force_i32, uint32_t chunk_rows, int ovf_thr_override,
-                             uint32_t xl_len, int32_t *scores_out, uint32_t *recomputed_tiles, const uint8_t *q2,
-                             uint32_t qlen2, int32_t *scores_out2, uint32_t chunk_rows_pair)
-{
-    return emu_search(codes, offsets, n, shard, nshards, group_len, mat32, gap, gap, q, qlen, K, force_i32, chunk_rows,
-                      ovf_thr_override, xl_len, scores_out, recomputed_tiles, q2, qlen2, scores_out2, chunk_rows_pair, 0);
-}
-
-extern "C" int swbemu_search_affine(const uint8_t *codes, const uint64_t *offsets, uint32_t n, uint32_t shard,
-                                    uint32_t nshards, uint32_t group_len, const int8_t *mat32, int gap_open,
-                                    int gap_extend, const uint8_t *q, uint32_t qlen, int K, int force_i32,
-                                    uint32_t chunk_rows, int ovf_thr_override, int32_t *scores_out,
-                                    uint32_t *recomputed_tiles)
-{
-    return emu_search(codes, offsets, n, shard, nshards, group_len, mat32, gap_open, gap_extend, q, qlen, K, force_i32,
-                      chunk_rows, ovf_thr_override, 0, scores_out, recomputed_tiles, nullptr, 0, nullptr, 0, 0);
-}
-
-// split_fill: work items a split launch should have before its K goes up from 8 to 16 / 32 (the engine passes the
-// GPU's warp slots); exercises the block-staged split kernels
-extern "C" int swbemu_search_split(const uint8_t *codes, const uint64_t *offsets, uint32_t n, uint32_t group_len,
-                                   const int8_t *mat32, int gap, const uint8_t *q, uint32_t qlen, int force_i32,
-                                   uint32_t chunk_rows, int ovf_thr_override, uint32_t xl_len, uint32_t split_fill,
-                                   int32_t *scores_out, uint32_t *recomputed_tiles)
-{
-    return emu_search(codes, offsets, n, 0, 1, group_len, mat32, gap, gap, q, qlen, 0, force_i32, chunk_rows,
-                      ovf_thr_override, xl_len, scores_out, recomputed_tiles, nullptr, 0, nullptr, 0, split_fill);
 }

@@ -93,3 +93,56 @@ def test_plan_rejects_bad_input(swb):
         swb.plan_describe(bad)
     info = swb.plan_describe(np.array([0], dtype=np.uint64))
     assert info.n_local == 0 and info.tiles == 0
+
+
+def test_group_refuses_without_gpu(swb):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(swb.SwbError) as ei:
+        swb.EngineGroup()
+    assert "no CPU fallback" in str(ei.value)
+
+
+def test_layout_rules(swb):
+    """the P x R layout of the engine group / of bench.py's ranks: P = the largest divisor of the device count that
+    keeps min_part sequences per part; query groups by longest-processing-time first"""
+    assert swb.layout_parts(570065, 1) == 1
+    assert swb.layout_parts(570065, 2) == 2
+    assert swb.layout_parts(570065, 4) == 2
+    assert swb.layout_parts(570065, 8) == 2
+    assert swb.layout_parts(5700650, 8) == 8
+    assert swb.layout_parts(100, 8) == 1
+    assert swb.layout_parts(900, 6, 300) == 3
+    # the 20 reference queries over 4 groups: within half a percent of equal
+    lens = [144, 189, 222, 375, 464, 567, 657, 729, 850, 1000, 1500, 2005, 2504, 3005, 3564, 4061, 4548, 4743, 5147, 5478]
+    rng = np.random.default_rng(1)
+    rng.shuffle(lens)
+    offs = _offsets(lens)
+    for groups in (1, 2, 4):
+        g = swb.layout_query_groups(offs, groups)
+        load = np.bincount(g, weights=np.array(lens, dtype=float), minlength=groups)
+        assert len(g) == 20 and g.max() < groups
+        assert load.max() / (sum(lens) / groups) < 1.005, (groups, load)
+    # 1,000 queries of the configs[4] length law over 8 groups
+    qlens = np.clip(np.round(np.random.default_rng(1785).lognormal(5.58, 0.75, 1000)), 30, 5478).astype(np.int64)
+    g = swb.layout_query_groups(_offsets(qlens), 8)
+    load = np.bincount(g, weights=qlens.astype(float), minlength=8)
+    assert load.max() / load.mean() < 1.001
+    # more groups than queries: the extra groups stay empty, nothing is lost
+    g = swb.layout_query_groups(_offsets([5, 9]), 4)
+    assert sorted(g.tolist()) == [0, 1] or len(set(g.tolist())) == 2
+    assert len(swb.layout_query_groups(_offsets([]), 3)) == 0
+
+
+def test_rebase_block_of_the_reference_scheme():
+    """V16R's exactness window for BLOSUM50 / gap 2 (swb_warp.cuh): neighbouring cells differ by at most
+    maxS + g = 17, so a pass of 512 rows over a block of 1,024 columns spans (512 + 1024 + 2) * 17 = 26,146 < 31,000
+    -- the rule swb_rebase_shift implements (restated here; the emulation tests run the policy itself)"""
+    max_s, min_s, gap, rows = 15, -5, 2, 512
+    step = max_s + gap
+    cols = (31000 - (-min_s) - gap - max_s) // step - rows - 2
+    shift = 0
+    while (2 << shift) <= cols:
+        shift += 1
+    assert shift == 10 and (rows + (1 << shift) + 2) * step + 5 + 2 + 15 <= 31000

@@ -20,44 +20,9 @@ _i32p = ctypes.POINTER(ctypes.c_int32)
 
 @pytest.fixture(scope="module")
 def emu():
-    so = os.path.join(ROOT, PKG, "lib", "libswbemu.so")
-    if not os.path.exists(so):
-        subprocess.run(["make", "-C", os.path.join(ROOT, PKG), "emu"], check=True, capture_output=True)
-    L = ctypes.CDLL(so)
-    L.swbemu_search.restype = ctypes.c_int
-    L.swbemu_search.argtypes = [_u8p, _u64p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, _i8p,
-                                ctypes.c_int, _u8p, ctypes.c_uint32, ctypes.c_int, ctypes.c_int, ctypes.c_uint32,
-                                ctypes.c_int, ctypes.c_uint32, _i32p, ctypes.POINTER(ctypes.c_uint32), _u8p,
-                                ctypes.c_uint32, _i32p, ctypes.c_uint32]
-
-    def search(codes, offs, m, q, K=32, group_len=384, force_i32=0, chunk_rows=0, thr=-1, gap=2, shard=0, nshards=1,
-               n_out=None, xl_len=8192, q2=None, chunk_rows_pair=0):
-        """q2 given: a query-pair job; returns ((scores, scores2), recomputed_tiles)"""
-        codes = np.ascontiguousarray(codes, dtype=np.uint8)
-        if len(codes) == 0:
-            codes = np.zeros(1, dtype=np.uint8)
-        offs = np.ascontiguousarray(offs, dtype=np.uint64)
-        q = np.ascontiguousarray(q, dtype=np.uint8)
-        m = np.ascontiguousarray(m, dtype=np.int8)
-        n = len(offs) - 1
-        out = np.full(n if n_out is None else n_out, -7, dtype=np.int32)
-        out2 = np.full(len(out), -7, dtype=np.int32)
-        rc = ctypes.c_uint32()
-        if q2 is not None:
-            q2 = np.ascontiguousarray(q2, dtype=np.uint8)
-            if len(q2) == 0:
-                q2 = np.zeros(1, dtype=np.uint8)[:0]
-        q2p = None if q2 is None else (q2.ctypes.data_as(_u8p) if len(q2) else ctypes.cast(out2.ctypes.data, _u8p))
-        r = L.swbemu_search(codes.ctypes.data_as(_u8p), offs.ctypes.data_as(_u64p), n, shard, nshards, group_len,
-                            m.ctypes.data_as(_i8p), gap, q.ctypes.data_as(_u8p) if len(q) else None, len(q), K,
-                            force_i32, chunk_rows, thr, xl_len, out.ctypes.data_as(_i32p), ctypes.byref(rc), q2p,
-                            0 if q2 is None else len(q2), out2.ctypes.data_as(_i32p), chunk_rows_pair)
-        assert r == 0
-        if q2 is not None:
-            return (out, out2), rc.value
-        return out, rc.value
-
-    return search
+    import emu_lib
+    emu_lib.load()
+    return emu_lib.search
 
 
 @pytest.mark.parametrize("K,group_len", [(0, 384), (8, 2000), (16, 384), (32, 384), (32, 64), (16, 16), (0, 16), (0, 64)])
@@ -164,54 +129,12 @@ def test_pipelined_passes_of_very_long_tiles(emu, oracle):
     assert np.array_equal(got, want)
 
 
-def test_query_pair_jobs(emu, oracle, subset, queries):
-    """V16Q: two queries in the halves of the s16x2 lanes against one DB sequence per lane; the tile is two work
-    items (first / second sequence of every pair). Unequal lengths, chunked profile, overflow of one query only."""
-    m = oracle.matrix("blosum50")
-    codes, offs = subset["codes"], subset["offsets"]
-    for na, nb, kw in (("P02232", "P05013", dict(K=0, group_len=384)), ("P01008", "P02232", dict(K=0, group_len=64)),
-                       ("P14942", "P14942", dict(K=16, group_len=16)),
-                       ("P27895", "P07327", dict(K=0, group_len=128, chunk_rows_pair=512))):
-        qa, qb = oracle.encode(queries[na]), oracle.encode(queries[nb])
-        (ga, gb), _ = emu(codes, offs, m, qa, q2=qb, **kw)
-        assert np.array_equal(ga, oracle.scan(qa, codes, offs, m)), (na, nb)
-        assert np.array_equal(gb, oracle.scan(qb, codes, offs, m)), (na, nb)
-    rng = np.random.default_rng(8)
-    w = np.full(2300, 17, dtype=np.uint8)
-    enc = [w, rng.integers(0, 20, 300).astype(np.uint8), w[:2200].copy(), rng.integers(0, 20, 50).astype(np.uint8),
-           np.zeros(0, np.uint8)]
-    c2, o2 = pack_db(enc)
-    qb = rng.integers(0, 20, 700).astype(np.uint8)
-    (ga, gb), rc = emu(c2, o2, m, w, q2=qb, K=0, group_len=384)
-    assert np.array_equal(ga, oracle.scan(w, c2, o2, m)) and ga[0] == 34500 and rc >= 1
-    assert np.array_equal(gb, oracle.scan(qb, c2, o2, m))
-    (ga, gb), _ = emu(c2, o2, m, qb[:9], q2=np.zeros(0, np.uint8), K=0)
-    assert np.array_equal(ga, oracle.scan(qb[:9], c2, o2, m)) and not gb.any()
-
-
 # ---- affine gaps (SURVEY 8f: "define affine penalty ?", SWSolver.cu:8) -------------------------------------------
 @pytest.fixture(scope="module")
 def emu_affine(emu):
-    L = ctypes.CDLL(os.path.join(ROOT, PKG, "lib", "libswbemu.so"))
-    L.swbemu_search_affine.restype = ctypes.c_int
-    L.swbemu_search_affine.argtypes = [_u8p, _u64p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32,
-                                       _i8p, ctypes.c_int, ctypes.c_int, _u8p, ctypes.c_uint32, ctypes.c_int,
-                                       ctypes.c_int, ctypes.c_uint32, ctypes.c_int, _i32p,
-                                       ctypes.POINTER(ctypes.c_uint32)]
-
     def search(codes, offs, m, q, go, ge, K=0, group_len=384, force_i32=0, chunk_rows=0, thr=-1):
-        codes = np.ascontiguousarray(codes, dtype=np.uint8)
-        offs = np.ascontiguousarray(offs, dtype=np.uint64)
-        q = np.ascontiguousarray(q, dtype=np.uint8)
-        m = np.ascontiguousarray(m, dtype=np.int8)
-        n = len(offs) - 1
-        out = np.full(n, -7, dtype=np.int32)
-        rc = ctypes.c_uint32()
-        r = L.swbemu_search_affine(codes.ctypes.data_as(_u8p), offs.ctypes.data_as(_u64p), n, 0, 1, group_len,
-                                   m.ctypes.data_as(_i8p), go, ge, q.ctypes.data_as(_u8p), len(q), K, force_i32,
-                                   chunk_rows, thr, out.ctypes.data_as(_i32p), ctypes.byref(rc))
-        assert r == 0
-        return out, rc.value
+        return emu(codes, offs, m, q, K=K, group_len=group_len, force_i32=force_i32, chunk_rows=chunk_rows, thr=thr,
+                   gap=go, gap_extend=ge, xl_len=0)
 
     return search
 
@@ -277,25 +200,9 @@ def test_affine_edges(emu_affine, oracle):
                 assert np.array_equal(got, want), (ql, go, ge, K, gl)
 
 
-def test_pipelined_passes_with_full_blocks(emu, oracle):
-    """split launches with enough work items run K = 16 / 32 strips over the block-staged chunk (the engine raises K
-    while the items still fill the GPU's warp slots; here split_fill = 1 always picks the largest K that applies)"""
-    L = ctypes.CDLL(os.path.join(ROOT, PKG, "lib", "libswbemu.so"))
-    L.swbemu_search_split.restype = ctypes.c_int
-    L.swbemu_search_split.argtypes = [_u8p, _u64p, ctypes.c_uint32, ctypes.c_uint32, _i8p, ctypes.c_int, _u8p,
-                                      ctypes.c_uint32, ctypes.c_int, ctypes.c_uint32, ctypes.c_int, ctypes.c_uint32,
-                                      ctypes.c_uint32, _i32p, ctypes.POINTER(ctypes.c_uint32)]
-
-    def run(codes, offs, m, q, group_len, xl_len, fill, chunk_rows=0, thr=-1, force_i32=0):
-        out = np.full(len(offs) - 1, -7, dtype=np.int32)
-        rc = ctypes.c_uint32()
-        r = L.swbemu_search_split(codes.ctypes.data_as(_u8p), offs.ctypes.data_as(_u64p), len(offs) - 1, group_len,
-                                  np.ascontiguousarray(m, dtype=np.int8).ctypes.data_as(_i8p), 2,
-                                  q.ctypes.data_as(_u8p), len(q), force_i32, chunk_rows, thr, xl_len, fill,
-                                  out.ctypes.data_as(_i32p), ctypes.byref(rc))
-        assert r == 0
-        return out, rc.value
-
+def test_pipelined_passes_with_16_row_strips(emu, oracle):
+    """split groups with 16 rows per lane (the engine picks them while the items still fill the GPU): s16 pass, the
+    exact recompute in both forms (rebased s16 and int32), several query chunks"""
     rng = np.random.default_rng(23)
     m = oracle.matrix("blosum50")
     lens = [1500, 1333, 900, 801, 640, 300, 280, 120, 64, 30, 7, 1200]
@@ -303,42 +210,80 @@ def test_pipelined_passes_with_full_blocks(emu, oracle):
     for ql in (100, 700, 1100):
         q = rng.integers(0, 20, ql).astype(np.uint8)
         want = oracle.scan(q, codes, offs, m)
-        for gl, xl, fill in ((16, 100, 1), (16, 600, 40), (32, 1000, 1)):
-            got, _ = run(codes, offs, m, q, gl, xl, fill)
-            assert np.array_equal(got, want), (ql, gl, xl, fill)
+        for gl, xl in ((16, 100), (16, 600), (32, 1000)):
+            got, _ = emu(codes, offs, m, q, K=0, group_len=gl, xl_len=xl, split_k=16)
+            assert np.array_equal(got, want), (ql, gl, xl)
     q = rng.integers(0, 20, 2300).astype(np.uint8)
     want = oracle.scan(q, codes, offs, m)
-    got, rc = run(codes, offs, m, q, 16, 500, 1, chunk_rows=1024, thr=40)  # chunks + int32 recompute (K = 16 split)
-    assert np.array_equal(got, want) and rc >= 3
-    got, _ = run(codes, offs, m, q, 16, 300, 1, force_i32=1)
-    assert np.array_equal(got, want)
+    for exact_i32 in (0, 1):
+        got, rc = emu(codes, offs, m, q, K=0, group_len=16, xl_len=500, chunk_rows=1024, thr=40, split_k=16,
+                      exact_i32=exact_i32, rebase_shift=6)
+        assert np.array_equal(got, want) and rc >= 3, exact_i32
+        got, _ = emu(codes, offs, m, q, K=0, group_len=16, xl_len=300, force_i32=1, split_k=16, exact_i32=exact_i32,
+                     rebase_shift=7)
+        assert np.array_equal(got, want), exact_i32
 
 
-def test_pipelined_passes_every_lane_group_class(oracle):
+def test_pipelined_passes_every_lane_group_class(emu, oracle):
     """a split set that reaches down to 2 lanes per pair: tiles with several pairs per warp (slots) publish one
     progress value for all of them, items map to (tile, pass) through the per-class tables"""
-    L = ctypes.CDLL(os.path.join(ROOT, PKG, "lib", "libswbemu.so"))
-    L.swbemu_search_split.restype = ctypes.c_int
-    L.swbemu_search_split.argtypes = [_u8p, _u64p, ctypes.c_uint32, ctypes.c_uint32, _i8p, ctypes.c_int, _u8p,
-                                      ctypes.c_uint32, ctypes.c_int, ctypes.c_uint32, ctypes.c_int, ctypes.c_uint32,
-                                      ctypes.c_uint32, _i32p, ctypes.POINTER(ctypes.c_uint32)]
     m = oracle.matrix("blosum50")
     rng = np.random.default_rng(99)
     lens = [17, 18, 20, 25, 31, 32, 33, 40, 60, 64, 65, 100, 128, 129, 200, 256, 257, 300, 500, 700, 5, 9, 12, 16]
     rng.shuffle(lens)
     codes, offs = pack_db(random_db(rng, lens, alphabet=20))
-    mm = np.ascontiguousarray(m, dtype=np.int8)
     for ql in (1, 9, 33, 257):
         q = rng.integers(0, 20, ql).astype(np.uint8)
         want = oracle.scan(q, codes, offs, m)
         for gl, xl in ((16, 16), (16, 40), (8, 8), (32, 32)):
-            for thr in (-1, 30):  # 30: most tiles also go through the pipelined int32 recompute
-                out = np.full(len(offs) - 1, -7, dtype=np.int32)
-                rc = ctypes.c_uint32()
-                r = L.swbemu_search_split(codes.ctypes.data_as(_u8p), offs.ctypes.data_as(_u64p), len(offs) - 1, gl,
-                                          mm.ctypes.data_as(_i8p), 2, q.ctypes.data_as(_u8p), len(q), 0, 0, thr, xl, 0,
-                                          out.ctypes.data_as(_i32p), ctypes.byref(rc))
-                assert r == 0 and np.array_equal(out, want), (ql, gl, xl, thr)
+            for thr in (-1, 30):  # 30: most tiles also go through the pipelined exact recompute
+                for exact_i32 in (0, 1):
+                    got, _ = emu(codes, offs, m, q, K=0, group_len=gl, xl_len=xl, thr=thr, exact_i32=exact_i32,
+                                 rebase_shift=6)
+                    assert np.array_equal(got, want), (ql, gl, xl, thr, exact_i32)
+
+
+def test_rebased_s16_is_exact_far_beyond_the_s16_range(emu, oracle):
+    """V16R (s16x2 relative to a base that follows the columns): the exact pass over every tile and the "direct" path
+    for long-against-long tiles, with true scores of 150,000 (ten thousand W-W matches at 15), several blocks per
+    pass, several passes per tile, pairs of very different length, one lane per pair up to 32 lanes per pair"""
+    m = oracle.matrix("blosum50")
+    rng = np.random.default_rng(5)
+    w = np.full(10000, 17, dtype=np.uint8)  # W: 15 per match
+    noisy = w.copy()
+    noisy[rng.choice(len(w), 600, replace=False)] = rng.integers(0, 20, 600)
+    enc = [w, noisy, w[:9000].copy(), rng.integers(0, 20, 4000).astype(np.uint8), w[:700].copy(),
+           rng.integers(0, 20, 90).astype(np.uint8), np.zeros(0, np.uint8)]
+    codes, offs = pack_db(enc)
+    want = oracle.scan(w, codes, offs, m)
+    assert want[0] == 150000 and want[2] == 135000 and want[1] > 100000
+    # direct: the long tiles never see the plain s16 pass (nothing is flagged there); the short ones go the normal way
+    got, rc = emu(codes, offs, m, w, K=0, group_len=128, xl_len=2000, split_k=16, direct_len=3000)
+    assert np.array_equal(got, want)
+    # flagged -> rebased recompute, pipelined (split_k 8) and not (xl_len 0), small blocks
+    got, rc = emu(codes, offs, m, w[:4000], K=0, group_len=128, xl_len=2000, split_k=8, rebase_shift=7)
+    assert np.array_equal(got, oracle.scan(w[:4000], codes, offs, m)) and rc >= 2
+    got, rc = emu(codes, offs, m, w[:4000], K=0, group_len=512, xl_len=0, rebase_shift=6)
+    assert np.array_equal(got, oracle.scan(w[:4000], codes, offs, m)) and rc >= 2
+    # one lane per pair through the rebased policy (its G = 1 case): group_len above every sequence
+    q = w[:3000]
+    got, rc = emu(codes[:int(offs[5])], offs[:6], m, q, K=0, group_len=16384, xl_len=0, force_i32=1, rebase_shift=8)
+    assert np.array_equal(got, oracle.scan(q, codes[:int(offs[5])], offs[:6], m))
+
+
+def test_rebased_s16_random_and_ident3(emu, oracle):
+    """V16R as the only pass (force) over random databases, both scoring presets, every K / group size mix"""
+    rng = np.random.default_rng(77)
+    for preset, alphabet in (("blosum50", 20), ("ident3", 4)):
+        m = oracle.matrix(preset)
+        lens = [900, 640, 333, 300, 280, 120, 64, 30, 7, 1, 0, 450]
+        codes, offs = pack_db(random_db(rng, lens, alphabet=alphabet))
+        for ql in (1, 40, 333, 1030):
+            q = rng.integers(0, alphabet, ql).astype(np.uint8)
+            want = oracle.scan(q, codes, offs, m)
+            for K, gl, xl, shift in ((0, 64, 0, 6), (8, 16, 200, 6), (16, 32, 64, 7), (0, 384, 0, 6)):
+                got, _ = emu(codes, offs, m, q, K=K, group_len=gl, xl_len=xl, force_i32=1, rebase_shift=shift)
+                assert np.array_equal(got, want), (preset, ql, K, gl, xl, shift)
 
 
 def test_randomized_configurations(emu, oracle):
@@ -356,6 +301,10 @@ def test_randomized_configurations(emu, oracle):
         K = int(rng.choice([0, 8, 16, 32]))
         xl = int(rng.choice([0, 16, 64, 256, 8192]))
         thr = int(rng.choice([-1, -1, 10, 40, 200]))
+        sk = int(rng.choice([8, 16]))
+        ex = int(rng.choice([0, 0, 1]))
+        dl = int(rng.choice([0, 0, 50, 300]))
         want = oracle.scan(q, codes, offs, m)
-        got, _ = emu(codes, offs, m, q, K=K, group_len=gl, xl_len=xl, thr=thr)
-        assert np.array_equal(got, want), (it, nseq, top, len(q), gl, K, xl, thr)
+        got, _ = emu(codes, offs, m, q, K=K, group_len=gl, xl_len=xl, thr=thr, split_k=sk, exact_i32=ex, direct_len=dl,
+                     rebase_shift=6)
+        assert np.array_equal(got, want), (it, nseq, top, len(q), gl, K, xl, thr, sk, ex, dl)

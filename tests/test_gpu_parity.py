@@ -265,8 +265,8 @@ def test_cli_and_reference_style_caller(swb, tmp_path):
 
 def test_config4_titin_scale_queries_and_targets(swb, oracle):
     """BASELINE configs[3]: queries of 7,000 / 20,000 / 35,213 residues against long targets, a 10 %-mutated copy and
-    the query itself (self score ~5.5 x L >> 32767: the s16 pass must flag it, the int32 pass must fix it). The
-    35,213-row query runs as five shared-memory chunks; 32-lane wavefront tiles carry the targets."""
+    the query itself (self score ~5.5 x L >> 32767: either the s16 pass flags it and the exact pass re-scores it, or
+    the tile goes to the rebased s16 policy at once). 16- and 32-lane wavefront tiles carry the targets."""
     rng = np.random.default_rng(1784)
     m = oracle.matrix("blosum50")
     targets = random_db(rng, np.round(np.exp(rng.uniform(np.log(5000), np.log(35213), 20))), alphabet=20)
@@ -285,7 +285,10 @@ def test_config4_titin_scale_queries_and_targets(swb, oracle):
             assert np.array_equal(got, want), qlen
             assert got[len(targets) + 1] > 5 * qlen and 5 * qlen > 32767  # the self hit
             st = e.stats()
-            assert st["recomputed_tiles"] >= 1 and st["tiles_by_group"][5] >= 1
+            assert st["tiles_by_group"][5] >= 1
+            # below direct_len (10,000 rows) the self hit is flagged by the s16 pass and re-scored; above it the long
+            # tiles are scored by the rebased policy at once and nothing may be left to flag
+            assert st["recomputed_tiles"] >= 1 or qlen >= 10000
     finally:
         e.close()
 
@@ -381,29 +384,195 @@ def test_pipelined_passes_option(swb, oracle):
         e.close()
 
 
-def test_query_pair_packing_option(swb, oracle, subset, queries):
-    """option pair_queries=1: a batch runs two queries per job in the halves of the s16x2 lanes (policy V16Q), one
-    database sequence per lane; odd batch sizes, very different lengths, chunked pair profile, overflow of one query"""
-    m = oracle.matrix("blosum50")
-    e = swb.Engine(0, pair_queries=1)
+def _host_topk(scores, ids, k):
+    """k best of a score vector: score descending, database id ascending (numpy restatement for the tests)"""
+    order = np.lexsort((ids, -scores.astype(np.int64)))[:k]
+    return ids[order], scores[order]
+
+
+def test_device_topk_equals_host_selection(swb, oracle):
+    """swb_search_batch_topk: the hit list selected on the device (radix select + sort in one block) must equal the
+    host selection over the full vectors -- many equal scores (ties break by ascending database id), k from 1 to
+    1024 and beyond the shard size, sharded ids, an empty query"""
+    rng = np.random.default_rng(31)
+    enc = random_db(rng, np.clip(np.round(rng.lognormal(4.2, 0.9, 5000)), 1, 3000), alphabet=6)  # small alphabet: ties
+    codes, offs = pack_db(enc)
+    qs = [rng.integers(0, 6, l).astype(np.uint8) for l in (5, 40, 333, 1200)] + [np.zeros(0, np.uint8)]
+    qcodes, qoffs = swb.pack_sequences(qs)
+    e = swb.Engine(0)
     try:
-        e.db_load(subset["codes"], subset["offsets"])
-        names = sorted(queries)[:7]
-        got = e.search_batch([swb.encode(queries[n]) for n in names])
-        for i, n in enumerate(names):
-            assert np.array_equal(got[i], oracle.scan(oracle.encode(queries[n]), subset["codes"], subset["offsets"], m)), n
-        rng = np.random.default_rng(4)
-        w = np.full(2400, 17, dtype=np.uint8)
-        enc = random_db(rng, rng.integers(1, 1500, 300), alphabet=20) + [w.copy(), w[:2300].copy()]
-        codes, offs = pack_db(enc)
-        e.db_load(codes, offs)
-        qs = [w, rng.integers(0, 20, 3000).astype(np.uint8), rng.integers(0, 20, 40).astype(np.uint8), np.zeros(0, np.uint8)]
-        got = e.search_batch(qs)
-        for i, q in enumerate(qs):
-            assert np.array_equal(got[i], oracle.scan(q, codes, offs, m)), i
-        assert got[0].max() == 15 * 2400 and e.stats()["recomputed_tiles"] >= 1
+        for shard, nshards in ((0, 1), (1, 3)):
+            e.db_load(codes, offs, shard, nshards)
+            ids_all = e.db_ids()
+            full = e.search_batch(qs)
+            for k in (1, 10, 100, 1024):
+                ids, top = e.search_batch_topk(qcodes, qoffs, k)
+                for qi in range(len(qs)):
+                    assert np.array_equal(e.fetch_scores(qi), full[qi])  # the full vectors stay resident
+                    wi, wt = _host_topk(full[qi], ids_all, k)
+                    assert np.array_equal(ids[qi], wi) and np.array_equal(top[qi], wt), (shard, k, qi)
+                    hi, ht = e.topk(full[qi], k)  # the older host-side call agrees too
+                    assert np.array_equal(hi, wi) and np.array_equal(ht, wt)
+        # a shard smaller than k: the tail is (0xffffffff, -1)
+        e.db_load(codes[:int(offs[7])], offs[:8])
+        ids, top = e.search_batch_topk(qcodes, qoffs, 16)
+        full = e.search_batch(qs)
+        for qi in range(len(qs)):
+            wi, wt = _host_topk(full[qi], np.arange(7, dtype=np.uint32), 16)
+            assert np.array_equal(ids[qi][:7], wi) and np.array_equal(top[qi][:7], wt)
+            assert (ids[qi][7:] == 0xFFFFFFFF).all() and (top[qi][7:] == -1).all()
+        with pytest.raises(swb.SwbError):
+            e.search_batch_topk(qcodes, qoffs, 2000)
     finally:
         e.close()
+
+
+def test_scatter_by_database_id_and_stale_results(swb, oracle):
+    """swb_search_batch_scatter: three engines (one per shard) fill one nq x n matrix by database id; results of a
+    previous database must not be readable after a reload (swb_fetch_scores used to index the new shard with them)"""
+    rng = np.random.default_rng(12)
+    enc = random_db(rng, rng.integers(1, 900, 400), alphabet=20)
+    codes, offs = pack_db(enc)
+    qs = [rng.integers(0, 20, l).astype(np.uint8) for l in (64, 500)]
+    qcodes, qoffs = swb.pack_sequences(qs)
+    m = oracle.matrix("blosum50")
+    out = np.full((2, len(enc)), -9, dtype=np.int32)
+    engines = [swb.Engine(0) for _ in range(3)]
+    try:
+        for s, e in enumerate(engines):
+            e.db_load(codes, offs, s, 3)
+            e.search_batch_scatter(qcodes, qoffs, out)
+        for qi, q in enumerate(qs):
+            assert np.array_equal(out[qi], oracle.scan(q, codes, offs, m)), qi
+        e = engines[0]
+        e.search_batch(qs, fetch=False)
+        assert e.fetch_scores(1) is not None
+        e.db_load(codes, offs, 0, 2)  # a larger shard: the old result matrix no longer matches
+        with pytest.raises(swb.SwbError):
+            e.fetch_scores(0)
+        e.search_batch(qs[:1], fetch=False)
+        assert np.array_equal(e.fetch_scores(0), oracle.scan(qs[0], codes, offs, m)[e.db_ids()])
+        with pytest.raises(swb.SwbError):
+            e.fetch_scores(1)
+    finally:
+        for e in engines:
+            e.close()
+
+
+def test_exact_pass_policies_far_beyond_the_s16_range(swb, oracle):
+    """True scores up to 151,500 (10,100 W-W matches at 15): the rebased s16 policy (V16R) as recompute of flagged
+    tiles, as the direct pass of long-against-long tiles (option direct_len), pipelined with 8 and 16 rows per lane and
+    not pipelined, and the int32 policy (option exact=1) must all reproduce the oracle"""
+    rng = np.random.default_rng(2026)
+    m = oracle.matrix("blosum50")
+    w = np.full(10100, 17, dtype=np.uint8)
+    noisy = w.copy()
+    noisy[rng.choice(len(w), 700, replace=False)] = rng.integers(0, 20, 700)
+    enc = random_db(rng, rng.integers(20, 2500, 200), alphabet=20) + [
+        w.copy(), noisy, w[:9000].copy(), rng.integers(0, 20, 12000).astype(np.uint8), w[:2300].copy(),
+        rng.integers(0, 20, 7000).astype(np.uint8)]
+    codes, offs = pack_db(enc)
+    queries = [w, rng.integers(0, 20, 9000).astype(np.uint8), noisy[:6000]]
+    want = [oracle.scan(q, codes, offs, m) for q in queries]
+    assert want[0].max() == 151500
+    configs = [dict(), dict(exact=1), dict(split=1, split_k=8, direct_len=4000), dict(split=1, split_k=16, direct_len=4000),
+               dict(split=1, split_k=16, direct_len=0), dict(split=0), dict(split=0, exact=1), dict(group_len=1536, split=1)]
+    for cfg in configs:
+        e = swb.Engine(0, **cfg)
+        try:
+            e.db_load(codes, offs)
+            for q, wv in zip(queries, want):
+                got = e.search(q)
+                assert np.array_equal(got, wv), (cfg, len(q))
+            batch = e.search_batch(queries)
+            for qi in range(len(queries)):
+                assert np.array_equal(batch[qi], want[qi]), (cfg, qi)
+        finally:
+            e.close()
+
+
+def _group_devices(n):
+    """n engines: real devices when the box has them, else several engines on device 0"""
+    import torch
+    have = torch.cuda.device_count()
+    return list(range(n)) if have >= n else [i % max(have, 1) for i in range(n)]
+
+
+@pytest.mark.parametrize("ndev,parts", [(2, 0), (4, 2), (4, 4), (8, 0), (8, 2), (3, 1)])
+def test_engine_group_matches_single_engine(swb, oracle, ndev, parts):
+    """swb_group_*: P database parts x R query groups in one process must return the matrix of a single engine, and
+    the merged device-side hit lists the host selection over that matrix"""
+    rng = np.random.default_rng(100 + ndev)
+    enc = random_db(rng, np.clip(np.round(rng.lognormal(4.5, 0.9, 1500)), 0, 5000), alphabet=8)
+    codes, offs = pack_db(enc)
+    qs = [rng.integers(0, 8, l).astype(np.uint8) for l in (700, 33, 1500, 260, 90, 1100, 8, 410, 5, 0, 222)]
+    qcodes, qoffs = swb.pack_sequences(qs)
+    m = oracle.matrix("blosum50")
+    g = swb.EngineGroup(_group_devices(ndev), min_part_sequences=300)
+    try:
+        if parts:
+            g.set_option("db_parts", parts)
+        g.db_load(codes, offs)
+        want_parts = parts if parts else swb.layout_parts(len(enc), ndev, 300)
+        assert g.db_parts() == want_parts and g.size() == ndev
+        full = g.search_batch_packed(qcodes, qoffs)
+        for qi in (0, 2, 4, 9):
+            assert np.array_equal(full[qi], oracle.scan(qs[qi], codes, offs, m)), qi
+        single = swb.Engine(0)
+        try:
+            single.db_load(codes, offs)
+            assert np.array_equal(single.search_batch(qs), full)
+        finally:
+            single.close()
+        ids, top = g.search_batch_topk(qcodes, qoffs, 25)
+        all_ids = np.arange(len(enc), dtype=np.uint32)
+        for qi in range(len(qs)):
+            wi, wt = _host_topk(full[qi], all_ids, 25)
+            assert np.array_equal(ids[qi], wi) and np.array_equal(top[qi], wt), qi
+        st = g.stats()
+        assert st["db_sequences"] == len(enc) and st["cells"] == sum(len(q) for q in qs) * int(offs[-1])
+        # lone queries and a reload
+        one = g.search_batch([qs[2]])
+        assert np.array_equal(one[0], full[2])
+        g.db_load(codes[:int(offs[40])], offs[:41])
+        assert np.array_equal(g.search_batch([qs[0]])[0], oracle.scan(qs[0], codes[:int(offs[40])], offs[:41], m))
+    finally:
+        g.close()
+
+
+@pytest.mark.parametrize("devices", ["0", "0,0", "0,0,0,0,0,0,0,0"])
+def test_dropin_on_several_devices(swb, subset, tmp_path, devices):
+    """the C++ drop-in (smith_waterman_cuda, bin/main) shards the database over every device of its engine group:
+    with 1, 2 and 8 engines the reference-style caller reproduces the golden file and bin/main prints the same
+    id:score lines (SWB_DEVICES names the devices; on a box with fewer GPUs the indices repeat)"""
+    import torch
+    have = torch.cuda.device_count()
+    n = len(devices.split(","))
+    env = dict(os.environ)
+    env["SWB_DEVICES"] = ",".join(str(i) for i in range(n)) if have >= n else devices
+    pkg = os.path.join(ROOT, "ece1782-smith-waterman-cuda_b200")
+    exe = str(tmp_path / "caller")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-I" + os.path.join(ROOT, "include"), "-o", exe,
+                    os.path.join(ROOT, "tests", "cpp", "caller_compat.cpp"), os.path.join(pkg, "lib", "SWSolver.o"),
+                    "-L" + os.path.join(pkg, "lib"), "-lswb", "-Wl,-rpath," + os.path.join(pkg, "lib")], check=True)
+    qpath = os.path.join(GOLDEN, "queries", "P01008.fasta")
+    dbpath = os.path.join(GOLDEN, "uniprot_subset.fasta")
+    r = subprocess.run([exe, qpath, dbpath, os.path.join(GOLDEN, "P01008.head111.txt")], capture_output=True, text=True,
+                       timeout=300, env=env)
+    assert r.returncode == 0 and "mismatches 0" in r.stdout, r.stdout + r.stderr
+    main = os.path.join(pkg, "bin", "main")
+    r = subprocess.run([main, "--query", qpath, "--db", dbpath], capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0, r.stderr
+    body = [l for l in r.stdout.split("\n")[2:2 + 111]]
+    gold = _gold("P01008")
+    assert [int(l.split(":")[0]) for l in body[:3]] == [56, 34, 13]
+    for l in body:
+        sid, sc = l.split(":")
+        assert int(sc) == gold[int(sid)]
+    if n == 1:  # --gpus is an extension that must not change the output
+        r2 = subprocess.run([main, "--query", qpath, "--db", dbpath, "--gpus", "1"], capture_output=True, text=True,
+                            timeout=300)
+        assert r2.returncode == 0 and r2.stdout.split("\n")[:113] == r.stdout.split("\n")[:113]
 
 
 def test_cli_missing_files_and_error_codes(swb, tmp_path):

@@ -76,6 +76,24 @@ def test_dbfile_roundtrip_and_rejects_garbage(swb, tmp_path):
         swb.dbfile_read(bad)
     with pytest.raises(swb.SwbError):
         swb.dbfile_read(str(tmp_path / "missing.swbdb"))
+    # a crafted header whose sizes wrap around to the file size (n = 2^28, residues chosen so that
+    # 32 + 8 * (n + 1) + residues == 40 modulo 2^64) must be rejected, not dereferenced
+    import struct
+    n_evil = 0x10000000
+    residues = (40 - 32 - 8 * (n_evil + 1)) % (1 << 64)
+    open(bad, "wb").write(b"SWBDB\x00\x01\x00" + struct.pack("<IiQQ", n_evil, 0, residues, 0) + b"\0" * 8)
+    assert os.path.getsize(bad) == 40
+    with pytest.raises(swb.SwbError):
+        swb.dbfile_read(bad)
+    # offsets that decrease or run past the residues are rejected too
+    swb.dbfile_write(path, codes, offs, first_id=0)
+    raw = bytearray(open(path, "rb").read())
+    for evil in (struct.pack("<Q", 400), struct.pack("<Q", 4)):  # offs[3] (6): beyond the end / below offs[2] = 5
+        broken = bytearray(raw)
+        broken[32 + 24:32 + 32] = evil
+        open(bad, "wb").write(bytes(broken))
+        with pytest.raises(swb.SwbError):
+            swb.dbfile_read(bad)
 
 
 def test_mkdb_tool(swb, tmp_path):

@@ -1,5 +1,6 @@
-"""N > 1 host path on CPU: two gloo ranks each take one residue-balanced shard (same planner the engine uses),
-score it, and exchange only small results (per-shard (ids, scores) and top-k lists) -- no data-path collective.
+"""N > 1 host path on CPU: gloo ranks take their cell of the P database parts x R query groups layout (same planner and
+layout rules the engine group uses), score it, and exchange only small results (per-shard (ids, scores) and top-k
+lists) -- no data-path collective.
 The merged vector / hit list must equal the unsharded oracle scan. Scores of a shard come from the host
 emulation of the warp program (test infrastructure), since this container has no GPU."""
 import importlib
@@ -15,52 +16,58 @@ from conftest import GOLDEN, PKG, ROOT
 
 
 def _worker(rank, world, port, q):
+    """One rank of the P x R layout bench.py uses under torchrun (include/swb.h, engine group): rank -> database part
+    rank % P, query group rank // P; the shard's scores come from the host emulation of the warp program."""
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        import ctypes
+        import emu_lib
         from oracle_lib import Oracle, pack_db, read_fasta, read_query
         swb = importlib.import_module(PKG)
         o = Oracle()
         _, seqs = read_fasta(os.path.join(GOLDEN, "uniprot_subset.fasta"))
         codes, offs = pack_db([o.encode(s) for s in seqs])
         m = o.matrix("blosum50")
-        query = o.encode(read_query(os.path.join(GOLDEN, "queries", "P02232.fasta")))
-        info, _, ids = swb.plan_describe(offs, rank, world, want_ids=True)
-        emu = ctypes.CDLL(os.path.join(ROOT, PKG, "lib", "libswbemu.so"))
-        u8p, i8p = ctypes.POINTER(ctypes.c_uint8), ctypes.POINTER(ctypes.c_int8)
-        u64p, i32p = ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_int32)
-        emu.swbemu_search.restype = ctypes.c_int
-        emu.swbemu_search.argtypes = [u8p, u64p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, i8p,
-                                      ctypes.c_int, u8p, ctypes.c_uint32, ctypes.c_int, ctypes.c_int, ctypes.c_uint32,
-                                      ctypes.c_int, ctypes.c_uint32, i32p, ctypes.POINTER(ctypes.c_uint32), u8p,
-                                      ctypes.c_uint32, i32p, ctypes.c_uint32]
-        mine = np.zeros(info.n_local, dtype=np.int32)
-        rc = ctypes.c_uint32()
-        assert emu.swbemu_search(codes.ctypes.data_as(u8p), offs.ctypes.data_as(u64p), len(seqs), rank, world, 384,
-                                 m.ctypes.data_as(i8p), 2, query.ctypes.data_as(u8p), len(query), 0, 0, 0, -1, 8192,
-                                 mine.ctypes.data_as(i32p), ctypes.byref(rc), None, 0, None, 0) == 0
-        order = np.lexsort((ids, -mine))[:10]
-        parts = [None] * world
-        dist.all_gather_object(parts, (ids.tolist(), mine.tolist(), ids[order].tolist(), mine[order].tolist()))
-        dist.barrier()
-        if rank == 0:
-            full = swb.merge_shard_scores(len(seqs), [(p[0], p[1]) for p in parts])
-            want = o.scan(query, codes, offs, m)
-            tid, ts = swb.merge_topk([(p[2], p[3]) for p in parts], 10)
-            worder = np.lexsort((np.arange(len(want)), -want))[:10]
-            ok = bool(np.array_equal(full, want) and np.array_equal(tid, worder.astype(np.uint32)) and
-                      np.array_equal(ts, want[worder]))
-            q.put(ok)
+        names = ["P02232", "P05013", "P14942", "P01008", "P07327"]
+        queries = [o.encode(read_query(os.path.join(GOLDEN, "queries", nme + ".fasta"))) for nme in names]
+        _, qoffs = swb.pack_sequences(queries)
+        # 60 sequences per part at least: world 2 -> P = 1 (two query groups), world 4 -> P = 1 too; forcing P = world
+        # is the pure database sharding
+        for parts in (swb.layout_parts(len(seqs), world, 60), world):
+            groups = world // parts
+            part, grp = rank % parts, rank // parts
+            group_of = swb.layout_query_groups(qoffs, groups)
+            mine_q = [qi for qi in range(len(queries)) if group_of[qi] == grp]
+            info, _, ids = swb.plan_describe(offs, part, parts, want_ids=True)
+            res = {}
+            for qi in mine_q:
+                sc, _ = emu_lib.search(codes, offs, m, queries[qi], K=0, shard=part, nshards=parts, n_out=info.n_local)
+                order = np.lexsort((ids, -sc.astype(np.int64)))[:10]
+                res[qi] = (sc.tolist(), ids[order].tolist(), sc[order].tolist())
+            gathered = [None] * world
+            dist.all_gather_object(gathered, (part, ids.tolist(), res))
+            dist.barrier()
+            if rank == 0:
+                ok = sorted(qi for g in gathered for qi in g[2]) == sorted(list(range(len(queries))) * parts)
+                for qi, query in enumerate(queries):
+                    want = o.scan(query, codes, offs, m)
+                    holders = [g for g in gathered if qi in g[2]]
+                    full = swb.merge_shard_scores(len(seqs), [(g[1], g[2][qi][0]) for g in holders])
+                    tid, ts = swb.merge_topk([(g[2][qi][1], g[2][qi][2]) for g in holders], 10)
+                    worder = np.lexsort((np.arange(len(want)), -want.astype(np.int64)))[:10]
+                    ok = ok and len(holders) == parts and bool(
+                        np.array_equal(full, want) and np.array_equal(tid, worder.astype(np.uint32)) and
+                        np.array_equal(ts, want[worder]))
+                q.put(ok)
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2])
-def test_two_rank_sharded_scan_gloo(world):
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_scan_gloo(world):
     so = os.path.join(ROOT, PKG, "lib", "libswbemu.so")
     if not os.path.exists(so):
         import subprocess
@@ -74,7 +81,8 @@ def test_two_rank_sharded_scan_gloo(world):
     for p in procs:
         p.join(300)
         assert p.exitcode == 0
-    assert q.get(timeout=10) is True
+    assert q.get(timeout=10) is True  # the layout rule's choice of parts
+    assert q.get(timeout=10) is True  # parts = world: pure database sharding
 
 
 def test_merge_helpers():

@@ -165,12 +165,21 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(power) if power else None}
 
 
+def host_threads():
+    """threads for the CPU legs: every core this process may run on (torchrun exports OMP_NUM_THREADS=1, which would
+    turn the reference arm into a one-core run if the OpenMP default were used)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_sample_gcups(codes, offsets, qnames, qtexts, budget_s, threads=0, keep=None):
     """Oracle (port of the reference recurrence) on a bounded stride sample of the workload. keep: a list that
     receives (stride, scores of query k at the sampled sequences) for a parity check against the GPU's scores."""
     from oracle_lib import Oracle
     o = Oracle()
-    cores = threads or o.max_threads()
+    cores = threads or host_threads()
     m = o.matrix("blosum50")
     n = len(offsets) - 1
     total_cells = float(sum(len(q) for q in qtexts)) * float(offsets[-1])
@@ -188,8 +197,8 @@ def cpu_sample_gcups(codes, offsets, qnames, qtexts, budget_s, threads=0, keep=N
         cells += len(qc) * sample_res
     dt = time.time() - t0
     return {"value": cells / dt * 1e-9, "unit": "GCUPS", "cores": cores, "kind": "port",
-            "sample": "oracle/sw_oracle.c (OpenMP over sequences), every %d-th of %d sequences x all %d queries, "
-                      "%.3g cells in %.1f s" % (stride, n, len(qtexts), cells, dt)}, dt
+            "sample": "oracle/sw_oracle.c (OpenMP over sequences, %d threads), every %d-th of %d sequences x all %d "
+                      "queries, %.3g cells in %.1f s" % (cores, stride, n, len(qtexts), cells, dt)}, dt
 
 
 def run_reference(args):
@@ -217,6 +226,50 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def ref_cuda_leg(qnames, budget_scale=0.25):
+    """The reference's own CUDA solver (SWSolver.cu:201-264 behind oracle/_ref/ref_cuda_scan, compiled unmodified for
+    sm_100a) on the same GPU in the same run, as a reported baseline: a 1/4-scale copy of the benchmark database (its
+    fixed 400 MB residue buffer and batching do not take the full one in reasonable time) against the reference
+    queries that fit its 1024-row limit (SWSolver.cu:85). Solver-call seconds exclude its FASTA parsing."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_cuda_scan")
+    if not os.path.exists(exe):
+        return {"unavailable": "oracle/_ref/ref_cuda_scan not built (needs /root/reference at build time)"}
+    import tempfile
+    letters = np.frombuffer(b"ARNDCQEGHILKMFPSTWYVBJZXU", dtype=np.uint8)
+    codes, offsets = synth_db(scale=budget_scale)
+    text = letters[np.minimum(codes, 24)].tobytes()
+    out = {"kernel": "f_scoreSequenceTiledCoalesced (reference SWSolver.cu, unmodified, -arch=sm_100a)", "unit": "GCUPS",
+           "db_sequences": int(len(offsets) - 1), "db_residues": int(offsets[-1]), "queries": {}}
+    with tempfile.TemporaryDirectory() as tmp:
+        dbpath = os.path.join(tmp, "db.fasta")
+        with open(dbpath, "wb") as f:
+            for i in range(len(offsets) - 1):
+                f.write(b">s%d\n" % i)
+                f.write(text[int(offsets[i]):int(offsets[i + 1])])
+                f.write(b"\n")
+        cells = secs = 0.0
+        for nme in qnames:
+            qpath = os.path.join(ROOT, "tests", "golden", "queries", nme + ".fasta")
+            try:
+                r = subprocess.run([exe, qpath, dbpath, "1"], capture_output=True, text=True, timeout=240)
+            except subprocess.TimeoutExpired:
+                out["queries"][nme] = "timeout"
+                continue
+            tl = [l for l in r.stdout.split("\n") if l.startswith("#TIME")]
+            if r.returncode != 0 or not tl:
+                out["queries"][nme] = "failed (exit %d)" % r.returncode
+                continue
+            f = dict(kv.split("=") for kv in tl[0].split()[1:])
+            c = float(f["qlen"]) * float(offsets[-1])
+            out["queries"][nme] = {"qlen": int(f["qlen"]), "solver_s": float(f["solver_s"]),
+                                   "gcups": c / float(f["solver_s"]) * 1e-9}
+            cells += c
+            secs += float(f["solver_s"])
+        out["value"] = cells / secs * 1e-9 if secs else None
+        out["timing"] = "wall clock around smith_waterman_cuda() (pack + managed-memory upload + launches + gather)"
+    return out
+
+
 def workload_config(offsets, qs, args):
     cfg = _workload_config(offsets, qs, args)
     if getattr(args, "affine", ""):
@@ -242,6 +295,30 @@ def _workload_config(offsets, qs, args):
             "l2": "inputs larger than L2 (packed residues + boundary scratch >> 126 MB)", "scale": args.scale}
 
 
+def sample_parity(swb, eng, codes, offsets, queries, local_of, fetch_row, threads, seconds):
+    """Oracle against the engine on a strided sample of THIS rank's shard for the given queries (global indices ->
+    code arrays). fetch_row(local query index) returns the shard's score vector. Returns (ok, description)."""
+    from oracle_lib import Oracle
+    o = Oracle()
+    ids = eng.db_ids()
+    if len(ids) == 0 or not queries:
+        return True, "empty shard or no queries"
+    lens = np.diff(offsets.astype(np.int64))[ids]
+    cells = float(sum(len(q) for q in queries.values())) * float(lens.sum())
+    stride = max(1, int(np.ceil(cells / (threads * 0.6e9 * seconds))))
+    pos = np.arange(0, len(ids), stride)
+    sel = ids[pos]
+    sc, so = swb.pack_sequences([codes[int(offsets[i]):int(offsets[i + 1])] for i in sel])
+    m = o.matrix("blosum50")
+    ok = True
+    for qi, q in queries.items():
+        want = o.scan(q, sc, so, m, 2, 0, 1, threads)
+        got = fetch_row(local_of[qi])[pos]
+        ok = ok and bool(np.array_equal(got, want))
+    return ok, "oracle vs GPU, every %d-th sequence of the rank's shard (%d sequences) x %d queries" % (
+        stride, len(sel), len(queries))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -249,23 +326,33 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--scale", type=float, default=1.0, help="database size factor (1.0 = the named workload)")
-    ap.add_argument("--workload", default="config2", help="config2 (default, the headline) or config5 (1,000 queries "
-                    "x UniProt-scale database; meant for 8 GPUs)")
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--workload", default="config2", help="config2 (default, the headline), config4 (long sequences) or "
+                    "config5 (1,000 queries x UniProt-scale database; meant for 8 GPUs)")
+    ap.add_argument("--e2e-steps", type=int, default=-1, help="warm end-to-end repetitions (default 2; config5: 1)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--parity-seconds", type=float, default=3.0, help="CPU budget of the per-rank oracle sample (N > 1)")
+    ap.add_argument("--topk", type=int, default=10)
+    ap.add_argument("--db-parts", type=int, default=0, help="database parts P of the P x R rank layout (0 = the layout "
+                    "rule of the engine group: the largest divisor of N with >= 250,000 sequences per part)")
+    ap.add_argument("--group", action="store_true", help="one process drives all --gpus devices through the engine "
+                    "group (swb_group_*) instead of one torchrun rank per GPU")
     ap.add_argument("--streams", type=int, default=0)
     ap.add_argument("--k", type=int, default=0)
     ap.add_argument("--group-len", type=int, default=0)
     ap.add_argument("--group-order", type=int, default=0)
-    ap.add_argument("--split", type=int, default=-1, help="pipelined passes for very long tiles: 1 on, 0 off (default)")
-    ap.add_argument("--pair-queries", type=int, default=-1, help="pack two queries of a batch per lane: 1 (default), 0")
+    ap.add_argument("--split", type=int, default=-1, help="pipelined passes for very long tiles: 1 on, 0 off, -1 "
+                    "(default) = the engine's rule: on for small shards")
+    ap.add_argument("--split-k", type=int, default=0, help="rows per lane of the pipelined groups: 0 auto, 8, 16")
+    ap.add_argument("--direct-len", type=int, default=-1, help="tiles / queries at least this long are scored by the "
+                    "rebased s16 policy at once (-1 = engine default 10000, 0 = never)")
+    ap.add_argument("--exact", type=int, default=-1, help="exact passes: 0 rebased s16 (default), 1 int32")
     ap.add_argument("--batch-order", type=int, default=-1, help="0 longest query first (default), 1 as given")
     ap.add_argument("--chunk-rows", type=int, default=0)
     ap.add_argument("--xl-len", type=int, default=0)
-    ap.add_argument("--split-fill", type=int, default=0)
     ap.add_argument("--synth-queries", type=int, default=0, help="N > 0: N synthetic queries of the configs[4] length law "
                     "instead of the 20 reference queries (a side measurement: short-query mix on the configs[1] DB)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-ref-cuda", action="store_true", help="skip the reference-CUDA-kernel leg (N = 1 default run)")
     ap.add_argument("--affine", default="", help="GO,GE: affine gaps instead of the reference's linear gap 2 (a side "
                     "measurement of the V16A kernels; not the headline metric, no CPU leg)")
     ap.add_argument("--per-query", action="store_true", help="also print device GCUPS per query")
@@ -284,66 +371,99 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     swb = importlib.import_module(PKG)
+    side = False  # a side measurement (not the named workload): no CPU / reference legs
     if args.workload == "config5":
         codes, offsets = synth_db_uniprot_scale()
         qs = synth_queries()
         names = ["q%d" % i for i in range(len(qs))]
-        args.no_cpu = True
+        side = True
     elif args.workload == "config4":
         codes, offsets, qs = synth_config4()
         names = ["L%d" % len(q) for q in qs]
-        args.no_cpu = True
+        side = True
     else:
         codes, offsets = synth_db(scale=args.scale)
         names, qs = load_queries(swb)
         if args.synth_queries:
             qs = synth_queries(args.synth_queries)
             names = ["q%d" % i for i in range(len(qs))]
-            args.no_cpu = True
-    qcodes, qoffs = swb.pack_sequences(qs)
+            side = True
+    if args.affine:
+        side = True
+    if side:
+        args.no_cpu = True
+        args.no_ref_cuda = True
+    big = args.workload == "config5"  # no nq x n host matrix at UniProt scale: device-side hit lists instead
+    if args.e2e_steps < 0:
+        args.e2e_steps = 1 if big else 2
+    n_total = len(offsets) - 1
     total_cells = float(sum(len(q) for q in qs)) * float(offsets[-1])
+    if args.group:
+        return run_group(args, swb, codes, offsets, qs, total_cells)
+
+    # rank layout: P database parts x R query groups (the engine group's rule); rank -> (part, group)
+    parts = args.db_parts if args.db_parts else swb.layout_parts(n_total, world)
+    if world % parts:
+        raise SystemExit("--db-parts must divide the number of ranks")
+    groups = world // parts
+    part, grp = rank % parts, rank // parts
+    _, qoffs_all = swb.pack_sequences(qs)
+    group_of = swb.layout_query_groups(qoffs_all, groups)
+    mine = [qi for qi in range(len(qs)) if group_of[qi] == grp]  # global indices of this rank's queries
+    local_of = {qi: k for k, qi in enumerate(mine)}
+    qcodes, qoffs = swb.pack_sequences([qs[qi] for qi in mine])
+    my_cells = float(sum(len(qs[qi]) for qi in mine))
 
     opts = {}
-    if args.streams:
-        opts["streams"] = args.streams
-    if args.k:
-        opts["k"] = args.k
-    if args.group_len:
-        opts["group_len"] = args.group_len
-    if args.group_order:
-        opts["group_order"] = args.group_order
-    if args.split >= 0:
-        opts["split"] = args.split
-    if args.pair_queries >= 0:
-        opts["pair_queries"] = args.pair_queries
-    if args.batch_order >= 0:
-        opts["batch_order"] = args.batch_order
-    if args.chunk_rows:
-        opts["chunk_rows"] = args.chunk_rows
-    if args.xl_len:
-        opts["xl_len"] = args.xl_len
-    if args.split_fill:
-        opts["split_fill"] = args.split_fill
+    for key, val, unset in (("streams", args.streams, 0), ("k", args.k, 0), ("group_len", args.group_len, 0),
+                            ("group_order", args.group_order, 0), ("split", args.split, -1),
+                            ("split_k", args.split_k, 0), ("direct_len", args.direct_len, -1), ("exact", args.exact, -1),
+                            ("batch_order", args.batch_order, -1), ("chunk_rows", args.chunk_rows, 0),
+                            ("xl_len", args.xl_len, 0)):
+        if val != unset:
+            opts[key] = val
     eng = swb.Engine(local, **opts)
     stream = torch.cuda.current_stream()
     eng.set_stream(stream.cuda_stream)
-    eng.db_load(codes, offsets, rank, world)
     if args.affine:
         go, ge = (int(x) for x in args.affine.split(","))
         eng.set_scoring_affine(swb.scoring_matrix(swb.SWB_SCORING_BLOSUM50_REF)[0], go, ge)
-        args.no_cpu = True
-    nloc = eng.db_count()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_resident():
-        eng.search_batch_packed(qcodes, qoffs, fetch=False)
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
-    for _ in range(args.warmup):
-        step_resident()
+    # One step = one scan of the whole database by all queries, scores (config5: the k best per query, selected on the
+    # device) copied back to host memory inside the step: SURVEY 8(d) times "first scoring kernel to last score D2H".
+    out = None
+
+    def step():
+        if big:
+            return eng.search_batch_topk(qcodes, qoffs, args.topk)
+        eng.search_batch_packed(qcodes, qoffs, fetch=True, out=out)
+        return None
+
+    # cold end to end: the first swb_db_load (allocations, plan, upload, pack) + the first scan of this process
+    barrier()
+    t0 = time.perf_counter()
+    eng.db_load(codes, offsets, part, parts)
+    nloc = eng.db_count()
+    if not big:
+        out = np.zeros((len(mine), nloc), dtype=np.int32)
+    step()
+    torch.cuda.synchronize()
+    cold_s = max_over_ranks(time.perf_counter() - t0)
+    cold_load_ms = eng.stats()["load_ms"]
+
+    for _ in range(max(0, args.warmup - 1)):  # the cold call above was the first warm-up step
+        step()
     sampler = ClockSampler(local)
     barrier()
     sampler.start()
@@ -352,38 +472,30 @@ def main():
     ev0.record(stream)
     launches = 0
     for _ in range(args.steps):
-        step_resident()
+        step()
         launches += eng.stats()["kernel_launches"]
     ev1.record(stream)
     barrier()
     clocks = sampler.stop()
-    ms = ev0.elapsed_time(ev1)
+    ms_max = max_over_ranks(ev0.elapsed_time(ev1))
     st = eng.stats()
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
     ms_per_step = ms_max / args.steps
     value = total_cells / (ms_per_step * 1e-3) * 1e-9
+    lt = torch.tensor([launches], dtype=torch.int64, device="cuda")
+    pc = torch.tensor([float(st["padded_cells"])], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(lt)
+        dist.all_reduce(pc)
+    launches, padded_cells = int(lt.item()), float(pc.item())
 
-    # configs[4] parity: 5 queries x a 1/1024 stride sample of this rank's shard against the oracle
-    sample_ok = None
-    if args.workload == "config5":
-        from oracle_lib import Oracle
-        o = Oracle()
-        ids = eng.db_ids()
-        sel = ids[::1024]
-        sub = [codes[int(offsets[i]):int(offsets[i + 1])] for i in sel]
-        sc, so = swb.pack_sequences(sub)
-        sample_ok = True
-        for qi in (0, 250, 500, 750, 999):
-            got = eng.fetch_scores(qi)[::1024]
-            want = o.scan(qs[qi], sc, so, o.matrix("blosum50"))
-            sample_ok = sample_ok and bool(np.array_equal(got, want))
-        args.e2e_steps = 0
+    # ---- parity on every rank: oracle on a strided sample of the rank's shard ------------------------------------
+    def fetch_row(k):
+        return eng.fetch_scores(k) if big else out[k]
 
-    # configs[3] parity: every query against its mutated copy and itself (the int32-recompute hits) and 6 targets
+    threads = max(1, host_threads() // world)
+    sample_ok, sample_desc = None, None
     if args.workload == "config4":
+        # every query against its mutated copy and itself (the beyond-s16 hits) and 6 targets
         from oracle_lib import Oracle
         o = Oracle()
         ids = eng.db_ids()
@@ -391,50 +503,86 @@ def main():
         pos = {int(g): k for k, g in enumerate(ids)}
         sc, so = swb.pack_sequences([codes[int(offsets[i]):int(offsets[i + 1])] for i in sel])
         sample_ok = True
-        for qi in range(len(qs)):
-            got = eng.fetch_scores(qi)[[pos[int(i)] for i in sel]]
-            want = o.scan(qs[qi], sc, so, o.matrix("blosum50"))
-            sample_ok = sample_ok and bool(np.array_equal(got, want))
+        for qi in mine:
+            got = fetch_row(local_of[qi])[[pos[int(i)] for i in sel]]
+            sample_ok = sample_ok and bool(np.array_equal(got, o.scan(qs[qi], sc, so, o.matrix("blosum50"))))
+        sample_desc = "oracle vs GPU: every query x (6 targets + the mutated copies + the queries themselves)"
+    elif not args.affine and (world > 1 or big or args.no_cpu):
+        chosen = mine if not big else mine[::max(1, len(mine) // 5)][:5]
+        sample_ok, sample_desc = sample_parity(swb, eng, codes, offsets, {qi: qs[qi] for qi in chosen}, local_of,
+                                               fetch_row, threads, args.parity_seconds)
+    if sample_ok is not None and world > 1:
+        t = torch.tensor([1 if sample_ok else 0], dtype=torch.int32, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        sample_ok = bool(t.item())
 
-    # end to end through the C ABI with host buffers (database upload + search + scores back), wall clock
-    big = args.workload == "config5"  # no nq x n host matrix at UniProt scale: top hits come from fetch_scores
-    out = np.zeros((1 if big else len(qs), nloc), dtype=np.int32)
+    # ---- hit lists: device-side selection per rank, merged on the host, checked three ways ---------------------------
+    #  (1) every rank: its device list == the host selection over the full vector of its shard
+    #  (2) rank 0: merged lists == the k best of the merged FULL vector   (3) == oracle scores of those ids
+    top_ok, top_desc = None, None
+    if not args.affine and len(qs) and n_total:
+        k = args.topk
+        dev_ids, dev_top = eng.search_batch_topk(qcodes, qoffs, k)
+        check = mine if not big else mine[::max(1, len(mine) // 3)][:3]
+        ids_mine = eng.db_ids()
+        ok1 = True
+        fulls = {}
+        for qi in check:
+            row = eng.fetch_scores(local_of[qi])
+            hi, ht = eng.topk(row, k)
+            ok1 = ok1 and bool(np.array_equal(hi, dev_ids[local_of[qi]]) and np.array_equal(ht, dev_top[local_of[qi]]))
+            fulls[qi] = row
+        payload = (part, ids_mine, {qi: (dev_ids[local_of[qi]], dev_top[local_of[qi]]) for qi in mine}, fulls, ok1)
+        gathered = [payload]
+        if world > 1:
+            gathered = [None] * world
+            dist.all_gather_object(gathered, payload)
+        if rank == 0:
+            from oracle_lib import Oracle
+            o = Oracle()
+            top_ok = all(g[4] for g in gathered)
+            nmerged = 0
+            for qi in range(len(qs)):
+                holders = [g for g in gathered if qi in g[2]]
+                mi, mt = swb.merge_topk([g[2][qi] for g in holders], k)
+                top_ok = top_ok and len(holders) == parts and len(mi) == min(k, n_total)
+                nmerged += 1
+                full_holders = [g for g in holders if qi in g[3]]
+                if len(full_holders) == parts:
+                    full = swb.merge_shard_scores(n_total, [(g[1], g[3][qi]) for g in full_holders])
+                    order = np.lexsort((np.arange(n_total), -full.astype(np.int64)))[:k]
+                    top_ok = top_ok and bool(np.array_equal(mi, order.astype(np.uint32)) and np.array_equal(mt, full[order]))
+                    sc, so = swb.pack_sequences([codes[int(offsets[i]):int(offsets[i + 1])] for i in mi])
+                    top_ok = top_ok and bool(np.array_equal(o.scan(qs[qi], sc, so, o.matrix("blosum50")), mt))
+            nfull = len(set(qi for g in gathered for qi in g[3]))
+            top_desc = ("per-rank device top-%d == host selection over the shard's full vector (%d queries); merged "
+                        "lists of %d queries (%d parts each); of those, %d also == top-%d of the merged full vector == "
+                        "oracle scores of those ids" % (k, nfull, nmerged, parts, nfull, k))
+
+    # ---- warm end to end through the C ABI with host buffers (database upload + scan + results back), wall clock ----
     e2e_times = []
-    for it in range(args.e2e_steps + 1 if args.e2e_steps > 0 else 0):
+    for it in range(args.e2e_steps):
         barrier()
         t0 = time.perf_counter()
-        eng.db_load(codes, offsets, rank, world)
-        eng.search_batch_packed(qcodes, qoffs, fetch=True, out=out)
+        eng.db_load(codes, offsets, part, parts)
+        step()
         torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        if it > 0:
-            e2e_times.append(float(tt.item()))
-    e2e_s = float(np.mean(e2e_times)) if e2e_times else float("nan")
+        e2e_times.append(max_over_ranks(time.perf_counter() - t0))
+    e2e_s = float(np.mean(e2e_times)) if e2e_times else cold_s
     load_ms = eng.stats()["load_ms"]
-    e2e = {"value": total_cells / e2e_s * 1e-9, "unit": "GCUPS",
-           "h2d_bytes_per_step": int(codes.nbytes + offsets.nbytes + qcodes.nbytes + qoffs.nbytes),
-           "d2h_bytes_per_step": int(4 * len(qs) * nloc), "seconds_per_step": e2e_s, "db_load_ms": load_ms,
-           "api": "swb_db_load + swb_search_batch (host buffers)"}
-
-    # host merge of the per-rank hit lists (top-10 per query), checks the sharded path end to end
-    top_ok = None
+    shard_bytes = int(eng.stats()["db_residues"]) if parts > 1 else int(codes.nbytes)
+    d2h = 8 * args.topk * len(mine) if big else int(4 * len(mine) * nloc)
+    bt = torch.tensor([float(shard_bytes + qcodes.nbytes + qoffs.nbytes), float(d2h)], dtype=torch.float64, device="cuda")
     if world > 1:
-        mine = []
-        for qi in range(len(qs)):
-            ids, top = eng.topk(eng.fetch_scores(qi) if big else out[qi], 10)
-            mine.append((ids.tolist(), top.tolist()))
-        gathered = [None] * world
-        dist.all_gather_object(gathered, mine)
-        if rank == 0:
-            merged = []
-            for qi in range(len(qs)):
-                allh = [(s, i) for r in range(world) for i, s in zip(*gathered[r][qi])]
-                allh.sort(key=lambda x: (-x[0], x[1]))
-                merged.append(allh[:10])
-            top_ok = all(len(mm) == 10 for mm in merged)
+        dist.all_reduce(bt)
+    e2e = {"value": total_cells / e2e_s * 1e-9, "unit": "GCUPS",
+           "h2d_bytes_per_step": int(bt[0].item()) + int(offsets.nbytes), "d2h_bytes_per_step": int(bt[1].item()),
+           "seconds_per_step": e2e_s, "db_load_ms": load_ms,
+           "warm": "mean of %d repetitions after the first (buffers already allocated)" % len(e2e_times) if e2e_times
+                   else "not run: value is the cold call",
+           "cold": {"value": total_cells / cold_s * 1e-9, "seconds_per_step": cold_s, "db_load_ms": cold_load_ms,
+                    "what": "first swb_db_load + first scan of the process (allocations, module load)"},
+           "api": "swb_db_load + %s (host buffers)" % ("swb_search_batch_topk" if big else "swb_search_batch")}
 
     if rank == 0:
         # roofline of the dominant kernel (swb_score_kernel<K,V16>): the ALU pipe (64 lanes/clk/SM). Per cell pair the
@@ -447,8 +595,7 @@ def main():
         per_kind = {swb.MICROBENCH_KINDS[k]: round(swb.microbench(local, k), 1) for k in (0, 1, 2, 3, 5, 6, 11, 12, 13)}
         vadd_off_alu = pair > 1.5 * alu
         instr_per_cell = (3.5 if vadd_off_alu else 4.5) / 2.0
-        padded_cells = float(st["padded_cells"])
-        ach_padded = padded_cells * world / (ms_per_step * 1e-3) * 1e-9  # cells the kernel really executes
+        ach_padded = padded_cells / (ms_per_step * 1e-3) * 1e-9  # cells the kernels really execute, all ranks
         peak_gcups = alu / instr_per_cell
         peaks = {}
         try:
@@ -456,16 +603,25 @@ def main():
         except Exception:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        residues = float(st["db_residues"])
-        alg_bytes = len(qs) * residues  # one byte of DB residue per query pass
+        # algorithmic bytes: one byte of database residue per query pass + 4 B of score per (query, sequence)
+        alg_bytes = float(sum(1 for _ in qs)) * float(offsets[-1]) + 4.0 * len(qs) * n_total
+        traffic, traffic_src = None, "no ncu --set full capture of this configuration is committed"
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
+            key = "%s_scale%g_n%d" % (args.workload, args.scale, world)
+            if key in tj:
+                traffic, traffic_src = tj[key]["dram_bytes_per_launch"], tj[key]["source"]
+        except Exception:
+            pass
         roofline = {"bound": "int_alu", "kernel": "swb_score_kernel<K,V16>", "achieved": value / world, "peak": peak_gcups,
                     "unit": "GCUPS", "frac": (value / world) / peak_gcups,
-                    # dram__bytes_read+write of ONE launch (Q = 4743 rows over the same database) from the committed
-                    # ncu --set full capture, profiles/r1_score_kernel_K32_V16_raw_selected.txt; the algorithmic bytes
-                    # of that launch are 0.203e9 (residues + scores): the rest is the strip-boundary rows
-                    "traffic": 32.44e9, "traffic_algorithmic": float(st["db_residues"]) + 4.0 * st["db_sequences"],
+                    "traffic": traffic, "traffic_source": traffic_src,
+                    "traffic_algorithmic_per_step": alg_bytes,
                     "achieved_incl_padding": ach_padded / world,
                     "frac_incl_padding": (ach_padded / world) / peak_gcups,
+                    "alu_instr_per_cell_pair": {"used": 2 * instr_per_cell, "if_vadd2_on_alu_pipe": 4.5,
+                                                "if_vadd2_off_alu_pipe": 3.5, "vadd2_off_alu_pipe": bool(vadd_off_alu),
+                                                "frac_if_4.5": (value / world) / (alu / 2.25)},
                     "peak_source": "measured live: ALU pipe issues %.0f Glane-instr/s (swb_microbench, viaddmax.relu alone); "
                                    "%.1f ALU-pipe instructions per cell pair (prmt + viaddmax.relu + viaddmax + 1/2 vimax3%s); "
                                    "a dependent-chain loop of the full mix reaches %.0f Glane-instr/s" % (
@@ -473,16 +629,24 @@ def main():
                                        "; vadd2 issues on another pipe: viaddmax+vadd2 = %.0f" % pair if vadd_off_alu
                                        else " + vadd2", mix),
                     "instr_rates_glane_per_s": per_kind,
-                    "hbm": {"achieved": alg_bytes / (ms_per_step * 1e-3) * 1e-9, "peak": hbm_peak, "unit": "GB/s",
-                            "frac": alg_bytes / (ms_per_step * 1e-3) * 1e-9 / hbm_peak,
+                    "hbm": {"achieved": alg_bytes / (ms_per_step * 1e-3) * 1e-9, "peak": hbm_peak * world, "unit": "GB/s",
+                            "frac": alg_bytes / (ms_per_step * 1e-3) * 1e-9 / (hbm_peak * world),
+                            "what": "database streaming: algorithmic bytes per step / step time (the path does "
+                                    "hundreds of cell updates per byte: HBM is not the bound)",
                             "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}}
+        cfg = workload_config(offsets, qs, args)
+        cfg["layout"] = {"db_parts": parts, "query_groups": groups,
+                         "rule": "P = largest divisor of N with >= 250,000 sequences per part; queries split LPT"}
+        cfg["value_includes"] = ("device-side top-%d per query copied to the host" % args.topk if big
+                                 else "all scores copied to the host (4 B x queries x sequences per step)")
         line = {"metric": METRIC, "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
-                "vs_baseline": None, "dtype": "s16x2 (int32 recompute on overflow)", "data": "synthetic",
-                "config": workload_config(offsets, qs, args), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+                "vs_baseline": None, "dtype": "s16x2 (exact rebased-s16 / int32 recompute on overflow)",
+                "data": "synthetic", "config": cfg, "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
                 "roofline": roofline, "engine": {k: st[k] for k in ("tiles", "tiles_by_group", "last_k",
                                                                     "recomputed_tiles", "sm_count")},
-                "topk_merge_ok": top_ok, "sample_parity_ok": sample_ok}
+                "topk_merge_ok": top_ok, "topk_check": top_desc, "sample_parity_ok": sample_ok,
+                "sample_parity": sample_desc}
         if not args.no_cpu and world == 1:  # the CPU baseline is reported at N = 1 only
             names_t, qtexts = load_queries(None)
             kept = []
@@ -490,15 +654,18 @@ def main():
             # the oracle's scores of that sample double as a parity check of the measured configuration (full-size
             # database, the engine's own choice of group_len and K): every query, every sampled sequence, bit-exact
             try:
-                if args.workload == "config2" and not args.synth_queries and not args.affine and e2e_times:
-                    line["sample_parity_ok"] = bool(all(
-                        np.array_equal(out[qi][0::stride], want) for qi, (stride, want) in enumerate(kept)))
-                    line["sample_parity"] = "oracle vs GPU scores, every %d-th sequence x %d queries" % (
-                        kept[0][0], len(kept))
+                line["sample_parity_ok"] = bool(all(
+                    np.array_equal(out[local_of[qi]][0::stride], want) for qi, (stride, want) in enumerate(kept)))
+                line["sample_parity"] = "oracle vs GPU scores, every %d-th sequence x %d queries" % (kept[0][0], len(kept))
             except Exception as ex:  # never lose the bench line to the checker
                 line["sample_parity"] = "check failed to run: %r" % (ex,)
         else:
             line["cpu_baseline"] = None
+        if not args.no_ref_cuda and world == 1:
+            try:
+                line["ref_cuda_baseline"] = ref_cuda_leg(["P02232", "P01008", "P27895"])
+            except Exception as ex:
+                line["ref_cuda_baseline"] = {"unavailable": repr(ex)}
         if args.per_query:
             pq = {}
             for nme, q in zip(names, qs):
@@ -512,6 +679,61 @@ def main():
     eng.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_group(args, swb, codes, offsets, qs, total_cells):
+    """--group: ONE process, every device behind the engine group (what the C++ drop-in uses). Device time = the
+    slowest device's CUDA-event time per step (swb_group_stats), wall clock beside it."""
+    g = swb.EngineGroup(args.gpus)
+    if args.db_parts:
+        g.set_option("db_parts", args.db_parts)
+    big = args.workload == "config5"
+    qcodes, qoffs = swb.pack_sequences(qs)
+    t0 = time.perf_counter()
+    g.db_load(codes, offsets)
+    out = None if big else np.zeros((len(qs), len(offsets) - 1), dtype=np.int32)
+
+    def step():
+        if big:
+            return g.search_batch_topk(qcodes, qoffs, args.topk)
+        return g.search_batch_packed(qcodes, qoffs, out=out)
+
+    step()
+    cold_s = time.perf_counter() - t0
+    for _ in range(max(0, args.warmup - 1)):
+        step()
+    dev_ms, wall = 0.0, time.perf_counter()
+    launches = 0
+    for _ in range(args.steps):
+        step()
+        s = g.stats()
+        dev_ms += s["device_ms"]
+        launches += s["kernel_launches"]
+    wall = time.perf_counter() - wall
+    ok = None
+    if not big:
+        from oracle_lib import Oracle
+        o = Oracle()
+        stride = 997
+        m = o.matrix("blosum50")
+        ok = all(np.array_equal(out[qi][0::stride], o.scan(qs[qi], codes, offsets, m, 2, 0, stride, host_threads())[0::stride])
+                 for qi in range(0, len(qs), max(1, len(qs) // 4)))
+    t1 = time.perf_counter()
+    g.db_load(codes, offsets)
+    step()
+    e2e_s = time.perf_counter() - t1
+    cfg = workload_config(offsets, qs, args)
+    cfg["layout"] = {"db_parts": g.db_parts(), "query_groups": g.size() // max(1, g.db_parts()), "process": "single (engine group)"}
+    line = {"metric": METRIC, "value": total_cells / (dev_ms / args.steps * 1e-3) * 1e-9, "unit": "GCUPS",
+            "n_gpus": g.size(), "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+            "wall_ms_per_step": wall / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "s16x2 (exact rebased-s16 / int32 recompute on overflow)", "data": "synthetic", "config": cfg,
+            "e2e": {"value": total_cells / e2e_s * 1e-9, "unit": "GCUPS", "seconds_per_step": e2e_s,
+                    "cold": {"value": total_cells / cold_s * 1e-9, "seconds_per_step": cold_s},
+                    "api": "swb_group_db_load + swb_group_search_batch%s (host buffers, one process)" % ("_topk" if big else "")},
+            "gpu_launches": launches, "sample_parity_ok": ok, "mode": "engine group, one process"}
+    print(json.dumps(line))
+    g.close()
 
 
 if __name__ == "__main__":

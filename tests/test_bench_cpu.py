@@ -60,3 +60,45 @@ def test_workload_config_names_the_workload():
     for wl in ("config2", "config4", "config5"):
         cfg = bench.workload_config(offsets, [np.zeros(5, np.uint8)], argparse.Namespace(workload=wl, scale=1.0, affine=""))
         assert "workload" in cfg and "model" not in cfg and cfg["db_sequences"] == len(offsets) - 1
+
+
+def test_reference_arm_uses_every_core_under_torchrun(monkeypatch):
+    """torchrun exports OMP_NUM_THREADS=1; the CPU legs must not inherit that (round-1 SCALE lines compared against a
+    one-core reference arm)"""
+    monkeypatch.setenv("OMP_NUM_THREADS", "1")
+    assert bench.host_threads() == len(os.sched_getaffinity(0))
+    codes, offsets = bench.synth_db(scale=0.002)
+    names, qtexts = bench.load_queries(None)
+    cb, _ = bench.cpu_sample_gcups(codes, offsets, names, qtexts[:1], 0.01)
+    assert cb["cores"] == bench.host_threads() and ("%d threads" % cb["cores"]) in cb["sample"]
+
+
+class _FakeEngine:
+    """stands in for the CUDA engine in the host-side parity helper: scores come from the oracle, one entry is
+    optionally corrupted"""
+
+    def __init__(self, oracle, codes, offsets, ids, queries, corrupt=False):
+        self.ids = ids
+        m = oracle.matrix("blosum50")
+        self.rows = [oracle.scan(q, codes, offsets, m)[ids] for q in queries]
+        if corrupt:
+            self.rows[-1][0] += 1
+
+    def db_ids(self):
+        return self.ids
+
+
+def test_per_rank_sample_parity_helper(oracle):
+    import importlib
+    swb = importlib.import_module("ece1782-smith-waterman-cuda_b200")
+    codes, offsets = bench.synth_db(scale=0.003)
+    n = len(offsets) - 1
+    _, _, ids = swb.plan_describe(offsets, 1, 2, want_ids=True)
+    rng = np.random.default_rng(0)
+    qs = {3: rng.integers(0, 20, 50).astype(np.uint8), 7: rng.integers(0, 20, 120).astype(np.uint8)}
+    local_of = {3: 0, 7: 1}
+    for corrupt in (False, True):
+        eng = _FakeEngine(oracle, codes, offsets, ids, list(qs.values()), corrupt)
+        ok, desc = bench.sample_parity(swb, eng, codes, offsets, qs, local_of, lambda k: eng.rows[k], 2, 0.0001)
+        assert ok == (not corrupt) and "every" in desc
+    assert len(ids) < n

@@ -6,6 +6,7 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#include <setjmp.h>
 #include <ucontext.h>
 #include <algorithm>
 #include <vector>
@@ -70,7 +71,15 @@ struct WarpSim {
     LaneFn fn;
     void *arg;
 
-    void yield() { swapcontext(&ctx[current], &sched); }
+    // Fibers are created with makecontext, but every later switch goes through _setjmp / _longjmp: swapcontext saves
+    // and restores the signal mask with a system call per switch, which dominated the emulation time.
+    jmp_buf sched_jb;
+    jmp_buf lane_jb[32];
+    bool started[32];
+    void yield()
+    {
+        if (!_setjmp(lane_jb[current])) _longjmp(sched_jb, 1);
+    }
     // all 32 lanes deposit, then all continue (lock-step point of a *_sync intrinsic)
     void rendezvous(int lane, uint32_t v)
     {
@@ -91,7 +100,7 @@ struct WarpSim {
         be.lane_id = w->current;
         w->fn(be, w->arg);
         w->done[be.lane_id] = true;
-        swapcontext(&w->ctx[be.lane_id], &w->sched);
+        _longjmp(w->sched_jb, 1);
     }
     void run(LaneFn f, void *a)
     {
@@ -102,6 +111,7 @@ struct WarpSim {
         for (int l = 0; l < 32; ++l) {
             stacks[l].resize(512 * 1024);
             done[l] = false;
+            started[l] = false;
             getcontext(&ctx[l]);
             ctx[l].uc_stack.ss_sp = stacks[l].data();
             ctx[l].uc_stack.ss_size = stacks[l].size();
@@ -115,7 +125,14 @@ struct WarpSim {
                 if (done[l]) continue;
                 alive = true;
                 current = l;
-                swapcontext(&sched, &ctx[l]);
+                if (!_setjmp(sched_jb)) {
+                    if (started[l]) {
+                        _longjmp(lane_jb[l], 1);
+                    } else {
+                        started[l] = true;
+                        setcontext(&ctx[l]);
+                    }
+                }
             }
             if (!alive) break;
         }

@@ -245,30 +245,38 @@ def test_pipelined_passes_every_lane_group_class(emu, oracle):
 
 def test_rebased_s16_is_exact_far_beyond_the_s16_range(emu, oracle):
     """V16R (s16x2 relative to a base that follows the columns): the exact pass over every tile and the "direct" path
-    for long-against-long tiles, with true scores of 150,000 (ten thousand W-W matches at 15), several blocks per
-    pass, several passes per tile, pairs of very different length, one lane per pair up to 32 lanes per pair"""
+    for long-against-long tiles, with true scores of 66,000 (4,400 W-W matches at 15: beyond even an unsigned 16-bit
+    range; the GPU suite repeats this at 151,500), several blocks per pass, several passes per tile, pairs of very
+    different length, one lane per pair up to 32 lanes per pair"""
     m = oracle.matrix("blosum50")
     rng = np.random.default_rng(5)
-    w = np.full(10000, 17, dtype=np.uint8)  # W: 15 per match
+    w = np.full(4400, 17, dtype=np.uint8)  # W: 15 per match
     noisy = w.copy()
-    noisy[rng.choice(len(w), 600, replace=False)] = rng.integers(0, 20, 600)
-    enc = [w, noisy, w[:9000].copy(), rng.integers(0, 20, 4000).astype(np.uint8), w[:700].copy(),
-           rng.integers(0, 20, 90).astype(np.uint8), np.zeros(0, np.uint8)]
-    codes, offs = pack_db(enc)
+    noisy[rng.choice(len(w), 300, replace=False)] = rng.integers(0, 20, 300)
+    small = [rng.integers(0, 20, 1800).astype(np.uint8), w[:700].copy(), rng.integers(0, 20, 90).astype(np.uint8),
+             np.zeros(0, np.uint8)]
+    codes, offs = pack_db([w, noisy] + small)
     want = oracle.scan(w, codes, offs, m)
-    assert want[0] == 150000 and want[2] == 135000 and want[1] > 100000
+    assert want[0] == 66000 and want[1] > 45000
     # direct: the long tiles never see the plain s16 pass (nothing is flagged there); the short ones go the normal way
-    got, rc = emu(codes, offs, m, w, K=0, group_len=128, xl_len=2000, split_k=16, direct_len=3000)
+    got, rc = emu(codes, offs, m, w, K=0, group_len=128, xl_len=1000, split_k=16, direct_len=1500, rebase_shift=8)
     assert np.array_equal(got, want)
     # flagged -> rebased recompute, pipelined (split_k 8) and not (xl_len 0), small blocks
-    got, rc = emu(codes, offs, m, w[:4000], K=0, group_len=128, xl_len=2000, split_k=8, rebase_shift=7)
-    assert np.array_equal(got, oracle.scan(w[:4000], codes, offs, m)) and rc >= 2
-    got, rc = emu(codes, offs, m, w[:4000], K=0, group_len=512, xl_len=0, rebase_shift=6)
-    assert np.array_equal(got, oracle.scan(w[:4000], codes, offs, m)) and rc >= 2
+    q = w[:2400]
+    codes, offs = pack_db([q.copy(), noisy[:2300].copy()] + small)
+    wq = oracle.scan(q, codes, offs, m)
+    assert wq.max() == 36000
+    got, rc = emu(codes, offs, m, q, K=0, group_len=128, xl_len=1000, split_k=8, rebase_shift=7)
+    assert np.array_equal(got, wq) and rc >= 1
+    got, rc = emu(codes, offs, m, q, K=0, group_len=512, xl_len=0, rebase_shift=6)
+    assert np.array_equal(got, wq) and rc >= 1
     # one lane per pair through the rebased policy (its G = 1 case): group_len above every sequence
-    q = w[:3000]
-    got, rc = emu(codes[:int(offs[5])], offs[:6], m, q, K=0, group_len=16384, xl_len=0, force_i32=1, rebase_shift=8)
-    assert np.array_equal(got, oracle.scan(q, codes[:int(offs[5])], offs[:6], m))
+    c3, o3 = pack_db(small)
+    got, rc = emu(c3, o3, m, q, K=0, group_len=16384, xl_len=0, force_i32=1, rebase_shift=8)
+    assert np.array_equal(got, oracle.scan(q, c3, o3, m))
+    c1, o1 = pack_db([w[:2400].copy(), w[:2300].copy()])
+    got, rc = emu(c1, o1, m, q, K=0, group_len=16384, xl_len=0, rebase_shift=6)  # flagged one-lane tile -> V16R
+    assert np.array_equal(got, oracle.scan(q, c1, o1, m)) and got[0] == 36000 and rc == 1
 
 
 def test_rebased_s16_random_and_ident3(emu, oracle):

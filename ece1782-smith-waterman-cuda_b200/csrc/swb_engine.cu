@@ -95,6 +95,7 @@ struct swb_engine {
     bool group_len_auto = true;  // swb_db_load picks group_len from the shard size (below) unless the option sets it
     int opt_batch_order = 0;  // batches: 0 = longest query first, 1 = in the caller's order
     int rebase_shift = 0;     // V16R block size for the current scoring scheme (0: V16R cannot run, exact passes use V32)
+    int rebase_shift32 = 0;   // the same for passes of 32 rows per lane (pipelined groups with split_k = 32)
     int opt_exact = 0;        // exact passes: 0 = V16R where the scheme allows it, 1 = always V32 (int32)
     int opt_split_k = 0;      // rows per lane of the pipelined-pass groups: 0 = auto, 8, 16
     uint32_t opt_direct_len = 10000;  // pipelined tiles at least this wide against queries at least this long skip the
@@ -352,7 +353,7 @@ extern "C" int swb_set_option(swb_engine *e, const char *key, int64_t value)
         if (value < 0 || value > 1) return fail(e, SWB_ERR_ARG, "exact must be 0 (rebased s16 where possible) or 1 (int32)");
         e->opt_exact = (int)value;
     } else if (!strcmp(key, "split_k")) {
-        if (value != 0 && value != 8 && value != 16) return fail(e, SWB_ERR_ARG, "split_k must be 0, 8 or 16");
+        if (value != 0 && value != 8 && value != 16 && value != 32) return fail(e, SWB_ERR_ARG, "split_k must be 0, 8, 16 or 32");
         e->opt_split_k = (int)value;
     } else if (!strcmp(key, "direct_len")) {
         if (value < 0 || value > (1ll << 31)) return fail(e, SWB_ERR_ARG, "direct_len out of range");
@@ -411,6 +412,7 @@ extern "C" int swb_set_scoring_affine(swb_engine *e, const int8_t *matrix, int a
     e->max_s = mx;
     e->min_s = mn;
     e->rebase_shift = e->affine ? 0 : swb_rebase_shift(mx, mn, gap, 16u * 32u);
+    e->rebase_shift32 = e->affine ? 0 : swb_rebase_shift(mx, mn, gap, 32u * 32u);
     CU(cudaMemcpy(e->d_mat, e->h_mat, sizeof m, cudaMemcpyHostToDevice));
     e->scoring_set = true;
     return SWB_OK;
@@ -517,13 +519,15 @@ int swb_db_load_sorted(swb_engine *e, const uint8_t *codes, const uint64_t *offs
     e->last_nq = 0;  // results of the previous database are gone (swb_fetch_scores must not index the new shard with them)
     // group_len (longest sequence that runs one lane per pair). One-lane tiles are the cheapest per cell (no shuffles,
     // conflict-free profile reads, least row padding), so a shard with plenty of tiles wants them for as many sequences
-    // as possible: measured on the benchmark database, 384 / 768 / 1536 give 8,830 / 9,094 / 9,108 GCUPS (20 reference
-    // queries) and 8,234 / 8,614 / 8,745 (150 short queries). A small shard is the opposite case: with about as many
-    // tiles as warp slots, the long one-lane tiles become its critical path (1/8 of the database: 7,234 with 768 against
-    // 8,312 with 384).
+    // as possible; a small shard is the opposite case: with about as many tiles as warp slots, long one-lane tiles
+    // become its critical path. Measured on fractions of the benchmark database, 20 reference queries, GCUPS for
+    // group_len 384 / 768 / 1536 (profiles/r2a_sweep_group_len.txt):
+    //   570 k sequences 8,868 / 9,115 / 9,153     285 k  8,834 / 8,960 / 8,882
+    //   142 k           8,709 / 8,792 / 8,358      71 k  8,384 / 7,616 / 5,403
     if (e->group_len_auto) {
         const uint64_t slots = (uint64_t)e->sm_count * (SWB_NT_LARGE / 32);
-        e->plan_opts.group_len = (uint64_t)(n / nshards) / 64u >= 2u * slots ? 1536u : 384u;
+        const uint64_t tiles64 = (uint64_t)(n / nshards) / 64u;  // one-lane tiles the shard would have
+        e->plan_opts.group_len = tiles64 >= 3u * slots ? 1536u : (4u * tiles64 >= 3u * slots ? 768u : 384u);
     }
     // An unsharded load uploads the caller's buffer as it is, which does not need the plan: the plan (length sort, tiling;
     // ~20 ms for Swiss-Prot) is built on a helper thread while this one stages and uploads the residues.
@@ -645,7 +649,7 @@ static int shape_for(swb_engine *e, int K, int mode, bool split, uint32_t smem_r
     const bool per_item = split;  // one warp per block, each work item stages the rows of its pass
     if (per_item) smem_rows = (uint32_t)K * 32u;
     ls.smem_rows = smem_rows;
-    ls.smem = (size_t)SWB_ALPHA * (smem_rows + 4);
+    ls.smem = (size_t)SWB_ALPHA * (smem_rows + (split ? 16 : 4));  // row stride as in swb_score_kernel
     if (ls.smem > e->smem_optin) return fail(e, SWB_ERR_ARG, "internal: query chunk does not fit shared memory");
     ls.block_cfg = ls.smem <= SWB_SMALL_SMEM_LIMIT ? SWB_BLOCK_SMALL : SWB_BLOCK_LARGE;
     int per_sm = 0;
@@ -730,6 +734,7 @@ static int enqueue_pass(swb_engine *e, Slot &s, int mode, SwbScoreParams &p, con
             if (rc != SWB_OK) return rc;
             p.row0 = ch.row0;
             p.rows = ch.rows;
+            p.rebase_shift = (uint32_t)(g.K > 16 ? e->rebase_shift32 : e->rebase_shift);
             p.smem_rows = ls.smem_rows;
             p.warps_active = ls.warps_active;
             p.first_chunk = ch.first;
@@ -799,6 +804,7 @@ static int enqueue_job(swb_engine *e, Slot &s, uint32_t qi, const uint8_t *q, ui
     // rows per lane of the split groups: 16 when that still leaves more work items than one-warp blocks fit on the GPU
     // (13 per SM with 16.5 KB of staged rows each), else 8 (twice the passes in flight per tile)
     auto pick_split_k = [&](const uint32_t *cnt) {
+        if (e->opt_split_k == 32 && r16 && !e->rebase_shift32) return 16;
         if (e->opt_split_k) return e->opt_split_k;
         uint64_t items16 = 0;
         for (int l = 1; l <= SWB_MAX_LOGG; ++l) items16 += (uint64_t)cnt[l] * swb_split_passes(rows, l, 16);
@@ -828,7 +834,7 @@ static int enqueue_job(swb_engine *e, Slot &s, uint32_t qi, const uint8_t *q, ui
         swb_plan_query(qlen, e->opt_k, affine ? 8 : 16, present, chunk_rows, qp1);
         prof8_rows = std::max(prof8_rows, qp1.prof_rows);
     }
-    if (split) prof8_rows = std::max(prof8_rows, swb_roundup(rows, 16u << SWB_MAX_LOGG));  // the last pass of a split item
+    if (split) prof8_rows = std::max(prof8_rows, swb_roundup(rows, 32u << SWB_MAX_LOGG));  // the last pass of a split item
     if (need_i32) {
         if (n_rest) {
             SwbLaunchGroup g;

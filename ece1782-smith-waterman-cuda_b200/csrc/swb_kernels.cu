@@ -24,11 +24,13 @@ struct DevBackend {
     }
     __device__ __forceinline__ void count(uint32_t *p) const { atomicAdd(p, 1u); }
     __device__ __forceinline__ void atomic_max(int32_t *p, int32_t v) const { atomicMax(p, v); }
-    // progress counters of SPLIT launches: publish after the boundary stores are visible, poll with a volatile load
+    // progress counters of SPLIT launches. The boundary stores of all lanes are ordered before the publishing lane's
+    // release store by the __syncwarp the caller executes first (barrier synchronisation is part of causality order,
+    // and a release is cumulative); the reader polls with acquire loads, so what it reads afterwards is at least as
+    // new. No full fence (MEMBAR.SC + cache invalidate) on either side.
     __device__ __forceinline__ void publish(uint32_t *p, uint32_t v) const
     {
-        __threadfence();
-        *reinterpret_cast<volatile uint32_t *>(p) = v;
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
     }
     // SPLIT launches: the warp copies `rows` profile rows of all 32 codes into its block's shared memory
     __device__ __forceinline__ void stage_rows(int8_t *dst, uint32_t dstride, const int8_t *prof, uint32_t pstride,
@@ -45,12 +47,12 @@ struct DevBackend {
     }
     __device__ __forceinline__ uint32_t wait_progress(const uint32_t *p, uint32_t need) const
     {
-        uint32_t v = *reinterpret_cast<const volatile uint32_t *>(p);
+        uint32_t v;
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
         while (v < need) {
-            __nanosleep(256);
-            v = *reinterpret_cast<const volatile uint32_t *>(p);
+            __nanosleep(128);
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
         }
-        __threadfence();
         return v;
     }
     __device__ __forceinline__ uint8_t ld_flag(const uint8_t *p) const { return __ldcg(p); }
@@ -81,7 +83,9 @@ template <int K, class V, int NT, int MINB, bool SPLIT>
 __global__ void __launch_bounds__(NT, MINB) swb_score_kernel(const SwbScoreParams p)
 {
     extern __shared__ __align__(16) int8_t sprof[];
-    const uint32_t sstride = p.smem_rows + 4u;
+    // code rows one bank apart (+4) for the word loads of the bulk kernels; SPLIT kernels (one warp per block, mostly
+    // one pair per warp: every lane reads the same code's row at its own offset) keep them 16-byte aligned for LDS.128
+    const uint32_t sstride = p.smem_rows + (SPLIT ? 16u : 4u);
     if (!SPLIT) {  // SPLIT: every work item stages the rows of its own pass (swb_warp_loop)
         const uint32_t wpr = p.smem_rows >> 2;  // words per code row
         for (uint32_t i = threadIdx.x; i < wpr * SWB_ALPHA; i += NT) {
@@ -218,6 +222,13 @@ static cudaError_t dispatch(int op, int K, int mode, bool split, int block_cfg, 
                                : occ_one<16, V16R, 32, 13, true>(smem, blocks);
             return op == 0 ? launch_one<16, V16, 32, 13, true>(*p, grid, smem, st)
                            : occ_one<16, V16, 32, 13, true>(smem, blocks);
+        }
+        if (K == 32 && !i32) {  // 33 KB of staged rows per work item: 6 blocks per SM
+            if (r16)
+                return op == 0 ? launch_one<32, V16R, 32, 6, true>(*p, grid, smem, st)
+                               : occ_one<32, V16R, 32, 6, true>(smem, blocks);
+            return op == 0 ? launch_one<32, V16, 32, 6, true>(*p, grid, smem, st)
+                           : occ_one<32, V16, 32, 6, true>(smem, blocks);
         }
         return cudaErrorInvalidValue;
     }

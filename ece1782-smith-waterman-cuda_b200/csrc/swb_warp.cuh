@@ -79,6 +79,20 @@ struct V16Base {
     }
     static SWB_HD int lo(T v) { return (int)(int16_t)(v & 0xffffu); }
     static SWB_HD int hi(T v) { return (int)(int16_t)(v >> 16); }
+    // LDW bytes of a profile row (4 rows per word): one LDS.32 / LDS.64 / LDS.128; the wide forms need rows that start
+    // on LDW-byte boundaries (the SPLIT kernels stage theirs that way)
+    template <int LDW> static SWB_HD void ld_prof(const uint32_t *p, uint32_t (&w)[LDW / 4])
+    {
+        if constexpr (LDW == 16) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(p);
+            w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+        } else if constexpr (LDW == 8) {
+            const uint2 v = *reinterpret_cast<const uint2 *>(p);
+            w[0] = v.x; w[1] = v.y;
+        } else {
+            w[0] = *p;
+        }
+    }
     // profile byte I (0..3) of the A word and of the B word, sign-extended into one s16x2
     template <int I> static SWB_HD T pair(uint32_t wa, uint32_t wb) { return swb_prmt(wa, wb, 0xC480u + 0x1111u * I); }
     template <class BE> static SWB_HD T shfl_up(BE &be, T v, int d, int w) { return be.shfl_up(v, d, w); }
@@ -108,7 +122,7 @@ struct V16 : V16Base {
     static SWB_HD int score_lo(T best, const C &) { return lo(best); }
     static SWB_HD int score_hi(T best, const C &) { return hi(best); }
     // one DB column against the K rows of this lane; returns the bottom H
-    template <int K>
+    template <int K, int LDW>
     static SWB_HD T column(T up, T &diag0, T (&left)[K], T &best, const C &cst, uint32_t codeA, uint32_t codeB,
                            const int8_t *prow, uint32_t sstride)
     {
@@ -118,10 +132,15 @@ struct V16 : V16Base {
         T dg = diag0;
         diag0 = add(up, cst.negg);
 #pragma unroll
-        for (int k4 = 0; k4 < K / 4; ++k4) {
-            const uint32_t wa = ra[k4];
-            const uint32_t wb = rb[k4];
-            T c[4];
+        for (int kw = 0; kw < K / 4; kw += LDW / 4) {
+            uint32_t wva[LDW / 4], wvb[LDW / 4];
+            ld_prof<LDW>(ra + kw, wva);
+            ld_prof<LDW>(rb + kw, wvb);
+#pragma unroll
+            for (int j = 0; j < LDW / 4; ++j) {
+                const int k4 = kw + j;
+                const uint32_t wa = wva[j], wb = wvb[j];
+                T c[4];
 #define SWB_CELL(I)                                                        \
     {                                                                      \
         const T s = pair<I>(wa, wb);                                       \
@@ -130,11 +149,12 @@ struct V16 : V16Base {
         h = __viaddmax_s16x2(h, cst.negg, c[I]);                           \
         left[4 * k4 + I] = add(h, cst.negg);                               \
     }
-            SWB_CELL(0) SWB_CELL(1)
-            best = __vimax3_s16x2(best, c[0], c[1]);
-            SWB_CELL(2) SWB_CELL(3)
-            best = __vimax3_s16x2(best, c[2], c[3]);
+                SWB_CELL(0) SWB_CELL(1)
+                best = __vimax3_s16x2(best, c[0], c[1]);
+                SWB_CELL(2) SWB_CELL(3)
+                best = __vimax3_s16x2(best, c[2], c[3]);
 #undef SWB_CELL
+            }
         }
         return h;
     }
@@ -212,7 +232,7 @@ struct V16R : V16Base {
         for (int k = 0; k < K; ++k) left[k] = sub(left[k], d);
         diag0 = sub(diag0, d);
     }
-    template <int K>
+    template <int K, int LDW>
     static SWB_HD T column(T up, T &diag0, T (&left)[K], T &best, const C &cst, uint32_t codeA, uint32_t codeB,
                            const int8_t *prow, uint32_t sstride)
     {
@@ -222,10 +242,15 @@ struct V16R : V16Base {
         T dg = diag0;
         diag0 = __viaddmax_s16x2(up, cst.negg, cst.fl);
 #pragma unroll
-        for (int k4 = 0; k4 < K / 4; ++k4) {
-            const uint32_t wa = ra[k4];
-            const uint32_t wb = rb[k4];
-            T c[4];
+        for (int kw = 0; kw < K / 4; kw += LDW / 4) {
+            uint32_t wva[LDW / 4], wvb[LDW / 4];
+            ld_prof<LDW>(ra + kw, wva);
+            ld_prof<LDW>(rb + kw, wvb);
+#pragma unroll
+            for (int j = 0; j < LDW / 4; ++j) {
+                const int k4 = kw + j;
+                const uint32_t wa = wva[j], wb = wvb[j];
+                T c[4];
 #define SWB_CELL(I)                                                        \
     {                                                                      \
         const T s = pair<I>(wa, wb);                                       \
@@ -234,11 +259,12 @@ struct V16R : V16Base {
         h = __viaddmax_s16x2(h, cst.negg, c[I]);                           \
         left[4 * k4 + I] = __viaddmax_s16x2(h, cst.negg, cst.fl);          \
     }
-            SWB_CELL(0) SWB_CELL(1)
-            best = __vimax3_s16x2(best, c[0], c[1]);
-            SWB_CELL(2) SWB_CELL(3)
-            best = __vimax3_s16x2(best, c[2], c[3]);
+                SWB_CELL(0) SWB_CELL(1)
+                best = __vimax3_s16x2(best, c[0], c[1]);
+                SWB_CELL(2) SWB_CELL(3)
+                best = __vimax3_s16x2(best, c[2], c[3]);
 #undef SWB_CELL
+            }
         }
         return h;
     }
@@ -259,7 +285,7 @@ struct V32 {
     static SWB_HD int score_lo(T best, const C &) { return best.a; }
     static SWB_HD int score_hi(T best, const C &) { return best.b; }
     static SWB_HD T max2(T a, T b) { return mk(mx(a.a, b.a), mx(a.b, b.b)); }
-    template <int K>
+    template <int K, int LDW>  // LDW (bytes per profile load) is a hint of the s16 policies: this one loads words
     static SWB_HD T column(T up, T &diag0, T (&left)[K], T &best, const C &cst, uint32_t codeA, uint32_t codeB,
                            const int8_t *prow, uint32_t sstride)
     {
@@ -343,7 +369,7 @@ struct V16A {
     static SWB_HD int score_lo(T best, const C &) { return V16Base::lo(best.h); }
     static SWB_HD int score_hi(T best, const C &) { return V16Base::hi(best.h); }
     static SWB_HD T max2(T a, T b) { return mk(V16Base::max2(a.h, b.h), a.f); }
-    template <int K>
+    template <int K, int LDW>  // LDW (bytes per profile load) is a hint of the s16 policies: this one loads words
     static SWB_HD T column(T up, T &diag0, T (&left)[K], T &best, const C &cst, uint32_t codeA, uint32_t codeB,
                            const int8_t *prow, uint32_t sstride)
     {
@@ -423,7 +449,7 @@ struct V32A {
     static SWB_HD int score_lo(T best, const C &) { return best.ha; }
     static SWB_HD int score_hi(T best, const C &) { return best.hb; }
     static SWB_HD T max2(T a, T b) { return mk(mx(a.ha, b.ha), mx(a.hb, b.hb), a.fa, a.fb); }
-    template <int K>
+    template <int K, int LDW>  // LDW (bytes per profile load) is a hint of the s16 policies: this one loads words
     static SWB_HD T column(T up, T &diag0, T (&left)[K], T &best, const C &cst, uint32_t codeA, uint32_t codeB,
                            const int8_t *prow, uint32_t sstride)
     {
@@ -495,7 +521,8 @@ struct V32A {
 // Boundary scratch layout (elements of V::T, base tile.bnd_off), values in the policy's h domain:
 //   G == 1 : [chunk c][lane][4 columns]   -> one 16/32-byte vector per lane and chunk
 //   G  > 1 : [slot][column]               -> the first lane of a group reads 4 columns as one vector, the last lane
-//                                            writes scalars (its columns lag G-1 behind, so they are not 4-aligned)
+//                                            writes 4 columns as one vector (every lane lags one chunk behind the
+//                                            lane above)
 //
 // SPLIT (32-lane tiles of very long sequences only): the passes of one tile are separate work items taken by different
 // warps, which run as a pipeline over the columns. The warp of pass ss publishes how many columns of its bottom row are
@@ -523,13 +550,12 @@ SWB_HD void swb_run_tile(BE &be, const SwbScoreParams &p, const SwbTile &tile, u
     const bool tail = (g == G - 1);
     const uint32_t rows_per_super = (uint32_t)K << logG;
     const uint32_t nsuper = (p.rows + rows_per_super - 1) / rows_per_super;
-    const uint32_t nsteps4 = GROUPED ? ((W + (uint32_t)G - 1u + 3u) >> 2) : nchunks;
     const uint8_t *res = p.residues + tile.res_off + (size_t)slot * 8u;
     const size_t res_stride = (size_t)P * 8u;
     T *bnd = reinterpret_cast<T *>(p.bnd) + tile.bnd_off;
     T best = V::hzero(cst);
     // V16R: base log of the boundary rows, [pass parity][slot][block] (see swb_blog_*)
-    const uint32_t cbmask = V::rebased ? (1u << p.rebase_shift) - 1u : 0u;
+    const uint32_t cbmask = V::rebased ? (1u << (p.rebase_shift - 2u)) - 1u : 0u;  // chunks per rebase block - 1
     const uint32_t blog_nb = V::rebased ? (W >> p.rebase_shift) + 2u : 0u;
     const size_t blog_par = ((size_t)W * (size_t)P >> 6) + 33u;
     uint2 *blog = V::rebased ? reinterpret_cast<uint2 *>(p.blog) + swb_blog_offset(tile.bnd_off, tile_idx) : nullptr;
@@ -547,143 +573,161 @@ SWB_HD void swb_run_tile(BE &be, const SwbScoreParams &p, const SwbTile &tile, u
 #pragma unroll
         for (int k = 0; k < K; ++k) left[k] = LZERO;
         T diag0 = LZERO;
-        T hprev = V::hzero(cst);
-        uint32_t aprev = SWB_PAD, bprev = SWB_PAD;
-        // V16R: this lane's column, the base difference to the row above, the amount of the latest rebase
-        int colg = -g;
-        T dconv = T(), dcur = T();
-        uint2 *blog_rd = nullptr, *blog_wr = nullptr;
-        if constexpr (V::rebased) {
-            blog_wr = blog + (size_t)((pass0 + ss) & 1u) * blog_par + (size_t)slot * blog_nb;
-            blog_rd = blog + (size_t)((pass0 + ss + 1u) & 1u) * blog_par + (size_t)slot * blog_nb;
-        }
-
-        // residue codes of the current chunk (4 columns x two sequences), fetched by the lead lane with byte loads:
-        // the codes arrive zero-extended in registers, so no ALU-pipe instruction is spent on unpacking them
         uint32_t ca[4], cb[4];
         T bc[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            ca[u] = SWB_PAD;
-            cb[u] = SWB_PAD;
-            bc[u] = V::hzero(cst);
-        }
+        for (int u = 0; u < 4; ++u) bc[u] = V::hzero(cst);
         bool top_cur = nchunks > 0 && read_top;  // bc holds values of the row above (uniform over the warp)
-        if (lead && nchunks > 0) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                ca[u] = be.ld_code(res + 2 * u);
-                cb[u] = be.ld_code(res + 2 * u + 1);
-            }
-        }
         if (wait_top) {
             const uint32_t need = W < 4u ? W : 4u;
             avail = be.wait_progress(prog + ss - 1, need);
         }
-        if (lead && nchunks > 0 && read_top) {
-            if (!GROUPED) {
-                V::ld4(be, bnd + (size_t)lane * 4u, bc);
-            } else {
-                V::ld4(be, bnd + (size_t)slot * W, bc);
-            }
-        }
-        for (uint32_t c = 0; c < nsteps4; ++c) {
-            // prefetch the next chunk of residues and of the top boundary row
-            uint32_t na[4], nb[4];
-            T bn[4];
+
+        if constexpr (!GROUPED) {
+            // One lane per pair: no exchange between lanes. Residue codes of a chunk (4 columns x two sequences) come
+            // as byte loads: zero-extended in registers, no ALU-pipe instruction is spent on unpacking them.
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                na[u] = SWB_PAD;
-                nb[u] = SWB_PAD;
-                bn[u] = V::hzero(cst);
+                ca[u] = nchunks > 0 ? be.ld_code(res + 2 * u) : (uint32_t)SWB_PAD;
+                cb[u] = nchunks > 0 ? be.ld_code(res + 2 * u + 1) : (uint32_t)SWB_PAD;
             }
-            const bool top_next = c + 1 < nchunks && read_top;
-            if (wait_top && c + 1 < nchunks) {
-                const uint32_t need = 4u * c + 8u < W ? 4u * c + 8u : W;
-                if (avail < need) avail = be.wait_progress(prog + ss - 1, need);
-            }
-            if (lead && c + 1 < nchunks) {
-                const uint8_t *rnext = res + (size_t)(c + 1) * res_stride;
+            if (nchunks > 0 && read_top) V::ld4(be, bnd + (size_t)lane * 4u, bc);
+            for (uint32_t c = 0; c < nchunks; ++c) {
+                // prefetch the next chunk of residues and of the top boundary row
+                uint32_t na[4], nb[4];
+                T bn[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    na[u] = be.ld_code(rnext + 2 * u);
-                    nb[u] = be.ld_code(rnext + 2 * u + 1);
+                    na[u] = SWB_PAD;
+                    nb[u] = SWB_PAD;
+                    bn[u] = V::hzero(cst);
                 }
-                if (read_top) {
-                    if (!GROUPED) {
-                        V::ld4(be, bnd + ((size_t)(c + 1) * 32u + lane) * 4u, bn);
-                    } else {
-                        V::ld4(be, bnd + (size_t)slot * W + (size_t)(c + 1) * 4u, bn);
+                if (c + 1 < nchunks) {
+                    const uint8_t *rnext = res + (size_t)(c + 1) * res_stride;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        na[u] = be.ld_code(rnext + 2 * u);
+                        nb[u] = be.ld_code(rnext + 2 * u + 1);
                     }
+                    if (read_top) V::ld4(be, bnd + ((size_t)(c + 1) * 32u + lane) * 4u, bn);
+                }
+                T outb[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    outb[u] = V::template column<K, 4>(bc[u], diag0, left, best, cst, ca[u], cb[u], prow, sstride);
+                if (write_bot) V::st4(be, bnd + ((size_t)c * 32u + lane) * 4u, outb);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    ca[u] = na[u];
+                    cb[u] = nb[u];
+                    bc[u] = bn[u];
                 }
             }
-            T outb[4];
+        } else {
+            // Lane-group wavefront, one chunk (4 columns) per lane and step: at step c lane g works on chunk c - g. Every
+            // lane loads the residue codes of its chunk itself (byte loads; the lane above touched the same line one
+            // step earlier), receives the four bottom H of the lane above -- its outputs of the previous step, i.e. of
+            // this very chunk -- with four shuffles, and the last lane stores its four bottom H as one vector. Lanes
+            // whose chunk lies before the first or behind the last one run on padding codes, which cannot raise a score.
+            constexpr int LDW = SPLIT ? (K >= 16 ? 16 : 8) : 4;  // bytes per profile load (SPLIT: aligned code rows)
+            const uint32_t nsteps = nchunks + (uint32_t)G - 1u;
+            T hout[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                uint32_t a = ca[u], b = cb[u];
-                T up = bc[u];
-                if (GROUPED) {
-                    const uint32_t a2 = be.shfl_up(aprev, 1, G);
-                    const uint32_t b2 = be.shfl_up(bprev, 1, G);
-                    const T u2 = V::shfl_up(be, hprev, 1, G);
-                    if constexpr (V::rebased) {
-                        // first column of a block: move to the new base. The first lane of the group takes it from its
-                        // own bottom row (the column just behind), the others receive the amount from the lane above,
-                        // which made the same move one column step ago.
-                        const T d2 = V::shfl_up(be, dcur, 1, G);
-                        if (colg > 0 && ((uint32_t)colg & cbmask) == 0u) {
-                            const T d = lead ? hprev : d2;
-                            dcur = d;
-                            V::template rebase<K>(d, diag0, left, best, cst);
-                            const uint32_t blk = (uint32_t)colg >> p.rebase_shift;
-                            if (lead) {
-                                dconv = T();
-                                if (read_top) {
-                                    const uint2 bw = be.ld_cg2(blog_rd + blk);
-                                    dconv = V::pack((int)bw.x - cst.baseA, (int)bw.y - cst.baseB);
-                                }
+            for (int u = 0; u < 4; ++u) hout[u] = V::hzero(cst);
+            // V16R: the base difference to the row above, the amount of this lane's latest rebase
+            T dconv = T(), dcur = T();
+            uint2 *blog_rd = nullptr, *blog_wr = nullptr;
+            if constexpr (V::rebased) {
+                blog_wr = blog + (size_t)((pass0 + ss) & 1u) * blog_par + (size_t)slot * blog_nb;
+                blog_rd = blog + (size_t)((pass0 + ss + 1u) & 1u) * blog_par + (size_t)slot * blog_nb;
+            }
+            {
+                const bool have = lead && nchunks > 0;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    ca[u] = have ? be.ld_code(res + 2 * u) : (uint32_t)SWB_PAD;
+                    cb[u] = have ? be.ld_code(res + 2 * u + 1) : (uint32_t)SWB_PAD;
+                }
+                if (have && read_top) V::ld4(be, bnd + (size_t)slot * W, bc);
+            }
+            for (uint32_t c = 0; c < nsteps; ++c) {
+                const int32_t cg = (int32_t)c - g;  // this lane's chunk
+                // prefetch: the codes of this lane's next chunk, the next chunk of the top boundary row (first lane)
+                uint32_t na[4], nb[4];
+                T bn[4];
+                const bool top_next = c + 1 < nchunks && read_top;
+                if (wait_top && c + 1 < nchunks) {
+                    const uint32_t need = 4u * c + 8u < W ? 4u * c + 8u : W;
+                    if (avail < need) avail = be.wait_progress(prog + ss - 1, need);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    na[u] = SWB_PAD;
+                    nb[u] = SWB_PAD;
+                    bn[u] = V::hzero(cst);
+                }
+                if ((uint32_t)(cg + 1) < nchunks) {
+                    const uint8_t *rnext = res + (size_t)(uint32_t)(cg + 1) * res_stride;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        na[u] = be.ld_code(rnext + 2 * u);
+                        nb[u] = be.ld_code(rnext + 2 * u + 1);
+                    }
+                }
+                if (lead && top_next) V::ld4(be, bnd + (size_t)slot * W + (size_t)(c + 1) * 4u, bn);
+                T up[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) up[u] = V::shfl_up(be, hout[u], 1, G);
+                if constexpr (V::rebased) {
+                    // first chunk of a block: move to the new base. The first lane of the group takes it from its own
+                    // bottom row (the column just behind), the others receive the amount from the lane above, which
+                    // made the same move one step ago (before it computed the values this lane has just received).
+                    const T d2 = V::shfl_up(be, dcur, 1, G);
+                    if (cg > 0 && ((uint32_t)cg & cbmask) == 0u) {
+                        const T d = lead ? hout[3] : d2;
+                        dcur = d;
+                        V::template rebase<K>(d, diag0, left, best, cst);
+                        const uint32_t blk = (uint32_t)cg >> (p.rebase_shift - 2u);
+                        if (lead) {
+                            dconv = T();
+                            if (read_top) {
+                                const uint2 bw = be.ld_cg2(blog_rd + blk);
+                                dconv = V::pack((int)bw.x - cst.baseA, (int)bw.y - cst.baseB);
                             }
-                            if (tail && write_bot) be.st_cg2(blog_wr + blk, make_uint2((uint32_t)cst.baseA, (uint32_t)cst.baseB));
                         }
-                        // the row above: relative to its writer's base -> to this lane's base; none: zero (absolute)
-                        up = top_cur ? V::add(up, dconv) : V::hzero(cst);
-                        ++colg;
-                    }
-                    if (!lead) { a = a2; b = b2; up = u2; }
-                }
-                const T h = V::template column<K>(up, diag0, left, best, cst, a, b, prow, sstride);
-                outb[u] = h;
-                hprev = h;
-                aprev = a;
-                bprev = b;
-            }
-            if (write_bot) {
-                if (!GROUPED) {
-                    V::st4(be, bnd + ((size_t)c * 32u + lane) * 4u, outb);
-                } else if (tail) {
-                    const int32_t col0 = (int32_t)(c * 4u) - (G - 1);  // column of outb[0]
-                    T *dst = bnd + (size_t)slot * W + col0;
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        if (col0 + u >= 0 && col0 + u < (int32_t)W) V::st(be, dst + u, outb[u]);
-                }
-                if (SPLIT && ((c & 15u) == 15u || c + 1 == nsteps4)) {
-                    // every slot's last lane has stored its columns: one lane publishes for the warp
-                    be.syncwarp();
-                    if (lane == 31) {
-                        const int32_t col0 = (int32_t)(c * 4u) - (G - 1);
-                        const int32_t done = col0 + 4 < 0 ? 0 : (col0 + 4 > (int32_t)W ? (int32_t)W : col0 + 4);
-                        be.publish(prog + ss, (uint32_t)done);
+                        if (tail && write_bot) be.st_cg2(blog_wr + blk, make_uint2((uint32_t)cst.baseA, (uint32_t)cst.baseB));
                     }
                 }
-            }
+                if (lead) {
+                    // the row above: relative to its writer's base -> to this lane's base (V16R); none: zero
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                ca[u] = na[u];
-                cb[u] = nb[u];
-                bc[u] = bn[u];
+                    for (int u = 0; u < 4; ++u) {
+                        if constexpr (V::rebased) up[u] = top_cur ? V::add(bc[u], dconv) : V::hzero(cst);
+                        else up[u] = bc[u];
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    hout[u] = V::template column<K, LDW>(up[u], diag0, left, best, cst, ca[u], cb[u], prow, sstride);
+                if (write_bot) {
+                    if (tail && (uint32_t)cg < nchunks) V::st4(be, bnd + (size_t)slot * W + (size_t)cg * 4u, hout);
+                    if (SPLIT && ((c & 7u) == 7u || c + 1 == nsteps)) {
+                        // every slot's last lane has stored its chunk: one lane publishes for the warp
+                        be.syncwarp();
+                        if (lane == 31) {
+                            const int32_t done = 4 * ((int32_t)c - (G - 1) + 1);
+                            be.publish(prog + ss, (uint32_t)(done < 0 ? 0 : (done > (int32_t)W ? (int32_t)W : done)));
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    ca[u] = na[u];
+                    cb[u] = nb[u];
+                    bc[u] = bn[u];
+                }
+                top_cur = top_next;
             }
-            top_cur = top_next;
         }
         if constexpr (V::rebased) {  // the next pass starts at base 0 again
             V::fold(best, cst);

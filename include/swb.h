@@ -74,7 +74,7 @@ void swb_destroy(swb_engine *e);
 /* e == NULL: error text of the last failed swb_create of this thread */
 const char *swb_last_error(const swb_engine *e);
 /* options: "group_len" (longest sequence handled by one lane per pair; set before db_load. Default 0 = chosen per
- *          load: 1536 for a shard with at least ~300 k sequences, 384 for smaller ones),
+ *          load from the shard size: 1536 for ~450 k sequences and more, 768 down to ~110 k, 384 below),
  *          "k" (query rows per lane: 0 = chosen per lane-group size and query, else 8, 16, 32),
  *          "streams" (queries of a batch in flight at once, 1..24, default 16; their scratch is allocated on first use),
  *          "group_order" (0 = auto, 1 = launch the long-sequence tiles first, 2 = launch the bulk first),
@@ -84,6 +84,11 @@ const char *swb_last_error(const swb_engine *e);
  *          different warps, 0 = never, -1 (default) = only on small shards, where those few tiles are the critical
  *          path of a query: +10 % at 1/8 of Swiss-Prot per GPU; on a large shard it costs ~0.5 %),
  *          "xl_len" (lane-group tiles wider than this are the ones "split" applies to, default 3072; before db_load),
+ *          "split_k" (query rows per lane of the pipelined groups: 0 = chosen per query, 8, 16, 32),
+ *          "exact" (scores beyond the s16 range: 0 (default) = the rebased s16 policy where the scoring scheme allows it
+ *          -- steps between neighbouring cells small enough for a 16-bit window -- else int32; 1 = always int32),
+ *          "direct_len" (pipelined tiles at least this wide, against a query at least this long, skip the plain s16
+ *          pass and are scored by the rebased policy at once; default 10000, 0 = never),
  *          "load_threads" (host threads that gather the residues of a sharded load, default 4),
  *          "chunk_rows" (query rows per launch for queries beyond shared memory; multiple of 1024, <= 7168) */
 int swb_set_option(swb_engine *e, const char *key, int64_t value);

@@ -190,10 +190,12 @@ void lane_main(HostBackend &be, void *a)
             swb_warp_loop<8, V32, true>(be, *la->p, la->sprof, la->sstride);
         } else if (la->mode == 2) {
             if (la->K == 8) swb_warp_loop<8, V16R, true>(be, *la->p, la->sprof, la->sstride);
-            else swb_warp_loop<16, V16R, true>(be, *la->p, la->sprof, la->sstride);
+            else if (la->K == 16) swb_warp_loop<16, V16R, true>(be, *la->p, la->sprof, la->sstride);
+            else swb_warp_loop<32, V16R, true>(be, *la->p, la->sprof, la->sstride);
         } else {
             if (la->K == 8) swb_warp_loop<8, V16, true>(be, *la->p, la->sprof, la->sstride);
-            else swb_warp_loop<16, V16, true>(be, *la->p, la->sprof, la->sstride);
+            else if (la->K == 16) swb_warp_loop<16, V16, true>(be, *la->p, la->sprof, la->sstride);
+            else swb_warp_loop<32, V16, true>(be, *la->p, la->sprof, la->sstride);
         }
     } else if (la->mode == 2) {
         if (la->K == 8) swb_warp_loop<8, V16R, false>(be, *la->p, la->sprof, la->sstride);
@@ -250,8 +252,8 @@ void run_pass(SwbScoreParams &p, int mode, const SwbQueryPlan &qp, const std::ve
             uint32_t counter = 0;
             p.counter = &counter;
             // stage the chunk's profile exactly like swb_score_kernel (split groups stage per work item)
-            const uint32_t sstride = p.smem_rows + 4u;
-            std::vector<uint32_t> sprof_words(((size_t)sstride * SWB_ALPHA + 64) / 4);
+            const uint32_t sstride = p.smem_rows + (g.split ? 16u : 4u);
+            std::vector<uint4> sprof_words(((size_t)sstride * SWB_ALPHA + 64) / 16);  // 16-byte aligned like shared memory
             int8_t *sprof = reinterpret_cast<int8_t *>(sprof_words.data());
             if (!g.split)
                 for (uint32_t code = 0; code < SWB_ALPHA; ++code)
@@ -313,7 +315,7 @@ extern "C" int swbemu_search(const uint8_t *codes, const uint64_t *offsets, uint
     }
     if (!chunk_rows) chunk_rows = 7168;
     if (!split_k) split_k = 8;
-    const int eng_shift = affine ? 0 : swb_rebase_shift(max_s, min_s, gap, 16u * 32u);
+    const int eng_shift = affine ? 0 : swb_rebase_shift(max_s, min_s, gap, (split_k > 16 ? 32u : 16u) * 32u);
     const bool r16 = !affine && eng_shift > 0 && !exact_i32;
     if (r16 && rebase_shift >= 6) {
         if (rebase_shift > eng_shift) return -3;  // a larger block than the scheme allows would not be exact
@@ -358,7 +360,7 @@ extern "C" int swbemu_search(const uint8_t *codes, const uint64_t *offsets, uint
     swb_plan_query(rows, K, 32, present, chunk_rows, qp0);
     swb_plan_query(rows, K, affine ? 8 : 16, present, chunk_rows, qp1);
     uint32_t prof_rows = std::max(qp0.prof_rows, qp1.prof_rows);
-    if (split) prof_rows = std::max(prof_rows, swb_roundup(rows, 16u << SWB_MAX_LOGG));
+    if (split) prof_rows = std::max(prof_rows, swb_roundup(rows, 32u << SWB_MAX_LOGG));
     const uint32_t stride = swb_roundup(std::max(prof_rows, 16u), 16);
     std::vector<uint8_t> prof((size_t)stride * SWB_ALPHA, 0);
     for (uint32_t r = 0; r < prof_rows; ++r) {

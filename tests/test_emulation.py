@@ -210,9 +210,9 @@ def test_pipelined_passes_with_16_row_strips(emu, oracle):
     for ql in (100, 700, 1100):
         q = rng.integers(0, 20, ql).astype(np.uint8)
         want = oracle.scan(q, codes, offs, m)
-        for gl, xl in ((16, 100), (16, 600), (32, 1000)):
-            got, _ = emu(codes, offs, m, q, K=0, group_len=gl, xl_len=xl, split_k=16)
-            assert np.array_equal(got, want), (ql, gl, xl)
+        for gl, xl, sk in ((16, 100, 16), (16, 600, 16), (32, 1000, 16), (16, 300, 32)):
+            got, _ = emu(codes, offs, m, q, K=0, group_len=gl, xl_len=xl, split_k=sk)
+            assert np.array_equal(got, want), (ql, gl, xl, sk)
     q = rng.integers(0, 20, 2300).astype(np.uint8)
     want = oracle.scan(q, codes, offs, m)
     for exact_i32 in (0, 1):
@@ -222,6 +222,8 @@ def test_pipelined_passes_with_16_row_strips(emu, oracle):
         got, _ = emu(codes, offs, m, q, K=0, group_len=16, xl_len=300, force_i32=1, split_k=16, exact_i32=exact_i32,
                      rebase_shift=7)
         assert np.array_equal(got, want), exact_i32
+    got, rc = emu(codes, offs, m, q, K=0, group_len=16, xl_len=500, thr=40, split_k=32, direct_len=1000, rebase_shift=6)
+    assert np.array_equal(got, want)
 
 
 def test_pipelined_passes_every_lane_group_class(emu, oracle):
@@ -309,7 +311,7 @@ def test_randomized_configurations(emu, oracle):
         K = int(rng.choice([0, 8, 16, 32]))
         xl = int(rng.choice([0, 16, 64, 256, 8192]))
         thr = int(rng.choice([-1, -1, 10, 40, 200]))
-        sk = int(rng.choice([8, 16]))
+        sk = int(rng.choice([8, 16, 32]))
         ex = int(rng.choice([0, 0, 1]))
         dl = int(rng.choice([0, 0, 50, 300]))
         want = oracle.scan(q, codes, offs, m)

@@ -18,7 +18,8 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libswb.so")
+# SWB_LIB: another build of the library (A/B measurements of kernel versions; tools/)
+LIB_PATH = os.environ.get("SWB_LIB") or os.path.join(_HERE, "lib", "libswb.so")
 
 SWB_SCORING_BLOSUM50_REF = 0
 SWB_SCORING_IDENT3 = 1

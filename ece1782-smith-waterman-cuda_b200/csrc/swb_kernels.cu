@@ -1,5 +1,6 @@
 // sm_100a kernels of the scan engine: score kernels (instantiations of swb_warp.cuh), query-profile
 // builder, device-side DB packer and score scatter. Host-side launch wrappers at the bottom.
+#include <atomic>
 #include "swb_kernels.h"
 #include "swb_warp.cuh"
 
@@ -153,23 +154,41 @@ __global__ void swb_clear_flagged_kernel(const SwbTile *__restrict__ tiles, uint
 }
 
 // ---------------------------------------------------------------------------------------------
+// The dynamic shared-memory limit of a kernel is per-device state shared by every engine (and host thread) of the
+// process: raising it to what one launch needs and lowering it for the next would race between the engines of a group.
+// It is set once per kernel and device to the device's opt-in maximum instead.
+template <int K, class V, int NT, int MINB, bool SPLIT>
+static cudaError_t allow_max_smem()
+{
+    static std::atomic<int> done[64];
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 64 && done[dev].load(std::memory_order_acquire)) return cudaSuccess;
+    int optin = 0;
+    if ((e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(swb_score_kernel<K, V, NT, MINB, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  optin)) != cudaSuccess)
+        return e;
+    if (dev < 64) done[dev].store(1, std::memory_order_release);
+    return cudaSuccess;
+}
+
 template <int K, class V, int NT, int MINB, bool SPLIT>
 static cudaError_t launch_one(const SwbScoreParams &p, int grid, size_t smem, cudaStream_t st)
 {
-    auto kern = swb_score_kernel<K, V, NT, MINB, SPLIT>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = allow_max_smem<K, V, NT, MINB, SPLIT>();
     if (e != cudaSuccess) return e;
-    kern<<<grid, NT, smem, st>>>(p);
+    swb_score_kernel<K, V, NT, MINB, SPLIT><<<grid, NT, smem, st>>>(p);
     return cudaGetLastError();
 }
 
 template <int K, class V, int NT, int MINB, bool SPLIT>
 static cudaError_t occ_one(size_t smem, int *blocks)
 {
-    auto kern = swb_score_kernel<K, V, NT, MINB, SPLIT>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = allow_max_smem<K, V, NT, MINB, SPLIT>();
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, kern, NT, smem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, swb_score_kernel<K, V, NT, MINB, SPLIT>, NT, smem);
 }
 
 // op: 0 = launch, 1 = occupancy query

@@ -623,13 +623,118 @@ SWB_HD void swb_run_tile(BE &be, const SwbScoreParams &p, const SwbTile &tile, u
                     bc[u] = bn[u];
                 }
             }
+        } else if constexpr (!SPLIT) {
+            // Lane-group wavefront, one COLUMN of lag per lane: at column step t lane g works on column t - g and hands
+            // its bottom H and the residue pair to lane g + 1 with shuffles; the first lane of a group fetches the
+            // residue codes and the top boundary row, the last lane stores the bottom row (scalars: its columns lag
+            // G - 1 behind, so they are not 4-aligned). Measured on B200 this form is the faster one for the tiles of
+            // the bulk launches (a warp shares its scheduler with three others, the short lag keeps its lanes' chains
+            // close together); the pipelined (SPLIT) launches below use one chunk of lag instead.
+            const uint32_t nsteps4 = (W + (uint32_t)G - 1u + 3u) >> 2;
+            T hprev = V::hzero(cst);
+            uint32_t aprev = SWB_PAD, bprev = SWB_PAD;
+            int colg = -g;  // V16R: this lane's column
+            T dconv = T(), dcur = T();
+            uint2 *blog_rd = nullptr, *blog_wr = nullptr;
+            const uint32_t colmask = V::rebased ? (1u << p.rebase_shift) - 1u : 0u;
+            if constexpr (V::rebased) {
+                blog_wr = blog + (size_t)((pass0 + ss) & 1u) * blog_par + (size_t)slot * blog_nb;
+                blog_rd = blog + (size_t)((pass0 + ss + 1u) & 1u) * blog_par + (size_t)slot * blog_nb;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                ca[u] = SWB_PAD;
+                cb[u] = SWB_PAD;
+            }
+            if (lead && nchunks > 0) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    ca[u] = be.ld_code(res + 2 * u);
+                    cb[u] = be.ld_code(res + 2 * u + 1);
+                }
+                if (read_top) V::ld4(be, bnd + (size_t)slot * W, bc);
+            }
+            for (uint32_t c = 0; c < nsteps4; ++c) {
+                // prefetch the next chunk of residues and of the top boundary row
+                uint32_t na[4], nb[4];
+                T bn[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    na[u] = SWB_PAD;
+                    nb[u] = SWB_PAD;
+                    bn[u] = V::hzero(cst);
+                }
+                const bool top_next = c + 1 < nchunks && read_top;
+                if (lead && c + 1 < nchunks) {
+                    const uint8_t *rnext = res + (size_t)(c + 1) * res_stride;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        na[u] = be.ld_code(rnext + 2 * u);
+                        nb[u] = be.ld_code(rnext + 2 * u + 1);
+                    }
+                    if (read_top) V::ld4(be, bnd + (size_t)slot * W + (size_t)(c + 1) * 4u, bn);
+                }
+                T outb[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    uint32_t a = ca[u], b = cb[u];
+                    T up = bc[u];
+                    const uint32_t a2 = be.shfl_up(aprev, 1, G);
+                    const uint32_t b2 = be.shfl_up(bprev, 1, G);
+                    const T u2 = V::shfl_up(be, hprev, 1, G);
+                    if constexpr (V::rebased) {
+                        // first column of a block: move to the new base. The first lane of the group takes it from its
+                        // own bottom row (the column just behind), the others receive the amount from the lane above,
+                        // which made the same move one column step ago.
+                        const T d2 = V::shfl_up(be, dcur, 1, G);
+                        if (colg > 0 && ((uint32_t)colg & colmask) == 0u) {
+                            const T d = lead ? hprev : d2;
+                            dcur = d;
+                            V::template rebase<K>(d, diag0, left, best, cst);
+                            const uint32_t blk = (uint32_t)colg >> p.rebase_shift;
+                            if (lead) {
+                                dconv = T();
+                                if (read_top) {
+                                    const uint2 bw = be.ld_cg2(blog_rd + blk);
+                                    dconv = V::pack((int)bw.x - cst.baseA, (int)bw.y - cst.baseB);
+                                }
+                            }
+                            if (tail && write_bot) be.st_cg2(blog_wr + blk, make_uint2((uint32_t)cst.baseA, (uint32_t)cst.baseB));
+                        }
+                        // the row above: relative to its writer's base -> to this lane's base; none: zero (absolute)
+                        up = top_cur ? V::add(up, dconv) : V::hzero(cst);
+                        ++colg;
+                    }
+                    if (!lead) { a = a2; b = b2; up = u2; }
+                    const T h = V::template column<K, 4>(up, diag0, left, best, cst, a, b, prow, sstride);
+                    outb[u] = h;
+                    hprev = h;
+                    aprev = a;
+                    bprev = b;
+                }
+                if (write_bot && tail) {
+                    const int32_t col0 = (int32_t)(c * 4u) - (G - 1);  // column of outb[0]
+                    T *dst = bnd + (size_t)slot * W + col0;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (col0 + u >= 0 && col0 + u < (int32_t)W) V::st(be, dst + u, outb[u]);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    ca[u] = na[u];
+                    cb[u] = nb[u];
+                    bc[u] = bn[u];
+                }
+                top_cur = top_next;
+            }
         } else {
-            // Lane-group wavefront, one chunk (4 columns) per lane and step: at step c lane g works on chunk c - g. Every
+            // Pipelined launches: lane-group wavefront with one CHUNK (4 columns) of lag per lane: at step c lane g
+            // works on chunk c - g. Every
             // lane loads the residue codes of its chunk itself (byte loads; the lane above touched the same line one
             // step earlier), receives the four bottom H of the lane above -- its outputs of the previous step, i.e. of
             // this very chunk -- with four shuffles, and the last lane stores its four bottom H as one vector. Lanes
             // whose chunk lies before the first or behind the last one run on padding codes, which cannot raise a score.
-            constexpr int LDW = SPLIT ? (K >= 16 ? 16 : 8) : 4;  // bytes per profile load (SPLIT: aligned code rows)
+            constexpr int LDW = K >= 16 ? 16 : 8;  // bytes per profile load (the SPLIT kernels stage aligned code rows)
             const uint32_t nsteps = nchunks + (uint32_t)G - 1u;
             T hout[4];
 #pragma unroll

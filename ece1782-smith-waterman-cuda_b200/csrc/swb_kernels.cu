@@ -56,6 +56,10 @@ struct DevBackend {
         }
         return v;
     }
+    __device__ __forceinline__ void prefetch_l2(const void *p) const
+    {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+    }
     __device__ __forceinline__ uint8_t ld_flag(const uint8_t *p) const { return __ldcg(p); }
     __device__ __forceinline__ SwbTile ld_tile(const SwbTile *p) const
     {

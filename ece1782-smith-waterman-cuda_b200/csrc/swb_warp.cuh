@@ -33,6 +33,10 @@
 #include <cuda_runtime.h>
 #include "swb_types.h"
 
+#ifndef SWB_PF_CHUNKS
+#define SWB_PF_CHUNKS 6u  // chunks (of 4 columns) that the L2 prefetch of the one-lane tiles runs ahead
+#endif
+
 // ---------------------------------------------------------------------------------------------
 // byte permute with sign replication (PTX prmt.b32 generic mode: selector nibble bit 3 = replicate
 // the sign of the selected byte)
@@ -223,14 +227,29 @@ struct V16R : V16Base {
         c.bestB = b > c.bestB ? b : c.bestB;
         best = 0x80008000u;
     }
-    // new base = old base + d (d: relative value of the reference cell): all row state moves by -d
+    // saturating per-half subtraction
+    static SWB_HD T subs(T a, T b)
+    {
+#ifdef __CUDA_ARCH__
+        return __vsubss2(a, b);
+#else
+        int l = lo(a) - lo(b), h = hi(a) - hi(b);
+        l = l < -32768 ? -32768 : (l > 32767 ? 32767 : l);
+        h = h < -32768 ? -32768 : (h > 32767 ? 32767 : h);
+        return pack(l, h);
+#endif
+    }
+    // new base = old base + d (d: relative value of the reference cell): all row state moves by -d. State that sits at
+    // the clamped floor (-32000: lanes running on the padding behind the last column, fed with "zero" from above while
+    // the base is beyond 32000) must stay there: a wrapping subtraction would turn it into a huge positive value that
+    // ends up in the running maximum. Saturate, then floor again in the new base.
     template <int K> static SWB_HD void rebase(T d, T &diag0, T (&left)[K], T &best, C &c)
     {
         fold(best, c);
         set_base(c, c.baseA + lo(d), c.baseB + hi(d));
 #pragma unroll
-        for (int k = 0; k < K; ++k) left[k] = sub(left[k], d);
-        diag0 = sub(diag0, d);
+        for (int k = 0; k < K; ++k) left[k] = max2(subs(left[k], d), c.fl);
+        diag0 = max2(subs(diag0, d), c.fl);
     }
     template <int K, int LDW>
     static SWB_HD T column(T up, T &diag0, T (&left)[K], T &best, const C &cst, uint32_t codeA, uint32_t codeB,
@@ -610,6 +629,14 @@ SWB_HD void swb_run_tile(BE &be, const SwbScoreParams &p, const SwbTile &tile, u
                         nb[u] = be.ld_code(rnext + 2 * u + 1);
                     }
                     if (read_top) V::ld4(be, bnd + ((size_t)(c + 1) * 32u + lane) * 4u, bn);
+                }
+                // The loads above run one chunk ahead, which covers an L2 hit but not a trip to HBM -- and with wide
+                // tiles the residues and boundary rows of all resident warps exceed the L2, so they do come from HBM
+                // (ncu: the first use of a residue code was the top stall of the kernel). Pull the lines of the chunk
+                // SWB_PF_CHUNKS ahead into L2 now; no register is tied up.
+                if (c + SWB_PF_CHUNKS < nchunks) {
+                    be.prefetch_l2(res + (size_t)(c + SWB_PF_CHUNKS) * res_stride);
+                    if (read_top) be.prefetch_l2(bnd + ((size_t)(c + SWB_PF_CHUNKS) * 32u + lane) * 4u);
                 }
                 T outb[4];
 #pragma unroll

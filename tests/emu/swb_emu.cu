@@ -45,6 +45,7 @@ struct HostBackend {
         return *p;
     }
 
+    void prefetch_l2(const void *) const {}
     uint8_t ld_flag(const uint8_t *p) const { return *p; }
     SwbTile ld_tile(const SwbTile *p) const { return *p; }
     uint32_t ld_code(const uint8_t *p) const { return *p; }

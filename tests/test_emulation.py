@@ -281,6 +281,22 @@ def test_rebased_s16_is_exact_far_beyond_the_s16_range(emu, oracle):
     assert np.array_equal(got, oracle.scan(q, c1, o1, m)) and got[0] == 36000 and rc == 1
 
 
+def test_rebased_s16_padding_lanes_at_the_clamped_floor(emu, oracle):
+    """Regression (found on the configs[3] workload): behind the last column of a tile the first lane keeps running on
+    padding with "zero" from above; once the base has passed 32000 that zero is the clamped floor, and a rebase inside
+    the padding used to wrap it into a huge positive value that reached the running maximum (score + ~32000). The pair
+    below is two configs[3] targets of ~21,400 residues against the first 30,000 rows of the 35,213-row query."""
+    import bench
+    codes, offs, qs = bench.synth_config4()
+    m = oracle.matrix("blosum50")
+    c2, o2 = pack_db([codes[int(offs[i]):int(offs[i + 1])] for i in (68, 1)])
+    q = qs[3][:30000]
+    want = oracle.scan(q, c2, o2, m)
+    assert want.min() > 32767
+    got, _ = emu(c2, o2, m, q, K=0, group_len=384, xl_len=3072, split_k=16, direct_len=3000)
+    assert np.array_equal(got, want)
+
+
 def test_rebased_s16_random_and_ident3(emu, oracle):
     """V16R as the only pass (force) over random databases, both scoring presets, every K / group size mix"""
     rng = np.random.default_rng(77)

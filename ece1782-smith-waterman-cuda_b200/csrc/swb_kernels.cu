@@ -46,14 +46,18 @@ struct DevBackend {
         }
         __syncwarp();
     }
-    __device__ __forceinline__ uint32_t wait_progress(const uint32_t *p, uint32_t need) const
+    // returns the published column count once it is at least `need`; if it was not on the first look, waits until the
+    // predecessor is SWB_SPLIT_HYST columns further (or done: `total`), so that the next poll is that far away
+    __device__ __forceinline__ uint32_t wait_progress(const uint32_t *p, uint32_t need, uint32_t total) const
     {
         uint32_t v;
         asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-        while (v < need) {
-            __nanosleep(128);
+        if (v >= need) return v;
+        const uint32_t want = need + SWB_SPLIT_HYST < total ? need + SWB_SPLIT_HYST : total;
+        do {
+            __nanosleep(200);
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-        }
+        } while (v < want);
         return v;
     }
     __device__ __forceinline__ void prefetch_l2(const void *p) const

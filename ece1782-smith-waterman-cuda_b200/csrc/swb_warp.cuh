@@ -33,6 +33,7 @@
 #include <cuda_runtime.h>
 #include "swb_types.h"
 
+#define SWB_SPLIT_HYST 256u  // columns a pipelined pass lets its predecessor get ahead once it has had to wait
 #ifndef SWB_PF_CHUNKS
 #define SWB_PF_CHUNKS 6u  // chunks (of 4 columns) that the L2 prefetch of the one-lane tiles runs ahead
 #endif
@@ -543,12 +544,16 @@ struct V32A {
 //                                            writes 4 columns as one vector (every lane lags one chunk behind the
 //                                            lane above)
 //
-// SPLIT (32-lane tiles of very long sequences only): the passes of one tile are separate work items taken by different
-// warps, which run as a pipeline over the columns. The warp of pass ss publishes how many columns of its bottom row are
-// in the boundary scratch (prog[ss], every 64 columns, after a fence); the warp of pass ss+1 polls it (with back-off)
-// before it reads
-// them. Items are handed out in (tile, pass) order by one counter, so a waiting warp always waits for an item that a
-// resident warp already owns: no deadlock. Scores of the passes are combined with atomicMax.
+// SPLIT (lane-group tiles of long sequences): the passes of one tile are separate work items taken by different warps,
+// which run as a pipeline over the columns. The warp of pass ss publishes how many columns of its bottom row are in the
+// boundary scratch (prog[ss], every 64 columns, release store); the warp of pass ss+1 polls it (acquire load, back-off)
+// before it reads them. A pass that had to wait resumes only once its predecessor is SWB_SPLIT_HYST columns ahead:
+// both run at the same speed, so that margin then lasts and the pass polls once per margin instead of stalling on a
+// round trip through L2 every few steps (ncu: 60 % of the stall samples of these kernels sat in the polling loop).
+// Items are handed out by one counter, pass-major inside a lane-group class (pass 0 of every tile, then pass 1, ...): a
+// waiting warp always waits for an item that was handed out before its own, i.e. that a resident warp owns or has
+// finished -- no deadlock -- and only a few passes per tile are in flight at a time, so little of a launch's first wave
+// is spent waiting for the pipeline of one tile to fill. Scores of the passes are combined with atomicMax.
 template <int K, class V, bool GROUPED, bool SPLIT, class BE>
 SWB_HD void swb_run_tile(BE &be, const SwbScoreParams &p, const SwbTile &tile, uint32_t tile_idx,
                          const int8_t *sprof, uint32_t sstride, uint32_t ss_begin = 0, uint32_t ss_count = 0xffffffffu,
@@ -599,7 +604,7 @@ SWB_HD void swb_run_tile(BE &be, const SwbScoreParams &p, const SwbTile &tile, u
         bool top_cur = nchunks > 0 && read_top;  // bc holds values of the row above (uniform over the warp)
         if (wait_top) {
             const uint32_t need = W < 4u ? W : 4u;
-            avail = be.wait_progress(prog + ss - 1, need);
+            avail = be.wait_progress(prog + ss - 1, need, W);
         }
 
         if constexpr (!GROUPED) {
@@ -790,7 +795,7 @@ SWB_HD void swb_run_tile(BE &be, const SwbScoreParams &p, const SwbTile &tile, u
                 const bool top_next = c + 1 < nchunks && read_top;
                 if (wait_top && c + 1 < nchunks) {
                     const uint32_t need = 4u * c + 8u < W ? 4u * c + 8u : W;
-                    if (avail < need) avail = be.wait_progress(prog + ss - 1, need);
+                    if (avail < need) avail = be.wait_progress(prog + ss - 1, need, W);
                 }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
@@ -843,7 +848,7 @@ SWB_HD void swb_run_tile(BE &be, const SwbScoreParams &p, const SwbTile &tile, u
                     hout[u] = V::template column<K, LDW>(up[u], diag0, left, best, cst, ca[u], cb[u], prow, sstride);
                 if (write_bot) {
                     if (tail && (uint32_t)cg < nchunks) V::st4(be, bnd + (size_t)slot * W + (size_t)cg * 4u, hout);
-                    if (SPLIT && ((c & 7u) == 7u || c + 1 == nsteps)) {
+                    if (SPLIT && ((c & 15u) == 15u || c + 1 == nsteps)) {
                         // every slot's last lane has stored its chunk: one lane publishes for the warp
                         be.syncwarp();
                         if (lane == 31) {
@@ -926,7 +931,8 @@ SWB_HD void swb_warp_loop(BE &be, const SwbScoreParams &p, const int8_t *sprof, 
                 }
             const uint32_t rows_per_pass = (uint32_t)K << l;
             const uint32_t passes = (p.rows + rows_per_pass - 1u) / rows_per_pass;
-            const uint32_t t = (v - item0) / passes, ss = (v - item0) - t * passes;
+            const uint32_t ntl = (p.split_item_end[SWB_MAX_LOGG - l] - item0) / passes;  // tiles of this class
+            const uint32_t ss = (v - item0) / ntl, t = (v - item0) - ss * ntl;            // pass-major
             const uint32_t ti = tile0 + t;
             if (p.only_flagged && !be.ld_flag(p.flags + ti)) continue;  // every pass of the tile skips alike
             const SwbTile tile = be.ld_tile(p.tiles + ti);

@@ -39,7 +39,7 @@ struct HostBackend {
                 memcpy(dst + (size_t)code * dstride, prof + (size_t)code * pstride + row0, rows);
         syncwarp();
     }
-    uint32_t wait_progress(const uint32_t *p, uint32_t need)
+    uint32_t wait_progress(const uint32_t *p, uint32_t need, uint32_t)
     {
         if (*p < need) abort();  // on the GPU this would be a spin that never ends: hand-out order guarantee broken
         return *p;

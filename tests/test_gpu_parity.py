@@ -491,6 +491,27 @@ def test_exact_pass_policies_far_beyond_the_s16_range(swb, oracle):
             e.close()
 
 
+def test_rebased_s16_padding_lanes_regression(swb, oracle):
+    """Two configs[3] targets of ~21,400 residues against the 35,213-row query: true scores just above 32767 with a
+    rebase block boundary inside the padding behind the last column -- the case in which padding lanes at the
+    clamped floor once wrapped into the running maximum (scores came out ~32000 too high). All pipelined strip
+    heights, direct and flagged-then-rescored."""
+    import bench
+    codes, offs, qs = bench.synth_config4()
+    m = oracle.matrix("blosum50")
+    ids = (68, 1, 149, 27, 79, 130)
+    c2, o2 = pack_db([codes[int(offs[i]):int(offs[i + 1])] for i in ids])
+    want = oracle.scan(qs[3], c2, o2, m)
+    assert want.min() > 32767
+    for cfg in (dict(), dict(split_k=8), dict(split_k=32), dict(direct_len=0), dict(direct_len=0, split_k=32)):
+        e = swb.Engine(0, **cfg)
+        try:
+            e.db_load(c2, o2)
+            assert np.array_equal(e.search(qs[3]), want), cfg
+        finally:
+            e.close()
+
+
 def _group_devices(n):
     """n engines: real devices when the box has them, else several engines on device 0"""
     import torch

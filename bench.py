@@ -333,7 +333,8 @@ def main():
     ap.add_argument("--parity-seconds", type=float, default=3.0, help="CPU budget of the per-rank oracle sample (N > 1)")
     ap.add_argument("--topk", type=int, default=10)
     ap.add_argument("--db-parts", type=int, default=0, help="database parts P of the P x R rank layout (0 = the layout "
-                    "rule of the engine group: the largest divisor of N with >= 250,000 sequences per part)")
+                    "rule of the engine group: the largest divisor of N with >= 450,000 sequences per part, more parts when the "
+                    "batch cannot fill the query groups evenly)")
     ap.add_argument("--group", action="store_true", help="one process drives all --gpus devices through the engine "
                     "group (swb_group_*) instead of one torchrun rank per GPU")
     ap.add_argument("--streams", type=int, default=0)
@@ -344,7 +345,7 @@ def main():
                     "(default) = the engine's rule: on for small shards")
     ap.add_argument("--split-k", type=int, default=0, help="rows per lane of the pipelined groups: 0 auto, 8, 16")
     ap.add_argument("--direct-len", type=int, default=-1, help="tiles / queries at least this long are scored by the "
-                    "rebased s16 policy at once (-1 = engine default 10000, 0 = never)")
+                    "rebased s16 policy at once (-1 = engine default 14000, 0 = never)")
     ap.add_argument("--exact", type=int, default=-1, help="exact passes: 0 rebased s16 (default), 1 int32")
     ap.add_argument("--batch-order", type=int, default=-1, help="0 longest query first (default), 1 as given")
     ap.add_argument("--chunk-rows", type=int, default=0)
@@ -402,12 +403,12 @@ def main():
         return run_group(args, swb, codes, offsets, qs, total_cells)
 
     # rank layout: P database parts x R query groups (the engine group's rule); rank -> (part, group)
-    parts = args.db_parts if args.db_parts else swb.layout_parts(n_total, world)
+    _, qoffs_all = swb.pack_sequences(qs)
+    parts = args.db_parts if args.db_parts else swb.layout_parts(n_total, world, qoffsets=qoffs_all)
     if world % parts:
         raise SystemExit("--db-parts must divide the number of ranks")
     groups = world // parts
     part, grp = rank % parts, rank // parts
-    _, qoffs_all = swb.pack_sequences(qs)
     group_of = swb.layout_query_groups(qoffs_all, groups)
     mine = [qi for qi in range(len(qs)) if group_of[qi] == grp]  # global indices of this rank's queries
     local_of = {qi: k for k, qi in enumerate(mine)}
@@ -636,7 +637,8 @@ def main():
                             "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}}
         cfg = workload_config(offsets, qs, args)
         cfg["layout"] = {"db_parts": parts, "query_groups": groups,
-                         "rule": "P = largest divisor of N with >= 250,000 sequences per part; queries split LPT"}
+                         "rule": "P = largest divisor of N with >= 450,000 sequences per part, raised while the batch "
+                                 "cannot fill N / P query groups evenly (LPT, heaviest group <= 1.02 x mean)"}
         cfg["value_includes"] = ("device-side top-%d per query copied to the host" % args.topk if big
                                  else "all scores copied to the host (4 B x queries x sequences per step)")
         line = {"metric": METRIC, "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps,

@@ -76,7 +76,7 @@ ABI_SYMBOLS = [
     "swb_group_create", "swb_group_create_env", "swb_group_destroy", "swb_group_last_error", "swb_group_size", "swb_group_engine",
     "swb_group_db_parts", "swb_group_set_option", "swb_group_set_scoring", "swb_group_set_scoring_preset",
     "swb_group_set_scoring_affine", "swb_group_db_load", "swb_group_search_batch", "swb_group_search_batch_topk",
-    "swb_group_stats", "swb_layout_parts", "swb_layout_query_groups",
+    "swb_group_stats", "swb_layout_parts", "swb_layout_parts_batch", "swb_layout_query_groups",
     "swb_microbench", "swb_align", "swb_read_fasta", "swb_read_uniprot_dat", "swb_free", "swb_dbfile_write",
     "swb_dbfile_open", "swb_dbfile_count", "swb_dbfile_first_id", "swb_dbfile_offsets", "swb_dbfile_codes",
     "swb_dbfile_close",
@@ -167,6 +167,8 @@ def lib():
     L.swb_group_stats.argtypes = [vp, ctypes.POINTER(SwbStats)]
     L.swb_layout_parts.restype = ctypes.c_int
     L.swb_layout_parts.argtypes = [ctypes.c_uint32, ctypes.c_int, ctypes.c_uint32]
+    L.swb_layout_parts_batch.restype = ctypes.c_int
+    L.swb_layout_parts_batch.argtypes = [ctypes.c_uint32, ctypes.c_int, ctypes.c_uint32, _u64p, ctypes.c_uint32]
     L.swb_layout_query_groups.restype = ctypes.c_int
     L.swb_layout_query_groups.argtypes = [_u64p, ctypes.c_uint32, ctypes.c_int, _u32p]
     L.swb_fetch_scores.restype = ctypes.c_int
@@ -302,9 +304,17 @@ def dbfile_read(path):
         L.swb_dbfile_close(h)
 
 
-def layout_parts(n, ndev, min_part_sequences=250000):
-    """database parts P of the P x R device grid (include/swb.h, engine group)"""
-    return int(lib().swb_layout_parts(int(n), int(ndev), int(min_part_sequences)))
+MIN_PART_SEQUENCES = 450000  # SWB_MIN_PART_SEQUENCES
+
+
+def layout_parts(n, ndev, min_part_sequences=MIN_PART_SEQUENCES, qoffsets=None):
+    """database parts P of the P x R device grid (include/swb.h, engine group); with the offsets of a batch, P also
+    makes sure the R = ndev / P query groups can be balanced (swb_layout_parts_batch)"""
+    if qoffsets is None:
+        return int(lib().swb_layout_parts(int(n), int(ndev), int(min_part_sequences)))
+    qoffsets = np.ascontiguousarray(qoffsets, dtype=np.uint64)
+    return int(lib().swb_layout_parts_batch(int(n), int(ndev), int(min_part_sequences), qoffsets.ctypes.data_as(_u64p),
+                                            len(qoffsets) - 1))
 
 
 def layout_query_groups(qoffsets, groups):

@@ -98,9 +98,10 @@ struct swb_engine {
     int rebase_shift32 = 0;   // the same for passes of 32 rows per lane (pipelined groups with split_k = 32)
     int opt_exact = 0;        // exact passes: 0 = V16R where the scheme allows it, 1 = always V32 (int32)
     int opt_split_k = 0;      // rows per lane of the pipelined-pass groups: 0 = auto, 8, 16
-    uint32_t opt_direct_len = 10000;  // pipelined tiles at least this wide against queries at least this long skip the
+    uint32_t opt_direct_len = 14000;  // pipelined tiles at least this wide against queries at least this long skip the
                               // plain s16 pass and are scored by V16R at once (their true scores pass 32767 anyway:
-                              // with the reference's gap of 2, random long sequences score ~2.7 per residue); 0 = never
+                              // with the reference's gap of 2, random long sequences score ~2.7 per residue, so pairs from ~12,000 residues
+                              // up overflow; measured on configs[3]: 10,000 / 14,000 -> 4,521 / 4,669 GCUPS); 0 = never
     int opt_split = -1;       // pipelined passes for the very long tiles: 1 on, 0 off, -1 auto = on for small shards
                               // (fewer tiles than twice the GPU's warp slots), where a few long tiles are the critical
                               // path of a query (+10 % at 1/8 of Swiss-Prot, +3 % at 1/4); on a large shard the bulk
@@ -655,6 +656,11 @@ static int shape_for(swb_engine *e, int K, int mode, bool split, uint32_t smem_r
     int per_sm = 0;
     CU(swb_score_occupancy(K, mode, split, ls.block_cfg, ls.smem, &per_sm));
     if (per_sm < 1) return fail(e, SWB_ERR_CUDA, "score kernel does not fit on an SM");
+    // Pipelined passes run one warp per block, and the passes of a tile advance at the pace of the slowest of them: an
+    // SM with 13 such warps has one scheduler with four and three with three, and every chain that has a pass on the
+    // crowded scheduler drags its other passes down with it (ncu: 40 % of the warp time spent waiting for the
+    // predecessor). Keep the schedulers evenly loaded: a multiple of four blocks per SM.
+    if (per_item && per_sm > 4 && !getenv("SWB_SPLIT_UNEVEN")) per_sm -= per_sm % 4;
     const int nt = per_item ? 32 : (ls.block_cfg == SWB_BLOCK_SMALL ? SWB_NT_SMALL : SWB_NT_LARGE);
     const int need = (int)((ntiles + nt / 32 - 1) / (nt / 32));
     const int slots = per_sm * e->sm_count;

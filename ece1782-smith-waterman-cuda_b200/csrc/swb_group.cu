@@ -78,7 +78,7 @@ struct swb_group {
     std::string err;
     int parts = 0;          // database parts P of the loaded layout (0 = nothing loaded)
     int parts_forced = 0;   // option "db_parts": 0 = choose per load
-    uint32_t min_part = 250000;  // option "min_part_sequences"
+    uint32_t min_part = SWB_MIN_PART_SEQUENCES;  // option "min_part_sequences"
     uint32_t n_total = 0;
     swb_stats_t stats;
     // runs f(device index) on every worker, returns the first error
@@ -246,6 +246,31 @@ extern "C" int swb_layout_query_groups(const uint64_t *qoffsets, uint32_t nq, in
         load[arg] += qoffsets[order[j] + 1] - qoffsets[order[j]] + 1;  // + 1: empty queries still spread out
     }
     return SWB_OK;
+}
+
+// The same with the batch in view: with P parts the queries split into R = ndev / P groups; if the batch is too small or
+// too uneven for R groups of (nearly) equal total length -- the heaviest group more than 2 % above the mean -- the next
+// larger P (fewer query groups) is taken.
+extern "C" int swb_layout_parts_batch(uint32_t n, int ndev, uint32_t min_part, const uint64_t *qoffsets, uint32_t nq)
+{
+    if (ndev < 1) return 1;
+    int P = swb_layout_parts(n, ndev, min_part);
+    if (!qoffsets || nq == 0) return P;
+    std::vector<uint32_t> group_of(nq);
+    for (; P < ndev; ++P) {
+        if (ndev % P) continue;
+        const int R = ndev / P;
+        swb_layout_query_groups(qoffsets, nq, R, group_of.data());
+        std::vector<uint64_t> load((size_t)R, 0);
+        uint64_t total = 0;
+        for (uint32_t q = 0; q < nq; ++q) {
+            load[group_of[q]] += qoffsets[q + 1] - qoffsets[q];
+            total += qoffsets[q + 1] - qoffsets[q];
+        }
+        const uint64_t heaviest = *std::max_element(load.begin(), load.end());
+        if ((double)heaviest * R <= 1.02 * (double)total) break;
+    }
+    return P;
 }
 
 extern "C" int swb_group_db_load(swb_group *g, const uint8_t *codes, const uint64_t *offsets, uint32_t n)

@@ -33,7 +33,12 @@
 #include <cuda_runtime.h>
 #include "swb_types.h"
 
-#define SWB_SPLIT_HYST 256u  // columns a pipelined pass lets its predecessor get ahead once it has had to wait
+#ifndef SWB_SPLIT_HYST
+// columns a pipelined pass lets its predecessor get ahead once it has had to wait. Measured on configs[3]: 0 / 16 / 32 /
+// 64 / 256 / 1024 -> 5,046 / 4,945 / 5,044 / 4,972 / 4,607 / 3,910 GCUPS: any margin only lengthens the fill of a tile's
+// pipeline, so a pass resumes as soon as the columns it needs are there.
+#define SWB_SPLIT_HYST 0u
+#endif
 #ifndef SWB_PF_CHUNKS
 #define SWB_PF_CHUNKS 6u  // chunks (of 4 columns) that the L2 prefetch of the one-lane tiles runs ahead
 #endif
@@ -547,9 +552,7 @@ struct V32A {
 // SPLIT (lane-group tiles of long sequences): the passes of one tile are separate work items taken by different warps,
 // which run as a pipeline over the columns. The warp of pass ss publishes how many columns of its bottom row are in the
 // boundary scratch (prog[ss], every 64 columns, release store); the warp of pass ss+1 polls it (acquire load, back-off)
-// before it reads them. A pass that had to wait resumes only once its predecessor is SWB_SPLIT_HYST columns ahead:
-// both run at the same speed, so that margin then lasts and the pass polls once per margin instead of stalling on a
-// round trip through L2 every few steps (ncu: 60 % of the stall samples of these kernels sat in the polling loop).
+// before it reads them (a resume margin, SWB_SPLIT_HYST, was measured and is 0).
 // Items are handed out by one counter, pass-major inside a lane-group class (pass 0 of every tile, then pass 1, ...): a
 // waiting warp always waits for an item that was handed out before its own, i.e. that a resident warp owns or has
 // finished -- no deadlock -- and only a few passes per tile are in flight at a time, so little of a launch's first wave

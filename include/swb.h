@@ -88,7 +88,7 @@ const char *swb_last_error(const swb_engine *e);
  *          "exact" (scores beyond the s16 range: 0 (default) = the rebased s16 policy where the scoring scheme allows it
  *          -- steps between neighbouring cells small enough for a 16-bit window -- else int32; 1 = always int32),
  *          "direct_len" (pipelined tiles at least this wide, against a query at least this long, skip the plain s16
- *          pass and are scored by the rebased policy at once; default 10000, 0 = never),
+ *          pass and are scored by the rebased policy at once; default 14000, 0 = never),
  *          "load_threads" (host threads that gather the residues of a sharded load, default 4),
  *          "chunk_rows" (query rows per launch for queries beyond shared memory; multiple of 1024, <= 7168) */
 int swb_set_option(swb_engine *e, const char *key, int64_t value);
@@ -149,8 +149,11 @@ int swb_align(swb_engine *e, const uint8_t *query, uint32_t qlen, uint32_t db_id
 /* One engine, one host worker thread and one stream set per device. The devices form P database parts x R query groups
  * (P * R = devices): device (p, r) keeps part p of the residue-balanced sharding resident and scores the queries of
  * group r of a batch (groups of equal total length, longest-processing-time first). P = the largest divisor of the
- * device count whose parts keep at least "min_part_sequences" sequences (default 250,000: smaller shards have fewer
- * warp tiles than a B200 has warp slots); option "db_parts" forces it (= devices: pure database sharding). */
+ * device count whose parts keep at least "min_part_sequences" sequences (default SWB_MIN_PART_SEQUENCES: measured on
+ * fractions of the benchmark database a B200 keeps its full rate down to about that size and loses 3 / 5 / 9 % at
+ * 1/2, 1/4, 1/8 of it, while a batch of a quarter of the 20 reference queries against the whole database loses 4 %);
+ * option "db_parts" forces it (= devices: pure database sharding). */
+#define SWB_MIN_PART_SEQUENCES 450000u
 typedef struct swb_group swb_group;
 /* devices == NULL: devices 0 .. ndev-1; ndev == 0: every visible device */
 int swb_group_create(swb_group **out, const int *devices, int ndev);
@@ -178,6 +181,9 @@ int swb_group_search_batch_topk(swb_group *g, const uint8_t *qcodes, const uint6
 int swb_group_stats(const swb_group *g, swb_stats_t *out);
 /* the layout rules, CPU only: P for n sequences on ndev devices; group_of[q] for R groups of a batch (LPT) */
 int swb_layout_parts(uint32_t n, int ndev, uint32_t min_part_sequences);
+/* the same with the batch in view: the next larger P while R = ndev / P query groups of (nearly) equal total length cannot
+ * be formed from this batch (heaviest group more than 2 % above the mean); bench.py lays out its ranks with it */
+int swb_layout_parts_batch(uint32_t n, int ndev, uint32_t min_part_sequences, const uint64_t *qoffsets, uint32_t nq);
 int swb_layout_query_groups(const uint64_t *qoffsets, uint32_t nq, int groups, uint32_t *group_of);
 
 /* ---- plan introspection, CPU only (host logic of swb_db_load) ------------------------------ */

@@ -108,9 +108,9 @@ def test_layout_rules(swb):
     """the P x R layout of the engine group / of bench.py's ranks: P = the largest divisor of the device count that
     keeps min_part sequences per part; query groups by longest-processing-time first"""
     assert swb.layout_parts(570065, 1) == 1
-    assert swb.layout_parts(570065, 2) == 2
-    assert swb.layout_parts(570065, 4) == 2
-    assert swb.layout_parts(570065, 8) == 2
+    assert swb.layout_parts(570065, 2) == 1
+    assert swb.layout_parts(570065, 8) == 1
+    assert swb.layout_parts(2 * 570065, 8) == 2
     assert swb.layout_parts(5700650, 8) == 8
     assert swb.layout_parts(100, 8) == 1
     assert swb.layout_parts(900, 6, 300) == 3
@@ -129,6 +129,14 @@ def test_layout_rules(swb):
     g = swb.layout_query_groups(_offsets(qlens), 8)
     load = np.bincount(g, weights=qlens.astype(float), minlength=8)
     assert load.max() / load.mean() < 1.001
+    # with the batch in view: 20 reference queries fill 2 or 4 groups evenly, not 8 (the longest query alone is 5 % above
+    # an eighth of the rows) -> two database parts on 8 devices; 1,000 queries fill 8 groups
+    assert swb.layout_parts(570065, 2, qoffsets=offs) == 1
+    assert swb.layout_parts(570065, 4, qoffsets=offs) == 1
+    assert swb.layout_parts(570065, 8, qoffsets=offs) == 2
+    assert swb.layout_parts(570065, 8, qoffsets=_offsets(qlens)) == 1
+    assert swb.layout_parts(5700650, 8, qoffsets=_offsets(qlens)) == 8
+    assert swb.layout_parts(570065, 8, qoffsets=_offsets([100])) == 8
     # more groups than queries: the extra groups stay empty, nothing is lost
     g = swb.layout_query_groups(_offsets([5, 9]), 4)
     assert sorted(g.tolist()) == [0, 1] or len(set(g.tolist())) == 2

@@ -668,6 +668,26 @@ def main():
                 line["ref_cuda_baseline"] = ref_cuda_leg(["P02232", "P01008", "P27895"])
             except Exception as ex:
                 line["ref_cuda_baseline"] = {"unavailable": repr(ex)}
+        if world == 1 and not args.affine and not big and top_ok is not None:
+            # traceback of the hit lists (cpu.cpp:76-108): every top-k hit of every query in one
+            # launch of swb_align_batch, wall clock incl. the copies; the aligned scores must equal the scan's
+            try:
+                hits = [(local_of[qi], int(sid)) for qi in mine for sid in dev_ids[local_of[qi]] if int(sid) != 0xFFFFFFFF]
+                want = [int(v) for qi in mine for sid, v in zip(dev_ids[local_of[qi]], dev_top[local_of[qi]])
+                        if int(sid) != 0xFFFFFFFF]
+                lens = [int(offsets[sid + 1] - offsets[sid]) for _, sid in hits]
+                mine_q = [qs[qi] for qi in mine]
+                eng.align_batch(mine_q, hits, lens)  # allocations
+                t0 = time.perf_counter()
+                res = eng.align_batch(mine_q, hits, lens)
+                dt = time.perf_counter() - t0
+                acells = float(sum(len(mine_q[h[0]]) * l for h, l in zip(hits, lens)))
+                line["align"] = {"hits": len(hits), "ms": dt * 1e3, "cells": acells, "gcups": acells / dt * 1e-9,
+                                 "scores_equal_scan": bool([r[0] for r in res] == want),
+                                 "api": "swb_align_batch: top-%d hits of %d queries, one launch, ops copied back" % (
+                                     args.topk, len(mine))}
+            except Exception as ex:
+                line["align"] = {"unavailable": repr(ex)}
         if args.per_query:
             pq = {}
             for nme, q in zip(names, qs):

@@ -77,7 +77,7 @@ ABI_SYMBOLS = [
     "swb_group_db_parts", "swb_group_set_option", "swb_group_set_scoring", "swb_group_set_scoring_preset",
     "swb_group_set_scoring_affine", "swb_group_db_load", "swb_group_search_batch", "swb_group_search_batch_topk",
     "swb_group_stats", "swb_layout_parts", "swb_layout_parts_batch", "swb_layout_query_groups",
-    "swb_microbench", "swb_align", "swb_read_fasta", "swb_read_uniprot_dat", "swb_free", "swb_dbfile_write",
+    "swb_microbench", "swb_align", "swb_align_batch", "swb_read_fasta", "swb_read_uniprot_dat", "swb_free", "swb_dbfile_write",
     "swb_dbfile_open", "swb_dbfile_count", "swb_dbfile_first_id", "swb_dbfile_offsets", "swb_dbfile_codes",
     "swb_dbfile_close",
 ]
@@ -182,6 +182,9 @@ def lib():
                                     ctypes.POINTER(SwbPlanInfo), _u32p, _u32p]
     L.swb_align.restype = ctypes.c_int
     L.swb_align.argtypes = [vp, _u8p, ctypes.c_uint32, ctypes.c_uint32, _i32p, _u32p, _u32p, _u8p, ctypes.c_uint32, _u32p]
+    L.swb_align_batch.restype = ctypes.c_int
+    L.swb_align_batch.argtypes = [vp, _u8p, _u64p, ctypes.c_uint32, _u32p, _u32p, ctypes.c_uint32, _i32p, _u32p, _u32p,
+                                  _u8p, _u64p, _u32p]
     L.swb_read_fasta.restype = ctypes.c_int
     L.swb_read_fasta.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(_u8p), ctypes.POINTER(_u64p), _u32p,
                                  _i32p]
@@ -490,6 +493,30 @@ class Engine:
         self._check(self._L.swb_align(self._h, qp, len(q), int(db_id), ctypes.byref(score), ctypes.byref(ei),
                                       ctypes.byref(ej), ops.ctypes.data_as(_u8p), cap, ctypes.byref(n)), "swb_align")
         return int(score.value), int(ei.value), int(ej.value), ops[:n.value].copy()
+
+    def align_batch(self, queries, hits, subject_lens):
+        """traceback alignments of a list of hits in one launch (swb_align_batch). queries: list of code arrays; hits:
+        list of (query index, db id); subject_lens: the subject length of every hit (sizes the ops buffers). Returns a
+        list of (score, end_i, end_j, ops)."""
+        qcodes, qoffs = pack_sequences([np.ascontiguousarray(q, dtype=np.uint8) for q in queries])
+        nh = len(hits)
+        hq = np.ascontiguousarray([h[0] for h in hits], dtype=np.uint32)
+        hd = np.ascontiguousarray([h[1] for h in hits], dtype=np.uint32)
+        room = np.asarray([len(queries[int(h[0])]) + int(l) + 1 for h, l in zip(hits, subject_lens)], dtype=np.uint64)
+        ooff = np.zeros(nh + 1, dtype=np.uint64)
+        ooff[1:] = np.cumsum(room)
+        ops = np.zeros(max(int(ooff[-1]), 1), dtype=np.uint8)
+        scores = np.zeros(max(nh, 1), dtype=np.int32)
+        ei = np.zeros(max(nh, 1), dtype=np.uint32)
+        ej = np.zeros(max(nh, 1), dtype=np.uint32)
+        cnt = np.zeros(max(nh, 1), dtype=np.uint32)
+        self._check(self._L.swb_align_batch(self._h, qcodes.ctypes.data_as(_u8p), qoffs.ctypes.data_as(_u64p), len(queries),
+                                            hq.ctypes.data_as(_u32p), hd.ctypes.data_as(_u32p), nh,
+                                            scores.ctypes.data_as(_i32p), ei.ctypes.data_as(_u32p),
+                                            ej.ctypes.data_as(_u32p), ops.ctypes.data_as(_u8p),
+                                            ooff.ctypes.data_as(_u64p), cnt.ctypes.data_as(_u32p)), "swb_align_batch")
+        return [(int(scores[h]), int(ei[h]), int(ej[h]), ops[int(ooff[h]):int(ooff[h]) + int(cnt[h])].copy())
+                for h in range(nh)]
 
     def stats(self):
         s = SwbStats()

@@ -132,8 +132,11 @@ struct swb_engine {
     uint32_t last_nq = 0;
     Slot slots[SWB_MAX_SLOTS];
     // scratch of swb_align (grow-only)
-    int32_t *d_align_h = nullptr;
-    uint8_t *d_align_dir = nullptr;
+    int32_t *d_align_h = nullptr;   // rolling H diagonals of the jobs too long for shared memory
+    uint8_t *d_align_dir = nullptr; // 2-bit directions of a wave of jobs
+    uint8_t *d_align_q = nullptr;   // the query codes of a swb_align_batch call
+    SwbAlignJob *d_align_jobs = nullptr;
+    size_t align_q_cap = 0, align_jobs_cap = 0;
     uint8_t *d_align_out = nullptr;  // [5 ints header | ops]
     uint8_t *h_align_out = nullptr;  // pinned
     size_t align_h_cap = 0, align_dir_cap = 0, align_out_cap = 0, align_hout_cap = 0;
@@ -204,6 +207,11 @@ static void free_db(swb_engine *e)
     e->tiles_cap = e->residues_cap = e->out_pos_cap = e->raw_cap = e->seq_off_cap = e->seq_len_cap = e->shard_ids_cap = 0;
     e->out_cap = 0;
     if (e->d_align_h) cudaFree(e->d_align_h);
+    if (e->d_align_q) cudaFree(e->d_align_q);
+    if (e->d_align_jobs) cudaFree(e->d_align_jobs);
+    e->d_align_q = nullptr;
+    e->d_align_jobs = nullptr;
+    e->align_q_cap = e->align_jobs_cap = 0;
     if (e->d_align_dir) cudaFree(e->d_align_dir);
     if (e->d_align_out) cudaFree(e->d_align_out);
     if (e->h_align_out) cudaFreeHost(e->h_align_out);
@@ -547,9 +555,53 @@ int swb_db_load_sorted(swb_engine *e, const uint8_t *codes, const uint64_t *offs
         planner.join();
         if (urc != SWB_OK) return urc;
     } else {
-        rc = swb_build_plan(offsets, n, shard, nshards, e->plan_opts, e->plan, sorted_order);
+        // A sharded load needs the head of the plan (the shard's sequences in sorted order) before it can gather; the
+        // tail (output order, tiles) is built on the helper thread beside the gather and the upload.
+        rc = swb_build_plan_head(offsets, n, shard, nshards, e->plan, sorted_order);
+        if (rc == 0) {
+            if (nshards > 1 && e->plan.n_local > 0)
+                planner = std::thread([&]() { swb_build_plan_tail(e->plan_opts, e->plan); });
+            else
+                swb_build_plan_tail(e->plan_opts, e->plan);
+        }
     }
+    struct Joiner {  // every return below joins the helper first
+        std::thread &t;
+        ~Joiner() { if (t.joinable()) t.join(); }
+    } joiner{planner};
     if (rc != 0) return fail(e, SWB_ERR_ARG, "bad offsets (decreasing, or a sequence longer than 2^31-16)");
+    const double t0b = wall_ms();
+    // a sharded load uploads only the shard's residues (gathered in sorted order), a full load the caller's buffer
+    const bool gather = nshards > 1;
+    std::vector<uint64_t> goff;
+    if (gather && e->plan.n_local > 0) {
+        // positions in the gathered stream, then the stream itself through the two pinned staging buffers: the host
+        // gather of slice i+1 (a few threads, byte-balanced) overlaps the asynchronous H2D of slice i. Reads seq_len and
+        // seq_off of the plan, which the tail does not touch.
+        const SwbPlan &ph = e->plan;
+        const uint32_t nl0 = ph.n_local;
+        const uint64_t raw_bytes0 = ph.residues_local;
+        goff.resize((size_t)nl0 + 1);
+        goff[0] = 0;
+        for (uint32_t s = 0; s < nl0; ++s) goff[s + 1] = goff[s] + ph.seq_len[s];
+        CU(GROW_DEV(e->d_raw, e->raw_cap, raw_bytes0));
+        if (raw_bytes0) {
+            const size_t stage = (size_t)std::min<uint64_t>(SWB_STAGE_BYTES, raw_bytes0);
+            for (int i = 0; i < 2; ++i) {
+                CU(GROW_HOST(e->h_stage[i], e->stage_cap[i], stage));
+                if (!e->ev_stage[i]) CU(cudaEventCreateWithFlags(&e->ev_stage[i], cudaEventDisableTiming));
+            }
+            int b = 0;
+            for (uint64_t done = 0; done < raw_bytes0; done += stage, b ^= 1) {
+                const uint64_t len = std::min<uint64_t>(stage, raw_bytes0 - done);
+                CU(cudaEventSynchronize(e->ev_stage[b]));
+                gather_range(ph, goff, codes, done, done + len, e->h_stage[b], e->load_threads);
+                CU(cudaMemcpyAsync(e->d_raw + done, e->h_stage[b], (size_t)len, cudaMemcpyHostToDevice, st));
+                CU(cudaEventRecord(e->ev_stage[b], st));
+            }
+        }
+    }
+    if (planner.joinable()) planner.join();
     const double t1 = wall_ms();
     SwbPlan &pl = e->plan;
     e->max_logg = 0;
@@ -558,8 +610,6 @@ int swb_db_load_sorted(swb_engine *e, const uint8_t *codes, const uint64_t *offs
     const uint32_t nl = pl.n_local;
     const uint32_t ntiles = (uint32_t)pl.tiles.size();
     const uint64_t base = n ? offsets[0] : 0;
-    // a sharded load uploads only the shard's residues (gathered in sorted order), a full load the caller's buffer
-    const bool gather = nshards > 1;
     const uint64_t raw_bytes = gather ? pl.residues_local : pl.residues_total;
     double t2 = t1, t3 = t1;
 
@@ -574,26 +624,6 @@ int swb_db_load_sorted(swb_engine *e, const uint8_t *codes, const uint64_t *offs
         for (int i = 0; i < SWB_MAX_SLOTS; ++i) e->slots[i].ready = false;  // per-stream scratch is (re)sized on first use
         t2 = wall_ms();
         if (gather) {
-            // positions in the gathered stream, then the stream itself through the two pinned staging buffers: the host
-            // gather of slice i+1 (a few threads, byte-balanced) overlaps the asynchronous H2D of slice i
-            std::vector<uint64_t> goff(nl + 1);
-            goff[0] = 0;
-            for (uint32_t s = 0; s < nl; ++s) goff[s + 1] = goff[s] + pl.seq_len[s];
-            if (raw_bytes) {
-                const size_t stage = (size_t)std::min<uint64_t>(SWB_STAGE_BYTES, raw_bytes);
-                for (int i = 0; i < 2; ++i) {
-                    CU(GROW_HOST(e->h_stage[i], e->stage_cap[i], stage));
-                    if (!e->ev_stage[i]) CU(cudaEventCreateWithFlags(&e->ev_stage[i], cudaEventDisableTiming));
-                }
-                int b = 0;
-                for (uint64_t done = 0; done < raw_bytes; done += stage, b ^= 1) {
-                    const uint64_t len = std::min<uint64_t>(stage, raw_bytes - done);
-                    CU(cudaEventSynchronize(e->ev_stage[b]));
-                    gather_range(pl, goff, codes, done, done + len, e->h_stage[b], e->load_threads);
-                    CU(cudaMemcpyAsync(e->d_raw + done, e->h_stage[b], (size_t)len, cudaMemcpyHostToDevice, st));
-                    CU(cudaEventRecord(e->ev_stage[b], st));
-                }
-            }
             for (uint32_t s = 0; s < nl; ++s) pl.seq_off[s] = goff[s];  // offsets into the uploaded buffer
             CU(cudaMemcpyAsync(e->d_shard_ids, pl.shard_ids.data(), sizeof(uint32_t) * nl, cudaMemcpyHostToDevice, st));
         } else {
@@ -610,8 +640,9 @@ int swb_db_load_sorted(swb_engine *e, const uint8_t *codes, const uint64_t *offs
     e->db_loaded = true;
     e->stats.load_ms = wall_ms() - t0;
     if (timing)
-        fprintf(stderr, "[swb] db_load: plan %.1f ms, alloc %.1f ms, stage+h2d enqueue %.1f ms, pack+sync %.1f ms, total %.1f ms\n",
-                t1 - t0, t2 - t1, t3 - t2, wall_ms() - t3, e->stats.load_ms);
+        fprintf(stderr, "[swb] db_load: plan (unsharded: beside the upload; sharded: its head) %.1f ms, sharded gather + h2d enqueue "
+                        "beside the plan's tail %.1f ms, alloc %.1f ms, tables h2d enqueue %.1f ms, pack+sync %.1f ms, total %.1f ms\n",
+                t0b - t0, t1 - t0b, t2 - t1, t3 - t2, wall_ms() - t3, e->stats.load_ms);
     e->stats.db_residues = pl.residues_local;
     e->stats.db_residues_total = pl.residues_total;
     e->stats.db_sequences = nl;
@@ -747,8 +778,7 @@ static int enqueue_pass(swb_engine *e, Slot &s, int mode, SwbScoreParams &p, con
             p.last_chunk = ch.last;
             p.counter = s.d_counters + counter++;
             CU(swb_launch_score(g.K, gmode, g.split, ls.block_cfg, p, ls.grid, ls.smem, st));
-            e->stats.kernel_launches += 1;
-        }
+            }
         p.recount = recount;
     }
     for (size_t gi = 1; gi < ng; ++gi) {  // join
@@ -914,8 +944,7 @@ static int enqueue_job(swb_engine *e, Slot &s, uint32_t qi, const uint8_t *q, ui
         if (g1[0].split) {  // pipelined work items combine their scores with atomicMax
             CU(cudaMemsetAsync(s.d_prog, 0, sizeof(uint32_t) * prog_words1, s.stream));
             CU(swb_launch_clear_flagged(e->d_tiles, (uint32_t)pl.tiles.size(), s.d_flags, p.scores, s.stream));
-            e->stats.kernel_launches += 1;
-        }
+            }
         if ((rc = enqueue_pass(e, s, mode1, p, qp1, g1, counter, s.d_prog, nullptr, nullptr)) != SWB_OK) return rc;
     }
     CU(swb_launch_scatter(s.d_sorted, e->d_out_pos, nl, out, s.stream));
@@ -988,7 +1017,6 @@ static int enqueue_results(swb_engine *e, Slot &s, uint32_t qa, const BatchOut &
         CU(GROW_HOST(s.h_topk, s.h_topk_cap, bytes));
         CU(swb_launch_topk(e->d_out + (size_t)qa * nl, nl, e->plan.nshards > 1 ? e->d_shard_ids : nullptr, bo.k, s.d_topk,
                            reinterpret_cast<int32_t *>(s.d_topk + bo.k), s.stream));
-        e->stats.kernel_launches += 1;
         CU(cudaMemcpyAsync(s.h_topk, s.d_topk, bytes, cudaMemcpyDeviceToHost, s.stream));
         s.pending_ids = bo.ids + (size_t)qa * bo.k;
         s.pending_top = bo.top + (size_t)qa * bo.k;
@@ -1165,61 +1193,124 @@ extern "C" int swb_fetch_scores(swb_engine *e, uint32_t query_index, int32_t *sc
     return SWB_OK;
 }
 
+// Traceback alignments of a list of hits in one launch (one block per hit; swb_kernels.cu). Hits are processed in waves
+// whose direction matrices (2 bits per cell) fit SWB_ALIGN_DIR_BUDGET; a wave is one kernel launch.
+#define SWB_ALIGN_DIR_BUDGET (4ull << 30)
+extern "C" int swb_align_batch(swb_engine *e, const uint8_t *qcodes, const uint64_t *qoffsets, uint32_t nq,
+                               const uint32_t *hit_query, const uint32_t *hit_db_id, uint32_t nhits, int32_t *scores,
+                               uint32_t *end_i, uint32_t *end_j, uint8_t *ops, const uint64_t *ops_offsets,
+                               uint32_t *nops)
+{
+    if (!e || !qoffsets || (nhits && (!hit_query || !hit_db_id || !scores)) || (ops && !ops_offsets)) return SWB_ERR_ARG;
+    if (!e->db_loaded) return fail(e, SWB_ERR_STATE, "swb_align before swb_db_load");
+    if (e->affine) return fail(e, SWB_ERR_STATE, "swb_align implements the linear gap model only");
+    for (uint32_t i = 0; i < nq; ++i)
+        if (qoffsets[i + 1] < qoffsets[i] || qoffsets[i + 1] - qoffsets[i] > 0x7ffffff0ull)
+            return fail(e, SWB_ERR_ARG, "bad query offsets");
+    const uint64_t qbytes = nq ? qoffsets[nq] - qoffsets[0] : 0;
+    if (qbytes && !qcodes) return SWB_ERR_ARG;
+    const SwbPlan &pl = e->plan;
+    std::vector<SwbAlignJob> jobs(nhits);
+    std::vector<uint32_t> live;  // hits with a non-empty matrix
+    live.reserve(nhits);
+    for (uint32_t h = 0; h < nhits; ++h) {
+        if (hit_query[h] >= nq) return fail(e, SWB_ERR_ARG, "hit_query out of range");
+        const std::vector<uint32_t>::const_iterator it =
+            std::lower_bound(pl.shard_ids.begin(), pl.shard_ids.end(), hit_db_id[h]);
+        if (it == pl.shard_ids.end() || *it != hit_db_id[h]) return fail(e, SWB_ERR_ARG, "db_id is not part of this shard");
+        const uint32_t spos = pl.sorted_of_out[(size_t)(it - pl.shard_ids.begin())];
+        SwbAlignJob &jb = jobs[h];
+        memset(&jb, 0, sizeof jb);
+        jb.q_off = qoffsets[hit_query[h]] - qoffsets[0];
+        jb.d_off = pl.seq_off[spos];
+        jb.m = (uint32_t)(qoffsets[hit_query[h] + 1] - qoffsets[hit_query[h]]);
+        jb.n = pl.seq_len[spos];
+        const uint64_t room = ops ? ops_offsets[h + 1] - ops_offsets[h] : 0;
+        if (ops && ops_offsets[h + 1] < ops_offsets[h]) return fail(e, SWB_ERR_ARG, "bad ops offsets");
+        jb.cap = (uint32_t)std::min<uint64_t>(room, 0xffffffffull);
+        scores[h] = 0;
+        if (end_i) end_i[h] = 0;
+        if (end_j) end_j[h] = 0;
+        if (nops) nops[h] = 0;
+        if (jb.m == 0 || jb.n == 0) continue;
+        if ((uint64_t)(jb.m + 1) * (((uint64_t)jb.n + 4) >> 2) > SWB_ALIGN_DIR_BUDGET)
+            return fail(e, SWB_ERR_ARG, "alignment matrix larger than 2^34 cells");
+        live.push_back(h);
+    }
+    if (live.empty()) return SWB_OK;
+    CU(cudaSetDevice(e->device));
+    cudaStream_t st = main_stream(e);
+    CU(GROW_DEV(e->d_align_q, e->align_q_cap, (size_t)qbytes));
+    CU(cudaMemcpyAsync(e->d_align_q, qcodes + qoffsets[0], (size_t)qbytes, cudaMemcpyHostToDevice, st));
+    const uint32_t smem_cap_ints = SWB_ALIGN_SMEM_MAX / sizeof(int32_t);
+    size_t at = 0;
+    while (at < live.size()) {
+        // one wave: as many of the remaining hits as the direction budget holds (at least one)
+        size_t end = at;
+        uint64_t dir_bytes = 0, hd_ints = 0, ops_bytes = 0;
+        uint32_t smem_ints = 0;
+        std::vector<SwbAlignJob> wave;
+        while (end < live.size()) {
+            SwbAlignJob jb = jobs[live[end]];
+            const uint64_t need = (uint64_t)(jb.m + 1) * (((uint64_t)jb.n + 4) >> 2);
+            if (end > at && dir_bytes + need > SWB_ALIGN_DIR_BUDGET) break;
+            jb.dir_off = dir_bytes;
+            dir_bytes += (need + 15u) & ~15ull;
+            jb.ops_off = ops_bytes;
+            ops_bytes += jb.cap;
+            const uint64_t hd = 3ull * (jb.m + 2);
+            if (hd <= smem_cap_ints) {
+                smem_ints = std::max<uint32_t>(smem_ints, (uint32_t)hd);
+            } else {
+                jb.hd_off = hd_ints;
+                hd_ints += hd;
+            }
+            wave.push_back(jb);
+            ++end;
+        }
+        const size_t nw = wave.size();
+        const size_t out_bytes = 5 * sizeof(int32_t) * nw + (size_t)ops_bytes;
+        CU(GROW_DEV(e->d_align_jobs, e->align_jobs_cap, sizeof(SwbAlignJob) * nw));
+        CU(GROW_DEV(e->d_align_h, e->align_h_cap, sizeof(int32_t) * (size_t)std::max<uint64_t>(hd_ints, 1)));
+        CU(GROW_DEV(e->d_align_dir, e->align_dir_cap, (size_t)dir_bytes));
+        CU(GROW_DEV(e->d_align_out, e->align_out_cap, out_bytes));
+        CU(GROW_HOST(e->h_align_out, e->align_hout_cap, out_bytes));
+        CU(cudaMemcpyAsync(e->d_align_jobs, wave.data(), sizeof(SwbAlignJob) * nw, cudaMemcpyHostToDevice, st));
+        int32_t *d_hdr = reinterpret_cast<int32_t *>(e->d_align_out);
+        uint8_t *d_ops = e->d_align_out + 5 * sizeof(int32_t) * nw;
+        CU(swb_launch_align_batch(e->d_align_jobs, (uint32_t)nw, e->d_align_q, e->d_raw, e->d_mat, e->gap, e->d_align_h,
+                                  e->d_align_dir, d_hdr, d_ops, smem_ints, st));
+        CU(cudaMemcpyAsync(e->h_align_out, e->d_align_out, out_bytes, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));  // the pageable `wave` vector was the source of an async copy: done by now
+        const int32_t *hdr = reinterpret_cast<const int32_t *>(e->h_align_out);
+        const uint8_t *hops = e->h_align_out + 5 * sizeof(int32_t) * nw;
+        for (size_t w = 0; w < nw; ++w) {
+            const uint32_t h = live[at + w];
+            scores[h] = hdr[5 * w];
+            if (end_i) end_i[h] = (uint32_t)hdr[5 * w + 1];
+            if (end_j) end_j[h] = (uint32_t)hdr[5 * w + 2];
+            const uint32_t cnt = (uint32_t)hdr[5 * w + 3];
+            if (nops) nops[h] = cnt;
+            if (!ops) continue;
+            if (hdr[5 * w + 4] || cnt > wave[w].cap)
+                return fail(e, SWB_ERR_ARG, "ops buffer too small (qlen + subject length always suffices)");
+            // the kernel walks from the end of the alignment to its start (cpu.cpp:80-103); hand it out start to end
+            uint8_t *dst = ops + ops_offsets[h];
+            const uint8_t *src = hops + wave[w].ops_off;
+            for (uint32_t k = 0; k < cnt; ++k) dst[k] = src[cnt - 1 - k];
+        }
+        at = end;
+    }
+    return SWB_OK;
+}
+
 extern "C" int swb_align(swb_engine *e, const uint8_t *query, uint32_t qlen, uint32_t db_id, int32_t *score,
                          uint32_t *end_i, uint32_t *end_j, uint8_t *ops, uint32_t cap, uint32_t *nops)
 {
     if (!e || (!query && qlen) || !score) return SWB_ERR_ARG;
-    if (!e->db_loaded) return fail(e, SWB_ERR_STATE, "swb_align before swb_db_load");
-    if (e->affine) return fail(e, SWB_ERR_STATE, "swb_align implements the linear gap model only");
-    const SwbPlan &pl = e->plan;
-    const std::vector<uint32_t>::const_iterator it = std::lower_bound(pl.shard_ids.begin(), pl.shard_ids.end(), db_id);
-    if (it == pl.shard_ids.end() || *it != db_id) return fail(e, SWB_ERR_ARG, "db_id is not part of this shard");
-    const uint32_t spos = pl.sorted_of_out[(size_t)(it - pl.shard_ids.begin())];
-    const uint32_t n = pl.seq_len[spos], m = qlen;
-    *score = 0;
-    if (end_i) *end_i = 0;
-    if (end_j) *end_j = 0;
-    if (nops) *nops = 0;
-    if (m == 0 || n == 0) return SWB_OK;
-    const uint64_t cells = (uint64_t)(m + 1) * (n + 1);
-    if (cells > (1ull << 31)) return fail(e, SWB_ERR_ARG, "alignment matrix larger than 2^31 cells");
-    CU(cudaSetDevice(e->device));
-    cudaStream_t st = main_stream(e);
-    Slot &s = e->slots[0];
-    if (qlen > s.query_cap) {
-        CU(cudaStreamSynchronize(s.stream));
-        if (s.h_query) cudaFreeHost(s.h_query);
-        if (s.d_query) cudaFree(s.d_query);
-        s.h_query = nullptr;
-        s.d_query = nullptr;
-        s.query_cap = 0;
-        const uint32_t qcap = swb_roundup(qlen, 4096);
-        CU(cudaMallocHost(&s.h_query, qcap));
-        CU(cudaMalloc(&s.d_query, qcap));
-        s.query_cap = qcap;
-    }
-    const size_t out_bytes = 5 * sizeof(int32_t) + (size_t)cap;
-    CU(GROW_DEV(e->d_align_h, e->align_h_cap, sizeof(int32_t) * 3 * (size_t)(m + 2)));
-    CU(GROW_DEV(e->d_align_dir, e->align_dir_cap, (size_t)cells));
-    CU(GROW_DEV(e->d_align_out, e->align_out_cap, out_bytes));
-    CU(GROW_HOST(e->h_align_out, e->align_hout_cap, out_bytes));
-    memcpy(s.h_query, query, qlen);
-    CU(cudaMemcpyAsync(s.d_query, s.h_query, qlen, cudaMemcpyHostToDevice, st));
-    CU(swb_launch_align(s.d_query, m, e->d_raw + pl.seq_off[spos], n, e->d_mat, e->gap, e->d_align_h, e->d_align_dir,
-                        reinterpret_cast<int32_t *>(e->d_align_out), e->d_align_out + 5 * sizeof(int32_t), cap, st));
-    CU(cudaMemcpyAsync(e->h_align_out, e->d_align_out, out_bytes, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    const int32_t *hdr = reinterpret_cast<const int32_t *>(e->h_align_out);
-    *score = hdr[0];
-    if (end_i) *end_i = (uint32_t)hdr[1];
-    if (end_j) *end_j = (uint32_t)hdr[2];
-    const uint32_t cnt = (uint32_t)hdr[3];
-    if (nops) *nops = cnt;
-    if (hdr[4] || cnt > cap) return fail(e, SWB_ERR_ARG, "ops buffer too small (qlen + subject length always suffices)");
-    // the kernel walks from the end of the alignment to its start (cpu.cpp:80-103); hand it out start to end
-    if (ops)
-        for (uint32_t k = 0; k < cnt; ++k) ops[k] = e->h_align_out[5 * sizeof(int32_t) + (cnt - 1 - k)];
-    return SWB_OK;
+    const uint64_t qoff[2] = {0, qlen}, ooff[2] = {0, ops ? cap : 0u};
+    const uint32_t hq = 0;
+    return swb_align_batch(e, query, qoff, 1, &hq, &db_id, 1, score, end_i, end_j, ops, ooff, nops);
 }
 
 extern "C" int swb_topk(const swb_engine *e, const int32_t *scores, uint32_t k, uint32_t *ids, int32_t *top)

@@ -464,20 +464,36 @@ cudaError_t swb_launch_topk(const int32_t *scores, uint32_t n, const uint32_t *i
 }
 
 // ---------------------------------------------------------------------------------------------
-// Alignment with traceback for one (query, subject) pair -- what the reference's cpu.cpp prints for two strings
+// Alignments with traceback for a list of (query, subject) hits -- what the reference's cpu.cpp prints for two strings
 // (cpu.cpp:39-103): fill with the update order LEFT, TOP, DIAG and strict '>' (cpu.cpp:47-64), keep the first
 // row-major maximum (cpu.cpp:66-70), walk back until a cell with no direction, i.e. H == 0 (cpu.cpp:80-103).
-// One block; anti-diagonal wavefront; three rolling H diagonals in global scratch; one direction byte per cell.
-__global__ void __launch_bounds__(512) swb_align_kernel(const uint8_t *__restrict__ q, uint32_t m,
-                                                        const uint8_t *__restrict__ d, uint32_t n,
-                                                        const int8_t *__restrict__ mat, int gap, int32_t *hdiag,
-                                                        uint8_t *dir, int32_t *out_hdr, uint8_t *out_ops, uint32_t cap)
+// One block per hit, all hits of a list in one launch. Anti-diagonal wavefront; the three rolling H diagonals live in
+// shared memory (in global scratch only for queries beyond ~18,000 rows); directions are packed 2 bits per cell,
+// rows of ceil((n + 1) / 4) bytes. A row always belongs to the same thread (row i -> thread (i - 1) mod block), so
+// the four cells of a direction byte are written by one thread on four consecutive diagonals: plain read-modify-write,
+// no atomics, and no clearing pass (the first cell written in a byte overwrites it).
+__global__ void __launch_bounds__(SWB_ALIGN_NT) swb_align_batch_kernel(const SwbAlignJob *__restrict__ jobs,
+                                                                       const uint8_t *__restrict__ qbuf,
+                                                                       const uint8_t *__restrict__ raw,
+                                                                       const int8_t *__restrict__ mat, int gap,
+                                                                       int32_t *hd_glob, uint8_t *dirbuf,
+                                                                       int32_t *out_hdr, uint8_t *out_ops,
+                                                                       uint32_t smem_ints)
 {
-    __shared__ int s_best[512];
-    __shared__ uint32_t s_bi[512], s_bj[512];
-    const uint32_t W = n + 1;
-    int32_t *h0 = hdiag, *h1 = hdiag + (m + 2), *h2 = hdiag + 2 * (size_t)(m + 2);
-    for (uint32_t i = threadIdx.x; i < 3 * (m + 2); i += blockDim.x) hdiag[i] = 0;
+    extern __shared__ int32_t s_hd[];
+    __shared__ int8_t s_mat[SWB_ALPHA * SWB_ALPHA];
+    __shared__ int s_best[SWB_ALIGN_NT];
+    __shared__ uint32_t s_bi[SWB_ALIGN_NT], s_bj[SWB_ALIGN_NT];
+    const SwbAlignJob jb = jobs[blockIdx.x];
+    const uint32_t m = jb.m, n = jb.n;
+    const uint8_t *q = qbuf + jb.q_off, *d = raw + jb.d_off;
+    uint8_t *dir = dirbuf + jb.dir_off;
+    const uint32_t Wb = (n + 4u) >> 2;  // bytes per direction row (columns 0 .. n)
+    const uint32_t tid = threadIdx.x;
+    int32_t *hd = 3u * (m + 2u) <= smem_ints ? s_hd : hd_glob + jb.hd_off;
+    int32_t *h0 = hd, *h1 = hd + (m + 2), *h2 = hd + 2 * (size_t)(m + 2);
+    for (uint32_t i = tid; i < 3 * (m + 2); i += SWB_ALIGN_NT) hd[i] = 0;
+    for (uint32_t i = tid; i < SWB_ALPHA * SWB_ALPHA; i += SWB_ALIGN_NT) s_mat[i] = mat[i];
     int best = 0;
     uint32_t bi = 0, bj = 0;
     __syncthreads();
@@ -485,64 +501,83 @@ __global__ void __launch_bounds__(512) swb_align_kernel(const uint8_t *__restric
     for (uint32_t dd = 2; dd <= m + n; ++dd) {
         const uint32_t ilo = dd > n ? dd - n : 1u;
         const uint32_t ihi = dd - 1 < m ? dd - 1 : m;
-        for (uint32_t i = ilo + threadIdx.x; i <= ihi; i += blockDim.x) {
+        // cells outside [ilo, ihi] of the new diagonal are borders (H = 0) for the next two diagonals
+        if (tid == 0) {
+            h2[ilo - 1] = 0;
+            h2[ihi + 1] = 0;
+        }
+        // first row of this thread at or after ilo
+        uint32_t i = ilo + (tid + SWB_ALIGN_NT - ((ilo - 1u) % SWB_ALIGN_NT)) % SWB_ALIGN_NT;
+        for (; i <= ihi; i += SWB_ALIGN_NT) {
             const uint32_t j = dd - i;
             int h = 0;
-            uint8_t t = 0;
+            uint32_t t = 0;
             const int left = h1[i] - gap;      // H(i, j-1)
             const int up = h1[i - 1] - gap;    // H(i-1, j)
-            const int dg = h0[i - 1] + mat[(uint32_t)(q[i - 1] & 31u) * SWB_ALPHA + (d[j - 1] & 31u)];
+            const int dg = h0[i - 1] + s_mat[(uint32_t)(q[i - 1] & 31u) * SWB_ALPHA + (d[j - 1] & 31u)];
             if (left > h) { h = left; t = 1; }
             if (up > h) { h = up; t = 2; }
             if (dg > h) { h = dg; t = 3; }
             h2[i] = h;
-            dir[(size_t)i * W + j] = t;
+            uint8_t *bp = dir + (size_t)i * Wb + (j >> 2);
+            const uint32_t sh = 2u * (j & 3u);
+            const uint32_t old = ((j & 3u) == 0u || j == 1u) ? 0u : (uint32_t)*bp;
+            *bp = (uint8_t)((old & ~(3u << sh)) | (t << sh));
             // first row-major maximum: larger value, else smaller i, else smaller j
             if (h > best || (h == best && h > 0 && (i < bi || (i == bi && j < bj)))) { best = h; bi = i; bj = j; }
-        }
-        __syncthreads();
-        // cells outside [ilo, ihi] of the new diagonal are borders (H = 0) for the next two diagonals
-        if (threadIdx.x == 0) {
-            if (ilo >= 1) h2[ilo - 1] = 0;
-            if (ihi + 1 <= m + 1) h2[ihi + 1] = 0;
         }
         int32_t *tmp = h0; h0 = h1; h1 = h2; h2 = tmp;
         __syncthreads();
     }
-    s_best[threadIdx.x] = best;
-    s_bi[threadIdx.x] = bi;
-    s_bj[threadIdx.x] = bj;
+    s_best[tid] = best;
+    s_bi[tid] = bi;
+    s_bj[tid] = bj;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        for (uint32_t k = 1; k < blockDim.x; ++k) {
+    if (tid == 0) {
+        for (uint32_t k = 1; k < SWB_ALIGN_NT; ++k) {
             const int v = s_best[k];
             if (v > best || (v == best && v > 0 && (s_bi[k] < bi || (s_bi[k] == bi && s_bj[k] < bj)))) {
                 best = v; bi = s_bi[k]; bj = s_bj[k];
             }
         }
+        uint8_t *ops = out_ops + jb.ops_off;
         uint32_t i = bi, j = bj, nops = 0;
         bool overflow = false;
         while (best > 0 && i > 0 && j > 0) {  // row 0 / column 0 are the H == 0 border (never written)
-            const uint8_t t = dir[(size_t)i * W + j];
+            const uint32_t t = ((uint32_t)dir[(size_t)i * Wb + (j >> 2)] >> (2u * (j & 3u))) & 3u;
             if (t == 0) break;
-            if (nops < cap) out_ops[nops] = t; else overflow = true;
+            if (nops < jb.cap) ops[nops] = (uint8_t)t; else overflow = true;
             ++nops;
             if (t == 1) --j;
             else if (t == 2) --i;
             else { --i; --j; }
         }
-        out_hdr[0] = best;
-        out_hdr[1] = (int32_t)bi;
-        out_hdr[2] = (int32_t)bj;
-        out_hdr[3] = (int32_t)nops;
-        out_hdr[4] = overflow ? 1 : 0;
+        int32_t *hdr = out_hdr + 5 * (size_t)blockIdx.x;
+        hdr[0] = best;
+        hdr[1] = (int32_t)bi;
+        hdr[2] = (int32_t)bj;
+        hdr[3] = (int32_t)nops;
+        hdr[4] = overflow ? 1 : 0;
     }
 }
 
-cudaError_t swb_launch_align(const uint8_t *q, uint32_t m, const uint8_t *d, uint32_t n, const int8_t *mat, int gap,
-                             int32_t *hdiag, uint8_t *dir, int32_t *out_hdr, uint8_t *out_ops, uint32_t cap,
-                             cudaStream_t st)
+cudaError_t swb_launch_align_batch(const SwbAlignJob *jobs, uint32_t njobs, const uint8_t *qbuf, const uint8_t *raw,
+                                   const int8_t *mat, int gap, int32_t *hd_glob, uint8_t *dir, int32_t *out_hdr,
+                                   uint8_t *out_ops, uint32_t smem_ints, cudaStream_t st)
 {
-    swb_align_kernel<<<1, 512, 0, st>>>(q, m, d, n, mat, gap, hdiag, dir, out_hdr, out_ops, cap);
+    if (njobs == 0) return cudaSuccess;
+    const size_t smem = (size_t)smem_ints * sizeof(int32_t);
+    static std::atomic<int> done[64];  // the limit is per-device state shared by all engines: set once (see allow_max_smem)
+    int dev = 0;
+    cudaError_t ce = cudaGetDevice(&dev);
+    if (ce != cudaSuccess) return ce;
+    if (dev >= 64 || !done[dev].load(std::memory_order_acquire)) {
+        ce = cudaFuncSetAttribute(swb_align_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)SWB_ALIGN_SMEM_MAX);
+        if (ce != cudaSuccess) return ce;
+        if (dev < 64) done[dev].store(1, std::memory_order_release);
+    }
+    swb_align_batch_kernel<<<njobs, SWB_ALIGN_NT, smem, st>>>(jobs, qbuf, raw, mat, gap, hd_glob, dir, out_hdr, out_ops,
+                                                             smem_ints);
     return cudaGetLastError();
 }

@@ -44,8 +44,11 @@ int swb_sort_by_length(const uint64_t *offsets, uint32_t n, std::vector<uint32_t
     return 0;
 }
 
-int swb_build_plan(const uint64_t *offsets, uint32_t n, uint32_t shard, uint32_t nshards, const SwbPlanOpts &o,
-                   SwbPlan &plan, const uint32_t *sorted_order)
+// Head of the plan: which sequences the shard owns, in sorted order, with their lengths and offsets in the caller's
+// buffer. That is all a sharded load needs to start gathering and uploading residues; the tail (output order, tiles)
+// can be built beside the upload.
+int swb_build_plan_head(const uint64_t *offsets, uint32_t n, uint32_t shard, uint32_t nshards, SwbPlan &plan,
+                        const uint32_t *sorted_order)
 {
     if (nshards == 0 || shard >= nshards) return -1;
     plan = SwbPlan();
@@ -69,12 +72,42 @@ int swb_build_plan(const uint64_t *offsets, uint32_t n, uint32_t shard, uint32_t
 
     // residue-balanced sharding: deal PAIRS of the length-sorted list round-robin, so every shard gets the
     // same length mix and its residue total differs from the others by at most one pair per round
-    plan.sorted_ids.reserve(n / nshards + 2);
-    for (uint32_t s = 0; s < n; ++s)
-        if ((s >> 1) % nshards == shard) plan.sorted_ids.push_back(order[s]);
+    if (nshards == 1) {
+        plan.sorted_ids.assign(order, order + n);
+    } else {
+        plan.sorted_ids.reserve(n / nshards + 2);
+        for (uint32_t p = shard; 2 * (uint64_t)p < n; p += nshards) {
+            plan.sorted_ids.push_back(order[2 * (size_t)p]);
+            if (2 * (uint64_t)p + 1 < n) plan.sorted_ids.push_back(order[2 * (size_t)p + 1]);
+        }
+    }
     plan.n_local = (uint32_t)plan.sorted_ids.size();
     const uint32_t nl = plan.n_local;
+    plan.seq_off.resize(nl);
+    plan.seq_len.resize(nl);
+    for (uint32_t s = 0; s < nl; ++s) {
+        plan.seq_off[s] = offsets[plan.sorted_ids[s]];
+        plan.seq_len[s] = len[plan.sorted_ids[s]];
+        plan.residues_local += plan.seq_len[s];
+    }
+    plan.max_len = nl ? plan.seq_len[0] : 0;
+    return 0;
+}
 
+int swb_build_plan(const uint64_t *offsets, uint32_t n, uint32_t shard, uint32_t nshards, const SwbPlanOpts &o,
+                   SwbPlan &plan, const uint32_t *sorted_order)
+{
+    const int rc = swb_build_plan_head(offsets, n, shard, nshards, plan, sorted_order);
+    if (rc != 0) return rc;
+    swb_build_plan_tail(o, plan);
+    return 0;
+}
+
+// Tail of the plan: output order and tiles. Reads only what the head left in `plan` (not seq_off, which a sharded load
+// rewrites to offsets in the gathered stream while this runs on a helper thread).
+void swb_build_plan_tail(const SwbPlanOpts &o, SwbPlan &plan)
+{
+    const uint32_t n = plan.n_total, nl = plan.n_local, nshards = plan.nshards;
     // output order = ascending DB id; rank_of[id] = position of id among the shard's ids (O(n), no sort)
     plan.shard_ids.resize(nl);
     plan.out_pos.resize(nl);
@@ -96,14 +129,6 @@ int swb_build_plan(const uint64_t *offsets, uint32_t n, uint32_t shard, uint32_t
     }
     plan.sorted_of_out.resize(nl);
     for (uint32_t s = 0; s < nl; ++s) plan.sorted_of_out[plan.out_pos[s]] = s;
-    plan.seq_off.resize(nl);
-    plan.seq_len.resize(nl);
-    for (uint32_t s = 0; s < nl; ++s) {
-        plan.seq_off[s] = offsets[plan.sorted_ids[s]];
-        plan.seq_len[s] = len[plan.sorted_ids[s]];
-        plan.residues_local += plan.seq_len[s];
-    }
-    plan.max_len = nl ? plan.seq_len[0] : 0;
 
     // tiles: consecutive pairs of the sorted list; the group size follows the tile's longest sequence
     const uint32_t npairs_total = (nl + 1) / 2;
@@ -156,7 +181,6 @@ int swb_build_plan(const uint64_t *offsets, uint32_t n, uint32_t shard, uint32_t
     }
     plan.res_bytes = res;
     plan.bnd_elems = bnd;
-    return 0;
 }
 
 void swb_plan_query(uint32_t qlen, int k_force, int k_max, uint32_t logg_present, uint32_t chunk_rows,

@@ -41,6 +41,11 @@ struct SwbPlan {
 // length as swb_sort_by_length returns them (several shards of one database share one sort), or NULL to sort here.
 int swb_build_plan(const uint64_t *offsets, uint32_t n, uint32_t shard, uint32_t nshards, const SwbPlanOpts &o,
                    SwbPlan &plan, const uint32_t *sorted_order = nullptr);
+// The same in two steps, for a sharded load that uploads while the tail is built: the head leaves sorted_ids, seq_len,
+// seq_off, residues_local / _total and max_len; the tail adds the output order and the tiles.
+int swb_build_plan_head(const uint64_t *offsets, uint32_t n, uint32_t shard, uint32_t nshards, SwbPlan &plan,
+                        const uint32_t *sorted_order = nullptr);
+void swb_build_plan_tail(const SwbPlanOpts &o, SwbPlan &plan);
 // ids 0..n-1 by descending length, ties in id order (stable); -1 on decreasing offsets / a length above 2^31-16
 int swb_sort_by_length(const uint64_t *offsets, uint32_t n, std::vector<uint32_t> &order);
 

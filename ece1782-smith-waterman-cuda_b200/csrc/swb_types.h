@@ -66,6 +66,18 @@ struct SwbScoreParams {
     void *blog;
 };
 
+// one traceback alignment of swb_align_batch (one block of swb_align_batch_kernel)
+struct SwbAlignJob {
+    uint64_t q_off;    // query codes, byte offset into the uploaded query buffer
+    uint64_t d_off;    // subject codes, byte offset into the raw residue buffer of the shard
+    uint64_t dir_off;  // byte offset of the job's direction matrix
+    uint64_t ops_off;  // byte offset of the job's ops in the output
+    uint64_t hd_off;   // int offset of the job's H diagonals in the global scratch (only when they do not fit shared memory)
+    uint32_t m, n;     // query rows, subject columns
+    uint32_t cap;      // ops capacity
+    uint32_t reserved;
+};
+
 // base log (V16R): element offset (uint2) of a tile's region, 2 * (((width * slots) >> 6) + 33) elements long
 SWB_HD size_t swb_blog_offset(uint64_t bnd_off, uint32_t tile_idx) { return 2u * ((size_t)(bnd_off >> 6) + 34u * (size_t)tile_idx); }
 SWB_HD size_t swb_blog_elems(uint64_t bnd_elems, uint32_t ntiles) { return 2u * ((size_t)(bnd_elems >> 6) + 34u * (size_t)ntiles) + 68u; }

@@ -144,6 +144,13 @@ int swb_stats(const swb_engine *e, swb_stats_t *out);
  * 2 = gap in the subject (FROM_TOP), 3 = aligned pair (FROM_TOP_LEFT). cap >= qlen + subject length always suffices. */
 int swb_align(swb_engine *e, const uint8_t *query, uint32_t qlen, uint32_t db_id, int32_t *score, uint32_t *end_i,
               uint32_t *end_j, uint8_t *ops, uint32_t cap, uint32_t *nops);
+/* The same for a list of hits in ONE launch (one thread block per hit; e.g. the top-k lists of a batch): hit h aligns query
+ * hit_query[h] of the batch (qcodes / qoffsets as in swb_search_batch) with database sequence hit_db_id[h] of this shard.
+ * ops of hit h go to ops[ops_offsets[h] .. ops_offsets[h+1]) (nhits + 1 offsets; room of qlen + subject length always
+ * suffices); ops may be NULL (scores and end cells only). end_i, end_j, nops may be NULL. */
+int swb_align_batch(swb_engine *e, const uint8_t *qcodes, const uint64_t *qoffsets, uint32_t nq, const uint32_t *hit_query,
+                    const uint32_t *hit_db_id, uint32_t nhits, int32_t *scores, uint32_t *end_i, uint32_t *end_j,
+                    uint8_t *ops, const uint64_t *ops_offsets, uint32_t *nops);
 
 /* ---- engine group: every GPU of the box in one process (the reference is one process, main.cpp:52-56) --- */
 /* One engine, one host worker thread and one stream set per device. The devices form P database parts x R query groups

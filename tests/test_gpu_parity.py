@@ -361,6 +361,74 @@ def test_traceback_alignment_matches_cpu_cpp_and_oracle(swb, oracle, subset, que
         e.close()
 
 
+def test_published_textbook_vector_on_gpu(swb):
+    """Durbin et al. 1998, fig. 2.6: HEAGAWGHEE x PAWHEAE under BLOSUM50 with gap 8 -> 28, AWGHE / AW-HE -- through the scan,
+    the traceback and the affine kernels with open == extend == 8 (an external known answer, see tests/test_oracle.py)"""
+    e = swb.Engine(0)
+    try:
+        m = swb.scoring_matrix(swb.SWB_SCORING_BLOSUM50_REF)[0]
+        q, d = swb.encode("HEAGAWGHEE"), swb.encode("PAWHEAE")
+        c, o = swb.pack_sequences([d, q, d])
+        e.set_scoring(m, 8)
+        e.db_load(c, o)
+        assert e.search(q).tolist()[0::2] == [28, 28]
+        score, ei, ej, ops = e.align(q, 0, len(d))
+        assert score == 28 and swb.render_alignment("HEAGAWGHEE", "PAWHEAE", ei, ej, ops) == ("AWGHE", "AW-HE")
+        e.set_scoring_affine(m, 8, 8)
+        e.db_load(c, o)
+        assert e.search(q).tolist()[0::2] == [28, 28]
+        e.set_scoring_affine(m, 12, 2)  # the same alignment with a one-residue gap at 12: 5 + 15 - 12 + 10 + 6
+        e.db_load(c, o)
+        assert e.search(q)[0] == 24
+    finally:
+        e.close()
+
+
+def test_align_batch_matches_single_calls_and_oracle(swb, oracle, subset, queries):
+    """swb_align_batch: the hit lists of several queries in ONE launch (one block per hit, H diagonals in shared memory,
+    2-bit directions) == swb_align hit by hit == the oracle's restatement of cpu.cpp:39-103; empty hits, repeated hits
+    and a 20,000-row query whose diagonals live in global scratch included"""
+    e = swb.Engine(0)
+    try:
+        e.db_load(subset["codes"], subset["offsets"])
+        names = ("P02232", "P01008", "P27895", "Q9UKN1")
+        qs = [swb.encode(queries[nm]) for nm in names]
+        ids, top = e.search_batch_topk(*swb.pack_sequences(qs), 6)
+        hits = [(qi, int(sid)) for qi in range(len(qs)) for sid in ids[qi]]
+        hits += [hits[3], (0, 110), (1, 0)]
+        lens = [len(subset["seqs"][sid]) for _, sid in hits]
+        got = e.align_batch(qs, hits, lens)
+        assert len(got) == len(hits)
+        for (qi, sid), (score, ei, ej, ops) in zip(hits, got):
+            subj = subset["seqs"][sid]
+            one = e.align(qs[qi], sid, len(subj))
+            assert (score, ei, ej) == one[:3] and np.array_equal(ops, one[3])
+            want = oracle.align(queries[names[qi]], subj, "blosum50")
+            assert score == want[0] and (ei, ej) == want[3]
+            assert swb.render_alignment(queries[names[qi]], subj, ei, ej, ops) == (want[1], want[2])
+        for qi in range(len(qs)):
+            assert [g[0] for g in got[6 * qi:6 * qi + 6]] == [int(v) for v in top[qi]]
+        # empty list, empty query
+        assert e.align_batch(qs, [], []) == []
+        z = e.align_batch([np.zeros(0, np.uint8), qs[0]], [(0, 5), (1, 5)], [len(subset["seqs"][5])] * 2)
+        assert z[0][0] == 0 and len(z[0][3]) == 0 and z[1][0] == e.align(qs[0], 5, len(subset["seqs"][5]))[0]
+        # a query beyond the shared-memory limit of the diagonals (3 * (m + 2) ints > 216 KB)
+        rng = np.random.default_rng(7)
+        subj = subset["seqs"][56]
+        letters = np.frombuffer(b"ARNDCQEGHILKMFPSTWYV", dtype=np.uint8)
+        long_txt = bytes(letters[rng.integers(0, 20, 20000)]).decode()
+        long_txt = long_txt[:9000] + subj[100:700] + long_txt[9600:]
+        lq = swb.encode(long_txt)
+        (score, ei, ej, ops), = e.align_batch([lq], [(0, 56)], [len(subj)])
+        want = oracle.align(long_txt, subj, "blosum50")
+        assert score == want[0] and (ei, ej) == want[3]
+        assert swb.render_alignment(long_txt, subj, ei, ej, ops) == (want[1], want[2])
+        with pytest.raises(swb.SwbError):
+            e.align_batch(qs, [(9, 0)], [10])
+    finally:
+        e.close()
+
+
 def test_pipelined_passes_option(swb, oracle):
     """option split=1: 32-lane tiles wider than xl_len hand out their passes as pipelined work items (progress
     counters in global memory, atomicMax merge); same scores, including a chunked query and an s16 overflow"""

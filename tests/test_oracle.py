@@ -111,3 +111,33 @@ def test_affine_restatement_against_independent_gotoh(oracle):
     c, o = pack_db([d])
     assert oracle.scan_affine(a, c, o, m, 3, 1)[0] == 16
     assert oracle.scan_affine(a, c, o, m, 12, 1)[0] == 10
+
+
+def test_published_textbook_vector_blosum50_gap8(oracle):
+    """An externally published known answer for the linear recurrence under BLOSUM50: Durbin, Eddy, Krogh & Mitchison,
+    'Biological sequence analysis' (1998), fig. 2.6 -- HEAGAWGHEE against PAWHEAE with gap penalty d = 8 has the best
+    local alignment AWGHE / AW-HE with score 28. Same matrix as the reference (SWSolver.cu:54-81), another gap than its
+    g = 2, so it pins the gap handling of the restatement independently of the reference's goldens. The affine
+    restatement with open == extend == 8 must give the same 28."""
+    m = oracle.matrix("blosum50")
+    s, a, b, end = oracle.align("HEAGAWGHEE", "PAWHEAE", "blosum50", gap=8)
+    assert (s, a, b) == (28, "AWGHE", "AW-HE") and end == (9, 5)
+    q, d = oracle.encode("HEAGAWGHEE"), oracle.encode("PAWHEAE")
+    assert oracle.score(q, d, m, gap=8) == 28
+    codes, offs = pack_db([d])
+    assert oracle.scan_affine(q, codes, offs, m, 8, 8)[0] == 28
+
+
+def test_affine_is_sandwiched_by_the_pinned_linear_oracle(oracle, subset, queries):
+    """No affine vectors exist in the reference ("parity unpinned"), but two facts tie the Gotoh restatement to the pinned
+    linear one: open == extend IS the linear recurrence, and a gap of length L costs between L * extend and L * open, so
+    linear(open) <= affine(open, extend) <= linear(extend) for every pair."""
+    m = oracle.matrix("blosum50")
+    codes, offs = pack_db([oracle.encode(s) for s in subset["seqs"][:40]])
+    for name in ("P02232", "P01008"):
+        q = oracle.encode(queries[name])
+        lin2 = oracle.scan(q, codes, offs, m)  # the reference's gap 2, pinned by its goldens
+        assert np.array_equal(oracle.scan_affine(q, codes, offs, m, 2, 2), lin2)
+        lin10 = oracle.scan_affine(q, codes, offs, m, 10, 10)
+        aff = oracle.scan_affine(q, codes, offs, m, 10, 2)
+        assert (lin10 <= aff).all() and (aff <= lin2).all() and (lin10 < lin2).any()

@@ -59,6 +59,8 @@ struct Slot {
     size_t bnd32_cap = 0;
     void *d_blog = nullptr;  // V16R: base log of the boundary rows
     size_t blog_cap = 0;
+    void *d_colstate = nullptr;  // one-lane tiles: parked row state per resident warp (swb_run_tile)
+    size_t colstate_cap = 0;
     int32_t *h_scores = nullptr;  // pinned, n_local
     size_t h_scores_cap = 0;
     int32_t *pending_dst = nullptr;   // caller memory the scores of the job in flight go to (finish_slot)
@@ -170,6 +172,9 @@ static void free_slot_db(Slot &s)
     if (s.d_bnd32) cudaFree(s.d_bnd32);
     if (s.d_blog) cudaFree(s.d_blog);
     s.d_blog = nullptr;
+    if (s.d_colstate) cudaFree(s.d_colstate);
+    s.d_colstate = nullptr;
+    s.colstate_cap = 0;
     s.blog_cap = 0;
     if (s.d_prog) cudaFree(s.d_prog);
     s.d_prog = nullptr;
@@ -777,6 +782,15 @@ static int enqueue_pass(swb_engine *e, Slot &s, int mode, SwbScoreParams &p, con
             p.first_chunk = ch.first;
             p.last_chunk = ch.last;
             p.counter = s.d_counters + counter++;
+            if (!g.split && (g.logg_mask & 1u)) {
+                // One-lane tiles park the row state of a pass group between column blocks: one region per warp of the
+                // launch. The one-lane tiles of a pass sit in exactly one launch group and the passes of a query follow
+                // each other in stream order, so one buffer per slot serves them all.
+                const size_t elem = gmode == SWB_MODE_I32A ? 16u : (gmode == SWB_MODE_I32 || gmode == SWB_MODE_S16A ? 8u : 4u);
+                const size_t warps = (size_t)ls.grid * (size_t)((ls.block_cfg == SWB_BLOCK_SMALL ? SWB_NT_SMALL : SWB_NT_LARGE) / 32);
+                CU(GROW_DEV(s.d_colstate, s.colstate_cap, warps * swb_colstate_elems(g.K) * elem));
+                p.colstate = s.d_colstate;
+            }
             CU(swb_launch_score(g.K, gmode, g.split, ls.block_cfg, p, ls.grid, ls.smem, st));
             }
         p.recount = recount;

@@ -7,6 +7,8 @@
 // ---------------------------------------------------------------------------------------------
 struct DevBackend {
     __device__ __forceinline__ int lane() const { return (int)(threadIdx.x & 31u); }
+    // index of this warp among the warps of the launch (its colstate region)
+    __device__ __forceinline__ uint32_t warp_slot() const { return blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); }
     __device__ __forceinline__ uint32_t shfl_up(uint32_t v, int d, int w) const
     {
         return __shfl_up_sync(0xffffffffu, v, (unsigned)d, w);

@@ -64,7 +64,15 @@ struct SwbScoreParams {
     // (pass parity, slot, block), see swb_blog_offset
     uint32_t rebase_shift;
     void *blog;
+    // one-lane-per-pair tiles: per resident warp, the row state of the passes of a group between two column blocks
+    // (swb_run_tile); swb_colstate_elems(K) elements of the policy's type per warp slot
+    void *colstate;
 };
+
+#ifndef SWB_PASS_GROUP
+#define SWB_PASS_GROUP 4u  // one-lane tiles: passes that walk over the column blocks together
+#endif
+SWB_HD size_t swb_colstate_elems(int K) { return (size_t)SWB_PASS_GROUP * (size_t)(K + 4) * 32u; }
 
 // one traceback alignment of swb_align_batch (one block of swb_align_batch_kernel)
 struct SwbAlignJob {

@@ -42,6 +42,9 @@
 #ifndef SWB_PF_CHUNKS
 #define SWB_PF_CHUNKS 6u  // chunks (of 4 columns) that the L2 prefetch of the one-lane tiles runs ahead
 #endif
+#ifndef SWB_BLOCK_CHUNKS
+#define SWB_BLOCK_CHUNKS 16u  // one-lane tiles: chunks per column block that the passes of a group share (see swb_run_tile)
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // byte permute with sign replication (PTX prmt.b32 generic mode: selector nibble bit 3 = replicate
@@ -589,6 +592,107 @@ SWB_HD void swb_run_tile(BE &be, const SwbScoreParams &p, const SwbTile &tile, u
     const uint32_t pass0 = V::rebased ? p.row0 / rows_per_super : 0u;  // passes of the query chunks before this launch
 
     const uint32_t ss_end = ss_count < nsuper - ss_begin ? ss_begin + ss_count : nsuper;
+    if constexpr (!GROUPED) {
+        // One lane per pair: no exchange between lanes. Residue codes of a chunk (4 columns x two sequences) come as byte
+        // loads: zero-extended in registers, no ALU-pipe instruction is spent on unpacking them.
+        //
+        // Order of the work: the obvious order -- pass after pass (K rows each) over the whole width -- streams the tile's
+        // residues and its boundary row (bottom row of one pass = top row of the next, 4 B per pair-column) through
+        // memory once per PASS, and with ~2,400 resident warps those streams are far larger than the L2: ncu showed
+        // 140 GB of DRAM traffic for one 5,478-row query against 0.2 GB of residues, and the first use of a loaded
+        // residue code as the top stall of the kernel. So the work is blocked twice: SWB_PASS_GROUP consecutive passes
+        // walk TOGETHER over column blocks of SWB_BLOCK_CHUNKS chunks -- block 0 by every pass of the group, then block
+        // 1, ... Inside a block the boundary row and the residues are reused from L1/L2 by the next pass a few
+        // microseconds later; what a pass needs to continue in the next block (its K row values and the diagonal
+        // element) is parked in a small per-warp scratch (colstate) meanwhile. Only the bottom row of a whole GROUP still
+        // goes through memory: 1 / SWB_PASS_GROUP of the traffic.
+        T *const cstate = reinterpret_cast<T *>(p.colstate) + (size_t)be.warp_slot() * swb_colstate_elems(K);
+        const size_t cs_pass = (size_t)(K + 4) * 32u;  // elements of T per parked pass: [K/4 + 1][lane][4]
+        for (uint32_t pg0 = ss_begin; pg0 < ss_end; pg0 += SWB_PASS_GROUP) {
+            const uint32_t pg1 = pg0 + SWB_PASS_GROUP < ss_end ? pg0 + SWB_PASS_GROUP : ss_end;
+            const uint32_t cbc = pg1 - pg0 > 1u ? SWB_BLOCK_CHUNKS : nchunks;  // a lone pass runs straight through
+            for (uint32_t cb0 = 0; cb0 < nchunks; cb0 += cbc) {
+                const uint32_t cb1 = cb0 + cbc < nchunks ? cb0 + cbc : nchunks;
+                for (uint32_t ss = pg0; ss < pg1; ++ss) {
+                    const int8_t *prow = sprof + (size_t)((ss - smem_ss0) * (uint32_t)K);
+                    const bool read_top = !(p.first_chunk && ss == 0);
+                    const bool write_bot = !(p.last_chunk && ss + 1 == nsuper);
+                    T *const park = cstate + (size_t)(ss - pg0) * cs_pass + (size_t)lane * 4u;
+                    T left[K];
+                    T diag0;
+                    if (cb0 == 0) {
+#pragma unroll
+                        for (int k = 0; k < K; ++k) left[k] = LZERO;
+                        diag0 = LZERO;
+                    } else {
+#pragma unroll
+                        for (int k4 = 0; k4 < K / 4; ++k4) V::ld4(be, park + (size_t)k4 * 128u, &left[4 * k4]);
+                        T d4[4];
+                        V::ld4(be, park + (size_t)(K / 4) * 128u, d4);
+                        diag0 = d4[0];
+                    }
+                    uint32_t ca[4], cb[4];
+                    T bc[4];
+                    {
+                        const uint8_t *r0 = res + (size_t)cb0 * res_stride;
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            ca[u] = be.ld_code(r0 + 2 * u);
+                            cb[u] = be.ld_code(r0 + 2 * u + 1);
+                            bc[u] = V::hzero(cst);
+                        }
+                        if (read_top) V::ld4(be, bnd + ((size_t)cb0 * 32u + lane) * 4u, bc);
+                    }
+                    for (uint32_t c = cb0; c < cb1; ++c) {
+                        // prefetch the next chunk of residues and of the top boundary row
+                        uint32_t na[4], nb[4];
+                        T bn[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            na[u] = SWB_PAD;
+                            nb[u] = SWB_PAD;
+                            bn[u] = V::hzero(cst);
+                        }
+                        if (c + 1 < cb1) {
+                            const uint8_t *rnext = res + (size_t)(c + 1) * res_stride;
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                na[u] = be.ld_code(rnext + 2 * u);
+                                nb[u] = be.ld_code(rnext + 2 * u + 1);
+                            }
+                            if (read_top) V::ld4(be, bnd + ((size_t)(c + 1) * 32u + lane) * 4u, bn);
+                        }
+                        // The loads above run one chunk ahead, which covers a cache hit but not a trip to HBM: the first
+                        // pass of a group meets residues and a boundary row that nobody touched recently. Pull the
+                        // lines of the chunk SWB_PF_CHUNKS ahead into L2 now; no register is tied up.
+                        if (ss == pg0 && c + SWB_PF_CHUNKS < nchunks) {
+                            be.prefetch_l2(res + (size_t)(c + SWB_PF_CHUNKS) * res_stride);
+                            if (read_top) be.prefetch_l2(bnd + ((size_t)(c + SWB_PF_CHUNKS) * 32u + lane) * 4u);
+                        }
+                        T outb[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            outb[u] = V::template column<K, 4>(bc[u], diag0, left, best, cst, ca[u], cb[u], prow, sstride);
+                        if (write_bot) V::st4(be, bnd + ((size_t)c * 32u + lane) * 4u, outb);
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            ca[u] = na[u];
+                            cb[u] = nb[u];
+                            bc[u] = bn[u];
+                        }
+                    }
+                    if (cb1 < nchunks) {
+#pragma unroll
+                        for (int k4 = 0; k4 < K / 4; ++k4) V::st4(be, park + (size_t)k4 * 128u, &left[4 * k4]);
+                        T d4[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) d4[u] = diag0;
+                        V::st4(be, park + (size_t)(K / 4) * 128u, d4);
+                    }
+                }
+            }
+        }
+    } else {
     for (uint32_t ss = ss_begin; ss < ss_end; ++ss) {
         // smem_ss0: the pass whose first row sits at row 0 of the staged profile (0 except in SPLIT launches)
         const int8_t *prow = sprof + (size_t)((((ss - smem_ss0) << logG) + (uint32_t)g) * (uint32_t)K);
@@ -610,55 +714,7 @@ SWB_HD void swb_run_tile(BE &be, const SwbScoreParams &p, const SwbTile &tile, u
             avail = be.wait_progress(prog + ss - 1, need, W);
         }
 
-        if constexpr (!GROUPED) {
-            // One lane per pair: no exchange between lanes. Residue codes of a chunk (4 columns x two sequences) come
-            // as byte loads: zero-extended in registers, no ALU-pipe instruction is spent on unpacking them.
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                ca[u] = nchunks > 0 ? be.ld_code(res + 2 * u) : (uint32_t)SWB_PAD;
-                cb[u] = nchunks > 0 ? be.ld_code(res + 2 * u + 1) : (uint32_t)SWB_PAD;
-            }
-            if (nchunks > 0 && read_top) V::ld4(be, bnd + (size_t)lane * 4u, bc);
-            for (uint32_t c = 0; c < nchunks; ++c) {
-                // prefetch the next chunk of residues and of the top boundary row
-                uint32_t na[4], nb[4];
-                T bn[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    na[u] = SWB_PAD;
-                    nb[u] = SWB_PAD;
-                    bn[u] = V::hzero(cst);
-                }
-                if (c + 1 < nchunks) {
-                    const uint8_t *rnext = res + (size_t)(c + 1) * res_stride;
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        na[u] = be.ld_code(rnext + 2 * u);
-                        nb[u] = be.ld_code(rnext + 2 * u + 1);
-                    }
-                    if (read_top) V::ld4(be, bnd + ((size_t)(c + 1) * 32u + lane) * 4u, bn);
-                }
-                // The loads above run one chunk ahead, which covers an L2 hit but not a trip to HBM -- and with wide
-                // tiles the residues and boundary rows of all resident warps exceed the L2, so they do come from HBM
-                // (ncu: the first use of a residue code was the top stall of the kernel). Pull the lines of the chunk
-                // SWB_PF_CHUNKS ahead into L2 now; no register is tied up.
-                if (c + SWB_PF_CHUNKS < nchunks) {
-                    be.prefetch_l2(res + (size_t)(c + SWB_PF_CHUNKS) * res_stride);
-                    if (read_top) be.prefetch_l2(bnd + ((size_t)(c + SWB_PF_CHUNKS) * 32u + lane) * 4u);
-                }
-                T outb[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    outb[u] = V::template column<K, 4>(bc[u], diag0, left, best, cst, ca[u], cb[u], prow, sstride);
-                if (write_bot) V::st4(be, bnd + ((size_t)c * 32u + lane) * 4u, outb);
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    ca[u] = na[u];
-                    cb[u] = nb[u];
-                    bc[u] = bn[u];
-                }
-            }
-        } else if constexpr (!SPLIT) {
+        if constexpr (!SPLIT) {
             // Lane-group wavefront, one COLUMN of lag per lane: at column step t lane g works on column t - g and hands
             // its bottom H and the residue pair to lane g + 1 with shuffles; the first lane of a group fetches the
             // residue codes and the top boundary row, the last lane stores the bottom row (scalars: its columns lag
@@ -874,6 +930,7 @@ SWB_HD void swb_run_tile(BE &be, const SwbScoreParams &p, const SwbTile &tile, u
             V::set_base(cst, 0, 0);
         }
         be.syncwarp();
+    }
     }
 
     if constexpr (V::rebased) {

@@ -22,6 +22,7 @@ struct HostBackend {
     WarpSim *w;
     int lane_id;
     int lane() const { return lane_id; }
+    uint32_t warp_slot() const { return 0; }  // one warp at a time
     uint32_t shfl_up(uint32_t v, int d, int width);
     uint32_t shfl_xor(uint32_t v, int m, int width);
     void syncwarp();
@@ -342,6 +343,8 @@ extern "C" int swbemu_search(const uint8_t *codes, const uint64_t *offsets, uint
     p.ovf_thr = ovf_thr_override >= 0 ? ovf_thr_override : 32767 - max_s;
     p.rebase_shift = (uint32_t)rebase_shift;
     p.blog = blog.data();
+    std::vector<uint64_t> colstate(swb_colstate_elems(32) * 2 + 8, 0x7f7f7f7f7f7f7f7full);  // up to 16 B per element
+    p.colstate = colstate.data();
     p.scores = sorted.data();
 
     // the split set and its direct part, as enqueue_job

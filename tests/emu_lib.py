@@ -15,26 +15,28 @@ _ARGS = [_u8p, _u64p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.
          ctypes.c_int, _u8p, ctypes.c_uint32, ctypes.c_int, ctypes.c_int, ctypes.c_uint32, ctypes.c_int,
          ctypes.c_uint32, ctypes.c_int, ctypes.c_int, ctypes.c_uint32, ctypes.c_int, _i32p,
          ctypes.POINTER(ctypes.c_uint32)]
-_lib = None
+_libs = {}
 
 
-def load():
-    global _lib
-    if _lib is None:
-        so = os.path.join(ROOT, PKG, "lib", "libswbemu.so")
+def load(variant=""):
+    """variant "": the warp program as the product compiles it; "_blk": the same source with tiny column blocks and pass
+    groups of three (-DSWB_BLOCK_CHUNKS=3 -DSWB_PASS_GROUP=3), so that small test inputs cross many block and group borders"""
+    if variant not in _libs:
+        so = os.path.join(ROOT, PKG, "lib", "libswbemu%s.so" % variant)
         if not os.path.exists(so):
             subprocess.run(["make", "-C", os.path.join(ROOT, PKG), "emu"], check=True, capture_output=True)
-        _lib = ctypes.CDLL(so)
-        _lib.swbemu_search.restype = ctypes.c_int
-        _lib.swbemu_search.argtypes = _ARGS
-    return _lib
+        lib = ctypes.CDLL(so)
+        lib.swbemu_search.restype = ctypes.c_int
+        lib.swbemu_search.argtypes = _ARGS
+        _libs[variant] = lib
+    return _libs[variant]
 
 
 def search(codes, offs, m, q, K=32, group_len=384, force_i32=0, chunk_rows=0, thr=-1, gap=2, gap_extend=None,
-           shard=0, nshards=1, n_out=None, xl_len=8192, split_k=0, exact_i32=0, direct_len=0, rebase_shift=0):
+           shard=0, nshards=1, n_out=None, xl_len=8192, split_k=0, exact_i32=0, direct_len=0, rebase_shift=0, variant=""):
     """One query through the emulated engine flow; returns (scores of the shard, recomputed tiles).
     force_i32: 1 = the exact pass alone over every tile (V16R, or V32 with exact_i32=1)."""
-    L = load()
+    L = load(variant)
     codes = np.ascontiguousarray(codes, dtype=np.uint8)
     if len(codes) == 0:
         codes = np.zeros(1, dtype=np.uint8)

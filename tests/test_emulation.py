@@ -334,3 +334,43 @@ def test_randomized_configurations(emu, oracle):
         got, _ = emu(codes, offs, m, q, K=K, group_len=gl, xl_len=xl, thr=thr, split_k=sk, exact_i32=ex, direct_len=dl,
                      rebase_shift=6)
         assert np.array_equal(got, want), (it, nseq, top, len(q), gl, K, xl, thr, sk, ex, dl)
+
+
+@pytest.mark.parametrize("variant", ["", "_blk"])
+def test_one_lane_tiles_in_column_blocks_and_pass_groups(oracle, subset, queries, variant):
+    """One-lane-per-pair tiles run SWB_PASS_GROUP passes together over column blocks of SWB_BLOCK_CHUNKS chunks, parking
+    their row state between blocks (swb_run_tile). Checked with the product's parameters (4 passes x 16 chunks) and with
+    a build of the same source that uses 3 x 3, so that every border case occurs on small inputs: widths below, at and
+    above a block, pass counts that are not a multiple of the group, query chunks, the int32 / affine policies (their
+    parked elements are 8 and 16 bytes), a real s16 overflow re-scored by V32."""
+    import emu_lib
+    emu_lib.load(variant)
+    m = oracle.matrix("blosum50")
+    rng = np.random.default_rng(23)
+    lens = [0, 1, 3, 4, 5, 11, 12, 13, 23, 24, 25, 47, 48, 49, 95, 96, 97, 130, 191, 192, 193, 260, 401, 777]
+    codes, offs = pack_db(random_db(rng, lens))
+    for ql in (1, 31, 32, 33, 96, 97, 130, 257):
+        q = rng.integers(0, 24, ql).astype(np.uint8)
+        want = oracle.scan(q, codes, offs, m)
+        for K in (8, 16, 32):
+            got, _ = emu_lib.search(codes, offs, m, q, K=K, group_len=4096, variant=variant)
+            assert np.array_equal(got, want), (variant, ql, K)
+        got, _ = emu_lib.search(codes, offs, m, q, K=16, group_len=4096, force_i32=1, exact_i32=1, variant=variant)
+        assert np.array_equal(got, want), (variant, ql, "V32")
+        wa = oracle.scan_affine(q, codes, offs, m, 10, 2)
+        got, _ = emu_lib.search(codes, offs, m, q, K=0, group_len=4096, gap=10, gap_extend=2, variant=variant)
+        assert np.array_equal(got, wa), (variant, ql, "V16A")
+        got, _ = emu_lib.search(codes, offs, m, q, K=8, group_len=4096, gap=10, gap_extend=2, force_i32=1, variant=variant)
+        assert np.array_equal(got, wa), (variant, ql, "V32A")
+    # query chunks (the boundary row of a chunk is the top row of the next launch) with one-lane tiles only
+    q = oracle.encode(queries["P04775"])  # 2005 rows -> two chunks of 1024
+    want = oracle.scan(q, subset["codes"], subset["offsets"], m)
+    got, rc = emu_lib.search(subset["codes"], subset["offsets"], m, q, K=32, group_len=4096, chunk_rows=1024, variant=variant)
+    assert np.array_equal(got, want) and rc == 0
+    # a real s16 overflow in a one-lane tile, re-scored by the int32 policy
+    w = np.full(2300, 17, dtype=np.uint8)
+    codes, offs = pack_db([w, rng.integers(0, 20, 300).astype(np.uint8), w[:2200].copy()])
+    want = oracle.scan(w, codes, offs, m)
+    assert want[0] == 34500
+    got, rc = emu_lib.search(codes, offs, m, w, K=0, group_len=4096, exact_i32=1, variant=variant)
+    assert np.array_equal(got, want) and rc >= 1

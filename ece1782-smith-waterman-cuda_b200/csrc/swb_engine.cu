@@ -782,17 +782,18 @@ static int enqueue_pass(swb_engine *e, Slot &s, int mode, SwbScoreParams &p, con
             p.first_chunk = ch.first;
             p.last_chunk = ch.last;
             p.counter = s.d_counters + counter++;
-            if (!g.split && (g.logg_mask & 1u)) {
+            if (!g.split && (g.logg_mask & 1u) && gmode == SWB_MODE_S16) {  // the one blocked policy (V16)
                 // One-lane tiles park the row state of a pass group between column blocks: one region per warp of the
                 // launch. The one-lane tiles of a pass sit in exactly one launch group and the passes of a query follow
                 // each other in stream order, so one buffer per slot serves them all.
-                const size_t elem = gmode == SWB_MODE_I32A ? 16u : (gmode == SWB_MODE_I32 || gmode == SWB_MODE_S16A ? 8u : 4u);
+                const size_t elem = sizeof(uint32_t);
                 const size_t warps = (size_t)ls.grid * (size_t)((ls.block_cfg == SWB_BLOCK_SMALL ? SWB_NT_SMALL : SWB_NT_LARGE) / 32);
                 CU(GROW_DEV(s.d_colstate, s.colstate_cap, warps * swb_colstate_elems(g.K) * elem));
                 p.colstate = s.d_colstate;
             }
             CU(swb_launch_score(g.K, gmode, g.split, ls.block_cfg, p, ls.grid, ls.smem, st));
-            }
+            e->stats.kernel_launches += 1;
+        }
         p.recount = recount;
     }
     for (size_t gi = 1; gi < ng; ++gi) {  // join
@@ -958,7 +959,8 @@ static int enqueue_job(swb_engine *e, Slot &s, uint32_t qi, const uint8_t *q, ui
         if (g1[0].split) {  // pipelined work items combine their scores with atomicMax
             CU(cudaMemsetAsync(s.d_prog, 0, sizeof(uint32_t) * prog_words1, s.stream));
             CU(swb_launch_clear_flagged(e->d_tiles, (uint32_t)pl.tiles.size(), s.d_flags, p.scores, s.stream));
-            }
+            e->stats.kernel_launches += 1;
+        }
         if ((rc = enqueue_pass(e, s, mode1, p, qp1, g1, counter, s.d_prog, nullptr, nullptr)) != SWB_OK) return rc;
     }
     CU(swb_launch_scatter(s.d_sorted, e->d_out_pos, nl, out, s.stream));
@@ -1031,6 +1033,7 @@ static int enqueue_results(swb_engine *e, Slot &s, uint32_t qa, const BatchOut &
         CU(GROW_HOST(s.h_topk, s.h_topk_cap, bytes));
         CU(swb_launch_topk(e->d_out + (size_t)qa * nl, nl, e->plan.nshards > 1 ? e->d_shard_ids : nullptr, bo.k, s.d_topk,
                            reinterpret_cast<int32_t *>(s.d_topk + bo.k), s.stream));
+        e->stats.kernel_launches += 1;
         CU(cudaMemcpyAsync(s.h_topk, s.d_topk, bytes, cudaMemcpyDeviceToHost, s.stream));
         s.pending_ids = bo.ids + (size_t)qa * bo.k;
         s.pending_top = bo.top + (size_t)qa * bo.k;
@@ -1272,7 +1275,7 @@ extern "C" int swb_align_batch(swb_engine *e, const uint8_t *qcodes, const uint6
             dir_bytes += (need + 15u) & ~15ull;
             jb.ops_off = ops_bytes;
             ops_bytes += jb.cap;
-            const uint64_t hd = 3ull * (jb.m + 2);
+            const uint64_t hd = swb_align_hd_ints(jb.m);
             if (hd <= smem_cap_ints) {
                 smem_ints = std::max<uint32_t>(smem_ints, (uint32_t)hd);
             } else {

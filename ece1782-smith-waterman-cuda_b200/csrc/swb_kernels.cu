@@ -472,8 +472,9 @@ cudaError_t swb_launch_topk(const int32_t *scores, uint32_t n, const uint32_t *i
 // One block per hit, all hits of a list in one launch. Anti-diagonal wavefront; the three rolling H diagonals live in
 // shared memory (in global scratch only for queries beyond ~18,000 rows); directions are packed 2 bits per cell,
 // rows of ceil((n + 1) / 4) bytes. A row always belongs to the same thread (row i -> thread (i - 1) mod block), so
-// the four cells of a direction byte are written by one thread on four consecutive diagonals: plain read-modify-write,
-// no atomics, and no clearing pass (the first cell written in a byte overwrites it).
+// the four cells of a direction byte are written by one thread on four consecutive diagonals: it collects them in a byte
+// per row next to the diagonals and stores each finished byte once -- no atomics, no read-modify-write of global
+// memory, no clearing pass.
 __global__ void __launch_bounds__(SWB_ALIGN_NT) swb_align_batch_kernel(const SwbAlignJob *__restrict__ jobs,
                                                                        const uint8_t *__restrict__ qbuf,
                                                                        const uint8_t *__restrict__ raw,
@@ -492,8 +493,9 @@ __global__ void __launch_bounds__(SWB_ALIGN_NT) swb_align_batch_kernel(const Swb
     uint8_t *dir = dirbuf + jb.dir_off;
     const uint32_t Wb = (n + 4u) >> 2;  // bytes per direction row (columns 0 .. n)
     const uint32_t tid = threadIdx.x;
-    int32_t *hd = 3u * (m + 2u) <= smem_ints ? s_hd : hd_glob + jb.hd_off;
+    int32_t *hd = swb_align_hd_ints(m) <= smem_ints ? s_hd : hd_glob + jb.hd_off;
     int32_t *h0 = hd, *h1 = hd + (m + 2), *h2 = hd + 2 * (size_t)(m + 2);
+    uint8_t *cur = reinterpret_cast<uint8_t *>(hd + 3 * (size_t)(m + 2));  // per row: the direction byte being filled
     for (uint32_t i = tid; i < 3 * (m + 2); i += SWB_ALIGN_NT) hd[i] = 0;
     for (uint32_t i = tid; i < SWB_ALPHA * SWB_ALPHA; i += SWB_ALIGN_NT) s_mat[i] = mat[i];
     int best = 0;
@@ -521,10 +523,10 @@ __global__ void __launch_bounds__(SWB_ALIGN_NT) swb_align_batch_kernel(const Swb
             if (up > h) { h = up; t = 2; }
             if (dg > h) { h = dg; t = 3; }
             h2[i] = h;
-            uint8_t *bp = dir + (size_t)i * Wb + (j >> 2);
-            const uint32_t sh = 2u * (j & 3u);
-            const uint32_t old = ((j & 3u) == 0u || j == 1u) ? 0u : (uint32_t)*bp;
-            *bp = (uint8_t)((old & ~(3u << sh)) | (t << sh));
+            // four cells of a row share a direction byte: collected next to the diagonals, stored when complete
+            const uint32_t b = (((j & 3u) == 0u || j == 1u) ? 0u : (uint32_t)cur[i]) | (t << (2u * (j & 3u)));
+            cur[i] = (uint8_t)b;
+            if ((j & 3u) == 3u || j == n) dir[(size_t)i * Wb + (j >> 2)] = (uint8_t)b;
             // first row-major maximum: larger value, else smaller i, else smaller j
             if (h > best || (h == best && h > 0 && (i < bi || (i == bi && j < bj)))) { best = h; bi = i; bj = j; }
         }

@@ -37,7 +37,7 @@ cudaError_t swb_launch_topk(const int32_t *scores, uint32_t n, const uint32_t *i
 cudaError_t swb_launch_scatter(const int32_t *sorted, const uint32_t *dst, uint32_t n, int32_t *out,
                                cudaStream_t st);
 // traceback alignments of a list of hits (cpu.cpp semantics), one block per job. hd_glob: rolling H diagonals of the jobs
-// whose 3 * (m + 2) ints exceed smem_ints (SwbAlignJob::hd_off); dir: 2-bit directions, (m + 1) * ceil((n + 1) / 4) bytes
+// whose swb_align_hd_ints(m) ints exceed smem_ints (SwbAlignJob::hd_off); dir: 2-bit directions, (m + 1) * ceil((n + 1) / 4) bytes
 // per job at dir_off; out_hdr: 5 ints per job {score, end_i, end_j, nops, ops_overflow}; out_ops: per job, from the END
 // of the alignment back to its start
 #define SWB_ALIGN_NT 256

@@ -86,6 +86,9 @@ struct SwbAlignJob {
     uint32_t reserved;
 };
 
+// ints of working storage per alignment job: three H diagonals of m + 2 entries and one direction byte per row
+SWB_HD uint64_t swb_align_hd_ints(uint32_t m) { return 3ull * ((uint64_t)m + 2u) + (((uint64_t)m + 5u) >> 2); }
+
 // base log (V16R): element offset (uint2) of a tile's region, 2 * (((width * slots) >> 6) + 33) elements long
 SWB_HD size_t swb_blog_offset(uint64_t bnd_off, uint32_t tile_idx) { return 2u * ((size_t)(bnd_off >> 6) + 34u * (size_t)tile_idx); }
 SWB_HD size_t swb_blog_elems(uint64_t bnd_elems, uint32_t ntiles) { return 2u * ((size_t)(bnd_elems >> 6) + 34u * (size_t)ntiles) + 68u; }

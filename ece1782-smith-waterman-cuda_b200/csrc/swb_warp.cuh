@@ -128,6 +128,7 @@ struct V16Base {
 //   c = viaddmax.relu(diag-g, S+g, left-g) ; h = viaddmax(h, -g, c) ; left' = vadd2(h, -g)
 struct V16 : V16Base {
     static const bool rebased = false;
+    static const bool blocked = true;  // one-lane tiles walk in pass groups over column blocks (swb_run_tile)
     struct C { T negg; };
     static SWB_HD C consts(const SwbScoreParams &p) { C c; c.negg = splat(-p.gap); return c; }
     static SWB_HD T hzero(const C &) { return 0u; }
@@ -191,6 +192,7 @@ struct V16 : V16Base {
 // blog); the reader adds (writer's base - its own base) with one vadd2 per column.
 struct V16R : V16Base {
     static const bool rebased = true;
+    static const bool blocked = false;
     static const bool is16 = false;  // exact: never flags, counts as a recompute pass
     struct C {
         T negg, fl, zrel;   // -g | floor of the row state (-g absolute) | zero (absolute) in the current base
@@ -302,6 +304,7 @@ struct V16R : V16Base {
 // V32: the same two sequences on two int32 lanes (no wrap for any realistic input).
 struct V32 {
     static const bool rebased = false;
+    static const bool blocked = false;
     struct T { int a, b; };
     struct C { int g; };
     static const bool is16 = false;
@@ -381,6 +384,7 @@ struct V32 {
 // V16A: two DB sequences per word (s16x2, 6.5 ALU-pipe instructions per cell pair); V32A: exact int32 recompute.
 struct V16A {
     static const bool rebased = false;
+    static const bool blocked = false;
     static const bool is16 = true;
     struct T { uint32_t h, f; };
     struct C { uint32_t neg_go, neg_ge; };
@@ -466,6 +470,7 @@ struct V16A {
 
 struct V32A {
     static const bool rebased = false;
+    static const bool blocked = false;
     static const bool is16 = false;
     struct T { int ha, hb, fa, fb; };
     struct C { int go, ge; };
@@ -606,11 +611,15 @@ SWB_HD void swb_run_tile(BE &be, const SwbScoreParams &p, const SwbTile &tile, u
         // microseconds later; what a pass needs to continue in the next block (its K row values and the diagonal
         // element) is parked in a small per-warp scratch (colstate) meanwhile. Only the bottom row of a whole GROUP still
         // goes through memory: 1 / SWB_PASS_GROUP of the traffic.
-        T *const cstate = reinterpret_cast<T *>(p.colstate) + (size_t)be.warp_slot() * swb_colstate_elems(K);
+        // Only the V16 policy is blocked: it is where the time goes, and its row state fits the registers beside the
+        // parking code; the two-value affine state (64 registers of rows at K = 32) spilled in the hot loop with it
+        // (measured: 4,905 against 5,249 GCUPS), so V16A / V32A / V32 keep pass groups of one, i.e. the straight order.
+        constexpr uint32_t PGV = V::blocked ? SWB_PASS_GROUP : 1u;
+        T *const cstate = PGV > 1u ? reinterpret_cast<T *>(p.colstate) + (size_t)be.warp_slot() * swb_colstate_elems(K) : nullptr;
         const size_t cs_pass = (size_t)(K + 4) * 32u;  // elements of T per parked pass: [K/4 + 1][lane][4]
-        for (uint32_t pg0 = ss_begin; pg0 < ss_end; pg0 += SWB_PASS_GROUP) {
-            const uint32_t pg1 = pg0 + SWB_PASS_GROUP < ss_end ? pg0 + SWB_PASS_GROUP : ss_end;
-            const uint32_t cbc = pg1 - pg0 > 1u ? SWB_BLOCK_CHUNKS : nchunks;  // a lone pass runs straight through
+        for (uint32_t pg0 = ss_begin; pg0 < ss_end; pg0 += PGV) {
+            const uint32_t pg1 = pg0 + PGV < ss_end ? pg0 + PGV : ss_end;
+            const uint32_t cbc = PGV > 1u && pg1 - pg0 > 1u ? SWB_BLOCK_CHUNKS : nchunks;  // a lone pass runs straight through
             for (uint32_t cb0 = 0; cb0 < nchunks; cb0 += cbc) {
                 const uint32_t cb1 = cb0 + cbc < nchunks ? cb0 + cbc : nchunks;
                 for (uint32_t ss = pg0; ss < pg1; ++ss) {
@@ -620,7 +629,7 @@ SWB_HD void swb_run_tile(BE &be, const SwbScoreParams &p, const SwbTile &tile, u
                     T *const park = cstate + (size_t)(ss - pg0) * cs_pass + (size_t)lane * 4u;
                     T left[K];
                     T diag0;
-                    if (cb0 == 0) {
+                    if (PGV == 1u || cb0 == 0) {
 #pragma unroll
                         for (int k = 0; k < K; ++k) left[k] = LZERO;
                         diag0 = LZERO;
@@ -681,7 +690,7 @@ SWB_HD void swb_run_tile(BE &be, const SwbScoreParams &p, const SwbTile &tile, u
                             bc[u] = bn[u];
                         }
                     }
-                    if (cb1 < nchunks) {
+                    if (PGV > 1u && cb1 < nchunks) {
 #pragma unroll
                         for (int k4 = 0; k4 < K / 4; ++k4) V::st4(be, park + (size_t)k4 * 128u, &left[4 * k4]);
                         T d4[4];

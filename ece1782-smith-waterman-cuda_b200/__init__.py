@@ -502,7 +502,9 @@ class Engine:
         nh = len(hits)
         hq = np.ascontiguousarray([h[0] for h in hits], dtype=np.uint32)
         hd = np.ascontiguousarray([h[1] for h in hits], dtype=np.uint32)
-        room = np.asarray([len(queries[int(h[0])]) + int(l) + 1 for h, l in zip(hits, subject_lens)], dtype=np.uint64)
+        qlen = [len(q) for q in queries]
+        room = np.asarray([(qlen[int(h[0])] if 0 <= int(h[0]) < len(qlen) else 0) + int(l) + 1
+                           for h, l in zip(hits, subject_lens)], dtype=np.uint64)  # a bad index is the C side's error to report
         ooff = np.zeros(nh + 1, dtype=np.uint64)
         ooff[1:] = np.cumsum(room)
         ops = np.zeros(max(int(ooff[-1]), 1), dtype=np.uint8)

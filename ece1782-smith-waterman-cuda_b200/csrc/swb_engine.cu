@@ -112,6 +112,7 @@ struct swb_engine {
     uint32_t cur_nq = 1;
     int nslots = 16;
     int load_threads = 4;  // host threads that gather a sharded load into the staging buffers
+    bool opt_static_wave = true;  // bulk launches: block-coherent first wave (swb_warp_loop)
     uint32_t chunk_rows = SWB_CHUNK_ROWS;  // query rows per launch for queries beyond shared memory
     bool chunk_rows_set = false;           // false: batches on small shards use 2048-row launches (below)
     // database
@@ -372,6 +373,8 @@ extern "C" int swb_set_option(swb_engine *e, const char *key, int64_t value)
     } else if (!strcmp(key, "direct_len")) {
         if (value < 0 || value > (1ll << 31)) return fail(e, SWB_ERR_ARG, "direct_len out of range");
         e->opt_direct_len = (uint32_t)value;
+    } else if (!strcmp(key, "static_wave")) {
+        e->opt_static_wave = value != 0;
     } else if (!strcmp(key, "load_threads")) {
         if (value < 1 || value > 64) return fail(e, SWB_ERR_ARG, "load_threads must be 1..64");
         e->load_threads = (int)value;
@@ -779,10 +782,15 @@ static int enqueue_pass(swb_engine *e, Slot &s, int mode, SwbScoreParams &p, con
             p.rebase_shift = (uint32_t)(g.K > 16 ? e->rebase_shift32 : e->rebase_shift);
             p.smem_rows = ls.smem_rows;
             p.warps_active = ls.warps_active;
+            {
+                const uint32_t nt = ls.block_cfg == SWB_BLOCK_SMALL ? SWB_NT_SMALL : SWB_NT_LARGE;
+                const uint32_t wpb = ls.warps_active ? ls.warps_active : nt / 32u;
+                p.static_wave = (g.split || !e->opt_static_wave) ? 0u : (uint32_t)ls.grid * wpb;
+            }
             p.first_chunk = ch.first;
             p.last_chunk = ch.last;
             p.counter = s.d_counters + counter++;
-            if (!g.split && (g.logg_mask & 1u) && gmode == SWB_MODE_S16) {  // the one blocked policy (V16)
+            if (SWB_PASS_GROUP > 1u && !g.split && (g.logg_mask & 1u) && gmode == SWB_MODE_S16) {  // blocked builds only
                 // One-lane tiles park the row state of a pass group between column blocks: one region per warp of the
                 // launch. The one-lane tiles of a pass sit in exactly one launch group and the passes of a query follow
                 // each other in stream order, so one buffer per slot serves them all.

@@ -7,6 +7,11 @@
 // ---------------------------------------------------------------------------------------------
 struct DevBackend {
     __device__ __forceinline__ int lane() const { return (int)(threadIdx.x & 31u); }
+    // first work item of this warp: its position among the working warps of the grid (wa = working warps per block, 0 = all)
+    __device__ __forceinline__ uint32_t static_item(uint32_t wa) const
+    {
+        return blockIdx.x * (wa ? wa : (blockDim.x >> 5)) + (threadIdx.x >> 5);
+    }
     // index of this warp among the warps of the launch (its colstate region)
     __device__ __forceinline__ uint32_t warp_slot() const { return blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); }
     __device__ __forceinline__ uint32_t shfl_up(uint32_t v, int d, int w) const

@@ -58,6 +58,8 @@ struct SwbScoreParams {
     uint32_t split_tile_start[SWB_MAX_LOGG];
     uint32_t split_item_end[SWB_MAX_LOGG];
     uint32_t warps_active;    // warps of a block that take work (0 = all): a launch with few tiles spreads them over the SMs
+    uint32_t static_wave;     // bulk launches: work items of the first wave, one per working warp of the grid, taken by
+                              // position (block-coherent); the counter hands out the items after them. 0 = all dynamic
     uint32_t *prog;           // [item] columns of its bottom row that a pass has published (zeroed per query)
     // V16R (rebased s16): columns per block = 1 << rebase_shift (chosen by the host from the scoring scheme so that a
     // pass over one block spans less than 2^15 score points); blog = base log of the boundary rows, two int32 per
@@ -69,8 +71,13 @@ struct SwbScoreParams {
     void *colstate;
 };
 
+// One-lane tiles: passes that walk over the column blocks together (swb_run_tile). 1 = the straight order, every pass over
+// the whole width -- the product default: the blocked order (4 passes x 16 chunks) cut the DRAM traffic of a 5,478-row
+// launch from 140 GB to 76 GB and raised the L2 hit rate from 58 % to 76 %, but ran 3.5 % SLOWER (8,952 against 9,278
+// GCUPS on the same GPU, profiles/r2n_*): the kernel is bound by the ALU pipe, not by memory, and the extra address
+// arithmetic of the nested loops lands on that pipe. Kept behind this macro as the measured answer to "why not block it".
 #ifndef SWB_PASS_GROUP
-#define SWB_PASS_GROUP 4u  // one-lane tiles: passes that walk over the column blocks together
+#define SWB_PASS_GROUP 1u
 #endif
 SWB_HD size_t swb_colstate_elems(int K) { return (size_t)SWB_PASS_GROUP * (size_t)(K + 4) * 32u; }
 

@@ -601,19 +601,18 @@ SWB_HD void swb_run_tile(BE &be, const SwbScoreParams &p, const SwbTile &tile, u
         // One lane per pair: no exchange between lanes. Residue codes of a chunk (4 columns x two sequences) come as byte
         // loads: zero-extended in registers, no ALU-pipe instruction is spent on unpacking them.
         //
-        // Order of the work: the obvious order -- pass after pass (K rows each) over the whole width -- streams the tile's
-        // residues and its boundary row (bottom row of one pass = top row of the next, 4 B per pair-column) through
-        // memory once per PASS, and with ~2,400 resident warps those streams are far larger than the L2: ncu showed
-        // 140 GB of DRAM traffic for one 5,478-row query against 0.2 GB of residues, and the first use of a loaded
-        // residue code as the top stall of the kernel. So the work is blocked twice: SWB_PASS_GROUP consecutive passes
-        // walk TOGETHER over column blocks of SWB_BLOCK_CHUNKS chunks -- block 0 by every pass of the group, then block
-        // 1, ... Inside a block the boundary row and the residues are reused from L1/L2 by the next pass a few
-        // microseconds later; what a pass needs to continue in the next block (its K row values and the diagonal
-        // element) is parked in a small per-warp scratch (colstate) meanwhile. Only the bottom row of a whole GROUP still
-        // goes through memory: 1 / SWB_PASS_GROUP of the traffic.
-        // Only the V16 policy is blocked: it is where the time goes, and its row state fits the registers beside the
-        // parking code; the two-value affine state (64 registers of rows at K = 32) spilled in the hot loop with it
-        // (measured: 4,905 against 5,249 GCUPS), so V16A / V32A / V32 keep pass groups of one, i.e. the straight order.
+        // Order of the work. The straight order -- pass after pass (K rows each) over the whole width -- streams the
+        // tile's residues and its boundary row (bottom row of one pass = top row of the next, 4 B per pair-column)
+        // through memory once per PASS, and with ~2,400 resident warps those streams are larger than the L2: ncu shows
+        // 140 GB of DRAM traffic for one 5,478-row query against 0.2 GB of residues. With SWB_PASS_GROUP > 1 the work is
+        // blocked twice instead: that many consecutive passes walk TOGETHER over column blocks of SWB_BLOCK_CHUNKS
+        // chunks (block 0 by every pass of the group, then block 1, ...), the boundary row and the residues of a block
+        // are reused from L1/L2 by the next pass a few microseconds later, and what a pass needs to continue in the next
+        // block (its K row values and the diagonal element) is parked in a small per-warp scratch (colstate); only the
+        // bottom row of a whole group still goes through memory. Measured on B200 (swb_types.h): half the DRAM traffic,
+        // 3.5 % slower -- the ALU pipe is the bound, not memory -- so the product builds with groups of one.
+        // Only the V16 policy can be blocked: the two-value affine state (64 registers of rows at K = 32) spilled in the
+        // hot loop with the parking code (4,905 against 5,249 GCUPS).
         constexpr uint32_t PGV = V::blocked ? SWB_PASS_GROUP : 1u;
         T *const cstate = PGV > 1u ? reinterpret_cast<T *>(p.colstate) + (size_t)be.warp_slot() * swb_colstate_elems(K) : nullptr;
         const size_t cs_pass = (size_t)(K + 4) * 32u;  // elements of T per parked pass: [K/4 + 1][lane][4]
@@ -983,8 +982,19 @@ SWB_HD void swb_run_tile(BE &be, const SwbScoreParams &p, const SwbTile &tile, u
 template <int K, class V, bool SPLIT, class BE>
 SWB_HD void swb_warp_loop(BE &be, const SwbScoreParams &p, const int8_t *sprof, uint32_t sstride)
 {
+    // First wave: warp w of block b starts with work item b * (warps per block) + w, every later item comes from the
+    // shared counter. Items are ordered longest first, so the warps of a block start on tiles of nearly the same length
+    // and finish together: a block (and its shared memory) leaves the SM when its SLOWEST warp is done, and with a
+    // first wave handed out in arrival order nearly every block held one of the longest tiles, i.e. seven waiting warps.
+    bool first = !SPLIT && p.static_wave != 0u;
     for (;;) {
-        const uint32_t v = be.next_tile(p.counter);
+        uint32_t v;
+        if (first) {
+            first = false;
+            v = be.static_item(p.warps_active);
+        } else {
+            v = be.next_tile(p.counter) + (SPLIT ? 0u : p.static_wave);
+        }
         if (v >= p.ntiles) break;
         if (SPLIT) {
             // one warp per block; it stages only the K << logG profile rows of its pass (sstride = K * 32 + 4).

@@ -23,6 +23,7 @@ struct HostBackend {
     int lane_id;
     int lane() const { return lane_id; }
     uint32_t warp_slot() const { return 0; }  // one warp at a time
+    uint32_t static_item(uint32_t) const { return 0; }
     uint32_t shfl_up(uint32_t v, int d, int width);
     uint32_t shfl_xor(uint32_t v, int m, int width);
     void syncwarp();
@@ -253,6 +254,7 @@ void run_pass(SwbScoreParams &p, int mode, const SwbQueryPlan &qp, const std::ve
             p.last_chunk = ch.last;
             uint32_t counter = 0;
             p.counter = &counter;
+            p.static_wave = g.split ? 0u : 1u;  // the one emulated warp takes item 0 by position, the rest from the counter
             // stage the chunk's profile exactly like swb_score_kernel (split groups stage per work item)
             const uint32_t sstride = p.smem_rows + (g.split ? 16u : 4u);
             std::vector<uint4> sprof_words(((size_t)sstride * SWB_ALPHA + 64) / 16);  // 16-byte aligned like shared memory

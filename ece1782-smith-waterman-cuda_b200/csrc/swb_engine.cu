@@ -112,7 +112,7 @@ struct swb_engine {
     uint32_t cur_nq = 1;
     int nslots = 16;
     int load_threads = 4;  // host threads that gather a sharded load into the staging buffers
-    bool opt_static_wave = true;  // bulk launches: block-coherent first wave (swb_warp_loop)
+    int opt_static_wave = -1;  // bulk launches: block-coherent first wave (swb_warp_loop): -1 auto, 0 off, 1 on
     uint32_t chunk_rows = SWB_CHUNK_ROWS;  // query rows per launch for queries beyond shared memory
     bool chunk_rows_set = false;           // false: batches on small shards use 2048-row launches (below)
     // database
@@ -374,7 +374,7 @@ extern "C" int swb_set_option(swb_engine *e, const char *key, int64_t value)
         if (value < 0 || value > (1ll << 31)) return fail(e, SWB_ERR_ARG, "direct_len out of range");
         e->opt_direct_len = (uint32_t)value;
     } else if (!strcmp(key, "static_wave")) {
-        e->opt_static_wave = value != 0;
+        e->opt_static_wave = value < 0 ? -1 : (value != 0);
     } else if (!strcmp(key, "load_threads")) {
         if (value < 1 || value > 64) return fail(e, SWB_ERR_ARG, "load_threads must be 1..64");
         e->load_threads = (int)value;
@@ -785,7 +785,15 @@ static int enqueue_pass(swb_engine *e, Slot &s, int mode, SwbScoreParams &p, con
             {
                 const uint32_t nt = ls.block_cfg == SWB_BLOCK_SMALL ? SWB_NT_SMALL : SWB_NT_LARGE;
                 const uint32_t wpb = ls.warps_active ? ls.warps_active : nt / 32u;
-                p.static_wave = (g.split || !e->opt_static_wave) ? 0u : (uint32_t)ls.grid * wpb;
+                // Block-coherent first wave (swb_warp_loop). Measured per rank workload of the multi-GPU layouts
+                // (profiles/r2o_sweep_static_wave.txt): +1.3 .. +1.6 % on half of Swiss-Prot with a quarter of the queries
+                // (1.7 tiles per warp), neutral on 1/4 and 1/8 of it and on the whole database with all 20 queries,
+                // -2.9 % on the whole database with a quarter of the queries (3.7 tiles per warp: there the widest tile is
+                // the critical path of the launch, and a block full of the widest tiles never gets a scheduler to
+                // itself). Auto: on when the launch has fewer than two tiles per working warp.
+                const uint32_t wave = (uint32_t)ls.grid * wpb;
+                const bool on = e->opt_static_wave > 0 || (e->opt_static_wave < 0 && p.ntiles < 2u * wave);
+                p.static_wave = (g.split || !on) ? 0u : wave;
             }
             p.first_chunk = ch.first;
             p.last_chunk = ch.last;

@@ -90,9 +90,9 @@ const char *swb_last_error(const swb_engine *e);
  *          "direct_len" (pipelined tiles at least this wide, against a query at least this long, skip the plain s16
  *          pass and are scored by the rebased policy at once; default 14000, 0 = never),
  *          "load_threads" (host threads that gather the residues of a sharded load, default 4),
- *          "static_wave" (1 (default) = the first work item of every warp of a bulk launch is taken by position, so the
- *          warps of a block start on tiles of similar length and the block leaves the SM together; 0 = all items from
- *          the shared counter in arrival order),
+ *          "static_wave" (1 = the first work item of every warp of a bulk launch is taken by position, so the warps of a
+ *          block start on tiles of similar length and the block leaves the SM together; 0 = all items from the shared
+ *          counter in arrival order; -1 (default) = by position when the launch has fewer than two tiles per warp),
  *          "chunk_rows" (query rows per launch for queries beyond shared memory; multiple of 1024, <= 7168) */
 int swb_set_option(swb_engine *e, const char *key, int64_t value);
 /* run on the caller's CUDA stream (cudaStream_t as void*); NULL = the engine's own stream */

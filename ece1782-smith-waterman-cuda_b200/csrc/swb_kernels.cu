@@ -129,7 +129,12 @@ __global__ void swb_profile_kernel(const uint8_t *__restrict__ q, uint32_t qlen,
 }
 
 // One block per tile (grid-stride): gathers the tile's sequences from the raw concatenated codes into
-// the interleaved 8-byte words the score kernel streams.
+// the interleaved 8-byte words the score kernel streams. The only HBM-bound kernel of the path (one read and one write
+// of the database per load: 405 MB in 0.22 ms = 1.9 TB/s, 0.28 of the measured copy rate; it runs once per database
+// load beside a 15 ms PCIe upload). A version that stages 128-column strips in shared memory (a warp reading 32
+// consecutive residues of ONE sequence per load, output words built from aligned 32-bit shared-memory reads) was
+// measured and is SLOWER: 0.346 ms against 0.29 ms under ncu (profiles/r2p_pack_kernel_ab.txt) -- three block barriers
+// per strip cost more than the scattered byte loads, which the L1 absorbs.
 __global__ void swb_pack_kernel(const SwbTile *__restrict__ tiles, uint32_t ntiles, const uint8_t *__restrict__ raw,
                                 const uint64_t *__restrict__ seq_off, const uint32_t *__restrict__ seq_len,
                                 uint32_t nseq, uint8_t *__restrict__ residues)

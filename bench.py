@@ -345,7 +345,7 @@ def main():
                     "(default) = the engine's rule: on for small shards")
     ap.add_argument("--split-k", type=int, default=0, help="rows per lane of the pipelined groups: 0 auto, 8, 16")
     ap.add_argument("--direct-len", type=int, default=-1, help="tiles / queries at least this long are scored by the "
-                    "rebased s16 policy at once (-1 = engine default 14000, 0 = never)")
+                    "rebased s16 policy at once (-1 = engine default 16000, 0 = never)")
     ap.add_argument("--exact", type=int, default=-1, help="exact passes: 0 rebased s16 (default), 1 int32")
     ap.add_argument("--batch-order", type=int, default=-1, help="0 longest query first (default), 1 as given")
     ap.add_argument("--chunk-rows", type=int, default=0)

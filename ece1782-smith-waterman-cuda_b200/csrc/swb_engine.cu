@@ -100,10 +100,11 @@ struct swb_engine {
     int rebase_shift32 = 0;   // the same for passes of 32 rows per lane (pipelined groups with split_k = 32)
     int opt_exact = 0;        // exact passes: 0 = V16R where the scheme allows it, 1 = always V32 (int32)
     int opt_split_k = 0;      // rows per lane of the pipelined-pass groups: 0 = auto, 8, 16
-    uint32_t opt_direct_len = 14000;  // pipelined tiles at least this wide against queries at least this long skip the
+    uint32_t opt_direct_len = 16000;  // pipelined tiles at least this wide against queries at least this long skip the
                               // plain s16 pass and are scored by V16R at once (their true scores pass 32767 anyway:
                               // with the reference's gap of 2, random long sequences score ~2.7 per residue, so pairs from ~12,000 residues
-                              // up overflow; measured on configs[3]: 10,000 / 14,000 -> 4,521 / 4,669 GCUPS); 0 = never
+                              // up overflow; measured on configs[3]: 10,000 / 14,000 -> 4,521 / 4,669 GCUPS, later
+                              // 14,000 / 16,000 / 18,000 / 21,000 -> 5,045 / 5,120 / 4,990 / 4,690); 0 = never
     int opt_split = -1;       // pipelined passes for the very long tiles: 1 on, 0 off, -1 auto = on for small shards
                               // (fewer tiles than twice the GPU's warp slots), where a few long tiles are the critical
                               // path of a query (+10 % at 1/8 of Swiss-Prot, +3 % at 1/4); on a large shard the bulk
@@ -689,7 +690,7 @@ static int shape_for(swb_engine *e, int K, int mode, bool split, uint32_t smem_r
     const bool per_item = split;  // one warp per block, each work item stages the rows of its pass
     if (per_item) smem_rows = (uint32_t)K * 32u;
     ls.smem_rows = smem_rows;
-    ls.smem = (size_t)SWB_ALPHA * (smem_rows + (split ? 16 : 4));  // row stride as in swb_score_kernel
+    ls.smem = (size_t)SWB_ALPHA * (smem_rows + (split ? 16 : SWB_BULK_LDW));  // row stride as in swb_score_kernel
     if (ls.smem > e->smem_optin) return fail(e, SWB_ERR_ARG, "internal: query chunk does not fit shared memory");
     ls.block_cfg = ls.smem <= SWB_SMALL_SMEM_LIMIT ? SWB_BLOCK_SMALL : SWB_BLOCK_LARGE;
     int per_sm = 0;
@@ -1236,7 +1237,7 @@ extern "C" int swb_align_batch(swb_engine *e, const uint8_t *qcodes, const uint6
 {
     if (!e || !qoffsets || (nhits && (!hit_query || !hit_db_id || !scores)) || (ops && !ops_offsets)) return SWB_ERR_ARG;
     if (!e->db_loaded) return fail(e, SWB_ERR_STATE, "swb_align before swb_db_load");
-    if (e->affine) return fail(e, SWB_ERR_STATE, "swb_align implements the linear gap model only");
+    const bool aff = e->affine;
     for (uint32_t i = 0; i < nq; ++i)
         if (qoffsets[i + 1] < qoffsets[i] || qoffsets[i + 1] - qoffsets[i] > 0x7ffffff0ull)
             return fail(e, SWB_ERR_ARG, "bad query offsets");
@@ -1266,7 +1267,7 @@ extern "C" int swb_align_batch(swb_engine *e, const uint8_t *qcodes, const uint6
         if (end_j) end_j[h] = 0;
         if (nops) nops[h] = 0;
         if (jb.m == 0 || jb.n == 0) continue;
-        if ((uint64_t)(jb.m + 1) * (((uint64_t)jb.n + 4) >> 2) > SWB_ALIGN_DIR_BUDGET)
+        if ((uint64_t)(jb.m + 1) * swb_align_row_bytes(jb.n, aff) > SWB_ALIGN_DIR_BUDGET)
             return fail(e, SWB_ERR_ARG, "alignment matrix larger than 2^34 cells");
         live.push_back(h);
     }
@@ -1285,13 +1286,13 @@ extern "C" int swb_align_batch(swb_engine *e, const uint8_t *qcodes, const uint6
         std::vector<SwbAlignJob> wave;
         while (end < live.size()) {
             SwbAlignJob jb = jobs[live[end]];
-            const uint64_t need = (uint64_t)(jb.m + 1) * (((uint64_t)jb.n + 4) >> 2);
+            const uint64_t need = (uint64_t)(jb.m + 1) * swb_align_row_bytes(jb.n, aff);
             if (end > at && dir_bytes + need > SWB_ALIGN_DIR_BUDGET) break;
             jb.dir_off = dir_bytes;
             dir_bytes += (need + 15u) & ~15ull;
             jb.ops_off = ops_bytes;
             ops_bytes += jb.cap;
-            const uint64_t hd = swb_align_hd_ints(jb.m);
+            const uint64_t hd = swb_align_hd_ints(jb.m, aff);
             if (hd <= smem_cap_ints) {
                 smem_ints = std::max<uint32_t>(smem_ints, (uint32_t)hd);
             } else {
@@ -1311,8 +1312,8 @@ extern "C" int swb_align_batch(swb_engine *e, const uint8_t *qcodes, const uint6
         CU(cudaMemcpyAsync(e->d_align_jobs, wave.data(), sizeof(SwbAlignJob) * nw, cudaMemcpyHostToDevice, st));
         int32_t *d_hdr = reinterpret_cast<int32_t *>(e->d_align_out);
         uint8_t *d_ops = e->d_align_out + 5 * sizeof(int32_t) * nw;
-        CU(swb_launch_align_batch(e->d_align_jobs, (uint32_t)nw, e->d_align_q, e->d_raw, e->d_mat, e->gap, e->d_align_h,
-                                  e->d_align_dir, d_hdr, d_ops, smem_ints, st));
+        CU(swb_launch_align_batch(e->d_align_jobs, (uint32_t)nw, e->d_align_q, e->d_raw, e->d_mat, e->gap, e->gap_extend, aff,
+                                  e->d_align_h, e->d_align_dir, d_hdr, d_ops, smem_ints, st));
         CU(cudaMemcpyAsync(e->h_align_out, e->d_align_out, out_bytes, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));  // the pageable `wave` vector was the source of an async copy: done by now
         const int32_t *hdr = reinterpret_cast<const int32_t *>(e->h_align_out);

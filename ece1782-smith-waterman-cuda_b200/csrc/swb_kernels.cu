@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(NT, MINB) swb_score_kernel(const SwbScoreParam
     extern __shared__ __align__(16) int8_t sprof[];
     // code rows one bank apart (+4) for the word loads of the bulk kernels; SPLIT kernels (one warp per block, mostly
     // one pair per warp: every lane reads the same code's row at its own offset) keep them 16-byte aligned for LDS.128
-    const uint32_t sstride = p.smem_rows + (SPLIT ? 16u : 4u);
+    const uint32_t sstride = p.smem_rows + (SPLIT ? 16u : (uint32_t)SWB_BULK_LDW);
     if (!SPLIT) {  // SPLIT: every work item stages the rows of its own pass (swb_warp_loop)
         const uint32_t wpr = p.smem_rows >> 2;  // words per code row
         for (uint32_t i = threadIdx.x; i < wpr * SWB_ALPHA; i += NT) {
@@ -485,10 +485,16 @@ cudaError_t swb_launch_topk(const int32_t *scores, uint32_t n, const uint32_t *i
 // the four cells of a direction byte are written by one thread on four consecutive diagonals: it collects them in a byte
 // per row next to the diagonals and stores each finished byte once -- no atomics, no read-modify-write of global
 // memory, no clearing pass.
+// AFF: Gotoh's three states (the reference has no affine code, so the tie-breaks are this repo's
+// definition, mirrored by the oracle's swo_align_affine): H takes its sources in cpu.cpp's order LEFT (E), TOP (F),
+// DIAG with strict '>'; a gap state prefers OPEN over EXTEND on a tie; 4 bits per cell (source of H, "E extended",
+// "F extended"), two more rolling diagonals each for E and F. With open == extend every choice coincides with the
+// linear walk.
+template <bool AFF>
 __global__ void __launch_bounds__(SWB_ALIGN_NT) swb_align_batch_kernel(const SwbAlignJob *__restrict__ jobs,
                                                                        const uint8_t *__restrict__ qbuf,
                                                                        const uint8_t *__restrict__ raw,
-                                                                       const int8_t *__restrict__ mat, int gap,
+                                                                       const int8_t *__restrict__ mat, int gap, int gap_ext,
                                                                        int32_t *hd_glob, uint8_t *dirbuf,
                                                                        int32_t *out_hdr, uint8_t *out_ops,
                                                                        uint32_t smem_ints)
@@ -497,16 +503,24 @@ __global__ void __launch_bounds__(SWB_ALIGN_NT) swb_align_batch_kernel(const Swb
     __shared__ int8_t s_mat[SWB_ALPHA * SWB_ALPHA];
     __shared__ int s_best[SWB_ALIGN_NT];
     __shared__ uint32_t s_bi[SWB_ALIGN_NT], s_bj[SWB_ALIGN_NT];
+    constexpr uint32_t BITS = AFF ? 4u : 2u;          // direction bits per cell
+    constexpr uint32_t PERB = 8u / BITS;              // cells per direction byte
+    constexpr uint32_t NDIAG = AFF ? 7u : 3u;         // rolling diagonals: 3 x H (+ 2 x E + 2 x F)
+    constexpr int NEG = -(1 << 28);
     const SwbAlignJob jb = jobs[blockIdx.x];
     const uint32_t m = jb.m, n = jb.n;
     const uint8_t *q = qbuf + jb.q_off, *d = raw + jb.d_off;
     uint8_t *dir = dirbuf + jb.dir_off;
-    const uint32_t Wb = (n + 4u) >> 2;  // bytes per direction row (columns 0 .. n)
+    const uint32_t Wb = swb_align_row_bytes(n, AFF);  // bytes per direction row (columns 0 .. n)
     const uint32_t tid = threadIdx.x;
-    int32_t *hd = swb_align_hd_ints(m) <= smem_ints ? s_hd : hd_glob + jb.hd_off;
-    int32_t *h0 = hd, *h1 = hd + (m + 2), *h2 = hd + 2 * (size_t)(m + 2);
-    uint8_t *cur = reinterpret_cast<uint8_t *>(hd + 3 * (size_t)(m + 2));  // per row: the direction byte being filled
-    for (uint32_t i = tid; i < 3 * (m + 2); i += SWB_ALIGN_NT) hd[i] = 0;
+    const size_t L = (size_t)m + 2;
+    int32_t *hd = swb_align_hd_ints(m, AFF) <= smem_ints ? s_hd : hd_glob + jb.hd_off;
+    int32_t *h0 = hd, *h1 = hd + L, *h2 = hd + 2 * L;
+    int32_t *e1 = hd + 3 * L, *e2 = hd + 4 * L, *f1 = hd + 5 * L, *f2 = hd + 6 * L;  // AFF only: previous / current
+    uint8_t *cur = reinterpret_cast<uint8_t *>(hd + NDIAG * L);  // per row: the direction byte being filled
+    for (uint32_t i = tid; i < 3 * L; i += SWB_ALIGN_NT) hd[i] = 0;
+    if (AFF)
+        for (uint32_t i = tid; i < 4 * L; i += SWB_ALIGN_NT) e1[i] = NEG;
     for (uint32_t i = tid; i < SWB_ALPHA * SWB_ALPHA; i += SWB_ALIGN_NT) s_mat[i] = mat[i];
     int best = 0;
     uint32_t bi = 0, bj = 0;
@@ -515,10 +529,14 @@ __global__ void __launch_bounds__(SWB_ALIGN_NT) swb_align_batch_kernel(const Swb
     for (uint32_t dd = 2; dd <= m + n; ++dd) {
         const uint32_t ilo = dd > n ? dd - n : 1u;
         const uint32_t ihi = dd - 1 < m ? dd - 1 : m;
-        // cells outside [ilo, ihi] of the new diagonal are borders (H = 0) for the next two diagonals
+        // cells outside [ilo, ihi] of the new diagonal are borders (H = 0, no gap state) for the next two diagonals
         if (tid == 0) {
             h2[ilo - 1] = 0;
             h2[ihi + 1] = 0;
+            if (AFF) {
+                e2[ilo - 1] = NEG; e2[ihi + 1] = NEG;
+                f2[ilo - 1] = NEG; f2[ihi + 1] = NEG;
+            }
         }
         // first row of this thread at or after ilo
         uint32_t i = ilo + (tid + SWB_ALIGN_NT - ((ilo - 1u) % SWB_ALIGN_NT)) % SWB_ALIGN_NT;
@@ -526,21 +544,33 @@ __global__ void __launch_bounds__(SWB_ALIGN_NT) swb_align_batch_kernel(const Swb
             const uint32_t j = dd - i;
             int h = 0;
             uint32_t t = 0;
-            const int left = h1[i] - gap;      // H(i, j-1)
-            const int up = h1[i - 1] - gap;    // H(i-1, j)
+            int left = h1[i] - gap;      // H(i, j-1) - open
+            int up = h1[i - 1] - gap;    // H(i-1, j) - open
+            if (AFF) {
+                const int ee = e1[i] - gap_ext, fe = f1[i - 1] - gap_ext;
+                if (ee > left) { left = ee; t |= 4u; }
+                if (fe > up) { up = fe; t |= 8u; }
+                e2[i] = left;
+                f2[i] = up;
+            }
             const int dg = h0[i - 1] + s_mat[(uint32_t)(q[i - 1] & 31u) * SWB_ALPHA + (d[j - 1] & 31u)];
-            if (left > h) { h = left; t = 1; }
-            if (up > h) { h = up; t = 2; }
-            if (dg > h) { h = dg; t = 3; }
+            if (left > h) { h = left; t = (t & 12u) | 1u; }
+            if (up > h) { h = up; t = (t & 12u) | 2u; }
+            if (dg > h) { h = dg; t = (t & 12u) | 3u; }
             h2[i] = h;
-            // four cells of a row share a direction byte: collected next to the diagonals, stored when complete
-            const uint32_t b = (((j & 3u) == 0u || j == 1u) ? 0u : (uint32_t)cur[i]) | (t << (2u * (j & 3u)));
+            // the cells of a row that share a direction byte are collected next to the diagonals, stored when complete
+            const uint32_t k = j & (PERB - 1u);
+            const uint32_t b = ((k == 0u || j == 1u) ? 0u : (uint32_t)cur[i]) | (t << (BITS * k));
             cur[i] = (uint8_t)b;
-            if ((j & 3u) == 3u || j == n) dir[(size_t)i * Wb + (j >> 2)] = (uint8_t)b;
+            if (k == PERB - 1u || j == n) dir[(size_t)i * Wb + j / PERB] = (uint8_t)b;
             // first row-major maximum: larger value, else smaller i, else smaller j
             if (h > best || (h == best && h > 0 && (i < bi || (i == bi && j < bj)))) { best = h; bi = i; bj = j; }
         }
         int32_t *tmp = h0; h0 = h1; h1 = h2; h2 = tmp;
+        if (AFF) {
+            tmp = e1; e1 = e2; e2 = tmp;
+            tmp = f1; f1 = f2; f2 = tmp;
+        }
         __syncthreads();
     }
     s_best[tid] = best;
@@ -555,15 +585,23 @@ __global__ void __launch_bounds__(SWB_ALIGN_NT) swb_align_batch_kernel(const Swb
             }
         }
         uint8_t *ops = out_ops + jb.ops_off;
-        uint32_t i = bi, j = bj, nops = 0;
+        uint32_t i = bi, j = bj, nops = 0, state = 0;  // state: 0 in H, 1 in E (gap in the query), 2 in F
         bool overflow = false;
         while (best > 0 && i > 0 && j > 0) {  // row 0 / column 0 are the H == 0 border (never written)
-            const uint32_t t = ((uint32_t)dir[(size_t)i * Wb + (j >> 2)] >> (2u * (j & 3u))) & 3u;
-            if (t == 0) break;
-            if (nops < jb.cap) ops[nops] = (uint8_t)t; else overflow = true;
+            const uint32_t t = ((uint32_t)dir[(size_t)i * Wb + j / PERB] >> (BITS * (j & (PERB - 1u)))) & (AFF ? 15u : 3u);
+            uint32_t op;
+            if (state == 0) {
+                op = t & 3u;
+                if (op == 0) break;
+                if (AFF && op != 3u) { state = op; continue; }  // enter the gap state of this very cell
+            } else {
+                op = state;
+                if (!(t & (state == 1u ? 4u : 8u))) state = 0;  // the gap was opened here: back to H after this column
+            }
+            if (nops < jb.cap) ops[nops] = (uint8_t)op; else overflow = true;
             ++nops;
-            if (t == 1) --j;
-            else if (t == 2) --i;
+            if (op == 1) --j;
+            else if (op == 2) --i;
             else { --i; --j; }
         }
         int32_t *hdr = out_hdr + 5 * (size_t)blockIdx.x;
@@ -576,8 +614,8 @@ __global__ void __launch_bounds__(SWB_ALIGN_NT) swb_align_batch_kernel(const Swb
 }
 
 cudaError_t swb_launch_align_batch(const SwbAlignJob *jobs, uint32_t njobs, const uint8_t *qbuf, const uint8_t *raw,
-                                   const int8_t *mat, int gap, int32_t *hd_glob, uint8_t *dir, int32_t *out_hdr,
-                                   uint8_t *out_ops, uint32_t smem_ints, cudaStream_t st)
+                                   const int8_t *mat, int gap_open, int gap_extend, bool affine, int32_t *hd_glob,
+                                   uint8_t *dir, int32_t *out_hdr, uint8_t *out_ops, uint32_t smem_ints, cudaStream_t st)
 {
     if (njobs == 0) return cudaSuccess;
     const size_t smem = (size_t)smem_ints * sizeof(int32_t);
@@ -586,12 +624,19 @@ cudaError_t swb_launch_align_batch(const SwbAlignJob *jobs, uint32_t njobs, cons
     cudaError_t ce = cudaGetDevice(&dev);
     if (ce != cudaSuccess) return ce;
     if (dev >= 64 || !done[dev].load(std::memory_order_acquire)) {
-        ce = cudaFuncSetAttribute(swb_align_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        ce = cudaFuncSetAttribute(swb_align_batch_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)SWB_ALIGN_SMEM_MAX);
+        if (ce == cudaSuccess)
+            ce = cudaFuncSetAttribute(swb_align_batch_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)SWB_ALIGN_SMEM_MAX);
         if (ce != cudaSuccess) return ce;
         if (dev < 64) done[dev].store(1, std::memory_order_release);
     }
-    swb_align_batch_kernel<<<njobs, SWB_ALIGN_NT, smem, st>>>(jobs, qbuf, raw, mat, gap, hd_glob, dir, out_hdr, out_ops,
-                                                             smem_ints);
+    if (affine)
+        swb_align_batch_kernel<true><<<njobs, SWB_ALIGN_NT, smem, st>>>(jobs, qbuf, raw, mat, gap_open, gap_extend, hd_glob,
+                                                                        dir, out_hdr, out_ops, smem_ints);
+    else
+        swb_align_batch_kernel<false><<<njobs, SWB_ALIGN_NT, smem, st>>>(jobs, qbuf, raw, mat, gap_open, gap_open, hd_glob,
+                                                                         dir, out_hdr, out_ops, smem_ints);
     return cudaGetLastError();
 }

@@ -36,12 +36,12 @@ cudaError_t swb_launch_topk(const int32_t *scores, uint32_t n, const uint32_t *i
                             int32_t *out_scores, cudaStream_t st);
 cudaError_t swb_launch_scatter(const int32_t *sorted, const uint32_t *dst, uint32_t n, int32_t *out,
                                cudaStream_t st);
-// traceback alignments of a list of hits (cpu.cpp semantics), one block per job. hd_glob: rolling H diagonals of the jobs
-// whose swb_align_hd_ints(m) ints exceed smem_ints (SwbAlignJob::hd_off); dir: 2-bit directions, (m + 1) * ceil((n + 1) / 4) bytes
-// per job at dir_off; out_hdr: 5 ints per job {score, end_i, end_j, nops, ops_overflow}; out_ops: per job, from the END
-// of the alignment back to its start
+// traceback alignments of a list of hits (cpu.cpp semantics; affine: Gotoh's three states), one block per job. hd_glob:
+// rolling diagonals of the jobs whose swb_align_hd_ints(m, affine) ints exceed smem_ints (SwbAlignJob::hd_off); dir:
+// packed directions, (m + 1) * swb_align_row_bytes(n, affine) bytes per job at dir_off; out_hdr: 5 ints per job {score,
+// end_i, end_j, nops, ops_overflow}; out_ops: per job, from the END of the alignment back to its start
 #define SWB_ALIGN_NT 256
 #define SWB_ALIGN_SMEM_MAX (216u * 1024u)
 cudaError_t swb_launch_align_batch(const SwbAlignJob *jobs, uint32_t njobs, const uint8_t *qbuf, const uint8_t *raw,
-                                   const int8_t *mat, int gap, int32_t *hd_glob, uint8_t *dir, int32_t *out_hdr,
-                                   uint8_t *out_ops, uint32_t smem_ints, cudaStream_t st);
+                                   const int8_t *mat, int gap_open, int gap_extend, bool affine, int32_t *hd_glob,
+                                   uint8_t *dir, int32_t *out_hdr, uint8_t *out_ops, uint32_t smem_ints, cudaStream_t st);

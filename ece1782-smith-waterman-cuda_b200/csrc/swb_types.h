@@ -71,6 +71,14 @@ struct SwbScoreParams {
     void *colstate;
 };
 
+// Bytes per shared-memory profile load of the bulk kernels (= the padding between code rows: 4 puts the rows one bank
+// apart, so the 32 lanes of an LDS.32 never conflict; 8 halves the LDS count -- 4.5 % fewer issue slots in the one-lane
+// loop -- but rows that are 16 codes apart share banks. Measured (profiles/r2r_sweep_lds64_ab.txt): 8 is 0.3 % slower on
+// the benchmark, 1 % with group_len 384, 2.6 % on the half-database rank workload -> 4)
+#ifndef SWB_BULK_LDW
+#define SWB_BULK_LDW 4
+#endif
+
 // One-lane tiles: passes that walk over the column blocks together (swb_run_tile). 1 = the straight order, every pass over
 // the whole width -- the product default: the blocked order (4 passes x 16 chunks) cut the DRAM traffic of a 5,478-row
 // launch from 140 GB to 76 GB and raised the L2 hit rate from 58 % to 76 %, but ran 3.5 % SLOWER (8,952 against 9,278
@@ -93,8 +101,13 @@ struct SwbAlignJob {
     uint32_t reserved;
 };
 
-// ints of working storage per alignment job: three H diagonals of m + 2 entries and one direction byte per row
-SWB_HD uint64_t swb_align_hd_ints(uint32_t m) { return 3ull * ((uint64_t)m + 2u) + (((uint64_t)m + 5u) >> 2); }
+// ints of working storage per alignment job: three H diagonals (affine: plus two each for E and F) of m + 2 entries and
+// one direction byte per row; bytes of one row of packed directions (2 bits per cell, affine 4) for columns 0 .. n
+SWB_HD uint64_t swb_align_hd_ints(uint32_t m, bool affine)
+{
+    return (affine ? 7ull : 3ull) * ((uint64_t)m + 2u) + (((uint64_t)m + 5u) >> 2);
+}
+SWB_HD uint32_t swb_align_row_bytes(uint32_t n, bool affine) { return affine ? (n + 2u) >> 1 : (n + 4u) >> 2; }
 
 // base log (V16R): element offset (uint2) of a tile's region, 2 * (((width * slots) >> 6) + 33) elements long
 SWB_HD size_t swb_blog_offset(uint64_t bnd_off, uint32_t tile_idx) { return 2u * ((size_t)(bnd_off >> 6) + 34u * (size_t)tile_idx); }

@@ -680,7 +680,7 @@ SWB_HD void swb_run_tile(BE &be, const SwbScoreParams &p, const SwbTile &tile, u
                         T outb[4];
 #pragma unroll
                         for (int u = 0; u < 4; ++u)
-                            outb[u] = V::template column<K, 4>(bc[u], diag0, left, best, cst, ca[u], cb[u], prow, sstride);
+                            outb[u] = V::template column<K, SWB_BULK_LDW>(bc[u], diag0, left, best, cst, ca[u], cb[u], prow, sstride);
                         if (write_bot) V::st4(be, bnd + ((size_t)c * 32u + lane) * 4u, outb);
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
@@ -805,7 +805,7 @@ SWB_HD void swb_run_tile(BE &be, const SwbScoreParams &p, const SwbTile &tile, u
                         ++colg;
                     }
                     if (!lead) { a = a2; b = b2; up = u2; }
-                    const T h = V::template column<K, 4>(up, diag0, left, best, cst, a, b, prow, sstride);
+                    const T h = V::template column<K, SWB_BULK_LDW>(up, diag0, left, best, cst, a, b, prow, sstride);
                     outb[u] = h;
                     hprev = h;
                     aprev = a;

@@ -88,7 +88,7 @@ const char *swb_last_error(const swb_engine *e);
  *          "exact" (scores beyond the s16 range: 0 (default) = the rebased s16 policy where the scoring scheme allows it
  *          -- steps between neighbouring cells small enough for a 16-bit window -- else int32; 1 = always int32),
  *          "direct_len" (pipelined tiles at least this wide, against a query at least this long, skip the plain s16
- *          pass and are scored by the rebased policy at once; default 14000, 0 = never),
+ *          pass and are scored by the rebased policy at once; default 16000, 0 = never),
  *          "load_threads" (host threads that gather the residues of a sharded load, default 4),
  *          "static_wave" (1 = the first work item of every warp of a bulk launch is taken by position, so the warps of a
  *          block start on tiles of similar length and the block leaves the SM together; 0 = all items from the shared
@@ -104,7 +104,9 @@ int swb_set_scoring(swb_engine *e, const int8_t *matrix, int alpha, int gap);
 int swb_set_scoring_preset(swb_engine *e, int preset);
 /* Affine gaps (Gotoh): a gap of length L costs gap_open + (L-1) * gap_extend, 0 <= gap_extend <= gap_open <= 64.
  * The reference only has the linear model ("define affine penalty ?", SWSolver.cu:8); gap_open == gap_extend is
- * that model and runs the same kernels as swb_set_scoring. swb_align stays linear-only. */
+ * that model and runs the same kernels as swb_set_scoring. swb_align / swb_align_batch follow the model that is set:
+ * under affine gaps they walk Gotoh's three states (H sources in cpu.cpp's order LEFT, TOP, DIAG with strict '>', a gap
+ * prefers to open over to extend on a tie); with gap_open == gap_extend that is exactly the linear walk. */
 int swb_set_scoring_affine(swb_engine *e, const int8_t *matrix, int alpha, int gap_open, int gap_extend);
 /* host helpers, usable without a GPU: the 32 x 32 preset matrix and the preset's char -> code map */
 int swb_scoring_matrix(int preset, int8_t *matrix32x32, int *gap);

@@ -279,3 +279,69 @@ void swo_scan_affine(const uint8_t *q, uint32_t qlen, const uint8_t *codes, cons
         out[k] = swo_score_affine(q, qlen, codes + off[k], (uint32_t)(off[k + 1] - off[k]), m, go, ge);
     }
 }
+
+/* Affine alignment with traceback: cpu.cpp:39-103 extended to Gotoh's three states. The reference has no such code, so
+ * the tie-breaks are this repo's definition (the engine's swb_align follows the same): H takes its sources in cpu.cpp's
+ * order LEFT (E), TOP (F), DIAG with strict '>'; a gap state prefers OPEN over EXTEND on a tie (extend only if strictly
+ * greater); first row-major maximum; walk back until H == 0. With go == ge every choice coincides with swo_align's
+ * (E(i,j) = H(i,j-1) - g is always an "open"), so the linear traceback -- pinned by the compiled cpu.cpp -- is the
+ * go == ge case of this one. a_out / b_out as in swo_align. */
+int32_t swo_align_affine(const uint8_t *q, const char *q_txt, uint32_t qlen, const uint8_t *d, const char *d_txt,
+                         uint32_t dlen, const int8_t *m, int32_t go, int32_t ge, char *a_out, char *b_out,
+                         uint32_t *end_i, uint32_t *end_j)
+{
+    const int32_t NEG = -(1 << 28);
+    size_t W = (size_t)dlen + 1, cells = ((size_t)qlen + 1) * W;
+    int32_t *H = (int32_t *)calloc(cells, sizeof(int32_t));
+    int32_t *E = (int32_t *)malloc(cells * sizeof(int32_t));
+    int32_t *F = (int32_t *)malloc(cells * sizeof(int32_t));
+    uint8_t *T = (uint8_t *)calloc(cells, 1); /* bits 0-1: source of H (0 none, 1 E, 2 F, 3 diag); 4: E extended; 8: F extended */
+    for (size_t k = 0; k < cells; ++k) E[k] = F[k] = NEG;
+    int32_t best = 0;
+    uint32_t bi = 0, bj = 0;
+    for (uint32_t i = 1; i <= qlen; ++i) {
+        for (uint32_t j = 1; j <= dlen; ++j) {
+            uint8_t t = 0;
+            int32_t e = H[i * W + j - 1] - go, f = H[(i - 1) * W + j] - go;
+            if (E[i * W + j - 1] - ge > e) { e = E[i * W + j - 1] - ge; t |= 4; }
+            if (F[(i - 1) * W + j] - ge > f) { f = F[(i - 1) * W + j] - ge; t |= 8; }
+            int32_t h = 0;
+            if (e > h) { h = e; t = (uint8_t)((t & 12) | 1); }
+            if (f > h) { h = f; t = (uint8_t)((t & 12) | 2); }
+            int32_t s = m[(size_t)q[i - 1] * SWO_ALPHA + d[j - 1]];
+            if (H[(i - 1) * W + j - 1] + s > h) { h = H[(i - 1) * W + j - 1] + s; t = (uint8_t)((t & 12) | 3); }
+            if (h > best) { best = h; bi = i; bj = j; }
+            H[i * W + j] = h;
+            E[i * W + j] = e;
+            F[i * W + j] = f;
+            T[i * W + j] = t;
+        }
+    }
+    size_t na = 0;
+    uint32_t i = bi, j = bj;
+    int state = 0; /* 0 = in H, 1 = in E (gap in the query), 2 = in F (gap in the subject) */
+    for (;;) {
+        uint8_t t = T[i * W + j];
+        if (state == 0) {
+            if ((t & 3) == 0) break; /* H == 0 */
+            if ((t & 3) == 3) { --i; --j; a_out[na] = q_txt[i]; b_out[na] = d_txt[j]; ++na; }
+            else state = (t & 3);
+        } else if (state == 1) {
+            --j; a_out[na] = '-'; b_out[na] = d_txt[j]; ++na;
+            if (!(t & 4)) state = 0;
+        } else {
+            --i; a_out[na] = q_txt[i]; b_out[na] = '-'; ++na;
+            if (!(t & 8)) state = 0;
+        }
+    }
+    for (size_t k = 0; k < na / 2; ++k) {
+        char c = a_out[k]; a_out[k] = a_out[na - 1 - k]; a_out[na - 1 - k] = c;
+        c = b_out[k]; b_out[k] = b_out[na - 1 - k]; b_out[na - 1 - k] = c;
+    }
+    a_out[na] = 0;
+    b_out[na] = 0;
+    if (end_i) *end_i = bi;
+    if (end_j) *end_j = bj;
+    free(H); free(E); free(F); free(T);
+    return best;
+}

@@ -256,7 +256,7 @@ void run_pass(SwbScoreParams &p, int mode, const SwbQueryPlan &qp, const std::ve
             p.counter = &counter;
             p.static_wave = g.split ? 0u : 1u;  // the one emulated warp takes item 0 by position, the rest from the counter
             // stage the chunk's profile exactly like swb_score_kernel (split groups stage per work item)
-            const uint32_t sstride = p.smem_rows + (g.split ? 16u : 4u);
+            const uint32_t sstride = p.smem_rows + (g.split ? 16u : (uint32_t)SWB_BULK_LDW);
             std::vector<uint4> sprof_words(((size_t)sstride * SWB_ALPHA + 64) / 16);  // 16-byte aligned like shared memory
             int8_t *sprof = reinterpret_cast<int8_t *>(sprof_words.data());
             if (!g.split)

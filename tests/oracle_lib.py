@@ -98,6 +98,22 @@ class Oracle:
                                _ptr(m, _i8p), gap, a, b, ctypes.byref(ei), ctypes.byref(ej))
         return int(s), a.value.decode(), b.value.decode(), (ei.value, ej.value)
 
+    def align_affine(self, qtxt, dtxt, go, ge, scheme="blosum50"):
+        """Gotoh alignment with traceback (swo_align_affine): (score, aligned a, aligned b, (end_i, end_j))"""
+        q = self.encode(qtxt, scheme)
+        d = self.encode(dtxt, scheme)
+        m = self.matrix(scheme)
+        a = ctypes.create_string_buffer(len(qtxt) + len(dtxt) + 1)
+        b = ctypes.create_string_buffer(len(qtxt) + len(dtxt) + 1)
+        ei, ej = ctypes.c_uint32(), ctypes.c_uint32()
+        self.lib.swo_align_affine.restype = ctypes.c_int32
+        self.lib.swo_align_affine.argtypes = [_u8p, ctypes.c_char_p, ctypes.c_uint32, _u8p, ctypes.c_char_p, ctypes.c_uint32,
+                                              _i8p, ctypes.c_int32, ctypes.c_int32, ctypes.c_char_p, ctypes.c_char_p,
+                                              ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32)]
+        s = self.lib.swo_align_affine(_ptr(q, _u8p), qtxt.encode(), len(q), _ptr(d, _u8p), dtxt.encode(), len(d),
+                                      _ptr(m, _i8p), go, ge, a, b, ctypes.byref(ei), ctypes.byref(ej))
+        return int(s), a.value.decode(), b.value.decode(), (ei.value, ej.value)
+
     def max_threads(self):
         return int(self.lib.swo_max_threads())
 

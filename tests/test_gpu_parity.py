@@ -384,6 +384,37 @@ def test_published_textbook_vector_on_gpu(swb):
         e.close()
 
 
+def test_affine_traceback_matches_oracle(swb, oracle, subset, queries):
+    """swb_align_batch under affine gaps (Gotoh's three states, 4 direction bits per cell) == the oracle's swo_align_affine
+    -- scores, end cells and both aligned strings -- for the top hits of two queries under three gap models; open ==
+    extend through the affine kernel path of the traceback is the linear walk the compiled cpu.cpp pins"""
+    m = swb.scoring_matrix(swb.SWB_SCORING_BLOSUM50_REF)[0]
+    e = swb.Engine(0)
+    try:
+        names = ("P02232", "P01008")
+        qs = [swb.encode(queries[nm]) for nm in names]
+        for go, ge in ((10, 2), (5, 1), (12, 0)):
+            e.set_scoring_affine(m, go, ge)
+            e.db_load(subset["codes"], subset["offsets"])
+            ids, top = e.search_batch_topk(*swb.pack_sequences(qs), 5)
+            hits = [(qi, int(sid)) for qi in range(len(qs)) for sid in ids[qi]] + [(0, 56), (1, 110)]
+            got = e.align_batch(qs, hits, [len(subset["seqs"][sid]) for _, sid in hits])
+            for (qi, sid), (score, ei, ej, ops) in zip(hits, got):
+                subj = subset["seqs"][sid]
+                want = oracle.align_affine(queries[names[qi]], subj, go, ge)
+                assert score == want[0] and (ei, ej) == want[3], (go, ge, qi, sid)
+                assert swb.render_alignment(queries[names[qi]], subj, ei, ej, ops) == (want[1], want[2]), (go, ge, qi, sid)
+            assert [g[0] for g in got[:5]] == [int(v) for v in top[0]]
+        # a gap that is extended: AAAA x AAGGAA with open 3 / extend 1
+        c, o = swb.pack_sequences([swb.encode("AAGGAA")])
+        e.set_scoring_affine(m, 3, 1)
+        e.db_load(c, o)
+        score, ei, ej, ops = e.align(swb.encode("AAAA"), 0, 6)
+        assert score == 16 and swb.render_alignment("AAAA", "AAGGAA", ei, ej, ops) == ("AA--AA", "AAGGAA")
+    finally:
+        e.close()
+
+
 def test_align_batch_matches_single_calls_and_oracle(swb, oracle, subset, queries):
     """swb_align_batch: the hit lists of several queries in ONE launch (one block per hit, H diagonals in shared memory,
     2-bit directions) == swb_align hit by hit == the oracle's restatement of cpu.cpp:39-103; empty hits, repeated hits
@@ -763,9 +794,8 @@ def test_affine_gaps_vs_gotoh_oracle(swb, oracle, subset, queries, group_len, k)
         batch = e.search_batch(qs)
         for q, got in zip(qs, batch):
             assert np.array_equal(got, oracle.scan_affine(q, codes, offs, m, 10, 2)), len(q)
-        # traceback is linear-only and says so
-        with pytest.raises(swb.SwbError):
-            e.align(qs[0], 0, int(offs[1] - offs[0]))
+        # traceback under the affine model: the score of the walk is the scan's score
+        assert e.align(qs[0], 0, int(offs[1] - offs[0]))[0] == batch[0][0]
         # go == ge: the linear kernels, the reference's goldens
         e.set_scoring_affine(m, 2, 2)
         e.set_option("chunk_rows", 7168)

@@ -141,3 +141,47 @@ def test_affine_is_sandwiched_by_the_pinned_linear_oracle(oracle, subset, querie
         lin10 = oracle.scan_affine(q, codes, offs, m, 10, 10)
         aff = oracle.scan_affine(q, codes, offs, m, 10, 2)
         assert (lin10 <= aff).all() and (aff <= lin2).all() and (lin10 < lin2).any()
+
+
+def _score_of_alignment(a, b, m, enc, go, ge):
+    """score of two aligned strings under an affine model (a gap of length L costs go + (L-1) ge)"""
+    total, gap_a, gap_b = 0, False, False
+    for x, y in zip(a, b):
+        if x == "-":
+            total -= ge if gap_a else go
+            gap_a, gap_b = True, False
+        elif y == "-":
+            total -= ge if gap_b else go
+            gap_a, gap_b = False, True
+        else:
+            total += int(m[enc(x)[0], enc(y)[0]])
+            gap_a = gap_b = False
+    return total
+
+
+def test_affine_traceback_restatement(oracle, subset, queries):
+    """swo_align_affine (cpu.cpp:39-103 extended to Gotoh's three states; parity unpinned like the affine scan): its
+    open == extend case must be the linear traceback that the compiled cpu.cpp pins, character for character; in
+    general the score must equal the score-only recurrence, the printed alignment must re-score to it, and ungapped
+    both strings must be substrings ending at the reported cell."""
+    ref = json.load(open(os.path.join(GOLDEN, "cpu_ref_ident3.json")))
+    for p in ref["pairs"]:
+        s, a, b, end = oracle.align_affine(p["a"], p["b"], 2, 2, "ident3")
+        assert (s, a, b) == (p["score"], p["aligned_a"], p["aligned_b"])
+    m = oracle.matrix("blosum50")
+    enc = lambda ch: oracle.encode(ch)
+    for name in ("P02232", "P01008"):
+        for sid in (0, 13, 16, 56):
+            subj = subset["seqs"][sid]
+            lin = oracle.align(queries[name], subj, "blosum50")
+            assert oracle.align_affine(queries[name], subj, 2, 2) == lin
+            for go, ge in ((10, 2), (5, 1), (12, 0)):
+                s, a, b, (ei, ej) = oracle.align_affine(queries[name], subj, go, ge)
+                c, o = pack_db([oracle.encode(subj)])
+                assert s == oracle.scan_affine(oracle.encode(queries[name]), c, o, m, go, ge)[0]
+                assert _score_of_alignment(a, b, m, enc, go, ge) == s
+                ua, ub = a.replace("-", ""), b.replace("-", "")
+                assert queries[name][ei - len(ua):ei] == ua and subj[ej - len(ub):ej] == ub
+    # hand-checked: AAAA x AAGGAA with open 3 / extend 1 joins the two halves through a two-residue gap (16)
+    assert oracle.align_affine("AAAA", "AAGGAA", 3, 1)[:3] == (16, "AA--AA", "AAGGAA")
+    assert oracle.align_affine("HEAGAWGHEE", "PAWHEAE", 8, 8)[:3] == (28, "AWGHE", "AW-HE")

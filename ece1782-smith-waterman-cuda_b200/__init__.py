@@ -46,7 +46,7 @@ class SwbStats(ctypes.Structure):
         ("kernel_launches", ctypes.c_uint32),
         ("last_k", ctypes.c_uint32),
         ("sm_count", ctypes.c_uint32),
-        ("reserved", ctypes.c_uint32),
+        ("pack_us", ctypes.c_uint32),
     ]
 
     def as_dict(self):

@@ -643,8 +643,14 @@ int swb_db_load_sorted(swb_engine *e, const uint8_t *codes, const uint64_t *offs
         CU(cudaMemcpyAsync(e->d_tiles, pl.tiles.data(), sizeof(SwbTile) * ntiles, cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(e->d_out_pos, pl.out_pos.data(), sizeof(uint32_t) * nl, cudaMemcpyHostToDevice, st));
         t3 = wall_ms();
+        // the one HBM-bound kernel of the path, timed on the device (ev_start / ev_stop are free: no search is in flight)
+        CU(cudaEventRecord(e->ev_start, st));
         CU(swb_launch_pack(e->d_tiles, ntiles, e->d_raw, e->d_seq_off, e->d_seq_len, nl, e->d_residues, st));
+        CU(cudaEventRecord(e->ev_stop, st));
         CU(cudaStreamSynchronize(st));
+        float pack_ms = 0.f;
+        CU(cudaEventElapsedTime(&pack_ms, e->ev_start, e->ev_stop));
+        e->stats.pack_us = (uint32_t)(pack_ms * 1000.f + 0.5f);
     }
     e->db_loaded = true;
     e->stats.load_ms = wall_ms() - t0;

@@ -65,7 +65,7 @@ typedef struct swb_stats_t {
     uint32_t kernel_launches;   /* kernels launched by the last search call */
     uint32_t last_k;            /* query rows per lane used by the last score kernel */
     uint32_t sm_count;
-    uint32_t reserved;
+    uint32_t pack_us;           /* device time of the pack kernel of the last swb_db_load, microseconds (CUDA events) */
 } swb_stats_t;
 
 /* ---- engine ------------------------------------------------------------------------------ */

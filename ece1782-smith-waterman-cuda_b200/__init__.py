@@ -77,7 +77,7 @@ ABI_SYMBOLS = [
     "swb_group_db_parts", "swb_group_set_option", "swb_group_set_scoring", "swb_group_set_scoring_preset",
     "swb_group_set_scoring_affine", "swb_group_db_load", "swb_group_search_batch", "swb_group_search_batch_topk",
     "swb_group_stats", "swb_layout_parts", "swb_layout_parts_batch", "swb_layout_query_groups",
-    "swb_microbench", "swb_align", "swb_align_batch", "swb_read_fasta", "swb_read_uniprot_dat", "swb_free", "swb_dbfile_write",
+    "swb_microbench", "swb_pack_time", "swb_align", "swb_align_batch", "swb_read_fasta", "swb_read_uniprot_dat", "swb_free", "swb_dbfile_write",
     "swb_dbfile_open", "swb_dbfile_count", "swb_dbfile_first_id", "swb_dbfile_offsets", "swb_dbfile_codes",
     "swb_dbfile_close",
 ]
@@ -206,6 +206,8 @@ def lib():
     L.swb_dbfile_codes.argtypes = [vp]
     L.swb_dbfile_close.restype = None
     L.swb_dbfile_close.argtypes = [vp]
+    L.swb_pack_time.restype = ctypes.c_int
+    L.swb_pack_time.argtypes = [vp, ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint64)]
     L.swb_microbench.restype = ctypes.c_int
     L.swb_microbench.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double),
                                  ctypes.POINTER(ctypes.c_double)]
@@ -519,6 +521,12 @@ class Engine:
                                             ooff.ctypes.data_as(_u64p), cnt.ctypes.data_as(_u32p)), "swb_align_batch")
         return [(int(scores[h]), int(ei[h]), int(ej[h]), ops[int(ooff[h]):int(ooff[h]) + int(cnt[h])].copy())
                 for h in range(nh)]
+
+    def pack_time(self, reps=10):
+        """(microseconds per launch, bytes read + written per launch) of the pack kernel of the loaded database"""
+        us, nbytes = ctypes.c_double(), ctypes.c_uint64()
+        self._check(self._L.swb_pack_time(self._h, reps, ctypes.byref(us), ctypes.byref(nbytes)), "swb_pack_time")
+        return us.value, int(nbytes.value)
 
     def stats(self):
         s = SwbStats()

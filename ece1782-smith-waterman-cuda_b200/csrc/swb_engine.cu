@@ -672,6 +672,31 @@ extern "C" int swb_db_load(swb_engine *e, const uint8_t *codes, const uint64_t *
     return swb_db_load_sorted(e, codes, offsets, n, shard, nshards, nullptr);
 }
 
+extern "C" int swb_pack_time(swb_engine *e, int reps, double *us_per_launch, uint64_t *bytes_per_launch)
+{
+    if (!e || !us_per_launch || reps < 1 || reps > 1000) return SWB_ERR_ARG;
+    if (!e->db_loaded) return fail(e, SWB_ERR_STATE, "swb_pack_time before swb_db_load");
+    const SwbPlan &pl = e->plan;
+    *us_per_launch = 0.0;
+    if (bytes_per_launch) *bytes_per_launch = pl.residues_local + pl.res_bytes;
+    if (pl.n_local == 0 || pl.tiles.empty()) return SWB_OK;
+    CU(cudaSetDevice(e->device));
+    cudaStream_t st = main_stream(e);
+    CU(cudaStreamSynchronize(st));
+    for (int i = 0; i < SWB_MAX_SLOTS; ++i) CU(cudaStreamSynchronize(e->slots[i].stream));
+    for (int r = 0; r <= reps; ++r) {  // launch 0 is the warm-up
+        if (r == 1) CU(cudaEventRecord(e->ev_start, st));
+        CU(swb_launch_pack(e->d_tiles, (uint32_t)pl.tiles.size(), e->d_raw, e->d_seq_off, e->d_seq_len, pl.n_local,
+                           e->d_residues, st));
+    }
+    CU(cudaEventRecord(e->ev_stop, st));
+    CU(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, e->ev_start, e->ev_stop));
+    *us_per_launch = (double)ms * 1000.0 / reps;
+    return SWB_OK;
+}
+
 extern "C" uint32_t swb_db_count(const swb_engine *e) { return (e && e->db_loaded) ? e->plan.n_local : 0; }
 
 extern "C" int swb_db_ids(const swb_engine *e, uint32_t *ids)

@@ -239,6 +239,11 @@ void swb_dbfile_close(swb_dbfile *d);
  * the single rate (vadd2 issues on another pipe -> 3.5 per pair), the other pairs at the single rate (same pipe). If
  * kind 11 did not double, the count would be 4.5. bench.py prints both variants and the flag it derived. */
 int swb_microbench(int device, int kind, double *glane_instr_per_s, double *ms);
+/* Re-runs the pack kernel of the loaded database `reps` times (same inputs, same output) and reports the mean device time
+ * per launch in microseconds and the bytes one launch reads + writes: the HBM figure of the one bandwidth-bound kernel of
+ * the path at steady clocks. (swb_stats_t::pack_us is the same kernel inside swb_db_load, right after an upload during
+ * which the SMs were idle.) */
+int swb_pack_time(swb_engine *e, int reps, double *us_per_launch, uint64_t *bytes_per_launch);
 
 #ifdef __cplusplus
 }

@@ -361,6 +361,23 @@ def test_traceback_alignment_matches_cpu_cpp_and_oracle(swb, oracle, subset, que
         e.close()
 
 
+def test_pack_time_reruns_the_pack_kernel_without_side_effects(swb, oracle, subset, queries):
+    """swb_pack_time (measurement support of bench.py's roofline.hbm_pack): re-running the pack kernel leaves the
+    resident database as it was"""
+    e = swb.Engine(0)
+    try:
+        with pytest.raises(swb.SwbError):
+            e.pack_time(3)
+        e.db_load(subset["codes"], subset["offsets"])
+        q = swb.encode(queries["P01008"])
+        before = e.search(q)
+        us, nbytes = e.pack_time(3)
+        assert us > 0 and nbytes >= 2 * int(subset["offsets"][-1])
+        assert np.array_equal(e.search(q), before) and np.array_equal(before, _gold("P01008"))
+    finally:
+        e.close()
+
+
 def test_published_textbook_vector_on_gpu(swb):
     """Durbin et al. 1998, fig. 2.6: HEAGAWGHEE x PAWHEAE under BLOSUM50 with gap 8 -> 28, AWGHE / AW-HE -- through the scan,
     the traceback and the affine kernels with open == extend == 8 (an external known answer, see tests/test_oracle.py)"""

@@ -1306,7 +1306,7 @@ extern "C" int swb_align_batch(swb_engine *e, const uint8_t *qcodes, const uint6
     CU(cudaSetDevice(e->device));
     cudaStream_t st = main_stream(e);
     CU(GROW_DEV(e->d_align_q, e->align_q_cap, (size_t)qbytes));
-    CU(cudaMemcpyAsync(e->d_align_q, qcodes + qoffsets[0], (size_t)qbytes, cudaMemcpyHostToDevice, st));
+    if (qbytes) CU(cudaMemcpyAsync(e->d_align_q, qcodes + qoffsets[0], (size_t)qbytes, cudaMemcpyHostToDevice, st));
     const uint32_t smem_cap_ints = SWB_ALIGN_SMEM_MAX / sizeof(int32_t);
     size_t at = 0;
     while (at < live.size()) {

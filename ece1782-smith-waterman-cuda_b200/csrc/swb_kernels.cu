@@ -128,25 +128,79 @@ __global__ void swb_profile_kernel(const uint8_t *__restrict__ q, uint32_t qlen,
         prof[(size_t)code * stride + r] = (int8_t)(mat[qc * SWB_ALPHA + code] + bias);
 }
 
-// One block per tile (grid-stride): gathers the tile's sequences from the raw concatenated codes into
-// the interleaved 8-byte words the score kernel streams. The only HBM-bound kernel of the path (one read and one write
-// of the database per load: 405 MB in 0.22 ms = 1.9 TB/s, 0.28 of the measured copy rate; it runs once per database
-// load beside a 15 ms PCIe upload). A version that stages 128-column strips in shared memory (a warp reading 32
-// consecutive residues of ONE sequence per load, output words built from aligned 32-bit shared-memory reads) was
-// measured and is SLOWER: 0.346 ms against 0.29 ms under ncu (profiles/r2p_pack_kernel_ab.txt) -- three block barriers
-// per strip cost more than the scattered byte loads, which the L1 absorbs.
-__global__ void swb_pack_kernel(const SwbTile *__restrict__ tiles, uint32_t ntiles, const uint8_t *__restrict__ raw,
-                                const uint64_t *__restrict__ seq_off, const uint32_t *__restrict__ seq_len,
-                                uint32_t nseq, uint8_t *__restrict__ residues)
+// One block per tile (grid-stride): gathers the tile's sequences from the raw concatenated codes into the interleaved
+// 8-byte words the score kernel streams ([chunk of 4 columns][slot][4 x (seqA, seqB)], same bytes as swb_pack_word,
+// which the host emulation uses). The only HBM-bound kernel of the path: one read and one write of the database per
+// load. Three versions were measured on the benchmark database (403 MB per launch, swb_pack_time):
+//   byte gathers, one output word per thread (16 LDG.U8 each)            282 us  1.4 TB/s  0.22 of the copy rate
+//   128-column strips staged through shared memory, block barriers        slower than the first (0.35 vs 0.29 ms, ncu)
+//   this one: 16 columns per thread, aligned 32-bit loads + funnel shifts  121 us  3.3 TB/s  0.50
+// The byte version was bound by L1 wavefronts (every lane of a load hits another sequence's sector and uses one byte
+// of it); here every loaded word is used whole and the stores of a warp are 32 consecutive words.
+// 16 consecutive residues of one sequence starting at column col0 as four words (columns past the end hold PAD): five
+// aligned 32-bit loads and four funnel shifts instead of sixteen byte loads. raw is a cudaMalloc'ed buffer with slack
+// behind the last residue (grow_dev), so the aligned word that holds the last byte is always readable.
+__device__ __forceinline__ void swb_pack_load16(const uint8_t *__restrict__ raw, uint64_t off, uint32_t len, uint32_t col0,
+                                                uint32_t (&v)[4])
+{
+    const uint32_t PADW = 0x01010101u * (uint32_t)SWB_PAD;
+    if (col0 >= len) {
+        v[0] = v[1] = v[2] = v[3] = PADW;
+        return;
+    }
+    const uint64_t a = off + col0;
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(raw + (a & ~3ull));
+    const uint32_t sh = (uint32_t)(a & 3ull) * 8u;
+    const uint32_t left = len - col0;  // residues from col0 on
+    uint32_t x[5];
+#pragma unroll
+    const uint32_t span = (uint32_t)(a & 3ull) + (left < 16u ? left : 16u);  // bytes from w[0] to the last one needed
+#pragma unroll
+    for (int k = 0; k < 5; ++k) x[k] = (4u * (uint32_t)k < span) ? __ldg(w + k) : 0u;  // never past the word that holds it
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        uint32_t t = __funnelshift_r(x[k], x[k + 1], sh) & 0x1f1f1f1fu;
+        const uint32_t have = left > 4u * (uint32_t)k ? left - 4u * (uint32_t)k : 0u;  // valid bytes of this word
+        if (have < 4u) {
+            const uint32_t keep = have ? (0xffffffffu >> (8u * (4u - have))) : 0u;
+            t = (t & keep) | (PADW & ~keep);
+        }
+        v[k] = t;
+    }
+}
+
+__global__ void __launch_bounds__(256) swb_pack_kernel(const SwbTile *__restrict__ tiles, uint32_t ntiles,
+                                                       const uint8_t *__restrict__ raw,
+                                                       const uint64_t *__restrict__ seq_off,
+                                                       const uint32_t *__restrict__ seq_len, uint32_t nseq,
+                                                       uint8_t *__restrict__ residues)
 {
     for (uint32_t ti = blockIdx.x; ti < ntiles; ti += gridDim.x) {
         const SwbTile t = tiles[ti];
         const uint32_t P = 32u >> t.logG;
-        const uint32_t total = (t.width >> 2) * P;
+        const uint32_t nch = t.width >> 2;
+        const uint32_t ngr = (nch + 3u) >> 2;  // groups of four chunks = 16 columns
         uint64_t *out = reinterpret_cast<uint64_t *>(residues + t.res_off);
-        for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
-            const uint32_t c = i / P, slot = i - c * P;
-            out[i] = swb_pack_word(t, c, slot, raw, seq_off, seq_len, nseq);
+        // one thread = 16 columns of one slot (both sequences of the pair): the 32 lanes of a warp write 32 consecutive
+        // 8-byte words per chunk, and every load is a 4-byte word of which all bytes are used
+        for (uint32_t i = threadIdx.x; i < ngr * P; i += blockDim.x) {
+            const uint32_t gq = i >> (5u - t.logG), slot = i & (P - 1u);
+            uint32_t va[4], vb[4];
+            uint32_t lenA = 0, lenB = 0;
+            uint64_t offA = 0, offB = 0;
+            const uint64_t sA = 2ull * ((uint64_t)t.first_pair + slot);
+            if (slot < t.npairs && sA < nseq) { lenA = seq_len[sA]; offA = seq_off[sA]; }
+            if (slot < t.npairs && sA + 1 < nseq) { lenB = seq_len[sA + 1]; offB = seq_off[sA + 1]; }
+            swb_pack_load16(raw, offA, lenA, gq * 16u, va);
+            swb_pack_load16(raw, offB, lenB, gq * 16u, vb);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t c = gq * 4u + (uint32_t)k;
+                if (c < nch) {
+                    const uint32_t lo = __byte_perm(va[k], vb[k], 0x5140), hi = __byte_perm(va[k], vb[k], 0x7362);
+                    out[(size_t)c * P + slot] = (uint64_t)lo | ((uint64_t)hi << 32);  // A0 B0 A1 B1 | A2 B2 A3 B3
+                }
+            }
         }
     }
 }

@@ -587,15 +587,16 @@ def main():
 
     if rank == 0:
         # roofline of the dominant kernel (swb_score_kernel<K,V16>): the ALU pipe (64 lanes/clk/SM). Per cell pair the
-        # kernel issues prmt + viaddmax.relu + viaddmax + 1/2 vimax3 on that pipe (3.5) and one vadd2, which the
-        # pairwise microbenchmark shows issuing on another pipe (viaddmax+vadd2 runs at twice the single rate); if it
-        # did not, the count would be 4.5. Peak = measured single-instruction issue rate / ALU instructions per cell.
+        # kernel issues prmt + vimax3.relu + 1/2 vimax3 on that pipe (2.5) and two vadd2, which the pairwise
+        # microbenchmark shows issuing on another pipe (viaddmax+vadd2 runs at twice the single rate); if they did
+        # not, the count would be 4.5. Peak = measured single-instruction issue rate / ALU instructions per cell.
+        # (Until profiles/r2x the cell had 3.5 ALU-pipe instructions; frac_vs_3.5 keeps that ceiling for comparison.)
         alu = swb.microbench(local, 0)      # Glane-instr/s of viaddmax.relu alone = the ALU pipe's issue rate
         pair = swb.microbench(local, 11)    # viaddmax + vadd2 in the same loop
-        mix = swb.microbench(local, 4)      # dependent-chain loop of the whole 4.5-instruction mix (a lower bound)
+        mix = swb.microbench(local, 14)     # dependent-chain loop of the whole 4.5-instruction mix (a lower bound)
         per_kind = {swb.MICROBENCH_KINDS[k]: round(swb.microbench(local, k), 1) for k in (0, 1, 2, 3, 5, 6, 11, 12, 13)}
         vadd_off_alu = pair > 1.5 * alu
-        instr_per_cell = (3.5 if vadd_off_alu else 4.5) / 2.0
+        instr_per_cell = (2.5 if vadd_off_alu else 4.5) / 2.0
         ach_padded = padded_cells / (ms_per_step * 1e-3) * 1e-9  # cells the kernels really execute, all ranks
         peak_gcups = alu / instr_per_cell
         peaks = {}
@@ -621,14 +622,22 @@ def main():
                     "achieved_incl_padding": ach_padded / world,
                     "frac_incl_padding": (ach_padded / world) / peak_gcups,
                     "alu_instr_per_cell_pair": {"used": 2 * instr_per_cell, "if_vadd2_on_alu_pipe": 4.5,
-                                                "if_vadd2_off_alu_pipe": 3.5, "vadd2_off_alu_pipe": bool(vadd_off_alu),
-                                                "frac_if_4.5": (value / world) / (alu / 2.25)},
+                                                "if_vadd2_off_alu_pipe": 2.5, "vadd2_off_alu_pipe": bool(vadd_off_alu),
+                                                "frac_if_4.5": (value / world) / (alu / 2.25),
+                                                "frac_vs_3.5": (value / world) / (alu / 1.75),
+                                                "issue_slots_per_cell_pair": 5.0,
+                                                "what": "2.5 = prmt + vimax3.relu + 1/2 vimax3; beside them 2 vadd2 on the "
+                                                        "other 64-lane pipe and 1/2 LDS: 5.0 issue slots per cell pair "
+                                                        "against one slot per clock and scheduler, so the issue-slot "
+                                                        "ceiling (alu x 2 / 2.5 per cell) is practically the same number; "
+                                                        "frac_vs_3.5 = against the ceiling of the round-1 cell "
+                                                        "(prmt + 2 viaddmax + 1/2 vimax3)"},
                     "peak_source": "measured live: ALU pipe issues %.0f Glane-instr/s (swb_microbench, viaddmax.relu alone); "
-                                   "%.1f ALU-pipe instructions per cell pair (prmt + viaddmax.relu + viaddmax + 1/2 vimax3%s); "
+                                   "%.1f ALU-pipe instructions per cell pair (prmt + vimax3.relu + 1/2 vimax3%s); "
                                    "a dependent-chain loop of the full mix reaches %.0f Glane-instr/s" % (
                                        alu, 2 * instr_per_cell,
                                        "; vadd2 issues on another pipe: viaddmax+vadd2 = %.0f" % pair if vadd_off_alu
-                                       else " + vadd2", mix),
+                                       else " + 2 vadd2", mix),
                     "instr_rates_glane_per_s": per_kind,
                     "hbm": {"achieved": alg_bytes / (ms_per_step * 1e-3) * 1e-9, "peak": hbm_peak * world, "unit": "GB/s",
                             "frac": alg_bytes / (ms_per_step * 1e-3) * 1e-9 / (hbm_peak * world),

@@ -352,7 +352,7 @@ def plan_describe(offsets, shard=0, nshards=1, group_len=0, want_ids=False):
 
 MICROBENCH_KINDS = ["viaddmax_s16x2_relu", "vimax3_s16x2", "vadd2", "prmt", "v16_mix", "viaddmax+imad", "imad",
                     "scalar_addmax", "v16b_mix", "hmnmx2+mask", "viaddmax+hmnmx2", "viaddmax+vadd2", "viaddmax+prmt",
-                    "viaddmax+vimax3"]
+                    "viaddmax+vimax3", "v16_mix_vimax3"]
 
 
 def microbench(device=0, kind=4):

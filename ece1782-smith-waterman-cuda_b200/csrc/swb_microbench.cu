@@ -20,7 +20,7 @@ __device__ __forceinline__ uint32_t swb_hmax2_bits(uint32_t a, uint32_t b)
 template <int KIND>
 __global__ void __launch_bounds__(256) swb_mb_kernel(uint32_t *out, uint32_t seed, int iters)
 {
-    uint32_t x[MB_CHAINS];
+    uint32_t x[MB_CHAINS], y = 0u, dprev = 0u;
     const uint32_t a = seed * 0x9E3779B9u + threadIdx.x, b = seed ^ 0x00010001u, one = (seed >> 31) + 1u;
 #pragma unroll
     for (int c = 0; c < MB_CHAINS; ++c) x[c] = a + c * 0x00030005u;
@@ -57,6 +57,15 @@ __global__ void __launch_bounds__(256) swb_mb_kernel(uint32_t *out, uint32_t see
                 asm volatile("prmt.b32 %0, %1, %2, 0xC480;" : "=r"(x[c]) : "r"(x[c]), "r"(b));
             }
             if (KIND == 13) { x[c] = __viaddmax_s16x2_relu(x[c], b, a); x[c] = __vimax3_s16x2(x[c], b, a); }
+            if (KIND == 14) {  // the score kernel's per-cell-pair mix since r2x: prmt, 2 vadd2, vimax3.relu, 1/2 vimax3
+                uint32_t sc;
+                asm volatile("prmt.b32 %0, %1, %2, 0xD591;" : "=r"(sc) : "r"(x[c]), "r"(b));
+                const uint32_t dd = __vadd2(x[c], sc);  // used twice (cell and running maximum): stays a vadd2
+                const uint32_t hh = __vimax3_s16x2_relu(dd, a, x[c]);
+                x[c] = __vadd2(hh, b);
+                if (c & 1) y = __vimax3_s16x2(y, dprev, dd);
+                dprev = dd;
+            }
             if (KIND == 8) {  // the biased policy's mix: prmt, vimax3, viaddmax, 1/2 vimax3 (ALU) + 3 imad (FMA)
                 uint32_t s, ds, l3;
                 asm volatile("prmt.b32 %0, %1, %2, 0xD591;" : "=r"(s) : "r"(x[c]), "r"(b));
@@ -72,18 +81,19 @@ __global__ void __launch_bounds__(256) swb_mb_kernel(uint32_t *out, uint32_t see
     uint32_t r = 0;
 #pragma unroll
     for (int c = 0; c < MB_CHAINS; ++c) r ^= x[c];
+    r ^= y;
     if (r == 0x12345678u) out[0] = r;
 }
 
-static const double kInstrPerIter[14] = {MB_CHAINS, MB_CHAINS, MB_CHAINS, MB_CHAINS, MB_CHAINS * 4.5, MB_CHAINS * 2.0,
+static const double kInstrPerIter[15] = {MB_CHAINS, MB_CHAINS, MB_CHAINS, MB_CHAINS, MB_CHAINS * 4.5, MB_CHAINS * 2.0,
                                          MB_CHAINS, MB_CHAINS, MB_CHAINS * 6.5, MB_CHAINS * 3.0, MB_CHAINS * 2.0,
-                                         MB_CHAINS * 2.0, MB_CHAINS * 2.0, MB_CHAINS * 2.0};
+                                         MB_CHAINS * 2.0, MB_CHAINS * 2.0, MB_CHAINS * 2.0, MB_CHAINS * 4.5};
 
-// kind 0 viaddmax.relu, 1 vimax3, 2 vadd2, 3 prmt, 4 V16 mix, 5 viaddmax+imad, 6 imad, 7 scalar add/max, 8 V16B mix.
+// kind 0 viaddmax.relu, 1 vimax3, 2 vadd2, 3 prmt, 4 V16 mix of round 1, 14 V16 mix now, 5 viaddmax+imad, 6 imad, 7 scalar add/max, 8 V16B mix.
 // Returns giga lane-instructions per second (warp instructions x 32) over the whole GPU.
 extern "C" int swb_microbench(int device, int kind, double *glane_instr_per_s, double *ms_out)
 {
-    if (kind < 0 || kind > 13 || !glane_instr_per_s) return SWB_ERR_ARG;
+    if (kind < 0 || kind > 14 || !glane_instr_per_s) return SWB_ERR_ARG;
     if (cudaSetDevice(device) != cudaSuccess) return SWB_ERR_CUDA;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return SWB_ERR_CUDA;
@@ -110,6 +120,7 @@ extern "C" int swb_microbench(int device, int kind, double *glane_instr_per_s, d
         case 11: swb_mb_kernel<11><<<grid, block>>>(d, 7u + rep, iters); break;
         case 12: swb_mb_kernel<12><<<grid, block>>>(d, 7u + rep, iters); break;
         case 13: swb_mb_kernel<13><<<grid, block>>>(d, 7u + rep, iters); break;
+        case 14: swb_mb_kernel<14><<<grid, block>>>(d, 7u + rep, iters); break;
         default: swb_mb_kernel<10><<<grid, block>>>(d, 7u + rep, iters); break;
         }
         cudaEventRecord(e1);

@@ -3,15 +3,22 @@
 //
 // Recurrence (reference: src/SWSolver.cu:246, src/cpu.cpp:45-72), linear gap g:
 //     H(i,j) = max(0, H(i-1,j-1) + S(q_i, d_j), H(i,j-1) - g, H(i-1,j) - g),   score = max H
-// restated so that the serial chain down a column is ONE fused op per cell:
-//     c(i,j) = max(0, H(i-1,j-1) + S, H(i,j-1) - g)               off the chain
-//     H(i,j) = max(H(i-1,j) - g, c(i,j))                          on the chain    (viaddmax)
+// restated so that the additions leave the ALU pipe (B200: VIADDMNMX / VIMNMX3 / PRMT share one 64-lane pipe, the
+// packed add VIADD.16x2 issues on another one at the same rate -- swb_microbench kinds 0..3, 11..13):
+//     d(i,j) = H(i-1,j-1) + S                                      vadd2      (off the chain)
+//     H(i,j) = max(0, d(i,j), H(i-1,j) - g, H(i,j-1) - g)          vimax3.relu
+//     H(i,j) - g                                                   vadd2      (kept per row; next cell's up-term)
+//     score  = max(0, max d): a maximal H is never the end of a gap, so the running maximum takes d -- which also keeps
+//     ptxas from folding the first vadd2 back into a VIADDMNMX.
+// (SWB_V16_FORM 0 is the round-1 cell: c = viaddmax.relu(diag, S, left); H = viaddmax(H_up, -g, c); left' = vadd2:
+//  one fused op on the chain, 3.5 ALU-pipe instructions per cell pair. Measured on one B200, 20 reference queries:
+//  9,062 -> 9,395 GCUPS with the new cell, profiles/r2x_*.)
 //
 // Three arithmetic policies run the same program:
 //   V16   two DB sequences in the halves of a 32-bit word, signed s16x2 DPX instructions
-//         (prmt, viaddmax.relu, viaddmax, vadd2, 1/2 vimax3 = 4.5 ALU-pipe instructions per cell pair)
+//         (prmt, vimax3.relu, 1/2 vimax3 = 2.5 ALU-pipe instructions per cell pair, 2 vadd2 beside them)
 //   V32   two int32 lanes; exact for any score; re-scores flagged one-lane tiles (and everything when V16R cannot run).
-//   V16R  packed s16x2 RELATIVE to a base that moves with the columns ("rebased"): exact for any score at 4.5
+//   V16R  packed s16x2 RELATIVE to a base that moves with the columns ("rebased"): exact for any score at 3.5
 //         ALU-pipe instructions per cell pair; lane-group tiles only. Re-scores flagged lane-group tiles and scores
 //         long-against-long tiles directly (their true scores pass 32767 anyway).
 //   V16A / V32A  the affine-gap versions of V16 / V32 (two values per element: H and F along the chain, H and E per row)
@@ -39,8 +46,21 @@
 // pipeline, so a pass resumes as soon as the columns it needs are there.
 #define SWB_SPLIT_HYST 0u
 #endif
+#ifndef SWB_V16_FORM
+// the cell of the V16 policy: 0 = two viaddmax + one vadd2 (one fused op on the chain down a column),
+// 1 = one vimax3.relu + two vadd2 (the additions issue beside the ALU pipe; two ops on the chain)
+#define SWB_V16_FORM 1
+#endif
 #ifndef SWB_PF_CHUNKS
 #define SWB_PF_CHUNKS 6u  // chunks (of 4 columns) that the L2 prefetch of the one-lane tiles runs ahead
+#endif
+#ifndef SWB_PF_MODE
+// L2 prefetch of the one-lane tiles: 0 = one prefetch.global.L2 per lane and chunk at the top of the chunk, 1 = none,
+// 2 = one cp.async.bulk.prefetch.L2 per warp for SWB_PF_SPAN chunks, 3 = as 0 but after the chunk's columns
+#define SWB_PF_MODE 3
+#endif
+#ifndef SWB_PF_SPAN
+#define SWB_PF_SPAN 2u
 #endif
 #ifndef SWB_BLOCK_CHUNKS
 #define SWB_BLOCK_CHUNKS 16u  // one-lane tiles: chunks per column block that the passes of a group share (see swb_run_tile)
@@ -125,7 +145,8 @@ struct V16Base {
 
 // ---------------------------------------------------------------------------------------------
 // V16: plain signed domain. Stored per row: H(k, j-1) - g. Profile entry: S + g.
-//   c = viaddmax.relu(diag-g, S+g, left-g) ; h = viaddmax(h, -g, c) ; left' = vadd2(h, -g)
+//   d = vadd2(diag-g, S+g) ; h = vimax3.relu(d, up-g, left-g) ; left' = vadd2(h, -g) ; best = max(best, d)
+//   (SWB_V16_FORM 0: c = viaddmax.relu(diag-g, S+g, left-g) ; h = viaddmax(h, -g, c) ; left' = vadd2(h, -g))
 struct V16 : V16Base {
     static const bool rebased = false;
     static const bool blocked = true;  // one-lane tiles walk in pass groups over column blocks (swb_run_tile)
@@ -145,6 +166,9 @@ struct V16 : V16Base {
         T h = up;
         T dg = diag0;
         diag0 = add(up, cst.negg);
+#if SWB_V16_FORM == 1
+        T hg = diag0;  // H(row above, this column) - g
+#endif
 #pragma unroll
         for (int kw = 0; kw < K / 4; kw += LDW / 4) {
             uint32_t wva[LDW / 4], wvb[LDW / 4];
@@ -155,6 +179,16 @@ struct V16 : V16Base {
                 const int k4 = kw + j;
                 const uint32_t wa = wva[j], wb = wvb[j];
                 T c[4];
+#if SWB_V16_FORM == 1
+#define SWB_CELL(I)                                                        \
+    {                                                                      \
+        const T s = pair<I>(wa, wb);                                       \
+        const T d = c[I] = add(dg, s);                                     \
+        dg = left[4 * k4 + I];                                             \
+        h = __vimax3_s16x2_relu(d, hg, dg);                                \
+        left[4 * k4 + I] = hg = add(h, cst.negg);                          \
+    }
+#else
 #define SWB_CELL(I)                                                        \
     {                                                                      \
         const T s = pair<I>(wa, wb);                                       \
@@ -163,6 +197,7 @@ struct V16 : V16Base {
         h = __viaddmax_s16x2(h, cst.negg, c[I]);                           \
         left[4 * k4 + I] = add(h, cst.negg);                               \
     }
+#endif
                 SWB_CELL(0) SWB_CELL(1)
                 best = __vimax3_s16x2(best, c[0], c[1]);
                 SWB_CELL(2) SWB_CELL(3)
@@ -187,7 +222,9 @@ struct V16 : V16Base {
 //     c = viaddmax(diag - g, S + g, left) ; h = viaddmax(h, -g, c) ; left' = viaddmax(h, -g, floor)
 // with floor = -g - base (clamped to -32000: far below every live value once base is large): the stored row state
 // max(h - g, -g) equals H - g for the true H = max(h, 0), h itself may run g below zero along the chain, which never
-// wins a later max (c >= left' >= -g). One viaddmax replaces V16's vadd2: 4.5 ALU-pipe instructions per cell pair.
+// wins a later max (c >= left' >= -g). One viaddmax replaces V16's vadd2: 4.5 ALU-pipe instructions per cell pair
+// in that form; SWB_V16_FORM 1 (the default) takes the sum out as a vadd2 like V16 and uses the floored row state of
+// the row above as the up-term: prmt, vimax3, viaddmax, 1/2 vimax3 = 3.5.
 // The boundary row between passes keeps relative values plus a log of the writer's base per block (SwbScoreParams::
 // blog); the reader adds (writer's base - its own base) with one vadd2 per column.
 struct V16R : V16Base {
@@ -271,6 +308,9 @@ struct V16R : V16Base {
         T h = up;
         T dg = diag0;
         diag0 = __viaddmax_s16x2(up, cst.negg, cst.fl);
+#if SWB_V16_FORM == 1
+        T hg = diag0;
+#endif
 #pragma unroll
         for (int kw = 0; kw < K / 4; kw += LDW / 4) {
             uint32_t wva[LDW / 4], wvb[LDW / 4];
@@ -281,6 +321,17 @@ struct V16R : V16Base {
                 const int k4 = kw + j;
                 const uint32_t wa = wva[j], wb = wvb[j];
                 T c[4];
+#if SWB_V16_FORM == 1
+                // up-term = the floored row state of the row above (flooring it changes nothing: left >= floor)
+#define SWB_CELL(I)                                                        \
+    {                                                                      \
+        const T s = pair<I>(wa, wb);                                       \
+        c[I] = add(dg, s);                                                 \
+        dg = left[4 * k4 + I];                                             \
+        h = __vimax3_s16x2(c[I], hg, dg);                                  \
+        left[4 * k4 + I] = hg = __viaddmax_s16x2(h, cst.negg, cst.fl);     \
+    }
+#else
 #define SWB_CELL(I)                                                        \
     {                                                                      \
         const T s = pair<I>(wa, wb);                                       \
@@ -289,6 +340,7 @@ struct V16R : V16Base {
         h = __viaddmax_s16x2(h, cst.negg, c[I]);                           \
         left[4 * k4 + I] = __viaddmax_s16x2(h, cst.negg, cst.fl);          \
     }
+#endif
                 SWB_CELL(0) SWB_CELL(1)
                 best = __vimax3_s16x2(best, c[0], c[1]);
                 SWB_CELL(2) SWB_CELL(3)
@@ -417,6 +469,21 @@ struct V16A {
             const uint32_t wa = ra[k4];
             const uint32_t wb = rb[k4];
             uint32_t hh[4];
+#if SWB_V16_FORM == 1
+#define SWB_CELL(I)                                                                          \
+    {                                                                                        \
+        const uint32_t s = V16Base::pair<I>(wa, wb);                                         \
+        const uint32_t e = __viaddmax_s16x2(left[4 * k4 + I].f, cst.neg_ge, left[4 * k4 + I].h); \
+        f = __viaddmax_s16x2(f, cst.neg_ge, hgo);                                            \
+        const uint32_t d = V16::add(dgo, s);                                                 \
+        h = __vimax3_s16x2_relu(d, e, f);                                                    \
+        dgo = left[4 * k4 + I].h;                                                            \
+        hgo = V16::add(h, cst.neg_go);                                                       \
+        left[4 * k4 + I].h = hgo;                                                            \
+        left[4 * k4 + I].f = e;                                                              \
+        hh[I] = d;                                                                           \
+    }
+#else
 #define SWB_CELL(I)                                                                          \
     {                                                                                        \
         const uint32_t s = V16Base::pair<I>(wa, wb);                                         \
@@ -429,6 +496,7 @@ struct V16A {
         left[4 * k4 + I].f = e;                                                              \
         hh[I] = h;                                                                           \
     }
+#endif
             SWB_CELL(0) SWB_CELL(1)
             best.h = __vimax3_s16x2(best.h, hh[0], hh[1]);
             SWB_CELL(2) SWB_CELL(3)
@@ -673,15 +741,31 @@ SWB_HD void swb_run_tile(BE &be, const SwbScoreParams &p, const SwbTile &tile, u
                         // The loads above run one chunk ahead, which covers a cache hit but not a trip to HBM: the first
                         // pass of a group meets residues and a boundary row that nobody touched recently. Pull the
                         // lines of the chunk SWB_PF_CHUNKS ahead into L2 now; no register is tied up.
+#if SWB_PF_MODE == 0
                         if (ss == pg0 && c + SWB_PF_CHUNKS < nchunks) {
                             be.prefetch_l2(res + (size_t)(c + SWB_PF_CHUNKS) * res_stride);
                             if (read_top) be.prefetch_l2(bnd + ((size_t)(c + SWB_PF_CHUNKS) * 32u + lane) * 4u);
                         }
+#elif SWB_PF_MODE == 2
+                        // one bulk prefetch per warp for SWB_PF_SPAN chunks at a time (one-lane tiles: a chunk of the
+                        // warp is 256 contiguous bytes of residues and 512 of boundary row)
+                        if (ss == pg0 && ((c - cb0) & (SWB_PF_SPAN - 1u)) == 0u && c + SWB_PF_CHUNKS < nchunks && lane == 0) {
+                            const uint32_t nc = c + SWB_PF_CHUNKS + SWB_PF_SPAN <= nchunks ? SWB_PF_SPAN : nchunks - c - SWB_PF_CHUNKS;
+                            be.prefetch_l2_bulk(res + (size_t)(c + SWB_PF_CHUNKS) * res_stride, nc * 256u);
+                            if (read_top) be.prefetch_l2_bulk(bnd + (size_t)(c + SWB_PF_CHUNKS) * 128u, nc * 512u);
+                        }
+#endif
                         T outb[4];
 #pragma unroll
                         for (int u = 0; u < 4; ++u)
                             outb[u] = V::template column<K, SWB_BULK_LDW>(bc[u], diag0, left, best, cst, ca[u], cb[u], prow, sstride);
                         if (write_bot) V::st4(be, bnd + ((size_t)c * 32u + lane) * 4u, outb);
+#if SWB_PF_MODE == 3
+                        if (ss == pg0 && c + SWB_PF_CHUNKS < nchunks) {
+                            be.prefetch_l2(res + (size_t)(c + SWB_PF_CHUNKS) * res_stride);
+                            if (read_top) be.prefetch_l2(bnd + ((size_t)(c + SWB_PF_CHUNKS) * 32u + lane) * 4u);
+                        }
+#endif
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
                             ca[u] = na[u];

@@ -230,14 +230,16 @@ void swb_dbfile_close(swb_dbfile *d);
 /* ---- measurement support (not on the scoring path) ------------------------------------------- */
 /* Issue rate of the integer SIMD instructions the score kernel is built from, whole GPU, in giga
  * lane-instructions/s. kind: 0 viaddmax.s16x2.relu, 1 vimax3.s16x2, 2 vadd2, 3 prmt, 4 a dependent-chain loop of the
- * score kernel's per-cell mix, 5 viaddmax+imad, 6 imad, 7 scalar add+max, 8 the mix of the (rejected) biased FMA-pipe
- * variant, 9 hmnmx2 (+ a mask), 10 viaddmax+hmnmx2 (18.3 T: the fp16 comparator shares the ALU pipe, so it cannot take
- * over the max), 11 viaddmax+vadd2, 12 viaddmax+prmt, 13 viaddmax+vimax3 in one loop.
+ * round-1 per-cell mix (two viaddmax), 5 viaddmax+imad, 6 imad, 7 scalar add+max, 8 the mix of the (rejected) biased
+ * FMA-pipe variant, 9 hmnmx2 (+ a mask), 10 viaddmax+hmnmx2 (18.3 T: the fp16 comparator shares the ALU pipe, so it
+ * cannot take over the max), 11 viaddmax+vadd2, 12 viaddmax+prmt, 13 viaddmax+vimax3 in one loop, 14 a dependent-chain
+ * loop of the present per-cell mix.
  * Roofline accounting (bench.py): the peak of the score kernel is the ALU-pipe issue rate (kind 0: 64 lanes/clk/SM)
- * divided by the ALU-pipe instructions per cell. Per cell PAIR the kernel issues prmt + viaddmax.relu + viaddmax +
- * 1/2 vimax3 on that pipe (3.5) plus one vadd2; kinds 11..13 decide where the vadd2 goes: viaddmax+vadd2 runs at twice
- * the single rate (vadd2 issues on another pipe -> 3.5 per pair), the other pairs at the single rate (same pipe). If
- * kind 11 did not double, the count would be 4.5. bench.py prints both variants and the flag it derived. */
+ * divided by the ALU-pipe instructions per cell. Per cell PAIR the V16 kernel issues prmt + vimax3.relu + 1/2 vimax3
+ * on that pipe (2.5) plus two vadd2; kinds 11..13 decide where the vadd2 goes: viaddmax+vadd2 runs at twice the single
+ * rate (vadd2 issues on another pipe -> 2.5 per pair), the other pairs at the single rate (same pipe). If kind 11 did
+ * not double, the count would be 4.5. (Until r2x the cell was prmt + viaddmax.relu + viaddmax + 1/2 vimax3 + one vadd2:
+ * 3.5 on the ALU pipe; bench.py prints the fraction against that ceiling too.) */
 int swb_microbench(int device, int kind, double *glane_instr_per_s, double *ms);
 /* Re-runs the pack kernel of the loaded database `reps` times (same inputs, same output) and reports the mean device time
  * per launch in microseconds and the bytes one launch reads + writes: the HBM figure of the one bandwidth-bound kernel of

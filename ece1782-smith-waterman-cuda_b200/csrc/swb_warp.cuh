@@ -59,6 +59,9 @@
 // 2 = one cp.async.bulk.prefetch.L2 per warp for SWB_PF_SPAN chunks, 3 = as 0 but after the chunk's columns
 #define SWB_PF_MODE 3
 #endif
+#ifndef SWB_CHUNK_UNROLL
+#define SWB_CHUNK_UNROLL 1  // unrolling of the chunk loop of the one-lane tiles (the rotation of the prefetched codes)
+#endif
 #ifndef SWB_PF_SPAN
 #define SWB_PF_SPAN 2u
 #endif
@@ -682,6 +685,7 @@ SWB_HD void swb_run_tile(BE &be, const SwbScoreParams &p, const SwbTile &tile, u
         // Only the V16 policy can be blocked: the two-value affine state (64 registers of rows at K = 32) spilled in the
         // hot loop with the parking code (4,905 against 5,249 GCUPS).
         constexpr uint32_t PGV = V::blocked ? SWB_PASS_GROUP : 1u;
+        constexpr int CHUNK_UNROLL = SWB_CHUNK_UNROLL;
         T *const cstate = PGV > 1u ? reinterpret_cast<T *>(p.colstate) + (size_t)be.warp_slot() * swb_colstate_elems(K) : nullptr;
         const size_t cs_pass = (size_t)(K + 4) * 32u;  // elements of T per parked pass: [K/4 + 1][lane][4]
         for (uint32_t pg0 = ss_begin; pg0 < ss_end; pg0 += PGV) {
@@ -719,6 +723,7 @@ SWB_HD void swb_run_tile(BE &be, const SwbScoreParams &p, const SwbTile &tile, u
                         }
                         if (read_top) V::ld4(be, bnd + ((size_t)cb0 * 32u + lane) * 4u, bc);
                     }
+#pragma unroll(CHUNK_UNROLL)
                     for (uint32_t c = cb0; c < cb1; ++c) {
                         // prefetch the next chunk of residues and of the top boundary row
                         uint32_t na[4], nb[4];

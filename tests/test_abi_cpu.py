@@ -130,10 +130,10 @@ def test_layout_rules(swb):
     load = np.bincount(g, weights=qlens.astype(float), minlength=8)
     assert load.max() / load.mean() < 1.001
     # with the batch in view: 20 reference queries fill 2 or 4 groups evenly, not 8 (the longest query alone is 5 % above
-    # an eighth of the rows) -> two database parts on 8 devices; 1,000 queries fill 8 groups
+    # an eighth of the rows) -> the database is split eight ways instead; 1,000 queries fill 8 groups
     assert swb.layout_parts(570065, 2, qoffsets=offs) == 1
     assert swb.layout_parts(570065, 4, qoffsets=offs) == 1
-    assert swb.layout_parts(570065, 8, qoffsets=offs) == 2
+    assert swb.layout_parts(570065, 8, qoffsets=offs) == 8
     assert swb.layout_parts(570065, 8, qoffsets=_offsets(qlens)) == 1
     assert swb.layout_parts(5700650, 8, qoffsets=_offsets(qlens)) == 8
     assert swb.layout_parts(570065, 8, qoffsets=_offsets([100])) == 8

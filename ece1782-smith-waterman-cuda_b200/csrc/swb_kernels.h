@@ -7,9 +7,13 @@
 // LARGE (one block per SM) when the profile of a long query fills most of the 227 KB of shared memory.
 #define SWB_BLOCK_SMALL 0
 #define SWB_BLOCK_LARGE 1
+#ifndef SWB_NT_SMALL
 #define SWB_NT_SMALL 256
+#endif
 #define SWB_MINB_SMALL 2
+#ifndef SWB_NT_LARGE
 #define SWB_NT_LARGE 512
+#endif
 
 // arithmetic policy of a score launch (swb_warp.cuh)
 #define SWB_MODE_S16 0    // V16: two DB sequences per lane, one query

@@ -311,7 +311,7 @@ struct V16R : V16Base {
         T h = up;
         T dg = diag0;
         diag0 = __viaddmax_s16x2(up, cst.negg, cst.fl);
-#if SWB_V16_FORM == 1
+#if SWB_V16_FORM >= 1
         T hg = diag0;
 #endif
 #pragma unroll
@@ -324,7 +324,7 @@ struct V16R : V16Base {
                 const int k4 = kw + j;
                 const uint32_t wa = wva[j], wb = wvb[j];
                 T c[4];
-#if SWB_V16_FORM == 1
+#if SWB_V16_FORM >= 1
                 // up-term = the floored row state of the row above (flooring it changes nothing: left >= floor)
 #define SWB_CELL(I)                                                        \
     {                                                                      \
@@ -472,7 +472,7 @@ struct V16A {
             const uint32_t wa = ra[k4];
             const uint32_t wb = rb[k4];
             uint32_t hh[4];
-#if SWB_V16_FORM == 1
+#if SWB_V16_FORM >= 1
 #define SWB_CELL(I)                                                                          \
     {                                                                                        \
         const uint32_t s = V16Base::pair<I>(wa, wb);                                         \

@@ -71,10 +71,6 @@ struct DevBackend {
     {
         asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
     }
-    __device__ __forceinline__ void prefetch_l2_bulk(const void *p, uint32_t bytes) const
-    {
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes));
-    }
     __device__ __forceinline__ uint8_t ld_flag(const uint8_t *p) const { return __ldcg(p); }
     __device__ __forceinline__ SwbTile ld_tile(const SwbTile *p) const
     {

@@ -54,17 +54,6 @@
 #ifndef SWB_PF_CHUNKS
 #define SWB_PF_CHUNKS 6u  // chunks (of 4 columns) that the L2 prefetch of the one-lane tiles runs ahead
 #endif
-#ifndef SWB_PF_MODE
-// L2 prefetch of the one-lane tiles: 0 = one prefetch.global.L2 per lane and chunk at the top of the chunk, 1 = none,
-// 2 = one cp.async.bulk.prefetch.L2 per warp for SWB_PF_SPAN chunks, 3 = as 0 but after the chunk's columns
-#define SWB_PF_MODE 3
-#endif
-#ifndef SWB_CHUNK_UNROLL
-#define SWB_CHUNK_UNROLL 1  // unrolling of the chunk loop of the one-lane tiles (the rotation of the prefetched codes)
-#endif
-#ifndef SWB_PF_SPAN
-#define SWB_PF_SPAN 2u
-#endif
 #ifndef SWB_BLOCK_CHUNKS
 #define SWB_BLOCK_CHUNKS 16u  // one-lane tiles: chunks per column block that the passes of a group share (see swb_run_tile)
 #endif
@@ -685,7 +674,6 @@ SWB_HD void swb_run_tile(BE &be, const SwbScoreParams &p, const SwbTile &tile, u
         // Only the V16 policy can be blocked: the two-value affine state (64 registers of rows at K = 32) spilled in the
         // hot loop with the parking code (4,905 against 5,249 GCUPS).
         constexpr uint32_t PGV = V::blocked ? SWB_PASS_GROUP : 1u;
-        constexpr int CHUNK_UNROLL = SWB_CHUNK_UNROLL;
         T *const cstate = PGV > 1u ? reinterpret_cast<T *>(p.colstate) + (size_t)be.warp_slot() * swb_colstate_elems(K) : nullptr;
         const size_t cs_pass = (size_t)(K + 4) * 32u;  // elements of T per parked pass: [K/4 + 1][lane][4]
         for (uint32_t pg0 = ss_begin; pg0 < ss_end; pg0 += PGV) {
@@ -723,7 +711,6 @@ SWB_HD void swb_run_tile(BE &be, const SwbScoreParams &p, const SwbTile &tile, u
                         }
                         if (read_top) V::ld4(be, bnd + ((size_t)cb0 * 32u + lane) * 4u, bc);
                     }
-#pragma unroll(CHUNK_UNROLL)
                     for (uint32_t c = cb0; c < cb1; ++c) {
                         // prefetch the next chunk of residues and of the top boundary row
                         uint32_t na[4], nb[4];
@@ -743,34 +730,21 @@ SWB_HD void swb_run_tile(BE &be, const SwbScoreParams &p, const SwbTile &tile, u
                             }
                             if (read_top) V::ld4(be, bnd + ((size_t)(c + 1) * 32u + lane) * 4u, bn);
                         }
-                        // The loads above run one chunk ahead, which covers a cache hit but not a trip to HBM: the first
-                        // pass of a group meets residues and a boundary row that nobody touched recently. Pull the
-                        // lines of the chunk SWB_PF_CHUNKS ahead into L2 now; no register is tied up.
-#if SWB_PF_MODE == 0
-                        if (ss == pg0 && c + SWB_PF_CHUNKS < nchunks) {
-                            be.prefetch_l2(res + (size_t)(c + SWB_PF_CHUNKS) * res_stride);
-                            if (read_top) be.prefetch_l2(bnd + ((size_t)(c + SWB_PF_CHUNKS) * 32u + lane) * 4u);
-                        }
-#elif SWB_PF_MODE == 2
-                        // one bulk prefetch per warp for SWB_PF_SPAN chunks at a time (one-lane tiles: a chunk of the
-                        // warp is 256 contiguous bytes of residues and 512 of boundary row)
-                        if (ss == pg0 && ((c - cb0) & (SWB_PF_SPAN - 1u)) == 0u && c + SWB_PF_CHUNKS < nchunks && lane == 0) {
-                            const uint32_t nc = c + SWB_PF_CHUNKS + SWB_PF_SPAN <= nchunks ? SWB_PF_SPAN : nchunks - c - SWB_PF_CHUNKS;
-                            be.prefetch_l2_bulk(res + (size_t)(c + SWB_PF_CHUNKS) * res_stride, nc * 256u);
-                            if (read_top) be.prefetch_l2_bulk(bnd + (size_t)(c + SWB_PF_CHUNKS) * 128u, nc * 512u);
-                        }
-#endif
                         T outb[4];
 #pragma unroll
                         for (int u = 0; u < 4; ++u)
                             outb[u] = V::template column<K, SWB_BULK_LDW>(bc[u], diag0, left, best, cst, ca[u], cb[u], prow, sstride);
                         if (write_bot) V::st4(be, bnd + ((size_t)c * 32u + lane) * 4u, outb);
-#if SWB_PF_MODE == 3
-                        if (ss == pg0 && c + SWB_PF_CHUNKS < nchunks) {
+                        // The loads above run one chunk ahead, which covers a cache hit but not a trip to HBM: the first
+                        // pass of a group meets residues and a boundary row that nobody touched recently. Pull the
+                        // lines of the chunk SWB_PF_CHUNKS ahead into L2; no register is tied up. HERE, behind the
+                        // columns: at the top of the chunk the next instruction that reused a register of the
+                        // prefetch's address pair waited on it for ~500 cycles per chunk (12.7 % of the stall samples,
+                        // profiles/r2y_*; 9,458 -> 10,003 GCUPS by moving it, profiles/r2z_sweep_pf_mode.txt).
+                        if (SWB_PF_CHUNKS > 0u && ss == pg0 && c + SWB_PF_CHUNKS < nchunks) {
                             be.prefetch_l2(res + (size_t)(c + SWB_PF_CHUNKS) * res_stride);
                             if (read_top) be.prefetch_l2(bnd + ((size_t)(c + SWB_PF_CHUNKS) * 32u + lane) * 4u);
                         }
-#endif
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
                             ca[u] = na[u];

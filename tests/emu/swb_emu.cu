@@ -48,7 +48,6 @@ struct HostBackend {
     }
 
     void prefetch_l2(const void *) const {}
-    void prefetch_l2_bulk(const void *, uint32_t) const {}
     uint8_t ld_flag(const uint8_t *p) const { return *p; }
     SwbTile ld_tile(const SwbTile *p) const { return *p; }
     uint32_t ld_code(const uint8_t *p) const { return *p; }

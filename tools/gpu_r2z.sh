@@ -1,5 +1,6 @@
 #!/bin/bash
-# 1-GPU box: L2-prefetch forms of the one-lane loop (SWB_PF_MODE) with the new V16 cell, same GPU
+# 1-GPU box: L2-prefetch forms of the one-lane loop with the new V16 cell, same GPU (the variants lived behind a macro
+# SWB_PF_MODE in commit da351ad: 0 top of the chunk, 1 none, 2 bulk prefetch per warp, 3 behind the columns = the code now)
 mkdir -p gpurun_out
 PKG=ece1782-smith-waterman-cuda_b200
 for v in "" pf1 pf2 pf2s4 pf3 ""; do

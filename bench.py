@@ -661,7 +661,8 @@ def main():
         cfg = workload_config(offsets, qs, args)
         cfg["layout"] = {"db_parts": parts, "query_groups": groups,
                          "rule": "P = largest divisor of N with >= 450,000 sequences per part; P = N when the batch "
-                                 "cannot fill N / P query groups evenly (LPT, heaviest group <= 1.02 x mean)"}
+                                 "cannot fill N / P query groups with >= 8 queries each, evenly (LPT, heaviest group "
+                                 "<= 1.02 x mean)"}
         cfg["value_includes"] = ("device-side top-%d per query copied to the host" % args.topk if big
                                  else "all scores copied to the host (4 B x queries x sequences per step)")
         line = {"metric": METRIC, "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps,

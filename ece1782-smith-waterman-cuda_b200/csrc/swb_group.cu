@@ -248,18 +248,26 @@ extern "C" int swb_layout_query_groups(const uint64_t *qoffsets, uint32_t nq, in
     return SWB_OK;
 }
 
-// The same with the batch in view: with P parts the queries split into R = ndev / P groups. If the batch is too small or
-// too uneven for R groups of (nearly) equal total length -- the heaviest group more than 2 % above the mean -- the
-// database is split over all the devices instead (P = ndev, one query group). Layouts in between were measured on an
-// 8 x B200 box with the 20 reference queries (profiles/r2k_*, r2w_*: P 2 x R 4 against P 8 x R 1): the same device
-// time within 1.5 % either way, but every query group uploads its own copy of a part through the same host, and end
-// to end the pure split was 17 % faster twice (58.8 against 49.7 TCUPS).
+// The same with the batch in view: with P parts the queries split into R = ndev / P groups. The database is split over
+// all the devices instead (P = ndev, one query group) when the batch is too small or too uneven for R groups: fewer
+// than SWB_MIN_GROUP_QUERIES queries per group, or the heaviest group more than 2 % above the mean total length.
+//  - Few queries per group: a query's launch ends with a tail in which its longest lane-group tiles run alone, and only
+//    other queries in flight fill it. Measured with the 20 reference queries on whole copies of Swiss-Prot: 10 per GPU
+//    0.98 of the 20-query rate (2 GPUs, profiles/r2zf_*), 5 per GPU 0.87 (4 GPUs) -- while an eighth of the database
+//    with all 20 queries runs at 0.89 of the whole (profiles/r2zd_*), a quarter necessarily above that.
+//  - Layouts in between (P 2 x R 4 on 8 GPUs, profiles/r2k_*, r2w_*): the same device time as the pure split within
+//    1.5 %, but every query group uploads its own copy of a part through the same host; end to end the pure split was
+//    17 % faster twice (58.8 against 49.7 TCUPS).
+#ifndef SWB_MIN_GROUP_QUERIES
+#define SWB_MIN_GROUP_QUERIES 8u
+#endif
 extern "C" int swb_layout_parts_batch(uint32_t n, int ndev, uint32_t min_part, const uint64_t *qoffsets, uint32_t nq)
 {
     if (ndev < 1) return 1;
     const int P = swb_layout_parts(n, ndev, min_part);
     if (!qoffsets || nq == 0 || P >= ndev) return P;
     const int R = ndev / P;
+    if (nq < SWB_MIN_GROUP_QUERIES * (uint32_t)R) return ndev;
     std::vector<uint32_t> group_of(nq);
     swb_layout_query_groups(qoffsets, nq, R, group_of.data());
     std::vector<uint64_t> load((size_t)R, 0);

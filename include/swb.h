@@ -193,9 +193,9 @@ int swb_group_search_batch_topk(swb_group *g, const uint8_t *qcodes, const uint6
 int swb_group_stats(const swb_group *g, swb_stats_t *out);
 /* the layout rules, CPU only: P for n sequences on ndev devices; group_of[q] for R groups of a batch (LPT) */
 int swb_layout_parts(uint32_t n, int ndev, uint32_t min_part_sequences);
-/* the same with the batch in view: P = ndev (one query group) when R = ndev / P query groups of (nearly) equal total
- * length cannot be formed from this batch (heaviest group more than 2 % above the mean); bench.py lays out its ranks
- * with it */
+/* the same with the batch in view: P = ndev (one query group) when R = ndev / P query groups would hold fewer than 8
+ * queries each or cannot be formed with (nearly) equal total length from this batch (heaviest group more than 2 % above
+ * the mean); bench.py lays out its ranks with it */
 int swb_layout_parts_batch(uint32_t n, int ndev, uint32_t min_part_sequences, const uint64_t *qoffsets, uint32_t nq);
 int swb_layout_query_groups(const uint64_t *qoffsets, uint32_t nq, int groups, uint32_t *group_of);
 

@@ -131,9 +131,11 @@ def test_layout_rules(swb):
     assert load.max() / load.mean() < 1.001
     # with the batch in view: 20 reference queries fill 2 or 4 groups evenly, not 8 (the longest query alone is 5 % above
     # an eighth of the rows) -> the database is split eight ways instead; 1,000 queries fill 8 groups
+    # ... and four groups would hold five queries each, too few to fill the tails of each other's launches
     assert swb.layout_parts(570065, 2, qoffsets=offs) == 1
-    assert swb.layout_parts(570065, 4, qoffsets=offs) == 1
+    assert swb.layout_parts(570065, 4, qoffsets=offs) == 4
     assert swb.layout_parts(570065, 8, qoffsets=offs) == 8
+    assert swb.layout_parts(570065, 4, qoffsets=_offsets(list(lens) * 2)) == 1
     assert swb.layout_parts(570065, 8, qoffsets=_offsets(qlens)) == 1
     assert swb.layout_parts(5700650, 8, qoffsets=_offsets(qlens)) == 8
     assert swb.layout_parts(570065, 8, qoffsets=_offsets([100])) == 8

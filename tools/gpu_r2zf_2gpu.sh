@@ -1,0 +1,13 @@
+#!/bin/bash
+# 2-GPU box: the driver's N = 2 command with the HEAD of the round (new V16 cell)
+mkdir -p gpurun_out
+TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
+timeout 300 $TR --nproc-per-node 2 --master-port 29641 bench.py --gpus 2 --steps 3 --warmup 3 --no-ref-cuda > gpurun_out/r2zf_bench_config2_2gpu.json 2> gpurun_out/r2zf_bench_config2_2gpu.err; echo "exit $?"
+python - <<'PY'
+import json
+try:
+    d=json.loads(open('gpurun_out/r2zf_bench_config2_2gpu.json').read().strip().split('\n')[-1])
+    print(round(d['value']), d['config']['layout'], 'e2e', round(d['e2e']['value']), 'load ms', round(d['e2e']['db_load_ms'],1), d['sample_parity_ok'], d['topk_merge_ok'], d['roofline']['frac'])
+except Exception as e: print('failed', e)
+PY
+tail -2 gpurun_out/r2zf_bench_config2_2gpu.err

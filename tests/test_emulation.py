@@ -374,3 +374,35 @@ def test_one_lane_tiles_in_column_blocks_and_pass_groups(oracle, subset, queries
     assert want[0] == 34500
     got, rc = emu_lib.search(codes, offs, m, w, K=0, group_len=4096, exact_i32=1, variant=variant)
     assert np.array_equal(got, want) and rc >= 1
+
+
+def test_running_maximum_over_diagonal_sums(emu, emu_affine, oracle):
+    """The s16 cells keep max(d) with d = H(i-1,j-1) + S instead of max(H) (csrc/swb_warp.cuh, SWB_V16_FORM 1): a maximal
+    H is never the end of a gap. Structured cases where the best cell sits in the first row / first column, right behind
+    a gap, or nowhere (score 0), linear and affine, every strip height and lane-group size."""
+    m = oracle.matrix("blosum50")
+    A, W, C, P = 0, 17, 4, 14
+    q = np.array([W] * 6 + [A] * 3 + [C] * 5, dtype=np.uint8)
+    enc = [
+        np.array([W], dtype=np.uint8),                                   # best in the first column
+        np.array([P] * 40 + [W], dtype=np.uint8),                        # best in the last column, first query row
+        np.array([W] * 6 + [P] * 2 + [C] * 5, dtype=np.uint8),           # gap in the target between two blocks
+        np.array([W] * 6 + [C] * 5, dtype=np.uint8),                     # gap in the query
+        np.array([P] * 70, dtype=np.uint8),                              # nothing aligns: 0
+        np.array([C] * 5 + [P] * 30 + [W] * 6 + [A] * 3 + [C] * 5 + [P] * 9, dtype=np.uint8),
+        np.zeros(0, dtype=np.uint8),
+    ]
+    rng = np.random.default_rng(11)
+    enc += [np.concatenate([rng.integers(0, 20, int(n)).astype(np.uint8), q[::-1], rng.integers(0, 20, 3).astype(np.uint8)])
+            for n in (0, 5, 130, 700)]
+    codes, offs = pack_db(enc)
+    want = oracle.scan(q, codes, offs, m)
+    assert want[0] == 15 and want[4] == 0 and want[2] > want[3] > 0
+    for K, gl in ((8, 8), (16, 16), (32, 384), (0, 64), (32, 32)):
+        got, _ = emu(codes, offs, m, q, K=K, group_len=gl)
+        assert np.array_equal(got, want), (K, gl)
+    for go, ge in ((10, 2), (3, 1)):
+        wanta = oracle.scan_affine(q, codes, offs, m, go, ge)
+        for K, gl in ((8, 8), (16, 64), (32, 384)):
+            got, _ = emu_affine(codes, offs, m, q, go, ge, K=K, group_len=gl)
+            assert np.array_equal(got, wanta), (go, ge, K, gl)

@@ -731,10 +731,11 @@ def run_group(args, swb, codes, offsets, qs, total_cells):
     """--group: ONE process, every device behind the engine group (what the C++ drop-in uses). Device time = the
     slowest device's CUDA-event time per step (swb_group_stats), wall clock beside it."""
     g = swb.EngineGroup(args.gpus)
-    if args.db_parts:
-        g.set_option("db_parts", args.db_parts)
     big = args.workload == "config5"
     qcodes, qoffs = swb.pack_sequences(qs)
+    # the bench knows its batch before it loads the database: the batch-aware layout rule, as for the ranks above
+    g.set_option("db_parts", args.db_parts if args.db_parts else
+                 swb.layout_parts(len(offsets) - 1, g.size(), qoffsets=qoffs))
     t0 = time.perf_counter()
     g.db_load(codes, offsets)
     out = None if big else np.zeros((len(qs), len(offsets) - 1), dtype=np.int32)
